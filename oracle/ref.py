@@ -1,0 +1,107 @@
+"""ctypes binding of oracle/_ref/libwap_ref.so (the compiled, unmodified reference).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libwap_ref.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("oracle/_ref/libwap_ref.so missing: run python oracle/build_ref.py")
+        L = C.CDLL(LIB_PATH)
+        L.ref_apm_create.restype = C.c_void_p
+        L.ref_apm_create.argtypes = [C.c_int] * 7
+        L.ref_apm_destroy.argtypes = [C.c_void_p]
+        L.ref_apm_run_i16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_apm_tick_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_apm_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_apm_bench.restype = C.c_double
+        L.ref_apm_bench.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_fft128.argtypes = [C.c_void_p, C.c_int]
+        L.ref_rdft256.argtypes = [C.c_void_p, C.c_int]
+        L.ref_hpf_create.restype = C.c_void_p
+        L.ref_hpf_create.argtypes = [C.c_int, C.c_int]
+        L.ref_hpf_destroy.argtypes = [C.c_void_p]
+        L.ref_hpf_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_3band_create.restype = C.c_void_p
+        L.ref_3band_destroy.argtypes = [C.c_void_p]
+        L.ref_3band_analysis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_3band_synthesis.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RefApm:
+    """One reference webrtc::AudioProcessing instance (= one call leg)."""
+
+    def __init__(self, aec=True, ns=True, ns_level=1, max_rate=48000, hpf=False,
+                 mc_render=False, mc_capture=False):
+        self.h = lib().ref_apm_create(int(aec), int(ns), int(ns_level), int(max_rate),
+                                      int(hpf), int(mc_render), int(mc_capture))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_apm_destroy(self.h)
+            self.h = None
+
+    def run_i16(self, rate, render, capture, render_ch=1, capture_ch=1, stats_every=0):
+        """render/capture: int16 [nframes*rate/100*ch] interleaved. Returns (out, stats)."""
+        n = rate // 100
+        capture = np.ascontiguousarray(capture, dtype=np.int16)
+        nframes = capture.size // (n * capture_ch)
+        if render is not None:
+            render = np.ascontiguousarray(render, dtype=np.int16)
+            assert render.size // (n * render_ch) >= nframes
+        out = np.zeros(nframes * n * capture_ch, dtype=np.int16)
+        ns = nframes // stats_every if stats_every else 0
+        stats = np.zeros((max(ns, 1), 6), dtype=np.float32)
+        err = lib().ref_apm_run_i16(self.h, rate, render_ch, capture_ch, nframes, _p(render),
+                                    _p(capture), _p(out), stats_every, _p(stats))
+        return out, stats[:ns], err
+
+    def tick_f32(self, rate, render, capture, render_ch=1, capture_ch=1):
+        capture = np.ascontiguousarray(capture, dtype=np.float32)
+        render = None if render is None else np.ascontiguousarray(render, dtype=np.float32)
+        out = np.zeros_like(capture)
+        err = lib().ref_apm_tick_f32(self.h, rate, render_ch, capture_ch, _p(render), _p(capture), _p(out))
+        return out, err
+
+    def stats(self):
+        s = np.zeros(6, dtype=np.float32)
+        lib().ref_apm_stats(self.h, _p(s))
+        return s
+
+
+def fft128(a, inverse=False):
+    a = np.array(a, dtype=np.float32).copy()
+    lib().ref_fft128(_p(a), int(inverse))
+    return a
+
+
+def rdft256(a, isgn=1):
+    a = np.array(a, dtype=np.float32).copy()
+    lib().ref_rdft256(_p(a), int(isgn))
+    return a
+
+
+def cpu_bench(aec, ns, ns_level, rate, streams, threads, warm, nframes, render, capture, stride=0):
+    render = np.ascontiguousarray(render, dtype=np.int16)
+    capture = np.ascontiguousarray(capture, dtype=np.int16)
+    return lib().ref_apm_bench(int(aec), int(ns), int(ns_level), rate, streams, threads, warm,
+                               nframes, _p(render), _p(capture), stride)

@@ -1,0 +1,260 @@
+// Test-harness code (NOT product code): a flat C ABI over the UNMODIFIED
+// reference (built by oracle/build_ref.py into oracle/_ref/libwap_ref.so) so
+// that pytest / bench.py can drive webrtc::AudioProcessing and a few of the
+// reference's internal DSP classes through ctypes.  Only tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it.
+//
+// Mirrors the loop of examples/run-offline.cpp:45-63 (reference), with the
+// rate / submodule selection BASELINE.json's configs name.
+#include <pthread.h>
+#include <sched.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "api/audio/audio_processing.h"
+#include "api/audio/builtin_audio_processing_builder.h"
+#include "api/audio/echo_canceller3_config.h"
+#include "api/environment/environment_factory.h"
+#include "api/scoped_refptr.h"
+#include "common_audio/third_party/ooura/fft_size_128/ooura_fft.h"
+#include "common_audio/third_party/ooura/fft_size_256/fft4g.h"
+#include "modules/audio_processing/aec3/aec3_common.h"
+#include "modules/audio_processing/high_pass_filter.h"
+#include "modules/audio_processing/ns/noise_suppressor.h"
+#include "modules/audio_processing/ns/ns_config.h"
+#include "modules/audio_processing/three_band_filter_bank.h"
+#include "modules/audio_processing/audio_buffer.h"
+#include "rtc_base/cpu_info.h"
+#include "rtc_base/system/arch.h"
+#include "system_wrappers/include/denormal_disabler.h"
+
+using webrtc::AudioProcessing;
+
+namespace {
+
+struct RefApm {
+  webrtc::scoped_refptr<AudioProcessing> apm;
+};
+
+AudioProcessing::Config MakeConfig(int aec, int ns, int ns_level, int max_rate,
+                                   int hpf, int mc_render, int mc_capture) {
+  AudioProcessing::Config c;
+  c.echo_canceller.enabled = aec != 0;
+  c.noise_suppression.enabled = ns != 0;
+  c.noise_suppression.level =
+      static_cast<AudioProcessing::Config::NoiseSuppression::Level>(ns_level);
+  c.pipeline.maximum_internal_processing_rate = max_rate;
+  c.pipeline.multi_channel_render = mc_render != 0;
+  c.pipeline.multi_channel_capture = mc_capture != 0;
+  c.high_pass_filter.enabled = hpf != 0;
+  return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- full APM
+void* ref_apm_create(int aec, int ns, int ns_level, int max_rate, int hpf,
+                     int mc_render, int mc_capture) {
+  auto* h = new RefApm;
+  webrtc::Environment env = webrtc::CreateEnvironment();
+  h->apm = webrtc::BuiltinAudioProcessingBuilder(
+               MakeConfig(aec, ns, ns_level, max_rate, hpf, mc_render, mc_capture))
+               .Build(env);
+  return h;
+}
+
+void ref_apm_destroy(void* p) { delete static_cast<RefApm*>(p); }
+
+// One 10 ms tick on interleaved int16 frames: render then capture, exactly as
+// examples/run-offline.cpp:58-59 (+ set_stream_delay_ms(0)).
+int ref_apm_tick_i16(void* p, int rate, int render_ch, int capture_ch,
+                     const int16_t* render, const int16_t* capture, int16_t* out,
+                     int16_t* render_out) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::StreamConfig rc(rate, render_ch), cc(rate, capture_ch);
+  std::vector<int16_t> scratch;
+  if (!render_out) {
+    scratch.resize(rc.num_frames() * render_ch);
+    render_out = scratch.data();
+  }
+  int e1 = 0;
+  if (render) e1 = h->apm->ProcessReverseStream(render, rc, rc, render_out);
+  h->apm->set_stream_delay_ms(0);
+  int e2 = h->apm->ProcessStream(capture, cc, cc, out);
+  return e1 ? e1 : e2;
+}
+
+// Same with planar float [-1,1] (channel-major: [ch][frame]).
+int ref_apm_tick_f32(void* p, int rate, int render_ch, int capture_ch,
+                     const float* render, const float* capture, float* out) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::StreamConfig rc(rate, render_ch), cc(rate, capture_ch);
+  const int n = rate / 100;
+  std::vector<const float*> rp(render_ch), cp(capture_ch);
+  std::vector<float*> op(capture_ch), rop(render_ch);
+  std::vector<float> rscratch(n * render_ch);
+  for (int i = 0; i < render_ch; ++i) {
+    rp[i] = render ? render + i * n : nullptr;
+    rop[i] = rscratch.data() + i * n;
+  }
+  for (int i = 0; i < capture_ch; ++i) {
+    cp[i] = capture + i * n;
+    op[i] = out + i * n;
+  }
+  int e1 = 0;
+  if (render) e1 = h->apm->ProcessReverseStream(rp.data(), rc, rc, rop.data());
+  h->apm->set_stream_delay_ms(0);
+  int e2 = h->apm->ProcessStream(cp.data(), cc, cc, op.data());
+  return e1 ? e1 : e2;
+}
+
+// stats: [has_erl, erl, has_erle, erle, has_delay, delay_ms]
+void ref_apm_stats(void* p, float* out6) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::AudioProcessingStats s = h->apm->GetStatistics();
+  out6[0] = s.echo_return_loss.has_value();
+  out6[1] = s.echo_return_loss.value_or(0.0);
+  out6[2] = s.echo_return_loss_enhancement.has_value();
+  out6[3] = s.echo_return_loss_enhancement.value_or(0.0);
+  out6[4] = s.delay_ms.has_value();
+  out6[5] = s.delay_ms.value_or(0);
+}
+
+// Run nframes ticks of int16 audio laid out [frame][sample*ch]; stats every
+// `stats_every` frames into stats_out (6 floats each) when non-null.
+int ref_apm_run_i16(void* p, int rate, int render_ch, int capture_ch, int nframes,
+                    const int16_t* render, const int16_t* capture, int16_t* out,
+                    int stats_every, float* stats_out) {
+  const int n = rate / 100;
+  int err = 0, k = 0;
+  for (int f = 0; f < nframes; ++f) {
+    int e = ref_apm_tick_i16(p, rate, render_ch, capture_ch,
+                             render ? render + (size_t)f * n * render_ch : nullptr,
+                             capture + (size_t)f * n * capture_ch,
+                             out + (size_t)f * n * capture_ch, nullptr);
+    if (e && !err) err = e;
+    if (stats_out && stats_every > 0 && (f + 1) % stats_every == 0)
+      ref_apm_stats(p, stats_out + 6 * k++);
+  }
+  return err;
+}
+
+// CPU baseline: `threads` pinned workers, each owning
+// streams t, t+T, ...; every stream is its own AudioProcessing instance fed
+// nframes ticks (the first `warm` untimed).  The audio for stream s is
+// render/capture + s*stride (int16, [frame][sample]) so callers can share one
+// buffer (stride 0) or give each stream its own.  Returns timed wall seconds.
+double ref_apm_bench(int aec, int ns, int ns_level, int rate, int streams,
+                     int threads, int warm, int nframes, const int16_t* render,
+                     const int16_t* capture, size_t stride) {
+  const int n = rate / 100;
+  std::vector<void*> h(streams);
+  for (auto& x : h) x = ref_apm_create(aec, ns, ns_level, 48000, 0, 0, 0);
+  std::atomic<int> ready{0};
+  std::atomic<bool> go{false};
+  std::vector<double> secs(threads, 0.0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    th.emplace_back([&, t] {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      CPU_SET(t % std::thread::hardware_concurrency(), &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+      std::vector<int16_t> out(n), ro(n);
+      for (int s = t; s < streams; s += threads)
+        for (int f = 0; f < warm; ++f)
+          ref_apm_tick_i16(h[s], rate, 1, 1, render + s * stride + (size_t)f * n,
+                           capture + s * stride + (size_t)f * n, out.data(), ro.data());
+      ready++;
+      while (!go.load()) std::this_thread::yield();
+      auto t0 = std::chrono::steady_clock::now();
+      for (int s = t; s < streams; s += threads)
+        for (int f = warm; f < nframes; ++f)
+          ref_apm_tick_i16(h[s], rate, 1, 1, render + s * stride + (size_t)f * n,
+                           capture + s * stride + (size_t)f * n, out.data(), ro.data());
+      secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+  }
+  while (ready.load() < threads) std::this_thread::yield();
+  go = true;
+  double mx = 0;
+  for (int t = 0; t < threads; ++t) {
+    th[t].join();
+    if (secs[t] > mx) mx = secs[t];
+  }
+  for (auto x : h) ref_apm_destroy(x);
+  return mx;
+}
+
+// ------------------------------------------------------------ stage level
+// Ooura 128-point real FFT as AEC3 uses it (reference
+// common_audio/third_party/ooura/fft_size_128/ooura_fft.cc:334-349); the
+// SSE2 bodies are selected when the stubbed cpu_info reports SSE2.
+void ref_fft128(float* a, int inverse) {
+  static webrtc::OouraFft sse2(true), plain(false);
+  webrtc::OouraFft& f =
+      webrtc::cpu_info::Supports(webrtc::cpu_info::ISA::kSSE2) ? sse2 : plain;
+  if (inverse) f.InverseFft(a); else f.Fft(a);
+}
+
+// fft4g 256-point real FFT as NS uses it (reference ns/ns_fft.cc:22-67).
+void ref_rdft256(float* a, int isgn) {
+  static size_t ip[2 + 16] = {0};  // sqrt(128)+2
+  static float w[128];
+  static bool init = false;
+  if (!init) {
+    ip[0] = 0;
+    float tmp[256] = {0};
+    webrtc::WebRtc_rdft(256, 1, tmp, ip, w);
+    init = true;
+  }
+  webrtc::WebRtc_rdft(256, isgn, a, ip, w);
+}
+
+void* ref_hpf_create(int rate, int channels) {
+  return new webrtc::HighPassFilter(rate, channels);
+}
+void ref_hpf_destroy(void* p) { delete static_cast<webrtc::HighPassFilter*>(p); }
+// data: [ch][n] planar, in place (reference high_pass_filter.cc:98-106).
+void ref_hpf_process(void* p, float* data, int channels, int n) {
+  std::vector<std::vector<float>> v(channels);
+  for (int c = 0; c < channels; ++c) v[c].assign(data + c * n, data + (c + 1) * n);
+  static_cast<webrtc::HighPassFilter*>(p)->Process(&v);
+  for (int c = 0; c < channels; ++c) std::memcpy(data + c * n, v[c].data(), n * sizeof(float));
+}
+
+void* ref_3band_create() { return new webrtc::ThreeBandFilterBank(); }
+void ref_3band_destroy(void* p) { delete static_cast<webrtc::ThreeBandFilterBank*>(p); }
+// in[480] -> out[3][160]  (reference three_band_filter_bank.cc:178-225)
+void ref_3band_analysis(void* p, const float* in, float* out) {
+  webrtc::ArrayView<const float, 480> iv(in, 480);
+  std::array<webrtc::ArrayView<float>, 3> ov = {
+      webrtc::ArrayView<float>(out, 160), webrtc::ArrayView<float>(out + 160, 160),
+      webrtc::ArrayView<float>(out + 320, 160)};
+  static_cast<webrtc::ThreeBandFilterBank*>(p)->Analysis(iv, ov);
+}
+// in[3][160] -> out[480]  (reference three_band_filter_bank.cc:233-278)
+void ref_3band_synthesis(void* p, const float* in, float* out) {
+  float* m = const_cast<float*>(in);
+  std::array<webrtc::ArrayView<float>, 3> iv = {
+      webrtc::ArrayView<float>(m, 160), webrtc::ArrayView<float>(m + 160, 160),
+      webrtc::ArrayView<float>(m + 320, 160)};
+  webrtc::ArrayView<float, 480> ov(out, 480);
+  static_cast<webrtc::ThreeBandFilterBank*>(p)->Synthesis(iv, ov);
+}
+
+int ref_isa_level() {
+  using webrtc::cpu_info::ISA;
+  return webrtc::cpu_info::Supports(ISA::kAVX2) ? 2
+         : webrtc::cpu_info::Supports(ISA::kSSE2) ? 1 : 0;
+}
+
+}  // extern "C"
