@@ -1,0 +1,104 @@
+// Device-side basics shared by every DSP stage of the batched APM engine.
+//
+// Execution model: ONE WARP ADVANCES ONE STREAM (call leg).  Every branch
+// that depends on stream state is therefore warp-uniform by construction; the
+// 32 lanes split the 64/65/128/129-bin vectors of the algorithm.  Per-warp
+// scratch lives in dynamic shared memory, persistent state in the stream's
+// slab of the HBM arena (wap_state.h).
+//
+// Numerics contract: FP32, flush-to-zero, no implicit
+// FMA contraction (nvcc -fmad=false); fmaf() appears only where the
+// reference's AVX2 path has an explicit fused multiply-add.  IEEE division
+// and square root (-prec-div=true -prec-sqrt=true).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(WAP_EMU)
+// g++ build for the test-only emulator (tests/emu/cuda_emu.h is force-included).
+#define WAP_DEVCONST static const
+#define WAP_DEV static inline
+#define WAP_DYN_SMEM() (emu::smem_ptr())
+#else
+#include <cuda_runtime.h>
+#define WAP_DEVCONST static __device__ const
+#define WAP_DEV static __device__ __forceinline__
+#define WAP_DYN_SMEM() (wap_dyn_smem_raw)
+extern __shared__ __align__(16) unsigned char wap_dyn_smem_raw[];
+#endif
+
+#define WAP_FULL 0xffffffffu
+
+namespace wap {
+
+// std::min / std::max semantics of the reference ((b < a) ? b : a etc.).
+WAP_DEV float fminr(float a, float b) { return (b < a) ? b : a; }
+WAP_DEV float fmaxr(float a, float b) { return (a < b) ? b : a; }
+WAP_DEV int imin(int a, int b) { return (b < a) ? b : a; }
+WAP_DEV int imax(int a, int b) { return (a < b) ? b : a; }
+WAP_DEV float clampr(float x, float lo, float hi) { return fminr(fmaxr(x, lo), hi); }
+
+WAP_DEV int lane_id() { return (int)(threadIdx.x & 31u); }
+
+template <class T>
+WAP_DEV T bcast(T v, int src) { return __shfl_sync(WAP_FULL, v, src); }
+
+// Sum over the warp in xor-butterfly order (NOT used where the reference's
+// summation order matters).
+WAP_DEV float warp_sum_any_order(float v) {
+  for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(WAP_FULL, v, m);
+  return v;
+}
+WAP_DEV float warp_max(float v) {
+  for (int m = 16; m; m >>= 1) v = fmaxf(v, __shfl_xor_sync(WAP_FULL, v, m));
+  return v;
+}
+WAP_DEV float warp_min(float v) {
+  for (int m = 16; m; m >>= 1) v = fminf(v, __shfl_xor_sync(WAP_FULL, v, m));
+  return v;
+}
+WAP_DEV int warp_or(int v) { return __any_sync(WAP_FULL, v); }
+
+// Left-to-right (reference order) sum of p[0..n) -- every lane evaluates the
+// same serial chain from shared memory, so the result is warp-uniform without
+// a broadcast.  Used wherever the reference runs std::accumulate and the value
+// feeds a threshold decision.
+WAP_DEV float serial_sum(const float* p, int n) {
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += p[i];
+  return s;
+}
+WAP_DEV float serial_sum_sq(const float* p, int n) {
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += p[i] * p[i];
+  return s;
+}
+
+// First index of the maximum (std::max_element semantics) over p[0..n).
+WAP_DEV int warp_argmax_first(const float* p, int n) {
+  const int lane = lane_id();
+  float best = -3.4e38f;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < n; i += 32) {
+    float v = p[i];
+    if (v > best) { best = v; bi = i; }
+  }
+  for (int m = 16; m; m >>= 1) {
+    float ov = __shfl_xor_sync(WAP_FULL, best, m);
+    int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  return bi;
+}
+
+WAP_DEV void warp_copy(float* dst, const float* src, int n) {
+  for (int i = lane_id(); i < n; i += 32) dst[i] = src[i];
+}
+WAP_DEV void warp_fill(float* dst, float v, int n) {
+  for (int i = lane_id(); i < n; i += 32) dst[i] = v;
+}
+WAP_DEV void warp_fill_i(int* dst, int v, int n) {
+  for (int i = lane_id(); i < n; i += 32) dst[i] = v;
+}
+
+}  // namespace wap
