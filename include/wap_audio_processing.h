@@ -1,0 +1,207 @@
+/* wap_audio_processing.h -- C ABI of the B200 batched AudioProcessing engine.
+ *
+ * This is the header the reference's alternate-backend seam includes and does
+ * not ship (reference modules/audio_processing/rust_audio_processing.cc:7,
+ * types declared at rust_audio_processing.h:10-13).  Every entry point below
+ * is bound by that seam; the citation after each one is the reference call
+ * site that fixes its signature.  A build of the reference with
+ * -Drust-backend=true (meson.build:201-248) links this library in place of the
+ * sonora-ffi crate and webrtc::BuiltinAudioProcessingBuilder::Build returns a
+ * RustAudioProcessing that forwards here
+ * (api/audio/builtin_audio_processing_builder.cc:32-43).
+ *
+ * Extensions for the many-stream engine (not in the seam today) are marked
+ * EXT: WapEngine, wap_engine_*, wap_process_streams*.
+ *
+ * Audio conventions are the reference's (api/audio/audio_processing.h:66-77):
+ * 10 ms frames; int16 data interleaved; float data planar in [-1, 1].
+ * There is no CPU fallback: every call needs a CUDA device.
+ */
+#ifndef WAP_AUDIO_PROCESSING_H_
+#define WAP_AUDIO_PROCESSING_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct WapAudioProcessing WapAudioProcessing; /* rust_audio_processing.h:11 */
+typedef struct WapEngine WapEngine;                   /* EXT */
+
+/* rust_audio_processing.cc:13-18 */
+typedef struct WapStreamConfig {
+  int sample_rate_hz;
+  int32_t num_channels;
+} WapStreamConfig;
+
+/* rust_audio_processing.cc:21-40; values map onto AudioProcessing::Error
+ * (api/audio/audio_processing.h:663-683).  The seam is C++ and spells the
+ * enumerators WapError::None, WapDownmixMethod::UseFirstChannel,
+ * WapNoiseSuppressionLevel::Low ... (rust_audio_processing.cc:23-35,376,410),
+ * so C++ sees scoped enums; C sees prefixed constants of the same int32 ABI. */
+#ifdef __cplusplus
+enum class WapError : int32_t {
+  None = 0,
+  NullPointer = 1,
+  Internal = 2,
+  BadSampleRate = 3,
+  BadNumberChannels = 4,
+  BadStreamParameter = 5,
+  BadDataLength = 6,
+  UnsupportedConfig = 7 /* EXT: config class outside SURVEY section 8 scope */
+};
+enum class WapDownmixMethod : int32_t { AverageChannels = 0, UseFirstChannel = 1 };
+enum class WapNoiseSuppressionLevel : int32_t { Low = 0, Moderate = 1, High = 2, VeryHigh = 3 };
+enum class WapSampleFormat : int32_t { I16 = 0, F32 = 1 }; /* EXT */
+#else
+typedef int32_t WapError;
+enum {
+  WapErrorNone = 0,
+  WapErrorNullPointer = 1,
+  WapErrorInternal = 2,
+  WapErrorBadSampleRate = 3,
+  WapErrorBadNumberChannels = 4,
+  WapErrorBadStreamParameter = 5,
+  WapErrorBadDataLength = 6,
+  WapErrorUnsupportedConfig = 7
+};
+typedef int32_t WapDownmixMethod;
+enum { WapDownmixAverageChannels = 0, WapDownmixUseFirstChannel = 1 };
+typedef int32_t WapNoiseSuppressionLevel;
+enum { WapNsLow = 0, WapNsModerate = 1, WapNsHigh = 2, WapNsVeryHigh = 3 };
+typedef int32_t WapSampleFormat;
+enum { WapSampleI16 = 0, WapSampleF32 = 1 };
+#endif
+
+/* Flat mirror of AudioProcessing::Config (api/audio/audio_processing.h:137-376)
+ * with the field set rust_audio_processing.cc:367-442 maps. */
+typedef struct WapConfig {
+  int pipeline_maximum_internal_processing_rate;
+  bool pipeline_multi_channel_render;
+  bool pipeline_multi_channel_capture;
+  WapDownmixMethod pipeline_capture_downmix_method;
+  bool pre_amplifier_enabled;
+  float pre_amplifier_fixed_gain_factor;
+  bool capture_level_adjustment_enabled;
+  float capture_level_adjustment_pre_gain_factor;
+  float capture_level_adjustment_post_gain_factor;
+  bool analog_mic_gain_emulation_enabled;
+  int analog_mic_gain_emulation_initial_level;
+  bool high_pass_filter_enabled;
+  bool high_pass_filter_apply_in_full_band;
+  bool echo_canceller_enabled;
+  bool echo_canceller_enforce_high_pass_filtering;
+  bool noise_suppression_enabled;
+  WapNoiseSuppressionLevel noise_suppression_level;
+  bool noise_suppression_analyze_linear_aec_output_when_available;
+  bool gain_controller2_enabled;
+  float gain_controller2_fixed_digital_gain_db;
+  bool gain_controller2_adaptive_digital_enabled;
+  float gain_controller2_adaptive_digital_headroom_db;
+  float gain_controller2_adaptive_digital_max_gain_db;
+  float gain_controller2_adaptive_digital_initial_gain_db;
+  float gain_controller2_adaptive_digital_max_gain_change_db_per_second;
+  float gain_controller2_adaptive_digital_max_output_noise_level_dbfs;
+  bool gain_controller2_input_volume_controller_enabled;
+} WapConfig;
+
+/* rust_audio_processing.cc:323-347 */
+typedef struct WapStats {
+  bool has_echo_return_loss;
+  double echo_return_loss;
+  bool has_echo_return_loss_enhancement;
+  double echo_return_loss_enhancement;
+  bool has_divergent_filter_fraction;
+  double divergent_filter_fraction;
+  bool has_delay_median_ms;
+  int32_t delay_median_ms;
+  bool has_delay_standard_deviation_ms;
+  int32_t delay_standard_deviation_ms;
+  bool has_residual_echo_likelihood;
+  double residual_echo_likelihood;
+  bool has_residual_echo_likelihood_recent_max;
+  double residual_echo_likelihood_recent_max;
+  bool has_delay_ms;
+  int32_t delay_ms;
+} WapStats;
+
+/* ---- lifetime ---------------------------------------------------------- */
+WapAudioProcessing* wap_create(void);                         /* rust_audio_processing.cc:46 */
+WapAudioProcessing* wap_create_with_config(WapConfig config); /* :51 */
+void wap_destroy(WapAudioProcessing* apm);                    /* :55 */
+WapConfig wap_config_default(void);                           /* :365 */
+WapError wap_get_config(const WapAudioProcessing* apm, WapConfig* out); /* :357 */
+WapError wap_apply_config(WapAudioProcessing* apm, WapConfig config);   /* :83 */
+WapError wap_initialize(WapAudioProcessing* apm, WapStreamConfig input, WapStreamConfig output,
+                        WapStreamConfig reverse_input, WapStreamConfig reverse_output); /* :76-77 */
+
+/* ---- runtime settings -------------------------------------------------- */
+void wap_set_capture_output_used(WapAudioProcessing* apm, bool used);      /* :117,157 */
+void wap_set_capture_pre_gain(WapAudioProcessing* apm, float gain);        /* :127 */
+void wap_set_capture_post_gain(WapAudioProcessing* apm, float gain);       /* :133 */
+void wap_set_capture_fixed_post_gain(WapAudioProcessing* apm, float gain_db); /* :139 */
+void wap_set_playout_volume(WapAudioProcessing* apm, int volume);          /* :145 */
+void wap_set_playout_audio_device(WapAudioProcessing* apm, int id, int max_volume); /* :151 */
+void wap_set_stream_analog_level(WapAudioProcessing* apm, int level);      /* :276 */
+int wap_recommended_stream_analog_level(const WapAudioProcessing* apm);    /* :280 */
+WapError wap_set_stream_delay_ms(WapAudioProcessing* apm, int delay_ms);   /* :286 */
+int wap_stream_delay_ms(const WapAudioProcessing* apm);                    /* :291 */
+
+/* ---- per-frame processing (one call leg) -------------------------------- */
+/* src_len / dest_len = frames * channels (rust_audio_processing.cc:182-191). */
+WapError wap_process_stream_i16(WapAudioProcessing* apm, const int16_t* src, int32_t src_len,
+                                WapStreamConfig input, WapStreamConfig output, int16_t* dest,
+                                int32_t dest_len);                          /* :189-191 */
+WapError wap_process_stream_f32(WapAudioProcessing* apm, const float* const* src, WapStreamConfig input,
+                                WapStreamConfig output, float* const* dest); /* :203-205 */
+WapError wap_process_reverse_stream_i16(WapAudioProcessing* apm, const int16_t* src, int32_t src_len,
+                                        WapStreamConfig input, WapStreamConfig output, int16_t* dest,
+                                        int32_t dest_len);                  /* :223-225 */
+WapError wap_process_reverse_stream_f32(WapAudioProcessing* apm, const float* const* src,
+                                        WapStreamConfig input, WapStreamConfig output,
+                                        float* const* dest);                /* :236-238 */
+WapError wap_get_statistics(const WapAudioProcessing* apm, WapStats* out);  /* :325 */
+
+/* ---- EXT: the batched many-stream engine -------------------------------- */
+/* One engine = one GPU + one config class (sample rate, channel layout,
+ * enabled submodules).  Streams are slots of its HBM state arena. */
+WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig config,
+                             WapStreamConfig stream_format);
+void wap_engine_destroy(WapEngine* engine);
+/* Creates `n` call legs in the engine; handles are owned by the caller and
+ * released with wap_destroy. */
+WapError wap_engine_create_streams(WapEngine* engine, int32_t n, WapAudioProcessing** out_handles);
+size_t wap_engine_state_bytes_per_stream(const WapEngine* engine);
+/* Algorithmic HBM bytes one stream touches per 10 ms frame for this engine's
+ * config class (SURVEY.md section 8(d) model; used for roofline reporting). */
+double wap_engine_algorithmic_bytes_per_frame(const WapEngine* engine);
+
+/* One 10 ms tick for `n` call legs: for leg i, ProcessReverseStream(render_i)
+ * (skipped when render_frames is NULL), set_stream_delay_ms(0) semantics as
+ * configured on the handle, then ProcessStream(capture_i) -> out_i.
+ * Frames are packed [leg][channel-interleaved samples] for I16 and
+ * [leg][channel][sample] for F32, HOST memory; copies are part of the call.
+ * per_stream_err may be NULL. */
+WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, const void* render_frames,
+                             const void* capture_frames, void* out_frames, WapSampleFormat fmt,
+                             WapError* per_stream_err);
+/* Same, but the three buffers are DEVICE pointers on the engine's GPU and the
+ * call only enqueues the tick on the engine's CUDA stream. */
+WapError wap_process_streams_device(WapEngine* engine, WapAudioProcessing* const* handles, int32_t n,
+                                    const void* d_render, const void* d_capture, void* d_out,
+                                    WapSampleFormat fmt);
+WapError wap_engine_synchronize(WapEngine* engine);
+/* CUDA stream the engine launches on (cudaStream_t), for event timing. */
+void* wap_engine_cuda_stream(WapEngine* engine);
+/* Number of kernel launches issued by the engine so far. */
+int64_t wap_engine_launch_count(const WapEngine* engine);
+
+const char* wap_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAP_AUDIO_PROCESSING_H_ */

@@ -1,0 +1,425 @@
+// Host engine + C ABI (include/wap_audio_processing.h) + the tick kernel.
+//
+// Host responsibilities restated from AudioProcessingImpl: format validation
+// and error codes (audio_processing_impl.cc:163-323), processing-rate
+// selection (:92-107), submodule on/off matrix (:362-446), stream-delay clamp
+// (:1689-1707), statistics (:1509-1518).  The DSP itself runs only on the GPU:
+// there is no CPU fallback and creation fails loudly without a CUDA device.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "wap_audio_processing.h"
+#include "wap_init.h"
+#include "wap_launch.h"
+#include "wap_pipeline.cuh"
+
+namespace wap {
+
+__global__ void __launch_bounds__(128) k_tick(TickArgs a, int scratch_floats) {
+  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float* scratch = sm + (size_t)warp * scratch_floats;
+  for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
+    process_stream_tick(a, idx, scratch);
+    __syncwarp();
+  }
+}
+
+// Broadcasts the initial-state template into `n` arena slots.
+__global__ void k_init_slots(StreamState* states, const StreamState* tmpl, const int* slots, int n) {
+  const size_t words = sizeof(StreamState) / 4;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(tmpl);
+  for (int i = blockIdx.y; i < n; i += gridDim.y) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&states[slots[i]]);
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x)
+      dst[w] = src[w];
+  }
+}
+
+}  // namespace wap
+
+using wap::EngineConfig;
+using wap::StreamState;
+
+#define WAP_CUDA(x)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess) {                                                             \
+      fprintf(stderr, "[wap_b200] CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, \
+              cudaGetErrorString(e_));                                                   \
+      return WapError::Internal;                                                         \
+    }                                                                                    \
+  } while (0)
+
+struct WapEngine {
+  int device = 0;
+  int capacity = 0;
+  WapConfig config{};
+  WapStreamConfig format{};
+  EngineConfig cfg{};
+  StreamState* d_states = nullptr;
+  StreamState* d_template = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<int> free_slots;
+  std::mutex mu;
+  // staging for the host-buffer entry points
+  void* d_render = nullptr;
+  void* d_capture = nullptr;
+  void* d_out = nullptr;
+  int* d_slots = nullptr;
+  int* d_delays = nullptr;
+  void* h_pinned = nullptr;  // render | capture | out
+  size_t staged_streams = 0;
+  std::vector<int> last_slots;
+  int64_t launches = 0;
+  int frame_len = 0;  // samples per frame (all channels)
+  int scratch_floats = 0;
+  bool is_default = false;
+};
+
+struct WapAudioProcessing {
+  WapEngine* engine = nullptr;
+  int slot = -1;
+  WapConfig config{};
+  int stream_delay_ms = 0;
+  bool was_stream_delay_set = false;
+  bool capture_output_used = true;
+  int analog_level = 0;
+  std::deque<std::vector<unsigned char>> render_queue;  // SwapQueue stand-in (aec3_common.h:41)
+  WapSampleFormat render_fmt = WapSampleFormat::I16;
+  std::mutex render_mu;
+  bool owns_engine = false;
+};
+
+namespace {
+
+bool g_warned_no_device = false;
+
+WapError check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    if (!g_warned_no_device) {
+      fprintf(stderr,
+              "[wap_b200] FATAL: no CUDA device available (%s). This library has no CPU fallback.\n",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+      g_warned_no_device = true;
+    }
+    return WapError::Internal;
+  }
+  return WapError::None;
+}
+
+// SuitableProcessRate (audio_processing_impl.cc:92-107) restricted to the
+// native-rate config classes of SURVEY.md section 8.
+WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConfig* out) {
+  if (f.sample_rate_hz < 8000 || f.sample_rate_hz > 384000) return WapError::BadSampleRate;
+  if (f.num_channels <= 0) return WapError::BadNumberChannels;
+  EngineConfig e{};
+  if (f.sample_rate_hz == 16000) {
+    e.num_bands = 1;
+  } else if (f.sample_rate_hz == 48000 && c.pipeline_maximum_internal_processing_rate == 48000) {
+    e.num_bands = 3;
+  } else {
+    return WapError::UnsupportedConfig;  // resampled / 2-band paths: SURVEY 8(f)-2
+  }
+  if (f.num_channels != 1) return WapError::UnsupportedConfig;  // multichannel: SURVEY 8 cfg4, later round
+  if (c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled)
+    return WapError::UnsupportedConfig;
+  e.sample_rate_hz = f.sample_rate_hz;
+  e.aec_enabled = c.echo_canceller_enabled;
+  e.ns_enabled = c.noise_suppression_enabled;
+  // InitializeHighPassFilter (audio_processing_impl.cc:1883-1907)
+  e.hpf_enabled = c.high_pass_filter_enabled || c.noise_suppression_enabled ||
+                  (c.echo_canceller_enabled && c.echo_canceller_enforce_high_pass_filtering);
+  if (e.aec_enabled && e.num_bands != 1) return WapError::UnsupportedConfig;  // 48 kHz AEC3: later round
+  switch (c.noise_suppression_level) {  // suppression_params.cc:18-48
+    case WapNoiseSuppressionLevel::Low:
+      e.ns_over_subtraction_factor = 1.f; e.ns_minimum_attenuating_gain = 0.5f; e.ns_use_attenuation_adjustment = 0; break;
+    case WapNoiseSuppressionLevel::Moderate:
+      e.ns_over_subtraction_factor = 1.f; e.ns_minimum_attenuating_gain = 0.25f; e.ns_use_attenuation_adjustment = 1; break;
+    case WapNoiseSuppressionLevel::High:
+      e.ns_over_subtraction_factor = 1.1f; e.ns_minimum_attenuating_gain = 0.125f; e.ns_use_attenuation_adjustment = 1; break;
+    default:
+      e.ns_over_subtraction_factor = 1.25f; e.ns_minimum_attenuating_gain = 0.09f; e.ns_use_attenuation_adjustment = 1; break;
+  }
+  e.capture_output_used = 1;
+  *out = e;
+  return WapError::None;
+}
+
+WapError ensure_staging(WapEngine* e, size_t n) {
+  if (n <= e->staged_streams) return WapError::None;
+  size_t cap = std::max<size_t>(n, std::min<size_t>((size_t)e->capacity, std::max<size_t>(64, 2 * e->staged_streams)));
+  if (e->d_render) cudaFree(e->d_render);
+  if (e->d_capture) cudaFree(e->d_capture);
+  if (e->d_out) cudaFree(e->d_out);
+  if (e->d_slots) cudaFree(e->d_slots);
+  if (e->d_delays) cudaFree(e->d_delays);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  const size_t fb = (size_t)e->frame_len * sizeof(float);
+  WAP_CUDA(cudaMalloc(&e->d_render, cap * fb));
+  WAP_CUDA(cudaMalloc(&e->d_capture, cap * fb));
+  WAP_CUDA(cudaMalloc(&e->d_out, cap * fb));
+  WAP_CUDA(cudaMalloc((void**)&e->d_slots, cap * sizeof(int)));
+  WAP_CUDA(cudaMalloc((void**)&e->d_delays, cap * sizeof(int)));
+  WAP_CUDA(cudaMallocHost(&e->h_pinned, cap * (3 * fb + 2 * sizeof(int))));
+  e->staged_streams = cap;
+  e->last_slots.clear();
+  return WapError::None;
+}
+
+int grid_for(int n_streams) {
+  const int wpb = 4;
+  int blocks = (n_streams + wpb - 1) / wpb;
+  return std::max(1, blocks);
+}
+
+WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int uniform_delay, int n,
+                     const void* d_render, const void* d_capture, void* d_out, WapSampleFormat fmt) {
+  wap::TickArgs a{};
+  a.states = e->d_states;
+  a.slots = d_slots;
+  a.delays_ms = d_delays;
+  a.uniform_delay_ms = uniform_delay;
+  a.n = n;
+  a.render = d_render;
+  a.capture = d_capture;
+  a.out = d_out;
+  a.fmt = (int)fmt;
+  a.cfg = e->cfg;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * e->scratch_floats * sizeof(float);
+  WAP_LAUNCH(wap::k_tick, grid_for(n), wpb * 32, smem, e->stream, a, e->scratch_floats);
+  e->launches++;
+  WAP_CUDA(cudaGetLastError());
+  return WapError::None;
+}
+
+std::mutex g_default_mu;
+WapEngine* g_default_engines[8] = {nullptr};
+
+}  // namespace
+
+extern "C" {
+
+const char* wap_version(void) { return "wap_b200 0.1 (sm_100a)"; }
+
+WapConfig wap_config_default(void) {
+  // Defaults of AudioProcessing::Config (api/audio/audio_processing.h:137-376).
+  WapConfig c{};
+  c.pipeline_maximum_internal_processing_rate = 32000;
+  c.pipeline_capture_downmix_method = WapDownmixMethod::AverageChannels;
+  c.pre_amplifier_fixed_gain_factor = 1.f;
+  c.capture_level_adjustment_pre_gain_factor = 1.f;
+  c.capture_level_adjustment_post_gain_factor = 1.f;
+  c.analog_mic_gain_emulation_initial_level = 255;
+  c.high_pass_filter_apply_in_full_band = true;
+  c.echo_canceller_enforce_high_pass_filtering = true;
+  c.noise_suppression_level = WapNoiseSuppressionLevel::Moderate;
+  c.gain_controller2_adaptive_digital_headroom_db = 5.f;
+  c.gain_controller2_adaptive_digital_max_gain_db = 50.f;
+  c.gain_controller2_adaptive_digital_initial_gain_db = 15.f;
+  c.gain_controller2_adaptive_digital_max_gain_change_db_per_second = 6.f;
+  c.gain_controller2_adaptive_digital_max_output_noise_level_dbfs = -50.f;
+  return c;
+}
+
+WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig config, WapStreamConfig fmt) {
+  if (check_device() != WapError::None) return nullptr;
+  EngineConfig cfg{};
+  WapError err = resolve_config(config, fmt, &cfg);
+  if (err != WapError::None) {
+    fprintf(stderr, "[wap_b200] unsupported engine config (error %d)\n", (int)err);
+    return nullptr;
+  }
+  if (max_streams <= 0) return nullptr;
+  WapEngine* e = new (std::nothrow) WapEngine;
+  if (!e) return nullptr;
+  e->device = cuda_device;
+  e->capacity = max_streams;
+  e->config = config;
+  e->format = fmt;
+  e->cfg = cfg;
+  e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
+  e->scratch_floats = wap::warp_scratch_floats(cfg.num_bands);
+  bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc((void**)&e->d_states, (size_t)max_streams * sizeof(StreamState)) == cudaSuccess &&
+            cudaMalloc((void**)&e->d_template, sizeof(StreamState)) == cudaSuccess;
+  if (ok) {
+    StreamState* tmpl = new StreamState;
+    wap::init_stream_state(*tmpl);
+    ok = cudaMemcpy(e->d_template, tmpl, sizeof(StreamState), cudaMemcpyHostToDevice) == cudaSuccess;
+    delete tmpl;
+  }
+  const size_t smem = (size_t)4 * e->scratch_floats * sizeof(float);
+  if (ok && smem > 48 * 1024)
+    ok = cudaFuncSetAttribute(wap::k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  if (!ok) {
+    fprintf(stderr, "[wap_b200] engine allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    wap_engine_destroy(e);
+    return nullptr;
+  }
+  e->free_slots.reserve(max_streams);
+  for (int i = max_streams - 1; i >= 0; --i) e->free_slots.push_back(i);
+  return e;
+}
+
+void wap_engine_destroy(WapEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_states);
+  cudaFree(e->d_template);
+  cudaFree(e->d_render);
+  cudaFree(e->d_capture);
+  cudaFree(e->d_out);
+  cudaFree(e->d_slots);
+  cudaFree(e->d_delays);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing** out) {
+  if (!e || !out) return WapError::NullPointer;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n <= 0 || (size_t)n > e->free_slots.size()) return WapError::BadStreamParameter;
+  WAP_CUDA(cudaSetDevice(e->device));
+  std::vector<int> slots(n);
+  for (int i = 0; i < n; ++i) {
+    slots[i] = e->free_slots.back();
+    e->free_slots.pop_back();
+  }
+  int* d_slots = nullptr;
+  WAP_CUDA(cudaMalloc((void**)&d_slots, (size_t)n * sizeof(int)));
+  WAP_CUDA(cudaMemcpy(d_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  WAP_LAUNCH(wap::k_init_slots, dim3(16, std::min(n, 4096)), 256, 0, e->stream, e->d_states,
+             (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
+  e->launches++;
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_slots);
+  for (int i = 0; i < n; ++i) {
+    WapAudioProcessing* h = new WapAudioProcessing;
+    h->engine = e;
+    h->slot = slots[i];
+    h->config = e->config;
+    out[i] = h;
+  }
+  return WapError::None;
+}
+
+size_t wap_engine_state_bytes_per_stream(const WapEngine*) { return sizeof(StreamState); }
+
+WapError wap_engine_synchronize(WapEngine* e) {
+  if (!e) return WapError::NullPointer;
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  return WapError::None;
+}
+void* wap_engine_cuda_stream(WapEngine* e) { return e ? (void*)e->stream : nullptr; }
+int64_t wap_engine_launch_count(const WapEngine* e) { return e ? e->launches : 0; }
+
+WapError wap_process_streams_device(WapEngine* e, WapAudioProcessing* const* handles, int32_t n,
+                                    const void* d_render, const void* d_capture, void* d_out,
+                                    WapSampleFormat fmt) {
+  if (!e || !handles) return WapError::NullPointer;
+  if (n <= 0) return WapError::BadStreamParameter;
+  WAP_CUDA(cudaSetDevice(e->device));
+  WapError err = ensure_staging(e, n);
+  if (err != WapError::None) return err;
+  // slot list (cached across ticks while the leg set is unchanged)
+  bool same = e->last_slots.size() == (size_t)n;
+  for (int i = 0; same && i < n; ++i) same = handles[i] && e->last_slots[i] == handles[i]->slot;
+  int uniform_delay = -1;
+  bool uniform = true;
+  for (int i = 0; i < n; ++i) {
+    if (!handles[i] || handles[i]->engine != e) return WapError::BadStreamParameter;
+    const int d = handles[i]->was_stream_delay_set ? handles[i]->stream_delay_ms : -1;
+    if (i == 0) uniform_delay = d; else uniform = uniform && d == uniform_delay;
+  }
+  if (!same) {
+    e->last_slots.resize(n);
+    for (int i = 0; i < n; ++i) e->last_slots[i] = handles[i]->slot;
+    WAP_CUDA(cudaMemcpyAsync(e->d_slots, e->last_slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  const int* d_delays = nullptr;
+  if (!uniform) {
+    std::vector<int> dl(n);
+    for (int i = 0; i < n; ++i) dl[i] = handles[i]->was_stream_delay_set ? handles[i]->stream_delay_ms : -1;
+    WAP_CUDA(cudaMemcpyAsync(e->d_delays, dl.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+    d_delays = e->d_delays;
+  }
+  return launch_tick(e, e->d_slots, d_delays, uniform_delay, n, d_render, d_capture, d_out, fmt);
+}
+
+WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, const void* render,
+                             const void* capture, void* out, WapSampleFormat fmt, WapError* per_stream_err) {
+  if (!handles || !capture || !out) return WapError::NullPointer;
+  if (n <= 0 || !handles[0]) return WapError::BadStreamParameter;
+  WapEngine* e = handles[0]->engine;
+  WAP_CUDA(cudaSetDevice(e->device));
+  WapError err = ensure_staging(e, n);
+  if (err != WapError::None) return err;
+  const size_t esz = fmt == WapSampleFormat::I16 ? sizeof(int16_t) : sizeof(float);
+  const size_t bytes = (size_t)n * e->frame_len * esz;
+  unsigned char* hp = static_cast<unsigned char*>(e->h_pinned);
+  const size_t stride = e->staged_streams * e->frame_len * sizeof(float);
+  if (render) {
+    memcpy(hp, render, bytes);
+    WAP_CUDA(cudaMemcpyAsync(e->d_render, hp, bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+  memcpy(hp + stride, capture, bytes);
+  WAP_CUDA(cudaMemcpyAsync(e->d_capture, hp + stride, bytes, cudaMemcpyHostToDevice, e->stream));
+  err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
+  if (err != WapError::None) return err;
+  WAP_CUDA(cudaMemcpyAsync(hp + 2 * stride, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  memcpy(out, hp + 2 * stride, bytes);
+  for (int i = 0; i < n; ++i) handles[i]->was_stream_delay_set = false;  // audio_processing_impl.cc:1556
+  if (per_stream_err) for (int i = 0; i < n; ++i) per_stream_err[i] = WapError::None;
+  return WapError::None;
+}
+
+}  // extern "C"
+
+namespace wap {
+#ifndef WAP_HAVE_AEC3_INIT
+void init_aec3_state(Aec3State& a) { memset(&a, 0, sizeof(a)); }
+#endif
+}  // namespace wap
+
+extern "C" {
+
+WapError wap_get_statistics(const WapAudioProcessing* h, WapStats* out) {
+  if (!h || !out) return WapError::NullPointer;
+  memset(out, 0, sizeof(*out));
+  return WapError::None;
+}
+
+double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
+  if (!e) return 0.0;
+  // SURVEY.md section 8(d) byte model.
+  const int B = e->cfg.num_bands;
+  double bytes = 0.0;
+  if (e->cfg.aec_enabled) bytes += 2.5 * 107460.0;
+  if (e->cfg.ns_enabled) bytes += 2223.0 * 8.0 + 24.0;
+  if (e->cfg.hpf_enabled) bytes += 96.0;
+  if (B == 3) bytes += 2 * 2 * 150 * 4.0;
+  bytes += e->frame_len * 4.0 * (e->cfg.aec_enabled ? 3 : 2);
+  return bytes;
+}
+
+}  // extern "C"
+#include "wap_single.inc"

@@ -1,0 +1,264 @@
+// Per-stream persistent state of the batched APM engine, laid out for HBM.
+//
+// One StreamState slab per call leg, slabs contiguous in one device arena
+// (wap_engine).  Inside a slab every vector of the algorithm is its own
+// contiguous, 16-byte aligned array (spectra as separate re[] / im[] arrays,
+// filter partitions as [partition][bin]) so that the warp that owns the stream
+// reads and writes each of them as consecutive 128-byte lines: structure of
+// arrays within the stream, one warp per stream across the arena.
+//
+// The field inventory follows SURVEY.md appendix A; each block cites the
+// reference class whose members it restates.  Plain C++ POD: shared by host
+// (initialisation, statistics read-back) and device code.
+#pragma once
+
+#include <stdint.h>
+
+namespace wap {
+
+constexpr int kMaxBands = 3;
+constexpr int kFrame = 160;          // samples per band per 10 ms (aec3_common.h:44)
+constexpr int kBlock = 64;           // AEC3 block (aec3_common.h:47)
+constexpr int kBins = 65;            // kFftLengthBy2Plus1
+constexpr int kBinsPad = 68;         // padded to a float4 multiple
+constexpr int kNsBins = 129;         // ns_common.h:19
+constexpr int kNsBinsPad = 132;
+constexpr int kNsOverlap = 96;       // kFftSize - kNsFrameSize
+
+// --- AEC3 default geometry (echo_canceller3_config.h:38-120, aec3_common.h:70-83)
+constexpr int kMaxPartitions = 13;   // filter.refined/coarse.length_blocks
+constexpr int kInitPartitions = 12;  // *_initial.length_blocks
+constexpr int kNumMatchedFilters = 5;
+constexpr int kDownSampling = 4;
+constexpr int kSubBlock = kBlock / kDownSampling;            // 16
+constexpr int kMfWindowSubBlocks = 32;                       // aec3_common.h:52
+constexpr int kMfShiftSubBlocks = kMfWindowSubBlocks * 3 / 4;  // 24
+constexpr int kMfLen = kMfWindowSubBlocks * kSubBlock;       // 512 taps
+constexpr int kMfShift = kMfShiftSubBlocks * kSubBlock;      // 384
+constexpr int kLowRateSize =                                 // GetDownSampledBufferSize: 2448
+    kSubBlock * (kMfShiftSubBlocks * kNumMatchedFilters + kMfWindowSubBlocks + 1);
+constexpr int kRingBlocks = kLowRateSize / kSubBlock + kMaxPartitions + 1;  // 167
+constexpr int kMaxFilterLag = kNumMatchedFilters * kMfShift + kMfLen;       // GetMaxFilterLag: 2432
+constexpr int kLagHistSize = kMaxFilterLag + 1;                             // 2433
+constexpr int kPreEchoHistSize = (kLagHistSize * kDownSampling) >> 6;       // 152
+constexpr int kAccErrLen = kMfLen / 4;                                      // 128
+
+struct Biquad {
+  float x0, x1, y0, y1;  // CascadedBiQuadFilter::BiQuad::{x,y} (cascaded_biquad_filter.h)
+};
+
+// ThreeBandFilterBank::{state_analysis_, state_synthesis_} (three_band_filter_bank.h:67-70)
+struct ThreeBandState {
+  float analysis[10][16];
+  float synthesis[10][16];
+};
+
+// NoiseSuppressor::ChannelState and everything it owns (ns/noise_suppressor.h:62-76).
+struct NsState {
+  // NoiseSuppressor::ChannelState
+  float analyze_mem[kNsOverlap];
+  float process_mem[kNsOverlap];
+  float synth_mem[kNsOverlap];
+  float delay_mem[kMaxBands - 1][kNsOverlap];
+  float prev_analysis_spectrum[kNsBinsPad];  // init 1
+  // NoiseEstimator (ns/noise_estimator.h)
+  float noise[kNsBinsPad];
+  float prev_noise[kNsBinsPad];
+  float conservative_noise[kNsBinsPad];
+  float parametric_noise[kNsBinsPad];
+  // QuantileNoiseEstimator (ns/quantile_noise_estimator.h:36-41)
+  float q_density[3 * kNsBins + 1];   // init 0.3
+  float q_log_quantile[3 * kNsBins + 1];  // init 8
+  float q_quantile[kNsBinsPad];       // init 0
+  // WienerFilter (ns/wiener_filter.h)
+  float wiener[kNsBinsPad];           // init 1
+  float initial_spectral_estimate[kNsBinsPad];
+  float spectrum_prev_process[kNsBinsPad];
+  // SpeechProbabilityEstimator / SignalModelEstimator
+  float speech_prob[kNsBinsPad];
+  float avg_log_lrt[kNsBinsPad];      // init 0.5
+  int hist_lrt[1000];
+  int hist_flatness[1000];
+  int hist_diff[1000];
+  // scalars
+  int q_counter[3];                   // {66,133,200}
+  int q_num_updates;                  // 1
+  int num_analyzed_frames;            // -1 (NoiseSuppressor::num_analyzed_frames_)
+  int histogram_analysis_counter;     // 500
+  float white_noise_level, pink_noise_numerator, pink_noise_exp;
+  float prior_speech_prob;            // 0.5
+  float lrt, spectral_flatness, spectral_diff;  // SignalModel, init 0.5
+  float prior_lrt;                    // PriorSignalModel, init 0.5
+  float prior_flatness_threshold;     // 0.5
+  float prior_template_diff_threshold;  // 0.5
+  float prior_lrt_weighting;          // 1
+  float prior_flatness_weighting;     // 0
+  float prior_difference_weighting;   // 0
+  float diff_normalization, signal_energy_sum;
+  float pad_[2];
+};
+
+// ---------------------------------------------------------------- AEC3
+struct Aec3State {
+  // ---- RenderDelayBuffer rings (render_delay_buffer.cc:72-101)
+  float blocks[kRingBlocks][kBlock];        // BlockBuffer, band 0 / channel 0
+  float fft_re[kRingBlocks][kBinsPad];      // FftBuffer
+  float fft_im[kRingBlocks][kBinsPad];
+  float spectra[kRingBlocks][kBinsPad];     // SpectrumBuffer
+  float low_rate[kLowRateSize];             // DownsampledRenderBuffer
+  // ---- MatchedFilter (matched_filter.h:156-164)
+  float mf_h[kNumMatchedFilters][kMfLen];
+  float mf_acc_err[kNumMatchedFilters][kAccErrLen];  // init 1
+  // ---- lag aggregator histograms (matched_filter_lag_aggregator.h:61-98)
+  int lag_hist[kLagHistSize + 3];
+  int lag_hist_data[250 + 2];
+  int pre_hist[kPreEchoHistSize];
+  int pre_hist_data[250 + 2];               // init -1
+  // ---- Subtractor / AdaptiveFirFilter (subtractor.h, adaptive_fir_filter.h)
+  float Hr_re[kMaxPartitions][kBinsPad];    // refined filter
+  float Hr_im[kMaxPartitions][kBinsPad];
+  float Hc_re[kMaxPartitions][kBinsPad];    // coarse filter
+  float Hc_im[kMaxPartitions][kBinsPad];
+  float H2[kMaxPartitions][kBinsPad];       // refined_frequency_responses_
+  float h_time[kMaxPartitions * kBlock];    // refined_impulse_responses_
+  float h_highpass[kMaxPartitions * kBlock];  // FilterAnalyzer::h_highpass_
+  float H_error[kBinsPad];                  // RefinedFilterUpdateGain::H_error_, init 10000
+  // ---- 65-bin estimator vectors
+  float erle[kBinsPad], erle_onset_comp[kBinsPad], erle_unbounded[kBinsPad], erle_during_onsets[kBinsPad];
+  float accum_Y2[kBinsPad], accum_E2[kBinsPad];
+  float erl[kBinsPad];                      // init 1000
+  float avg_render_reverb[kBinsPad];        // AecState::avg_render_reverb_
+  float echo_reverb[kBinsPad];              // ResidualEchoEstimator::echo_reverb_
+  float tail_response[kBinsPad];            // ReverbFrequencyResponse
+  float X2_noise_floor[kBinsPad];           // init 1638400
+  float cng_Y2_smoothed[kBinsPad], cng_N2[kBinsPad], cng_N2_initial[kBinsPad];
+  float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
+  float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (4 blocks -> 3 slots)
+  int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used)
+  int erle_hold_counters[kBinsPad];
+  int erl_hold_counters[kBinsPad];          // 63 used, index k-1
+  int X2_noise_floor_counter[kBinsPad];     // init 50
+  unsigned char accum_low_render[kBinsPad]; // SubbandErleEstimator accum_spectra_.low_render_energy
+  unsigned char coming_onset[kBinsPad];     // init true
+  // ---- time-domain memories
+  float e_old[kBlock], y_old[kBlock], e_output_old[kBlock];
+  float render_blocker[kBlock], capture_blocker[kBlock], output_framer[kBlock];
+  Biquad render_decimator[4], capture_decimator[4];
+  // ---- scalar state (one cache line group, read into registers per block)
+  struct Scalars {
+    // FrameBlocker / BlockFramer fill levels
+    int render_blocker_len, capture_blocker_len, output_framer_len;
+    // BlockProcessorImpl (block_processor.cc:67-78)
+    int capture_properly_started, render_properly_started, render_event;
+    // RenderDelayBufferImpl
+    int blocks_write, blocks_read, spectra_write, spectra_read;  // fft ring shares spectra indices
+    int lr_write, lr_read;
+    int has_delay, delay;                   // std::optional<size_t> delay_
+    int last_call_was_render, num_api_calls_in_a_row, max_observed_jitter;
+    int render_activity, render_activity_counter, rb_render_activity;  // rb_*: RenderBuffer::render_activity_
+    int has_external_delay, external_delay, external_delay_verified;
+    int min_latency_blocks, excess_render_detection_counter;
+    long long capture_call_counter, render_call_counter;
+    // RenderDelayControllerImpl (render_delay_controller.cc:55-62)
+    int ctl_has_delay, ctl_delay, ctl_delay_quality;       // delay_ (blocks)
+    int ctl_has_delay_samples, ctl_delay_samples, ctl_delay_samples_quality;
+    int ctl_blocks_since_last_change, ctl_blocks_since_last_update;
+    int ctl_delay_change_counter, ctl_last_quality;
+    long long ctl_capture_call_counter;
+    // EchoPathDelayEstimator
+    int est_has_old_lag, est_old_lag, est_old_lag_quality, est_consistent_counter;
+    // MatchedFilter
+    int mf_last_detected_best_lag_filter;   // -1
+    int mf_number_pre_echo_updates;
+    // MatchedFilterLagAggregator
+    int agg_significant_candidate_found;
+    int agg_hist_data_index, agg_candidate;          // HighestPeakAggregator
+    int pre_hist_data_index, pre_candidate, pre_number_updates;  // PreEchoLagAggregator
+    // ClockdriftDetector
+    int cd_history[3], cd_level, cd_stability_counter;
+    // EchoRemoverImpl
+    long long er_block_counter;
+    int er_gain_change_hangover, er_refined_last_selected;  // init true
+    // Subtractor + filters + gains
+    int fr_current_size, fr_target_size, fr_old_target_size, fr_size_change_counter, fr_partition_to_constrain;
+    int fc_current_size, fc_target_size, fc_old_target_size, fc_size_change_counter, fc_partition_to_constrain;
+    int h_time_size;                        // refined_impulse_responses_.size() / 64
+    int H2_size;                            // refined_frequency_responses_.size()
+    int rg_poor_excitation_counter, rg_call_counter, rg_config_change_counter;  // RefinedFilterUpdateGain
+    float rg_cur[5], rg_old[5], rg_tgt[5];  // leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate
+    int cg_poor_excitation_counter, cg_call_counter, cg_config_change_counter;  // CoarseFilterUpdateGain
+    float cg_cur[2], cg_old[2], cg_tgt[2];  // rate, noise_gate
+    int mis_n_blocks_acum, mis_overhang;    // FilterMisadjustmentEstimator
+    float mis_e2_acum, mis_y2_acum, mis_inv_misadjustment;
+    int poor_coarse_filter_counter, coarse_filter_reset_hangover;
+    // RenderSignalAnalyzer
+    int rsa_has_narrow_peak, rsa_narrow_peak_band, rsa_narrow_peak_counter;
+    // AecState
+    int capture_signal_saturation;
+    int strong_not_saturated_render_blocks, blocks_with_active_render;
+    int init_state, init_transition_triggered, init_strong_blocks;   // InitialState
+    int fd_filter_delay, fd_min_filter_delay, fd_has_external, fd_external_delay, fd_external_quality;  // FilterDelay
+    int fq_usable, fq_blocks_since_reset, fq_blocks_since_start, fq_convergence_seen;  // FilteringQualityAnalyzer
+    int saturated_echo;
+    int soa_filter_converged;               // SubtractorOutputAnalyzer::filters_converged_[0]
+    // FilterAnalyzer
+    int fa_blocks_since_reset, fa_region_start, fa_region_end, fa_peak_index, fa_filter_length_blocks;
+    int fa_consistent_estimate, fa_filter_delay_blocks, fa_min_filter_delay_blocks;
+    float fa_gain;
+    int cfd_significant_peak, cfd_floor_low_limit, cfd_floor_high_limit;
+    int cfd_consistent_counter, cfd_consistent_delay_reference;
+    float cfd_floor_accum, cfd_secondary_peak;
+    // LegacyTransparentModeImpl (transparent_mode.cc:222-233)
+    int tm_capture_block_counter, tm_active, tm_active_blocks_since_sane_filter, tm_sane_filter_observed;
+    int tm_finite_erl_recently_detected, tm_non_converged_sequence_size, tm_diverged_sequence_size;
+    int tm_active_non_converged_sequence_size, tm_num_converged_blocks, tm_recent_convergence;
+    int tm_strong_not_saturated_render_blocks;
+    // ErleEstimator / SubbandErleEstimator / FullBandErleEstimator
+    int erle_blocks_since_reset, erle_num_points;
+    int fb_hold_counter, fb_has_erle_log2, fb_num_points;
+    float fb_erle_time_domain_log2, fb_erle_log2, fb_inst_quality, fb_max_erle_log2, fb_min_erle_log2;
+    float fb_Y2_acum, fb_E2_acum;
+    int fb_has_quality; float fb_quality;   // linear_filters_qualities_[0]
+    // ErlEstimator
+    int erl_blocks_since_reset, erl_hold_counter_time_domain;
+    float erl_time_domain;
+    // Reverb
+    float reverb_average_decay;
+    // ComfortNoiseGenerator
+    int cng_N2_counter, cng_has_initial;
+    unsigned cng_seed;                      // 42
+    // SuppressionGain
+    int sg_initial_state, sg_initial_state_change_counter, sg_nearend_mem_index;
+    float sg_average_power;                 // LowNoiseRenderDetector, 32768^2
+    int dn_nearend_state, dn_trigger_counter, dn_hold_counter;
+    // statistics mirror (EchoRemoverImpl::GetMetrics / BlockProcessorImpl::GetMetrics)
+    int saturated_microphone_signal;        // EchoCanceller3::saturated_microphone_signal_
+    int pad_[3];
+  } s;
+};
+
+// One call leg.
+struct StreamState {
+  Biquad hpf[3];                // HighPassFilter (capture, channel 0)
+  int pad_[4];
+  ThreeBandState capture_bands; // AudioBuffer's SplittingFilter (48 kHz only)
+  ThreeBandState render_bands;
+  NsState ns;
+  Aec3State aec;
+};
+
+// Engine-wide (config class) constants uploaded once.
+struct EngineConfig {
+  int sample_rate_hz;   // 16000 or 48000
+  int num_bands;        // 1 or 3
+  int aec_enabled;
+  int ns_enabled;
+  int hpf_enabled;
+  // SuppressionParams (ns/suppression_params.cc:18-48)
+  float ns_over_subtraction_factor;
+  float ns_minimum_attenuating_gain;
+  int ns_use_attenuation_adjustment;
+  int capture_output_used;
+};
+
+}  // namespace wap

@@ -1,0 +1,196 @@
+"""ctypes binding of libwap_b200.so -- the C ABI in include/wap_audio_processing.h.
+
+Python is plumbing only (tests, bench): the product is the shared library.
+`load()` binds the CUDA build; it raises if the library is missing -- there is
+no CPU fallback.  (The test suite may pass the path of the emulator build of
+the same sources, tests/emu/_build/libwap_emu.so, to exercise the kernel
+source on a GPU-less box; that library is test infrastructure.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.normpath(os.path.join(_HERE, "..", "libwap_b200.so"))
+
+NS_LOW, NS_MODERATE, NS_HIGH, NS_VERY_HIGH = 0, 1, 2, 3
+ERR_NONE = 0
+ERRORS = {0: "None", 1: "NullPointer", 2: "Internal", 3: "BadSampleRate", 4: "BadNumberChannels",
+          5: "BadStreamParameter", 6: "BadDataLength", 7: "UnsupportedConfig"}
+
+
+class WapStreamConfig(C.Structure):
+    _fields_ = [("sample_rate_hz", C.c_int), ("num_channels", C.c_int32)]
+
+
+class WapConfig(C.Structure):
+    _fields_ = [
+        ("pipeline_maximum_internal_processing_rate", C.c_int),
+        ("pipeline_multi_channel_render", C.c_bool),
+        ("pipeline_multi_channel_capture", C.c_bool),
+        ("pipeline_capture_downmix_method", C.c_int32),
+        ("pre_amplifier_enabled", C.c_bool),
+        ("pre_amplifier_fixed_gain_factor", C.c_float),
+        ("capture_level_adjustment_enabled", C.c_bool),
+        ("capture_level_adjustment_pre_gain_factor", C.c_float),
+        ("capture_level_adjustment_post_gain_factor", C.c_float),
+        ("analog_mic_gain_emulation_enabled", C.c_bool),
+        ("analog_mic_gain_emulation_initial_level", C.c_int),
+        ("high_pass_filter_enabled", C.c_bool),
+        ("high_pass_filter_apply_in_full_band", C.c_bool),
+        ("echo_canceller_enabled", C.c_bool),
+        ("echo_canceller_enforce_high_pass_filtering", C.c_bool),
+        ("noise_suppression_enabled", C.c_bool),
+        ("noise_suppression_level", C.c_int32),
+        ("noise_suppression_analyze_linear_aec_output_when_available", C.c_bool),
+        ("gain_controller2_enabled", C.c_bool),
+        ("gain_controller2_fixed_digital_gain_db", C.c_float),
+        ("gain_controller2_adaptive_digital_enabled", C.c_bool),
+        ("gain_controller2_adaptive_digital_headroom_db", C.c_float),
+        ("gain_controller2_adaptive_digital_max_gain_db", C.c_float),
+        ("gain_controller2_adaptive_digital_initial_gain_db", C.c_float),
+        ("gain_controller2_adaptive_digital_max_gain_change_db_per_second", C.c_float),
+        ("gain_controller2_adaptive_digital_max_output_noise_level_dbfs", C.c_float),
+        ("gain_controller2_input_volume_controller_enabled", C.c_bool),
+    ]
+
+
+class WapStats(C.Structure):
+    _fields_ = [
+        ("has_echo_return_loss", C.c_bool), ("echo_return_loss", C.c_double),
+        ("has_echo_return_loss_enhancement", C.c_bool), ("echo_return_loss_enhancement", C.c_double),
+        ("has_divergent_filter_fraction", C.c_bool), ("divergent_filter_fraction", C.c_double),
+        ("has_delay_median_ms", C.c_bool), ("delay_median_ms", C.c_int32),
+        ("has_delay_standard_deviation_ms", C.c_bool), ("delay_standard_deviation_ms", C.c_int32),
+        ("has_residual_echo_likelihood", C.c_bool), ("residual_echo_likelihood", C.c_double),
+        ("has_residual_echo_likelihood_recent_max", C.c_bool), ("residual_echo_likelihood_recent_max", C.c_double),
+        ("has_delay_ms", C.c_bool), ("delay_ms", C.c_int32),
+    ]
+
+
+# Every symbol include/wap_audio_processing.h declares.
+EXPORTS = [
+    "wap_create", "wap_create_with_config", "wap_destroy", "wap_config_default", "wap_get_config",
+    "wap_apply_config", "wap_initialize", "wap_set_capture_output_used", "wap_set_capture_pre_gain",
+    "wap_set_capture_post_gain", "wap_set_capture_fixed_post_gain", "wap_set_playout_volume",
+    "wap_set_playout_audio_device", "wap_set_stream_analog_level", "wap_recommended_stream_analog_level",
+    "wap_set_stream_delay_ms", "wap_stream_delay_ms", "wap_process_stream_i16", "wap_process_stream_f32",
+    "wap_process_reverse_stream_i16", "wap_process_reverse_stream_f32", "wap_get_statistics",
+    "wap_engine_create", "wap_engine_destroy", "wap_engine_create_streams", "wap_engine_state_bytes_per_stream",
+    "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
+    "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
+]
+
+_libs = {}
+
+
+def load(path=None):
+    path = path or os.environ.get("WAP_B200_LIB") or DEFAULT_LIB
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build it with webrtc-audio-processing_b200/build.py "
+                           "(CUDA extension required; there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    vp, i32, sc, cfg = C.c_void_p, C.c_int32, WapStreamConfig, WapConfig
+    L.wap_config_default.restype = cfg
+    L.wap_create.restype = vp
+    L.wap_create_with_config.restype = vp
+    L.wap_create_with_config.argtypes = [cfg]
+    L.wap_destroy.argtypes = [vp]
+    L.wap_get_config.argtypes = [vp, C.POINTER(cfg)]
+    L.wap_apply_config.argtypes = [vp, cfg]
+    L.wap_initialize.argtypes = [vp, sc, sc, sc, sc]
+    L.wap_set_stream_delay_ms.argtypes = [vp, C.c_int]
+    L.wap_stream_delay_ms.argtypes = [vp]
+    L.wap_set_capture_output_used.argtypes = [vp, C.c_bool]
+    L.wap_process_stream_i16.argtypes = [vp, vp, i32, sc, sc, vp, i32]
+    L.wap_process_reverse_stream_i16.argtypes = [vp, vp, i32, sc, sc, vp, i32]
+    L.wap_process_stream_f32.argtypes = [vp, vp, sc, sc, vp]
+    L.wap_process_reverse_stream_f32.argtypes = [vp, vp, sc, sc, vp]
+    L.wap_get_statistics.argtypes = [vp, C.POINTER(WapStats)]
+    L.wap_engine_create.restype = vp
+    L.wap_engine_create.argtypes = [C.c_int, i32, cfg, sc]
+    L.wap_engine_destroy.argtypes = [vp]
+    L.wap_engine_create_streams.argtypes = [vp, i32, vp]
+    L.wap_engine_state_bytes_per_stream.restype = C.c_size_t
+    L.wap_engine_state_bytes_per_stream.argtypes = [vp]
+    L.wap_engine_algorithmic_bytes_per_frame.restype = C.c_double
+    L.wap_engine_algorithmic_bytes_per_frame.argtypes = [vp]
+    L.wap_process_streams.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    L.wap_process_streams_device.argtypes = [vp, vp, i32, vp, vp, vp, i32]
+    L.wap_engine_synchronize.argtypes = [vp]
+    L.wap_engine_cuda_stream.restype = vp
+    L.wap_engine_cuda_stream.argtypes = [vp]
+    L.wap_engine_launch_count.restype = C.c_int64
+    L.wap_engine_launch_count.argtypes = [vp]
+    L.wap_version.restype = C.c_char_p
+    _libs[path] = L
+    return L
+
+
+def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False):
+    c = lib.wap_config_default()
+    c.echo_canceller_enabled = bool(aec)
+    c.noise_suppression_enabled = bool(ns)
+    c.noise_suppression_level = int(ns_level)
+    c.pipeline_maximum_internal_processing_rate = int(max_rate)
+    c.high_pass_filter_enabled = bool(hpf)
+    return c
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """Batched engine: `n` call legs of one config class on one GPU."""
+
+    def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, **cfg):
+        self.lib = lib or load()
+        self.rate, self.channels, self.n = rate, channels, n_streams
+        self.frame = rate // 100 * channels
+        self.config = make_config(self.lib, **cfg)
+        self.h = self.lib.wap_engine_create(device, capacity or n_streams, self.config,
+                                            WapStreamConfig(rate, channels))
+        if not self.h:
+            raise RuntimeError("wap_engine_create failed (no CUDA device or unsupported config)")
+        self.handles = (C.c_void_p * n_streams)()
+        err = self.lib.wap_engine_create_streams(self.h, n_streams, self.handles)
+        if err:
+            raise RuntimeError("wap_engine_create_streams: " + ERRORS.get(err, str(err)))
+
+    def set_stream_delay_ms(self, ms):
+        for h in self.handles:
+            self.lib.wap_set_stream_delay_ms(h, ms)
+
+    def process(self, render, capture):
+        """render/capture: [n, frame] int16 or float32 (render may be None). Returns out [n, frame]."""
+        capture = np.ascontiguousarray(capture)
+        fmt = 0 if capture.dtype == np.int16 else 1
+        if render is not None:
+            render = np.ascontiguousarray(render, dtype=capture.dtype)
+        out = np.empty_like(capture)
+        err = self.lib.wap_process_streams(self.handles, self.n, _ptr(render), _ptr(capture), _ptr(out), fmt, None)
+        if err:
+            raise RuntimeError("wap_process_streams: " + ERRORS.get(err, str(err)))
+        return out
+
+    def stats(self, i=0):
+        s = WapStats()
+        self.lib.wap_get_statistics(self.handles[i], C.byref(s))
+        return s
+
+    def close(self):
+        if self.h:
+            for h in self.handles:
+                self.lib.wap_destroy(h)
+            self.lib.wap_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
