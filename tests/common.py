@@ -1,0 +1,69 @@
+"""Shared helpers of the parity tests."""
+import os
+
+import numpy as np
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def run_engine(lib, rate, render, capture, n_streams=1, delay_ms=None, **cfg):
+    """Drive n identical legs through wap_process_streams; returns [frames, frame_len] of leg 0
+    and checks that all legs agree bit for bit."""
+    import wap_b200
+    fl = rate // 100
+    nf = capture.size // fl
+    eng = wap_b200.Engine(n_streams, rate, lib=lib, **cfg)
+    out = np.zeros((nf, fl), np.int16)
+    for f in range(nf):
+        c = np.tile(capture[f * fl:(f + 1) * fl], (n_streams, 1))
+        r = None if render is None else np.tile(render[f * fl:(f + 1) * fl], (n_streams, 1))
+        if delay_ms is not None:
+            eng.set_stream_delay_ms(delay_ms)
+        o = eng.process(r, c)
+        assert all(np.array_equal(o[0], o[i]) for i in range(1, n_streams))
+        out[f] = o[0]
+    eng.close()
+    return out
+
+
+# ---- synthetic generator of SURVEY.md section 8(d) (xorshift64* as webrtc::Random)
+class WebRtcRandom:
+    """webrtc::Random (rtc_base/random.h:71-77, random.cc:52-56) restated."""
+
+    def __init__(self, seed):
+        self.state = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next_output(self):
+        s = self.state
+        s ^= s >> 12
+        s ^= (s << 25) & 0xFFFFFFFFFFFFFFFF
+        s ^= s >> 27
+        self.state = s
+        return (s * 2685821657736338717) & 0xFFFFFFFFFFFFFFFF
+
+    def rand_float(self):
+        return float(self.next_output() - 1) / float(0xFFFFFFFFFFFFFFFE + 1)
+
+
+def synthetic_leg(i, n_frames, rate=16000):
+    """Render/capture int16 for stream i: gated white-noise render, 3-tap echo path with
+    per-stream delay, noise floor + double-talk bursts."""
+    n = n_frames * rate // 100
+    rng_r = np.random.default_rng(1000 + 2 * i)
+    rng_n = np.random.default_rng(1001 + 2 * i)
+    t = np.arange(n) / rate
+    x = rng_r.uniform(-8000, 8000, n)
+    x *= ((t % 1.0) < 0.9)
+    D = 64 * (1 + (i % 48)) + (7 * i) % 64
+    y = np.zeros(n)
+    for g, d in ((0.5, D), (0.25, D + 37), (0.1, D + 160)):
+        y[d:] += g * x[:n - d]
+    y += rng_n.uniform(-50, 50, n)
+    y += rng_n.uniform(-3000, 3000, n) * ((t % 2.0) > 1.7)
+    return (np.clip(np.round(x), -32768, 32767).astype(np.int16),
+            np.clip(np.round(y), -32768, 32767).astype(np.int16))
