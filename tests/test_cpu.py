@@ -1,0 +1,136 @@
+"""-m "not gpu": (1) the oracle (compiled reference, oracle/_ref) is pinned against the
+reference's own known-answer vectors and against its recorded outputs; (2) the C ABI
+library loads and exports every symbol include/*.h declares; (3) the kernel SOURCE,
+compiled for the CPU warp emulator (tests/emu, test infrastructure), matches the
+oracle -- this is how kernels are debugged on the GPU-less build box; the parity
+tests proper are the -m gpu ones."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, golden, run_engine
+
+TOL_FS = 1e-4
+
+
+# ------------------------------------------------------------------ oracle pinning
+def test_oracle_isa_is_avx2(oracle):
+    assert oracle.lib().ref_isa_level() == 2
+
+
+def test_oracle_hpf_known_answer(oracle):
+    """Reference KAT: tests/unit/high_pass_filter_unittest.cc:198-330 (kReferenceInput /
+    kReference, tolerance 1/32768, last frame compared)."""
+    kat = golden("hpf_kat.npz")
+    L = oracle.lib()
+    for name in ("MonoInitial", "MonoConverged"):
+        x, want = kat[name + "_in"], kat[name + "_ref"]
+        h = L.ref_hpf_create(16000, 1)
+        last = None
+        for f in range(x.size // 160):
+            fr = x[f * 160:(f + 1) * 160].astype(np.float32).copy()
+            L.ref_hpf_process(h, fr.ctypes.data_as(C.c_void_p), 1, 160)
+            last = fr
+        L.ref_hpf_destroy(h)
+        assert np.abs(last[:want.size] - want).max() <= 1.0 / 32768
+
+
+@pytest.mark.parametrize("tag,kw,rate,use_far", [
+    ("ns_mod_16k", dict(aec=False, ns=True, ns_level=1), 16000, False),
+    ("aec_ns_16k", dict(aec=True, ns=True, ns_level=1), 16000, True),
+])
+def test_oracle_matches_recorded_run(oracle, tag, kw, rate, use_far):
+    """Detects a silently different oracle build (flags, ISA path)."""
+    sp = golden("speech_%dk.npz" % (rate // 1000))
+    n = 300 * rate // 100
+    out, _, err = oracle.RefApm(max_rate=48000, **kw).run_i16(rate, sp["far"][:n] if use_far else None, sp["near"][:n])
+    assert err == 0
+    assert np.array_equal(out, golden("ref_outputs.npz")[tag][:n])
+
+
+# ------------------------------------------------------------------ C ABI surface
+def _declared_symbols():
+    syms = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        src = open(os.path.join(ROOT, "include", fn)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(wap_[a-z0-9_]+)\s*\(", src))
+    return syms
+
+
+def test_abi_library_exports_every_declared_symbol():
+    import wap_b200
+    L = wap_b200.load()  # the CUDA build; loads without a GPU (cudart is linked statically)
+    declared = _declared_symbols()
+    assert declared and declared == set(wap_b200.EXPORTS), declared ^ set(wap_b200.EXPORTS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_product_does_not_link_oracle_or_emulator():
+    import subprocess
+    import wap_b200
+    out = subprocess.run(["ldd", wap_b200.DEFAULT_LIB], capture_output=True, text=True).stdout
+    assert "wap_ref" not in out and "wap_emu" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "webrtc-audio-processing_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".inc", ".py", ".cc")):
+                txt = open(os.path.join(root, f)).read()
+                assert "libwap_ref" not in txt and "import ref" not in txt, f
+
+
+# ------------------------------------------------------------------ kernel source on the emulator
+def test_emu_fft128_bit_exact(emu_lib, oracle):
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((33, 128)) * 4000).astype(np.float32)
+    for inv in (0, 1):
+        y = x.copy()
+        assert emu_lib.wapdbg_fft128(y.ctypes.data_as(C.c_void_p), len(y), inv) == 0
+        r = np.stack([oracle.fft128(v, bool(inv)) for v in x])
+        assert np.array_equal(y.view(np.uint32), r.view(np.uint32))
+
+
+def test_emu_fft256_bit_exact(emu_lib, oracle):
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((17, 256)) * 4000).astype(np.float32)
+    for inv in (0, 1):
+        y = x.copy()
+        assert emu_lib.wapdbg_fft256(y.ctypes.data_as(C.c_void_p), len(y), inv) == 0
+        r = np.stack([oracle.rdft256(v, -1 if inv else 1) for v in x])
+        assert np.array_equal(y.view(np.uint32), r.view(np.uint32))
+
+
+def test_emu_hpf_known_answer(emu_lib):
+    """The device HPF against the reference's literal KAT (high_pass_filter_unittest.cc)."""
+    import wap_b200
+    kat = golden("hpf_kat.npz")
+    for name in ("MonoInitial", "MonoConverged"):
+        x, want = kat[name + "_in"], kat[name + "_ref"]
+        eng = wap_b200.Engine(1, 16000, lib=emu_lib, aec=False, ns=False, hpf=True)
+        last = None
+        for f in range(x.size // 160):
+            # KAT samples are fed in the float [-1,1] convention (x32768 is exact in fp32)
+            last = eng.process(None, (x[f * 160:(f + 1) * 160] / 8.0).astype(np.float32)[None, :])[0] * 8.0
+        eng.close()
+        assert np.abs(last[:want.size] - want).max() <= 1.0 / 32768
+
+
+def test_emu_ns_parity_16k(emu_lib, oracle):
+    near = golden("speech_16k.npz")["near"][:250 * 160]
+    ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=1).run_i16(16000, None, near)
+    assert err == 0
+    out = run_engine(emu_lib, 16000, None, near, n_streams=2, aec=False, ns=True, ns_level=1)
+    d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32))
+    assert d.max() <= TOL_FS * 32768, d.max()
+
+
+def test_emu_ns_parity_48k_three_band(emu_lib, oracle):
+    near = golden("speech_48k.npz")["near"][:120 * 480]
+    ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=2, max_rate=48000).run_i16(48000, None, near)
+    assert err == 0
+    out = run_engine(emu_lib, 48000, None, near, n_streams=1, aec=False, ns=True, ns_level=2)
+    d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32))
+    assert d.max() <= TOL_FS * 32768, d.max()
