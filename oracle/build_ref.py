@@ -52,13 +52,18 @@ def reference_sources():
     return sorted(srcs)
 
 
+DUMP = False  # second variant: -DWEBRTC_APM_DEBUG_DUMP=1 (stage taps via ApmDataDumper)
+
+
 def compile_one(src):
     tag = hashlib.sha1(src.encode()).hexdigest()[:10]
-    obj = os.path.join(OBJ, os.path.basename(src).rsplit(".", 1)[0] + "_" + tag + ".o")
+    obj = os.path.join(OBJ + ("_dump" if DUMP else ""), os.path.basename(src).rsplit(".", 1)[0] + "_" + tag + ".o")
     if os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
         return obj, None
     cxx = src.endswith(".cc")
     cmd = (["g++", "-std=c++23"] if cxx else ["gcc", "-std=c11"]) + COMMON
+    if DUMP:
+        cmd = [c.replace("-DWEBRTC_APM_DEBUG_DUMP=0", "-DWEBRTC_APM_DEBUG_DUMP=1") for c in cmd]
     if "avx2" in os.path.basename(src):
         cmd += ["-mavx2", "-mfma"]
     cmd += ["-c", src, "-o", obj]
@@ -66,14 +71,19 @@ def compile_one(src):
     return obj, (r.stderr if r.returncode else None)
 
 
-def build(verbose=True):
+def build(verbose=True, dump=False):
+    """dump=True builds oracle/_ref/libwap_ref_dump.so: the same sources with the
+    reference's own ApmDataDumper taps compiled in (used to localise divergences)."""
+    global DUMP, LIB
+    DUMP = dump
+    LIB = os.path.join(OUT, "libwap_ref_dump.so" if dump else "libwap_ref.so")
     if not os.path.isdir(REF):
         if os.path.exists(LIB):
             if verbose:
                 print("oracle/_ref: reference sources absent, using prebuilt", LIB)
             return LIB
         raise RuntimeError("no /root/reference and no prebuilt oracle/_ref/libwap_ref.so")
-    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(OBJ + ("_dump" if dump else ""), exist_ok=True)
     srcs = reference_sources() + [os.path.join(HERE, "cpu_info_stub.cc"),
                                   os.path.join(HERE, "ref_driver.cc")]
     objs, errs = [], []
@@ -94,4 +104,4 @@ def build(verbose=True):
 
 
 if __name__ == "__main__":
-    build()
+    build(dump="--dump" in sys.argv)

@@ -26,6 +26,7 @@
 #include "common_audio/third_party/ooura/fft_size_256/fft4g.h"
 #include "modules/audio_processing/aec3/aec3_common.h"
 #include "modules/audio_processing/high_pass_filter.h"
+#include "modules/audio_processing/logging/apm_data_dumper.h"
 #include "modules/audio_processing/ns/noise_suppressor.h"
 #include "modules/audio_processing/ns/ns_config.h"
 #include "modules/audio_processing/three_band_filter_bank.h"
@@ -249,6 +250,14 @@ void ref_3band_synthesis(void* p, const float* in, float* out) {
       webrtc::ArrayView<float>(m + 320, 160)};
   webrtc::ArrayView<float, 480> ov(out, 480);
   static_cast<webrtc::ThreeBandFilterBank*>(p)->Synthesis(iv, ov);
+}
+
+// Stage taps: with the -DWEBRTC_APM_DEBUG_DUMP=1 variant (libwap_ref_dump.so) every
+// ApmDataDumper::DumpRaw call of the reference writes <dir>/<name>_<inst>-<reinit>.dat.
+int ref_dump_activate(const char* dir) {
+  webrtc::ApmDataDumper::SetOutputDirectory(dir);
+  webrtc::ApmDataDumper::SetActivated(true);
+  return webrtc::ApmDataDumper::IsAvailable() ? 1 : 0;
 }
 
 int ref_isa_level() {
