@@ -86,6 +86,8 @@ def build(verbose=True, dump=False):
     os.makedirs(OBJ + ("_dump" if dump else ""), exist_ok=True)
     srcs = reference_sources() + [os.path.join(HERE, "cpu_info_stub.cc"),
                                   os.path.join(HERE, "ref_driver.cc")]
+    if dump:  # ApmDataDumper::DumpWav needs the wav writer, which meson only builds for tests
+        srcs += [os.path.join(REF, "webrtc", "common_audio", f) for f in ("wav_file.cc", "wav_header.cc")]
     objs, errs = [], []
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         for obj, err in ex.map(compile_one, srcs):

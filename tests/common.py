@@ -31,6 +31,34 @@ def run_engine(lib, rate, render, capture, n_streams=1, delay_ms=None, **cfg):
     return out
 
 
+def run_legs(lib, rate, legs, stats_every=0, delay_ms=0, **cfg):
+    """Drive len(legs) different call legs (list of (render, capture) int16 arrays) through ONE
+    batched engine, one wap_process_streams call per 10 ms tick.  Returns (out [n, samples],
+    stats [n, k, 3] = (erl, erle, delay_ms) sampled every `stats_every` frames)."""
+    import wap_b200
+    n = len(legs)
+    fl = rate // 100
+    nf = min(l[1].size for l in legs) // fl
+    eng = wap_b200.Engine(n, rate, lib=lib, **cfg)
+    out = np.zeros((n, nf * fl), np.int16)
+    stats = []
+    R = np.stack([l[0][:nf * fl] for l in legs]).reshape(n, nf, fl)
+    Cc = np.stack([l[1][:nf * fl] for l in legs]).reshape(n, nf, fl)
+    for f in range(nf):
+        if delay_ms is not None:
+            eng.set_stream_delay_ms(delay_ms)
+        out[:, f * fl:(f + 1) * fl] = eng.process(R[:, f], Cc[:, f])
+        if stats_every and (f + 1) % stats_every == 0:
+            row = []
+            for i in range(n):
+                st = eng.stats(i)
+                row.append((st.echo_return_loss, st.echo_return_loss_enhancement, st.delay_ms))
+            stats.append(row)
+    eng.close()
+    st = np.array(stats, dtype=np.float64).transpose(1, 0, 2) if stats else np.zeros((n, 0, 3))
+    return out, st
+
+
 # ---- synthetic generator of SURVEY.md section 8(d) (xorshift64* as webrtc::Random)
 class WebRtcRandom:
     """webrtc::Random (rtc_base/random.h:71-77, random.cc:52-56) restated."""

@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "webrtc-audio-processing_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-LIB = os.path.join(OUT, "libwap_emu.so")
+# WAP_EMU_O0=1: unoptimised variant (no code cloning), for WAP_EMU_CHECK_DIVERGENCE runs.
+O0 = bool(os.environ.get("WAP_EMU_O0"))
+LIB = os.path.join(OUT, "libwap_emu_O0.so" if O0 else "libwap_emu.so")
 
 
 def build(verbose=True):
@@ -23,13 +25,13 @@ def build(verbose=True):
         glob.glob(os.path.join(ROOT, "include", "*.h"))
     if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+    cmd = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
            "-DWAP_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", HERE, "-I", CSRC,
            "-I", os.path.join(ROOT, "include"), "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
            "-Wno-unused-variable"]
     for s in srcs:
         cmd += ["-x", "c++", s]
-    cmd += ["-x", "c++", os.path.join(HERE, "cuda_emu.cc"), "-o", LIB, "-lpthread"]
+    cmd += ["-x", "c++", os.path.join(HERE, "cuda_emu.cc"), "-o", LIB, "-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

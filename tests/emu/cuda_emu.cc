@@ -1,4 +1,8 @@
 // Test-only CUDA execution emulator runtime (see cuda_emu.h).  x86-64 only.
+#include <dlfcn.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include "cuda_emu.h"
 
 namespace emu {
@@ -88,15 +92,58 @@ void yield_next() {
   emu_switch(&me->sp, next->sp);
 }
 
+namespace {
+constexpr int kTraceDepth = 6;
+void report_divergence(void* const* a, int na, void* const* b, int nb) {
+  std::fprintf(stderr, "emu: lanes of one warp met at a barrier from different call sites\n first lane:\n");
+  backtrace_symbols_fd(a, na, 2);
+  std::fprintf(stderr, " this lane (%d):\n", (int)(g_cur->tid.x & 31));
+  backtrace_symbols_fd(b, nb, 2);
+  std::abort();
+}
+}  // namespace
+
 void warp_barrier() {
   Warp& w = *g_cur->warp;
   unsigned g = w.gen;
+  static const bool check = getenv("WAP_EMU_CHECK_DIVERGENCE") != nullptr;
+  if (check) {
+    void* pcs[kTraceDepth];
+    int n = backtrace(pcs, kTraceDepth);
+    if (w.arrived == 0) {
+      w.first_n = n;
+      for (int i = 0; i < n; ++i) w.first_trace[i] = pcs[i];
+    } else if (n != w.first_n || std::memcmp(pcs, w.first_trace, n * sizeof(void*)) != 0) {
+      report_divergence(w.first_trace, w.first_n, pcs, n);
+    }
+  }
   if (++w.arrived == 32) {
     w.arrived = 0;
     w.gen++;
     return;
   }
-  while (w.gen == g) yield_next();
+  g_cur->wait_pc = __builtin_return_address(0);
+  unsigned long spins = 0;
+  while (w.gen == g) {
+    yield_next();
+    if (++spins == 2000000ul) {
+      // Some lanes of this warp will never arrive (exited, or a barrier inside
+      // lane-divergent control flow): report where every lane is waiting.
+      std::fprintf(stderr, "emu: warp barrier deadlock (arrived %d/32). lane: waiting-at / done\n", w.arrived);
+      Block* b = g_block;
+      for (size_t t = 0; t < b->threads.size(); ++t)
+        if (b->threads[t].warp == &w)
+        {
+          Dl_info di{};
+          void* pc = b->threads[t].wait_pc;
+          if (pc) dladdr(pc, &di);
+          std::fprintf(stderr, "  lane %2zu: +0x%lx %s\n", t & 31,
+                       pc ? (unsigned long)((char*)pc - (char*)di.dli_fbase) : 0ul, b->threads[t].done ? "done" : "");
+        }
+      std::abort();
+    }
+  }
+  g_cur->wait_pc = nullptr;
 }
 
 void block_barrier() {
@@ -110,7 +157,35 @@ void block_barrier() {
   while (b->barrier_gen == g) yield_next();
 }
 
+namespace {
+void emu_segv(int sig) {
+  void* frames[48];
+  int n = backtrace(frames, 48);
+  const char msg[] = "emu: fatal signal in emulated kernel, backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+void install_segv_handler() {
+  static bool done = false;
+  if (done || !getenv("WAP_EMU_BACKTRACE")) return;
+  done = true;
+  static unsigned char alt[1 << 16];
+  stack_t ss{};
+  ss.ss_sp = alt;
+  ss.ss_size = sizeof(alt);
+  sigaltstack(&ss, nullptr);
+  struct sigaction sa{};
+  sa.sa_handler = emu_segv;
+  sa.sa_flags = SA_ONSTACK;
+  sigaction(SIGSEGV, &sa, nullptr);
+  sigaction(SIGBUS, &sa, nullptr);
+  sigaction(SIGFPE, &sa, nullptr);
+}
+}  // namespace
+
 void run_block(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem_bytes) {
+  install_segv_handler();
   unsigned old_csr = _mm_getcsr();
   _mm_setcsr(old_csr | 0x8040);  // FTZ | DAZ, as the device build's -ftz=true
   size_t nthreads = (size_t)block.x * block.y * block.z;

@@ -64,6 +64,8 @@ struct Warp {
   int arrived = 0;
   unsigned gen = 0;
   uint64_t xchg[32];
+  void* first_trace[8] = {};  // call stack of the first lane at the current barrier (divergence check)
+  int first_n = 0;
 };
 
 struct Thread {
@@ -71,6 +73,7 @@ struct Thread {
   uint3 tid{0, 0, 0};
   Warp* warp = nullptr;
   bool done = false;
+  void* wait_pc = nullptr;  // call site of the barrier this lane is parked at (deadlock reports)
 };
 
 struct Block {

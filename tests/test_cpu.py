@@ -134,3 +134,55 @@ def test_emu_ns_parity_48k_three_band(emu_lib, oracle):
     out = run_engine(emu_lib, 48000, None, near, n_streams=1, aec=False, ns=True, ns_level=2)
     d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32))
     assert d.max() <= TOL_FS * 32768, d.max()
+
+
+# ------------------------------------------------------------------ AEC3 on the emulator
+def _check_aec(out, stats, ref_out, ref_stats):
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32))
+    assert d.max() <= TOL_FS * 32768, (int(d.max()), int(np.argmax(d > TOL_FS * 32768)) // 160)
+    # ERLE within 0.1 dB (north_star); ERL and the reported delay as diagnostics.
+    assert np.abs(stats[:, 1] - ref_stats[:, 3]).max() <= 0.1
+    assert np.abs(stats[:, 0] - ref_stats[:, 1]).max() <= 0.1
+    assert np.array_equal(stats[:, 2], ref_stats[:, 5])
+
+
+def test_emu_aec3_ns_parity_speech(emu_lib, oracle):
+    """cfg 1 shape: AEC3 + NS(moderate), 16 kHz mono, the reference's own far/near speech fixture."""
+    from common import run_legs
+    sp = golden("speech_16k.npz")
+    n = 300 * 160
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(
+        16000, sp["far"][:n], sp["near"][:n], stats_every=50)
+    assert err == 0
+    assert np.array_equal(ref_out, golden("ref_outputs.npz")["aec_ns_16k"][:n])
+    out, stats = run_legs(emu_lib, 16000, [(sp["far"][:n], sp["near"][:n])], stats_every=50,
+                          aec=True, ns=True, ns_level=1)
+    _check_aec(out[0], stats[0], ref_out, ref_stats)
+
+
+def test_emu_aec3_parity_synthetic_legs(emu_lib, oracle):
+    """AEC3 only, three legs with different echo-path delays in ONE batched engine (the
+    synthetic generator of SURVEY.md section 8d), 4 s: covers delay estimation, the
+    alignment change, filter convergence and the exit from the initial state."""
+    from common import run_legs, synthetic_leg
+    ids = (1, 20, 47)
+    legs = [synthetic_leg(i, 400) for i in ids]
+    out, stats = run_legs(emu_lib, 16000, legs, stats_every=100, aec=True, ns=False)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=False).run_i16(16000, far, near, stats_every=100)
+        assert err == 0
+        _check_aec(out[k], stats[k], ref_out, ref_stats)
+    assert stats[:, -1, 2].min() > 0  # every leg found a non-zero render delay
+
+
+def test_emu_render_before_first_capture_is_dropped_with_ns(emu_lib, oracle):
+    """AudioProcessingImpl re-initialises on the first ProcessStream call when NS is enabled
+    (audio_processing_impl.cc:558-559,894-925,1874-1881), so the first render frame never
+    reaches AEC3; without NS it does.  The first two output frames expose the difference."""
+    from common import run_legs, synthetic_leg
+    far, near = synthetic_leg(0, 6)
+    for ns in (False, True):
+        ref_out, _, err = oracle.RefApm(aec=True, ns=ns, ns_level=1).run_i16(16000, far, near)
+        assert err == 0
+        out, _ = run_legs(emu_lib, 16000, [(far, near)], aec=True, ns=ns, ns_level=1)
+        assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import golden, run_engine
+from common import golden, run_engine, run_legs, synthetic_leg
 
 pytestmark = pytest.mark.gpu
 TOL_FS = 1e-4  # of full scale => 3.2768 int16 LSB
@@ -44,3 +44,66 @@ def test_ns_parity_speech(gpu_lib, oracle, rate, level, tag):
     out = run_engine(gpu_lib, rate, None, near[:nf * fl], n_streams=3, aec=False, ns=True, ns_level=level)
     d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32))
     assert d.max() <= TOL_FS * 32768, (d.max(), int(np.argmax(d > TOL_FS * 32768)) // fl)
+
+
+def _check_aec(out, stats, ref_out, ref_stats, tag):
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32))
+    assert d.max() <= TOL_FS * 32768, (tag, int(d.max()), int(np.argmax(d > TOL_FS * 32768)) // 160)
+    # ERLE within 0.1 dB (BASELINE.json north_star); ERL / delay as diagnostics
+    assert np.abs(stats[:, 1] - ref_stats[:, 3]).max() <= 0.1, tag
+    assert np.abs(stats[:, 0] - ref_stats[:, 1]).max() <= 0.1, tag
+    assert np.array_equal(stats[:, 2], ref_stats[:, 5]), tag
+
+
+def test_aec3_ns_parity_speech(gpu_lib, oracle):
+    """BASELINE config 1: 16 kHz mono AEC3 + NS(moderate) on the reference's speech fixture (7 s)."""
+    sp = golden("speech_16k.npz")
+    nf = sp["near"].size // 160
+    far, near = sp["far"][:nf * 160], sp["near"][:nf * 160]
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near, stats_every=50)
+    assert err == 0
+    n_gold = min(ref_out.size, golden("ref_outputs.npz")["aec_ns_16k"].size)
+    assert np.array_equal(ref_out[:n_gold], golden("ref_outputs.npz")["aec_ns_16k"][:n_gold])
+    out, stats = run_legs(gpu_lib, 16000, [(far, near)] * 2, stats_every=50, aec=True, ns=True, ns_level=1)
+    assert np.array_equal(out[0], out[1])
+    _check_aec(out[0], stats[0], ref_out, ref_stats, "speech")
+
+
+@pytest.mark.parametrize("ns", [False, True])
+def test_aec3_parity_synthetic_legs_10s(gpu_lib, oracle, ns):
+    """BASELINE config 2 shape at test size: 24 legs with echo-path delays spread over
+    4-196 ms in ONE batched engine, 10 s each (passes the 2.5 s initial state, the 500-block
+    ERLE start-up, the NS 200-frame start-up and one 500-frame NS histogram update)."""
+    ids = list(range(0, 48, 2))
+    legs = [synthetic_leg(i, 1000) for i in ids]
+    out, stats = run_legs(gpu_lib, 16000, legs, stats_every=100, aec=True, ns=ns, ns_level=1)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=ns, ns_level=1).run_i16(16000, far, near, stats_every=100)
+        assert err == 0
+        _check_aec(out[k], stats[k], ref_out, ref_stats, "leg %d" % ids[k])
+    # the canceller did something: ERLE above 5 dB for most legs at the end
+    assert np.median(stats[:, -1, 1]) > 5.0
+
+
+def test_aec3_no_render_passes_capture_through(gpu_lib, oracle):
+    """Edge case (block_processor.cc:123-131): no render data => capture is only delayed by one block."""
+    far, near = synthetic_leg(3, 50)
+    ref = oracle.RefApm(aec=True, ns=False)
+    ref_out, _, err = ref.run_i16(16000, None, near)
+    assert err == 0
+    out = run_engine(gpu_lib, 16000, None, near, n_streams=2, delay_ms=0, aec=True, ns=False)
+    assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
+
+
+def test_aec3_saturated_capture_and_silence(gpu_lib, oracle):
+    """Edge cases: full-scale (saturating) capture, then digital silence on both sides."""
+    rng = np.random.default_rng(5)
+    n = 300 * 160
+    far = (rng.uniform(-1, 1, n) * 20000).astype(np.int16)
+    near = np.clip(np.roll(far.astype(np.int32), 200) * 2, -32768, 32767).astype(np.int16)  # clipped echo
+    far[200 * 160:] = 0
+    near[200 * 160:] = 0
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near, stats_every=50)
+    assert err == 0
+    out, stats = run_legs(gpu_lib, 16000, [(far, near)], stats_every=50, aec=True, ns=True, ns_level=1)
+    _check_aec(out[0], stats[0], ref_out, ref_stats, "saturated")

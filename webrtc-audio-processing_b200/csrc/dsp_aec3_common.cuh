@@ -1,0 +1,179 @@
+// AEC3 on one warp per call leg: constants of the default EchoCanceller3Config,
+// the per-warp shared-memory scratch and small helpers shared by the stages.
+//
+// Execution pattern (see wap_dev.cuh): vector phases run on all 32 lanes over
+// the 64-sample / 65-bin arrays; the scalar control logic of the reference's
+// classes (counters, optionals, state machines) runs on lane 0 against the copy
+// of Aec3Scalars staged in shared memory, separated from the vector phases by
+// __syncwarp().  All per-stream branches are warp-uniform.
+#pragma once
+
+#include "dsp_fft.cuh"
+#include "dsp_filters.cuh"
+#include "wap_dev.cuh"
+#include "wap_state.h"
+
+namespace wap {
+
+// Default EchoCanceller3Config (reference api/audio/echo_canceller3_config.h:21-275);
+// the engine accepts only this config class (wap_engine.cu validates).
+namespace ec3 {
+constexpr int kDefaultDelay = 5;               // delay.default_delay
+constexpr int kHeadroomSamples = 32;           // delay.delay_headroom_samples
+constexpr int kHysteresisLimitBlocks = 1;      // delay.hysteresis_limit_blocks
+constexpr int kThrInitial = 5, kThrConverged = 20;  // delay.delay_selection_thresholds
+constexpr float kMfSmoothing = 0.7f;           // delay_estimate_smoothing (both variants)
+constexpr float kMfThreshold = 0.2f;           // delay_candidate_detection_threshold
+constexpr float kMfExcitationLimit = 150.f;    // render_levels.poor_excitation_render_limit
+constexpr float kActiveRenderLimit = 100.f;    // render_levels.active_render_limit
+constexpr int kExcessRenderInterval = 250;     // buffering.excess_render_detection_interval_blocks
+constexpr int kMaxExcessRenderBlocks = 8;      // buffering.max_allowed_excess_render_blocks
+constexpr int kConfigChangeDuration = 250;     // filter.config_change_duration_blocks
+constexpr float kInitialStateSeconds = 2.5f;   // filter.initial_state_seconds
+constexpr int kCoarseResetHangover = 25;       // filter.coarse_reset_hangover_blocks
+// filter.refined / refined_initial: leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate
+#define WAP_EC3_REFINED {0.00005f, 0.05f, 0.001f, 2.f, 20075344.f}
+#define WAP_EC3_REFINED_INITIAL {0.005f, 0.5f, 0.001f, 2.f, 20075344.f}
+#define WAP_EC3_COARSE {0.7f, 20075344.f}
+#define WAP_EC3_COARSE_INITIAL {0.9f, 20075344.f}
+constexpr float kErleMin = 1.f, kErleMaxL = 4.f, kErleMaxH = 1.5f;  // erle
+constexpr float kDefaultGain = 1.f;            // ep_strength.default_gain
+constexpr float kDefaultLen = 0.83f;           // ep_strength.default_len (= nearend_len)
+constexpr float kNoiseFloorHold = 50;          // echo_model.noise_floor_hold
+constexpr float kMinNoiseFloorPower = 1638400.f;
+constexpr float kStationaryGateSlope = 10.f;
+constexpr float kNoiseGatePower = 27509.42f;
+constexpr float kNoiseGateSlope = 0.3f;
+constexpr float kLowRenderLimit = 4 * 64.f, kNormalRenderLimit = 64.f, kFloorPower = 2 * 64.f;
+constexpr float kAudibilityThreshold = 10.f;   // lf = mf = hf
+constexpr float kFloorFirstIncrease = 0.00001f;
+constexpr int kLastLfSmoothingBand = 5, kLastPermanentLfSmoothingBand = 0;
+constexpr int kLastLfBand = 5, kFirstHfBand = 8;
+constexpr int kLimitingGainBand = 16;          // high_frequency_suppression (bands_in_limiting_gain = 1)
+// dominant_nearend_detection
+constexpr float kDnEnrThreshold = .25f, kDnEnrExitThreshold = 10.f, kDnSnrThreshold = 30.f;
+constexpr int kDnHoldDuration = 50, kDnTriggerThreshold = 12;
+// suppressor tunings: {lf.enr_transparent, lf.enr_suppress, lf.emr_transparent, hf..., max_inc, max_dec_lf}
+struct Tuning { float lf_t, lf_s, lf_e, hf_t, hf_s, hf_e, max_inc, max_dec_lf; };
+#define WAP_EC3_NORMAL_TUNING {.3f, .4f, .3f, .07f, .1f, .3f, 2.0f, 0.25f}
+#define WAP_EC3_NEAREND_TUNING {1.09f, 1.1f, .3f, .1f, .3f, .3f, 2.0f, 0.25f}
+}  // namespace ec3
+
+constexpr int kNumBlocksPerSecond = 250;
+constexpr int kMaxRingDelay = kRingBlocks - 1 - kMaxPartitions;  // RenderDelayBufferImpl::MaxDelay(): 153
+
+// RenderDelayBuffer::BufferingEvent
+enum { kEventNone = 0, kEventRenderUnderrun = 1, kEventRenderOverrun = 2 };
+// EchoPathVariability::DelayAdjustment
+enum { kDelayAdjNone = 0, kDelayAdjBufferFlush = 1, kDelayAdjNewDetectedDelay = 2 };
+// DelayEstimate::Quality
+enum { kQualityCoarse = 0, kQualityRefined = 1 };
+
+struct EchoPathVariability {  // echo_path_variability.h:16-29
+  int gain_change, delay_change, clock_drift;
+};
+
+// Shared-memory scratch of one warp for the AEC3 stage.  The matched-filter
+// buffers and the echo-remover vectors are never live at the same time.
+struct AecMfScratch {
+  float xw[2080];          // linearised low-rate window: xw[j] = low_rate[(read + j) % size]
+  float h[kMfLen];         // matched filter being processed
+  float inst_err[kAccErrLen];  // MatchedFilter::instantaneous_accumulated_error_
+  float q[kAccErrLen];     // per-4-tap partial sums / prefix sums of the accumulated-error core
+  float err_sum[kNumMatchedFilters];
+  int updated[kNumMatchedFilters];
+  int peak[kNumMatchedFilters];
+};
+struct AecRemoverScratch {
+  float e_ref[kBlock], e_coa[kBlock], s_ref[kBlock], s_coa[kBlock], e[kBlock];
+  float Er_re[kBinsPad], Er_im[kBinsPad], Ec_re[kBinsPad], Ec_im[kBinsPad];
+  float E2_ref[kBinsPad], E2_coa[kBinsPad];
+  float X2_ref[kBinsPad], X2_coa[kBinsPad];
+  float G_re[kBinsPad], G_im[kBinsPad];      // S (filter output) then G (update gain)
+  float Y_re[kBinsPad], Y_im[kBinsPad], E_re[kBinsPad], E_im[kBinsPad];
+  float Y2[kBinsPad], E2[kBinsPad], S2_lin[kBinsPad], R2[kBinsPad], R2_unb[kBinsPad];
+  float N_re[kBinsPad], N_im[kBinsPad];      // comfort noise
+  float gain[kBinsPad];
+  float v0[kBinsPad], v1[kBinsPad], v2[kBinsPad], v3[kBinsPad], v4[kBinsPad];
+  float x_aligned[kBlock];                   // render block at -MinDirectPathFilterDelay
+};
+struct AecScratch {
+  Aec3Scalars s;           // staged copy of Aec3State::s
+  float fftA[128];         // lanes 0-15
+  float fftB[128];         // lanes 16-31
+  float x[kBlock];         // render block being inserted / GetBlock(0)
+  float y[kBlock];         // capture block (in / out)
+  float ds[kSubBlock];     // decimated sub-block
+  float red[32];           // reduction / broadcast exchange
+  int ired[32];
+  union {
+    AecMfScratch mf;
+    AecRemoverScratch rm;
+  };
+};
+
+WAP_DEV int ring_inc(int i, int size) { return i < size - 1 ? i + 1 : 0; }
+WAP_DEV int ring_dec(int i, int size) { return i > 0 ? i - 1 : size - 1; }
+WAP_DEV int ring_off(int i, int off, int size) { return (size + i + off) % size; }
+
+// FftData::CopyFromPackedArray / CopyToPackedArray (fft_data.h:77-98)
+WAP_DEV void packed_to_reim(const float* a, float* re, float* im) {
+  for (int k = lane_id(); k < kBins; k += 32) {
+    if (k == 0) { re[0] = a[0]; im[0] = 0.f; }
+    else if (k == 64) { re[64] = a[1]; im[64] = 0.f; }
+    else { re[k] = a[2 * k]; im[k] = a[2 * k + 1]; }
+  }
+}
+WAP_DEV void reim_to_packed(const float* re, const float* im, float* a) {
+  for (int k = lane_id(); k < kBins; k += 32) {
+    if (k == 0) a[0] = re[0];
+    else if (k == 64) a[1] = re[64];
+    else { a[2 * k] = re[k]; a[2 * k + 1] = im[k]; }
+  }
+}
+// FftData::SpectrumAVX2 (fft_data_avx2.cc:21-33): fused for bins 0..63, plain for bin 64.
+WAP_DEV float power_bin(float re, float im, int k) {
+  return (k < 64) ? fmaf(re, re, im * im) : re * re + im * im;
+}
+WAP_DEV void power_spectrum(const float* re, const float* im, float* out) {
+  for (int k = lane_id(); k < kBins; k += 32) out[k] = power_bin(re[k], im[k], k);
+}
+
+// Two 128-point transforms side by side: lanes 0-15 on fftA, lanes 16-31 on fftB.
+WAP_DEV void fft_pair(AecScratch& sc, bool inverse, bool second_on) {
+  const int lane = lane_id();
+  float* a = (lane < 16) ? sc.fftA : sc.fftB;
+  const bool on = (lane < 16) || second_on;
+  __syncwarp();
+  if (inverse) fft128_inverse(a, lane & 15, on);
+  else fft128_forward(a, lane & 15, on);
+}
+
+// FastApproxLog2f (aec3_common.cc:37-52)
+WAP_DEV float fast_approx_log2f(float in) {
+  float out = __uint2float_rn(__float_as_uint(in));
+  out *= 1.1920929e-7f;
+  out -= 126.942695f;
+  return out;
+}
+
+// std::inner_product(x, x + n, x, 0.f): every lane evaluates the same chain.
+WAP_DEV float energy_serial(const float* p, int n) { return serial_sum_sq(p, n); }
+
+// First index of the maximum of an int array (std::max_element), warp-wide.
+WAP_DEV int warp_argmax_first_int(const int* p, int n) {
+  const int lane = lane_id();
+  int best = -2147483647 - 1, bi = 0x7fffffff;
+  for (int i = lane; i < n; i += 32) {
+    const int v = p[i];
+    if (v > best) { best = v; bi = i; }
+  }
+  for (int m = 16; m; m >>= 1) {
+    const int ov = __shfl_xor_sync(WAP_FULL, best, m);
+    const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  return bi;
+}
+
+}  // namespace wap

@@ -1,0 +1,481 @@
+// AEC3 delay estimation for one call leg: capture decimator, the five matched
+// filters (NLMS cross-correlators on the decimated render ring), the lag
+// aggregators, clock-drift detector and RenderDelayController.
+//
+// Arithmetic follows the reference's AVX2 path, which is part of the parity
+// contract:
+//   MatchedFilterCore_AVX2 / _AccumulatedError_AVX2  aec3/matched_filter_avx2.cc:45-270
+//   MatchedFilter::Update                            aec3/matched_filter.cc:657-778
+//   MatchedFilterLagAggregator                       aec3/matched_filter_lag_aggregator.cc:73-189
+//   EchoPathDelayEstimator::EstimateDelay            aec3/echo_path_delay_estimator.cc:66-131
+//   RenderDelayControllerImpl::GetDelay              aec3/render_delay_controller.cc:113-168
+//
+// Lane mapping of one dot product: the AVX2 core keeps 16 h*x accumulators and
+// 16 x*x accumulators, each a chain of fused multiply-adds over every 16th tap.
+// Lanes 0-15 own the h*x chains, lanes 16-31 the x*x chains, so a warp
+// evaluates exactly the reference's 32 chains and then its fixed combine tree.
+#pragma once
+
+#include "dsp_aec3_common.cuh"
+#include "dsp_aec3_render.cuh"
+
+namespace wap {
+
+constexpr float kMfX2SumThreshold = 512.f * ec3::kMfExcitationLimit * ec3::kMfExcitationLimit;
+
+// Copies the part of the low-rate ring the five filters can see into shared
+// memory, linearised from the read index.
+WAP_DEV void mf_stage_window(const Aec3State& a, AecScratch& sc) {
+  const int read = sc.s.lr_read;
+  for (int j = lane_id(); j < 4 * kMfShift + kSubBlock + kMfLen; j += 32) {
+    int r = read + j;
+    if (r >= kLowRateSize) r -= kLowRateSize;
+    sc.mf.xw[j] = a.low_rate[r];
+  }
+  __syncwarp();
+}
+
+// hsum over the 8 "c" values of one accumulator group in the order of hsum_ab
+// (matched_filter_avx2.cc:35-43): ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7)),
+// c_j = chain_j + chain_{j+8}.  Works on both half-warps at once.
+WAP_DEV float mf_hsum16(float acc) {
+  acc += __shfl_xor_sync(WAP_FULL, acc, 8);
+  acc += __shfl_xor_sync(WAP_FULL, acc, 1);
+  acc += __shfl_xor_sync(WAP_FULL, acc, 2);
+  acc += __shfl_xor_sync(WAP_FULL, acc, 4);
+  return acc;
+}
+
+// One matched filter, 16 decimated capture samples, non-accumulating core
+// (matched_filter_avx2.cc:151-270).  h lives in sc.mf.h.
+WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
+  const int lane = lane_id();
+  const int half = lane >> 4, L = lane & 15;
+  float* h = sc.mf.h;
+  float error_sum = 0.f;
+  int updated = 0;
+  for (int i = 0; i < kSubBlock; ++i) {
+    const int base = n * kMfShift + kSubBlock - 1 - i;  // window tap 0 in xw
+    int x_start = sc.s.lr_read + base;                   // position in the reference's ring
+    if (x_start >= kLowRateSize) x_start -= kLowRateSize;
+    const float* x = sc.mf.xw + base;
+    const int chunk1 = imin(kMfLen, kLowRateSize - x_start);
+    const int chunk2 = kMfLen - chunk1;
+    const int v1 = chunk1 >> 4, v2 = chunk2 >> 4;
+    float acc = 0.f;
+    for (int k = 0; k < v1; ++k) {
+      const int t = L + 16 * k;
+      const float xv = x[t];
+      acc = half ? fmaf(xv, xv, acc) : fmaf(h[t], xv, acc);
+    }
+    for (int k = 0; k < v2; ++k) {
+      const int t = chunk1 + L + 16 * k;
+      const float xv = x[t];
+      acc = half ? fmaf(xv, xv, acc) : fmaf(h[t], xv, acc);
+    }
+    acc = mf_hsum16(acc);
+    const float vec_s = __shfl_sync(WAP_FULL, acc, 0);
+    const float vec_x2 = __shfl_sync(WAP_FULL, acc, 16);
+    // Scalar remainders of the two chunks (separate multiply and add), in order.
+    float s = 0.f, x2_sum = 0.f;
+    for (int t = 16 * v1; t < chunk1; ++t) {
+      const float xk = x[t];
+      x2_sum += xk * xk;
+      s += h[t] * xk;
+    }
+    for (int t = chunk1 + 16 * v2; t < kMfLen; ++t) {
+      const float xk = x[t];
+      x2_sum += xk * xk;
+      s += h[t] * xk;
+    }
+    x2_sum += vec_x2;
+    s += vec_s;
+    const float yi = y[i];
+    const float e = yi - s;
+    const bool saturation = yi >= 32000.f || yi <= -32000.f;
+    error_sum += e * e;
+    __syncwarp();
+    if (x2_sum > kMfX2SumThreshold && !saturation) {
+      const float alpha = ec3::kMfSmoothing * e / x2_sum;
+      // Vector part of each chunk is fused, the (<8 tap) tails are not.
+      const int f1 = (chunk1 >> 3) << 3;
+      const int f2 = chunk1 + ((chunk2 >> 3) << 3);
+      for (int t = lane; t < kMfLen; t += 32) {
+        const bool fused = (t < chunk1) ? (t < f1) : (t < f2);
+        const float xv = x[t];
+        h[t] = fused ? fmaf(xv, alpha, h[t]) : h[t] + alpha * xv;
+      }
+      updated = 1;
+    }
+    __syncwarp();
+  }
+  *error_sum_out = error_sum;
+  *updated_out = updated;
+}
+
+// Same filter with the accumulated-error side output (winner of the previous
+// block only; matched_filter_avx2.cc:45-149).
+WAP_DEV void mf_core_accumulated_error(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
+  const int lane = lane_id();
+  float* h = sc.mf.h;
+  float* q = sc.mf.q;
+  float* inst = sc.mf.inst_err;
+  for (int g = lane; g < kAccErrLen; g += 32) inst[g] = 0.f;
+  float error_sum = 0.f;
+  int updated = 0;
+  for (int i = 0; i < kSubBlock; ++i) {
+    const int base = n * kMfShift + kSubBlock - 1 - i;
+    const float* x = sc.mf.xw + base;
+    // x*x: 16 fused chains over every 16th tap (lanes 0-15).
+    float acc = 0.f;
+    if (lane < 16) {
+      for (int k = 0; k < kMfLen / 16; ++k) {
+        const float xv = x[lane + 16 * k];
+        acc = fmaf(xv, xv, acc);
+      }
+    }
+    // h*x: plain products, summed four at a time as (p0+p1)+(p2+p3).
+    for (int g = lane; g < kAccErrLen; g += 32) {
+      const int t = 4 * g;
+      const float p0 = h[t] * x[t], p1 = h[t + 1] * x[t + 1], p2 = h[t + 2] * x[t + 2], p3 = h[t + 3] * x[t + 3];
+      q[g] = (p0 + p1) + (p2 + p3);
+    }
+    __syncwarp();
+    // Strictly serial running sum over the 128 groups.
+    if (lane == 0) {
+      float s_acum = 0.f;
+      for (int g = 0; g < kAccErrLen; ++g) {
+        s_acum += q[g];
+        q[g] = s_acum;
+      }
+    }
+    __syncwarp();
+    const float yi = y[i];
+    for (int g = lane; g < kAccErrLen; g += 32) {
+      const float eg = q[g] - yi;
+      inst[g] = fmaf(eg, eg, inst[g]);
+    }
+    const float s_acum = q[kAccErrLen - 1];
+    // x2_sum = ((d0 + d1) + d2) + d3, d_m = c_m + c_{m+4}, c_j = chain_j + chain_{j+8}.
+    acc += __shfl_xor_sync(WAP_FULL, acc, 8);
+    acc += __shfl_xor_sync(WAP_FULL, acc, 4);
+    const float d0 = __shfl_sync(WAP_FULL, acc, 0), d1 = __shfl_sync(WAP_FULL, acc, 1);
+    const float d2 = __shfl_sync(WAP_FULL, acc, 2), d3 = __shfl_sync(WAP_FULL, acc, 3);
+    const float x2_sum = ((d0 + d1) + d2) + d3;
+    const float e = yi - s_acum;
+    const bool saturation = yi >= 32000.f || yi <= -32000.f;
+    error_sum += e * e;
+    __syncwarp();
+    if (x2_sum > kMfX2SumThreshold && !saturation) {
+      const float alpha = ec3::kMfSmoothing * e / x2_sum;
+      for (int t = lane; t < kMfLen; t += 32) h[t] = fmaf(x[t], alpha, h[t]);
+      updated = 1;
+    }
+    __syncwarp();
+  }
+  *error_sum_out = error_sum;
+  *updated_out = updated;
+}
+
+// aec3::MaxSquarePeakIndex (matched_filter.cc:558-591) for a 512-tap filter:
+// first maximum among even taps, first maximum among odd taps, odd wins only
+// when strictly larger.
+WAP_DEV int mf_max_square_peak_index(const float* h) {
+  const int lane = lane_id();
+  float best = -1.f;
+  int bi = 0;
+  for (int t = lane; t < kMfLen; t += 32) {  // lane parity == tap parity
+    const float v = h[t] * h[t];
+    if (v > best) { best = v; bi = t; }
+  }
+  for (int m = 2; m < 32; m <<= 1) {
+    const float ov = __shfl_xor_sync(WAP_FULL, best, m);
+    const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const float even_v = __shfl_sync(WAP_FULL, best, 0), odd_v = __shfl_sync(WAP_FULL, best, 1);
+  const int even_i = __shfl_sync(WAP_FULL, bi, 0), odd_i = __shfl_sync(WAP_FULL, bi, 1);
+  return (odd_v > even_v) ? odd_i : even_i;
+}
+
+// MatchedFilter::Reset (matched_filter.cc:641-655)
+WAP_DEV void mf_reset(Aec3State& a, AecScratch& sc, bool full_reset) {
+  const int lane = lane_id();
+  for (int i = lane; i < kNumMatchedFilters * kMfLen; i += 32) (&a.mf_h[0][0])[i] = 0.f;
+  if (full_reset) {
+    for (int i = lane; i < kNumMatchedFilters * kAccErrLen; i += 32) (&a.mf_acc_err[0][0])[i] = 1.f;
+    if (lane == 0) sc.s.mf_number_pre_echo_updates = 0;
+  }
+  __syncwarp();
+}
+
+// MatchedFilterLagAggregator::Reset (matched_filter_lag_aggregator.cc:62-70)
+WAP_DEV void lag_aggregator_reset(Aec3State& a, AecScratch& sc, bool hard_reset) {
+  const int lane = lane_id();
+  for (int i = lane; i < kLagHistSize; i += 32) a.lag_hist[i] = 0;
+  for (int i = lane; i < 250; i += 32) { a.lag_hist_data[i] = 0; a.pre_hist_data[i] = -1; }
+  for (int i = lane; i < kPreEchoHistSize; i += 32) a.pre_hist[i] = 0;
+  if (lane == 0) {
+    sc.s.agg_hist_data_index = 0;
+    sc.s.pre_hist_data_index = 0;
+    sc.s.pre_candidate = 0;
+    if (hard_reset) sc.s.agg_significant_candidate_found = 0;
+  }
+  __syncwarp();
+}
+
+// EchoPathDelayEstimator::Reset(reset_lag_aggregator, reset_delay_confidence) (:123-131)
+WAP_DEV void delay_estimator_reset(Aec3State& a, AecScratch& sc, bool reset_lag_aggregator, bool reset_delay_confidence) {
+  if (reset_lag_aggregator) lag_aggregator_reset(a, sc, reset_delay_confidence);
+  mf_reset(a, sc, reset_lag_aggregator);
+  if (lane_id() == 0) {
+    sc.s.est_has_old_lag = 0;
+    sc.s.est_consistent_counter = 0;
+  }
+  __syncwarp();
+}
+
+// RenderDelayControllerImpl::Reset (render_delay_controller.cc:103-111)
+WAP_DEV void delay_controller_reset(Aec3State& a, AecScratch& sc, bool reset_delay_confidence) {
+  if (lane_id() == 0) {
+    sc.s.ctl_has_delay = 0;
+    sc.s.ctl_has_delay_samples = 0;
+    sc.s.ctl_delay_change_counter = 0;
+    if (reset_delay_confidence) sc.s.ctl_last_quality = kQualityCoarse;
+  }
+  delay_estimator_reset(a, sc, true, reset_delay_confidence);
+}
+
+// ClockdriftDetector::Update (clockdrift_detector.cc:21-60), lane 0.
+WAP_DEV void clockdrift_update(Aec3Scalars& s, int delay_estimate) {
+  if (delay_estimate == s.cd_history[0]) {
+    if (++s.cd_stability_counter > 7500) s.cd_level = 0;
+    return;
+  }
+  s.cd_stability_counter = 0;
+  const int d1 = s.cd_history[0] - delay_estimate;
+  const int d2 = s.cd_history[1] - delay_estimate;
+  const int d3 = s.cd_history[2] - delay_estimate;
+  const bool probable_up = (d1 == -1 && d2 == -2) || (d1 == -2 && d2 == -1);
+  const bool drift_up = probable_up && d3 == -3;
+  const bool probable_down = (d1 == 1 && d2 == 2) || (d1 == 2 && d2 == 1);
+  const bool drift_down = probable_down && d3 == 3;
+  if (drift_up || drift_down) s.cd_level = 2;                                   // kVerified
+  else if ((probable_up || probable_down) && s.cd_level == 0) s.cd_level = 1;  // kProbable
+  s.cd_history[2] = s.cd_history[1];
+  s.cd_history[1] = s.cd_history[0];
+  s.cd_history[0] = delay_estimate;
+}
+
+// RenderDelayControllerImpl::GetDelay for the capture block in sc.y.  Leaves the
+// controller's delay_ in sc.s.ctl_{has_delay,delay,delay_quality}.
+WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  __syncwarp();
+  // ---- EchoPathDelayEstimator::EstimateDelay: capture decimation
+  decimate_block(sc.y, sc.fftA, sc.ds, a.capture_decimator);
+  const float* y = sc.ds;
+  // ---- MatchedFilter::Update
+  mf_stage_window(a, sc);
+  float error_sum_anchor = 0.f;
+  for (int k = 0; k < kSubBlock; ++k) error_sum_anchor += y[k] * y[k];
+  const int last_best = s.mf_last_detected_best_lag_filter;
+  for (int n = 0; n < kNumMatchedFilters; ++n) {
+    for (int t = lane; t < kMfLen; t += 32) sc.mf.h[t] = a.mf_h[n][t];
+    __syncwarp();
+    float error_sum;
+    int updated;
+    if (n == last_best) mf_core_accumulated_error(sc, n, y, &error_sum, &updated);
+    else mf_core(sc, n, y, &error_sum, &updated);
+    const int peak = mf_max_square_peak_index(sc.mf.h);
+    for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = sc.mf.h[t];
+    if (lane == 0) {
+      sc.mf.err_sum[n] = error_sum;
+      sc.mf.updated[n] = updated;
+      sc.mf.peak[n] = peak;
+    }
+    __syncwarp();
+  }
+  // winner selection (matched_filter.cc:729-776), lane 0
+  if (lane == 0) {
+    float winner_error_sum = error_sum_anchor;
+    int has_winner_lag = 0, winner_lag = 0, winner_index = -1;
+    int has_prev = 0, prev_lag = 0, alignment_shift = 0;
+    for (int n = 0; n < kNumMatchedFilters; ++n) {
+      const int lag_estimate = sc.mf.peak[n];
+      const float error_sum = sc.mf.err_sum[n];
+      const bool reliable = lag_estimate > 2 && lag_estimate < (kMfLen - 10) &&
+                            error_sum < ec3::kMfThreshold * error_sum_anchor;
+      const int lag = lag_estimate + alignment_shift;
+      if (sc.mf.updated[n] && reliable && error_sum < winner_error_sum) {
+        winner_error_sum = error_sum;
+        winner_index = n;
+        if (has_prev && prev_lag == lag) {
+          winner_lag = prev_lag;
+          winner_index = n - 1;
+        } else {
+          winner_lag = lag;
+        }
+        has_winner_lag = 1;
+      }
+      has_prev = 1;
+      prev_lag = lag;
+      alignment_shift += kMfShift;
+    }
+    sc.ired[0] = winner_index;
+    sc.ired[1] = winner_lag;
+    sc.ired[2] = winner_lag;  // pre_echo_lag
+    sc.ired[3] = 0;           // update accumulated error?
+    if (winner_index != -1 && last_best == winner_index) {
+      if (error_sum_anchor > 1.0f) {
+        sc.ired[3] = 1;
+        s.mf_number_pre_echo_updates++;
+      }
+    }
+    (void)has_winner_lag;
+  }
+  __syncwarp();
+  const int winner_index = sc.ired[0];
+  const int winner_lag = sc.ired[1];
+  if (winner_index != -1) {
+    if (sc.ired[3]) {
+      // UpdateAccumulatedError (matched_filter.cc:43-58)
+      const float one_over_anchor = 1.0f / error_sum_anchor;
+      for (int k = lane; k < kAccErrLen; k += 32) {
+        const float error_norm = sc.mf.inst_err[k] * one_over_anchor;
+        float acc = a.mf_acc_err[winner_index][k];
+        if (error_norm < acc) acc = error_norm;
+        else acc += 0.015f * (error_norm - acc);
+        a.mf_acc_err[winner_index][k] = acc;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (last_best == winner_index && s.mf_number_pre_echo_updates >= 50) {
+        // ComputePreEchoLag (matched_filter.cc:60-76)
+        const int shift_winner = winner_index * kMfShift;
+        int pre = winner_lag - shift_winner;
+        const int maximum_pre_echo_lag = imin(pre / 4, kAccErrLen);
+        for (int k = maximum_pre_echo_lag - 1; k >= 0; --k) {
+          if (a.mf_acc_err[winner_index][k] > 0.5f) break;
+          pre = (k + 1) * 4 - 1;
+        }
+        sc.ired[2] = pre + shift_winner;
+      }
+      s.mf_last_detected_best_lag_filter = winner_index;
+    }
+    __syncwarp();
+  }
+  const int pre_echo_lag = sc.ired[2];
+
+  // ---- MatchedFilterLagAggregator::Aggregate
+  int has_agg = 0, agg_quality = 0, agg_delay = 0;
+  if (winner_index != -1) {
+    const int headroom = ec3::kHeadroomSamples / kDownSampling;
+    // PreEchoLagAggregator::Aggregate (:139-183)
+    {
+      int blk = imax(0, pre_echo_lag - headroom) >> 4;
+      blk = imin(imax(blk, 0), kPreEchoHistSize - 1);
+      if (lane == 0) {
+        const int old = a.pre_hist_data[s.pre_hist_data_index];
+        if (old != -1) --a.pre_hist[old];
+        a.pre_hist_data[s.pre_hist_data_index] = blk;
+        ++a.pre_hist[blk];
+        s.pre_hist_data_index = (s.pre_hist_data_index + 1) % 250;
+      }
+      __syncwarp();
+      int cand = 0;
+      if (s.pre_number_updates < kNumBlocksPerSecond * 2) {
+        float penalization = 1.0f, max_value = -1.0f;
+        for (int w = 0; w + kMfWindowSubBlocks <= kPreEchoHistSize; w += kMfWindowSubBlocks) {
+          const int v = a.pre_hist[w + lane];
+          // first maximum inside the 32-bin window
+          int best = v, bi = lane;
+          for (int m = 16; m; m >>= 1) {
+            const int ov = __shfl_xor_sync(WAP_FULL, best, m);
+            const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+          }
+          const float weighted = (float)best * penalization;
+          if (weighted > max_value) {
+            max_value = weighted;
+            cand = w + bi;
+          }
+          penalization *= 0.7f;
+        }
+        __syncwarp();
+        if (lane == 0) s.pre_number_updates++;
+      } else {
+        cand = warp_argmax_first_int(a.pre_hist, kPreEchoHistSize);
+      }
+      if (lane == 0) s.pre_candidate = cand << 4;
+      __syncwarp();
+    }
+    // HighestPeakAggregator::Aggregate (:115-127)
+    {
+      const int lag = imax(0, winner_lag - headroom);
+      if (lane == 0) {
+        --a.lag_hist[a.lag_hist_data[s.agg_hist_data_index]];
+        a.lag_hist_data[s.agg_hist_data_index] = lag;
+        ++a.lag_hist[lag];
+        s.agg_hist_data_index = (s.agg_hist_data_index + 1) % 250;
+      }
+      __syncwarp();
+      const int cand = warp_argmax_first_int(a.lag_hist, kLagHistSize);
+      const int count = a.lag_hist[cand];
+      const int sig = s.agg_significant_candidate_found || count > ec3::kThrConverged;
+      if (count > ec3::kThrConverged || (count > ec3::kThrInitial && !sig)) {
+        has_agg = 1;
+        agg_quality = sig ? kQualityRefined : kQualityCoarse;
+        agg_delay = s.pre_candidate;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s.agg_candidate = cand;
+        s.agg_significant_candidate_found = sig;
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- rest of EstimateDelay + RenderDelayControllerImpl::GetDelay, lane 0
+  if (lane == 0) {
+    if (has_agg && agg_quality == kQualityRefined) clockdrift_update(s, s.agg_candidate);
+    if (has_agg) agg_delay *= kDownSampling;
+    if (s.est_has_old_lag && has_agg && s.est_old_lag == agg_delay) ++s.est_consistent_counter;
+    else s.est_consistent_counter = 0;
+    s.est_has_old_lag = has_agg;
+    s.est_old_lag = agg_delay;
+    sc.ired[4] = s.est_consistent_counter > kNumBlocksPerSecond / 2;
+  }
+  __syncwarp();
+  if (sc.ired[4]) delay_estimator_reset(a, sc, false, false);
+  if (lane == 0) {
+    if (has_agg) {
+      if (!s.ctl_has_delay_samples || agg_delay != s.ctl_delay_samples) s.ctl_delay_change_counter = 0;
+      s.ctl_has_delay_samples = 1;
+      s.ctl_delay_samples = agg_delay;
+      s.ctl_delay_samples_quality = agg_quality;
+    }
+    if (s.ctl_delay_change_counter < 2 * kNumBlocksPerSecond) ++s.ctl_delay_change_counter;
+    if (s.ctl_has_delay_samples) {
+      const bool use_hysteresis =
+          s.ctl_last_quality == kQualityRefined && s.ctl_delay_samples_quality == kQualityRefined;
+      // ComputeBufferDelay (render_delay_controller.cc:65-82)
+      const int hysteresis = use_hysteresis ? ec3::kHysteresisLimitBlocks : 0;
+      int new_delay_blocks = s.ctl_delay_samples >> 6;
+      if (s.ctl_has_delay) {
+        const int current = s.ctl_delay;
+        if (new_delay_blocks > current && new_delay_blocks <= current + hysteresis) new_delay_blocks = current;
+      }
+      s.ctl_has_delay = 1;
+      s.ctl_delay = new_delay_blocks;
+      s.ctl_delay_quality = s.ctl_delay_samples_quality;
+      s.ctl_last_quality = s.ctl_delay_samples_quality;
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace wap

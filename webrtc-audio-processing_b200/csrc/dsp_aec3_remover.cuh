@@ -1,0 +1,921 @@
+// AEC3 echo remover for one call leg (mono render / mono capture): everything
+// EchoRemoverImpl::ProcessCapture runs after the linear stage.
+//   EchoRemoverImpl::{ProcessCapture, FormLinearFilterOutput}     aec3/echo_remover.cc:254-529
+//   AecState (+ InitialState, FilterDelay, FilteringQualityAnalyzer,
+//             SaturationDetector)                                 aec3/aec_state.cc:115-496
+//   SubtractorOutputAnalyzer                                      aec3/subtractor_output_analyzer.cc:26-66
+//   FilterAnalyzer (+ ConsistentFilterDetector)                   aec3/filter_analyzer.cc:80-291
+//   LegacyTransparentModeImpl                                     aec3/transparent_mode.cc:132-233
+//   SubbandErleEstimator / FullBandErleEstimator / ErlEstimator   aec3/subband_erle_estimator.cc:72-259,
+//                                                                 aec3/fullband_erle_estimator.cc:50-192,
+//                                                                 aec3/erl_estimator.cc:43-149
+//   ReverbModel / ReverbFrequencyResponse                         aec3/reverb_model.cc:25-53,
+//                                                                 aec3/reverb_frequency_response.cc:61-106
+//   ResidualEchoEstimator                                         aec3/residual_echo_estimator.cc:193-425
+//   ComfortNoiseGenerator                                         aec3/comfort_noise_generator.cc:60-192
+//   SuppressionGain (+ DominantNearendDetector, MovingAverage)    aec3/suppression_gain.cc:124-477,
+//                                                                 aec3/dominant_nearend_detector.cc:37-81
+//   SuppressionFilter::ApplyGain                                  aec3/suppression_filter.cc:88-183
+// Lanes own frequency bins (k = lane, lane + 32, 64).  The reference's
+// std::accumulate reductions are evaluated as left-to-right chains, several of
+// them side by side on different lanes, and exchanged through shared memory.
+#pragma once
+
+#include "dsp_aec3_common.cuh"
+#include "dsp_aec3_subtractor.cuh"
+
+namespace wap {
+
+WAP_DEVCONST ec3::Tuning kNormalTuning = WAP_EC3_NORMAL_TUNING;
+WAP_DEVCONST ec3::Tuning kNearendTuning = WAP_EC3_NEAREND_TUNING;
+
+constexpr float kX2BandEnergyThreshold = 44015068.0f;  // subband/fullband ERLE, ERL kX2Min
+constexpr float kActiveRenderEnergy = ec3::kActiveRenderLimit * ec3::kActiveRenderLimit * 64.f;
+
+// Left-to-right sum of p[from..to) -- the order std::accumulate uses.
+WAP_DEV float chain_sum(const float* p, int from, int to) {
+  float s = 0.f;
+  for (int i = from; i < to; ++i) s += p[i];
+  return s;
+}
+
+// ---- ErleEstimator::Reset / FullBandErleEstimator::Reset / SubbandErleEstimator::Reset
+WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
+  const int lane = lane_id();
+  for (int k = lane; k < kBins; k += 32) {
+    a.erle[k] = ec3::kErleMin;
+    a.erle_onset_comp[k] = ec3::kErleMin;
+    a.erle_unbounded[k] = ec3::kErleMin;
+    a.coming_onset[k] = 1;
+    a.erle_hold_counters[k] = 0;
+    a.accum_Y2[k] = 0.f;
+    a.accum_E2[k] = 0.f;
+    a.accum_low_render[k] = 0;
+  }
+  if (lane == 0) {
+    Aec3Scalars& s = sc.s;
+    s.erle_num_points = 0;
+    // ErleInstantaneous::Reset
+    s.fb_has_erle_log2 = 0;
+    s.fb_inst_quality = 0.f;
+    s.fb_num_points = 0;
+    s.fb_E2_acum = 0.f;
+    s.fb_Y2_acum = 0.f;
+    s.fb_max_erle_log2 = -10.f;
+    s.fb_min_erle_log2 = 33.f;
+    s.fb_erle_time_domain_log2 = fast_approx_log2f(ec3::kErleMin + 1e-3f);
+    s.fb_hold_counter = 0;
+    if (delay_change) s.erle_blocks_since_reset = 0;
+  }
+  __syncwarp();
+}
+
+// ---- FilterAnalyzer::Reset (filter_analyzer.cc:71-78), lane 0
+WAP_DEV void filter_analyzer_reset(Aec3Scalars& s) {
+  s.fa_blocks_since_reset = 0;
+  s.fa_region_start = 0;
+  s.fa_region_end = 0;
+  s.fa_peak_index = 0;
+  s.fa_gain = ec3::kDefaultGain;
+  s.cfd_significant_peak = 0;
+  s.cfd_floor_accum = 0.f;
+  s.cfd_secondary_peak = 0.f;
+  s.cfd_floor_low_limit = 0;
+  s.cfd_floor_high_limit = 0;
+  s.cfd_consistent_counter = 0;
+  s.cfd_consistent_delay_reference = -10;
+  s.fa_filter_delay_blocks = 0;
+}
+
+// ---- AecState::HandleEchoPathChange (aec_state.cc:152-188)
+WAP_DEV void aec_state_handle_echo_path_change(Aec3State& a, AecScratch& sc, const EchoPathVariability& v) {
+  Aec3Scalars& s = sc.s;
+  __syncwarp();
+  if (v.delay_change != kDelayAdjNone) {
+    if (lane_id() == 0) {
+      filter_analyzer_reset(s);
+      s.capture_signal_saturation = 0;
+      s.strong_not_saturated_render_blocks = 0;
+      s.blocks_with_active_render = 0;
+      s.init_state = 1;  // InitialState::Reset
+      s.init_strong_blocks = 0;
+      // LegacyTransparentModeImpl::Reset
+      s.tm_non_converged_sequence_size = 10000;
+      s.tm_diverged_sequence_size = 0;
+      s.tm_strong_not_saturated_render_blocks = 0;
+      s.erl_blocks_since_reset = 0;  // ErlEstimator::Reset
+      // FilteringQualityAnalyzer::Reset
+      s.fq_usable = 0;
+      s.fq_blocks_since_reset = 0;
+    }
+    erle_reset(a, sc, true);
+  } else if (v.gain_change) {
+    erle_reset(a, sc, false);
+  }
+  if (lane_id() == 0) s.soa_filter_converged = 0;
+  __syncwarp();
+}
+
+// ---- FilterAnalyzer::Update for the single capture channel.
+// Outputs (lane 0, staged scalars): fa_consistent_estimate, fa_gain,
+// fa_filter_delay_blocks.  Uses r.v0 / r.x_aligned as scratch.
+WAP_DEV void filter_analyzer_update(Aec3State& a, AecScratch& sc) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  const int size = s.h_time_size * kBlock;
+  if (lane == 0) {
+    ++s.fa_blocks_since_reset;
+    // SetRegionToAnalyze
+    s.fa_region_start = s.fa_region_end >= size - 1 ? 0 : s.fa_region_end + 1;
+    s.fa_region_end = imin(s.fa_region_start + kBlock - 1, size - 1);
+  }
+  __syncwarp();
+  const int start = s.fa_region_start, end = s.fa_region_end;
+  // PreProcessFilters: h_highpass_.resize() exposes zeros; 3-tap high-pass over the region.
+  for (int i = s.fa_hp_size + lane; i < size; i += 32) a.h_highpass[i] = 0.f;
+  for (int k = start + lane; k <= end; k += 32) {
+    float tmp = 0.f;
+    if (k >= 2) {
+      tmp += a.h_time[k] * 0.7929742f;
+      tmp += a.h_time[k - 1] * -0.36072128f;
+      tmp += a.h_time[k - 2] * -0.47047766f;
+    }
+    a.h_highpass[k] = tmp;
+    r.v0[k - start] = tmp;
+  }
+  __syncwarp();
+  // FindPeakIndex over the region (first maximum that beats the current peak).
+  const int peak_in = imin(s.fa_peak_index, size - 1);
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  for (int k = start + lane; k <= end; k += 32) {
+    const float v = r.v0[k - start] * r.v0[k - start];
+    if (v > best) { best = v; bi = k; }
+  }
+  for (int m = 16; m; m >>= 1) {
+    const float ov = __shfl_xor_sync(WAP_FULL, best, m);
+    const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const float hp_in = a.h_highpass[peak_in];
+  const int peak = (best > hp_in * hp_in) ? bi : peak_in;
+  const int delay_blocks = peak >> 6;
+  const float h_peak = a.h_highpass[peak];
+  __syncwarp();
+  if (lane == 0) {
+    s.fa_hp_size = size;
+    s.fa_peak_index = peak;
+    s.fa_filter_delay_blocks = delay_blocks;
+    // UpdateFilterGain
+    const bool sufficient_time_to_converge = s.fa_blocks_since_reset > 5 * kNumBlocksPerSecond;
+    if (sufficient_time_to_converge && s.fa_consistent_estimate) {
+      s.fa_gain = fabsf(h_peak);
+    } else if (s.fa_gain) {
+      s.fa_gain = fmaxr(s.fa_gain, fabsf(h_peak));
+    }
+    s.fa_filter_length_blocks = (int)((float)size * (1.f / kBlock));
+    // ConsistentFilterDetector::Detect, first part
+    if (start == 0) {
+      s.cfd_floor_accum = 0.f;
+      s.cfd_secondary_peak = 0.f;
+      s.cfd_floor_low_limit = peak < 64 ? 0 : peak - 64;
+      s.cfd_floor_high_limit = peak > size - 129 ? 0 : peak + 128;
+    }
+    float accum = s.cfd_floor_accum, secondary = s.cfd_secondary_peak;
+    for (int k = start; k < imin(end + 1, s.cfd_floor_low_limit); ++k) {
+      const float abs_h = fabsf(r.v0[k - start]);
+      accum += abs_h;
+      secondary = fmaxr(secondary, abs_h);
+    }
+    for (int k = imax(s.cfd_floor_high_limit, start); k <= end; ++k) {
+      const float abs_h = fabsf(r.v0[k - start]);
+      accum += abs_h;
+      secondary = fmaxr(secondary, abs_h);
+    }
+    s.cfd_floor_accum = accum;
+    s.cfd_secondary_peak = secondary;
+    if (end == size - 1) {
+      const float filter_floor = accum / (float)(s.cfd_floor_low_limit + size - s.cfd_floor_high_limit);
+      const float abs_peak = fabsf(h_peak);
+      s.cfd_significant_peak = abs_peak > 10.f * filter_floor && abs_peak > 2.f * secondary;
+    }
+  }
+  __syncwarp();
+  if (s.cfd_significant_peak) {
+    const float* xb = a.blocks[ring_off(s.blocks_read, -delay_blocks, kRingBlocks)];
+    for (int i = lane; i < kBlock; i += 32) r.x_aligned[i] = xb[i];
+    __syncwarp();
+    const float x_energy = energy_serial(r.x_aligned, kBlock);
+    __syncwarp();
+    if (lane == 0) {
+      const bool active_render_block = x_energy > kActiveRenderEnergy;
+      if (s.cfd_consistent_delay_reference == delay_blocks) {
+        if (active_render_block) ++s.cfd_consistent_counter;
+      } else {
+        s.cfd_consistent_counter = 0;
+        s.cfd_consistent_delay_reference = delay_blocks;
+      }
+    }
+  }
+  if (lane == 0) s.fa_consistent_estimate = (float)s.cfd_consistent_counter > 1.5f * kNumBlocksPerSecond;
+  __syncwarp();
+}
+
+// ---- AecState::Update (aec_state.cc:190-342).  Inputs in sc.rm: Y2, E2 (spectrum of the
+// formed linear output), sc.red[0..6] subtractor metrics.  `ext_has/ext_delay` is
+// the block processor's estimated delay.
+WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext_delay) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  const float y2 = sc.red[0], e2_refined = sc.red[1], e2_coarse = sc.red[2];
+  const float s_refined_max_abs = sc.red[5], s_coarse_max_abs = sc.red[6];
+
+  // SubtractorOutputAnalyzer::Update
+  constexpr float kConvergenceThreshold = 50 * 50 * kBlock;
+  constexpr float kConvergenceThresholdLowLevel = 20 * 20 * kBlock;
+  const bool refined_filter_converged = e2_refined < 0.5f * y2 && y2 > kConvergenceThreshold;
+  const bool coarse_filter_converged_strict = e2_coarse < 0.05f * y2 && y2 > kConvergenceThreshold;
+  const bool any_coarse_filter_converged = e2_coarse < 0.3f * y2 && y2 > kConvergenceThresholdLowLevel;
+  const float min_e2 = fminr(e2_refined, e2_coarse);
+  const bool all_filters_diverged = min_e2 > 1.5f * y2 && y2 > 30.f * 30.f * kBlock;
+  const bool any_filter_converged = refined_filter_converged || coarse_filter_converged_strict;
+  __syncwarp();
+  if (lane == 0) s.soa_filter_converged = any_filter_converged;
+
+  filter_analyzer_update(a, sc);
+  const bool any_filter_consistent = s.fa_consistent_estimate != 0;
+  const float max_echo_path_gain = s.fa_gain;
+
+  // FilterDelay::Update
+  if (lane == 0) {
+    if (ext_has && (!s.fd_has_external || s.fd_external_delay != ext_delay)) {
+      s.fd_has_external = 1;
+      s.fd_external_delay = ext_delay;
+    }
+    const bool may_not_have_converged = s.strong_not_saturated_render_blocks < 2 * kNumBlocksPerSecond;
+    if (may_not_have_converged && s.fd_has_external) s.fd_filter_delay = ec3::kHeadroomSamples / kBlock;
+    else s.fd_filter_delay = s.fa_filter_delay_blocks;
+    s.fd_min_filter_delay = s.fd_filter_delay;
+  }
+  __syncwarp();
+  const int delay = s.fd_min_filter_delay;
+
+  // aligned render block, render counters
+  {
+    const float* xb = a.blocks[ring_off(s.blocks_read, -delay, kRingBlocks)];
+    for (int i = lane; i < kBlock; i += 32) r.x_aligned[i] = xb[i];
+  }
+  __syncwarp();
+  const float render_energy = energy_serial(r.x_aligned, kBlock);
+  const bool active_render = render_energy > kActiveRenderEnergy;
+  const bool saturated_capture = s.capture_signal_saturation != 0;
+  const bool usable_linear_before = s.fq_usable != 0;
+  float max_sample_l = 0.f;
+  for (int i = lane; i < kBlock; i += 32) max_sample_l = fmaxf(max_sample_l, fabsf(r.x_aligned[i]));
+  const float max_sample = warp_max(max_sample_l);
+  __syncwarp();
+  if (lane == 0) {
+    s.blocks_with_active_render += active_render ? 1 : 0;
+    s.strong_not_saturated_render_blocks += (active_render && !saturated_capture) ? 1 : 0;
+  }
+
+  // ComputeAvgRenderReverb: r.v1 = avg_render_spectrum_with_reverb, r.v2 = X2 at the delay.
+  const int idx_at_delay = ring_off(s.spectra_read, delay, kRingBlocks);
+  const int idx_past = ring_inc(idx_at_delay, kRingBlocks);
+  for (int k = lane; k < kBins; k += 32) {
+    const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * ec3::kDefaultLen;
+    a.avg_render_reverb[k] = rev;
+    const float x2 = a.spectra[idx_at_delay][k];
+    r.v2[k] = x2;
+    r.v1[k] = x2 + rev;
+  }
+  __syncwarp();
+  if (s.init_transition_triggered) erle_reset(a, sc, false);
+
+  // Four 65-term chains side by side: X2_reverb, Y2, E2, X2.
+  if (lane < 4) {
+    const float* p = lane == 0 ? r.v1 : lane == 1 ? r.Y2 : lane == 2 ? r.E2 : r.v2;
+    sc.red[16 + lane] = chain_sum(p, 0, kBins);
+  }
+  __syncwarp();
+  const float X2rev_sum = sc.red[16], Y2_sum = sc.red[17], E2_sum = sc.red[18], X2_sum = sc.red[19];
+  const bool converged = any_filter_converged;
+
+  // ---- ErleEstimator::Update
+  if (lane == 0) sc.ired[8] = (++s.erle_blocks_since_reset < 2 * kNumBlocksPerSecond) ? 0 : 1;
+  __syncwarp();
+  if (sc.ired[8]) {
+    // SubbandErleEstimator::Update
+    const bool restart = converged && s.erle_num_points == 6;
+    const int num_points = converged ? (restart ? 1 : s.erle_num_points + 1) : s.erle_num_points;
+    const bool update_bands = converged && num_points == 6;
+    for (int k = lane; k < kBins; k += 32) {
+      float accY = a.accum_Y2[k], accE = a.accum_E2[k];
+      int low = a.accum_low_render[k];
+      if (converged) {  // UpdateAccumulatedSpectra
+        if (restart) { accY = 0.f; accE = 0.f; low = 0; }
+        accY = r.Y2[k] + accY;
+        accE = r.E2[k] + accE;
+        low = low || r.v1[k] < kX2BandEnergyThreshold;
+        a.accum_Y2[k] = accY;
+        a.accum_E2[k] = accE;
+        a.accum_low_render[k] = low;
+      }
+      if (k >= 1 && k < 64) {
+        float erle = a.erle[k], erle_oc = a.erle_onset_comp[k], erle_u = a.erle_unbounded[k];
+        int hold = a.erle_hold_counters[k], onset = a.coming_onset[k];
+        if (update_bands && accE > 0.f) {  // UpdateBands
+          const float new_erle = accY / accE;
+          if (!low) {
+            if (onset) onset = 0;
+            hold = 250;  // kBlocksForOnsetDetection
+          }
+          const float max_erle = k < 32 ? ec3::kErleMaxL : ec3::kErleMaxH;
+          float alpha = 0.05f;
+          if (new_erle < erle) alpha = low ? 0.f : 0.1f;
+          erle = clampr(erle + alpha * (new_erle - erle), ec3::kErleMin, max_erle);
+          alpha = 0.05f;
+          if (new_erle < erle_oc) alpha = low ? 0.f : 0.1f;
+          erle_oc = clampr(erle_oc + alpha * (new_erle - erle_oc), ec3::kErleMin, max_erle);
+          alpha = 0.05f;
+          if (new_erle < erle_u) alpha = low ? 0.f : 0.1f;
+          erle_u = clampr(erle_u + alpha * (new_erle - erle_u), ec3::kErleMin, 100000.0f);
+        }
+        // DecreaseErlePerBandForLowRenderSignals (erle_during_onsets_ stays at min_erle)
+        --hold;
+        if (hold <= 250 - 100) {
+          if (erle_oc > ec3::kErleMin) erle_oc = fmaxr(ec3::kErleMin, 0.97f * erle_oc);
+          if (hold <= 0) { onset = 1; hold = 0; }
+        }
+        a.erle[k] = erle;
+        a.erle_onset_comp[k] = erle_oc;
+        a.erle_unbounded[k] = erle_u;
+        a.erle_hold_counters[k] = hold;
+        a.coming_onset[k] = onset;
+        if (k == 1) { a.erle[0] = erle; a.erle_onset_comp[0] = erle_oc; a.erle_unbounded[0] = erle_u; }
+        if (k == 63) { a.erle[64] = erle; a.erle_onset_comp[64] = erle_oc; a.erle_unbounded[64] = erle_u; }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      s.erle_num_points = num_points;
+      // FullBandErleEstimator::Update
+      if (converged && X2rev_sum > kX2BandEnergyThreshold * (float)kBins) {
+        // ErleInstantaneous::Update
+        bool update_estimates = false;
+        s.fb_E2_acum += E2_sum;
+        s.fb_Y2_acum += Y2_sum;
+        if (++s.fb_num_points == 6) {
+          if (s.fb_E2_acum > 0.f) {
+            update_estimates = true;
+            s.fb_erle_log2 = fast_approx_log2f(s.fb_Y2_acum / s.fb_E2_acum + 1e-3f);
+            s.fb_has_erle_log2 = 1;
+          }
+          s.fb_num_points = 0;
+          s.fb_E2_acum = 0.f;
+          s.fb_Y2_acum = 0.f;
+        }
+        if (update_estimates) {
+          s.fb_max_erle_log2 -= 0.0004f;
+          s.fb_max_erle_log2 = fmaxr(s.fb_max_erle_log2, s.fb_erle_log2);
+          s.fb_min_erle_log2 += 0.0004f;
+          s.fb_min_erle_log2 = fminr(s.fb_min_erle_log2, s.fb_erle_log2);
+          float quality_estimate = 0.f;
+          if (s.fb_max_erle_log2 > s.fb_min_erle_log2)
+            quality_estimate = (s.fb_erle_log2 - s.fb_min_erle_log2) / (s.fb_max_erle_log2 - s.fb_min_erle_log2);
+          if (quality_estimate > s.fb_inst_quality) s.fb_inst_quality = quality_estimate;
+          else s.fb_inst_quality += 0.07f * (quality_estimate - s.fb_inst_quality);
+          s.fb_hold_counter = 100;  // kBlocksToHoldErle
+          s.fb_erle_time_domain_log2 += 0.05f * (s.fb_erle_log2 - s.fb_erle_time_domain_log2);
+          s.fb_erle_time_domain_log2 = fmaxr(s.fb_erle_time_domain_log2, fast_approx_log2f(ec3::kErleMin + 1e-3f));
+        }
+      }
+      --s.fb_hold_counter;
+      if (s.fb_hold_counter == 0) {  // ResetAccumulators
+        s.fb_has_erle_log2 = 0;
+        s.fb_inst_quality = 0.f;
+        s.fb_num_points = 0;
+        s.fb_E2_acum = 0.f;
+        s.fb_Y2_acum = 0.f;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- ErlEstimator::Update (render spectrum at the delay, capture spectrum)
+  if (lane == 0) sc.ired[9] = (++s.erl_blocks_since_reset < 2 * kNumBlocksPerSecond || !converged) ? 0 : 1;
+  __syncwarp();
+  if (sc.ired[9]) {
+    for (int k = 1 + lane; k < 64; k += 32) {
+      float erl = a.erl[k];
+      int hold = a.erl_hold_counters[k - 1];
+      const float X2 = r.v2[k];
+      if (X2 > kX2BandEnergyThreshold) {
+        const float new_erl = r.Y2[k] / X2;
+        if (new_erl < erl) {
+          hold = 1000;
+          erl += 0.1f * (new_erl - erl);
+          erl = fmaxr(erl, 0.01f);
+        }
+      }
+      --hold;
+      erl = hold > 0 ? erl : fminr(1000.f, 2.f * erl);
+      a.erl[k] = erl;
+      a.erl_hold_counters[k - 1] = hold;
+      if (k == 1) a.erl[0] = erl;
+      if (k == 63) a.erl[64] = erl;
+    }
+    if (lane == 0) {
+      if (X2_sum > kX2BandEnergyThreshold * (float)kBins) {
+        const float new_erl = Y2_sum / X2_sum;
+        if (new_erl < s.erl_time_domain) {
+          s.erl_hold_counter_time_domain = 1000;
+          s.erl_time_domain += 0.1f * (new_erl - s.erl_time_domain);
+          s.erl_time_domain = fmaxr(s.erl_time_domain, 0.01f);
+        }
+      }
+      --s.erl_hold_counter_time_domain;
+      s.erl_time_domain = s.erl_hold_counter_time_domain > 0 ? s.erl_time_domain : fminr(1000.f, 2.f * s.erl_time_domain);
+    }
+    __syncwarp();
+  }
+
+  // ---- scalar state machines, lane 0
+  if (lane == 0) {
+    // SaturationDetector::Update
+    s.saturated_echo = 0;
+    if (saturated_capture) {
+      if (usable_linear_before) {
+        s.saturated_echo = s_refined_max_abs > 20000.f || s_coarse_max_abs > 20000.f;
+      } else {
+        const float peak_echo_amplitude = max_sample * max_echo_path_gain * 10.f;
+        s.saturated_echo = peak_echo_amplitude > 32000;
+      }
+    }
+    // InitialState::Update
+    s.init_strong_blocks += (active_render && !saturated_capture) ? 1 : 0;
+    const int prev_initial_state = s.init_state;
+    s.init_state = (float)s.init_strong_blocks < ec3::kInitialStateSeconds * kNumBlocksPerSecond;
+    s.init_transition_triggered = !s.init_state && prev_initial_state;
+    // LegacyTransparentModeImpl::Update
+    ++s.tm_capture_block_counter;
+    s.tm_strong_not_saturated_render_blocks += (active_render && !saturated_capture) ? 1 : 0;
+    if (any_filter_consistent && delay < 5) {
+      s.tm_sane_filter_observed = 1;
+      s.tm_active_blocks_since_sane_filter = 0;
+    } else if (active_render) {
+      ++s.tm_active_blocks_since_sane_filter;
+    }
+    bool sane_filter_recently_seen;
+    if (!s.tm_sane_filter_observed) sane_filter_recently_seen = s.tm_capture_block_counter <= 5 * kNumBlocksPerSecond;
+    else sane_filter_recently_seen = s.tm_active_blocks_since_sane_filter <= 30 * kNumBlocksPerSecond;
+    if (any_filter_converged) {
+      s.tm_recent_convergence = 1;
+      s.tm_active_non_converged_sequence_size = 0;
+      s.tm_non_converged_sequence_size = 0;
+      ++s.tm_num_converged_blocks;
+    } else {
+      if (++s.tm_non_converged_sequence_size > 20 * kNumBlocksPerSecond) s.tm_num_converged_blocks = 0;
+      if (active_render && ++s.tm_active_non_converged_sequence_size > 60 * kNumBlocksPerSecond)
+        s.tm_recent_convergence = 0;
+    }
+    if (!all_filters_diverged) s.tm_diverged_sequence_size = 0;
+    else if (++s.tm_diverged_sequence_size >= 60) s.tm_non_converged_sequence_size = 10000;
+    if (s.tm_active_non_converged_sequence_size > 60 * kNumBlocksPerSecond) s.tm_finite_erl_recently_detected = 0;
+    if (s.tm_num_converged_blocks > 50) s.tm_finite_erl_recently_detected = 1;
+    if (s.tm_finite_erl_recently_detected) s.tm_active = 0;
+    else if (sane_filter_recently_seen && s.tm_recent_convergence) s.tm_active = 0;
+    else s.tm_active = s.tm_strong_not_saturated_render_blocks > 6 * kNumBlocksPerSecond;
+    // FilteringQualityAnalyzer::Update
+    const bool filter_update = active_render && !saturated_capture;
+    s.fq_blocks_since_reset += filter_update ? 1 : 0;
+    s.fq_blocks_since_start += filter_update ? 1 : 0;
+    s.fq_convergence_seen = s.fq_convergence_seen || any_filter_converged;
+    const bool sufficient_at_startup = (float)s.fq_blocks_since_start > kNumBlocksPerSecond * 0.4f;
+    const bool sufficient_at_reset = sufficient_at_startup && (float)s.fq_blocks_since_reset > kNumBlocksPerSecond * 0.2f;
+    bool usable = sufficient_at_startup && sufficient_at_reset;
+    usable = usable && (ext_has || s.fq_convergence_seen);
+    usable = usable && !s.tm_active;
+    s.fq_usable = usable;
+  }
+  __syncwarp();
+
+  // ---- ReverbModelEstimator::Update -> ReverbFrequencyResponse::Update
+  if (s.fb_has_erle_log2) {
+    const float quality = fminr(1.f, fmaxr(0.f, s.fb_inst_quality));
+    const float* tail = a.H2[s.H2_size - 1];
+    const float* direct = a.H2[s.fd_filter_delay];
+    if (lane < 2) sc.red[16 + lane] = chain_sum(lane == 0 ? direct : tail, 1, kBins);
+    __syncwarp();
+    const float direct_path_energy = sc.red[16], tail_energy = sc.red[17];
+    const float average_decay = direct_path_energy == 0.f ? 0.f : tail_energy / direct_path_energy;
+    const float smoothing = 0.2f * quality;
+    const float avg = s.reverb_average_decay + smoothing * (average_decay - s.reverb_average_decay);
+    for (int k = lane; k < kBins; k += 32) r.v3[k] = fmaxr(tail[k], direct[k] * avg);
+    __syncwarp();
+    if (lane == 0) {
+      s.reverb_average_decay = avg;
+      for (int k = 1; k < 64; ++k) {  // in-place recursion, ascending k
+        const float avg_neighbour = 0.5f * (r.v3[k - 1] + r.v3[k + 1]);
+        r.v3[k] = fmaxr(r.v3[k], avg_neighbour);
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < kBins; k += 32) a.tail_response[k] = r.v3[k];
+  }
+  __syncwarp();
+}
+
+// ---- ComfortNoiseGenerator::Compute.  `nearend` = capture spectrum chosen by the caller.
+// Output: r.N_re / r.N_im (lower-band comfort noise).
+WAP_DEV void cng_compute(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const float* nearend) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  const float noise_floor = cfg.cng_noise_floor;  // GetNoiseFloorFactor(), computed on the host
+  __syncwarp();
+  const bool saturated_capture = s.capture_signal_saturation != 0;
+  const int counter = s.cng_N2_counter;
+  const bool has_initial = s.cng_has_initial != 0;
+  const bool drop_initial = !saturated_capture && has_initial && counter + 1 == 1000;
+  const bool use_initial = has_initial && !drop_initial;
+  for (int k = lane; k < kBins; k += 32) {
+    float N2 = a.cng_N2[k], N2i = a.cng_N2_initial[k];
+    if (!saturated_capture) {
+      float Y2s = a.cng_Y2_smoothed[k];
+      Y2s = Y2s + 0.1f * (nearend[k] - Y2s);
+      a.cng_Y2_smoothed[k] = Y2s;
+      if (counter > 50) N2 = Y2s < N2 ? (0.9f * Y2s + 0.1f * N2) * 1.0002f : N2 * 1.0002f;
+      if (use_initial) N2i = N2 > N2i ? N2i + 0.001f * (N2 - N2i) : N2;
+      N2 = fmaxr(N2, noise_floor);
+      if (use_initial) {
+        N2i = fmaxr(N2i, noise_floor);
+        a.cng_N2_initial[k] = N2i;
+      }
+      a.cng_N2[k] = N2;
+    }
+    // GenerateComfortNoise
+    const float N = sqrtf(use_initial ? N2i : N2);
+    float re = 0.f, im = 0.f;
+    if (k >= 1 && k < 64) {
+      const unsigned seed_k = (kLcgA[k] * s.cng_seed + kLcgC[k]) & 0x7fffffffu;
+      const int i = (int)(seed_k >> 26);
+      re = N * kSqrt2Sin[i];
+      im = N * kSqrt2Sin[(i + 8) & 31];
+    }
+    r.N_re[k] = re;
+    r.N_im[k] = im;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (!saturated_capture && has_initial) {
+      ++s.cng_N2_counter;
+      if (drop_initial) s.cng_has_initial = 0;
+    }
+    s.cng_seed = (kLcgA[63] * s.cng_seed + kLcgC[63]) & 0x7fffffffu;
+  }
+  __syncwarp();
+}
+
+// ---- ResidualEchoEstimator::Estimate.  Outputs r.R2, r.R2_unb.
+WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  const bool dominant_nearend = s.dn_nearend_state != 0;
+  const bool usable = s.fq_usable != 0;
+  const bool saturated_echo = s.saturated_echo != 0;
+  const bool transparent = s.tm_active != 0;
+  const float* X2_latest = a.spectra[s.spectra_read];
+  const float echo_path_gain = transparent ? 0.01f * 0.01f : ec3::kDefaultGain * ec3::kDefaultGain;
+  const int delay = s.fd_min_filter_delay;
+  const bool add_reverb = usable || !transparent;
+  const int first_reverb_partition = usable ? s.fa_filter_length_blocks + 1 : delay + 1;
+  const float* X2_reverb_src = a.spectra[ring_off(s.spectra_read, first_reverb_partition, kRingBlocks)];
+  const float* erle = dominant_nearend ? a.erle : a.erle_onset_comp;
+  const int w0 = ring_off(s.spectra_read, imax(0, delay - 1), kRingBlocks);
+  const int wn = delay + 1 - imax(0, delay - 1) + 1;  // spectra in the window
+  for (int k = lane; k < kBins; k += 32) {
+    // UpdateRenderNoisePower
+    float floor = a.X2_noise_floor[k];
+    {
+      const float p = X2_latest[k];
+      int cnt = a.X2_noise_floor_counter[k];
+      if (p < floor) {
+        floor = p;
+        cnt = 0;
+      } else if (cnt >= (int)ec3::kNoiseFloorHold) {
+        floor = fmaxr(floor * 1.1f, ec3::kMinNoiseFloorPower);
+      } else {
+        ++cnt;
+      }
+      a.X2_noise_floor[k] = floor;
+      a.X2_noise_floor_counter[k] = cnt;
+    }
+    float R2, R2u;
+    if (usable) {
+      if (saturated_echo) {
+        R2 = R2u = r.Y2[k];
+      } else {
+        R2 = r.S2_lin[k] / erle[k];
+        R2u = r.S2_lin[k] / a.erle_unbounded[k];
+      }
+    } else if (saturated_echo) {
+      R2 = R2u = r.Y2[k];
+    } else {
+      // EchoGeneratingPower + ApplyNoiseGate + stationary-noise subtraction
+      float X2 = 0.f;
+      int idx = w0;
+      for (int j = 0; j < wn; ++j) {
+        X2 = fmaxr(X2, a.spectra[idx][k]);
+        idx = ring_inc(idx, kRingBlocks);
+      }
+      if (ec3::kNoiseGatePower > X2) X2 = fmaxr(0.f, X2 - ec3::kNoiseGateSlope * (ec3::kNoiseGatePower - X2));
+      X2 -= ec3::kStationaryGateSlope * floor;
+      X2 = fmaxr(0.f, X2);
+      R2 = R2u = X2 * echo_path_gain;
+    }
+    if (add_reverb) {
+      // UpdateReverb + AddReverb
+      const float scaling = usable ? a.tail_response[k] : echo_path_gain;
+      const float rev = (a.echo_reverb[k] + X2_reverb_src[k] * scaling) * ec3::kDefaultLen;
+      a.echo_reverb[k] = rev;
+      R2 += rev;
+      R2u += rev;
+    }
+    r.R2[k] = R2;
+    r.R2_unb[k] = R2u;
+  }
+  __syncwarp();
+}
+
+// GainParameters thresholds for bin k (suppression_gain.cc:452-477).
+WAP_DEV void gain_params(const ec3::Tuning& t, int k, float* enr_transparent, float* enr_suppress, float* emr_transparent) {
+  float aa;
+  if (k <= ec3::kLastLfBand) aa = 0.f;
+  else if (k < ec3::kFirstHfBand) aa = (k - ec3::kLastLfBand) / (float)(ec3::kFirstHfBand - ec3::kLastLfBand);
+  else aa = 1.f;
+  *enr_transparent = (1 - aa) * t.lf_t + aa * t.hf_t;
+  *enr_suppress = (1 - aa) * t.lf_s + aa * t.hf_s;
+  *emr_transparent = (1 - aa) * t.lf_e + aa * t.hf_e;
+}
+
+// ---- SuppressionGain::GetGain for one band.  `nearend` / `echo_spectrum` chosen
+// by the caller; output r.gain (amplitude domain).  sc.x = render block 0.
+WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float* nearend, bool clock_drift) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  // DominantNearendDetector::Update on (nearend, R2_unbounded, N2): three 15-term
+  // chains; LowNoiseRenderDetector::Detect: one 64-term chain with running maximum.
+  if (lane < 3) {
+    const float* p = lane == 0 ? nearend : lane == 1 ? r.R2_unb : a.cng_N2;
+    sc.red[16 + lane] = chain_sum(p, 1, 16);
+  } else if (lane == 3) {
+    float x2_sum = 0.f, x2_max = 0.f;
+    for (int i = 0; i < kBlock; ++i) {
+      const float x2 = sc.x[i] * sc.x[i];
+      x2_sum += x2;
+      x2_max = fmaxr(x2_max, x2);
+    }
+    sc.red[19] = x2_sum;
+    sc.red[20] = x2_max;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const float ne_sum = sc.red[16], echo_sum = sc.red[17], noise_sum = sc.red[18];
+    if (echo_sum < ec3::kDnEnrThreshold * ne_sum && ne_sum > ec3::kDnSnrThreshold * noise_sum) {
+      if (++s.dn_trigger_counter >= ec3::kDnTriggerThreshold) {
+        s.dn_hold_counter = ec3::kDnHoldDuration;
+        s.dn_trigger_counter = ec3::kDnTriggerThreshold;
+      }
+    } else {
+      s.dn_trigger_counter = imax(0, s.dn_trigger_counter - 1);
+    }
+    if (echo_sum > ec3::kDnEnrExitThreshold * ne_sum && echo_sum > ec3::kDnSnrThreshold * noise_sum) s.dn_hold_counter = 0;
+    s.dn_hold_counter = imax(0, s.dn_hold_counter - 1);
+    s.dn_nearend_state = s.dn_hold_counter > 0;
+    // LowNoiseRenderDetector
+    const float x2_sum = sc.red[19] / 1, x2_max = sc.red[20];
+    constexpr float kThreshold = 50.f * 50.f * 64.f;
+    sc.ired[8] = s.sg_average_power < kThreshold && x2_max < 3 * s.sg_average_power;
+    s.sg_average_power = s.sg_average_power * 0.9f + x2_sum * 0.1f;
+  }
+  __syncwarp();
+  const bool low_noise_render = sc.ired[8] != 0;
+  const bool nearend_state = s.dn_nearend_state != 0;
+  const bool saturated_echo = s.saturated_echo != 0;
+  const ec3::Tuning& tun = nearend_state ? kNearendTuning : kNormalTuning;
+  const float min_echo_power = low_noise_render ? ec3::kLowRenderLimit : ec3::kNormalRenderLimit;
+  const int mem_index = s.sg_nearend_mem_index;
+  // LowerBandGain
+  for (int k = lane; k < kBins; k += 32) {
+    const float last_gain = a.last_gain[k];
+    const float max_gain = fminr(fmaxr(last_gain * tun.max_inc, ec3::kFloorFirstIncrease), 1.f);
+    // MovingAverage::Average (mem_len 4 -> 3 stored blocks, scaling 1/4)
+    const float in = nearend[k];
+    float ne = in;
+    ne = a.nearend_mem[0][k] + ne;
+    ne = a.nearend_mem[1][k] + ne;
+    ne = a.nearend_mem[2][k] + ne;
+    ne *= 0.25f;
+    a.nearend_mem[mem_index][k] = in;
+    // WeightEchoForAudibility (the three ranges share threshold and normaliser)
+    const float threshold = ec3::kFloorPower * ec3::kAudibilityThreshold;
+    const float normalizer = 1.f / (threshold - ec3::kFloorPower);
+    const float echo = r.R2[k];
+    float weighted = echo;
+    if (echo < threshold) {
+      const float tmp = (threshold - echo) * normalizer;
+      weighted = echo * fmaxr(0.f, 1.f - tmp * tmp);
+    }
+    // GetMinGain
+    float min_gain = 0.f;
+    if (!saturated_echo) {
+      min_gain = weighted > 0.f ? min_echo_power / weighted : 1.f;
+      min_gain = fminr(min_gain, 1.f);
+      if (k <= ec3::kLastLfSmoothingBand) {  // lf_smoothing_during_initial_phase = true
+        if (a.last_nearend[k] > a.last_echo[k] || k <= ec3::kLastPermanentLfSmoothingBand) {
+          min_gain = fmaxr(min_gain, last_gain * tun.max_dec_lf);
+          min_gain = fminr(min_gain, 1.f);
+        }
+      }
+    }
+    // GainToNoAudibleEcho (masker = comfort noise spectrum N2)
+    float enr_t, enr_s, emr_t;
+    gain_params(tun, k, &enr_t, &enr_s, &emr_t);
+    const float enr = weighted / (ne + 1.f);
+    const float emr = weighted / (a.cng_N2[k] + 1.f);
+    float g = 1.0f;
+    if (enr > enr_t && emr > emr_t) {
+      g = (enr_s - enr) / (enr_s - enr_t);
+      g = fmaxr(g, emr_t / emr);
+    }
+    g = fmaxr(fminr(g, max_gain), min_gain);
+    r.gain[k] = fminr(1.f, g);
+    a.last_nearend[k] = ne;
+    a.last_echo[k] = weighted;
+  }
+  __syncwarp();
+  {
+    // LimitLowFrequencyGains / LimitHighFrequencyGains
+    const float g12 = fminr(r.gain[1], r.gain[2]);
+    const bool limit_hf = !nearend_state || clock_drift;
+    const float min_upper_gain = fminr(1.f, r.gain[ec3::kLimitingGainBand]);
+    const float g63 = limit_hf ? fminr(r.gain[63], min_upper_gain) : r.gain[63];
+    __syncwarp();
+    for (int k = lane; k < kBins; k += 32) {
+      float g = r.gain[k];
+      if (k <= 1) g = g12;
+      if (limit_hf) {
+        if (k > ec3::kLimitingGainBand) g = fminr(g, min_upper_gain);
+        if (k == 64) g = g63;
+      }
+      a.last_gain[k] = g;
+      r.gain[k] = sqrtf(g);
+    }
+  }
+  if (lane == 0) s.sg_nearend_mem_index = (mem_index + 1) % 3;
+  __syncwarp();
+}
+
+// ---- EchoRemoverImpl::ProcessCapture.  sc.y = capture block (in/out).
+WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, EchoPathVariability v,
+                                          bool capture_signal_saturation, int ext_has, int ext_delay) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  // x = render_buffer->GetBlock(0)
+  {
+    const float* xb = a.blocks[s.blocks_read];
+    for (int i = lane; i < kBlock; i += 32) sc.x[i] = xb[i];
+  }
+  if (lane == 0) s.capture_signal_saturation = capture_signal_saturation;
+  if (v.delay_change != kDelayAdjNone || v.gain_change) {
+    if (v.gain_change) {  // act on a gain change only once per frame
+      const bool act = s.er_gain_change_hangover == 0;
+      __syncwarp();
+      if (act) {
+        if (lane == 0) s.er_gain_change_hangover = 3;
+      } else {
+        v.gain_change = 0;
+      }
+    }
+    __syncwarp();
+    subtractor_handle_echo_path_change(a, sc, v);
+    aec_state_handle_echo_path_change(a, sc, v);
+    if (v.delay_change != kDelayAdjNone && lane == 0) s.sg_initial_state = 1;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (s.er_gain_change_hangover > 0) --s.er_gain_change_hangover;
+  }
+  __syncwarp();
+
+  render_signal_analyzer_update(a, sc, s.fd_min_filter_delay);
+
+  if (s.init_transition_triggered) {
+    if (lane == 0) {
+      subtractor_exit_initial_state(s);
+      s.sg_initial_state = 0;
+    }
+    __syncwarp();
+  }
+
+  subtractor_process(a, sc, s.capture_signal_saturation != 0);
+
+  // FormLinearFilterOutput (echo_remover.cc:497-529)
+  {
+    const float y2 = sc.red[0], e2_refined = sc.red[1], e2_coarse = sc.red[2], s2_refined = sc.red[3], s2_coarse = sc.red[4];
+    bool use_refined_output = true;
+    if (e2_coarse < 0.9f * e2_refined && y2 > 30.f * 30.f * kBlock &&
+        (s2_refined > 60.f * 60.f * kBlock || s2_coarse > 60.f * 60.f * kBlock)) {
+      use_refined_output = false;
+    } else if (e2_coarse < e2_refined && y2 < e2_refined) {
+      use_refined_output = false;
+    }
+    const float* from = s.er_refined_last_selected ? r.e_ref : r.e_coa;
+    const float* to = use_refined_output ? r.e_ref : r.e_coa;
+    for (int i = lane; i < kBlock; i += 32) {
+      float o = to[i];
+      if (from != to && i < 30) {  // SignalTransition
+        const float aa = (i + 1) * (1.f / 31);
+        o = aa * to[i] + (1.f - aa) * from[i];
+      }
+      r.e[i] = o;
+    }
+    __syncwarp();
+    if (lane == 0) s.er_refined_last_selected = use_refined_output;
+  }
+  // WindowedPaddedFft of y and e (sqrt-Hanning), spectra.
+  for (int i = lane; i < kBlock; i += 32) {
+    sc.fftA[i] = a.y_old[i] * kSqrtHanning128[i];
+    sc.fftA[kBlock + i] = sc.y[i] * kSqrtHanning128[kBlock + i];
+    sc.fftB[i] = a.e_old[i] * kSqrtHanning128[i];
+    sc.fftB[kBlock + i] = r.e[i] * kSqrtHanning128[kBlock + i];
+    a.y_old[i] = sc.y[i];
+    a.e_old[i] = r.e[i];
+  }
+  fft_pair(sc, false, true);
+  packed_to_reim(sc.fftA, r.Y_re, r.Y_im);
+  packed_to_reim(sc.fftB, r.E_re, r.E_im);
+  __syncwarp();
+  for (int k = lane; k < kBins; k += 32) {
+    const float dr = r.Y_re[k] - r.E_re[k], di = r.Y_im[k] - r.E_im[k];
+    r.S2_lin[k] = dr * dr + di * di;  // LinearEchoPower
+    r.Y2[k] = power_bin(r.Y_re[k], r.Y_im[k], k);
+    r.E2[k] = power_bin(r.E_re[k], r.E_im[k], k);
+  }
+  __syncwarp();
+  // nearend_spectrum is bound before AecState::Update changes UsableLinearEstimate().
+  const bool nearend_is_E2 = s.fq_usable != 0;
+  aec_state_update(a, sc, ext_has, ext_delay);
+
+  const float* nearend = nearend_is_E2 ? r.E2 : r.Y2;
+  cng_compute(a, cfg, sc, nearend);
+
+  if (cfg.capture_output_used) {
+    residual_echo_estimate(a, sc);
+    const bool usable = s.fq_usable != 0;
+    if (usable) {
+      for (int k = lane; k < kBins; k += 32) r.E2[k] = fminr(r.E2[k], r.Y2[k]);
+      __syncwarp();
+    }
+    // echo_spectrum only matters for the upper bands (B > 1).
+    suppression_gain_get_gain(a, sc, nearend, v.clock_drift != 0);
+
+    // SuppressionFilter::ApplyGain
+    const float* Yf_re = usable ? r.E_re : r.Y_re;
+    const float* Yf_im = usable ? r.E_im : r.Y_im;
+    for (int k = lane; k < kBins; k += 32) {
+      const float g = r.gain[k];
+      const float noise_gain = sqrtf(1.f - g * g);
+      const float E_real = Yf_re[k] * g;
+      const float E_imag = Yf_im[k] * g;
+      const float re = E_real + noise_gain * r.N_re[k];
+      const float im = E_imag + noise_gain * r.N_im[k];
+      if (k == 0) sc.fftA[0] = re;
+      else if (k == 64) sc.fftA[1] = re;
+      else { sc.fftA[2 * k] = re; sc.fftA[2 * k + 1] = im; }
+    }
+    fft_pair(sc, true, false);
+    constexpr float kIfftNormalization = 2.f / 128;
+    for (int i = lane; i < kBlock; i += 32) {
+      float e0 = a.e_output_old[i] * kSqrtHanning128[kBlock + i];
+      e0 += sc.fftA[i] * kSqrtHanning128[i];
+      e0 = e0 * kIfftNormalization;
+      a.e_output_old[i] = sc.fftA[kBlock + i];
+      sc.y[i] = clampr(e0, -32768.f, 32767.f);
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace wap

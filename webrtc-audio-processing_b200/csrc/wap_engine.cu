@@ -98,6 +98,7 @@ struct WapAudioProcessing {
   WapSampleFormat render_fmt = WapSampleFormat::I16;
   std::mutex render_mu;
   bool owns_engine = false;
+  WapStats cached_stats{};  // ApmStatsReporter::cached_stats_
 };
 
 namespace {
@@ -153,6 +154,9 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
       e.ns_over_subtraction_factor = 1.25f; e.ns_minimum_attenuating_gain = 0.09f; e.ns_use_attenuation_adjustment = 1; break;
   }
   e.capture_output_used = 1;
+  e.reinit_on_first_capture = (c.noise_suppression_enabled || c.gain_controller2_enabled ||
+                               f.sample_rate_hz != 16000 || f.num_channels != 1) ? 1 : 0;
+  e.cng_noise_floor = 64.f * powf(10.f, (90.30899869919436f + -96.03406f) * 0.1f);
   *out = e;
   return WapError::None;
 }
@@ -394,19 +398,49 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
 
 }  // extern "C"
 
-namespace wap {
-#ifndef WAP_HAVE_AEC3_INIT
-void init_aec3_state(Aec3State& a) { memset(&a, 0, sizeof(a)); }
-#endif
-}  // namespace wap
-
 extern "C" {
 
-WapError wap_get_statistics(const WapAudioProcessing* h, WapStats* out) {
-  if (!h || !out) return WapError::NullPointer;
-  memset(out, 0, sizeof(*out));
+// AudioProcessingImpl::GetStatistics (audio_processing_impl.cc:1509-1518,2312-2320):
+// the statistics of the capture frame that filled ApmStatsReporter's one-slot
+// queue (EchoRemoverImpl::GetMetrics echo_remover.cc:247-252 and
+// BlockProcessorImpl::GetMetrics block_processor.cc:222-227, evaluated on the
+// scalars the tick kernel latched), else the previously returned ones.
+WapError wap_get_statistics(const WapAudioProcessing* hc, WapStats* out) {
+  if (!hc || !out) return WapError::NullPointer;
+  WapAudioProcessing* h = const_cast<WapAudioProcessing*>(hc);
+  if (h->engine && h->slot >= 0 && h->engine->cfg.aec_enabled) {
+    WapEngine* e = h->engine;
+    WAP_CUDA(cudaSetDevice(e->device));
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+    wap::Aec3Scalars s;
+    WAP_CUDA(cudaMemcpy(&s, &e->d_states[h->slot].aec.s, sizeof(s), cudaMemcpyDeviceToHost));
+    if (s.stats_slot_full) {
+      WapStats st;
+      memset(&st, 0, sizeof(st));
+      st.has_echo_return_loss = true;
+      st.echo_return_loss = -10.0 * log10((double)s.stats_erl_time_domain);
+      st.has_echo_return_loss_enhancement = true;
+      // Log2TodB (aec3_common.cc:54-56): double product rounded to float.
+      st.echo_return_loss_enhancement = (double)(float)(3.0102999566398121 * (double)s.stats_erle_log2);
+      st.has_delay_ms = true;
+      st.delay_ms = s.stats_delay_blocks * 4;  // block_size_ms = 4
+      h->cached_stats = st;
+      const int zero = 0;
+      WAP_CUDA(cudaMemcpy(&e->d_states[h->slot].aec.s.stats_slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    }
+  }
+  *out = h->cached_stats;
   return WapError::None;
 }
+
+// Test / tooling hook: raw copy of one leg's state slab (wap_state.h layout).
+int wapdbg_read_state(const WapAudioProcessing* h, void* out, size_t bytes) {
+  if (!h || !h->engine || h->slot < 0 || bytes > sizeof(StreamState)) return -1;
+  WapEngine* e = h->engine;
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) return -1;
+  return cudaMemcpy(out, &e->d_states[h->slot], bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+size_t wapdbg_state_size(void) { return sizeof(StreamState); }
 
 double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (!e) return 0.0;

@@ -83,7 +83,9 @@ WAP_DEV void process_stream_tick(const TickArgs& a, int idx, float* scratch) {
   AecScratch& aec_sc = *reinterpret_cast<AecScratch*>(dsp);
 
   // ---------------- render side (ProcessReverseStream)
-  if (a.render && cfg.aec_enabled) {
+  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
+  __syncwarp();
+  if (a.render && cfg.aec_enabled && render_live) {
     load_frame(a.render, idx, flen, a.fmt, full);
     if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.render_bands.analysis);
     aec3_buffer_render_frame(st.aec, cfg, bands, aec_sc);
@@ -91,6 +93,7 @@ WAP_DEV void process_stream_tick(const TickArgs& a, int idx, float* scratch) {
   if (!a.capture) return;
 
   // ---------------- capture side (ProcessStream)
+  if (lane_id() == 0) st.seen_capture = 1;
   load_frame(a.capture, idx, flen, a.fmt, full);
   if (cfg.hpf_enabled) {
     biquad_cascade<3>(full, flen, B == 3 ? kHpf48k : kHpf16k, st.hpf);

@@ -99,6 +99,103 @@ struct NsState {
 };
 
 // ---------------------------------------------------------------- AEC3
+// Scalar state of every AEC3 class (one group, staged in shared memory for the
+// duration of a tick and mutated by lane 0; see dsp_aec3.cuh).  std::optional
+// members are split into has_x / x.
+struct Aec3Scalars {
+  // FrameBlocker / BlockFramer fill levels (frame_blocker.cc, block_framer.cc)
+  int render_blocker_len, capture_blocker_len, output_framer_len;
+  // EchoCanceller3::saturated_microphone_signal_
+  int saturated_microphone_signal;
+  // BlockProcessorImpl (block_processor.cc:67-78)
+  int capture_properly_started, render_properly_started, render_event;
+  int bp_has_estimated_delay, bp_est_quality, bp_est_delay;  // estimated_delay_
+  // RenderDelayBufferImpl (render_delay_buffer.cc:72-101)
+  int blocks_write, blocks_read, spectra_write, spectra_read;  // fft ring shares the spectra indices
+  int lr_write, lr_read;
+  int has_delay, delay;
+  int last_call_was_render, num_api_calls_in_a_row, max_observed_jitter;
+  int render_activity, render_activity_counter, rb_render_activity;  // rb_: RenderBuffer::render_activity_
+  int has_external_delay, external_delay, external_delay_verified;
+  int min_latency_blocks, excess_render_detection_counter;
+  // RenderDelayControllerImpl (render_delay_controller.cc:55-62)
+  int ctl_has_delay, ctl_delay, ctl_delay_quality;
+  int ctl_has_delay_samples, ctl_delay_samples, ctl_delay_samples_quality;
+  int ctl_delay_change_counter, ctl_last_quality;
+  // EchoPathDelayEstimator
+  int est_has_old_lag, est_old_lag, est_consistent_counter;
+  // MatchedFilter (matched_filter.h:156-164)
+  int mf_last_detected_best_lag_filter;   // -1
+  int mf_number_pre_echo_updates;
+  // MatchedFilterLagAggregator
+  int agg_significant_candidate_found;
+  int agg_hist_data_index, agg_candidate;                     // HighestPeakAggregator (candidate -1)
+  int pre_hist_data_index, pre_candidate, pre_number_updates; // PreEchoLagAggregator
+  // ClockdriftDetector
+  int cd_history[3], cd_level, cd_stability_counter;
+  // EchoRemoverImpl
+  int er_gain_change_hangover, er_refined_last_selected;  // init true
+  // AdaptiveFirFilter x2 (refined, coarse)
+  int fr_current_size, fr_target_size, fr_old_target_size, fr_size_change_counter, fr_partition_to_constrain;
+  int fc_current_size, fc_target_size, fc_old_target_size, fc_size_change_counter, fc_partition_to_constrain;
+  int h_time_size;                        // refined_impulse_responses_.size() / 64
+  int H2_size;                            // refined_frequency_responses_.size()
+  // RefinedFilterUpdateGain / CoarseFilterUpdateGain
+  int rg_poor_excitation_counter, rg_call_counter, rg_config_change_counter;
+  float rg_cur[5], rg_old[5], rg_tgt[5];  // leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate
+  int cg_poor_excitation_counter, cg_call_counter, cg_config_change_counter;
+  float cg_cur[2], cg_old[2], cg_tgt[2];  // rate, noise_gate
+  // Subtractor::FilterMisadjustmentEstimator + coarse re-seed logic
+  int mis_n_blocks_acum, mis_overhang;
+  float mis_e2_acum, mis_y2_acum, mis_inv_misadjustment;
+  int poor_coarse_filter_counter, coarse_filter_reset_hangover;
+  // RenderSignalAnalyzer
+  int rsa_has_narrow_peak, rsa_narrow_peak_band, rsa_narrow_peak_counter;
+  // AecState
+  int capture_signal_saturation;
+  int strong_not_saturated_render_blocks, blocks_with_active_render;
+  int init_state, init_transition_triggered, init_strong_blocks;   // InitialState
+  int fd_filter_delay, fd_min_filter_delay, fd_has_external, fd_external_delay;  // FilterDelay
+  int fq_usable, fq_blocks_since_reset, fq_blocks_since_start, fq_convergence_seen;  // FilteringQualityAnalyzer
+  int saturated_echo;
+  int soa_filter_converged;               // SubtractorOutputAnalyzer::filters_converged_[0]
+  // FilterAnalyzer (+ ConsistentFilterDetector)
+  int fa_blocks_since_reset, fa_region_start, fa_region_end, fa_peak_index, fa_filter_length_blocks;
+  int fa_consistent_estimate, fa_filter_delay_blocks, fa_min_filter_delay_blocks;
+  int fa_hp_size;                         // h_highpass_.size() in samples
+  float fa_gain;
+  int cfd_significant_peak, cfd_floor_low_limit, cfd_floor_high_limit;
+  int cfd_consistent_counter, cfd_consistent_delay_reference;
+  float cfd_floor_accum, cfd_secondary_peak;
+  // LegacyTransparentModeImpl (transparent_mode.cc:222-233)
+  int tm_capture_block_counter, tm_active, tm_active_blocks_since_sane_filter, tm_sane_filter_observed;
+  int tm_finite_erl_recently_detected, tm_non_converged_sequence_size, tm_diverged_sequence_size;
+  int tm_active_non_converged_sequence_size, tm_num_converged_blocks, tm_recent_convergence;
+  int tm_strong_not_saturated_render_blocks;
+  // ErleEstimator / SubbandErleEstimator / FullBandErleEstimator
+  int erle_blocks_since_reset, erle_num_points;
+  int fb_hold_counter, fb_has_erle_log2, fb_num_points;
+  float fb_erle_time_domain_log2, fb_erle_log2, fb_inst_quality, fb_max_erle_log2, fb_min_erle_log2;
+  float fb_Y2_acum, fb_E2_acum;
+  int fb_has_quality; float fb_quality;   // linear_filters_qualities_[0]
+  // ErlEstimator
+  int erl_blocks_since_reset, erl_hold_counter_time_domain;
+  float erl_time_domain;
+  // ReverbFrequencyResponse
+  float reverb_average_decay;
+  // ComfortNoiseGenerator
+  int cng_N2_counter, cng_has_initial;
+  unsigned cng_seed;                      // 42
+  // SuppressionGain (+ LowNoiseRenderDetector, DominantNearendDetector)
+  int sg_initial_state, sg_nearend_mem_index;
+  float sg_average_power;
+  int dn_nearend_state, dn_trigger_counter, dn_hold_counter;
+  // ApmStatsReporter one-slot queue (audio_processing_impl.cc:2312-2327)
+  int stats_slot_full;
+  float stats_erl_time_domain, stats_erle_log2;
+  int stats_delay_blocks, stats_has_delay;
+};
+
 struct Aec3State {
   // ---- RenderDelayBuffer rings (render_delay_buffer.cc:72-101)
   float blocks[kRingBlocks][kBlock];        // BlockBuffer, band 0 / channel 0
@@ -124,7 +221,7 @@ struct Aec3State {
   float h_highpass[kMaxPartitions * kBlock];  // FilterAnalyzer::h_highpass_
   float H_error[kBinsPad];                  // RefinedFilterUpdateGain::H_error_, init 10000
   // ---- 65-bin estimator vectors
-  float erle[kBinsPad], erle_onset_comp[kBinsPad], erle_unbounded[kBinsPad], erle_during_onsets[kBinsPad];
+  float erle[kBinsPad], erle_onset_comp[kBinsPad], erle_unbounded[kBinsPad];  // init 1 (min_erle)
   float accum_Y2[kBinsPad], accum_E2[kBinsPad];
   float erl[kBinsPad];                      // init 1000
   float avg_render_reverb[kBinsPad];        // AecState::avg_render_reverb_
@@ -133,114 +230,28 @@ struct Aec3State {
   float X2_noise_floor[kBinsPad];           // init 1638400
   float cng_Y2_smoothed[kBinsPad], cng_N2[kBinsPad], cng_N2_initial[kBinsPad];
   float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
-  float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (4 blocks -> 3 slots)
-  int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used)
+  float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (mem_len 4 -> 3 slots)
+  int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used, index k-1)
   int erle_hold_counters[kBinsPad];
   int erl_hold_counters[kBinsPad];          // 63 used, index k-1
   int X2_noise_floor_counter[kBinsPad];     // init 50
-  unsigned char accum_low_render[kBinsPad]; // SubbandErleEstimator accum_spectra_.low_render_energy
-  unsigned char coming_onset[kBinsPad];     // init true
+  int accum_low_render[kBinsPad];           // SubbandErleEstimator accum_spectra_.low_render_energy
+  int coming_onset[kBinsPad];               // init true
   // ---- time-domain memories
   float e_old[kBlock], y_old[kBlock], e_output_old[kBlock];
   float render_blocker[kBlock], capture_blocker[kBlock], output_framer[kBlock];
   Biquad render_decimator[4], capture_decimator[4];
-  // ---- scalar state (one cache line group, read into registers per block)
-  struct Scalars {
-    // FrameBlocker / BlockFramer fill levels
-    int render_blocker_len, capture_blocker_len, output_framer_len;
-    // BlockProcessorImpl (block_processor.cc:67-78)
-    int capture_properly_started, render_properly_started, render_event;
-    // RenderDelayBufferImpl
-    int blocks_write, blocks_read, spectra_write, spectra_read;  // fft ring shares spectra indices
-    int lr_write, lr_read;
-    int has_delay, delay;                   // std::optional<size_t> delay_
-    int last_call_was_render, num_api_calls_in_a_row, max_observed_jitter;
-    int render_activity, render_activity_counter, rb_render_activity;  // rb_*: RenderBuffer::render_activity_
-    int has_external_delay, external_delay, external_delay_verified;
-    int min_latency_blocks, excess_render_detection_counter;
-    long long capture_call_counter, render_call_counter;
-    // RenderDelayControllerImpl (render_delay_controller.cc:55-62)
-    int ctl_has_delay, ctl_delay, ctl_delay_quality;       // delay_ (blocks)
-    int ctl_has_delay_samples, ctl_delay_samples, ctl_delay_samples_quality;
-    int ctl_blocks_since_last_change, ctl_blocks_since_last_update;
-    int ctl_delay_change_counter, ctl_last_quality;
-    long long ctl_capture_call_counter;
-    // EchoPathDelayEstimator
-    int est_has_old_lag, est_old_lag, est_old_lag_quality, est_consistent_counter;
-    // MatchedFilter
-    int mf_last_detected_best_lag_filter;   // -1
-    int mf_number_pre_echo_updates;
-    // MatchedFilterLagAggregator
-    int agg_significant_candidate_found;
-    int agg_hist_data_index, agg_candidate;          // HighestPeakAggregator
-    int pre_hist_data_index, pre_candidate, pre_number_updates;  // PreEchoLagAggregator
-    // ClockdriftDetector
-    int cd_history[3], cd_level, cd_stability_counter;
-    // EchoRemoverImpl
-    long long er_block_counter;
-    int er_gain_change_hangover, er_refined_last_selected;  // init true
-    // Subtractor + filters + gains
-    int fr_current_size, fr_target_size, fr_old_target_size, fr_size_change_counter, fr_partition_to_constrain;
-    int fc_current_size, fc_target_size, fc_old_target_size, fc_size_change_counter, fc_partition_to_constrain;
-    int h_time_size;                        // refined_impulse_responses_.size() / 64
-    int H2_size;                            // refined_frequency_responses_.size()
-    int rg_poor_excitation_counter, rg_call_counter, rg_config_change_counter;  // RefinedFilterUpdateGain
-    float rg_cur[5], rg_old[5], rg_tgt[5];  // leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate
-    int cg_poor_excitation_counter, cg_call_counter, cg_config_change_counter;  // CoarseFilterUpdateGain
-    float cg_cur[2], cg_old[2], cg_tgt[2];  // rate, noise_gate
-    int mis_n_blocks_acum, mis_overhang;    // FilterMisadjustmentEstimator
-    float mis_e2_acum, mis_y2_acum, mis_inv_misadjustment;
-    int poor_coarse_filter_counter, coarse_filter_reset_hangover;
-    // RenderSignalAnalyzer
-    int rsa_has_narrow_peak, rsa_narrow_peak_band, rsa_narrow_peak_counter;
-    // AecState
-    int capture_signal_saturation;
-    int strong_not_saturated_render_blocks, blocks_with_active_render;
-    int init_state, init_transition_triggered, init_strong_blocks;   // InitialState
-    int fd_filter_delay, fd_min_filter_delay, fd_has_external, fd_external_delay, fd_external_quality;  // FilterDelay
-    int fq_usable, fq_blocks_since_reset, fq_blocks_since_start, fq_convergence_seen;  // FilteringQualityAnalyzer
-    int saturated_echo;
-    int soa_filter_converged;               // SubtractorOutputAnalyzer::filters_converged_[0]
-    // FilterAnalyzer
-    int fa_blocks_since_reset, fa_region_start, fa_region_end, fa_peak_index, fa_filter_length_blocks;
-    int fa_consistent_estimate, fa_filter_delay_blocks, fa_min_filter_delay_blocks;
-    float fa_gain;
-    int cfd_significant_peak, cfd_floor_low_limit, cfd_floor_high_limit;
-    int cfd_consistent_counter, cfd_consistent_delay_reference;
-    float cfd_floor_accum, cfd_secondary_peak;
-    // LegacyTransparentModeImpl (transparent_mode.cc:222-233)
-    int tm_capture_block_counter, tm_active, tm_active_blocks_since_sane_filter, tm_sane_filter_observed;
-    int tm_finite_erl_recently_detected, tm_non_converged_sequence_size, tm_diverged_sequence_size;
-    int tm_active_non_converged_sequence_size, tm_num_converged_blocks, tm_recent_convergence;
-    int tm_strong_not_saturated_render_blocks;
-    // ErleEstimator / SubbandErleEstimator / FullBandErleEstimator
-    int erle_blocks_since_reset, erle_num_points;
-    int fb_hold_counter, fb_has_erle_log2, fb_num_points;
-    float fb_erle_time_domain_log2, fb_erle_log2, fb_inst_quality, fb_max_erle_log2, fb_min_erle_log2;
-    float fb_Y2_acum, fb_E2_acum;
-    int fb_has_quality; float fb_quality;   // linear_filters_qualities_[0]
-    // ErlEstimator
-    int erl_blocks_since_reset, erl_hold_counter_time_domain;
-    float erl_time_domain;
-    // Reverb
-    float reverb_average_decay;
-    // ComfortNoiseGenerator
-    int cng_N2_counter, cng_has_initial;
-    unsigned cng_seed;                      // 42
-    // SuppressionGain
-    int sg_initial_state, sg_initial_state_change_counter, sg_nearend_mem_index;
-    float sg_average_power;                 // LowNoiseRenderDetector, 32768^2
-    int dn_nearend_state, dn_trigger_counter, dn_hold_counter;
-    // statistics mirror (EchoRemoverImpl::GetMetrics / BlockProcessorImpl::GetMetrics)
-    int saturated_microphone_signal;        // EchoCanceller3::saturated_microphone_signal_
-    int pad_[3];
-  } s;
+  Aec3Scalars s;
 };
 
 // One call leg.
 struct StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)
-  int pad_[4];
+  // 1 once a capture frame has been processed.  Until then the reference may
+  // still re-initialise on its first ProcessStream call (EngineConfig::
+  // reinit_on_first_capture) and render audio received earlier is lost.
+  int seen_capture;
+  int pad_[3];
   ThreeBandState capture_bands; // AudioBuffer's SplittingFilter (48 kHz only)
   ThreeBandState render_bands;
   NsState ns;
@@ -259,6 +270,18 @@ struct EngineConfig {
   float ns_minimum_attenuating_gain;
   int ns_use_attenuation_adjustment;
   int capture_output_used;
+  // ComfortNoiseGenerator::noise_floor_ = GetNoiseFloorFactor(-96.03406 dBFS)
+  // (comfort_noise_generator.cc:41-45), evaluated on the host.
+  float cng_noise_floor;
+  // AudioProcessingImpl re-runs InitializeLocked() on the first ProcessStream
+  // call when the capture format differs from the constructor's default
+  // (16 kHz mono, audio_processing_impl.h:415-418) or when a submodule that
+  // SubmoduleStates tracks by pointer (noise suppressor, AGC2) was created by the
+  // constructor's own InitializeLocked() after UpdateActiveSubmoduleStates() ran
+  // (audio_processing_impl.cc:558-559,894-925,1874-1881).  That rebuilds
+  // EchoCanceller3, so render frames queued before the first capture frame are
+  // dropped.  Reproduced because it changes the output of the first frames.
+  int reinit_on_first_capture;
 };
 
 }  // namespace wap
