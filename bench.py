@@ -3,15 +3,17 @@
 
 One "step" = one 10 ms tick of the hot path over all S call legs of this GPU
 (ProcessReverseStream + set_stream_delay_ms(0) + ProcessStream per leg, i.e. one
-wap_process_streams call = one k_tick launch).  metric = legs that can be served
+wap_process_streams call = k_front + k_delay + k_echo).  metric = legs that can be served
 in real time = S * 10 ms / tick time, summed over GPUs (legs shard across GPUs
 with no collective: "scaling": "weak").
 
   value : device-resident timing (int16 frames already in HBM, wap_process_streams_device)
   e2e   : same metric through the host-buffer C ABI (wap_process_streams), H2D of the
           render+capture frames and D2H of the output inside the timed region
-  roofline : algorithmic bytes (SURVEY.md 8(d) byte model, wap_engine_algorithmic_bytes_per_frame)
-             * S / tick time against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline : for the dominant kernel of the tick: its algorithmic bytes (SURVEY.md 8(d) byte
+             model split per kernel) * S / its launch duration (CUDA events around each kernel
+             on the engine's stream) against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json); "whole_tick" gives the same for all three kernels together
   cpu_baseline : the compiled reference (oracle/_ref) on the host cores, one
              AudioProcessing instance per leg, bounded sample
 
@@ -247,6 +249,24 @@ def run_b200(a):
     sampler.stop_flag = True
     sampler.join()
 
+    # ---- per-kernel durations (CUDA events on the engine's stream around each of the three
+    # tick kernels, live, separate from the throughput loop above so it is not perturbed)
+    kt_ticks = max(10, min(a.steps, 50))
+    L.wap_engine_enable_kernel_timing(eng.h, True)
+    for _ in range(kt_ticks):
+        tick_device(t); t += 1
+    barrier()
+    kms = (C.c_double * 3)()
+    n_timed = L.wap_engine_read_kernel_timing(eng.h, kms)
+    kbytes = (C.c_double * 3)()
+    L.wap_engine_algorithmic_bytes_per_kernel(eng.h, kbytes)
+    L.wap_engine_enable_kernel_timing(eng.h, False)
+    kernels = []
+    for name, m, bts in zip(("k_front", "k_delay", "k_echo"), kms, kbytes):
+        per = m / max(1, n_timed)
+        kernels.append({"name": name, "ms_per_launch": per, "algorithmic_bytes_per_leg_frame": bts,
+                        "achieved_gbs": (bts * S / (per * 1e-3) / 1e9) if per > 0 else 0.0})
+
     # ---- end to end through the host-buffer ABI (pinned host frames in, result out)
     h_r = render.cpu().pin_memory().numpy()
     h_c = capture.cpu().pin_memory().numpy()
@@ -278,7 +298,9 @@ def run_b200(a):
     e2e_value = total_legs * 10.0 / (e2e_ms / e2e_steps)
     alg = L.wap_engine_algorithmic_bytes_per_frame(eng.h)
     peak, peak_src = peaks()
-    achieved = alg * S / (ms_step * 1e-3) / 1e9
+    dom = max(kernels, key=lambda k: k["ms_per_launch"])   # the dominant kernel of a tick
+    achieved = dom["achieved_gbs"]
+    whole_tick = alg * S / (ms_step * 1e-3) / 1e9
     state_bytes = L.wap_engine_state_bytes_per_stream(eng.h)
     eng.close()
     if rank == 0:
@@ -297,8 +319,12 @@ def run_b200(a):
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "k_tick", "algorithmic_bytes_per_leg_frame": alg,
-                             "frac_of_nominal_8TBs": achieved / 8000.0}}
+                             "kernel": dom["name"],
+                             "algorithmic_bytes_per_leg_frame": dom["algorithmic_bytes_per_leg_frame"],
+                             "ms_per_launch": dom["ms_per_launch"],
+                             "whole_tick": {"algorithmic_bytes_per_leg_frame": alg, "achieved": whole_tick,
+                                            "frac": whole_tick / peak, "frac_of_nominal_8TBs": whole_tick / 8000.0},
+                             "kernels": kernels}}
         if not a.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_reference(a, a.cpu_seconds)

@@ -193,6 +193,12 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
 WapError wap_process_streams_device(WapEngine* engine, WapAudioProcessing* const* handles, int32_t n,
                                     const void* d_render, const void* d_capture, void* d_out,
                                     WapSampleFormat fmt);
+/* One tick is three kernels (k_front, k_delay, k_echo).  While kernel timing is enabled
+ * every tick records CUDA events around them on the engine's stream (and waits), so a
+ * bench can attribute time and algorithmic bytes per kernel; out arrays have 3 entries. */
+WapError wap_engine_enable_kernel_timing(WapEngine* engine, bool on);
+int64_t wap_engine_read_kernel_timing(const WapEngine* engine, double* out_ms);
+void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* engine, double* out_bytes);
 WapError wap_engine_synchronize(WapEngine* engine);
 /* CUDA stream the engine launches on (cudaStream_t), for event timing. */
 void* wap_engine_cuda_stream(WapEngine* engine);

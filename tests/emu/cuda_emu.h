@@ -228,6 +228,11 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)1; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 #define cudaStreamNonBlocking 1
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }

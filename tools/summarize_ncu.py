@@ -47,7 +47,7 @@ def main(tag, out):
                              capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         h, units = rows[0], rows[1]
-        lines += ["## k_tick, ncu --set full (per launch)", ""]
+        lines += ["## tick kernels, ncu --set full (per launch)", ""]
         for r in rows[2:]:
             lines.append("launch id %s: %s" % (r[0], r[h.index("Kernel Name")][:50]))
             for w in WANT:

@@ -12,6 +12,12 @@
 // then capture frame" (and for the single-leg entry points, whose queued render
 // frames are drained in front of the capture frame) that is the same sequence of
 // BufferRender / ProcessCapture block calls.
+//
+// A tick runs as three kernels: k_front (one thread per leg: frame -> block
+// slicing, the serial IIRs, RenderDelayBuffer::Insert bookkeeping), k_delay (one
+// warp per leg: delay estimation for all capture blocks of the tick -- nothing in
+// it depends on the echo remover) and k_echo (one warp per leg: render FFTs, NS,
+// echo remover, output).  TickScratch carries the per-block hand-over.
 #pragma once
 
 #include "dsp_aec3_common.cuh"
@@ -39,27 +45,6 @@ WAP_DEV void aec3_unstage_scalars(Aec3State& a, const AecScratch& sc) {
   __syncwarp();
 }
 
-// FrameBlocker::InsertSubFrameAndExtractBlock: block = buffered samples + the
-// head of the sub-frame; the tail of the sub-frame becomes the new buffer.
-WAP_DEV void blocker_insert_and_extract(float* buffer, int* len, const float* sub_frame, float* block) {
-  const int lane = lane_id();
-  const int n = *len;
-  const int samples_to_block = kBlock - n;
-  __syncwarp();
-  for (int i = lane; i < kBlock; i += 32) block[i] = i < n ? buffer[i] : sub_frame[i - n];
-  __syncwarp();
-  for (int i = lane; i < kSubFrame - samples_to_block; i += 32) buffer[i] = sub_frame[samples_to_block + i];
-  __syncwarp();
-  if (lane == 0) *len = kSubFrame - samples_to_block;
-  __syncwarp();
-}
-// FrameBlocker::ExtractBlock
-WAP_DEV void blocker_extract(const float* buffer, int* len, float* block) {
-  for (int i = lane_id(); i < kBlock; i += 32) block[i] = buffer[i];
-  __syncwarp();
-  if (lane_id() == 0) *len = 0;
-  __syncwarp();
-}
 // BlockFramer::InsertBlockAndExtractSubFrame
 WAP_DEV void framer_insert_and_extract(float* buffer, int* len, const float* block, float* sub_frame) {
   const int lane = lane_id();
@@ -81,37 +66,22 @@ WAP_DEV void framer_insert(float* buffer, int* len, const float* block) {
   __syncwarp();
 }
 
-// EmptyRenderQueue for one queued render frame (band 0, 160 samples).
-WAP_DEV void aec3_buffer_render_frame(Aec3State& a, const EngineConfig& cfg, const float* band0, AecScratch& sc) {
-  aec3_stage_scalars(a, sc);
-  for (int sub = 0; sub < 2; ++sub) {
-    blocker_insert_and_extract(a.render_blocker, &sc.s.render_blocker_len, band0 + sub * kSubFrame, sc.x);
-    aec3_buffer_render_block(a, sc);
-  }
-  if (sc.s.render_blocker_len == kBlock) {
-    blocker_extract(a.render_blocker, &sc.s.render_blocker_len, sc.x);
-    aec3_buffer_render_block(a, sc);
-  }
-  aec3_unstage_scalars(a, sc);
-}
-
-// EchoCanceller3::AnalyzeCapture: microphone saturation over the full-band frame.
-WAP_DEV void aec3_analyze_capture(Aec3State& a, const float* full, int n) {
-  int sat = 0;
-  for (int i = lane_id(); i < n; i += 32) sat |= (full[i] >= 32700.0f || full[i] <= -32700.0f) ? 1 : 0;
-  sat = warp_or(sat);
-  if (lane_id() == 0) a.s.saturated_microphone_signal = sat ? 1 : 0;
-  __syncwarp();
-}
-
-// BlockProcessorImpl::ProcessCapture for the capture block in sc.y (in place).
-WAP_DEV void aec3_process_capture_block(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, bool echo_path_gain_change) {
+// ---------------------------------------------------------------- k_delay
+// BlockProcessorImpl::ProcessCapture up to (not including) the echo remover, for
+// capture block b of this tick: start-up gating, over/under-run handling, delay
+// estimation and render-buffer alignment.  Writes the hand-over record for k_echo.
+WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int b) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
+  CaptureBlockRec& rec = ts.crec[b];
   __syncwarp();
-  if (!s.render_properly_started) return;  // no render data yet: capture passes through
+  if (!s.render_properly_started) {  // no render data yet: capture passes through
+    if (lane == 0) rec.process = 0;
+    return;
+  }
   const bool first_capture = !s.capture_properly_started;
   const bool render_overrun = s.render_event == kEventRenderOverrun;
+  if (lane < kSubBlock) sc.ds[lane] = ts.cap_ds[b][lane];
   __syncwarp();
   if (first_capture) {
     if (lane == 0) {
@@ -121,12 +91,9 @@ WAP_DEV void aec3_process_capture_block(Aec3State& a, const EngineConfig& cfg, A
     __syncwarp();
     delay_controller_reset(a, sc, true);
   }
-  EchoPathVariability v;
-  v.gain_change = echo_path_gain_change ? 1 : 0;
-  v.delay_change = kDelayAdjNone;
-  v.clock_drift = 0;
+  int delay_change = kDelayAdjNone;
   if (render_overrun) {
-    v.delay_change = kDelayAdjBufferFlush;
+    delay_change = kDelayAdjBufferFlush;
     delay_controller_reset(a, sc, true);
   }
   __syncwarp();
@@ -142,50 +109,94 @@ WAP_DEV void aec3_process_capture_block(Aec3State& a, const EngineConfig& cfg, A
     s.bp_has_estimated_delay = s.ctl_has_delay;
     s.bp_est_delay = s.ctl_delay;
     s.bp_est_quality = s.ctl_delay_quality;
-    sc.ired[0] = 0;
-    if (s.ctl_has_delay) sc.ired[0] = rdb_align_from_delay(s, s.ctl_delay) ? 1 : 0;
+    if (s.ctl_has_delay && rdb_align_from_delay(s, s.ctl_delay)) delay_change = kDelayAdjNewDetectedDelay;
+    rec.process = 1;
+    rec.blocks_read = s.blocks_read;
+    rec.spectra_read = s.spectra_read;
+    rec.gain_change = 0;  // capture_.echo_path_gain_change: analog level / playout volume changes only
+    rec.delay_change = delay_change;
+    rec.clock_drift = s.cd_level != 0;
+    rec.est_has = s.bp_has_estimated_delay;
+    rec.est_delay = s.bp_est_delay;
   }
   __syncwarp();
-  if (sc.ired[0]) v.delay_change = kDelayAdjNewDetectedDelay;
-  v.clock_drift = s.cd_level != 0;
-  __syncwarp();
-  echo_remover_process_capture(a, cfg, sc, v, s.saturated_microphone_signal != 0, s.bp_has_estimated_delay,
-                               s.bp_est_delay);
 }
 
-// EchoCanceller3::ProcessCapture for one capture frame (band 0 in place).
-// `delay_ms` >= 0 : AudioProcessingImpl forwarded set_stream_delay_ms() through
-// SetAudioBufferDelay (audio_processing_impl.cc:1409-1411).
-WAP_DEV void aec3_process_capture_frame(Aec3State& a, const EngineConfig& cfg, float* band0, int delay_ms,
-                                        AecScratch& sc) {
+// All capture blocks of this tick.
+WAP_DEV void aec3_delay_frame(Aec3State& a, TickScratch& ts, AecScratch& sc) {
+  const int nb = ts.n_capture_blocks;
+  if (nb == 0) return;
   aec3_stage_scalars(a, sc);
-  if (delay_ms >= 0) {
-    if (lane_id() == 0) rdb_set_audio_buffer_delay(sc.s, delay_ms);
+  for (int b = 0; b < nb; ++b) aec3_delay_block(a, sc, ts, b);
+  aec3_unstage_scalars(a, sc);
+}
+
+// ---------------------------------------------------------------- k_echo
+// Render blocks of this tick: vector half of the insert.
+WAP_DEV void aec3_echo_render(Aec3State& a, const TickScratch& ts, AecScratch& sc) {
+  const int lane = lane_id();
+  for (int r = 0; r < ts.n_render_blocks; ++r) {
     __syncwarp();
+    for (int i = lane; i < kBlock; i += 32) sc.x[i] = ts.render_blocks[r][i];
+    aec3_render_insert_vector(a, sc, ts.rins[r]);
   }
+}
+
+// EchoRemover for capture block b (sc.y in/out) against the render-buffer view k_delay recorded.
+WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const TickScratch& ts, int b) {
+  const int lane = lane_id();
+  __syncwarp();
+  for (int i = lane; i < kBlock; i += 32) sc.y[i] = ts.capture_blocks[b][i];
+  const CaptureBlockRec& rec = ts.crec[b];
+  if (!rec.process) {
+    __syncwarp();
+    return;
+  }
+  if (lane == 0) {
+    sc.s.blocks_read = rec.blocks_read;
+    sc.s.spectra_read = rec.spectra_read;
+  }
+  __syncwarp();
+  EchoPathVariability v;
+  v.gain_change = rec.gain_change;
+  v.delay_change = rec.delay_change;
+  v.clock_drift = rec.clock_drift;
+  echo_remover_process_capture(a, cfg, sc, v, sc.s.saturated_microphone_signal != 0, rec.est_has, rec.est_delay);
+}
+
+// EchoCanceller3::ProcessCapture for one capture frame (band 0 in place): the echo
+// remover on the 2-3 blocks k_front sliced, BlockFramer back into the frame.
+WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* band0, const TickScratch& ts,
+                               AecScratch& sc) {
+  aec3_stage_scalars(a, sc);
+  // The staged read indices are the ones after the last block; blocks see their own.
+  const int final_blocks_read = sc.s.blocks_read, final_spectra_read = sc.s.spectra_read;
+  __syncwarp();
   for (int sub = 0; sub < 2; ++sub) {
-    float* sub_frame = band0 + sub * kSubFrame;
-    blocker_insert_and_extract(a.capture_blocker, &sc.s.capture_blocker_len, sub_frame, sc.y);
-    aec3_process_capture_block(a, cfg, sc, false);
-    framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, sub_frame);
+    aec3_echo_block(a, cfg, sc, ts, sub);
+    framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, band0 + sub * kSubFrame);
   }
-  if (sc.s.capture_blocker_len == kBlock) {
-    blocker_extract(a.capture_blocker, &sc.s.capture_blocker_len, sc.y);
-    aec3_process_capture_block(a, cfg, sc, false);
+  if (ts.n_capture_blocks == 3) {
+    aec3_echo_block(a, cfg, sc, ts, 2);
     framer_insert(a.output_framer, &sc.s.output_framer_len, sc.y);
   }
+  __syncwarp();
   // ApmStatsReporter::UpdateStatistics (audio_processing_impl.cc:2322-2328): a
   // one-slot queue -- while the slot is full (nobody called GetStatistics) the
   // newer statistics are discarded.
-  if (lane_id() == 0 && !sc.s.stats_slot_full) {
+  if (lane_id() == 0) {
     Aec3Scalars& s = sc.s;
-    s.stats_slot_full = 1;
-    s.stats_erl_time_domain = s.erl_time_domain;
-    s.stats_erle_log2 = s.fb_erle_time_domain_log2;
-    // BlockProcessorImpl::GetMetrics reports RenderDelayBuffer::Delay() == ComputeDelay()
-    // (render_delay_buffer.cc:57), not the aligned delay_.
-    s.stats_has_delay = 1;
-    s.stats_delay_blocks = rdb_compute_delay(s);
+    s.blocks_read = final_blocks_read;
+    s.spectra_read = final_spectra_read;
+    if (!s.stats_slot_full) {
+      s.stats_slot_full = 1;
+      s.stats_erl_time_domain = s.erl_time_domain;
+      s.stats_erle_log2 = s.fb_erle_time_domain_log2;
+      // BlockProcessorImpl::GetMetrics reports RenderDelayBuffer::Delay() == ComputeDelay()
+      // (render_delay_buffer.cc:57), not the aligned delay_.
+      s.stats_has_delay = 1;
+      s.stats_delay_blocks = rdb_compute_delay(s);
+    }
   }
   aec3_unstage_scalars(a, sc);
 }

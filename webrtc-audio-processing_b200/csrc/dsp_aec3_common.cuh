@@ -73,13 +73,21 @@ struct EchoPathVariability {  // echo_path_variability.h:16-29
   int gain_change, delay_change, clock_drift;
 };
 
-// Shared-memory scratch of one warp for the AEC3 stage.  The matched-filter
-// buffers and the echo-remover vectors are never live at the same time.
+// Shared-memory scratch of one warp for the AEC3 stages.  The matched-filter
+// buffers (k_delay) and the echo-remover vectors (k_echo) are never live at the
+// same time; k_delay only allocates up to the end of `mf`.
+constexpr int kMfWin = kMfLen + kSubBlock - 1;   // 527 low-rate samples one filter sees in a block
+constexpr int kMfWinPad = 544;                   // second window starts 16 banks after the first
 struct AecMfScratch {
-  float xw[2080];          // linearised low-rate window: xw[j] = low_rate[(read + j) % size]
-  float h[kMfLen];         // matched filter being processed
+  // Linearised low-rate windows: xp[w] = low_rate[(read + n*384 + w) % size], w < 527, so that
+  // tap t of capture sample i is xp[15 - i + t].  The pair path keeps two filters' windows
+  // (the second at +560 floats: other half of the banks); the one-filter paths use the first.
+  float xp[2 * kMfWinPad + 32];
+  float h[kMfLen];         // matched filter being processed (one-filter paths)
   float inst_err[kAccErrLen];  // MatchedFilter::instantaneous_accumulated_error_
   float q[kAccErrLen];     // per-4-tap partial sums / prefix sums of the accumulated-error core
+  float x2chain[2][32];    // pair path: the 31 distinct x*x chains of a block, per filter
+  float x2sum[2][kSubBlock];   // pair path: x2_sum of every capture sample, per filter
   float err_sum[kNumMatchedFilters];
   int updated[kNumMatchedFilters];
   int peak[kNumMatchedFilters];
@@ -99,17 +107,18 @@ struct AecRemoverScratch {
 };
 struct AecScratch {
   Aec3Scalars s;           // staged copy of Aec3State::s
-  float fftA[128];         // lanes 0-15
-  float fftB[128];         // lanes 16-31
-  float x[kBlock];         // render block being inserted / GetBlock(0)
-  float y[kBlock];         // capture block (in / out)
-  float ds[kSubBlock];     // decimated sub-block
+  float ds[kSubBlock];     // decimated capture sub-block
   float red[32];           // reduction / broadcast exchange
   int ired[32];
   union {
     AecMfScratch mf;
     AecRemoverScratch rm;
   };
+  // k_echo only:
+  float fftA[128];         // lanes 0-15
+  float fftB[128];         // lanes 16-31
+  float x[kBlock];         // render block being inserted / GetBlock(0)
+  float y[kBlock];         // capture block (in / out)
 };
 
 WAP_DEV int ring_inc(int i, int size) { return i < size - 1 ? i + 1 : 0; }

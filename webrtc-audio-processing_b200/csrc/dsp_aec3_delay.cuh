@@ -23,16 +23,16 @@ namespace wap {
 
 constexpr float kMfX2SumThreshold = 512.f * ec3::kMfExcitationLimit * ec3::kMfExcitationLimit;
 
-// Copies the part of the low-rate ring the five filters can see into shared
-// memory, linearised from the read index.
-WAP_DEV void mf_stage_window(const Aec3State& a, AecScratch& sc) {
-  const int read = sc.s.lr_read;
-  for (int j = lane_id(); j < 4 * kMfShift + kSubBlock + kMfLen; j += 32) {
-    int r = read + j;
+// Copies the part of the low-rate ring filter n sees during this block into shared
+// memory, linearised: dst[w] = low_rate[(read + n*shift + w) % size], w < 527.
+WAP_DEV void mf_stage_window(const Aec3State& a, const AecScratch& sc, int n, float* dst) {
+  int start = sc.s.lr_read + n * kMfShift;
+  if (start >= kLowRateSize) start -= kLowRateSize;
+  for (int w = lane_id(); w < kMfWin; w += 32) {
+    int r = start + w;
     if (r >= kLowRateSize) r -= kLowRateSize;
-    sc.mf.xw[j] = a.low_rate[r];
+    dst[w] = a.low_rate[r];
   }
-  __syncwarp();
 }
 
 // hsum over the 8 "c" values of one accumulator group in the order of hsum_ab
@@ -47,7 +47,8 @@ WAP_DEV float mf_hsum16(float acc) {
 }
 
 // One matched filter, 16 decimated capture samples, non-accumulating core
-// (matched_filter_avx2.cc:151-270).  h lives in sc.mf.h.
+// (matched_filter_avx2.cc:151-270), general version: handles the ring wrap inside the
+// window (chunked chains + scalar tails).  h lives in sc.mf.h, the window in sc.mf.xp.
 WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
   const int lane = lane_id();
   const int half = lane >> 4, L = lane & 15;
@@ -55,10 +56,9 @@ WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out
   float error_sum = 0.f;
   int updated = 0;
   for (int i = 0; i < kSubBlock; ++i) {
-    const int base = n * kMfShift + kSubBlock - 1 - i;  // window tap 0 in xw
-    int x_start = sc.s.lr_read + base;                   // position in the reference's ring
+    int x_start = sc.s.lr_read + n * kMfShift + kSubBlock - 1 - i;  // position in the reference's ring
     if (x_start >= kLowRateSize) x_start -= kLowRateSize;
-    const float* x = sc.mf.xw + base;
+    const float* x = sc.mf.xp + (kSubBlock - 1 - i);                // tap 0 of sample i
     const int chunk1 = imin(kMfLen, kLowRateSize - x_start);
     const int chunk2 = kMfLen - chunk1;
     const int v1 = chunk1 >> 4, v2 = chunk2 >> 4;
@@ -124,8 +124,7 @@ WAP_DEV void mf_core_accumulated_error(AecScratch& sc, int n, const float* y, fl
   float error_sum = 0.f;
   int updated = 0;
   for (int i = 0; i < kSubBlock; ++i) {
-    const int base = n * kMfShift + kSubBlock - 1 - i;
-    const float* x = sc.mf.xw + base;
+    const float* x = sc.mf.xp + (kSubBlock - 1 - i);
     // x*x: 16 fused chains over every 16th tap (lanes 0-15).
     float acc = 0.f;
     if (lane < 16) {
@@ -175,6 +174,105 @@ WAP_DEV void mf_core_accumulated_error(AecScratch& sc, int n, const float* y, fl
   }
   *error_sum_out = error_sum;
   *updated_out = updated;
+}
+
+// Two matched filters side by side, one per half-warp, for blocks in which neither
+// window crosses the end of the reference's ring (chunk1 == 512 for all 16 capture
+// samples, no scalar tails): the non-accumulating core of matched_filter_avx2.cc:
+// 151-270 with
+//  * the 32 taps of chain L (t = L + 16k) and their h in REGISTERS of lane L, so the
+//    NLMS update reuses the x values the dot product loaded and h never touches
+//    shared memory;
+//  * the x*x chains computed once per block instead of once per sample: chain j of
+//    sample i runs over x[s - i + j + 16k], k = 0..31, i.e. it is chain 0 of "sample
+//    i - j".  The block therefore has only 31 distinct chains (E[m], m = -15..15, each
+//    the same fused 32-term recursion the reference evaluates), and x2_sum of sample i
+//    is the reference's hsum tree over E[i - j].
+// nA / nB: filter indices (nB < 0: second half idle).
+WAP_DEV void mf_pair_fast(Aec3State& a, AecScratch& sc, int nA, int nB, const float* y) {
+  const int lane = lane_id();
+  const int hw = lane >> 4, L = lane & 15;
+  const int n = hw ? nB : nA;
+  const bool on = n >= 0;
+  const int nn = on ? n : nA;
+  float* xp = sc.mf.xp + hw * (kMfWinPad + 16);
+  __syncwarp();
+  mf_stage_window(a, sc, nA, sc.mf.xp);
+  if (nB >= 0) mf_stage_window(a, sc, nB, sc.mf.xp + kMfWinPad + 16);
+  float h[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) h[k] = a.mf_h[nn][L + 16 * k];
+  __syncwarp();
+  // ---- the 31 x*x chains of this block: E[15 - L] = chain L of sample 0, E[15 + L] = chain 0 of sample L
+  {
+    float c_init = 0.f, c_new = 0.f;
+    const float* x0 = xp + (kSubBlock - 1) + L;  // tap L of sample 0
+    const float* x1 = xp + (kSubBlock - 1) - L;  // tap 0 of sample L
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float u = x0[16 * k], v = x1[16 * k];
+      c_init = fmaf(u, u, c_init);
+      c_new = fmaf(v, v, c_new);
+    }
+    sc.mf.x2chain[hw][15 - L] = c_init;
+    if (L > 0) sc.mf.x2chain[hw][15 + L] = c_new;
+  }
+  __syncwarp();
+  {
+    // x2_sum of sample i = L: c_j = chain_j + chain_{j+8}; ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7))  (hsum_ab)
+    const float* E = sc.mf.x2chain[hw] + 15 + L;  // E[-j] = chain j of sample L
+    const float c0 = E[0] + E[-8], c1 = E[-1] + E[-9], c2 = E[-2] + E[-10], c3 = E[-3] + E[-11];
+    const float c4 = E[-4] + E[-12], c5 = E[-5] + E[-13], c6 = E[-6] + E[-14], c7 = E[-7] + E[-15];
+    sc.mf.x2sum[hw][L] = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+  }
+  __syncwarp();
+  float error_sum = 0.f;
+  int updated = 0;
+#pragma unroll 1
+  for (int i = 0; i < kSubBlock; ++i) {
+    const float* x = xp + (kSubBlock - 1 - i) + L;
+    float xv[32];
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      xv[k] = x[16 * k];
+      acc = fmaf(h[k], xv[k], acc);
+    }
+    const float s = mf_hsum16(acc);     // uniform within the half-warp; reference: s = 0 + hsum
+    const float x2_sum = sc.mf.x2sum[hw][i];
+    const float yi = y[i];
+    const float e = yi - s;
+    const bool saturation = yi >= 32000.f || yi <= -32000.f;
+    error_sum += e * e;
+    if (on && x2_sum > kMfX2SumThreshold && !saturation) {
+      const float alpha = ec3::kMfSmoothing * e / x2_sum;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) h[k] = fmaf(xv[k], alpha, h[k]);
+      updated = 1;
+    }
+  }
+  // ---- write back, MaxSquarePeakIndex: tap parity == lane parity (t = L + 16k)
+  float best = -1.f;
+  int bi = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (on) a.mf_h[nn][L + 16 * k] = h[k];
+    const float v = h[k] * h[k];
+    if (v > best) { best = v; bi = L + 16 * k; }
+  }
+  for (int m = 2; m < 16; m <<= 1) {
+    const float ov = __shfl_xor_sync(WAP_FULL, best, m);
+    const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const float odd_v = __shfl_xor_sync(WAP_FULL, best, 1);
+  const int odd_i = __shfl_xor_sync(WAP_FULL, bi, 1);
+  if (on && L == 0) {  // lane with the even-tap maximum; odd wins only when strictly larger
+    sc.mf.err_sum[n] = error_sum;
+    sc.mf.updated[n] = updated;
+    sc.mf.peak[n] = (odd_v > best) ? odd_i : bi;
+  }
+  __syncwarp();
 }
 
 // aec3::MaxSquarePeakIndex (matched_filter.cc:558-591) for a 512-tap filter:
@@ -267,21 +365,35 @@ WAP_DEV void clockdrift_update(Aec3Scalars& s, int delay_estimate) {
   s.cd_history[0] = delay_estimate;
 }
 
-// RenderDelayControllerImpl::GetDelay for the capture block in sc.y.  Leaves the
-// controller's delay_ in sc.s.ctl_{has_delay,delay,delay_quality}.
+// RenderDelayControllerImpl::GetDelay for the decimated capture block in sc.ds
+// (EchoPathDelayEstimator::EstimateDelay's capture decimation ran in k_front).
+// Leaves the controller's delay_ in sc.s.ctl_{has_delay,delay,delay_quality}.
 WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
   __syncwarp();
-  // ---- EchoPathDelayEstimator::EstimateDelay: capture decimation
-  decimate_block(sc.y, sc.fftA, sc.ds, a.capture_decimator);
   const float* y = sc.ds;
   // ---- MatchedFilter::Update
-  mf_stage_window(a, sc);
   float error_sum_anchor = 0.f;
   for (int k = 0; k < kSubBlock; ++k) error_sum_anchor += y[k] * y[k];
   const int last_best = s.mf_last_detected_best_lag_filter;
+  // Filters whose window does not wrap in the reference's ring during this block (and
+  // that do not need the accumulated-error side output) go through the pair path.
+  int fast[kNumMatchedFilters];
+  int nfast = 0;
+  unsigned slow_mask = 0;
   for (int n = 0; n < kNumMatchedFilters; ++n) {
+    int x_start0 = s.lr_read + n * kMfShift + kSubBlock - 1;
+    if (x_start0 >= kLowRateSize) x_start0 -= kLowRateSize;
+    const bool no_wrap = x_start0 >= kSubBlock - 1 && x_start0 + kMfLen <= kLowRateSize;
+    if (no_wrap && n != last_best) fast[nfast++] = n;
+    else slow_mask |= 1u << n;
+  }
+  for (int p = 0; p < nfast; p += 2) mf_pair_fast(a, sc, fast[p], p + 1 < nfast ? fast[p + 1] : -1, y);
+  for (int n = 0; n < kNumMatchedFilters; ++n) {
+    if (!((slow_mask >> n) & 1u)) continue;
+    __syncwarp();
+    mf_stage_window(a, sc, n, sc.mf.xp);
     for (int t = lane; t < kMfLen; t += 32) sc.mf.h[t] = a.mf_h[n][t];
     __syncwarp();
     float error_sum;

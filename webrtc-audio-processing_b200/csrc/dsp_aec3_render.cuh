@@ -106,60 +106,19 @@ WAP_DEV int rdb_prepare_capture_processing(Aec3Scalars& s) {
   return event;
 }
 
-// Decimator::Decimate (decimator.cc:75-91): 3-section low-pass, 1-section
-// high-pass, keep every 4th sample.  `work` is a 64-float scratch.
-WAP_DEV void decimate_block(const float* in, float* work, float* out16, Biquad* state) {
+// Vector half of RenderDelayBufferImpl::InsertBlock (:387-429) for the block in sc.x:
+// block ring, FFT of [previous block | new block], power spectrum.  The scalar half
+// (indices, events, decimation into the low-rate ring) already ran in k_front, which
+// left the ring positions in `rec`.
+WAP_DEV void aec3_render_insert_vector(Aec3State& a, AecScratch& sc, const RenderInsertRec& rec) {
   const int lane = lane_id();
-  for (int i = lane; i < kBlock; i += 32) work[i] = in[i];
+  const int previous_write = rec.previous_write, bw = rec.blocks_write, sw = rec.spectra_write;
   __syncwarp();
-  biquad_cascade<4>(work, kBlock, kDecimator4, state);
-  if (lane < kSubBlock) out16[lane] = work[lane * kDownSampling];
-  __syncwarp();
-}
-
-// RenderDelayBufferImpl::Insert + InsertBlock (:200-242, :387-429) for the block
-// in sc.x; sets sc.s.render_event the way BlockProcessorImpl::BufferRender does
-// (block_processor.cc:201-216).
-WAP_DEV void aec3_buffer_render_block(Aec3State& a, AecScratch& sc) {
-  const int lane = lane_id();
-  Aec3Scalars& s = sc.s;
-  __syncwarp();
-  // DetectActiveRender (:413-418) is evaluated before the scalars change.
-  const float x_energy = energy_serial(sc.x, kBlock);
-  if (lane == 0) {
-    if (s.has_delay) {
-      if (!s.last_call_was_render) {
-        s.last_call_was_render = 1;
-        s.num_api_calls_in_a_row = 1;
-      } else if (++s.num_api_calls_in_a_row > s.max_observed_jitter) {
-        s.max_observed_jitter = s.num_api_calls_in_a_row;
-      }
-    }
-    sc.ired[0] = s.blocks_write;  // previous_write
-    // IncrementWriteIndices (:455-460)
-    s.lr_write = ring_off(s.lr_write, -kSubBlock, kLowRateSize);
-    s.blocks_write = ring_inc(s.blocks_write, kRingBlocks);
-    s.spectra_write = ring_dec(s.spectra_write, kRingBlocks);
-    // RenderOverrun (:481-483)
-    s.render_event = (s.lr_read == s.lr_write || s.blocks_read == s.blocks_write) ? kEventRenderOverrun : kEventNone;
-    if (!s.render_activity) {
-      s.render_activity_counter +=
-          (x_energy > (ec3::kActiveRenderLimit * ec3::kActiveRenderLimit) * 64.f) ? 1 : 0;
-      s.render_activity = s.render_activity_counter >= 20;
-    }
-  }
-  __syncwarp();
-  const int previous_write = sc.ired[0];
-  const int bw = s.blocks_write, sw = s.spectra_write, lw = s.lr_write;
-  // InsertBlock: block ring, decimated low-rate ring (stored reversed), FFT of
-  // [previous block | new block], power spectrum.
   for (int i = lane; i < kBlock; i += 32) {
     a.blocks[bw][i] = sc.x[i];
     sc.fftA[i] = a.blocks[previous_write][i];
     sc.fftA[kBlock + i] = sc.x[i];
   }
-  decimate_block(sc.x, sc.fftB, sc.ds, a.render_decimator);
-  if (lane < kSubBlock) a.low_rate[lw + lane] = sc.ds[kSubBlock - 1 - lane];
   fft_pair(sc, false, false);
   for (int k = lane; k < kBins; k += 32) {
     float re, im;
@@ -169,11 +128,6 @@ WAP_DEV void aec3_buffer_render_block(Aec3State& a, AecScratch& sc) {
     a.fft_re[sw][k] = re;
     a.fft_im[sw][k] = im;
     a.spectra[sw][k] = power_bin(re, im, k);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    if (s.render_event != kEventNone) rdb_reset(s);
-    s.render_properly_started = 1;
   }
   __syncwarp();
 }

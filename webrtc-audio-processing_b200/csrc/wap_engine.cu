@@ -23,13 +23,30 @@
 
 namespace wap {
 
-__global__ void __launch_bounds__(128) k_tick(TickArgs a, int scratch_floats) {
+// One 10 ms tick = k_front -> (k_delay) -> k_echo on the engine's stream.
+__global__ void __launch_bounds__(128) k_front(TickArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.n) front_leg(a, idx);
+}
+
+__global__ void __launch_bounds__(128, 4) k_delay(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   float* scratch = sm + (size_t)warp * scratch_floats;
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
-    process_stream_tick(a, idx, scratch);
+    delay_stream_tick(a, idx, scratch);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) k_echo(TickArgs a, int scratch_floats) {
+  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float* scratch = sm + (size_t)warp * scratch_floats;
+  for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
+    echo_stream_tick(a, idx, scratch);
     __syncwarp();
   }
 }
@@ -82,7 +99,13 @@ struct WapEngine {
   std::vector<int> last_slots;
   int64_t launches = 0;
   int frame_len = 0;  // samples per frame (all channels)
-  int scratch_floats = 0;
+  int echo_scratch_floats = 0;
+  // optional per-kernel timing (bench roofline): events around the three tick kernels
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double kernel_ms[3] = {0, 0, 0};
+  int64_t timed_ticks = 0;
+  int delay_scratch_floats = 0;
   bool is_default = false;
 };
 
@@ -202,9 +225,30 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   a.fmt = (int)fmt;
   a.cfg = e->cfg;
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * e->scratch_floats * sizeof(float);
-  WAP_LAUNCH(wap::k_tick, grid_for(n), wpb * 32, smem, e->stream, a, e->scratch_floats);
+  const bool timing = e->timing;
+  if (timing) cudaEventRecord(e->ev[0], e->stream);
+  WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
   e->launches++;
+  if (timing) cudaEventRecord(e->ev[1], e->stream);
+  if (e->cfg.aec_enabled && d_capture) {
+    const size_t smem_d = (size_t)wpb * e->delay_scratch_floats * sizeof(float);
+    WAP_LAUNCH(wap::k_delay, grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
+    e->launches++;
+  }
+  if (timing) cudaEventRecord(e->ev[2], e->stream);
+  const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
+  WAP_LAUNCH(wap::k_echo, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  e->launches++;
+  if (timing) {
+    cudaEventRecord(e->ev[3], e->stream);
+    WAP_CUDA(cudaEventSynchronize(e->ev[3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev[k], e->ev[k + 1]);
+      e->kernel_ms[k] += ms;
+    }
+    e->timed_ticks++;
+  }
   WAP_CUDA(cudaGetLastError());
   return WapError::None;
 }
@@ -255,7 +299,8 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->format = fmt;
   e->cfg = cfg;
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
-  e->scratch_floats = wap::warp_scratch_floats(cfg.num_bands);
+  e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
+  e->delay_scratch_floats = wap::delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&e->d_states, (size_t)max_streams * sizeof(StreamState)) == cudaSuccess &&
@@ -266,9 +311,12 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
     ok = cudaMemcpy(e->d_template, tmpl, sizeof(StreamState), cudaMemcpyHostToDevice) == cudaSuccess;
     delete tmpl;
   }
-  const size_t smem = (size_t)4 * e->scratch_floats * sizeof(float);
-  if (ok && smem > 48 * 1024)
-    ok = cudaFuncSetAttribute(wap::k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
+  const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
+  if (ok && smem_e > 48 * 1024)
+    ok = cudaFuncSetAttribute(wap::k_echo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
+  if (ok && smem_d > 48 * 1024)
+    ok = cudaFuncSetAttribute(wap::k_delay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d) == cudaSuccess;
   if (!ok) {
     fprintf(stderr, "[wap_b200] engine allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     wap_engine_destroy(e);
@@ -291,6 +339,7 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_slots);
   cudaFree(e->d_delays);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  for (int k = 0; k < 4; ++k) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -441,6 +490,36 @@ int wapdbg_read_state(const WapAudioProcessing* h, void* out, size_t bytes) {
   return cudaMemcpy(out, &e->d_states[h->slot], bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 size_t wapdbg_state_size(void) { return sizeof(StreamState); }
+
+// Per-kernel timing for the roofline report: while enabled every tick records CUDA
+// events around k_front / k_delay / k_echo on the engine's stream and waits for them.
+WapError wap_engine_enable_kernel_timing(WapEngine* e, bool on) {
+  if (!e) return WapError::NullPointer;
+  WAP_CUDA(cudaSetDevice(e->device));
+  if (on && !e->ev[0])
+    for (int k = 0; k < 4; ++k) WAP_CUDA(cudaEventCreate(&e->ev[k]));
+  e->timing = on;
+  for (int k = 0; k < 3; ++k) e->kernel_ms[k] = 0;
+  e->timed_ticks = 0;
+  return WapError::None;
+}
+// out_ms[3] = accumulated milliseconds of {k_front, k_delay, k_echo}; returns the number of timed ticks.
+int64_t wap_engine_read_kernel_timing(const WapEngine* e, double* out_ms) {
+  if (!e || !out_ms) return 0;
+  for (int k = 0; k < 3; ++k) out_ms[k] = e->kernel_ms[k];
+  return e->timed_ticks;
+}
+// Algorithmic HBM bytes per leg-frame attributed to each tick kernel (SURVEY.md 8(d) groups):
+// k_front: audio in + HPF state; k_delay: the "delay estimation" group; k_echo: the rest.
+void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* e, double* out_bytes) {
+  if (!e || !out_bytes) return;
+  const double total = wap_engine_algorithmic_bytes_per_frame(e);
+  const double front = e->frame_len * 4.0 * (e->cfg.aec_enabled ? 2 : 1) + (e->cfg.hpf_enabled ? 96.0 : 0.0);
+  const double delay = e->cfg.aec_enabled ? 2.5 * 40256.0 : 0.0;
+  out_bytes[0] = front;
+  out_bytes[1] = delay;
+  out_bytes[2] = total - front - delay;
+}
 
 double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (!e) return 0.0;

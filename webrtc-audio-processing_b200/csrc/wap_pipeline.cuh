@@ -1,51 +1,28 @@
 // Per-stream frame pipeline: the body of AudioProcessingImpl::
 // ProcessRenderStreamLocked / ProcessCaptureStreamLocked for the enabled
-// submodules (reference audio_processing_impl.cc:1264-1561,1653-1687), run by
-// one warp per stream.
+// submodules (reference audio_processing_impl.cc:1264-1561,1653-1687): the
+// warp-per-leg bodies of k_delay and k_echo (k_front's body is dsp_front.cuh).
 #pragma once
 
+#include <stddef.h>
+
 #include "dsp_aec3.cuh"
+#include "dsp_front.cuh"
 #include "dsp_filters.cuh"
 #include "dsp_ns.cuh"
 #include "wap_dev.cuh"
 #include "wap_state.h"
+#include "wap_tick.h"
 
 namespace wap {
 
-struct TickArgs {
-  StreamState* states;
-  const int* slots;       // [n] arena slot of each stream, or nullptr => slot i
-  const int* delays_ms;   // [n] per-stream set_stream_delay_ms value (-1 unset) or nullptr
-  int uniform_delay_ms;   // used when delays_ms == nullptr (-1 unset)
-  int n;
-  const void* render;     // [n][frame] or nullptr
-  const void* capture;    // [n][frame] or nullptr
-  void* out;              // [n][frame]
-  int fmt;                // 0 = int16, 1 = float [-1,1]
-  EngineConfig cfg;
-};
-
 // Shared-memory footprint of one warp, in floats.
-WAP_DEV constexpr int scratch_floats_frame(int bands) { return 2 * kFrame * bands; }
 constexpr int kScratchFloatsDsp =
     (int)((sizeof(NsScratch) > sizeof(AecScratch) ? sizeof(NsScratch) : sizeof(AecScratch)) / sizeof(float)) + 4;
-inline int warp_scratch_floats(int bands) { return 2 * kFrame * bands + kScratchFloatsDsp; }
-
-WAP_DEV void load_frame(const void* src, size_t stream, int len, int fmt, float* dst) {
-  const int lane = lane_id();
-  if (fmt == 0) {
-    const int16_t* p = reinterpret_cast<const int16_t*>(src) + stream * len;
-    for (int i = lane; i < len; i += 32) dst[i] = (float)p[i];  // S16ToFloatS16
-  } else {
-    const float* p = reinterpret_cast<const float*>(src) + stream * len;
-    for (int i = lane; i < len; i += 32) {  // FloatToFloatS16 (audio_util.h:65-69)
-      float v = p[i];
-      v = fminr(v, 1.f);
-      v = fmaxr(v, -1.f);
-      dst[i] = v * 32768.f;
-    }
-  }
-  __syncwarp();
+// k_echo: two frame buffers + the DSP scratch; k_delay: the AEC3 scratch only.
+inline int echo_scratch_floats(int bands) { return 2 * kFrame * bands + kScratchFloatsDsp; }
+inline int delay_scratch_floats() {
+  return (int)((offsetof(AecScratch, mf) + sizeof(AecMfScratch)) / sizeof(float)) + 4;
 }
 
 WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float* src) {
@@ -69,44 +46,39 @@ WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float
   }
 }
 
-// One 10 ms tick of one stream.
-WAP_DEV void process_stream_tick(const TickArgs& a, int idx, float* scratch) {
+// k_delay body: AEC3 delay estimation of one leg for the capture blocks of this tick.
+WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
+  const int slot = a.slots ? a.slots[idx] : idx;
+  StreamState& st = a.states[slot];
+  AecScratch& sc = *reinterpret_cast<AecScratch*>(scratch);
+  aec3_delay_frame(st.aec, st.tick, sc);
+}
+
+// k_echo body: everything after the front end for one leg (reference
+// audio_processing_impl.cc:1359-1448 for the enabled submodules).
+WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   const EngineConfig& cfg = a.cfg;
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
+  const TickScratch& ts = st.tick;
   float* full = scratch;
   float* bands = (B == 1) ? full : scratch + flen;
   void* dsp = scratch + 2 * flen;
   NsScratch& ns_sc = *reinterpret_cast<NsScratch*>(dsp);
   AecScratch& aec_sc = *reinterpret_cast<AecScratch*>(dsp);
 
-  // ---------------- render side (ProcessReverseStream)
-  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
-  __syncwarp();
-  if (a.render && cfg.aec_enabled && render_live) {
-    load_frame(a.render, idx, flen, a.fmt, full);
-    if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.render_bands.analysis);
-    aec3_buffer_render_frame(st.aec, cfg, bands, aec_sc);
-  }
+  // ---------------- render side: ring / FFT / spectrum writes for the blocks k_front sliced
+  if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc);
   if (!a.capture) return;
 
-  // ---------------- capture side (ProcessStream)
-  if (lane_id() == 0) st.seen_capture = 1;
-  load_frame(a.capture, idx, flen, a.fmt, full);
-  if (cfg.hpf_enabled) {
-    biquad_cascade<3>(full, flen, B == 3 ? kHpf48k : kHpf16k, st.hpf);
-  }
-  if (cfg.aec_enabled) {
-    aec3_analyze_capture(st.aec, full, flen);
-  }
+  // ---------------- capture side (the frame is already high-pass filtered)
+  for (int i = lane_id(); i < flen; i += 32) full[i] = ts.capture_frame[i];
+  __syncwarp();
   if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
-  if (cfg.aec_enabled) {
-    const int d = a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms;
-    aec3_process_capture_frame(st.aec, cfg, bands, d, aec_sc);
-  }
+  if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc);
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
   if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
   __syncwarp();

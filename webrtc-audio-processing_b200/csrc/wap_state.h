@@ -244,6 +244,28 @@ struct Aec3State {
   Aec3Scalars s;
 };
 
+// Hand-over between the three kernels of one tick (k_front -> k_delay -> k_echo).
+// Lives in the leg's slab; only meaningful inside a tick.
+struct RenderInsertRec {   // RenderDelayBufferImpl::Insert: where k_echo writes block r
+  int blocks_write, spectra_write, previous_write, pad_;
+};
+struct CaptureBlockRec {   // BlockProcessorImpl::ProcessCapture: what EchoRemover sees for block b
+  int process;             // 0 => no render data yet, block passes through
+  int blocks_read, spectra_read;            // render-buffer read indices after AlignFromDelay
+  int gain_change, delay_change, clock_drift;  // EchoPathVariability
+  int est_has, est_delay;                   // estimated_delay_
+};
+struct TickScratch {
+  int n_render_blocks, n_capture_blocks;
+  int pad_[2];
+  RenderInsertRec rins[3];
+  CaptureBlockRec crec[3];
+  float render_blocks[3][kBlock];
+  float capture_blocks[3][kBlock];          // after the high-pass filter
+  float cap_ds[3][kSubBlock];               // decimated capture blocks
+  float capture_frame[kFrame * kMaxBands];  // full-band capture frame after the high-pass filter
+};
+
 // One call leg.
 struct StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)
@@ -256,6 +278,7 @@ struct StreamState {
   ThreeBandState render_bands;
   NsState ns;
   Aec3State aec;
+  TickScratch tick;
 };
 
 // Engine-wide (config class) constants uploaded once.

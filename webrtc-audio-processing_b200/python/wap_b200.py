@@ -80,6 +80,7 @@ EXPORTS = [
     "wap_engine_create", "wap_engine_destroy", "wap_engine_create_streams", "wap_engine_state_bytes_per_stream",
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
+    "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
 ]
 
 _libs = {}
@@ -125,6 +126,10 @@ def load(path=None):
     L.wap_engine_cuda_stream.argtypes = [vp]
     L.wap_engine_launch_count.restype = C.c_int64
     L.wap_engine_launch_count.argtypes = [vp]
+    L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
+    L.wap_engine_read_kernel_timing.restype = C.c_int64
+    L.wap_engine_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    L.wap_engine_algorithmic_bytes_per_kernel.argtypes = [vp, C.POINTER(C.c_double)]
     L.wap_version.restype = C.c_char_p
     _libs[path] = L
     return L
