@@ -95,3 +95,16 @@ def synthetic_leg(i, n_frames, rate=16000):
     y += rng_n.uniform(-3000, 3000, n) * ((t % 2.0) > 1.7)
     return (np.clip(np.round(x), -32768, 32767).astype(np.int16),
             np.clip(np.round(y), -32768, 32767).astype(np.int16))
+
+
+def vanishing_echo_leg(n_frames, rate=16000, seed=11):
+    """Loud white render (+-30000) with a single-tap echo path (0.6, 100 samples) that
+    disappears after 3 s, over a +-400 noise floor."""
+    rng = np.random.default_rng(seed)
+    n = n_frames * rate // 100
+    x = rng.uniform(-30000, 30000, n)
+    y = np.zeros(n)
+    y[100:] = 0.6 * x[:-100]
+    y[3 * rate:] = 0
+    y += rng.uniform(-400, 400, n)
+    return (np.round(x).astype(np.int16), np.clip(np.round(y), -32768, 32767).astype(np.int16))

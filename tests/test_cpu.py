@@ -186,3 +186,15 @@ def test_emu_render_before_first_capture_is_dropped_with_ns(emu_lib, oracle):
         assert err == 0
         out, _ = run_legs(emu_lib, 16000, [(far, near)], aec=True, ns=ns, ns_level=1)
         assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
+
+
+def test_emu_aec3_echo_path_vanishes_loud_render(emu_lib, oracle):
+    """Near-full-scale render whose echo path disappears after 3 s: drives the refined filter
+    into the misadjustment rescale (subtractor.cc:246-257,345-375) and the coarse-filter
+    re-seed (subtractor.cc:297-316)."""
+    from common import run_legs, vanishing_echo_leg
+    far, near = vanishing_echo_leg(450)
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=False).run_i16(16000, far, near, stats_every=50)
+    assert err == 0
+    out, stats = run_legs(emu_lib, 16000, [(far, near)], stats_every=50, aec=True, ns=False)
+    _check_aec(out[0], stats[0], ref_out, ref_stats)

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import golden, run_engine, run_legs, synthetic_leg
+from common import golden, run_engine, run_legs, synthetic_leg, vanishing_echo_leg
 
 pytestmark = pytest.mark.gpu
 TOL_FS = 1e-4  # of full scale => 3.2768 int16 LSB
@@ -107,3 +107,12 @@ def test_aec3_saturated_capture_and_silence(gpu_lib, oracle):
     assert err == 0
     out, stats = run_legs(gpu_lib, 16000, [(far, near)], stats_every=50, aec=True, ns=True, ns_level=1)
     _check_aec(out[0], stats[0], ref_out, ref_stats, "saturated")
+
+
+def test_aec3_echo_path_vanishes_loud_render(gpu_lib, oracle):
+    """Misadjustment rescale + coarse re-seed paths (subtractor.cc:246-257,297-316,345-375)."""
+    far, near = vanishing_echo_leg(800)
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near, stats_every=50)
+    assert err == 0
+    out, stats = run_legs(gpu_lib, 16000, [(far, near)], stats_every=50, aec=True, ns=True, ns_level=1)
+    _check_aec(out[0], stats[0], ref_out, ref_stats, "vanishing echo")

@@ -169,69 +169,191 @@ WAP_DEV bool render_signal_analyzer_mask(const Aec3State& a, float* mask) {
   return any_poor;
 }
 
-// One adaptive filter: S = sum_p X_p * H_p (ApplyFilter_Avx2), then the
-// time-domain prediction error (PredictionError, subtractor.cc:49-65).
-WAP_DEV void fir_filter_and_error(const Aec3State& a, AecScratch& sc, const float (*H_re)[kBinsPad],
-                                  const float (*H_im)[kBinsPad], int num_partitions, float* e_out, float* s_out) {
+// Row of the render FFT / spectrum rings that partition p pairs with (adaptive_fir_filter.cc:139-151).
+WAP_DEV int ring_row(int pos, int p) {
+  const int row = pos + p;
+  return row >= kRingBlocks ? row - kRingBlocks : row;
+}
+
+// Both adaptive filters at once: S = sum_p X_p * H_p (ApplyFilter_Avx2: per bin, partitions
+// in order, separate multiplies and adds) for the refined filter (-> sc.fftA, packed) and the
+// coarse filter (-> sc.fftB); the render partitions X_p are loaded once and shared.  All loads
+// of a bin are issued before the arithmetic so they overlap in the memory system.
+WAP_DEV void fir_filter_both(const Aec3State& a, AecScratch& sc, int P_r, int P_c) {
   const int lane = lane_id();
   const int pos = sc.s.spectra_read;
+  const int pmax = imax(P_r, P_c);
   __syncwarp();
   for (int k = lane; k < kBins; k += 32) {
+    float Xr[kMaxPartitions], Xi[kMaxPartitions];
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      const int row = ring_row(pos, p);
+      Xr[p] = p < pmax ? a.fft_re[row][k] : 0.f;
+      Xi[p] = p < pmax ? a.fft_im[row][k] : 0.f;
+    }
+    float Hre[kMaxPartitions], Him[kMaxPartitions];
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      Hre[p] = p < P_r ? a.Hr_re[p][k] : 0.f;
+      Him[p] = p < P_r ? a.Hr_im[p][k] : 0.f;
+    }
     float S_re = 0.f, S_im = 0.f;
-    int xp = pos;
-    for (int p = 0; p < num_partitions; ++p) {
-      const float X_re = a.fft_re[xp][k], X_im = a.fft_im[xp][k];
-      const float Hre = H_re[p][k], Him = H_im[p][k];
-      const float aa = X_re * Hre, bb = X_im * Him, cc = X_re * Him, dd = X_im * Hre;
-      S_re = S_re + (aa - bb);
-      S_im = S_im + (cc + dd);
-      xp = ring_inc(xp, kRingBlocks);
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      if (p < P_r) {
+        const float aa = Xr[p] * Hre[p], bb = Xi[p] * Him[p], cc = Xr[p] * Him[p], dd = Xi[p] * Hre[p];
+        S_re = S_re + (aa - bb);
+        S_im = S_im + (cc + dd);
+      }
     }
     if (k == 0) sc.fftA[0] = S_re;
     else if (k == 64) sc.fftA[1] = S_re;
     else { sc.fftA[2 * k] = S_re; sc.fftA[2 * k + 1] = S_im; }
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      Hre[p] = p < P_c ? a.Hc_re[p][k] : 0.f;
+      Him[p] = p < P_c ? a.Hc_im[p][k] : 0.f;
+    }
+    S_re = 0.f; S_im = 0.f;
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      if (p < P_c) {
+        const float aa = Xr[p] * Hre[p], bb = Xi[p] * Him[p], cc = Xr[p] * Him[p], dd = Xi[p] * Hre[p];
+        S_re = S_re + (aa - bb);
+        S_im = S_im + (cc + dd);
+      }
+    }
+    if (k == 0) sc.fftB[0] = S_re;
+    else if (k == 64) sc.fftB[1] = S_re;
+    else { sc.fftB[2 * k] = S_re; sc.fftB[2 * k + 1] = S_im; }
   }
-  fft_pair(sc, true, false);
-  constexpr float kScale = 1.0f / 64;
-  for (int i = lane; i < kBlock; i += 32) {
-    const float t = sc.fftA[kBlock + i];
-    e_out[i] = sc.y[i] - t * kScale;
-    s_out[i] = kScale * t;
-  }
-  __syncwarp();
 }
 
-// AdaptPartitions_Avx2: H_p += conj(X_p) * G.
+// PredictionError (subtractor.cc:49-65) from the inverse transform in `buf`.
+WAP_DEV void prediction_error(const float* buf, const float* y, float* e_out, float* s_out) {
+  constexpr float kScale = 1.0f / 64;
+  for (int i = lane_id(); i < kBlock; i += 32) {
+    const float t = buf[kBlock + i];
+    e_out[i] = y[i] - t * kScale;
+    s_out[i] = kScale * t;
+  }
+}
+
+// AdaptPartitions_Avx2: H_p += conj(X_p) * G for one filter (used on the rare coarse re-seed path).
 WAP_DEV void fir_adapt_partitions(const Aec3State& a, AecScratch& sc, float (*H_re)[kBinsPad], float (*H_im)[kBinsPad],
                                   int num_partitions, const float* G_re, const float* G_im) {
   const int pos = sc.s.spectra_read;
   for (int k = lane_id(); k < kBins; k += 32) {
     const float Gre = G_re[k], Gim = G_im[k];
-    int xp = pos;
     for (int p = 0; p < num_partitions; ++p) {
-      const float X_re = a.fft_re[xp][k], X_im = a.fft_im[xp][k];
+      const int row = ring_row(pos, p);
+      const float X_re = a.fft_re[row][k], X_im = a.fft_im[row][k];
       const float aa = X_re * Gre, bb = X_im * Gim, cc = X_re * Gim, dd = X_im * Gre;
       H_re[p][k] = H_re[p][k] + (aa + bb);
       H_im[p][k] = H_im[p][k] + (cc - dd);
-      xp = ring_inc(xp, kRingBlocks);
     }
   }
   __syncwarp();
 }
 
-// AdaptiveFirFilter::Constrain / ConstrainAndUpdateImpulseResponse (:645-706)
-// for partition p; `impulse` (may be null) receives the 64 retained taps.
-WAP_DEV void fir_constrain(AecScratch& sc, float* H_re_p, float* H_im_p, float* impulse) {
+// ComputeFrequencyResponse_Avx2 for one bin of one partition (single render channel: max with 0).
+WAP_DEV float h2_bin(float re, float im, int k) {
+  const float v = (k < 64) ? fmaf(im, im, re * re) : re * re + im * im;
+  return fmaxr(0.f, v);
+}
+
+// Both filters' AdaptPartitions_Avx2 in one pass over the render partitions (X_p loaded once),
+// plus ComputeFrequencyResponse of the refined filter from the values just written (the partition
+// that Constrain() rewrites afterwards is redone by the caller).  coarse == false: refined only.
+WAP_DEV void fir_adapt_both(Aec3State& a, AecScratch& sc, int P_r, int P_c, const float* Gr_re, const float* Gr_im,
+                            const float* Gc_re, const float* Gc_im, bool coarse) {
+  const int lane = lane_id();
+  const int pos = sc.s.spectra_read;
+  const int pmax = coarse ? imax(P_r, P_c) : P_r;
+  for (int k = lane; k < kBins; k += 32) {
+    float Xr[kMaxPartitions], Xi[kMaxPartitions];
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      const int row = ring_row(pos, p);
+      Xr[p] = p < pmax ? a.fft_re[row][k] : 0.f;
+      Xi[p] = p < pmax ? a.fft_im[row][k] : 0.f;
+    }
+    float Hre[kMaxPartitions], Him[kMaxPartitions];
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      Hre[p] = p < P_r ? a.Hr_re[p][k] : 0.f;
+      Him[p] = p < P_r ? a.Hr_im[p][k] : 0.f;
+    }
+    {
+      const float Gre = Gr_re[k], Gim = Gr_im[k];
+#pragma unroll
+      for (int p = 0; p < kMaxPartitions; ++p) {
+        if (p < P_r) {
+          const float aa = Xr[p] * Gre, bb = Xi[p] * Gim, cc = Xr[p] * Gim, dd = Xi[p] * Gre;
+          const float re = Hre[p] + (aa + bb), im = Him[p] + (cc - dd);
+          a.Hr_re[p][k] = re;
+          a.Hr_im[p][k] = im;
+          a.H2[p][k] = h2_bin(re, im, k);
+        }
+      }
+    }
+    if (coarse) {
+#pragma unroll
+      for (int p = 0; p < kMaxPartitions; ++p) {
+        Hre[p] = p < P_c ? a.Hc_re[p][k] : 0.f;
+        Him[p] = p < P_c ? a.Hc_im[p][k] : 0.f;
+      }
+      const float Gre = Gc_re[k], Gim = Gc_im[k];
+#pragma unroll
+      for (int p = 0; p < kMaxPartitions; ++p) {
+        if (p < P_c) {
+          const float aa = Xr[p] * Gre, bb = Xi[p] * Gim, cc = Xr[p] * Gim, dd = Xi[p] * Gre;
+          a.Hc_re[p][k] = Hre[p] + (aa + bb);
+          a.Hc_im[p][k] = Him[p] + (cc - dd);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// AdaptiveFirFilter::Constrain / ConstrainAndUpdateImpulseResponse (:645-706) for one partition
+// of each filter side by side (refined on lanes 0-15 / fftA, coarse on lanes 16-31 / fftB);
+// `impulse` receives the 64 retained taps of the refined partition.  second == false: refined only.
+WAP_DEV void fir_constrain_pair(AecScratch& sc, float* Hr_re_p, float* Hr_im_p, float* impulse, float* Hc_re_p,
+                                float* Hc_im_p, bool second) {
+  const int lane = lane_id();
+  __syncwarp();
+  reim_to_packed(Hr_re_p, Hr_im_p, sc.fftA);
+  if (second) reim_to_packed(Hc_re_p, Hc_im_p, sc.fftB);
+  fft_pair(sc, true, second);
+  constexpr float kScale = 1.0f / 64;
+  for (int i = lane; i < kBlock; i += 32) {
+    const float v = sc.fftA[i] * kScale;
+    sc.fftA[i] = v;
+    sc.fftA[kBlock + i] = 0.f;
+    impulse[i] = v;
+    if (second) {
+      sc.fftB[i] = sc.fftB[i] * kScale;
+      sc.fftB[kBlock + i] = 0.f;
+    }
+  }
+  fft_pair(sc, false, second);
+  packed_to_reim(sc.fftA, Hr_re_p, Hr_im_p);
+  if (second) packed_to_reim(sc.fftB, Hc_re_p, Hc_im_p);
+  __syncwarp();
+}
+// One partition of one filter (coarse re-seed path).
+WAP_DEV void fir_constrain(AecScratch& sc, float* H_re_p, float* H_im_p) {
   const int lane = lane_id();
   __syncwarp();
   reim_to_packed(H_re_p, H_im_p, sc.fftA);
   fft_pair(sc, true, false);
   constexpr float kScale = 1.0f / 64;
   for (int i = lane; i < kBlock; i += 32) {
-    const float v = sc.fftA[i] * kScale;
-    sc.fftA[i] = v;
+    sc.fftA[i] = sc.fftA[i] * kScale;
     sc.fftA[kBlock + i] = 0.f;
-    if (impulse) impulse[i] = v;
   }
   fft_pair(sc, false, false);
   packed_to_reim(sc.fftA, H_re_p, H_im_p);
@@ -250,6 +372,12 @@ WAP_DEV void stage_zero_padded_hanning(const float* x, float* buf) {
 // render rings; outputs in sc.rm (e_ref, e_coa, s_ref, s_coa, E2_ref, E2_coa,
 // Er) and sc.red[0..6] = {y2, e2_refined, e2_coarse, s2_refined, s2_coarse,
 // s_refined_max_abs, s_coarse_max_abs}.
+//
+// The refined and the coarse filter are processed together wherever the reference's
+// data flow allows it (their outputs, their gains and, unless the coarse filter is
+// being re-seeded from the refined one, their adaptation are independent): the
+// render partitions are read once per pass instead of once per filter, and the
+// 128-point transforms run two at a time on the two half-warps.
 WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_capture) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
@@ -259,19 +387,25 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
   // RenderBuffer::SpectralSum(s) (render_buffer.cc:42-83): one running sum per bin.
   {
     const int pmax = imax(P_r, P_c);
+    const int pos = s.spectra_read;
     for (int k = lane; k < kBins; k += 32) {
+      float X2[kMaxPartitions];
+#pragma unroll
+      for (int j = 0; j < kMaxPartitions; ++j) X2[j] = j < pmax ? a.spectra[ring_row(pos, j)][k] : 0.f;
       float x2 = 0.f;
-      int pos = s.spectra_read;
-      for (int j = 0; j < pmax; ++j) {
-        x2 += a.spectra[pos][k];
-        pos = ring_inc(pos, kRingBlocks);
+#pragma unroll
+      for (int j = 0; j < kMaxPartitions; ++j) {
+        if (j < pmax) x2 += X2[j];
         if (j + 1 == P_r) r.X2_ref[k] = x2;
         if (j + 1 == P_c) r.X2_coa[k] = x2;
       }
     }
   }
-  fir_filter_and_error(a, sc, a.Hr_re, a.Hr_im, P_r, r.e_ref, r.s_ref);
-  fir_filter_and_error(a, sc, a.Hc_re, a.Hc_im, P_c, r.e_coa, r.s_coa);
+  fir_filter_both(a, sc, P_r, P_c);
+  fft_pair(sc, true, true);
+  prediction_error(sc.fftA, sc.y, r.e_ref, r.s_ref);
+  prediction_error(sc.fftB, sc.y, r.e_coa, r.s_coa);
+  __syncwarp();
 
   // SubtractorOutput::ComputeMetrics (subtractor_output.cc:39-59): five serial
   // sums of squares, one per lane, plus the two peak magnitudes.
@@ -339,9 +473,10 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
   power_spectrum(r.Er_re, r.Er_im, r.E2_ref);
   const bool poor_excitation = render_signal_analyzer_mask(a, r.v0);  // r.v0 = narrow-band mask
 
-  // ---- refined filter update
+  // ---- scalar part of both updates (lane 0), in the reference's order: refined gain,
+  // refined UpdateSize, coarse-filter bookkeeping, coarse gain, coarse UpdateSize.
   if (lane == 0) {
-    sc.ired[1] = 1;  // G == 0 ?
+    sc.ired[1] = 1;  // refined G == 0 ?
     if (!refined_filters_adjusted) {
       ++s.rg_call_counter;
       gain_update_current_config(s.rg_cur, s.rg_old, s.rg_tgt, 5, &s.rg_config_change_counter);
@@ -351,73 +486,8 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
       sc.ired[1] = zero;
     }
     sc.ired[2] = s.coarse_filter_reset_hangover > 0;  // disallow_leakage_diverged
-  }
-  __syncwarp();
-  if (!refined_filters_adjusted) {
-    const bool zero_gain = sc.ired[1] != 0;
-    const bool disallow_leakage_diverged = sc.ired[2] != 0;
-    const float leak_conv = s.rg_cur[0], leak_div = s.rg_cur[1], err_floor = s.rg_cur[2], err_ceil = s.rg_cur[3],
-                noise_gate = s.rg_cur[4];
-    const int H2_size = s.H2_size;
-    for (int k = lane; k < kBins; k += 32) {
-      // ComputeErl (adaptive_fir_filter_erl_avx2.cc:27-40)
-      float erl = 0.f;
-      for (int j = 0; j < H2_size; ++j) erl += a.H2[j][k];
-      float H_error = a.H_error[k];
-      const float X2 = r.X2_ref[k], E2r = r.E2_ref[k];
-      if (zero_gain) {
-        r.G_re[k] = 0.f;
-        r.G_im[k] = 0.f;
-      } else {
-        float mu = 0.f;
-        if (X2 >= noise_gate) mu = H_error / (0.5f * H_error * X2 + (float)P_r * E2r);
-        if (r.v0[k] != 0.f) mu = 0.f;
-        H_error -= 0.5f * mu * X2 * H_error;
-        r.G_re[k] = mu * r.Er_re[k];
-        r.G_im[k] = mu * r.Er_im[k];
-      }
-      if (E2r <= r.E2_coa[k] || disallow_leakage_diverged) H_error += leak_conv * erl;
-      else H_error += leak_div * erl;
-      H_error = fmaxr(H_error, err_floor);
-      H_error = fminr(H_error, err_ceil);
-      a.H_error[k] = H_error;
-    }
-  } else {
-    for (int k = lane; k < kBins; k += 32) { r.G_re[k] = 0.f; r.G_im[k] = 0.f; }
-  }
-  __syncwarp();
-  // AdaptiveFirFilter::Adapt(render_buffer, G, &impulse_response) for the refined filter.
-  if (lane == 0) {
     sc.ired[3] = fir_update_size(&s.fr_current_size, &s.fr_target_size, &s.fr_old_target_size,
                                  &s.fr_size_change_counter, &s.fr_partition_to_constrain);
-  }
-  __syncwarp();
-  {
-    const int P = s.fr_current_size;
-    fir_zero_partitions(a.Hr_re, a.Hr_im, sc.ired[3], P);
-    __syncwarp();
-    fir_adapt_partitions(a, sc, a.Hr_re, a.Hr_im, P, r.G_re, r.G_im);
-    // impulse_response->resize(): newly exposed taps are zero.
-    for (int i = s.h_time_size * kBlock + lane; i < P * kBlock; i += 32) a.h_time[i] = 0.f;
-    const int p = s.fr_partition_to_constrain;
-    fir_constrain(sc, a.Hr_re[p], a.Hr_im[p], a.h_time + p * kBlock);
-    if (lane == 0) {
-      s.h_time_size = P;
-      s.fr_partition_to_constrain = p < (P - 1) ? p + 1 : 0;
-      s.H2_size = P;
-    }
-    // ComputeFrequencyResponse_Avx2 (single render channel: max with 0).
-    for (int pp = 0; pp < P; ++pp)
-      for (int k = lane; k < kBins; k += 32) {
-        const float re = a.Hr_re[pp][k], im = a.Hr_im[pp][k];
-        const float v = (k < 64) ? fmaf(im, im, re * re) : re * re + im * im;
-        a.H2[pp][k] = fmaxr(0.f, v);
-      }
-    __syncwarp();
-  }
-
-  // ---- coarse filter update
-  if (lane == 0) {
     s.poor_coarse_filter_counter = e2_refined < e2_coarse ? s.poor_coarse_filter_counter + 1 : 0;
     sc.ired[4] = s.poor_coarse_filter_counter < 5;
     if (sc.ired[4]) {
@@ -426,59 +496,108 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
       s.poor_coarse_filter_counter = 0;
       s.coarse_filter_reset_hangover = ec3::kCoarseResetHangover;
     }
-  }
-  __syncwarp();
-  const bool coarse_ok = sc.ired[4] != 0;
-  if (!coarse_ok) {
-    // coarse_filter_->SetFilter(refined size, refined H) (:733-747)
-    const int np = imin(P_c, s.fr_current_size);
-    for (int i = lane; i < np * kBinsPad; i += 32) {
-      (&a.Hc_re[0][0])[i] = (&a.Hr_re[0][0])[i];
-      (&a.Hc_im[0][0])[i] = (&a.Hr_im[0][0])[i];
-    }
-    __syncwarp();
-  }
-  if (lane == 0) {
     ++s.cg_call_counter;
     gain_update_current_config(s.cg_cur, s.cg_old, s.cg_tgt, 2, &s.cg_config_change_counter);
     if (poor_excitation) s.cg_poor_excitation_counter = 0;
     sc.ired[5] = (unsigned)(++s.cg_poor_excitation_counter) < (unsigned)P_c || saturated_capture ||
                  (unsigned)s.cg_call_counter <= (unsigned)P_c;
+    sc.ired[6] = fir_update_size(&s.fc_current_size, &s.fc_target_size, &s.fc_old_target_size,
+                                 &s.fc_size_change_counter, &s.fc_partition_to_constrain);
   }
   __syncwarp();
+  const bool coarse_ok = sc.ired[4] != 0;
+  const int P_r2 = s.fr_current_size, P_c2 = s.fc_current_size;  // after UpdateSize
+  // ---- RefinedFilterUpdateGain::Compute -> r.G ; CoarseFilterUpdateGain::Compute -> r.v1 / r.v2
   {
-    const bool zero_gain = sc.ired[5] != 0;
-    const float rate = s.cg_cur[0], noise_gate = s.cg_cur[1];
-    const float* E_re = coarse_ok ? r.Ec_re : r.Er_re;
-    const float* E_im = coarse_ok ? r.Ec_im : r.Er_im;
+    const bool zero_ref = sc.ired[1] != 0, zero_coa = sc.ired[5] != 0;
+    const bool disallow_leakage_diverged = sc.ired[2] != 0;
+    const float leak_conv = s.rg_cur[0], leak_div = s.rg_cur[1], err_floor = s.rg_cur[2], err_ceil = s.rg_cur[3],
+                noise_gate = s.rg_cur[4];
+    const float rate = s.cg_cur[0], noise_gate_c = s.cg_cur[1];
+    const float* Ecx_re = coarse_ok ? r.Ec_re : r.Er_re;
+    const float* Ecx_im = coarse_ok ? r.Ec_im : r.Er_im;
+    const int H2_size = s.H2_size;
     for (int k = lane; k < kBins; k += 32) {
-      if (zero_gain) {
+      const bool masked = r.v0[k] != 0.f;
+      if (!refined_filters_adjusted) {
+        // ComputeErl (adaptive_fir_filter_erl_avx2.cc:27-40)
+        float h2[kMaxPartitions];
+#pragma unroll
+        for (int j = 0; j < kMaxPartitions; ++j) h2[j] = j < H2_size ? a.H2[j][k] : 0.f;
+        float erl = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxPartitions; ++j)
+          if (j < H2_size) erl += h2[j];
+        float H_error = a.H_error[k];
+        const float X2 = r.X2_ref[k], E2r = r.E2_ref[k];
+        if (zero_ref) {
+          r.G_re[k] = 0.f;
+          r.G_im[k] = 0.f;
+        } else {
+          float mu = 0.f;
+          if (X2 >= noise_gate) mu = H_error / (0.5f * H_error * X2 + (float)P_r * E2r);
+          if (masked) mu = 0.f;
+          H_error -= 0.5f * mu * X2 * H_error;
+          r.G_re[k] = mu * r.Er_re[k];
+          r.G_im[k] = mu * r.Er_im[k];
+        }
+        if (E2r <= r.E2_coa[k] || disallow_leakage_diverged) H_error += leak_conv * erl;
+        else H_error += leak_div * erl;
+        H_error = fmaxr(H_error, err_floor);
+        H_error = fminr(H_error, err_ceil);
+        a.H_error[k] = H_error;
+      } else {
         r.G_re[k] = 0.f;
         r.G_im[k] = 0.f;
+      }
+      if (zero_coa) {
+        r.v1[k] = 0.f;
+        r.v2[k] = 0.f;
       } else {
         const float X2 = r.X2_coa[k];
         float mu = 0.f;
-        if (X2 > noise_gate) mu = rate / X2;
-        if (r.v0[k] != 0.f) mu = 0.f;
-        r.G_re[k] = mu * E_re[k];
-        r.G_im[k] = mu * E_im[k];
+        if (X2 > noise_gate_c) mu = rate / X2;
+        if (masked) mu = 0.f;
+        r.v1[k] = mu * Ecx_re[k];
+        r.v2[k] = mu * Ecx_im[k];
       }
     }
   }
   __syncwarp();
-  if (lane == 0) {
-    sc.ired[3] = fir_update_size(&s.fc_current_size, &s.fc_target_size, &s.fc_old_target_size,
-                                 &s.fc_size_change_counter, &s.fc_partition_to_constrain);
-  }
+  // ---- AdaptiveFirFilter::Adapt for both filters
+  fir_zero_partitions(a.Hr_re, a.Hr_im, sc.ired[3], P_r2);   // UpdateSize: newly exposed partitions
+  // impulse_response->resize(): newly exposed taps are zero.
+  for (int i = s.h_time_size * kBlock + lane; i < P_r2 * kBlock; i += 32) a.h_time[i] = 0.f;
+  if (coarse_ok) fir_zero_partitions(a.Hc_re, a.Hc_im, sc.ired[6], P_c2);
   __syncwarp();
-  {
-    const int P = s.fc_current_size;
-    fir_zero_partitions(a.Hc_re, a.Hc_im, sc.ired[3], P);
+  const int pr = s.fr_partition_to_constrain, pc = s.fc_partition_to_constrain;
+  if (coarse_ok) {
+    fir_adapt_both(a, sc, P_r2, P_c2, r.G_re, r.G_im, r.v1, r.v2, true);
+    fir_constrain_pair(sc, a.Hr_re[pr], a.Hr_im[pr], a.h_time + pr * kBlock, a.Hc_re[pc], a.Hc_im[pc], true);
+  } else {
+    // Coarse filter re-seeded from the adapted refined filter (subtractor.cc:305-316):
+    // strictly sequential.
+    fir_adapt_both(a, sc, P_r2, P_c2, r.G_re, r.G_im, r.v1, r.v2, false);
+    fir_constrain_pair(sc, a.Hr_re[pr], a.Hr_im[pr], a.h_time + pr * kBlock, nullptr, nullptr, false);
+    // coarse_filter_->SetFilter(refined size, refined H) (:733-747)
+    const int np = imin(P_c, P_r2);
+    for (int i = lane; i < np * kBinsPad; i += 32) {
+      (&a.Hc_re[0][0])[i] = (&a.Hr_re[0][0])[i];
+      (&a.Hc_im[0][0])[i] = (&a.Hr_im[0][0])[i];
+    }
     __syncwarp();
-    fir_adapt_partitions(a, sc, a.Hc_re, a.Hc_im, P, r.G_re, r.G_im);
-    const int p = s.fc_partition_to_constrain;
-    fir_constrain(sc, a.Hc_re[p], a.Hc_im[p], nullptr);
-    if (lane == 0) s.fc_partition_to_constrain = p < (P - 1) ? p + 1 : 0;
+    fir_zero_partitions(a.Hc_re, a.Hc_im, sc.ired[6], P_c2);
+    __syncwarp();
+    fir_adapt_partitions(a, sc, a.Hc_re, a.Hc_im, P_c2, r.v1, r.v2);
+    fir_constrain(sc, a.Hc_re[pc], a.Hc_im[pc]);
+  }
+  // ComputeFrequencyResponse of the partition Constrain() rewrote.
+  for (int k = lane; k < kBins; k += 32) a.H2[pr][k] = h2_bin(a.Hr_re[pr][k], a.Hr_im[pr][k], k);
+  if (lane == 0) {
+    s.h_time_size = P_r2;
+    s.H2_size = P_r2;
+    s.fr_partition_to_constrain = pr < (P_r2 - 1) ? pr + 1 : 0;
+    s.fc_partition_to_constrain = pc < (P_c2 - 1) ? pc + 1 : 0;
   }
   // e_refined clamp (subtractor.cc:333-334)
   for (int i = lane; i < kBlock; i += 32) r.e_ref[i] = clampr(r.e_ref[i], -32768.f, 32767.f);

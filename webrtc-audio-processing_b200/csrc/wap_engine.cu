@@ -33,7 +33,13 @@ __global__ void __launch_bounds__(128, 4) k_delay(TickArgs a, int scratch_floats
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
-  float* scratch = sm + (size_t)warp * scratch_floats;
+  unsigned scratch_off = (unsigned)warp * (unsigned)scratch_floats;
+#if !defined(WAP_EMU)
+  // Opaque to the optimiser: keeps the per-warp offset in one register instead of
+  // re-deriving it from tid / the kernel parameter at every shared-memory access.
+  asm volatile("" : "+r"(scratch_off));
+#endif
+  float* scratch = sm + scratch_off;
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
     delay_stream_tick(a, idx, scratch);
     __syncwarp();
@@ -44,7 +50,13 @@ __global__ void __launch_bounds__(128, 4) k_echo(TickArgs a, int scratch_floats)
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
-  float* scratch = sm + (size_t)warp * scratch_floats;
+  unsigned scratch_off = (unsigned)warp * (unsigned)scratch_floats;
+#if !defined(WAP_EMU)
+  // Opaque to the optimiser: keeps the per-warp offset in one register instead of
+  // re-deriving it from tid / the kernel parameter at every shared-memory access.
+  asm volatile("" : "+r"(scratch_off));
+#endif
+  float* scratch = sm + scratch_off;
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
     echo_stream_tick(a, idx, scratch);
     __syncwarp();

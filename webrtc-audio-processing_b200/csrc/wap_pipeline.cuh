@@ -65,7 +65,11 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   const TickScratch& ts = st.tick;
   float* full = scratch;
   float* bands = (B == 1) ? full : scratch + flen;
-  void* dsp = scratch + 2 * flen;
+  unsigned dsp_off = 2u * (unsigned)flen;
+#if !defined(WAP_EMU)
+  asm volatile("" : "+r"(dsp_off));  // see k_echo: one register instead of re-reading cfg at every access
+#endif
+  void* dsp = scratch + dsp_off;
   NsScratch& ns_sc = *reinterpret_cast<NsScratch*>(dsp);
   AecScratch& aec_sc = *reinterpret_cast<AecScratch*>(dsp);
 
