@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Attribute the executed warp instructions of k_tick to source lines.
-usage: tools/ncu_lines.py <report.ncu-rep> [top_n]
+usage: tools/ncu_lines.py <report.ncu-rep> [top_n] [kernel] [profiled .so]
 Joins `ncu --page source --print-source sass --csv` (per-SASS-instruction counters) with the line
 table of the cubin inside libwap_b200.so (nvdisasm -g).  The .so must be the one that was profiled."""
 import csv, io, os, re, subprocess, sys, tempfile, collections
@@ -8,9 +8,10 @@ import csv, io, os, re, subprocess, sys, tempfile, collections
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-kernel = sys.argv[3] if len(sys.argv) > 3 else "k_tick"
+kernel = sys.argv[3] if len(sys.argv) > 3 else "k_echo"
+so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "webrtc-audio-processing_b200", "libwap_b200.so")
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "webrtc-audio-processing_b200", "libwap_b200.so")],
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)],
                cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.startswith("wap_engine") and f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout

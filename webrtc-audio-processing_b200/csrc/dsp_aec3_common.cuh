@@ -78,14 +78,19 @@ struct EchoPathVariability {  // echo_path_variability.h:16-29
 // same time; k_delay only allocates up to the end of `mf`.
 constexpr int kMfWin = kMfLen + kSubBlock - 1;   // 527 low-rate samples one filter sees in a block
 constexpr int kMfWinPad = 544;                   // second window starts 16 banks after the first
+constexpr int kMfShiftCopy = 528;                // one shifted window copy of the accumulated-error path
+static_assert(4 * kMfShiftCopy >= 2 * kMfWinPad + 32, "pair path windows must fit");
 struct AecMfScratch {
   // Linearised low-rate windows: xp[w] = low_rate[(read + n*384 + w) % size], w < 527, so that
   // tap t of capture sample i is xp[15 - i + t].  The pair path keeps two filters' windows
   // (the second at +560 floats: other half of the banks); the one-filter paths use the first.
-  float xp[2 * kMfWinPad + 32];
-  float h[kMfLen];         // matched filter being processed (one-filter paths)
+  // The accumulated-error path keeps FOUR copies of its window, copy sh shifted by sh samples
+  // (xs(sh)[w] = window[w + sh], 528 floats each), so that the 4 consecutive taps a lane owns
+  // can be fetched with one aligned 128-bit load whatever the sample's offset is.
+  alignas(16) float xp[4 * kMfShiftCopy];
+  alignas(16) float h[kMfLen];         // matched filter being processed (general one-filter path)
   float inst_err[kAccErrLen];  // MatchedFilter::instantaneous_accumulated_error_
-  float q[kAccErrLen];     // per-4-tap partial sums / prefix sums of the accumulated-error core
+  alignas(16) float q[kAccErrLen];     // per-4-tap partial sums / prefix sums of the accumulated-error core
   float x2chain[2][32];    // pair path: the 31 distinct x*x chains of a block, per filter
   float x2sum[2][kSubBlock];   // pair path: x2_sum of every capture sample, per filter
   float err_sum[kNumMatchedFilters];

@@ -113,67 +113,137 @@ WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out
   *updated_out = updated;
 }
 
-// Same filter with the accumulated-error side output (winner of the previous
-// block only; matched_filter_avx2.cc:45-149).
-WAP_DEV void mf_core_accumulated_error(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
+// The filter that won the previous block, with the accumulated-error side output
+// (MatchedFilterCore_AccumulatedError_AVX2, matched_filter_avx2.cc:45-149).  The
+// reference linearises the window first, so there is no ring-wrap chunking here:
+//  * h*x: plain products, summed four taps at a time as (p0+p1)+(p2+p3), then a STRICTLY
+//    serial running sum over the 128 groups (s_acum) whose every prefix feeds the
+//    instantaneous accumulated error.  Lane l owns taps 4l+b+128m (b,m < 4), i.e. groups
+//    l+32m, with h, the x values and the error accumulators in registers; the prefix
+//    sum itself is one dependent chain, run by lane 0 on the group sums in shared memory;
+//  * x*x: 16 fused chains combined as ((d0+d1)+d2)+d3, d_m = c_m + c_{m+4},
+//    c_j = chain_j + chain_{j+8}; the chains come from the per-block table (see mf_pair_fast);
+//  * update: fused over all taps.
+// Results go to sc.mf.{err_sum,updated,peak}[n] and sc.mf.inst_err.
+WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) {
   const int lane = lane_id();
-  float* h = sc.mf.h;
-  float* q = sc.mf.q;
-  float* inst = sc.mf.inst_err;
-  for (int g = lane; g < kAccErrLen; g += 32) inst[g] = 0.f;
+  __syncwarp();
+  // ---- stage the window, four shifted copies
+  {
+    int start = sc.s.lr_read + n * kMfShift;
+    if (start >= kLowRateSize) start -= kLowRateSize;
+    for (int w = lane; w < kMfWin; w += 32) {
+      int r = start + w;
+      if (r >= kLowRateSize) r -= kLowRateSize;
+      const float v = a.low_rate[r];
+#pragma unroll
+      for (int sh = 0; sh < 4; ++sh)
+        if (w >= sh) sc.mf.xp[sh * kMfShiftCopy + w - sh] = v;
+    }
+  }
+  float h[16];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const float4 v = *reinterpret_cast<const float4*>(&a.mf_h[n][4 * lane + 128 * m]);
+    h[4 * m] = v.x; h[4 * m + 1] = v.y; h[4 * m + 2] = v.z; h[4 * m + 3] = v.w;
+  }
+  __syncwarp();
+  // ---- x*x chains of the block (copy 0 is the unshifted window)
+  {
+    const int hw = lane >> 4, L = lane & 15;
+    const float* x = hw ? sc.mf.xp + (kSubBlock - 1) - L : sc.mf.xp + (kSubBlock - 1) + L;
+    float c = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float u = x[16 * k];
+      c = fmaf(u, u, c);
+    }
+    if (hw == 0) sc.mf.x2chain[0][15 - L] = c;       // chain L of sample 0
+    else if (L > 0) sc.mf.x2chain[0][15 + L] = c;    // chain 0 of sample L
+  }
+  __syncwarp();
+  if (lane < kSubBlock) {
+    const float* E = sc.mf.x2chain[0] + 15 + lane;
+    const float d0 = (E[0] + E[-8]) + (E[-4] + E[-12]), d1 = (E[-1] + E[-9]) + (E[-5] + E[-13]);
+    const float d2 = (E[-2] + E[-10]) + (E[-6] + E[-14]), d3 = (E[-3] + E[-11]) + (E[-7] + E[-15]);
+    sc.mf.x2sum[0][lane] = ((d0 + d1) + d2) + d3;
+  }
+  __syncwarp();
+  float inst[4] = {0.f, 0.f, 0.f, 0.f};
   float error_sum = 0.f;
   int updated = 0;
+#pragma unroll 1
   for (int i = 0; i < kSubBlock; ++i) {
-    const float* x = sc.mf.xp + (kSubBlock - 1 - i);
-    // x*x: 16 fused chains over every 16th tap (lanes 0-15).
-    float acc = 0.f;
-    if (lane < 16) {
-      for (int k = 0; k < kMfLen / 16; ++k) {
-        const float xv = x[lane + 16 * k];
-        acc = fmaf(xv, xv, acc);
-      }
-    }
-    // h*x: plain products, summed four at a time as (p0+p1)+(p2+p3).
-    for (int g = lane; g < kAccErrLen; g += 32) {
-      const int t = 4 * g;
-      const float p0 = h[t] * x[t], p1 = h[t + 1] * x[t + 1], p2 = h[t + 2] * x[t + 2], p3 = h[t + 3] * x[t + 3];
-      q[g] = (p0 + p1) + (p2 + p3);
+    const int o = kSubBlock - 1 - i;
+    const float* x = sc.mf.xp + (o & 3) * kMfShiftCopy + (o & ~3) + 4 * lane;
+    float xv[16];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float4 v = *reinterpret_cast<const float4*>(x + 128 * m);
+      xv[4 * m] = v.x; xv[4 * m + 1] = v.y; xv[4 * m + 2] = v.z; xv[4 * m + 3] = v.w;
+      const float p0 = h[4 * m] * v.x, p1 = h[4 * m + 1] * v.y, p2 = h[4 * m + 2] * v.z, p3 = h[4 * m + 3] * v.w;
+      sc.mf.q[lane + 32 * m] = (p0 + p1) + (p2 + p3);
     }
     __syncwarp();
-    // Strictly serial running sum over the 128 groups.
-    if (lane == 0) {
+    if (lane == 0) {  // the one dependent chain of the block: 128 additions in order
       float s_acum = 0.f;
-      for (int g = 0; g < kAccErrLen; ++g) {
-        s_acum += q[g];
-        q[g] = s_acum;
+#pragma unroll 4
+      for (int g = 0; g < kAccErrLen; g += 4) {
+        float4 v = *reinterpret_cast<const float4*>(&sc.mf.q[g]);
+        s_acum += v.x; v.x = s_acum;
+        s_acum += v.y; v.y = s_acum;
+        s_acum += v.z; v.z = s_acum;
+        s_acum += v.w; v.w = s_acum;
+        *reinterpret_cast<float4*>(&sc.mf.q[g]) = v;
       }
     }
     __syncwarp();
     const float yi = y[i];
-    for (int g = lane; g < kAccErrLen; g += 32) {
-      const float eg = q[g] - yi;
-      inst[g] = fmaf(eg, eg, inst[g]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float eg = sc.mf.q[lane + 32 * m] - yi;
+      inst[m] = fmaf(eg, eg, inst[m]);
     }
-    const float s_acum = q[kAccErrLen - 1];
-    // x2_sum = ((d0 + d1) + d2) + d3, d_m = c_m + c_{m+4}, c_j = chain_j + chain_{j+8}.
-    acc += __shfl_xor_sync(WAP_FULL, acc, 8);
-    acc += __shfl_xor_sync(WAP_FULL, acc, 4);
-    const float d0 = __shfl_sync(WAP_FULL, acc, 0), d1 = __shfl_sync(WAP_FULL, acc, 1);
-    const float d2 = __shfl_sync(WAP_FULL, acc, 2), d3 = __shfl_sync(WAP_FULL, acc, 3);
-    const float x2_sum = ((d0 + d1) + d2) + d3;
+    const float s_acum = sc.mf.q[kAccErrLen - 1];
+    const float x2_sum = sc.mf.x2sum[0][i];
     const float e = yi - s_acum;
     const bool saturation = yi >= 32000.f || yi <= -32000.f;
     error_sum += e * e;
     __syncwarp();
     if (x2_sum > kMfX2SumThreshold && !saturation) {
       const float alpha = ec3::kMfSmoothing * e / x2_sum;
-      for (int t = lane; t < kMfLen; t += 32) h[t] = fmaf(x[t], alpha, h[t]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = fmaf(xv[j], alpha, h[j]);
       updated = 1;
     }
-    __syncwarp();
   }
-  *error_sum_out = error_sum;
-  *updated_out = updated;
+  // ---- write back; MaxSquarePeakIndex (first maximum among even taps, among odd taps)
+  float best_e = -1.f, best_o = -1.f;
+  int bi_e = 0, bi_o = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    *reinterpret_cast<float4*>(&a.mf_h[n][4 * lane + 128 * m]) = make_float4(h[4 * m], h[4 * m + 1], h[4 * m + 2], h[4 * m + 3]);
+    sc.mf.inst_err[lane + 32 * m] = inst[m];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float v = h[4 * m + b] * h[4 * m + b];
+      const int t = 4 * lane + 128 * m + b;
+      if (b & 1) { if (v > best_o || (v == best_o && t < bi_o)) { best_o = v; bi_o = t; } }
+      else { if (v > best_e || (v == best_e && t < bi_e)) { best_e = v; bi_e = t; } }
+    }
+  }
+  for (int msk = 16; msk; msk >>= 1) {
+    const float ove = __shfl_xor_sync(WAP_FULL, best_e, msk), ovo = __shfl_xor_sync(WAP_FULL, best_o, msk);
+    const int oie = __shfl_xor_sync(WAP_FULL, bi_e, msk), oio = __shfl_xor_sync(WAP_FULL, bi_o, msk);
+    if (ove > best_e || (ove == best_e && oie < bi_e)) { best_e = ove; bi_e = oie; }
+    if (ovo > best_o || (ovo == best_o && oio < bi_o)) { best_o = ovo; bi_o = oio; }
+  }
+  if (lane == 0) {
+    sc.mf.err_sum[n] = error_sum;
+    sc.mf.updated[n] = updated;
+    sc.mf.peak[n] = (best_o > best_e) ? bi_o : bi_e;
+  }
+  __syncwarp();
 }
 
 // Two matched filters side by side, one per half-warp, for blocks in which neither
@@ -315,6 +385,7 @@ WAP_DEV void lag_aggregator_reset(Aec3State& a, AecScratch& sc, bool hard_reset)
   for (int i = lane; i < kPreEchoHistSize; i += 32) a.pre_hist[i] = 0;
   if (lane == 0) {
     sc.s.agg_hist_data_index = 0;
+    sc.s.agg_candidate_valid = 0;  // candidate_ itself survives a Reset(); it is recomputed by the next Aggregate
     sc.s.pre_hist_data_index = 0;
     sc.s.pre_candidate = 0;
     if (hard_reset) sc.s.agg_significant_candidate_found = 0;
@@ -392,14 +463,17 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   for (int p = 0; p < nfast; p += 2) mf_pair_fast(a, sc, fast[p], p + 1 < nfast ? fast[p + 1] : -1, y);
   for (int n = 0; n < kNumMatchedFilters; ++n) {
     if (!((slow_mask >> n) & 1u)) continue;
+    if (n == last_best) {
+      mf_acc_filter(a, sc, n, y);
+      continue;
+    }
     __syncwarp();
     mf_stage_window(a, sc, n, sc.mf.xp);
     for (int t = lane; t < kMfLen; t += 32) sc.mf.h[t] = a.mf_h[n][t];
     __syncwarp();
     float error_sum;
     int updated;
-    if (n == last_best) mf_core_accumulated_error(sc, n, y, &error_sum, &updated);
-    else mf_core(sc, n, y, &error_sum, &updated);
+    mf_core(sc, n, y, &error_sum, &updated);
     const int peak = mf_max_square_peak_index(sc.mf.h);
     for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = sc.mf.h[t];
     if (lane == 0) {
@@ -524,17 +598,33 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
       if (lane == 0) s.pre_candidate = cand << 4;
       __syncwarp();
     }
-    // HighestPeakAggregator::Aggregate (:115-127)
+    // HighestPeakAggregator::Aggregate (:115-127).  candidate_ is the FIRST index of the
+    // histogram maximum (std::max_element).  One bin loses a count and one gains one per call,
+    // so the argmax is maintained incrementally and the 2433-bin scan only runs when the bin
+    // that lost a count was the candidate itself (or after a reset).
     {
       const int lag = imax(0, winner_lag - headroom);
+      const int idx = s.agg_hist_data_index;
+      const int old_lag = a.lag_hist_data[idx];
+      const int prev_cand = s.agg_candidate;
+      const bool valid = s.agg_candidate_valid != 0;
+      __syncwarp();
       if (lane == 0) {
-        --a.lag_hist[a.lag_hist_data[s.agg_hist_data_index]];
-        a.lag_hist_data[s.agg_hist_data_index] = lag;
+        --a.lag_hist[old_lag];
+        a.lag_hist_data[idx] = lag;
         ++a.lag_hist[lag];
-        s.agg_hist_data_index = (s.agg_hist_data_index + 1) % 250;
+        s.agg_hist_data_index = (idx + 1) % 250;
       }
       __syncwarp();
-      const int cand = warp_argmax_first_int(a.lag_hist, kLagHistSize);
+      int cand;
+      if (!valid || (old_lag == prev_cand && old_lag != lag)) {
+        cand = warp_argmax_first_int(a.lag_hist, kLagHistSize);
+      } else if (old_lag == lag) {
+        cand = prev_cand;  // histogram unchanged
+      } else {
+        const int vmax = a.lag_hist[prev_cand], v = a.lag_hist[lag];
+        cand = (v > vmax || (v == vmax && lag < prev_cand)) ? lag : prev_cand;
+      }
       const int count = a.lag_hist[cand];
       const int sig = s.agg_significant_candidate_found || count > ec3::kThrConverged;
       if (count > ec3::kThrConverged || (count > ec3::kThrInitial && !sig)) {
@@ -545,6 +635,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
       __syncwarp();
       if (lane == 0) {
         s.agg_candidate = cand;
+        s.agg_candidate_valid = 1;
         s.agg_significant_candidate_found = sig;
       }
       __syncwarp();

@@ -20,10 +20,14 @@ namespace wap {
 constexpr int kScratchFloatsDsp =
     (int)((sizeof(NsScratch) > sizeof(AecScratch) ? sizeof(NsScratch) : sizeof(AecScratch)) / sizeof(float)) + 4;
 // k_echo: two frame buffers + the DSP scratch; k_delay: the AEC3 scratch only.
-inline int echo_scratch_floats(int bands) { return 2 * kFrame * bands + kScratchFloatsDsp; }
+// (rounded to 16 bytes: the scratch structs hold 128-bit aligned members)
+inline int echo_scratch_floats(int bands) { return (2 * kFrame * bands + kScratchFloatsDsp + 3) & ~3; }
 inline int delay_scratch_floats() {
-  return (int)((offsetof(AecScratch, mf) + sizeof(AecMfScratch)) / sizeof(float)) + 4;
+  return ((int)((offsetof(AecScratch, mf) + sizeof(AecMfScratch)) / sizeof(float)) + 4 + 3) & ~3;
 }
+static_assert(offsetof(StreamState, aec) % 16 == 0 && offsetof(Aec3State, mf_h) % 16 == 0 &&
+                  sizeof(StreamState) % 16 == 0 && offsetof(AecScratch, mf) % 16 == 0,
+              "128-bit accesses need 16-byte aligned state and scratch members");
 
 WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float* src) {
   const int lane = lane_id();

@@ -54,7 +54,7 @@ struct ThreeBandState {
 };
 
 // NoiseSuppressor::ChannelState and everything it owns (ns/noise_suppressor.h:62-76).
-struct NsState {
+struct alignas(16) NsState {
   // NoiseSuppressor::ChannelState
   float analyze_mem[kNsOverlap];
   float process_mem[kNsOverlap];
@@ -130,6 +130,7 @@ struct Aec3Scalars {
   // MatchedFilterLagAggregator
   int agg_significant_candidate_found;
   int agg_hist_data_index, agg_candidate;                     // HighestPeakAggregator (candidate -1)
+  int agg_candidate_valid;                                    // agg_candidate is the argmax of the current histogram
   int pre_hist_data_index, pre_candidate, pre_number_updates; // PreEchoLagAggregator
   // ClockdriftDetector
   int cd_history[3], cd_level, cd_stability_counter;
@@ -196,7 +197,7 @@ struct Aec3Scalars {
   int stats_delay_blocks, stats_has_delay;
 };
 
-struct Aec3State {
+struct alignas(16) Aec3State {
   // ---- RenderDelayBuffer rings (render_delay_buffer.cc:72-101)
   float blocks[kRingBlocks][kBlock];        // BlockBuffer, band 0 / channel 0
   float fft_re[kRingBlocks][kBinsPad];      // FftBuffer
@@ -255,7 +256,7 @@ struct CaptureBlockRec {   // BlockProcessorImpl::ProcessCapture: what EchoRemov
   int gain_change, delay_change, clock_drift;  // EchoPathVariability
   int est_has, est_delay;                   // estimated_delay_
 };
-struct TickScratch {
+struct alignas(16) TickScratch {
   int n_render_blocks, n_capture_blocks;
   int pad_[2];
   RenderInsertRec rins[3];
@@ -267,7 +268,7 @@ struct TickScratch {
 };
 
 // One call leg.
-struct StreamState {
+struct alignas(16) StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)
   // 1 once a capture frame has been processed.  Until then the reference may
   // still re-initialise on its first ProcessStream call (EngineConfig::
