@@ -55,7 +55,8 @@ for r in rows[hi + 1:]:
     per_line[loc] += n
     samp_line[loc] += s
     per_file[loc[0] if loc else None] += n
-    ops[text.split()[0] if not text.startswith("@") else text.split()[1]] += n
+    tk = text.split()
+    ops[(tk[1] if tk and tk[0].startswith("@") and len(tk) > 1 else tk[0]) if tk else "?"] += n
     total += n
 print("total warp instructions executed: %d" % total)
 print("\nby file:")

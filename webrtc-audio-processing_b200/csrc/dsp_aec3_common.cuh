@@ -8,6 +8,8 @@
 // __syncwarp().  All per-stream branches are warp-uniform.
 #pragma once
 
+#include <stddef.h>
+
 #include "dsp_fft.cuh"
 #include "dsp_filters.cuh"
 #include "wap_dev.cuh"
@@ -98,17 +100,33 @@ struct AecMfScratch {
   int peak[kNumMatchedFilters];
 };
 struct AecRemoverScratch {
-  float e_ref[kBlock], e_coa[kBlock], s_ref[kBlock], s_coa[kBlock], e[kBlock];
-  float Er_re[kBinsPad], Er_im[kBinsPad], Ec_re[kBinsPad], Ec_im[kBinsPad];
-  float E2_ref[kBinsPad], E2_coa[kBinsPad];
-  float X2_ref[kBinsPad], X2_coa[kBinsPad];
-  float G_re[kBinsPad], G_im[kBinsPad];      // S (filter output) then G (update gain)
-  float Y_re[kBinsPad], Y_im[kBinsPad], E_re[kBinsPad], E_im[kBinsPad];
-  float Y2[kBinsPad], E2[kBinsPad], S2_lin[kBinsPad], R2[kBinsPad], R2_unb[kBinsPad];
-  float N_re[kBinsPad], N_im[kBinsPad];      // comfort noise
-  float gain[kBinsPad];
-  float v0[kBinsPad], v1[kBinsPad], v2[kBinsPad], v3[kBinsPad], v4[kBinsPad];
+  float e_ref[kBlock], e_coa[kBlock], e[kBlock];
+  float v0[kBinsPad], v1[kBinsPad], v2[kBinsPad], v3[kBinsPad];
   float x_aligned[kBlock];                   // render block at -MinDirectPathFilterDelay
+  // The linear stage (Subtractor::Process) and the stages after it never need their
+  // vectors at the same time; only e_ref / e_coa and the scalar metrics cross over.
+  union {
+    struct {  // Subtractor::Process
+      float s_ref[kBlock], s_coa[kBlock];
+      float Er_re[kBinsPad], Er_im[kBinsPad], Ec_re[kBinsPad], Ec_im[kBinsPad];
+      float E2_ref[kBinsPad], E2_coa[kBinsPad];
+      float X2_ref[kBinsPad], X2_coa[kBinsPad];
+      float G_re[kBinsPad], G_im[kBinsPad];      // refined update gain
+    };
+    struct {  // AecState / CNG / residual echo / suppression gain / suppression filter
+      float Y_re[kBinsPad], Y_im[kBinsPad], E_re[kBinsPad], E_im[kBinsPad];
+      float Y2[kBinsPad], E2[kBinsPad], S2_lin[kBinsPad], R2[kBinsPad], R2_unb[kBinsPad];
+      float N_re[kBinsPad], N_im[kBinsPad];      // comfort noise
+      float gain[kBinsPad];
+    };
+  };
+};
+struct AecEchoScratch {     // k_echo only
+  float fftA[128];         // lanes 0-15
+  float fftB[128];         // lanes 16-31
+  float x[kBlock];         // render block being inserted / GetBlock(0)
+  float y[kBlock];         // capture block (in / out)
+  AecRemoverScratch rm;
 };
 struct AecScratch {
   Aec3Scalars s;           // staged copy of Aec3State::s
@@ -116,15 +134,20 @@ struct AecScratch {
   float red[32];           // reduction / broadcast exchange
   int ired[32];
   union {
-    AecMfScratch mf;
-    AecRemoverScratch rm;
+    AecMfScratch mf;       // k_delay
+    struct {               // k_echo (same members as AecEchoScratch)
+      float fftA[128];
+      float fftB[128];
+      float x[kBlock];
+      float y[kBlock];
+      AecRemoverScratch rm;
+    };
   };
-  // k_echo only:
-  float fftA[128];         // lanes 0-15
-  float fftB[128];         // lanes 16-31
-  float x[kBlock];         // render block being inserted / GetBlock(0)
-  float y[kBlock];         // capture block (in / out)
 };
+// Each kernel allocates the common head plus its own member of the union.
+constexpr size_t kAecScratchHead = offsetof(AecScratch, mf);
+constexpr size_t kAecDelayScratchBytes = kAecScratchHead + sizeof(AecMfScratch);
+constexpr size_t kAecEchoScratchBytes = kAecScratchHead + sizeof(AecEchoScratch);
 
 WAP_DEV int ring_inc(int i, int size) { return i < size - 1 ? i + 1 : 0; }
 WAP_DEV int ring_dec(int i, int size) { return i > 0 ? i - 1 : size - 1; }

@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(128, 4) k_delay(TickArgs a, int scratch_floats
   }
 }
 
-__global__ void __launch_bounds__(128, 4) k_echo(TickArgs a, int scratch_floats) {
+#ifndef WAP_ECHO_MINBLOCKS
+#define WAP_ECHO_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -272,7 +275,12 @@ WapEngine* g_default_engines[8] = {nullptr};
 
 extern "C" {
 
-const char* wap_version(void) { return "wap_b200 0.1 (sm_100a)"; }
+const char* wap_version(void) {
+  static char v[160];
+  snprintf(v, sizeof(v), "wap_b200 0.2 (sm_100a; per-warp smem: k_delay %d B, k_echo %d B at 16 kHz; k_echo min blocks/SM %d)",
+           wap::delay_scratch_floats() * 4, wap::echo_scratch_floats(1) * 4, WAP_ECHO_MINBLOCKS);
+  return v;
+}
 
 WapConfig wap_config_default(void) {
   // Defaults of AudioProcessing::Config (api/audio/audio_processing.h:137-376).

@@ -18,13 +18,11 @@ namespace wap {
 
 // Shared-memory footprint of one warp, in floats.
 constexpr int kScratchFloatsDsp =
-    (int)((sizeof(NsScratch) > sizeof(AecScratch) ? sizeof(NsScratch) : sizeof(AecScratch)) / sizeof(float)) + 4;
-// k_echo: two frame buffers + the DSP scratch; k_delay: the AEC3 scratch only.
+    (int)((sizeof(NsScratch) > kAecEchoScratchBytes ? sizeof(NsScratch) : kAecEchoScratchBytes) / sizeof(float)) + 4;
+// k_echo: two frame buffers + the DSP scratch; k_delay: the AEC3 delay-stage scratch only.
 // (rounded to 16 bytes: the scratch structs hold 128-bit aligned members)
 inline int echo_scratch_floats(int bands) { return (2 * kFrame * bands + kScratchFloatsDsp + 3) & ~3; }
-inline int delay_scratch_floats() {
-  return ((int)((offsetof(AecScratch, mf) + sizeof(AecMfScratch)) / sizeof(float)) + 4 + 3) & ~3;
-}
+inline int delay_scratch_floats() { return ((int)(kAecDelayScratchBytes / sizeof(float)) + 4 + 3) & ~3; }
 static_assert(offsetof(StreamState, aec) % 16 == 0 && offsetof(Aec3State, mf_h) % 16 == 0 &&
                   sizeof(StreamState) % 16 == 0 && offsetof(AecScratch, mf) % 16 == 0,
               "128-bit accesses need 16-byte aligned state and scratch members");
