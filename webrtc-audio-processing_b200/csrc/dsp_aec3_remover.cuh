@@ -792,6 +792,9 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   Aec3Scalars& s = sc.s;
   AecRemoverScratch& r = sc.rm;
   __syncwarp();
+  // The estimator vectors and time-domain memories the stages after the linear filter touch
+  // (H_error .. output_framer, contiguous in the slab): on their way while the subtractor runs.
+  warp_prefetch_l1(a.H_error, (int)(reinterpret_cast<const char*>(a.render_decimator) - reinterpret_cast<const char*>(a.H_error)));
   // x = render_buffer->GetBlock(0)
   {
     const float* xb = a.blocks[s.blocks_read];

@@ -184,7 +184,18 @@ WAP_DEV void fir_filter_both(const Aec3State& a, AecScratch& sc, int P_r, int P_
   const int pos = sc.s.spectra_read;
   const int pmax = imax(P_r, P_c);
   __syncwarp();
-  for (int k = lane; k < kBins; k += 32) {
+  // Bin 64 (real only: FftData::CopyToPackedArray drops im[64]) would cost a third, almost empty
+  // pass of the loop below.  Instead lane p forms partition p's term and the terms are added in
+  // partition order through shuffles -- the same sequence of additions.
+  float t_ref = 0.f, t_coa = 0.f;
+  if (lane < pmax) {
+    const int row = ring_row(pos, lane);
+    const float X_re = a.fft_re[row][64], X_im = a.fft_im[row][64];
+    if (lane < P_r) t_ref = X_re * a.Hr_re[lane][64] - X_im * a.Hr_im[lane][64];
+    if (lane < P_c) t_coa = X_re * a.Hc_re[lane][64] - X_im * a.Hc_im[lane][64];
+  }
+#pragma unroll
+  for (int k = lane; k < 64; k += 32) {
     float Xr[kMaxPartitions], Xi[kMaxPartitions];
 #pragma unroll
     for (int p = 0; p < kMaxPartitions; ++p) {
@@ -208,7 +219,6 @@ WAP_DEV void fir_filter_both(const Aec3State& a, AecScratch& sc, int P_r, int P_
       }
     }
     if (k == 0) sc.fftA[0] = S_re;
-    else if (k == 64) sc.fftA[1] = S_re;
     else { sc.fftA[2 * k] = S_re; sc.fftA[2 * k + 1] = S_im; }
 #pragma unroll
     for (int p = 0; p < kMaxPartitions; ++p) {
@@ -225,8 +235,20 @@ WAP_DEV void fir_filter_both(const Aec3State& a, AecScratch& sc, int P_r, int P_
       }
     }
     if (k == 0) sc.fftB[0] = S_re;
-    else if (k == 64) sc.fftB[1] = S_re;
     else { sc.fftB[2 * k] = S_re; sc.fftB[2 * k + 1] = S_im; }
+  }
+  {
+    float S_ref = 0.f, S_coa = 0.f;
+#pragma unroll
+    for (int p = 0; p < kMaxPartitions; ++p) {
+      const float tr = __shfl_sync(WAP_FULL, t_ref, p), tc = __shfl_sync(WAP_FULL, t_coa, p);
+      if (p < P_r) S_ref = S_ref + tr;
+      if (p < P_c) S_coa = S_coa + tc;
+    }
+    if (lane == 0) {
+      sc.fftA[1] = S_ref;
+      sc.fftB[1] = S_coa;
+    }
   }
 }
 
@@ -271,7 +293,27 @@ WAP_DEV void fir_adapt_both(Aec3State& a, AecScratch& sc, int P_r, int P_c, cons
   const int lane = lane_id();
   const int pos = sc.s.spectra_read;
   const int pmax = coarse ? imax(P_r, P_c) : P_r;
-  for (int k = lane; k < kBins; k += 32) {
+  // Bin 64: one partition per lane instead of a third, almost empty pass over the bins.
+  if (lane < pmax) {
+    const int row = ring_row(pos, lane);
+    const float X_re = a.fft_re[row][64], X_im = a.fft_im[row][64];
+    if (lane < P_r) {
+      const float Gre = Gr_re[64], Gim = Gr_im[64];
+      const float aa = X_re * Gre, bb = X_im * Gim, cc = X_re * Gim, dd = X_im * Gre;
+      const float re = a.Hr_re[lane][64] + (aa + bb), im = a.Hr_im[lane][64] + (cc - dd);
+      a.Hr_re[lane][64] = re;
+      a.Hr_im[lane][64] = im;
+      a.H2[lane][64] = h2_bin(re, im, 64);
+    }
+    if (coarse && lane < P_c) {
+      const float Gre = Gc_re[64], Gim = Gc_im[64];
+      const float aa = X_re * Gre, bb = X_im * Gim, cc = X_re * Gim, dd = X_im * Gre;
+      a.Hc_re[lane][64] = a.Hc_re[lane][64] + (aa + bb);
+      a.Hc_im[lane][64] = a.Hc_im[lane][64] + (cc - dd);
+    }
+  }
+#pragma unroll
+  for (int k = lane; k < 64; k += 32) {
     float Xr[kMaxPartitions], Xi[kMaxPartitions];
 #pragma unroll
     for (int p = 0; p < kMaxPartitions; ++p) {
@@ -384,11 +426,14 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
   AecRemoverScratch& r = sc.rm;
   __syncwarp();
   const int P_r = s.fr_current_size, P_c = s.fc_current_size;
-  // RenderBuffer::SpectralSum(s) (render_buffer.cc:42-83): one running sum per bin.
+  // RenderBuffer::SpectralSum(s) (render_buffer.cc:42-83): one running sum per bin (bin 64: one
+  // partition per lane, added in order through shuffles).
   {
     const int pmax = imax(P_r, P_c);
     const int pos = s.spectra_read;
-    for (int k = lane; k < kBins; k += 32) {
+    const float x64 = lane < pmax ? a.spectra[ring_row(pos, lane)][64] : 0.f;
+#pragma unroll
+    for (int k = lane; k < 64; k += 32) {
       float X2[kMaxPartitions];
 #pragma unroll
       for (int j = 0; j < kMaxPartitions; ++j) X2[j] = j < pmax ? a.spectra[ring_row(pos, j)][k] : 0.f;
@@ -399,6 +444,14 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
         if (j + 1 == P_r) r.X2_ref[k] = x2;
         if (j + 1 == P_c) r.X2_coa[k] = x2;
       }
+    }
+    float x2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxPartitions; ++j) {
+      const float t = __shfl_sync(WAP_FULL, x64, j);
+      if (j < pmax) x2 += t;
+      if (lane == 0 && j + 1 == P_r) r.X2_ref[64] = x2;
+      if (lane == 0 && j + 1 == P_c) r.X2_coa[64] = x2;
     }
   }
   fir_filter_both(a, sc, P_r, P_c);

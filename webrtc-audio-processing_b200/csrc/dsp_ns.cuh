@@ -14,7 +14,7 @@ namespace wap {
 
 // Per-warp shared-memory scratch for the NS stage.
 struct NsScratch {
-  float buf[256];            // extended frame / packed spectrum
+  float buf[256 + 8];        // extended frame / packed spectrum (+ room for two 129-term chains)
   float spec[kNsBinsPad];    // magnitude spectrum
   float prior[kNsBinsPad];   // prior SNR  (Analyze) / filter (Process)
   float post[kNsBinsPad];    // post SNR
@@ -105,31 +105,25 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   ns_magnitude(sc.buf, sc.spec);
 
   // signal_energy, signal_spectral_sum, conservative-noise average, and the
-  // flatness log-sum are four independent serial chains.
+  // flatness log-sum are four independent serial chains (std::accumulate order).  Their
+  // terms are formed by all lanes first, so that the four chains then run the SAME
+  // instruction stream on four lanes (one pointer each) instead of four divergent loops.
   {
     const float* a = sc.buf;
-    const float* spec = sc.spec;
-    const float* cn = st.conservative_noise;
-    if (lane == 0) {
-      float s = 0.f;
-      for (int i = 0; i < kNsBins; ++i) {
-        const float re = (i == 0) ? a[0] : (i == 128 ? a[1] : a[2 * i]);
-        const float im = (i == 0 || i == 128) ? 0.f : a[2 * i + 1];
-        s += re * re + im * im;
-      }
-      sc.red[0] = s;
-    } else if (lane == 1) {
-      float s = 0.f;
-      for (int i = 0; i < kNsBins; ++i) s += spec[i];
-      sc.red[1] = s;
-    } else if (lane == 2) {
-      float s = 0.f;
-      for (int i = 0; i < kNsBins; ++i) s += cn[i];
-      sc.red[2] = s;
-    } else if (lane == 3) {
-      float s = 0.f;
-      for (int i = 1; i < kNsBins; ++i) s += ns_log_approx(spec[i]);
-      sc.red[3] = s;
+    for (int i = lane; i < kNsBins; i += 32) {
+      const float re = (i == 0) ? a[0] : (i == 128 ? a[1] : a[2 * i]);
+      const float im = (i == 0 || i == 128) ? 0.f : a[2 * i + 1];
+      sc.prior[i] = re * re + im * im;
+      sc.post[i] = st.conservative_noise[i];
+      sc.tmp[i] = ns_log_approx(sc.spec[i]);   // also the input of the quantile estimator below
+    }
+    __syncwarp();
+    if (lane < 4) {
+      const float* p = lane == 0 ? sc.prior : lane == 1 ? sc.spec : lane == 2 ? sc.post : sc.tmp;
+      float s = (lane == 3) ? 0.f : p[0];      // the log-sum starts at bin 1; 0.f + p[0] == p[0]
+#pragma unroll 4
+      for (int i = 1; i < kNsBins; ++i) s += p[i];
+      sc.red[lane] = s;
     }
     __syncwarp();
   }
@@ -146,8 +140,6 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   {
     int counter[3] = {st.q_counter[0], st.q_counter[1], st.q_counter[2]};
     int num_updates = st.q_num_updates;
-    __syncwarp();
-    for (int i = lane; i < kNsBins; i += 32) sc.tmp[i] = ns_log_approx(sc.spec[i]);
     __syncwarp();
     for (int s = 0; s < 3; ++s) {
       const float one_by_counter_plus_1 = 1.f / ((float)counter[s] + 1.f);
@@ -292,13 +284,26 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   {
     const float noise_average = noise_sum * (1.f / kNsBins);
     const float signal_average = signal_spectral_sum * (1.f / kNsBins);
+    // three chains (covariance, noise variance, signal variance): terms by all lanes, then
+    // the same serial loop on three lanes.  sc.tmp and sc.buf (the packed spectrum) are free
+    // here; sc.prior / sc.post hold the SNRs the LRT update still needs.
+    float* t0 = sc.tmp;
+    float* t1 = sc.buf;
+    float* t2 = sc.buf + 132;
+    __syncwarp();
+    for (int i = lane; i < kNsBins; i += 32) {
+      const float sd = sc.spec[i] - signal_average;
+      const float nd = st.conservative_noise[i] - noise_average;
+      t0[i] = sd * nd;
+      t1[i] = nd * nd;
+      t2[i] = sd * sd;
+    }
+    __syncwarp();
     if (lane < 3) {
+      const float* p = lane == 0 ? t0 : lane == 1 ? t1 : t2;
       float s = 0.f;
-      for (int i = 0; i < kNsBins; ++i) {
-        const float sd = sc.spec[i] - signal_average;
-        const float nd = st.conservative_noise[i] - noise_average;
-        s += (lane == 0) ? sd * nd : (lane == 1 ? nd * nd : sd * sd);
-      }
+#pragma unroll 4
+      for (int i = 0; i < kNsBins; ++i) s += p[i];
       sc.red[8 + lane] = s;
     }
     __syncwarp();
@@ -492,7 +497,7 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   const int naf = st.num_analyzed_frames;
   ns_form_windowed_frame(bands, st.process_mem, sc.buf);
   // energies_before_filtering: serial sum over the 256 windowed samples.
-  const float energy_before = serial_sum_sq(sc.buf, 256);
+  const float energy_before = serial_sum_sq_v4(sc.buf, 256);
   __syncwarp();
   fft256_forward(sc.buf, lane);
   ns_magnitude(sc.buf, sc.spec);
@@ -564,7 +569,7 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   fft256_inverse(sc.buf, lane);
   for (int i = lane; i < 256; i += 32) sc.buf[i] *= (2.f / 256.f);
   __syncwarp();
-  const float energy_after = serial_sum_sq(sc.buf, 256);
+  const float energy_after = serial_sum_sq_v4(sc.buf, 256);
   __syncwarp();
   // synthesis window
   for (int i = lane; i < 256; i += 32) {

@@ -65,12 +65,28 @@ WAP_DEV int warp_or(int v) { return __any_sync(WAP_FULL, v); }
 // feeds a threshold decision.
 WAP_DEV float serial_sum(const float* p, int n) {
   float s = 0.f;
+#pragma unroll 4
   for (int i = 0; i < n; ++i) s += p[i];
   return s;
 }
 WAP_DEV float serial_sum_sq(const float* p, int n) {
   float s = 0.f;
+#pragma unroll 4
   for (int i = 0; i < n; ++i) s += p[i] * p[i];
+  return s;
+}
+// Same chains for 16-byte aligned shared-memory arrays with n % 4 == 0: 128-bit loads.
+WAP_DEV float serial_sum_sq_v4(const float* p, int n) {
+  float s = 0.f;
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll 4
+  for (int i = 0; i < n / 4; ++i) {
+    const float4 v = q[i];
+    s += v.x * v.x;
+    s += v.y * v.y;
+    s += v.z * v.z;
+    s += v.w * v.w;
+  }
   return s;
 }
 
@@ -89,6 +105,22 @@ WAP_DEV int warp_argmax_first(const float* p, int n) {
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
   return bi;
+}
+
+// Non-blocking prefetch of [p, p + bytes) into L1 / L2 by the whole warp (one 128-byte line per
+// lane and step).  Phases that follow find their state vectors on chip instead of paying one
+// exposed DRAM/L2 round trip per small loop.
+WAP_DEV void warp_prefetch_l1(const void* p, int bytes) {
+#if !defined(WAP_EMU)
+  const char* c = reinterpret_cast<const char*>(p);
+  for (int off = lane_id() * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + off));
+#endif
+}
+WAP_DEV void warp_prefetch_l2(const void* p, int bytes) {
+#if !defined(WAP_EMU)
+  const char* c = reinterpret_cast<const char*>(p);
+  for (int off = lane_id() * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#endif
 }
 
 WAP_DEV void warp_copy(float* dst, const float* src, int n) {

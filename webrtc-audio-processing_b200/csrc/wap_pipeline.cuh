@@ -75,6 +75,13 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   NsScratch& ns_sc = *reinterpret_cast<NsScratch*>(dsp);
   AecScratch& aec_sc = *reinterpret_cast<AecScratch*>(dsp);
 
+  // Start pulling in what the later phases stream: the noise suppressor's vectors (up to the
+  // histograms) and the two adaptive filters.
+  if (a.capture) {
+    if (cfg.ns_enabled) warp_prefetch_l2(&st.ns, (int)offsetof(NsState, hist_lrt));
+    if (cfg.aec_enabled)
+      warp_prefetch_l2(st.aec.Hr_re, (int)(reinterpret_cast<const char*>(st.aec.h_time) - reinterpret_cast<const char*>(st.aec.Hr_re)));
+  }
   // ---------------- render side: ring / FFT / spectrum writes for the blocks k_front sliced
   if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc);
   if (!a.capture) return;
