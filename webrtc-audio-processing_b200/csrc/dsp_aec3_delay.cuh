@@ -47,49 +47,64 @@ WAP_DEV float mf_hsum16(float acc) {
 }
 
 // One matched filter, 16 decimated capture samples, non-accumulating core
-// (matched_filter_avx2.cc:151-270), general version: handles the ring wrap inside the
-// window (chunked chains + scalar tails).  h lives in sc.mf.h, the window in sc.mf.xp.
+// (matched_filter_avx2.cc:151-270), general version for blocks in which the window crosses
+// the end of the reference's ring: per sample the 512 taps split at the wrap into two
+// chunks; in each chunk the first floor(len/16)*16 taps feed the 16 fused chains (lane =
+// tap index mod 16 WITHIN the chunk), the remaining len%16 taps are added to the scalar
+// sums with separate multiply and add, in order.  Lanes 0-15 run the h*x chains, lanes
+// 16-31 the x*x chains -- the same code on a per-lane operand pointer (h or x).
+// h lives in sc.mf.h, the window in sc.mf.xp.
 WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
   const int lane = lane_id();
   const int half = lane >> 4, L = lane & 15;
   float* h = sc.mf.h;
   float error_sum = 0.f;
   int updated = 0;
+#pragma unroll 1
   for (int i = 0; i < kSubBlock; ++i) {
     int x_start = sc.s.lr_read + n * kMfShift + kSubBlock - 1 - i;  // position in the reference's ring
     if (x_start >= kLowRateSize) x_start -= kLowRateSize;
     const float* x = sc.mf.xp + (kSubBlock - 1 - i);                // tap 0 of sample i
+    const float* pa = half ? x : h;                                  // first operand of this lane's chain
     const int chunk1 = imin(kMfLen, kLowRateSize - x_start);
     const int chunk2 = kMfLen - chunk1;
     const int v1 = chunk1 >> 4, v2 = chunk2 >> 4;
     float acc = 0.f;
-    for (int k = 0; k < v1; ++k) {
-      const int t = L + 16 * k;
-      const float xv = x[t];
-      acc = half ? fmaf(xv, xv, acc) : fmaf(h[t], xv, acc);
+    {
+      const float* qa = pa + L;
+      const float* qx = x + L;
+      int k = 0;
+      for (; k + 4 <= v1; k += 4, qa += 64, qx += 64) {
+        acc = fmaf(qa[0], qx[0], acc);
+        acc = fmaf(qa[16], qx[16], acc);
+        acc = fmaf(qa[32], qx[32], acc);
+        acc = fmaf(qa[48], qx[48], acc);
+      }
+      for (; k < v1; ++k, qa += 16, qx += 16) acc = fmaf(qa[0], qx[0], acc);
+      qa = pa + chunk1 + L;
+      qx = x + chunk1 + L;
+      for (k = 0; k + 4 <= v2; k += 4, qa += 64, qx += 64) {
+        acc = fmaf(qa[0], qx[0], acc);
+        acc = fmaf(qa[16], qx[16], acc);
+        acc = fmaf(qa[32], qx[32], acc);
+        acc = fmaf(qa[48], qx[48], acc);
+      }
+      for (; k < v2; ++k, qa += 16, qx += 16) acc = fmaf(qa[0], qx[0], acc);
     }
-    for (int k = 0; k < v2; ++k) {
-      const int t = chunk1 + L + 16 * k;
-      const float xv = x[t];
-      acc = half ? fmaf(xv, xv, acc) : fmaf(h[t], xv, acc);
+    acc = mf_hsum16(acc);   // uniform within each half: h*x on lanes 0-15, x*x on lanes 16-31
+    // Scalar tails: r1 taps after chunk 1's groups, then r2 after chunk 2's (r1 + r2 is 0 or 16).
+    // One product per lane, then the additions in tap order through shuffles.
+    const int r1 = chunk1 & 15, r2 = chunk2 & 15;
+    float tail = 0.f;
+    if (r1 + r2) {
+      const int t = L < r1 ? 16 * v1 + L : chunk1 + 16 * v2 + (L - r1);
+      const float p = pa[t] * x[t];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tail += __shfl_sync(WAP_FULL, p, (lane & 16) | j);
     }
-    acc = mf_hsum16(acc);
-    const float vec_s = __shfl_sync(WAP_FULL, acc, 0);
-    const float vec_x2 = __shfl_sync(WAP_FULL, acc, 16);
-    // Scalar remainders of the two chunks (separate multiply and add), in order.
-    float s = 0.f, x2_sum = 0.f;
-    for (int t = 16 * v1; t < chunk1; ++t) {
-      const float xk = x[t];
-      x2_sum += xk * xk;
-      s += h[t] * xk;
-    }
-    for (int t = chunk1 + 16 * v2; t < kMfLen; ++t) {
-      const float xk = x[t];
-      x2_sum += xk * xk;
-      s += h[t] * xk;
-    }
-    x2_sum += vec_x2;
-    s += vec_s;
+    const float mine = tail + acc;                      // reference: s += vec (x2_sum += vec)
+    const float s = __shfl_sync(WAP_FULL, mine, 0);
+    const float x2_sum = __shfl_sync(WAP_FULL, mine, 16);
     const float yi = y[i];
     const float e = yi - s;
     const bool saturation = yi >= 32000.f || yi <= -32000.f;
@@ -97,14 +112,23 @@ WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out
     __syncwarp();
     if (x2_sum > kMfX2SumThreshold && !saturation) {
       const float alpha = ec3::kMfSmoothing * e / x2_sum;
-      // Vector part of each chunk is fused, the (<8 tap) tails are not.
-      const int f1 = (chunk1 >> 3) << 3;
-      const int f2 = chunk1 + ((chunk2 >> 3) << 3);
-      for (int t = lane; t < kMfLen; t += 32) {
-        const bool fused = (t < chunk1) ? (t < f1) : (t < f2);
-        const float xv = x[t];
-        h[t] = fused ? fmaf(xv, alpha, h[t]) : h[t] + alpha * xv;
+      // The groups of 8 of each chunk are fused, the (< 8 tap) ends are not: those few taps are
+      // computed unfused from the old h first and written over the fused result afterwards.
+      const int f1 = chunk1 & ~7, n1 = chunk1 - f1;
+      const int f2 = chunk1 + (chunk2 & ~7), n2 = kMfLen - f2;
+      int tn = -1;
+      float hn = 0.f;
+      if (lane < n1) tn = f1 + lane;
+      else if (lane - n1 < n2) tn = f2 + (lane - n1);
+      if (tn >= 0) hn = h[tn] + alpha * x[tn];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < kMfLen / 32; ++k) {
+        const int t = lane + 32 * k;
+        h[t] = fmaf(x[t], alpha, h[t]);
       }
+      __syncwarp();
+      if (tn >= 0) h[tn] = hn;
       updated = 1;
     }
     __syncwarp();
