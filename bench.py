@@ -219,6 +219,7 @@ def run_b200(a):
 
     def tick_device(t):
         k = t % CYCLE
+        L.wap_streams_set_delay_ms(eng.handles, S, 0)   # set_stream_delay_ms(0) per leg, as the reference arm
         err = L.wap_process_streams_device(eng.h, eng.handles, S, render[k].data_ptr(), capture[k].data_ptr(),
                                            out.data_ptr(), 0)
         assert err == 0, err
@@ -275,11 +276,11 @@ def run_b200(a):
 
     def tick_host(tt):
         k = tt % CYCLE
+        L.wap_streams_set_delay_ms(eng.handles, S, 0)
         err = L.wap_process_streams(eng.handles, S, h_r[k].ctypes.data_as(C.c_void_p), h_c[k].ctypes.data_as(C.c_void_p),
                                     h_o.ctypes.data_as(C.c_void_p), 0, None)
         assert err == 0, err
     for _ in range(3):
-        eng.set_stream_delay_ms(0)
         tick_host(t); t += 1
     barrier()
     w0 = time.perf_counter()

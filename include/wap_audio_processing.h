@@ -188,6 +188,9 @@ double wap_engine_algorithmic_bytes_per_frame(const WapEngine* engine);
 WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, const void* render_frames,
                              const void* capture_frames, void* out_frames, WapSampleFormat fmt,
                              WapError* per_stream_err);
+/* set_stream_delay_ms(delay_ms) on `n` legs at once (same clamp / warning code as the
+ * single-leg call); the per-tick companion of wap_process_streams. */
+WapError wap_streams_set_delay_ms(WapAudioProcessing* const* handles, int32_t n, int delay_ms);
 /* Same, but the three buffers are DEVICE pointers on the engine's GPU and the
  * call only enqueues the tick on the engine's CUDA stream. */
 WapError wap_process_streams_device(WapEngine* engine, WapAudioProcessing* const* handles, int32_t n,

@@ -220,6 +220,20 @@ WapError ensure_staging(WapEngine* e, size_t n) {
   return WapError::None;
 }
 
+bool is_pinned_host(const void* p) {
+#if defined(WAP_EMU)
+  (void)p;
+  return false;
+#else
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();  // unregistered host memory on older runtimes: clear the error
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+#endif
+}
+
 int grid_for(int n_streams) {
   const int wpb = 4;
   int blocks = (n_streams + wpb - 1) / wpb;
@@ -449,17 +463,26 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
   const size_t bytes = (size_t)n * e->frame_len * esz;
   unsigned char* hp = static_cast<unsigned char*>(e->h_pinned);
   const size_t stride = e->staged_streams * e->frame_len * sizeof(float);
-  if (render) {
+  // Page-locked caller buffers are copied from / to directly; pageable ones go through the
+  // engine's pinned staging area.
+  const void* src_r = render;
+  const void* src_c = capture;
+  if (render && !is_pinned_host(render)) {
     memcpy(hp, render, bytes);
-    WAP_CUDA(cudaMemcpyAsync(e->d_render, hp, bytes, cudaMemcpyHostToDevice, e->stream));
+    src_r = hp;
   }
-  memcpy(hp + stride, capture, bytes);
-  WAP_CUDA(cudaMemcpyAsync(e->d_capture, hp + stride, bytes, cudaMemcpyHostToDevice, e->stream));
+  if (!is_pinned_host(capture)) {
+    memcpy(hp + stride, capture, bytes);
+    src_c = hp + stride;
+  }
+  if (render) WAP_CUDA(cudaMemcpyAsync(e->d_render, src_r, bytes, cudaMemcpyHostToDevice, e->stream));
+  WAP_CUDA(cudaMemcpyAsync(e->d_capture, src_c, bytes, cudaMemcpyHostToDevice, e->stream));
   err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
   if (err != WapError::None) return err;
-  WAP_CUDA(cudaMemcpyAsync(hp + 2 * stride, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+  const bool out_pinned = is_pinned_host(out);
+  WAP_CUDA(cudaMemcpyAsync(out_pinned ? out : (void*)(hp + 2 * stride), e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
   WAP_CUDA(cudaStreamSynchronize(e->stream));
-  memcpy(out, hp + 2 * stride, bytes);
+  if (!out_pinned) memcpy(out, hp + 2 * stride, bytes);
   for (int i = 0; i < n; ++i) handles[i]->was_stream_delay_set = false;  // audio_processing_impl.cc:1556
   if (per_stream_err) for (int i = 0; i < n; ++i) per_stream_err[i] = WapError::None;
   return WapError::None;

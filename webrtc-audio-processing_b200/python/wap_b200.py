@@ -80,7 +80,7 @@ EXPORTS = [
     "wap_engine_create", "wap_engine_destroy", "wap_engine_create_streams", "wap_engine_state_bytes_per_stream",
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
-    "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
+    "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
 ]
 
 _libs = {}
@@ -126,6 +126,7 @@ def load(path=None):
     L.wap_engine_cuda_stream.argtypes = [vp]
     L.wap_engine_launch_count.restype = C.c_int64
     L.wap_engine_launch_count.argtypes = [vp]
+    L.wap_streams_set_delay_ms.argtypes = [vp, i32, C.c_int]
     L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
     L.wap_engine_read_kernel_timing.restype = C.c_int64
     L.wap_engine_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double)]
@@ -167,8 +168,7 @@ class Engine:
             raise RuntimeError("wap_engine_create_streams: " + ERRORS.get(err, str(err)))
 
     def set_stream_delay_ms(self, ms):
-        for h in self.handles:
-            self.lib.wap_set_stream_delay_ms(h, ms)
+        self.lib.wap_streams_set_delay_ms(self.handles, self.n, ms)
 
     def process(self, render, capture):
         """render/capture: [n, frame] int16 or float32 (render may be None). Returns out [n, frame]."""
