@@ -27,6 +27,7 @@ def lib():
         L.ref_apm_tick_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_apm_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_apm_set_capture_output_used.argtypes = [C.c_void_p, C.c_int]
         L.ref_apm_bench.restype = C.c_double
         L.ref_apm_bench.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_size_t]
         L.ref_fft128.argtypes = [C.c_void_p, C.c_int]
@@ -81,6 +82,9 @@ class RefApm:
         out = np.zeros_like(capture)
         err = lib().ref_apm_tick_f32(self.h, rate, render_ch, capture_ch, _p(render), _p(capture), _p(out))
         return out, err
+
+    def set_capture_output_used(self, used):
+        lib().ref_apm_set_capture_output_used(self.h, int(used))
 
     def stats(self):
         s = np.zeros(6, dtype=np.float32)

@@ -117,6 +117,10 @@ int ref_apm_tick_f32(void* p, int rate, int render_ch, int capture_ch,
   return e1 ? e1 : e2;
 }
 
+void ref_apm_set_capture_output_used(void* p, int used) {
+  static_cast<RefApm*>(p)->apm->set_output_will_be_muted(!used);
+}
+
 // stats: [has_erl, erl, has_erle, erle, has_delay, delay_ms]
 void ref_apm_stats(void* p, float* out6) {
   auto* h = static_cast<RefApm*>(p);

@@ -1,0 +1,125 @@
+"""The seam's contract exercised on the emulator build of the product sources:
+error codes, delay clamp, mute / un-mute, single-leg entry points, int16 / float equivalence.
+Mirrors the reference's APM API tests (tests/unit/audio_processing_unittest.cc,
+audio_processing_impl_unittest.cc) for the part of the surface the seam forwards."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import golden, synthetic_leg
+
+TOL = 1e-4 * 32768
+
+
+def _sc(wap_b200, rate, ch=1):
+    return wap_b200.WapStreamConfig(rate, ch)
+
+
+def test_error_codes_and_delay_clamp(emu_lib):
+    import wap_b200
+    L = emu_lib
+    h = L.wap_create()
+    assert h
+    x = np.zeros(160, np.int16)
+    y = np.zeros(160, np.int16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ok = _sc(wap_b200, 16000)
+    # audio_processing_impl.cc:163-323 through rust_audio_processing.cc:21-40
+    assert L.wap_process_stream_i16(h, p(x), 160, _sc(wap_b200, 7000), _sc(wap_b200, 7000), p(y), 160) == 3   # BadSampleRate
+    assert L.wap_process_stream_i16(h, p(x), 160, _sc(wap_b200, 16000, 0), ok, p(y), 160) == 4               # BadNumberChannels
+    assert L.wap_process_stream_i16(h, p(x), 100, ok, ok, p(y), 160) == 6                                     # BadDataLength
+    assert L.wap_process_stream_i16(None, p(x), 160, ok, ok, p(y), 160) == 1                                  # NullPointer
+    # set_stream_delay_ms clamps to [0, 500] and reports the warning (audio_processing_impl.cc:1689-1707)
+    assert L.wap_set_stream_delay_ms(h, 20) == 0 and L.wap_stream_delay_ms(h) == 20
+    assert L.wap_set_stream_delay_ms(h, -5) == 5 and L.wap_stream_delay_ms(h) == 0
+    assert L.wap_set_stream_delay_ms(h, 900) == 5 and L.wap_stream_delay_ms(h) == 500
+    # statistics are empty before the first capture frame (ApmStatsReporter::cached_stats_)
+    st = wap_b200.WapStats()
+    assert L.wap_get_statistics(h, C.byref(st)) == 0
+    assert not st.has_echo_return_loss and not st.has_delay_ms
+    L.wap_destroy(h)
+
+
+def test_single_leg_entry_points_match_the_reference(emu_lib, oracle):
+    """wap_process_reverse_stream_i16 + wap_set_stream_delay_ms + wap_process_stream_i16 on one
+    handle (what RustAudioProcessing forwards) == the reference, including GetStatistics."""
+    import wap_b200
+    L = emu_lib
+    far, near = synthetic_leg(9, 120)
+    ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near, stats_every=40)
+    assert err == 0
+    cfg = wap_b200.make_config(L, aec=True, ns=True, ns_level=1)
+    h = L.wap_create_with_config(cfg)
+    sc = _sc(wap_b200, 16000)
+    out = np.zeros_like(near)
+    scratch = np.zeros(160, np.int16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    stats = []
+    for f in range(120):
+        r = np.ascontiguousarray(far[f * 160:(f + 1) * 160])
+        c = np.ascontiguousarray(near[f * 160:(f + 1) * 160])
+        o = np.zeros(160, np.int16)
+        assert L.wap_process_reverse_stream_i16(h, p(r), 160, sc, sc, p(scratch), 160) == 0
+        assert np.array_equal(scratch, r)          # render passes through unchanged
+        assert L.wap_set_stream_delay_ms(h, 0) == 0
+        assert L.wap_process_stream_i16(h, p(c), 160, sc, sc, p(o), 160) == 0
+        out[f * 160:(f + 1) * 160] = o
+        if (f + 1) % 40 == 0:
+            st = wap_b200.WapStats()
+            L.wap_get_statistics(h, C.byref(st))
+            stats.append((st.echo_return_loss, st.echo_return_loss_enhancement, st.delay_ms))
+    L.wap_destroy(h)
+    assert np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
+    stats = np.array(stats)
+    assert np.abs(stats[:, 1] - ref_stats[:, 3]).max() <= 0.1
+    assert np.array_equal(stats[:, 2], ref_stats[:, 5])
+
+
+def test_float_and_int16_entry_points_agree(emu_lib):
+    import wap_b200
+    far, near = synthetic_leg(4, 60)
+    outs = []
+    for dt in (np.int16, np.float32):
+        eng = wap_b200.Engine(1, 16000, lib=emu_lib, aec=True, ns=True, ns_level=1)
+        o = []
+        for f in range(60):
+            r = far[f * 160:(f + 1) * 160][None, :]
+            c = near[f * 160:(f + 1) * 160][None, :]
+            if dt is np.float32:
+                r, c = (r / 32768.0).astype(np.float32), (c / 32768.0).astype(np.float32)
+            eng.set_stream_delay_ms(0)
+            y = eng.process(r, c)[0]
+            o.append(y if dt is np.int16 else y * 32768.0)
+        eng.close()
+        outs.append(np.concatenate(o).astype(np.float64))
+    # FloatS16ToS16 rounds; the float path keeps the fraction
+    assert np.abs(outs[0] - outs[1]).max() <= 0.5 + 1e-3
+
+
+def test_mute_unmute_matches_reference(emu_lib, oracle):
+    """set_output_will_be_muted: AEC3 skips the suppressor, NS its synthesis, and the first frame
+    after un-muting is zeroed (audio_processing_impl.cc:818-838,1450,1540-1552)."""
+    import wap_b200
+    far, near = synthetic_leg(2, 90)
+    ref = oracle.RefApm(aec=True, ns=True, ns_level=1)
+    eng = wap_b200.Engine(2, 16000, lib=emu_lib, aec=True, ns=True, ns_level=1)
+    ref_out = np.zeros_like(near)
+    out = np.zeros((2, near.size), np.int16)
+    for f in range(90):
+        if f == 30:
+            ref.set_capture_output_used(False)
+            eng.set_capture_output_used(False, legs=[0])   # leg 1 stays un-muted
+        if f == 60:
+            ref.set_capture_output_used(True)
+            eng.set_capture_output_used(True, legs=[0])
+        sl = slice(f * 160, (f + 1) * 160)
+        o, _, err = ref.run_i16(16000, far[sl], near[sl])
+        assert err == 0
+        ref_out[sl] = o
+        eng.set_stream_delay_ms(0)
+        out[:, sl] = eng.process(np.stack([far[sl]] * 2), np.stack([near[sl]] * 2))
+    eng.close()
+    assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
+    assert np.all(out[0][60 * 160:61 * 160] == 0)             # zeroed frame after un-muting
+    assert not np.array_equal(out[0], out[1])                  # the flag is per leg

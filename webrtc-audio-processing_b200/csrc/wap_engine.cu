@@ -131,6 +131,7 @@ struct WapAudioProcessing {
   int stream_delay_ms = 0;
   bool was_stream_delay_set = false;
   bool capture_output_used = true;
+  bool capture_output_used_dirty = false;  // not yet written to the leg's state slab
   int analog_level = 0;
   std::deque<std::vector<unsigned char>> render_queue;  // SwapQueue stand-in (aec3_common.h:41)
   WapSampleFormat render_fmt = WapSampleFormat::I16;
@@ -439,6 +440,15 @@ WapError wap_process_streams_device(WapEngine* e, WapAudioProcessing* const* han
     for (int i = 0; i < n; ++i) e->last_slots[i] = handles[i]->slot;
     WAP_CUDA(cudaMemcpyAsync(e->d_slots, e->last_slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    WapAudioProcessing* h = handles[i];
+    if (h->capture_output_used_dirty) {  // rare: un/mute events
+      const int v = h->capture_output_used ? 1 : 0;
+      WAP_CUDA(cudaMemcpyAsync(&e->d_states[h->slot].capture_output_used, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      WAP_CUDA(cudaStreamSynchronize(e->stream));
+      h->capture_output_used_dirty = false;
+    }
   }
   const int* d_delays = nullptr;
   if (!uniform) {

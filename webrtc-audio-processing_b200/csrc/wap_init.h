@@ -106,6 +106,8 @@ inline void init_aec3_state(Aec3State& a) {
 
 inline void init_stream_state(StreamState& st) {
   memset(&st, 0, sizeof(st));
+  st.capture_output_used = 1;
+  st.capture_output_used_last_frame = 1;
   init_ns_state(st.ns);
   init_aec3_state(st.aec);
 }

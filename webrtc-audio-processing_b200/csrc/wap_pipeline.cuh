@@ -59,12 +59,17 @@ WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
 // k_echo body: everything after the front end for one leg (reference
 // audio_processing_impl.cc:1359-1448 for the enabled submodules).
 WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
-  const EngineConfig& cfg = a.cfg;
+  EngineConfig cfg = a.cfg;
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
   const TickScratch& ts = st.tick;
+  // set_output_will_be_muted / kCaptureOutputUsed are per leg.
+  const bool output_used = st.capture_output_used != 0;
+  const bool output_used_last_frame = st.capture_output_used_last_frame != 0;
+  cfg.capture_output_used = output_used ? 1 : 0;
+  __syncwarp();
   float* full = scratch;
   float* bands = (B == 1) ? full : scratch + flen;
   unsigned dsp_off = 2u * (unsigned)flen;
@@ -95,6 +100,12 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
   if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
   __syncwarp();
+  // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
+  if (!output_used_last_frame && output_used) {
+    for (int i = lane_id(); i < flen; i += 32) full[i] = 0.f;
+    __syncwarp();
+  }
+  if (lane_id() == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
   store_frame(a.out, idx, flen, a.fmt, full);
 }
 

@@ -274,7 +274,11 @@ struct alignas(16) StreamState {
   // still re-initialise on its first ProcessStream call (EngineConfig::
   // reinit_on_first_capture) and render audio received earlier is lost.
   int seen_capture;
-  int pad_[3];
+  // AudioProcessingImpl::ApmCaptureState::{capture_output_used, capture_output_used_last_frame}
+  // (audio_processing_impl.cc:818-838,1540-1552); both start true.
+  int capture_output_used;
+  int capture_output_used_last_frame;
+  int pad_[1];
   ThreeBandState capture_bands; // AudioBuffer's SplittingFilter (48 kHz only)
   ThreeBandState render_bands;
   NsState ns;

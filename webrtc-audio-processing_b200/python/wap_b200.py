@@ -170,6 +170,10 @@ class Engine:
     def set_stream_delay_ms(self, ms):
         self.lib.wap_streams_set_delay_ms(self.handles, self.n, ms)
 
+    def set_capture_output_used(self, used, legs=None):
+        for i in (range(self.n) if legs is None else legs):
+            self.lib.wap_set_capture_output_used(self.handles[i], bool(used))
+
     def process(self, render, capture):
         """render/capture: [n, frame] int16 or float32 (render may be None). Returns out [n, frame]."""
         capture = np.ascontiguousarray(capture)
