@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import golden, run_engine, run_legs, synthetic_leg, vanishing_echo_leg
+from common import golden, run_engine, run_legs, synthetic_leg, synthetic_leg_48k, vanishing_echo_leg
 
 pytestmark = pytest.mark.gpu
 TOL_FS = 1e-4  # of full scale => 3.2768 int16 LSB
@@ -116,3 +116,20 @@ def test_aec3_echo_path_vanishes_loud_render(gpu_lib, oracle):
     assert err == 0
     out, stats = run_legs(gpu_lib, 16000, [(far, near)], stats_every=50, aec=True, ns=True, ns_level=1)
     _check_aec(out[0], stats[0], ref_out, ref_stats, "vanishing echo")
+
+
+def test_aec3_ns_parity_48k_three_band(gpu_lib, oracle):
+    """48 kHz mono AEC3 + NS (three bands, upper-band gain / comfort noise, PostFilter): the speech
+    fixture and six synthetic legs, two of them with a clipped, HF-heavy render."""
+    sp = golden("speech_48k.npz")
+    n = 300 * 480
+    legs = [(sp["far"][:n], sp["near"][:n])] + [synthetic_leg_48k(i, 300, 3.5 if i % 3 == 2 else 1.0) for i in range(6)]
+    out, stats = run_legs(gpu_lib, 48000, legs, stats_every=50, aec=True, ns=True, ns_level=1)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1, max_rate=48000).run_i16(
+            48000, far, near, stats_every=50)
+        assert err == 0
+        d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32))
+        assert d.max() <= TOL_FS * 32768, (k, int(d.max()))
+        assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1, k
+        assert np.array_equal(stats[k][:, 2], ref_stats[:, 5]), k

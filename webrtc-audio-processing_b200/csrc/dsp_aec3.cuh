@@ -58,6 +58,16 @@ WAP_DEV void framer_insert_and_extract(float* buffer, int* len, const float* blo
   if (lane == 0) *len = kBlock - samples_to_frame;
   __syncwarp();
 }
+// Same for an upper band, with the fill level passed by value.
+WAP_DEV void framer_insert_and_extract_local(float* buffer, int n, const float* block, float* sub_frame) {
+  const int lane = lane_id();
+  const int samples_to_frame = kSubFrame - n;
+  __syncwarp();
+  for (int i = lane; i < kSubFrame; i += 32) sub_frame[i] = i < n ? buffer[i] : block[i - n];
+  __syncwarp();
+  for (int i = lane; i < kBlock - samples_to_frame; i += 32) buffer[i] = block[samples_to_frame + i];
+  __syncwarp();
+}
 // BlockFramer::InsertBlock
 WAP_DEV void framer_insert(float* buffer, int* len, const float* block) {
   for (int i = lane_id(); i < kBlock; i += 32) buffer[i] = block[i];
@@ -133,22 +143,33 @@ WAP_DEV void aec3_delay_frame(Aec3State& a, TickScratch& ts, AecScratch& sc) {
 
 // ---------------------------------------------------------------- k_echo
 // Render blocks of this tick: vector half of the insert.
-WAP_DEV void aec3_echo_render(Aec3State& a, const TickScratch& ts, AecScratch& sc) {
+WAP_DEV void aec3_echo_render(Aec3State& a, const TickScratch& ts, AecScratch& sc, UpperBandState* up) {
   const int lane = lane_id();
   for (int r = 0; r < ts.n_render_blocks; ++r) {
     __syncwarp();
     for (int i = lane; i < kBlock; i += 32) sc.x[i] = ts.render_blocks[r][i];
     aec3_render_insert_vector(a, sc, ts.rins[r]);
+    if (up) {  // bands 1-2 of the block ring
+      const int bw = ts.rins[r].blocks_write;
+      for (int i = lane; i < 2 * kBlock; i += 32) (&up->blocks_hi[bw][0][0])[i] = (&up->render_blocks_hi[r][0][0])[i];
+    }
   }
 }
 
 // EchoRemover for capture block b (sc.y in/out) against the render-buffer view k_delay recorded.
-WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const TickScratch& ts, int b) {
+// 3-band legs: bands 1-2 of the block come back in sc.x / sc.rm.x_aligned.
+WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const TickScratch& ts, int b,
+                             UpperBandState* up) {
   const int lane = lane_id();
   __syncwarp();
   for (int i = lane; i < kBlock; i += 32) sc.y[i] = ts.capture_blocks[b][i];
   const CaptureBlockRec& rec = ts.crec[b];
   if (!rec.process) {
+    if (up)
+      for (int i = lane; i < kBlock; i += 32) {
+        sc.x[i] = up->capture_blocks_hi[b][0][i];
+        sc.rm.x_aligned[i] = up->capture_blocks_hi[b][1][i];
+      }
     __syncwarp();
     return;
   }
@@ -161,23 +182,38 @@ WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& 
   v.gain_change = rec.gain_change;
   v.delay_change = rec.delay_change;
   v.clock_drift = rec.clock_drift;
-  echo_remover_process_capture(a, cfg, sc, v, sc.s.saturated_microphone_signal != 0, rec.est_has, rec.est_delay);
+  echo_remover_process_capture(a, cfg, sc, v, sc.s.saturated_microphone_signal != 0, rec.est_has, rec.est_delay, up, b);
 }
 
 // EchoCanceller3::ProcessCapture for one capture frame (band 0 in place): the echo
 // remover on the 2-3 blocks k_front sliced, BlockFramer back into the frame.
 WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* band0, const TickScratch& ts,
-                               AecScratch& sc) {
+                               AecScratch& sc, UpperBandState* up) {
   aec3_stage_scalars(a, sc);
   // The staged read indices are the ones after the last block; blocks see their own.
   const int final_blocks_read = sc.s.blocks_read, final_spectra_read = sc.s.spectra_read;
   __syncwarp();
+  // BlockFramer per band: the three framers fill in lock-step, so the upper bands work on a
+  // copy of the band-0 fill level.
   for (int sub = 0; sub < 2; ++sub) {
-    aec3_echo_block(a, cfg, sc, ts, sub);
+    aec3_echo_block(a, cfg, sc, ts, sub, up);
+    const int len = sc.s.output_framer_len;
+    __syncwarp();
+    if (up) {
+      int l1 = len, l2 = len;
+      framer_insert_and_extract_local(up->output_framer_hi[0], l1, sc.x, band0 + kFrame + sub * kSubFrame);
+      framer_insert_and_extract_local(up->output_framer_hi[1], l2, sc.rm.x_aligned, band0 + 2 * kFrame + sub * kSubFrame);
+    }
     framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, band0 + sub * kSubFrame);
   }
   if (ts.n_capture_blocks == 3) {
-    aec3_echo_block(a, cfg, sc, ts, 2);
+    aec3_echo_block(a, cfg, sc, ts, 2, up);
+    if (up) {
+      for (int i = lane_id(); i < kBlock; i += 32) {
+        up->output_framer_hi[0][i] = sc.x[i];
+        up->output_framer_hi[1][i] = sc.rm.x_aligned[i];
+      }
+    }
     framer_insert(a.output_framer, &sc.s.output_framer_len, sc.y);
   }
   __syncwarp();

@@ -532,7 +532,9 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
 
 // ---- ComfortNoiseGenerator::Compute.  `nearend` = capture spectrum chosen by the caller.
 // Output: r.N_re / r.N_im (lower-band comfort noise).
-WAP_DEV void cng_compute(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const float* nearend) {
+// hi: also keep what the upper-band comfort noise needs -- r.v1 = sqrt spectrum, r.v3 / r.v2 = the
+// per-bin sqrt(2)*sin / sqrt(2)*cos factors, sc.red[24] = high_band_noise_level.
+WAP_DEV void cng_compute(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, const float* nearend, bool hi = false) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
   AecRemoverScratch& r = sc.rm;
@@ -560,17 +562,27 @@ WAP_DEV void cng_compute(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, 
     }
     // GenerateComfortNoise
     const float N = sqrtf(use_initial ? N2i : N2);
-    float re = 0.f, im = 0.f;
+    float re = 0.f, im = 0.f, fx = 0.f, fy = 0.f;
     if (k >= 1 && k < 64) {
       const unsigned seed_k = (kLcgA[k] * s.cng_seed + kLcgC[k]) & 0x7fffffffu;
       const int i = (int)(seed_k >> 26);
-      re = N * kSqrt2Sin[i];
-      im = N * kSqrt2Sin[(i + 8) & 31];
+      fx = kSqrt2Sin[i];
+      fy = kSqrt2Sin[(i + 8) & 31];
+      re = N * fx;
+      im = N * fy;
     }
     r.N_re[k] = re;
     r.N_im[k] = im;
+    if (hi) { r.v1[k] = N; r.v3[k] = fx; r.v2[k] = fy; }
   }
   __syncwarp();
+  if (hi) {
+    // high_band_noise_level = accumulate(N[32..64]) / 33 (comfort_noise_generator.cc:73-78)
+    constexpr float kOneByNumBands = 1.f / (kBins / 2 + 1);
+    float acc = 0.f;
+    for (int k = kBins / 2; k < kBins; ++k) acc += r.v1[k];
+    if (lane == 0) sc.red[24] = acc * kOneByNumBands;
+  }
   if (lane == 0) {
     if (!saturated_capture && has_initial) {
       ++s.cng_N2_counter;
@@ -785,9 +797,47 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   __syncwarp();
 }
 
+// ---- SuppressionGain::UpperBandsGain (suppression_gain.cc:124-217) for a 3-band leg.
+// sc.x = band 0 of the render block GetBlock(0), r.gain = lower-band gain (amplitude domain).
+WAP_DEV float upper_bands_gain(const Aec3State& a, AecScratch& sc, const UpperBandState& up, const float* echo_spectrum) {
+  const int lane = lane_id();
+  const Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  __syncwarp();
+  if (s.rsa_has_narrow_peak && s.rsa_narrow_peak_band > kBins - 10) return 0.001f;
+  // gain_below_8_khz = min over low_band_gain[32..64]
+  float g = r.gain[32 + lane];
+  if (lane == 0) g = fminr(g, r.gain[64]);
+  for (int m = 16; m; m >>= 1) g = fminf(g, __shfl_xor_sync(WAP_FULL, g, m));
+  const float gain_below_8_khz = g;
+  if (s.saturated_echo) return fminr(0.001f, gain_below_8_khz);
+  // band energies: three serial sums of squares (std::accumulate), one per lane
+  if (lane < 3) {
+    const float* p = lane == 0 ? sc.x : up.blocks_hi[s.blocks_read][lane - 1];
+    float acc = 0.f;
+    for (int i = 0; i < kBlock; ++i) acc = acc + p[i] * p[i];
+    sc.red[16 + lane] = acc;
+  }
+  __syncwarp();
+  const float low_band_energy = sc.red[16];
+  const float high_band_energy = fmaxr(fmaxr(0.f, sc.red[17]), sc.red[18]);
+  float anti_howling_gain;
+  const float activation_threshold = kBlock * 400.f;  // anti_howling_activation_threshold
+  if (high_band_energy < fmaxr(low_band_energy, activation_threshold)) anti_howling_gain = 1.f;
+  else anti_howling_gain = 1.f * sqrtf(low_band_energy / high_band_energy);  // anti_howling_gain = 1
+  // gain_bound: max_gain_during_echo == 1 in the default config, so the echo/noise test cannot lower it.
+  const float gain_bound = 1.f;
+  (void)echo_spectrum;
+  __syncwarp();
+  return fminr(fminr(gain_below_8_khz, anti_howling_gain), gain_bound);
+}
+
 // ---- EchoRemoverImpl::ProcessCapture.  sc.y = capture block (in/out).
+// `up` / `b`: 48 kHz legs only -- bands 1-2 of capture block b (up->capture_blocks_hi[b]) are
+// processed too and returned in sc.x (band 1) and sc.rm.x_aligned (band 2).
 WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, EchoPathVariability v,
-                                          bool capture_signal_saturation, int ext_has, int ext_delay) {
+                                          bool capture_signal_saturation, int ext_has, int ext_delay,
+                                          UpperBandState* up = nullptr, int b = 0) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
   AecRemoverScratch& r = sc.rm;
@@ -822,7 +872,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   }
   __syncwarp();
 
-  render_signal_analyzer_update(a, sc, s.fd_min_filter_delay);
+  render_signal_analyzer_update(a, sc, s.fd_min_filter_delay, up ? up->blocks_hi[s.blocks_read][0] : nullptr);
 
   if (s.init_transition_triggered) {
     if (lane == 0) {
@@ -882,7 +932,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   aec_state_update(a, sc, ext_has, ext_delay);
 
   const float* nearend = nearend_is_E2 ? r.E2 : r.Y2;
-  cng_compute(a, cfg, sc, nearend);
+  cng_compute(a, cfg, sc, nearend, up != nullptr);
 
   if (cfg.capture_output_used) {
     residual_echo_estimate(a, sc);
@@ -891,8 +941,10 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
       for (int k = lane; k < kBins; k += 32) r.E2[k] = fminr(r.E2[k], r.Y2[k]);
       __syncwarp();
     }
-    // echo_spectrum only matters for the upper bands (B > 1).
     suppression_gain_get_gain(a, sc, nearend, v.clock_drift != 0);
+    // SuppressionGain::UpperBandsGain (suppression_gain.cc:124-217); echo_spectrum = S2_linear or R2.
+    float high_bands_gain = 1.f;
+    if (up) high_bands_gain = upper_bands_gain(a, sc, *up, usable ? r.S2_lin : r.R2);
 
     // SuppressionFilter::ApplyGain
     const float* Yf_re = usable ? r.E_re : r.Y_re;
@@ -907,8 +959,14 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
       if (k == 0) sc.fftA[0] = re;
       else if (k == 64) sc.fftA[1] = re;
       else { sc.fftA[2 * k] = re; sc.fftA[2 * k + 1] = im; }
+      if (up) {  // comfort_noise_high_band (GenerateComfortNoise): level * (x, y), zero at DC / Nyquist
+        const float lvl = sc.red[24];
+        if (k == 0) sc.fftB[0] = 0.f;
+        else if (k == 64) sc.fftB[1] = 0.f;
+        else { sc.fftB[2 * k] = lvl * r.v3[k]; sc.fftB[2 * k + 1] = lvl * r.v2[k]; }
+      }
     }
-    fft_pair(sc, true, false);
+    fft_pair(sc, true, up != nullptr);
     constexpr float kIfftNormalization = 2.f / 128;
     for (int i = lane; i < kBlock; i += 32) {
       float e0 = a.e_output_old[i] * kSqrtHanning128[kBlock + i];
@@ -916,6 +974,29 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
       e0 = e0 * kIfftNormalization;
       a.e_output_old[i] = sc.fftA[kBlock + i];
       sc.y[i] = clampr(e0, -32768.f, 32767.f);
+    }
+    if (up) {
+      // Upper bands (suppression_filter.cc:153-181): gain, comfort noise on band 1, one block of
+      // delay (swap with e_output_old_), clamp.
+      const float noise_scaling = 0.4f * sqrtf(1.f - high_bands_gain * high_bands_gain);
+      const float ngain = noise_scaling * kIfftNormalization;
+      __syncwarp();
+      for (int i = lane; i < kBlock; i += 32) {
+        float e1 = up->capture_blocks_hi[b][0][i] * high_bands_gain;
+        e1 += sc.fftB[i] * ngain;
+        const float e2 = up->capture_blocks_hi[b][1][i] * high_bands_gain;
+        const float o1 = up->e_output_old_hi[0][i], o2 = up->e_output_old_hi[1][i];
+        up->e_output_old_hi[0][i] = e1;
+        up->e_output_old_hi[1][i] = e2;
+        sc.x[i] = clampr(o1, -32768.f, 32767.f);
+        r.x_aligned[i] = clampr(o2, -32768.f, 32767.f);
+      }
+    }
+  } else if (up) {
+    __syncwarp();
+    for (int i = lane; i < kBlock; i += 32) {
+      sc.x[i] = up->capture_blocks_hi[b][0][i];
+      r.x_aligned[i] = up->capture_blocks_hi[b][1][i];
     }
   }
   __syncwarp();

@@ -114,7 +114,8 @@ WAP_DEV void gain_update_current_config(float* cur, float* old, const float* tgt
 
 // RenderSignalAnalyzer::Update (render_signal_analyzer.cc:131-141) for the
 // spectrum at `delay_partitions` and the latest render block in sc.x.
-WAP_DEV void render_signal_analyzer_update(Aec3State& a, AecScratch& sc, int delay_partitions) {
+// x_band1: band 1 of the latest render block for 3-band legs (else nullptr).
+WAP_DEV void render_signal_analyzer_update(Aec3State& a, AecScratch& sc, int delay_partitions, const float* x_band1 = nullptr) {
   const int lane = lane_id();
   Aec3Scalars& s = sc.s;
   __syncwarp();
@@ -131,6 +132,8 @@ WAP_DEV void render_signal_analyzer_update(Aec3State& a, AecScratch& sc, int del
   const int peak_bin = warp_argmax_first(X2_latest, kBins);
   float max_abs_l = 0.f;
   for (int i = lane; i < kBlock; i += 32) max_abs_l = fmaxf(max_abs_l, fabsf(sc.x[i]));
+  if (x_band1)
+    for (int i = lane; i < kBlock; i += 32) max_abs_l = fmaxf(max_abs_l, fabsf(x_band1[i]));
   const float max_abs = warp_max(max_abs_l);
   if (lane == 0) {
     if (s.rsa_has_narrow_peak && ++s.rsa_narrow_peak_counter > kMaxPartitions) s.rsa_has_narrow_peak = 0;

@@ -144,6 +144,31 @@ WAP_DEV void three_band_analysis(const float* full, float* bands, float* sub, fl
   __syncwarp();
 }
 
+// The same analysis run by ONE thread (k_front, one thread per leg): identical expression
+// trees, the loops over the 160 output samples are simply serial.  `bands` must be zeroed by
+// the caller; `sub` is a 160-float thread-local scratch.
+WAP_DEV void three_band_analysis_thread(const float* full, float* bands, float* sub, float (*state)[16]) {
+  for (int ds = 0; ds < 3; ++ds) {
+    for (int k = 0; k < 160; ++k) sub[k] = full[2 - ds + 3 * k];
+    for (int shift = 0; shift < 4; ++shift) {
+      const int index = ds + shift * 3;
+      if (index == 3 || index == 9) continue;
+      const int fi = index < 3 ? index : (index < 9 ? index - 1 : index - 2);
+      for (int k = 0; k < 160; ++k) {
+        const float o = band_filter_sample(sub, state[fi], kBandFilter[fi], shift, k);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) bands[b * 160 + k] += kBandDct[fi][b] * o;
+      }
+    }
+    for (int shift = 0; shift < 4; ++shift) {
+      const int index = ds + shift * 3;
+      if (index == 3 || index == 9) continue;
+      const int fi = index < 3 ? index : (index < 9 ? index - 1 : index - 2);
+      for (int j = 0; j < 15; ++j) state[fi][j] = sub[160 - 15 + j];
+    }
+  }
+}
+
 // Synthesis: bands[3][160] -> full[480].  Reference ThreeBandFilterBank::Synthesis
 // (three_band_filter_bank.cc:233-278).
 WAP_DEV void three_band_synthesis(const float* bands, float* full, float* sub, float (*state)[16]) {

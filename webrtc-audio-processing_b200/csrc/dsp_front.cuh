@@ -86,6 +86,18 @@ WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const flo
   s.render_properly_started = 1;
 }
 
+// FrameBlocker for one upper band (no decimation, no bookkeeping): the continuous stream
+// [blocker buffer | 160 new samples] cut into `nb` blocks; the rest stays buffered.
+WAP_DEV void front_slice_band(const float* band, float* blocker, int L, int nb, float (*blocks)[2][kBlock], int bi) {
+  for (int b = 0; b < nb; ++b)
+    for (int j = 0; j < kBlock; ++j) {
+      const int k = kBlock * b + j - L;
+      blocks[b][bi][j] = k < 0 ? blocker[L + k] : band[k];
+    }
+  const int rem = L + kFrame - kBlock * nb;
+  for (int j = 0; j < rem; ++j) blocker[j] = band[kFrame - rem + j];
+}
+
 // The front end of one tick for leg `idx` (thread-private).
 WAP_DEV void front_leg(const TickArgs& a, int idx) {
   const EngineConfig& cfg = a.cfg;
@@ -96,15 +108,30 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   TickScratch& ts = st.tick;
   Aec3State& aec = st.aec;
   Aec3Scalars& s = aec.s;
+  UpperBandState* up = (B == 3 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
   const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
   const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
   // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
   // drains the render queue (audio_processing_impl.cc:1409-1415).
   if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms);
+  float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
+  float sub[kFrame];
 
-  // ---------------- render: FrameBlocker -> BlockProcessor::BufferRender
+  // ---------------- render: [band split] -> FrameBlocker -> BlockProcessor::BufferRender
   int nrb = 0;
   if (a.render && cfg.aec_enabled && render_live) {
+    const float* band0;
+    if (B == 3) {
+      // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
+      for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
+      float* full = ts.capture_frame;  // borrowed as the thread's 480-sample input buffer
+      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
+      three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
+      band0 = frame;
+    } else {
+      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
+      band0 = frame;
+    }
     const int L = s.render_blocker_len;
     const int total = L + kFrame;
     nrb = total / kBlock;
@@ -112,19 +139,23 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     for (int r = 0; r < nrb; ++r) {
       for (int j = 0; j < kBlock; ++j) {
         const int k = kBlock * r + j - L;
-        x[j] = k < 0 ? aec.render_blocker[L + k] : front_load_sample(a.render, idx, flen, a.fmt, k);
+        x[j] = k < 0 ? aec.render_blocker[L + k] : band0[k];
       }
       front_render_insert(aec, ts, r, x);
     }
     const int rem = total - kBlock * nrb;
-    for (int j = 0; j < rem; ++j) aec.render_blocker[j] = front_load_sample(a.render, idx, flen, a.fmt, kFrame - rem + j);
+    for (int j = 0; j < rem; ++j) aec.render_blocker[j] = band0[kFrame - rem + j];
+    if (up) {
+      front_slice_band(frame + kFrame, up->render_blocker_hi[0], L, nrb, up->render_blocks_hi, 0);
+      front_slice_band(frame + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
+    }
     s.render_blocker_len = rem;
   }
   ts.n_render_blocks = nrb;
   ts.n_capture_blocks = 0;
   if (!a.capture) return;
 
-  // ---------------- capture: high-pass filter, saturation, FrameBlocker, decimator
+  // ---------------- capture: high-pass filter, saturation, [band split], FrameBlocker, decimator
   st.seen_capture = 1;
   {
     const BiquadCoef* hc = (B == 3) ? kHpf48k : kHpf16k;
@@ -144,6 +175,15 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     if (cfg.aec_enabled) s.saturated_microphone_signal = sat;
   }
   if (!cfg.aec_enabled) return;
+  const float* cap0 = ts.capture_frame;
+  if (B == 3) {
+    // AudioBuffer::SplitIntoFrequencyBands on the capture side (audio_processing_impl.cc:1359-1363);
+    // k_echo finds the three bands in ts.capture_frame instead of the full-band frame.
+    for (int i = 0; i < flen; ++i) frame[i] = 0.f;
+    three_band_analysis_thread(ts.capture_frame, frame, sub, st.capture_bands.analysis);
+    for (int i = 0; i < flen; ++i) ts.capture_frame[i] = frame[i];
+    cap0 = frame;
+  }
   {
     const int L = s.capture_blocker_len;
     const int total = L + kFrame;
@@ -154,7 +194,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     for (int b = 0; b < ncb; ++b) {
       for (int j = 0; j < kBlock; ++j) {
         const int k = kBlock * b + j - L;
-        const float y = k < 0 ? aec.capture_blocker[L + k] : ts.capture_frame[k];
+        const float y = k < 0 ? aec.capture_blocker[L + k] : cap0[k];
         ts.capture_blocks[b][j] = y;
         if (decimate) {
           float v = biquad_step(kDecimator4[0], d0, y);
@@ -170,10 +210,51 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       aec.capture_decimator[3] = d3;
     }
     const int rem = total - kBlock * ncb;
-    for (int j = 0; j < rem; ++j) aec.capture_blocker[j] = ts.capture_frame[kFrame - rem + j];
+    for (int j = 0; j < rem; ++j) aec.capture_blocker[j] = cap0[kFrame - rem + j];
+    if (up) {
+      front_slice_band(frame + kFrame, up->capture_blocker_hi[0], L, ncb, up->capture_blocks_hi, 0);
+      front_slice_band(frame + 2 * kFrame, up->capture_blocker_hi[1], L, ncb, up->capture_blocks_hi, 1);
+    }
     s.capture_blocker_len = rem;
     ts.n_capture_blocks = ncb;
   }
+}
+
+// PostFilter::Process (post_filter.cc:64-72) + output conversion for 48 kHz AEC3 legs: k_echo left
+// the merged full-band frame in ts.capture_frame; another serial IIR, hence one thread per leg.
+WAP_DEVCONST BiquadCoef kPostFilter48k[4] = {
+    {0.56142156f, 1.11499931f, 0.56142156f, 1.57914249f, 0.63379496f},
+    {1.00000000f, 1.88944170f, 1.00000000f, 1.55130066f, 0.68708719f},
+    {1.00000000f, 1.76057310f, 1.00000000f, 1.53001328f, 0.78591224f},
+    {1.00000000f, 1.67448535f, 1.00000000f, 1.56506670f, 0.92096576f}};
+
+WAP_DEV void post_leg(const TickArgs& a, int idx) {
+  const int slot = a.slots ? a.slots[idx] : idx;
+  StreamState& st = a.states[slot];
+  UpperBandState& up = a.upper[slot];
+  const int flen = kFrame * 3;
+  Biquad p0 = up.post_filter[0], p1 = up.post_filter[1], p2 = up.post_filter[2], p3 = up.post_filter[3];
+  const bool zero = st.tick.pad_[0] != 0;  // first frame after un-muting (set by k_echo)
+  for (int i = 0; i < flen; ++i) {
+    float v = st.tick.capture_frame[i];
+    if (st.capture_output_used) {
+      v = biquad_step(kPostFilter48k[0], p0, v);
+      v = biquad_step(kPostFilter48k[1], p1, v);
+      v = biquad_step(kPostFilter48k[2], p2, v);
+      v = biquad_step(kPostFilter48k[3], p3, v);
+    }
+    if (zero) v = 0.f;
+    if (a.fmt == 0) {  // FloatS16ToS16 (audio_util.h:52-56)
+      float w = fminr(v, 32767.f);
+      w = fmaxr(w, -32768.f);
+      reinterpret_cast<int16_t*>(a.out)[(size_t)idx * flen + i] = (int16_t)(w + copysignf(0.5f, w));
+    } else {           // FloatS16ToFloat (audio_util.h:71-76)
+      float w = fminr(v, 32768.f);
+      w = fmaxr(w, -32768.f);
+      reinterpret_cast<float*>(a.out)[(size_t)idx * flen + i] = w * (1.f / 32768.f);
+    }
+  }
+  up.post_filter[0] = p0; up.post_filter[1] = p1; up.post_filter[2] = p2; up.post_filter[3] = p3;
 }
 
 }  // namespace wap

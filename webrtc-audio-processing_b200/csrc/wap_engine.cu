@@ -66,6 +66,12 @@ __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, in
   }
 }
 
+// 48 kHz AEC3 legs only: PostFilter + output conversion, one thread per leg.
+__global__ void __launch_bounds__(128) k_post(TickArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.n) post_leg(a, idx);
+}
+
 // Broadcasts the initial-state template into `n` arena slots.
 __global__ void k_init_slots(StreamState* states, const StreamState* tmpl, const int* slots, int n) {
   const size_t words = sizeof(StreamState) / 4;
@@ -99,6 +105,7 @@ struct WapEngine {
   WapStreamConfig format{};
   EngineConfig cfg{};
   StreamState* d_states = nullptr;
+  wap::UpperBandState* d_upper = nullptr;  // 48 kHz AEC3 engines only
   StreamState* d_template = nullptr;
   cudaStream_t stream = nullptr;
   std::vector<int> free_slots;
@@ -181,7 +188,6 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   // InitializeHighPassFilter (audio_processing_impl.cc:1883-1907)
   e.hpf_enabled = c.high_pass_filter_enabled || c.noise_suppression_enabled ||
                   (c.echo_canceller_enabled && c.echo_canceller_enforce_high_pass_filtering);
-  if (e.aec_enabled && e.num_bands != 1) return WapError::UnsupportedConfig;  // 48 kHz AEC3: later round
   switch (c.noise_suppression_level) {  // suppression_params.cc:18-48
     case WapNoiseSuppressionLevel::Low:
       e.ns_over_subtraction_factor = 1.f; e.ns_minimum_attenuating_gain = 0.5f; e.ns_use_attenuation_adjustment = 0; break;
@@ -245,6 +251,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
                      const void* d_render, const void* d_capture, void* d_out, WapSampleFormat fmt) {
   wap::TickArgs a{};
   a.states = e->d_states;
+  a.upper = e->d_upper;
   a.slots = d_slots;
   a.delays_ms = d_delays;
   a.uniform_delay_ms = uniform_delay;
@@ -269,6 +276,10 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
   WAP_LAUNCH(wap::k_echo, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
+  if (e->d_upper && d_capture) {
+    WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
+    e->launches++;
+  }
   if (timing) {
     cudaEventRecord(e->ev[3], e->stream);
     WAP_CUDA(cudaEventSynchronize(e->ev[3]));
@@ -340,6 +351,10 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&e->d_states, (size_t)max_streams * sizeof(StreamState)) == cudaSuccess &&
             cudaMalloc((void**)&e->d_template, sizeof(StreamState)) == cudaSuccess;
+  if (ok && cfg.aec_enabled && cfg.num_bands == 3) {
+    const size_t ub = (size_t)max_streams * sizeof(wap::UpperBandState);
+    ok = cudaMalloc((void**)&e->d_upper, ub) == cudaSuccess && cudaMemset(e->d_upper, 0, ub) == cudaSuccess;
+  }
   if (ok) {
     StreamState* tmpl = new StreamState;
     wap::init_stream_state(*tmpl);
@@ -367,6 +382,7 @@ void wap_engine_destroy(WapEngine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_states);
+  cudaFree(e->d_upper);
   cudaFree(e->d_template);
   cudaFree(e->d_render);
   cudaFree(e->d_capture);
@@ -394,6 +410,8 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
   WAP_CUDA(cudaMemcpy(d_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
   WAP_LAUNCH(wap::k_init_slots, dim3(16, std::min(n, 4096)), 256, 0, e->stream, e->d_states,
              (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
+  if (e->d_upper)
+    for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
   e->launches++;
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(d_slots);
@@ -574,6 +592,7 @@ void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* e, double* out_byt
   out_bytes[2] = total - front - delay;
 }
 
+static const double kBlockBytesHi = 2 * 64;  // floats of bands 1-2 per block
 double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (!e) return 0.0;
   // SURVEY.md section 8(d) byte model.
@@ -583,6 +602,8 @@ double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (e->cfg.ns_enabled) bytes += 2223.0 * 8.0 + 24.0;
   if (e->cfg.hpf_enabled) bytes += 96.0;
   if (B == 3) bytes += 2 * 2 * 150 * 4.0;
+  if (B == 3 && e->cfg.aec_enabled)  // render split state, upper-band ring / delay / framers, PostFilter state
+    bytes += 2 * 150 * 4.0 + 2.5 * (4.0 * kBlockBytesHi * 5) + 128.0;
   bytes += e->frame_len * 4.0 * (e->cfg.aec_enabled ? 3 : 2);
   return bytes;
 }

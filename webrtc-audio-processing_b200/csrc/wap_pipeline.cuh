@@ -88,24 +88,36 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       warp_prefetch_l2(st.aec.Hr_re, (int)(reinterpret_cast<const char*>(st.aec.h_time) - reinterpret_cast<const char*>(st.aec.Hr_re)));
   }
   // ---------------- render side: ring / FFT / spectrum writes for the blocks k_front sliced
-  if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc);
+  UpperBandState* up = (B == 3 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
+  if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc, up);
   if (!a.capture) return;
 
   // ---------------- capture side (the frame is already high-pass filtered)
-  for (int i = lane_id(); i < flen; i += 32) full[i] = ts.capture_frame[i];
-  __syncwarp();
-  if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
+  if (up) {  // k_front already split the capture frame (it needs band 0 for the blocks)
+    for (int i = lane_id(); i < flen; i += 32) bands[i] = ts.capture_frame[i];
+    __syncwarp();
+  } else {
+    for (int i = lane_id(); i < flen; i += 32) full[i] = ts.capture_frame[i];
+    __syncwarp();
+    if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
+  }
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
-  if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc);
+  if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
   if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
   __syncwarp();
   // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
-  if (!output_used_last_frame && output_used) {
+  if (!up && !output_used_last_frame && output_used) {
     for (int i = lane_id(); i < flen; i += 32) full[i] = 0.f;
     __syncwarp();
   }
   if (lane_id() == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
+  if (up) {
+    // 48 kHz AEC3: PostFilter (a serial IIR) and the output conversion run in k_post.
+    for (int i = lane_id(); i < flen; i += 32) st.tick.capture_frame[i] = full[i];
+    if (lane_id() == 0) st.tick.pad_[0] = (!output_used_last_frame && output_used) ? 1 : 0;
+    return;
+  }
   store_frame(a.out, idx, flen, a.fmt, full);
 }
 

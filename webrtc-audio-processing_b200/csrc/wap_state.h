@@ -267,6 +267,20 @@ struct alignas(16) TickScratch {
   float capture_frame[kFrame * kMaxBands];  // full-band capture frame after the high-pass filter
 };
 
+// Extra state of a 48 kHz (three-band) AEC3 leg; lives in a second arena that only
+// engines of that config class allocate.  Bands 1 and 2 only ever see gains, comfort
+// noise and delays (reference aec3/suppression_filter.cc:153-183), but the render ring
+// keeps them because UpperBandsGain / RenderSignalAnalyzer read GetBlock(0).
+struct alignas(16) UpperBandState {
+  float blocks_hi[kRingBlocks][2][kBlock];      // BlockBuffer, bands 1-2 (render_delay_buffer.cc:387-400)
+  float e_output_old_hi[2][kBlock];             // SuppressionFilter::e_output_old_[1..2]
+  float render_blocker_hi[2][kBlock], capture_blocker_hi[2][kBlock], output_framer_hi[2][kBlock];
+  Biquad post_filter[4];                        // PostFilter (post_filter.cc:27-72), 48 kHz only
+  // tick scratch (k_front -> k_echo -> k_post)
+  float render_blocks_hi[3][2][kBlock];
+  float capture_blocks_hi[3][2][kBlock];
+};
+
 // One call leg.
 struct alignas(16) StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)

@@ -6,6 +6,7 @@ namespace wap {
 
 struct TickArgs {
   StreamState* states;
+  UpperBandState* upper;  // [arena slot] for 48 kHz AEC3 engines, else nullptr
   const int* slots;       // [n] arena slot of each stream, or nullptr => slot i
   const int* delays_ms;   // [n] per-stream set_stream_delay_ms value (-1 unset) or nullptr
   int uniform_delay_ms;   // used when delays_ms == nullptr (-1 unset)
