@@ -300,6 +300,14 @@ def run_b200(a):
     alg = L.wap_engine_algorithmic_bytes_per_frame(eng.h)
     peak, peak_src = peaks()
     dom = max(kernels, key=lambda k: k["ms_per_launch"])   # the dominant kernel of a tick
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (per leg-frame,
+    # scaled to this run's leg count); null when no capture is on record.
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)[dom["name"]]["dram_bytes_per_leg_frame"] * S
+    except Exception:
+        pass
     achieved = dom["achieved_gbs"]
     whole_tick = alg * S / (ms_step * 1e-3) / 1e9
     state_bytes = L.wap_engine_state_bytes_per_stream(eng.h)
@@ -319,7 +327,8 @@ def run_b200(a):
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                              "kernel": dom["name"],
                              "algorithmic_bytes_per_leg_frame": dom["algorithmic_bytes_per_leg_frame"],
                              "ms_per_launch": dom["ms_per_launch"],

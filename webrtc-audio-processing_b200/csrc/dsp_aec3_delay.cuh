@@ -53,11 +53,11 @@ WAP_DEV float mf_hsum16(float acc) {
 // tap index mod 16 WITHIN the chunk), the remaining len%16 taps are added to the scalar
 // sums with separate multiply and add, in order.  Lanes 0-15 run the h*x chains, lanes
 // 16-31 the x*x chains -- the same code on a per-lane operand pointer (h or x).
-// h lives in sc.mf.h, the window in sc.mf.xp.
+// h lives in (sc.mf.xp + kMfHOffset), the window in sc.mf.xp.
 WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
   const int lane = lane_id();
   const int half = lane >> 4, L = lane & 15;
-  float* h = sc.mf.h;
+  float* h = (sc.mf.xp + kMfHOffset);
   float error_sum = 0.f;
   int updated = 0;
 #pragma unroll 1
@@ -493,13 +493,13 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
     }
     __syncwarp();
     mf_stage_window(a, sc, n, sc.mf.xp);
-    for (int t = lane; t < kMfLen; t += 32) sc.mf.h[t] = a.mf_h[n][t];
+    for (int t = lane; t < kMfLen; t += 32) (sc.mf.xp + kMfHOffset)[t] = a.mf_h[n][t];
     __syncwarp();
     float error_sum;
     int updated;
     mf_core(sc, n, y, &error_sum, &updated);
-    const int peak = mf_max_square_peak_index(sc.mf.h);
-    for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = sc.mf.h[t];
+    const int peak = mf_max_square_peak_index((sc.mf.xp + kMfHOffset));
+    for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = (sc.mf.xp + kMfHOffset)[t];
     if (lane == 0) {
       sc.mf.err_sum[n] = error_sum;
       sc.mf.updated[n] = updated;

@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(128) k_front(TickArgs a) {
   if (idx < a.n) front_leg(a, idx);
 }
 
-__global__ void __launch_bounds__(128, 4) k_delay(TickArgs a, int scratch_floats) {
+#ifndef WAP_DELAY_MINBLOCKS
+#define WAP_DELAY_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
