@@ -123,3 +123,70 @@ def test_mute_unmute_matches_reference(emu_lib, oracle):
     assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
     assert np.all(out[0][60 * 160:61 * 160] == 0)             # zeroed frame after un-muting
     assert not np.array_equal(out[0], out[1])                  # the flag is per leg
+
+
+def test_legs_joining_later_and_slot_reuse(emu_lib, oracle):
+    """Ragged batches: legs created on different ticks run different 2/3-block cadences inside the
+    same launch; a destroyed leg's arena slot is re-initialised for the next leg."""
+    import wap_b200
+    L = emu_lib
+    nf = 50
+    legs = [synthetic_leg(i, nf) for i in range(3)]
+    refs = []
+    for far, near in legs:
+        o, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)
+        assert err == 0
+        refs.append(o)
+    eng = wap_b200.Engine(1, 16000, lib=L, capacity=2, aec=True, ns=True, ns_level=1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hs = [eng.handles[0], None]
+    out = [np.zeros(nf * 160, np.int16) for _ in range(3)]
+    start = {0: 0, 1: 7, 2: 31}   # leg 1 joins at tick 7; leg 0 leaves at tick 30, leg 2 takes its slot
+    live = {0: hs[0]}
+    for t in range(nf + 31):
+        if t == 7:
+            h1 = (C.c_void_p * 1)()
+            assert L.wap_engine_create_streams(eng.h, 1, h1) == 0
+            live[1] = h1[0]
+            # capacity is 2: a third simultaneous leg is refused
+            h_extra = (C.c_void_p * 1)()
+            assert L.wap_engine_create_streams(eng.h, 1, h_extra) == 5
+        if t == 30:
+            L.wap_destroy(live.pop(0))
+        if t == 31:
+            h2 = (C.c_void_p * 1)()
+            assert L.wap_engine_create_streams(eng.h, 1, h2) == 0
+            live[2] = h2[0]
+        ids = [i for i in sorted(live) if 0 <= t - start[i] < nf]
+        if not ids:
+            continue
+        hh = (C.c_void_p * len(ids))(*[live[i] for i in ids])
+        r = np.stack([legs[i][0][(t - start[i]) * 160:(t - start[i] + 1) * 160] for i in ids])
+        c = np.stack([legs[i][1][(t - start[i]) * 160:(t - start[i] + 1) * 160] for i in ids])
+        o = np.zeros_like(c)
+        assert L.wap_streams_set_delay_ms(hh, len(ids), 0) == 0
+        assert L.wap_process_streams(hh, len(ids), p(r), p(c), p(o), 0, None) == 0
+        for k, i in enumerate(ids):
+            out[i][(t - start[i]) * 160:(t - start[i] + 1) * 160] = o[k]
+    for i in range(3):
+        n = min(nf, nf + 31 - start[i]) * 160
+        if i == 0:
+            n = 30 * 160   # leg 0 left after 30 ticks
+        assert np.abs(out[i][:n].astype(np.int32) - refs[i][:n].astype(np.int32)).max() <= TOL, i
+    for h in live.values():
+        L.wap_destroy(h)
+    eng.handles = (C.c_void_p * 0)()
+    eng.n = 0
+    eng.close()
+
+
+@pytest.mark.parametrize("level", [0, 3])
+def test_ns_levels_low_and_very_high(emu_lib, oracle, level):
+    """NoiseSuppression kLow / kVeryHigh (suppression_params.cc:18-48); kModerate / kHigh are covered
+    by the parity tests."""
+    from common import run_engine
+    near = golden("speech_16k.npz")["near"][:120 * 160]
+    ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=level).run_i16(16000, None, near)
+    assert err == 0
+    out = run_engine(emu_lib, 16000, None, near, n_streams=1, aec=False, ns=True, ns_level=level)
+    assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
