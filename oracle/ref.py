@@ -21,6 +21,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.ref_apm_create.restype = C.c_void_p
         L.ref_apm_create.argtypes = [C.c_int] * 7
+        L.ref_apm_create_agc2.restype = C.c_void_p
+        L.ref_apm_create_agc2.argtypes = [C.c_int] * 5 + [C.c_float]
         L.ref_apm_destroy.argtypes = [C.c_void_p]
         L.ref_apm_run_i16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -52,9 +54,13 @@ class RefApm:
     """One reference webrtc::AudioProcessing instance (= one call leg)."""
 
     def __init__(self, aec=True, ns=True, ns_level=1, max_rate=48000, hpf=False,
-                 mc_render=False, mc_capture=False):
-        self.h = lib().ref_apm_create(int(aec), int(ns), int(ns_level), int(max_rate),
-                                      int(hpf), int(mc_render), int(mc_capture))
+                 mc_render=False, mc_capture=False, agc2=False, agc2_fixed_gain_db=0.0):
+        if agc2:
+            self.h = lib().ref_apm_create_agc2(int(aec), int(ns), int(ns_level), int(max_rate), 1,
+                                               float(agc2_fixed_gain_db))
+        else:
+            self.h = lib().ref_apm_create(int(aec), int(ns), int(ns_level), int(max_rate),
+                                          int(hpf), int(mc_render), int(mc_capture))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -72,6 +72,17 @@ void* ref_apm_create(int aec, int ns, int ns_level, int max_rate, int hpf,
   return h;
 }
 
+// Same with GainController2 in its default sub-configuration (fixed digital gain + limiter).
+void* ref_apm_create_agc2(int aec, int ns, int ns_level, int max_rate, int agc2, float fixed_gain_db) {
+  auto* h = new RefApm;
+  webrtc::Environment env = webrtc::CreateEnvironment();
+  AudioProcessing::Config c = MakeConfig(aec, ns, ns_level, max_rate, 0, 0, 0);
+  c.gain_controller2.enabled = agc2 != 0;
+  c.gain_controller2.fixed_digital.gain_db = fixed_gain_db;
+  h->apm = webrtc::BuiltinAudioProcessingBuilder(c).Build(env);
+  return h;
+}
+
 void ref_apm_destroy(void* p) { delete static_cast<RefApm*>(p); }
 
 // One 10 ms tick on interleaved int16 frames: render then capture, exactly as

@@ -128,3 +128,15 @@ def synthetic_leg_48k(i, n_frames, hf_boost=1.0):
     y += rng_n.uniform(-3000, 3000, n) * ((t % 2.0) > 1.7)
     return (np.clip(np.round(x), -32768, 32767).astype(np.int16),
             np.clip(np.round(y), -32768, 32767).astype(np.int16))
+
+
+def loud_bursty_signal(rate, n_frames, seed=3):
+    """Noise bursts + gated tone with peaks near 23 k: pushed through a fixed digital gain this
+    drives the AGC2 limiter through its identity, knee, limiter and saturation regions and through
+    the first-sub-frame attack interpolation."""
+    rng = np.random.default_rng(seed)
+    n = n_frames * rate // 100
+    t = np.arange(n) / rate
+    env = 1500 + 14000 * (np.sin(2 * np.pi * 1.3 * t) > 0.2) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.37 * t) ** 2)
+    x = rng.uniform(-1, 1, n) * env + 9000 * np.sin(2 * np.pi * 440 * t) * (t % 0.7 < 0.3)
+    return x.clip(-32768, 32767).astype(np.int16)

@@ -214,3 +214,32 @@ def test_emu_aec3_ns_parity_48k_three_band(emu_lib, oracle):
             48000, far, near, stats_every=50)
         assert err == 0
         _check_aec(out[k], stats[k], ref_out, ref_stats)
+
+
+@pytest.mark.parametrize("rate,gain_db", [(16000, 0.0), (16000, 12.0), (48000, 20.0)])
+def test_emu_agc2_fixed_gain_and_limiter(emu_lib, oracle, rate, gain_db):
+    """GainController2, default sub-configuration (fixed digital gain + limiter) on its own
+    (gain_controller2.cc:183-260, agc2/limiter.cc, fixed_digital_level_estimator.cc,
+    interpolated_gain_curve.cc); at 48 kHz nothing is multi-band, so no band split either."""
+    from common import loud_bursty_signal
+    x = loud_bursty_signal(rate, 150)
+    ref_out, _, err = oracle.RefApm(aec=False, ns=False, max_rate=48000, agc2=True,
+                                    agc2_fixed_gain_db=gain_db).run_i16(rate, None, x)
+    assert err == 0
+    out = run_engine(emu_lib, rate, None, x, n_streams=1, aec=False, ns=False, agc2=True, agc2_fixed_gain_db=gain_db)
+    assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
+    if gain_db > 0:
+        assert np.abs(ref_out).max() >= 32000   # the limiter really worked
+
+
+def test_emu_full_chain_aec3_ns_agc2(emu_lib, oracle):
+    """BASELINE config 5 shape at test size: AEC3 + NS + AGC2 (fixed 6 dB + limiter), 16 kHz mono."""
+    from common import run_legs, synthetic_leg
+    legs = [synthetic_leg(i, 250) for i in (6, 29)]
+    out, stats = run_legs(emu_lib, 16000, legs, stats_every=50, aec=True, ns=True, ns_level=1, agc2=True,
+                          agc2_fixed_gain_db=6.0)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1, agc2=True,
+                                                agc2_fixed_gain_db=6.0).run_i16(16000, far, near, stats_every=50)
+        assert err == 0
+        _check_aec(out[k], stats[k], ref_out, ref_stats)

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import golden, run_engine, run_legs, synthetic_leg, synthetic_leg_48k, vanishing_echo_leg
+from common import golden, loud_bursty_signal, run_engine, run_legs, synthetic_leg, synthetic_leg_48k, vanishing_echo_leg
 
 pytestmark = pytest.mark.gpu
 TOL_FS = 1e-4  # of full scale => 3.2768 int16 LSB
@@ -133,3 +133,27 @@ def test_aec3_ns_parity_48k_three_band(gpu_lib, oracle):
         assert d.max() <= TOL_FS * 32768, (k, int(d.max()))
         assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1, k
         assert np.array_equal(stats[k][:, 2], ref_stats[:, 5]), k
+
+
+@pytest.mark.parametrize("rate", [16000, 48000])
+def test_full_chain_aec3_ns_agc2(gpu_lib, oracle, rate):
+    """BASELINE config 5 shape at test size: AEC3 + NS + AGC2 (fixed 6 dB gain + limiter)."""
+    gen = synthetic_leg if rate == 16000 else synthetic_leg_48k
+    legs = [gen(i, 400) for i in range(4)]
+    out, stats = run_legs(gpu_lib, rate, legs, stats_every=100, aec=True, ns=True, ns_level=1, agc2=True,
+                          agc2_fixed_gain_db=6.0)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1, max_rate=48000, agc2=True,
+                                                agc2_fixed_gain_db=6.0).run_i16(rate, far, near, stats_every=100)
+        assert err == 0
+        d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32))
+        assert d.max() <= TOL_FS * 32768, (k, int(d.max()))
+        assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1, k
+
+
+def test_agc2_limiter_regions(gpu_lib, oracle):
+    x = loud_bursty_signal(16000, 300)
+    ref_out, _, err = oracle.RefApm(aec=False, ns=False, agc2=True, agc2_fixed_gain_db=12.0).run_i16(16000, None, x)
+    assert err == 0 and np.abs(ref_out).max() >= 32000
+    out = run_engine(gpu_lib, 16000, None, x, n_streams=2, aec=False, ns=False, agc2=True, agc2_fixed_gain_db=12.0)
+    assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768

@@ -183,7 +183,11 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
     return WapError::UnsupportedConfig;  // resampled / 2-band paths: SURVEY 8(f)-2
   }
   if (f.num_channels != 1) return WapError::UnsupportedConfig;  // multichannel: SURVEY 8 cfg4, later round
-  if (c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled)
+  if (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) return WapError::UnsupportedConfig;
+  // AGC2: fixed digital gain + limiter (the default sub-configuration); the adaptive digital
+  // controller and the input volume controller are SURVEY 8(f)-1.
+  if (c.gain_controller2_enabled &&
+      (c.gain_controller2_adaptive_digital_enabled || c.gain_controller2_input_volume_controller_enabled))
     return WapError::UnsupportedConfig;
   e.sample_rate_hz = f.sample_rate_hz;
   e.aec_enabled = c.echo_canceller_enabled;
@@ -202,6 +206,9 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
       e.ns_over_subtraction_factor = 1.25f; e.ns_minimum_attenuating_gain = 0.09f; e.ns_use_attenuation_adjustment = 1; break;
   }
   e.capture_output_used = 1;
+  e.agc2_enabled = c.gain_controller2_enabled ? 1 : 0;
+  e.split_bands = (e.num_bands == 3 && (c.high_pass_filter_enabled || e.ns_enabled || e.aec_enabled)) ? 1 : 0;
+  e.agc2_fixed_gain = powf(10.0f, c.gain_controller2_fixed_digital_gain_db / 20.0f);  // DbToRatio (audio_util.h:85-87)
   e.reinit_on_first_capture = (c.noise_suppression_enabled || c.gain_controller2_enabled ||
                                f.sample_rate_hz != 16000 || f.num_channels != 1) ? 1 : 0;
   e.cng_noise_floor = 64.f * powf(10.f, (90.30899869919436f + -96.03406f) * 0.1f);

@@ -108,6 +108,7 @@ inline void init_stream_state(StreamState& st) {
   memset(&st, 0, sizeof(st));
   st.capture_output_used = 1;
   st.capture_output_used_last_frame = 1;
+  st.agc2.last_scaling_factor = 1.f;  // limiter.h
   init_ns_state(st.ns);
   init_aec3_state(st.aec);
 }

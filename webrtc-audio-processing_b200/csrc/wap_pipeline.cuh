@@ -7,6 +7,7 @@
 #include <stddef.h>
 
 #include "dsp_aec3.cuh"
+#include "dsp_agc2.cuh"
 #include "dsp_front.cuh"
 #include "dsp_filters.cuh"
 #include "dsp_ns.cuh"
@@ -71,7 +72,7 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   cfg.capture_output_used = output_used ? 1 : 0;
   __syncwarp();
   float* full = scratch;
-  float* bands = (B == 1) ? full : scratch + flen;
+  float* bands = (B == 1 || !cfg.split_bands) ? full : scratch + flen;
   unsigned dsp_off = 2u * (unsigned)flen;
 #if !defined(WAP_EMU)
   asm volatile("" : "+r"(dsp_off));  // see k_echo: one register instead of re-reading cfg at every access
@@ -99,13 +100,16 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   } else {
     for (int i = lane_id(); i < flen; i += 32) full[i] = ts.capture_frame[i];
     __syncwarp();
-    if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
+    if (cfg.split_bands) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
   }
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
   if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
-  if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
+  if (cfg.split_bands) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
   __syncwarp();
+  // GainController2 runs on the merged full-band frame, only while the output is used
+  // (audio_processing_impl.cc:1450-1477), before the PostFilter.
+  if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, flen, reinterpret_cast<float*>(dsp));
   // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
   if (!up && !output_used_last_frame && output_used) {
     for (int i = lane_id(); i < flen; i += 32) full[i] = 0.f;

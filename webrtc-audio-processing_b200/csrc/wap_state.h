@@ -281,6 +281,12 @@ struct alignas(16) UpperBandState {
   float capture_blocks_hi[3][2][kBlock];
 };
 
+// Limiter of GainController2 (agc2/limiter.h:56-63, fixed_digital_level_estimator.h).
+struct Agc2State {
+  float filter_state_level;    // FixedDigitalLevelEstimator::filter_state_level_, init 0
+  float last_scaling_factor;   // Limiter::last_scaling_factor_, init 1
+};
+
 // One call leg.
 struct alignas(16) StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)
@@ -293,6 +299,8 @@ struct alignas(16) StreamState {
   int capture_output_used;
   int capture_output_used_last_frame;
   int pad_[1];
+  Agc2State agc2;
+  int pad2_[2];
   ThreeBandState capture_bands; // AudioBuffer's SplittingFilter (48 kHz only)
   ThreeBandState render_bands;
   NsState ns;
@@ -324,6 +332,12 @@ struct EngineConfig {
   // EchoCanceller3, so render frames queued before the first capture frame are
   // dropped.  Reproduced because it changes the output of the first frames.
   int reinit_on_first_capture;
+  // GainController2, default sub-configuration: fixed digital gain (DbToRatio on the host) + limiter.
+  int agc2_enabled;
+  float agc2_fixed_gain;
+  // SubmoduleStates::CaptureMultiBandProcessingPresent (audio_processing_impl.cc:399-412): the
+  // 48 kHz frame is only split into bands when a multi-band submodule is active.
+  int split_bands;
 };
 
 }  // namespace wap

@@ -136,8 +136,11 @@ def load(path=None):
     return L
 
 
-def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False):
+def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False, agc2=False,
+                agc2_fixed_gain_db=0.0):
     c = lib.wap_config_default()
+    c.gain_controller2_enabled = bool(agc2)
+    c.gain_controller2_fixed_digital_gain_db = float(agc2_fixed_gain_db)
     c.echo_canceller_enabled = bool(aec)
     c.noise_suppression_enabled = bool(ns)
     c.noise_suppression_level = int(ns_level)
