@@ -203,6 +203,10 @@ WapError wap_engine_enable_kernel_timing(WapEngine* engine, bool on);
 int64_t wap_engine_read_kernel_timing(const WapEngine* engine, double* out_ms);
 void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* engine, double* out_bytes);
 WapError wap_engine_synchronize(WapEngine* engine);
+/* wap_process_streams on a large batch cuts the legs into ranges so the PCIe copies of one range
+ * overlap the kernels of another. chunks = 0: automatic (4 ranges of whole occupancy waves from
+ * 4 waves up), 1: off, 2..8: that many ranges. Results do not depend on it. */
+WapError wap_engine_set_pipeline_chunks(WapEngine* engine, int32_t chunks);
 /* CUDA stream the engine launches on (cudaStream_t), for event timing. */
 void* wap_engine_cuda_stream(WapEngine* engine);
 /* Number of kernel launches issued by the engine so far. */

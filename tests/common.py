@@ -31,7 +31,7 @@ def run_engine(lib, rate, render, capture, n_streams=1, delay_ms=None, **cfg):
     return out
 
 
-def run_legs(lib, rate, legs, stats_every=0, delay_ms=0, **cfg):
+def run_legs(lib, rate, legs, stats_every=0, delay_ms=0, pipeline_chunks=None, **cfg):
     """Drive len(legs) different call legs (list of (render, capture) int16 arrays) through ONE
     batched engine, one wap_process_streams call per 10 ms tick.  Returns (out [n, samples],
     stats [n, k, 3] = (erl, erle, delay_ms) sampled every `stats_every` frames)."""
@@ -40,6 +40,8 @@ def run_legs(lib, rate, legs, stats_every=0, delay_ms=0, **cfg):
     fl = rate // 100
     nf = min(l[1].size for l in legs) // fl
     eng = wap_b200.Engine(n, rate, lib=lib, **cfg)
+    if pipeline_chunks is not None:
+        eng.set_pipeline_chunks(pipeline_chunks)
     out = np.zeros((n, nf * fl), np.int16)
     stats = []
     R = np.stack([l[0][:nf * fl] for l in legs]).reshape(n, nf, fl)

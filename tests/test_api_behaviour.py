@@ -190,3 +190,21 @@ def test_ns_levels_low_and_very_high(emu_lib, oracle, level):
     assert err == 0
     out = run_engine(emu_lib, 16000, None, near, n_streams=1, aec=False, ns=True, ns_level=level)
     assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
+
+
+def test_pipelined_host_tick_matches_plain(emu_lib, oracle):
+    """wap_engine_set_pipeline_chunks: cutting the batch into leg ranges (ragged last range)
+    changes nothing in the output."""
+    import wap_b200
+    from common import run_legs
+    legs = [synthetic_leg(i, 30) for i in range(11)]
+    ref, _ = run_legs(emu_lib, 16000, legs, pipeline_chunks=1, aec=True, ns=True, ns_level=1)
+    out, _ = run_legs(emu_lib, 16000, legs, pipeline_chunks=3, aec=True, ns=True, ns_level=1)
+    assert np.array_equal(ref, out)
+    far, near = legs[10]
+    ref_out, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)
+    assert err == 0 and np.array_equal(out[10], ref_out[:out[10].size])
+    eng = wap_b200.Engine(2, 16000, lib=emu_lib, aec=True, ns=False)
+    with pytest.raises(RuntimeError):
+        eng.set_pipeline_chunks(99)
+    eng.close()

@@ -157,3 +157,23 @@ def test_agc2_limiter_regions(gpu_lib, oracle):
     assert err == 0 and np.abs(ref_out).max() >= 32000
     out = run_engine(gpu_lib, 16000, None, x, n_streams=2, aec=False, ns=False, agc2=True, agc2_fixed_gain_db=12.0)
     assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
+
+
+@pytest.mark.parametrize("chunks", [3, 0])
+def test_large_batch_pipelined_host_path(gpu_lib, oracle, chunks):
+    """wap_process_streams on a large batch cuts the legs into ranges whose PCIe copies overlap
+    the kernels of another range (3 forced ragged ranges of 8200 legs; automatic = 4 wave-aligned
+    ranges of 47400 legs): 8 distinct legs tiled, every copy equals the reference output."""
+    ids = [1, 6, 11, 18, 23, 30, 37, 44]
+    nf = 150 if chunks else 40
+    base = [synthetic_leg(i, nf) for i in ids]
+    n = 8200 if chunks else 47400
+    legs = [base[i % 8] for i in range(n)]
+    out, _ = run_legs(gpu_lib, 16000, legs, pipeline_chunks=chunks, aec=True, ns=True, ns_level=1)
+    for k in range(8):
+        far, near = base[k]
+        ref_out, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)
+        assert err == 0
+        d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32)).max()
+        assert d <= TOL_FS * 32768, (k, d)
+        assert np.array_equal(out[k::8], np.broadcast_to(out[k], out[k::8].shape))

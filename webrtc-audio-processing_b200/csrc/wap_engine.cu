@@ -101,6 +101,8 @@ using wap::StreamState;
     }                                                                                    \
   } while (0)
 
+constexpr int kMaxChunks = 8;
+
 struct WapEngine {
   int device = 0;
   int capacity = 0;
@@ -122,6 +124,11 @@ struct WapEngine {
   void* h_pinned = nullptr;  // render | capture | out
   size_t staged_streams = 0;
   std::vector<int> last_slots;
+  std::vector<WapAudioProcessing*> last_handles;  // the handle array last_slots was built from
+  // per-leg host state indexed by slot, so the per-tick bookkeeping walks contiguous memory
+  std::vector<int> leg_delay_ms;            // last set_stream_delay_ms value
+  std::vector<unsigned char> leg_delay_set; // was_stream_delay_set (cleared by every capture frame)
+  int dirty_legs = 0;                       // handles whose capture_output_used is not yet in the slab
   int64_t launches = 0;
   int frame_len = 0;  // samples per frame (all channels)
   int echo_scratch_floats = 0;
@@ -132,6 +139,11 @@ struct WapEngine {
   int64_t timed_ticks = 0;
   int delay_scratch_floats = 0;
   bool is_default = false;
+  int sm_count = 148;
+  int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
+  // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {}, ev_start = nullptr;
 };
 
 struct WapAudioProcessing {
@@ -234,6 +246,7 @@ WapError ensure_staging(WapEngine* e, size_t n) {
   WAP_CUDA(cudaMallocHost(&e->h_pinned, cap * (3 * fb + 2 * sizeof(int))));
   e->staged_streams = cap;
   e->last_slots.clear();
+  e->last_handles.clear();
   return WapError::None;
 }
 
@@ -304,6 +317,22 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   return WapError::None;
 }
 
+// Number of leg ranges the host-buffer tick is pipelined over (1 = plain copy/compute/copy).
+int pipeline_chunks(WapEngine* e, int n) {
+  int chunks = e->forced_chunks ? e->forced_chunks : (n >= 4 * e->sm_count * 80 ? 4 : 1);
+  if (e->timing || n < 2 * chunks) chunks = 1;
+  if (chunks > 1 && !e->copy_in) {
+    bool ok = cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < kMaxChunks; ++k)
+      ok = cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return 1;
+  }
+  return chunks;
+}
+
 std::mutex g_default_mu;
 WapEngine* g_default_engines[8] = {nullptr};
 
@@ -358,6 +387,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
   e->delay_scratch_floats = wap::delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
+            cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&e->d_states, (size_t)max_streams * sizeof(StreamState)) == cudaSuccess &&
             cudaMalloc((void**)&e->d_template, sizeof(StreamState)) == cudaSuccess;
@@ -382,6 +412,8 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
     wap_engine_destroy(e);
     return nullptr;
   }
+  e->leg_delay_ms.assign(max_streams, 0);
+  e->leg_delay_set.assign(max_streams, 0);
   e->free_slots.reserve(max_streams);
   for (int i = max_streams - 1; i >= 0; --i) e->free_slots.push_back(i);
   return e;
@@ -401,6 +433,13 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_delays);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   for (int k = 0; k < 4; ++k) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+  for (int k = 0; k < kMaxChunks; ++k) {
+    if (e->ev_in[k]) cudaEventDestroy(e->ev_in[k]);
+    if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+  }
+  if (e->ev_start) cudaEventDestroy(e->ev_start);
+  if (e->copy_in) cudaStreamDestroy(e->copy_in);
+  if (e->copy_out) cudaStreamDestroy(e->copy_out);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -425,7 +464,10 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
   e->launches++;
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(d_slots);
+  e->last_handles.clear();
   for (int i = 0; i < n; ++i) {
+    e->leg_delay_ms[slots[i]] = 0;
+    e->leg_delay_set[slots[i]] = 0;
     WapAudioProcessing* h = new WapAudioProcessing;
     h->engine = e;
     h->slot = slots[i];
@@ -442,50 +484,73 @@ WapError wap_engine_synchronize(WapEngine* e) {
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   return WapError::None;
 }
+WapError wap_engine_set_pipeline_chunks(WapEngine* e, int32_t chunks) {
+  if (!e) return WapError::NullPointer;
+  if (chunks < 0 || chunks > kMaxChunks) return WapError::BadStreamParameter;
+  e->forced_chunks = chunks;
+  return WapError::None;
+}
 void* wap_engine_cuda_stream(WapEngine* e) { return e ? (void*)e->stream : nullptr; }
 int64_t wap_engine_launch_count(const WapEngine* e) { return e ? e->launches : 0; }
 
-WapError wap_process_streams_device(WapEngine* e, WapAudioProcessing* const* handles, int32_t n,
-                                    const void* d_render, const void* d_capture, void* d_out,
-                                    WapSampleFormat fmt) {
+// Per-tick host bookkeeping in front of the launches: slot list, un/mute flags, stream delays.
+static WapError prepare_tick(WapEngine* e, WapAudioProcessing* const* handles, int32_t n, const int** d_delays_out,
+                             int* uniform_delay_out) {
   if (!e || !handles) return WapError::NullPointer;
   if (n <= 0) return WapError::BadStreamParameter;
   WAP_CUDA(cudaSetDevice(e->device));
   WapError err = ensure_staging(e, n);
   if (err != WapError::None) return err;
-  // slot list (cached across ticks while the leg set is unchanged)
-  bool same = e->last_slots.size() == (size_t)n;
-  for (int i = 0; same && i < n; ++i) same = handles[i] && e->last_slots[i] == handles[i]->slot;
-  int uniform_delay = -1;
-  bool uniform = true;
-  for (int i = 0; i < n; ++i) {
-    if (!handles[i] || handles[i]->engine != e) return WapError::BadStreamParameter;
-    const int d = handles[i]->was_stream_delay_set ? handles[i]->stream_delay_ms : -1;
-    if (i == 0) uniform_delay = d; else uniform = uniform && d == uniform_delay;
-  }
+  // slot list (cached across ticks while the caller passes the same handle array)
+  const bool same = e->last_handles.size() == (size_t)n &&
+                    memcmp(handles, e->last_handles.data(), (size_t)n * sizeof(handles[0])) == 0;
   if (!same) {
+    for (int i = 0; i < n; ++i)
+      if (!handles[i] || handles[i]->engine != e) return WapError::BadStreamParameter;
     e->last_slots.resize(n);
     for (int i = 0; i < n; ++i) e->last_slots[i] = handles[i]->slot;
+    e->last_handles.assign(handles, handles + n);
     WAP_CUDA(cudaMemcpyAsync(e->d_slots, e->last_slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
   }
-  for (int i = 0; i < n; ++i) {
-    WapAudioProcessing* h = handles[i];
-    if (h->capture_output_used_dirty) {  // rare: un/mute events
+  const int* slots = e->last_slots.data();
+  int uniform_delay = e->leg_delay_set[slots[0]] ? e->leg_delay_ms[slots[0]] : -1;
+  bool uniform = true;
+  for (int i = 1; i < n; ++i) {
+    const int d = e->leg_delay_set[slots[i]] ? e->leg_delay_ms[slots[i]] : -1;
+    uniform = uniform && d == uniform_delay;
+  }
+  if (e->dirty_legs > 0) {  // rare: un/mute events
+    for (int i = 0; i < n; ++i) {
+      WapAudioProcessing* h = handles[i];
+      if (!h->capture_output_used_dirty) continue;
       const int v = h->capture_output_used ? 1 : 0;
       WAP_CUDA(cudaMemcpyAsync(&e->d_states[h->slot].capture_output_used, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
       WAP_CUDA(cudaStreamSynchronize(e->stream));
       h->capture_output_used_dirty = false;
+      e->dirty_legs--;
     }
   }
   const int* d_delays = nullptr;
   if (!uniform) {
     std::vector<int> dl(n);
-    for (int i = 0; i < n; ++i) dl[i] = handles[i]->was_stream_delay_set ? handles[i]->stream_delay_ms : -1;
+    for (int i = 0; i < n; ++i) dl[i] = e->leg_delay_set[slots[i]] ? e->leg_delay_ms[slots[i]] : -1;
     WAP_CUDA(cudaMemcpyAsync(e->d_delays, dl.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
     d_delays = e->d_delays;
   }
+  *d_delays_out = d_delays;
+  *uniform_delay_out = uniform_delay;
+  return WapError::None;
+}
+
+WapError wap_process_streams_device(WapEngine* e, WapAudioProcessing* const* handles, int32_t n,
+                                    const void* d_render, const void* d_capture, void* d_out,
+                                    WapSampleFormat fmt) {
+  const int* d_delays = nullptr;
+  int uniform_delay = -1;
+  WapError err = prepare_tick(e, handles, n, &d_delays, &uniform_delay);
+  if (err != WapError::None) return err;
   return launch_tick(e, e->d_slots, d_delays, uniform_delay, n, d_render, d_capture, d_out, fmt);
 }
 
@@ -513,15 +578,58 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     memcpy(hp + stride, capture, bytes);
     src_c = hp + stride;
   }
-  if (render) WAP_CUDA(cudaMemcpyAsync(e->d_render, src_r, bytes, cudaMemcpyHostToDevice, e->stream));
-  WAP_CUDA(cudaMemcpyAsync(e->d_capture, src_c, bytes, cudaMemcpyHostToDevice, e->stream));
-  err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
-  if (err != WapError::None) return err;
   const bool out_pinned = is_pinned_host(out);
-  WAP_CUDA(cudaMemcpyAsync(out_pinned ? out : (void*)(hp + 2 * stride), e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
-  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  void* dst_o = out_pinned ? out : (void*)(hp + 2 * stride);
+  const int chunks = pipeline_chunks(e, n);
+  if (chunks <= 1) {
+    if (render) WAP_CUDA(cudaMemcpyAsync(e->d_render, src_r, bytes, cudaMemcpyHostToDevice, e->stream));
+    WAP_CUDA(cudaMemcpyAsync(e->d_capture, src_c, bytes, cudaMemcpyHostToDevice, e->stream));
+    err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
+    if (err != WapError::None) return err;
+    WAP_CUDA(cudaMemcpyAsync(dst_o, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    for (int i = 0; i < n; ++i) e->leg_delay_set[e->last_slots[i]] = 0;  // audio_processing_impl.cc:1556
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+  } else {
+    // Large batch: the legs are cut into `chunks` ranges; host->device copies run on one copy
+    // stream, the tick kernels of each range on the engine stream, device->host copies on a
+    // second copy stream, so the PCIe traffic of one range hides behind the kernels of another.
+    const size_t leg_bytes = (size_t)e->frame_len * esz;
+    WAP_CUDA(cudaEventRecord(e->ev_start, e->stream));
+    WAP_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
+    // Range length: a whole number of full-occupancy waves of both warp-per-leg kernels
+    // (4 and 5 CTAs of 4 legs per SM), so cutting the batch adds no partial waves.
+    const int wave = e->forced_chunks ? 4 : e->sm_count * 80;
+    const int per = ((n + chunks - 1) / chunks + wave - 1) / wave * wave;
+    for (int c = 0, off = 0; off < n; ++c, off += per) {
+      const int cnt = std::min(per, n - off);
+      const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
+      if (render)
+        WAP_CUDA(cudaMemcpyAsync((char*)e->d_render + bo, (const char*)src_r + bo, bc, cudaMemcpyHostToDevice, e->copy_in));
+      WAP_CUDA(cudaMemcpyAsync((char*)e->d_capture + bo, (const char*)src_c + bo, bc, cudaMemcpyHostToDevice, e->copy_in));
+      WAP_CUDA(cudaEventRecord(e->ev_in[c], e->copy_in));
+    }
+    // host bookkeeping runs while the first copies are in flight
+    const int* d_delays = nullptr;
+    int uniform_delay = -1;
+    err = prepare_tick(e, handles, n, &d_delays, &uniform_delay);
+    if (err != WapError::None) return err;
+    for (int c = 0, off = 0; off < n; ++c, off += per) {
+      const int cnt = std::min(per, n - off);
+      const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
+      WAP_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in[c], 0));
+      err = launch_tick(e, e->d_slots + off, d_delays ? d_delays + off : nullptr, uniform_delay, cnt,
+                        render ? (const void*)((const char*)e->d_render + bo) : nullptr, (const char*)e->d_capture + bo,
+                        (char*)e->d_out + bo, fmt);
+      if (err != WapError::None) return err;
+      WAP_CUDA(cudaEventRecord(e->ev_done[c], e->stream));
+      WAP_CUDA(cudaStreamWaitEvent(e->copy_out, e->ev_done[c], 0));
+      WAP_CUDA(cudaMemcpyAsync((char*)dst_o + bo, (const char*)e->d_out + bo, bc, cudaMemcpyDeviceToHost, e->copy_out));
+    }
+    for (int i = 0; i < n; ++i) e->leg_delay_set[e->last_slots[i]] = 0;  // audio_processing_impl.cc:1556
+    WAP_CUDA(cudaStreamSynchronize(e->copy_out));
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+  }
   if (!out_pinned) memcpy(out, hp + 2 * stride, bytes);
-  for (int i = 0; i < n; ++i) handles[i]->was_stream_delay_set = false;  // audio_processing_impl.cc:1556
   if (per_stream_err) for (int i = 0; i < n; ++i) per_stream_err[i] = WapError::None;
   return WapError::None;
 }

@@ -81,6 +81,7 @@ EXPORTS = [
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
     "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
+    "wap_engine_set_pipeline_chunks",
 ]
 
 _libs = {}
@@ -128,6 +129,7 @@ def load(path=None):
     L.wap_engine_launch_count.argtypes = [vp]
     L.wap_streams_set_delay_ms.argtypes = [vp, i32, C.c_int]
     L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
+    L.wap_engine_set_pipeline_chunks.argtypes = [vp, i32]
     L.wap_engine_read_kernel_timing.restype = C.c_int64
     L.wap_engine_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.wap_engine_algorithmic_bytes_per_kernel.argtypes = [vp, C.POINTER(C.c_double)]
@@ -172,6 +174,11 @@ class Engine:
 
     def set_stream_delay_ms(self, ms):
         self.lib.wap_streams_set_delay_ms(self.handles, self.n, ms)
+
+    def set_pipeline_chunks(self, chunks):
+        err = self.lib.wap_engine_set_pipeline_chunks(self.h, int(chunks))
+        if err:
+            raise RuntimeError("wap_engine_set_pipeline_chunks -> WapError %d" % err)
 
     def set_capture_output_used(self, used, legs=None):
         for i in (range(self.n) if legs is None else legs):
