@@ -130,7 +130,7 @@ def run_reference(a):
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "real-time streams", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU leg
@@ -341,12 +341,21 @@ def run_b200(a):
             except Exception as e:  # oracle missing on this box
                 line["cpu_baseline"] = {"value": None, "unit": "real-time streams", "cores": os.cpu_count(),
                                         "kind": "reference", "sample": "unavailable: %s" % e}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else written to fd 1 by libraries
+    (NCCL's version banner, torchrun chatter) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
