@@ -112,17 +112,17 @@ def vanishing_echo_leg(n_frames, rate=16000, seed=11):
     return (np.round(x).astype(np.int16), np.clip(np.round(y), -32768, 32767).astype(np.int16))
 
 
-def synthetic_leg_48k(i, n_frames, hf_boost=1.0):
-    """48 kHz variant of synthetic_leg: full-band white render (so bands 1-2 carry as much energy
-    as band 0 -- drives SuppressionGain::UpperBandsGain's anti-howling branch), 3-tap echo path."""
-    rate = 48000
+def synthetic_leg_48k(i, n_frames, hf_boost=1.0, rate=48000):
+    """48 kHz (or 32 kHz) variant of synthetic_leg: full-band white render (so the upper bands carry
+    as much energy as band 0 -- drives SuppressionGain::UpperBandsGain's anti-howling branch),
+    3-tap echo path."""
     n = n_frames * rate // 100
     rng_r = np.random.default_rng(5000 + 2 * i)
     rng_n = np.random.default_rng(5001 + 2 * i)
     t = np.arange(n) / rate
     x = rng_r.uniform(-8000, 8000, n) * hf_boost
     x *= ((t % 1.0) < 0.9)
-    D = 3 * (64 * (1 + (i % 24)) + (7 * i) % 64)
+    D = (rate // 16000) * (64 * (1 + (i % 24)) + (7 * i) % 64)
     y = np.zeros(n)
     for g, d in ((0.5, D), (0.25, D + 111), (0.1, D + 480)):
         y[d:] += g * x[:n - d]

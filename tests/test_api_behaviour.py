@@ -208,3 +208,19 @@ def test_pipelined_host_tick_matches_plain(emu_lib, oracle):
     with pytest.raises(RuntimeError):
         eng.set_pipeline_chunks(99)
     eng.close()
+
+
+def test_native_rates_and_unsupported_formats(emu_lib):
+    """16 / 32 / 48 kHz mono engines exist (48 kHz with maximum_internal_processing_rate = 48000);
+    resampled rates and multichannel are outside the built scope and are refused, not approximated."""
+    import wap_b200
+    for rate in (16000, 32000, 48000):
+        eng = wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
+        x = np.zeros((1, rate // 100), np.int16)
+        assert eng.process(x, x).shape == (1, rate // 100)
+        eng.close()
+    for rate in (8000, 44100):
+        with pytest.raises(RuntimeError):
+            wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 48000, lib=emu_lib, aec=True, ns=True, max_rate=32000)

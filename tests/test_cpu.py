@@ -216,7 +216,44 @@ def test_emu_aec3_ns_parity_48k_three_band(emu_lib, oracle):
         _check_aec(out[k], stats[k], ref_out, ref_stats)
 
 
-@pytest.mark.parametrize("rate,gain_db", [(16000, 0.0), (16000, 12.0), (48000, 20.0)])
+def _speech_32k(n_frames):
+    """The 16 kHz speech fixture held at 32 kHz (sample repetition): the images above 8 kHz give the
+    upper band real content."""
+    sp = golden("speech_16k.npz")
+    n = n_frames * 160
+    return np.repeat(sp["far"][:n], 2), np.repeat(sp["near"][:n], 2)
+
+
+def test_emu_ns_parity_32k_two_band(emu_lib, oracle):
+    """32 kHz: two-band QMF split / merge (splitting_filter.cc:68-101, signal_processing/
+    splitting_filter.c:31-204), NS on band 0 and its upper-band gain on band 1, 32 kHz high-pass."""
+    _, near = _speech_32k(150)
+    ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=2).run_i16(32000, None, near)
+    assert err == 0
+    out = run_engine(emu_lib, 32000, None, near, n_streams=1, aec=False, ns=True, ns_level=2)
+    d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max()
+    assert d <= TOL_FS * 32768, d
+
+
+def test_emu_aec3_ns_parity_32k_two_band(emu_lib, oracle):
+    """32 kHz mono AEC3 + NS: two bands on both sides, AEC3 on band 0 with one upper band
+    (gain / comfort noise / one-block delay), no PostFilter (post_filter.cc:44-52)."""
+    from common import run_legs, synthetic_leg_48k
+    legs = [_speech_32k(150), synthetic_leg_48k(7, 150, 3.5, rate=32000)]  # 2nd: clipped, HF-heavy render
+    out, stats = run_legs(emu_lib, 32000, legs, stats_every=50, aec=True, ns=True, ns_level=1)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(32000, far, near, stats_every=50)
+        assert err == 0
+        _check_aec(out[k], stats[k], ref_out, ref_stats)
+    # AEC3 alone (no re-initialisation-free path differences, no NS upper-band gain)
+    far, near = legs[1]
+    ref_out, _, err = oracle.RefApm(aec=True, ns=False).run_i16(32000, far, near)
+    assert err == 0
+    out, _ = run_legs(emu_lib, 32000, [legs[1]], aec=True, ns=False)
+    assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
+
+
+@pytest.mark.parametrize("rate,gain_db", [(16000, 0.0), (16000, 12.0), (32000, 14.0), (48000, 20.0)])
 def test_emu_agc2_fixed_gain_and_limiter(emu_lib, oracle, rate, gain_db):
     """GainController2, default sub-configuration (fixed digital gain + limiter) on its own
     (gain_controller2.cc:183-260, agc2/limiter.cc, fixed_digital_level_estimator.cc,

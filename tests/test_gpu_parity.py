@@ -135,11 +135,14 @@ def test_aec3_ns_parity_48k_three_band(gpu_lib, oracle):
         assert np.array_equal(stats[k][:, 2], ref_stats[:, 5]), k
 
 
-@pytest.mark.parametrize("rate", [16000, 48000])
+@pytest.mark.parametrize("rate", [16000, 32000, 48000])
 def test_full_chain_aec3_ns_agc2(gpu_lib, oracle, rate):
-    """BASELINE config 5 shape at test size: AEC3 + NS + AGC2 (fixed 6 dB gain + limiter)."""
-    gen = synthetic_leg if rate == 16000 else synthetic_leg_48k
-    legs = [gen(i, 400) for i in range(4)]
+    """BASELINE config 5 shape at test size: AEC3 + NS + AGC2 (fixed 6 dB gain + limiter), at the
+    three native rates (one band, two-band QMF, three-band filter bank)."""
+    if rate == 16000:
+        legs = [synthetic_leg(i, 400) for i in range(4)]
+    else:
+        legs = [synthetic_leg_48k(i, 400, 1.0 + i, rate=rate) for i in range(4)]
     out, stats = run_legs(gpu_lib, rate, legs, stats_every=100, aec=True, ns=True, ns_level=1, agc2=True,
                           agc2_fixed_gain_db=6.0)
     for k, (far, near) in enumerate(legs):
@@ -177,3 +180,13 @@ def test_large_batch_pipelined_host_path(gpu_lib, oracle, chunks):
         d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32)).max()
         assert d <= TOL_FS * 32768, (k, d)
         assert np.array_equal(out[k::8], np.broadcast_to(out[k], out[k::8].shape))
+
+
+def test_ns_parity_32k_two_band(gpu_lib, oracle):
+    """32 kHz NS-only (very high) with the two-band QMF, 6 s of held 16 kHz speech."""
+    near = np.repeat(golden("speech_16k.npz")["near"][:600 * 160], 2)
+    ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=3).run_i16(32000, None, near)
+    assert err == 0
+    out = run_engine(gpu_lib, 32000, None, near, n_streams=3, aec=False, ns=True, ns_level=3)
+    d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max()
+    assert d <= TOL_FS * 32768, d

@@ -18,6 +18,10 @@ WAP_DEVCONST BiquadCoef kHpf16k[3] = {
     {0.8773539420715290582f, -1.754683920749088077f, 0.8773539420715289472f, -1.881687317862849707f, 0.8880584644559580410f},
     {1.0f, -1.999810143464515022f, 1.0f, -1.976035417167170793f, 0.9779708644868606582f},
     {1.0f, -1.999669231394235469f, 1.0f, -1.994265767864654482f, 0.9954861594635392441f}};
+WAP_DEVCONST BiquadCoef kHpf32k[3] = {  // high_pass_filter.cc:37-46
+    {0.9102055685511306615f, -1.820404922871161624f, 0.9102055685511306615f, -1.940710875829138482f, 0.9423512845457852061f},
+    {1.0f, -1.999952541587768806f, 1.0f, -1.988434609801665420f, 0.9889212529819323416f},
+    {1.0f, -1.999917315632020021f, 1.0f, -1.997434723613889629f, 0.9977401885079651978f}};
 WAP_DEVCONST BiquadCoef kHpf48k[3] = {
     {0.9213790163564168f, -1.8427552370064049f, 0.9213790163564168f, -1.9604500061078971f, 0.9611862979079667f},
     {1.0f, -1.9999789078432082f, 1.0f, -1.9923834169149972f, 0.9926001112941157f},
@@ -199,6 +203,78 @@ WAP_DEV void three_band_synthesis(const float* bands, float* full, float* sub, f
     }
 #pragma unroll
     for (int r = 0; r < 5; ++r) full[us + 3 * (lane + 32 * r)] = acc[r];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------ two-band QMF (32 kHz)
+// SplittingFilter::TwoBands{Analysis,Synthesis} (splitting_filter.cc:68-101) ->
+// WebRtcSpl_{Analysis,Synthesis}QMF (common_audio/signal_processing/splitting_filter.c:
+// 136-204): the even and odd samples each pass three cascaded first-order all-pass
+// sections (WebRtcSpl_AllPassQMF, :31-134), the band signals are their half sum / half
+// difference.  The reference keeps six state floats per branch of which two are duplicates;
+// four are stored here: {x[-1], y1[-1], y2[-1], y3[-1]}.
+WAP_DEVCONST float kQmfAllPass1[3] = {0.0979309082f, 0.5643005371f, 0.8737335205f};
+WAP_DEVCONST float kQmfAllPass2[3] = {0.32551574707f, 0.74862670898f, 0.96145629882f};
+constexpr int kQmfStateFloats = 4;
+
+// One all-pass branch, serial: y_i[n] = y_{i-1}[n-1] + a_i * (y_{i-1}[n] - y_i[n-1]).
+WAP_DEV void qmf_allpass_branch(const float* in, int stride, int n, const float* c, float* st, float* out) {
+  float xp = st[0], y1p = st[1], y2p = st[2], y3p = st[3];
+  for (int k = 0; k < n; ++k) {
+    const float x = in[k * stride];
+    const float y1 = xp + c[0] * (x - y1p);
+    const float y2 = y1p + c[1] * (y1 - y2p);
+    const float y3 = y2p + c[2] * (y2 - y3p);
+    out[k] = y3;
+    xp = x; y1p = y1; y2p = y2; y3p = y3;
+  }
+  st[0] = xp; st[1] = y1p; st[2] = y2p; st[3] = y3p;
+}
+
+// Analysis by ONE thread (k_front): full[320] -> bands[2][160]; state = 2 x kQmfStateFloats.
+WAP_DEV void two_band_analysis_thread(const float* full, float* bands, float* state) {
+  qmf_allpass_branch(full + 1, 2, kFrame, kQmfAllPass1, state, bands);                              // odd samples
+  qmf_allpass_branch(full, 2, kFrame, kQmfAllPass2, state + kQmfStateFloats, bands + kFrame);       // even samples
+  for (int i = 0; i < kFrame; ++i) {
+    const float f1 = bands[i], f2 = bands[kFrame + i];
+    bands[i] = (f1 + f2) * 0.5f;
+    bands[kFrame + i] = (f1 - f2) * 0.5f;
+  }
+}
+
+// Analysis by a warp: the two serial branches run on lanes 0 and 1.  `tmp`: 320-float scratch.
+WAP_DEV void two_band_analysis(const float* full, float* bands, float* tmp, float* state) {
+  const int lane = lane_id();
+  __syncwarp();
+  if (lane == 0) qmf_allpass_branch(full + 1, 2, kFrame, kQmfAllPass1, state, tmp);
+  if (lane == 1) qmf_allpass_branch(full, 2, kFrame, kQmfAllPass2, state + kQmfStateFloats, tmp + kFrame);
+  __syncwarp();
+  for (int i = lane; i < kFrame; i += 32) {
+    const float f1 = tmp[i], f2 = tmp[kFrame + i];
+    bands[i] = (f1 + f2) * 0.5f;
+    bands[kFrame + i] = (f1 - f2) * 0.5f;
+  }
+  __syncwarp();
+}
+
+// Synthesis by a warp: bands[2][160] -> full[320], saturated to the int16 range like the reference.
+WAP_DEV void two_band_synthesis(const float* bands, float* full, float* tmp, float* state) {
+  const int lane = lane_id();
+  __syncwarp();
+  for (int i = lane; i < kFrame; i += 32) {
+    const float lo = bands[i], hi = bands[kFrame + i];
+    tmp[i] = lo + hi;
+    tmp[kFrame + i] = lo - hi;
+  }
+  __syncwarp();
+  if (lane == 0) qmf_allpass_branch(tmp, 1, kFrame, kQmfAllPass2, state, tmp);
+  if (lane == 1) qmf_allpass_branch(tmp + kFrame, 1, kFrame, kQmfAllPass1, state + kQmfStateFloats, tmp + kFrame);
+  __syncwarp();
+  for (int i = lane; i < kFrame; i += 32) {
+    const float f1 = tmp[i], f2 = tmp[kFrame + i];
+    full[2 * i] = f2 > -32768.0f ? (f2 < 32767.0f ? f2 : 32767.0f) : -32768.0f;
+    full[2 * i + 1] = f1 > -32768.0f ? (f1 < 32767.0f ? f1 : 32767.0f) : -32768.0f;
   }
   __syncwarp();
 }

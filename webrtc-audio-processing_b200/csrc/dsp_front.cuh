@@ -108,7 +108,9 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   TickScratch& ts = st.tick;
   Aec3State& aec = st.aec;
   Aec3Scalars& s = aec.s;
-  UpperBandState* up = (B == 3 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
+  // 32 kHz legs run the upper-band code of the 3-band path with a second upper band that stays
+  // all-zero (it never raises the band-energy maximum and its output is dropped).
+  UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
   const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
   const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
   // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
@@ -121,12 +123,13 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   int nrb = 0;
   if (a.render && cfg.aec_enabled && render_live) {
     const float* band0;
-    if (B == 3) {
+    if (B >= 2) {
       // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
       for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
-      float* full = ts.capture_frame;  // borrowed as the thread's 480-sample input buffer
+      float* full = ts.capture_frame;  // borrowed as the thread's 320/480-sample input buffer
       for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
-      three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
+      if (B == 3) three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
+      else two_band_analysis_thread(full, frame, &st.render_bands.analysis[0][0]);
       band0 = frame;
     } else {
       for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
@@ -147,7 +150,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     for (int j = 0; j < rem; ++j) aec.render_blocker[j] = band0[kFrame - rem + j];
     if (up) {
       front_slice_band(frame + kFrame, up->render_blocker_hi[0], L, nrb, up->render_blocks_hi, 0);
-      front_slice_band(frame + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
+      if (B == 3) front_slice_band(frame + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
     }
     s.render_blocker_len = rem;
   }
@@ -158,7 +161,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   // ---------------- capture: high-pass filter, saturation, [band split], FrameBlocker, decimator
   st.seen_capture = 1;
   {
-    const BiquadCoef* hc = (B == 3) ? kHpf48k : kHpf16k;
+    const BiquadCoef* hc = (B == 3) ? kHpf48k : (B == 2 ? kHpf32k : kHpf16k);
     Biquad h0 = st.hpf[0], h1 = st.hpf[1], h2 = st.hpf[2];
     int sat = 0;
     for (int i = 0; i < flen; ++i) {
@@ -176,11 +179,12 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   }
   if (!cfg.aec_enabled) return;
   const float* cap0 = ts.capture_frame;
-  if (B == 3) {
+  if (B >= 2) {
     // AudioBuffer::SplitIntoFrequencyBands on the capture side (audio_processing_impl.cc:1359-1363);
-    // k_echo finds the three bands in ts.capture_frame instead of the full-band frame.
+    // k_echo finds the bands in ts.capture_frame instead of the full-band frame.
     for (int i = 0; i < flen; ++i) frame[i] = 0.f;
-    three_band_analysis_thread(ts.capture_frame, frame, sub, st.capture_bands.analysis);
+    if (B == 3) three_band_analysis_thread(ts.capture_frame, frame, sub, st.capture_bands.analysis);
+    else two_band_analysis_thread(ts.capture_frame, frame, &st.capture_bands.analysis[0][0]);
     for (int i = 0; i < flen; ++i) ts.capture_frame[i] = frame[i];
     cap0 = frame;
   }
@@ -213,7 +217,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     for (int j = 0; j < rem; ++j) aec.capture_blocker[j] = cap0[kFrame - rem + j];
     if (up) {
       front_slice_band(frame + kFrame, up->capture_blocker_hi[0], L, ncb, up->capture_blocks_hi, 0);
-      front_slice_band(frame + 2 * kFrame, up->capture_blocker_hi[1], L, ncb, up->capture_blocks_hi, 1);
+      if (B == 3) front_slice_band(frame + 2 * kFrame, up->capture_blocker_hi[1], L, ncb, up->capture_blocks_hi, 1);
     }
     s.capture_blocker_len = rem;
     ts.n_capture_blocks = ncb;

@@ -110,7 +110,7 @@ struct WapEngine {
   WapStreamConfig format{};
   EngineConfig cfg{};
   StreamState* d_states = nullptr;
-  wap::UpperBandState* d_upper = nullptr;  // 48 kHz AEC3 engines only
+  wap::UpperBandState* d_upper = nullptr;  // 32 / 48 kHz AEC3 engines only
   StreamState* d_template = nullptr;
   cudaStream_t stream = nullptr;
   std::vector<int> free_slots;
@@ -189,10 +189,12 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   EngineConfig e{};
   if (f.sample_rate_hz == 16000) {
     e.num_bands = 1;
+  } else if (f.sample_rate_hz == 32000) {
+    e.num_bands = 2;  // two-band QMF (splitting_filter.cc:68-101)
   } else if (f.sample_rate_hz == 48000 && c.pipeline_maximum_internal_processing_rate == 48000) {
     e.num_bands = 3;
   } else {
-    return WapError::UnsupportedConfig;  // resampled / 2-band paths: SURVEY 8(f)-2
+    return WapError::UnsupportedConfig;  // resampled paths: SURVEY 8(f)-2
   }
   if (f.num_channels != 1) return WapError::UnsupportedConfig;  // multichannel: SURVEY 8 cfg4, later round
   if (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) return WapError::UnsupportedConfig;
@@ -219,7 +221,7 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   }
   e.capture_output_used = 1;
   e.agc2_enabled = c.gain_controller2_enabled ? 1 : 0;
-  e.split_bands = (e.num_bands == 3 && (c.high_pass_filter_enabled || e.ns_enabled || e.aec_enabled)) ? 1 : 0;
+  e.split_bands = (e.num_bands >= 2 && (c.high_pass_filter_enabled || e.ns_enabled || e.aec_enabled)) ? 1 : 0;
   e.agc2_fixed_gain = powf(10.0f, c.gain_controller2_fixed_digital_gain_db / 20.0f);  // DbToRatio (audio_util.h:85-87)
   e.reinit_on_first_capture = (c.noise_suppression_enabled || c.gain_controller2_enabled ||
                                f.sample_rate_hz != 16000 || f.num_channels != 1) ? 1 : 0;
@@ -299,7 +301,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
   WAP_LAUNCH(wap::k_echo, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
-  if (e->d_upper && d_capture) {
+  if (e->d_upper && e->cfg.num_bands == 3 && d_capture) {  // PostFilter: 48 kHz only (post_filter.cc:44-52)
     WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
     e->launches++;
   }
@@ -391,7 +393,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&e->d_states, (size_t)max_streams * sizeof(StreamState)) == cudaSuccess &&
             cudaMalloc((void**)&e->d_template, sizeof(StreamState)) == cudaSuccess;
-  if (ok && cfg.aec_enabled && cfg.num_bands == 3) {
+  if (ok && cfg.aec_enabled && cfg.num_bands >= 2) {
     const size_t ub = (size_t)max_streams * sizeof(wap::UpperBandState);
     ok = cudaMalloc((void**)&e->d_upper, ub) == cudaSuccess && cudaMemset(e->d_upper, 0, ub) == cudaSuccess;
   }
@@ -720,7 +722,8 @@ double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (e->cfg.ns_enabled) bytes += 2223.0 * 8.0 + 24.0;
   if (e->cfg.hpf_enabled) bytes += 96.0;
   if (B == 3) bytes += 2 * 2 * 150 * 4.0;
-  if (B == 3 && e->cfg.aec_enabled)  // render split state, upper-band ring / delay / framers, PostFilter state
+  if (B == 2) bytes += 2 * 2 * 8 * 4.0;
+  if (B >= 2 && e->cfg.aec_enabled)  // render split state, upper-band ring / delay / framers, PostFilter state
     bytes += 2 * 150 * 4.0 + 2.5 * (4.0 * kBlockBytesHi * 5) + 128.0;
   bytes += e->frame_len * 4.0 * (e->cfg.aec_enabled ? 3 : 2);
   return bytes;

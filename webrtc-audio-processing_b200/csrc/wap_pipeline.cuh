@@ -22,7 +22,8 @@ constexpr int kScratchFloatsDsp =
     (int)((sizeof(NsScratch) > kAecEchoScratchBytes ? sizeof(NsScratch) : kAecEchoScratchBytes) / sizeof(float)) + 4;
 // k_echo: two frame buffers + the DSP scratch; k_delay: the AEC3 delay-stage scratch only.
 // (rounded to 16 bytes: the scratch structs hold 128-bit aligned members)
-inline int echo_scratch_floats(int bands) { return (2 * kFrame * bands + kScratchFloatsDsp + 3) & ~3; }
+// (a 2-band leg is laid out like a 3-band one: AEC3 writes an unused third band)
+inline int echo_scratch_floats(int bands) { return (2 * kFrame * (bands == 2 ? 3 : bands) + kScratchFloatsDsp + 3) & ~3; }
 inline int delay_scratch_floats() { return ((int)(kAecDelayScratchBytes / sizeof(float)) + 4 + 3) & ~3; }
 static_assert(offsetof(StreamState, aec) % 16 == 0 && offsetof(Aec3State, mf_h) % 16 == 0 &&
                   sizeof(StreamState) % 16 == 0 && offsetof(AecScratch, mf) % 16 == 0,
@@ -71,9 +72,10 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   const bool output_used_last_frame = st.capture_output_used_last_frame != 0;
   cfg.capture_output_used = output_used ? 1 : 0;
   __syncwarp();
+  const int lay = kFrame * (B == 2 ? 3 : B);  // buffer stride: see echo_scratch_floats
   float* full = scratch;
-  float* bands = (B == 1 || !cfg.split_bands) ? full : scratch + flen;
-  unsigned dsp_off = 2u * (unsigned)flen;
+  float* bands = (B == 1 || !cfg.split_bands) ? full : scratch + lay;
+  unsigned dsp_off = 2u * (unsigned)lay;
 #if !defined(WAP_EMU)
   asm volatile("" : "+r"(dsp_off));  // see k_echo: one register instead of re-reading cfg at every access
 #endif
@@ -89,7 +91,7 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       warp_prefetch_l2(st.aec.Hr_re, (int)(reinterpret_cast<const char*>(st.aec.h_time) - reinterpret_cast<const char*>(st.aec.Hr_re)));
   }
   // ---------------- render side: ring / FFT / spectrum writes for the blocks k_front sliced
-  UpperBandState* up = (B == 3 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
+  UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
   if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc, up);
   if (!a.capture) return;
 
@@ -100,23 +102,30 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   } else {
     for (int i = lane_id(); i < flen; i += 32) full[i] = ts.capture_frame[i];
     __syncwarp();
-    if (cfg.split_bands) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
+    if (cfg.split_bands) {
+      if (B == 3) three_band_analysis(full, bands, reinterpret_cast<float*>(dsp), st.capture_bands.analysis);
+      else two_band_analysis(full, bands, reinterpret_cast<float*>(dsp), &st.capture_bands.analysis[0][0]);
+    }
   }
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
   if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
-  if (cfg.split_bands) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
+  if (cfg.split_bands) {
+    if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);
+    else two_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), &st.capture_bands.synthesis[0][0]);
+  }
   __syncwarp();
   // GainController2 runs on the merged full-band frame, only while the output is used
   // (audio_processing_impl.cc:1450-1477), before the PostFilter.
   if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, flen, reinterpret_cast<float*>(dsp));
   // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
-  if (!up && !output_used_last_frame && output_used) {
+  const bool post = up && B == 3;  // 48 kHz AEC3: PostFilter + output conversion in k_post
+  if (!post && !output_used_last_frame && output_used) {
     for (int i = lane_id(); i < flen; i += 32) full[i] = 0.f;
     __syncwarp();
   }
   if (lane_id() == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
-  if (up) {
+  if (post) {
     // 48 kHz AEC3: PostFilter (a serial IIR) and the output conversion run in k_post.
     for (int i = lane_id(); i < flen; i += 32) st.tick.capture_frame[i] = full[i];
     if (lane_id() == 0) st.tick.pad_[0] = (!output_used_last_frame && output_used) ? 1 : 0;

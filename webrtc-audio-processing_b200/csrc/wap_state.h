@@ -311,7 +311,7 @@ struct alignas(16) StreamState {
 // Engine-wide (config class) constants uploaded once.
 struct EngineConfig {
   int sample_rate_hz;   // 16000 or 48000
-  int num_bands;        // 1 or 3
+  int num_bands;        // 1 (16 kHz), 2 (32 kHz) or 3 (48 kHz)
   int aec_enabled;
   int ns_enabled;
   int hpf_enabled;
