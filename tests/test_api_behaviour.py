@@ -210,17 +210,19 @@ def test_pipelined_host_tick_matches_plain(emu_lib, oracle):
     eng.close()
 
 
-def test_native_rates_and_unsupported_formats(emu_lib):
-    """16 / 32 / 48 kHz mono engines exist (48 kHz with maximum_internal_processing_rate = 48000);
-    resampled rates and multichannel are outside the built scope and are refused, not approximated."""
+def test_rates_and_unsupported_formats(emu_lib):
+    """Mono engines exist for every API rate up to 48 kHz that has whole 10 ms frames (native 16 / 32 /
+    48 kHz, the others through the sinc resamplers); multichannel and rates above 48 kHz are outside
+    the built scope and are refused, not approximated."""
     import wap_b200
-    for rate in (16000, 32000, 48000):
-        eng = wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
+    for rate, max_rate in ((16000, 32000), (32000, 32000), (48000, 48000), (48000, 32000), (8000, 32000),
+                           (44100, 32000), (24000, 48000)):
+        eng = wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True, max_rate=max_rate)
         x = np.zeros((1, rate // 100), np.int16)
         assert eng.process(x, x).shape == (1, rate // 100)
         eng.close()
-    for rate in (8000, 44100):
+    for rate in (96000, 22050):
         with pytest.raises(RuntimeError):
             wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
     with pytest.raises(RuntimeError):
-        wap_b200.Engine(1, 48000, lib=emu_lib, aec=True, ns=True, max_rate=32000)
+        wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=True, ns=True)

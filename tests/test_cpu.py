@@ -253,6 +253,63 @@ def test_emu_aec3_ns_parity_32k_two_band(emu_lib, oracle):
     assert np.abs(out[0].astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL_FS * 32768
 
 
+@pytest.mark.parametrize("rate,kw", [
+    (48000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),  # the reference's default
+    (48000, dict(aec=False, ns=True, ns_level=2)),                                   # routing for 48 kHz clients
+    (48000, dict(aec=False, ns=False, hpf=True)),
+    (44100, dict(aec=True, ns=True, ns_level=1)),
+    (44100, dict(aec=False, ns=False, agc2=True, agc2_fixed_gain_db=6.0)),            # no band split: 44.1 -> 48 kHz
+    (8000, dict(aec=True, ns=True, ns_level=1)),
+    (24000, dict(aec=False, ns=True, ns_level=1)),
+])
+def test_emu_resampled_rates(emu_lib, oracle, rate, kw):
+    """API rate != processing rate (maximum_internal_processing_rate = 32000, the default):
+    PushSincResampler on the way in (render and capture) and out, the 48 kHz
+    capture_fullband_audio side path, the 48 kHz high-pass coefficients it selects for 32 kHz
+    data (audio_processing_impl.cc:598-611,632-692,1451-1460,1892)."""
+    from common import run_legs, synthetic_leg_48k
+    legs = [synthetic_leg_48k(3 + k, 80, 2.0, rate=rate) for k in range(2)]
+    out, stats = run_legs(emu_lib, rate, legs, stats_every=40 if kw["aec"] else 0, max_rate=32000, **kw)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(max_rate=32000, **kw).run_i16(
+            rate, far if kw["aec"] else None, near, stats_every=40 if kw["aec"] else 0)
+        assert err == 0
+        d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32)).max()
+        assert d <= TOL_FS * 32768, (k, d)
+        assert np.abs(ref_out.astype(np.int32)).mean() > 1.0
+        if kw["aec"]:
+            assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1
+
+
+def test_emu_resampled_float_interface_and_mute(emu_lib, oracle):
+    """48 kHz float frames under the default config: the float interface resamples before scaling
+    to FloatS16 and scales back before the output resampler does not apply (fullband path); while
+    the output is muted the fullband buffer keeps the unprocessed input and its resampler rests."""
+    import wap_b200
+    from common import synthetic_leg_48k
+    far, near = synthetic_leg_48k(5, 60, 1.5, rate=48000)
+    kw = dict(aec=True, ns=True, ns_level=1)
+    eng = wap_b200.Engine(1, 48000, lib=emu_lib, max_rate=32000, **kw)
+    ref = oracle.RefApm(max_rate=32000, **kw)
+    worst = 0.0
+    for f in range(60):
+        if f == 20:
+            eng.set_capture_output_used(False); ref.set_capture_output_used(False)
+        if f == 35:
+            eng.set_capture_output_used(True); ref.set_capture_output_used(True)
+        c = (near[f * 480:(f + 1) * 480].astype(np.float32) / 32768.0).reshape(1, 480)
+        r = (far[f * 480:(f + 1) * 480].astype(np.float32) / 32768.0).reshape(1, 480)
+        eng.set_stream_delay_ms(0)
+        o = eng.process(r, c)
+        ro, err = ref.tick_f32(48000, r.reshape(-1), c.reshape(-1))
+        assert err == 0
+        worst = max(worst, float(np.abs(o.reshape(-1) - ro).max()))
+        if 20 <= f < 35:
+            assert np.array_equal(o.reshape(-1), c.reshape(-1))  # muted: the input comes back
+    assert worst <= TOL_FS, worst
+    eng.close()
+
+
 @pytest.mark.parametrize("rate,gain_db", [(16000, 0.0), (16000, 12.0), (32000, 14.0), (48000, 20.0)])
 def test_emu_agc2_fixed_gain_and_limiter(emu_lib, oracle, rate, gain_db):
     """GainController2, default sub-configuration (fixed digital gain + limiter) on its own

@@ -190,3 +190,24 @@ def test_ns_parity_32k_two_band(gpu_lib, oracle):
     out = run_engine(gpu_lib, 32000, None, near, n_streams=3, aec=False, ns=True, ns_level=3)
     d = np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max()
     assert d <= TOL_FS * 32768, d
+
+
+@pytest.mark.parametrize("rate,kw", [
+    (48000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),
+    (48000, dict(aec=False, ns=True, ns_level=2)),
+    (44100, dict(aec=True, ns=True, ns_level=1)),
+    (8000, dict(aec=True, ns=True, ns_level=1)),
+])
+def test_resampled_rates(gpu_lib, oracle, rate, kw):
+    """API rate != processing rate under the reference's default maximum_internal_processing_rate
+    (32 kHz): sinc resamplers in and out, 48 kHz fullband side path; 6 legs x 4 s."""
+    legs = [synthetic_leg_48k(i, 400, 1.0 + 0.5 * i, rate=rate) for i in range(6)]
+    out, stats = run_legs(gpu_lib, rate, legs, stats_every=100 if kw["aec"] else 0, max_rate=32000, **kw)
+    for k, (far, near) in enumerate(legs):
+        ref_out, ref_stats, err = oracle.RefApm(max_rate=32000, **kw).run_i16(
+            rate, far if kw["aec"] else None, near, stats_every=100 if kw["aec"] else 0)
+        assert err == 0
+        d = np.abs(out[k].astype(np.int32) - ref_out.astype(np.int32)).max()
+        assert d <= TOL_FS * 32768, (k, int(d))
+        if kw["aec"]:
+            assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1, k

@@ -34,6 +34,7 @@ WAP_DEV float biquad_step(const BiquadCoef& c, Biquad& m, float x) {
 // S16ToFloatS16 / FloatToFloatS16 (audio_util.h:52-69) for sample i of leg `leg`.
 WAP_DEV float front_load_sample(const void* src, size_t leg, int len, int fmt, int i) {
   if (fmt == 0) return (float)(reinterpret_cast<const int16_t*>(src)[leg * len + i]);
+  if (fmt == 2) return reinterpret_cast<const float*>(src)[leg * len + i];  // already FloatS16 (k_resample)
   float v = reinterpret_cast<const float*>(src)[leg * len + i];
   v = fminr(v, 1.f);
   v = fmaxr(v, -1.f);
@@ -161,7 +162,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   // ---------------- capture: high-pass filter, saturation, [band split], FrameBlocker, decimator
   st.seen_capture = 1;
   {
-    const BiquadCoef* hc = (B == 3) ? kHpf48k : (B == 2 ? kHpf32k : kHpf16k);
+    const BiquadCoef* hc = cfg.hpf_rate == 48000 ? kHpf48k : (cfg.hpf_rate == 32000 ? kHpf32k : kHpf16k);
     Biquad h0 = st.hpf[0], h1 = st.hpf[1], h2 = st.hpf[2];
     int sat = 0;
     for (int i = 0; i < flen; ++i) {

@@ -29,6 +29,14 @@ __global__ void __launch_bounds__(128) k_front(TickArgs a) {
   if (idx < a.n) front_leg(a, idx);
 }
 
+// Resampled engines: API-rate frames -> processing-rate FloatS16 frames, one warp per leg.
+__global__ void __launch_bounds__(128) k_resample(TickArgs a) {
+  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());  // 4 warps x 2 * kRsMaxRequest floats
+  const int warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 4 + warp;
+  if (idx < a.n) resample_in_tick(a, idx, sm + warp * 2 * kRsMaxRequest);
+}
+
 #ifndef WAP_DELAY_MINBLOCKS
 #define WAP_DELAY_MINBLOCKS 5
 #endif
@@ -140,6 +148,12 @@ struct WapEngine {
   int delay_scratch_floats = 0;
   bool is_default = false;
   int sm_count = 148;
+  // resampled engines (API rate != processing rate)
+  wap::ResamplerState* d_rs = nullptr;   // [capacity][kRsPerLeg]
+  float* d_rs_kernels = nullptr;         // in | out tables
+  float* d_rs_render = nullptr;          // [staged][proc frame]
+  float* d_rs_capture = nullptr;
+  double rs_ratio_in = 1.0, rs_ratio_out = 1.0;
   int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
   // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -187,15 +201,24 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   if (f.sample_rate_hz < 8000 || f.sample_rate_hz > 384000) return WapError::BadSampleRate;
   if (f.num_channels <= 0) return WapError::BadNumberChannels;
   EngineConfig e{};
-  if (f.sample_rate_hz == 16000) {
-    e.num_bands = 1;
-  } else if (f.sample_rate_hz == 32000) {
-    e.num_bands = 2;  // two-band QMF (splitting_filter.cc:68-101)
-  } else if (f.sample_rate_hz == 48000 && c.pipeline_maximum_internal_processing_rate == 48000) {
-    e.num_bands = 3;
-  } else {
-    return WapError::UnsupportedConfig;  // resampled paths: SURVEY 8(f)-2
+  // InitializeLocked (audio_processing_impl.cc:632-692): the processing rate is the lowest native
+  // rate that covers the API rate, capped by maximum_internal_processing_rate when a multi-band
+  // submodule is active.
+  if (f.sample_rate_hz % 100 != 0 || f.sample_rate_hz > 48000) return WapError::UnsupportedConfig;
+  if (c.pipeline_maximum_internal_processing_rate != 32000 && c.pipeline_maximum_internal_processing_rate != 48000)
+    return WapError::UnsupportedConfig;
+  const bool multi_band = c.high_pass_filter_enabled || c.noise_suppression_enabled || c.echo_canceller_enabled;
+  const int uppermost = multi_band ? c.pipeline_maximum_internal_processing_rate : 48000;
+  int proc = uppermost;
+  for (int rate : {16000, 32000, 48000}) {
+    if (rate >= uppermost) { proc = uppermost; break; }
+    if (rate >= f.sample_rate_hz) { proc = rate; break; }
   }
+  e.num_bands = proc / 16000;
+  e.api_frame = f.sample_rate_hz / 100;
+  e.resample = proc != f.sample_rate_hz ? 1 : 0;
+  e.fullband_out = (proc < f.sample_rate_hz && f.sample_rate_hz == 48000) ? 1 : 0;
+  e.hpf_rate = e.fullband_out ? 48000 : proc;
   if (f.num_channels != 1) return WapError::UnsupportedConfig;  // multichannel: SURVEY 8 cfg4, later round
   if (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) return WapError::UnsupportedConfig;
   // AGC2: fixed digital gain + limiter (the default sub-configuration); the adaptive digital
@@ -203,7 +226,7 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   if (c.gain_controller2_enabled &&
       (c.gain_controller2_adaptive_digital_enabled || c.gain_controller2_input_volume_controller_enabled))
     return WapError::UnsupportedConfig;
-  e.sample_rate_hz = f.sample_rate_hz;
+  e.sample_rate_hz = proc;
   e.aec_enabled = c.echo_canceller_enabled;
   e.ns_enabled = c.noise_suppression_enabled;
   // InitializeHighPassFilter (audio_processing_impl.cc:1883-1907)
@@ -246,6 +269,13 @@ WapError ensure_staging(WapEngine* e, size_t n) {
   WAP_CUDA(cudaMalloc((void**)&e->d_slots, cap * sizeof(int)));
   WAP_CUDA(cudaMalloc((void**)&e->d_delays, cap * sizeof(int)));
   WAP_CUDA(cudaMallocHost(&e->h_pinned, cap * (3 * fb + 2 * sizeof(int))));
+  if (e->cfg.resample) {
+    if (e->d_rs_render) cudaFree(e->d_rs_render);
+    if (e->d_rs_capture) cudaFree(e->d_rs_capture);
+    const size_t pb = (size_t)wap::kFrame * e->cfg.num_bands * sizeof(float);
+    WAP_CUDA(cudaMalloc((void**)&e->d_rs_render, cap * pb));
+    WAP_CUDA(cudaMalloc((void**)&e->d_rs_capture, cap * pb));
+  }
   e->staged_streams = cap;
   e->last_slots.clear();
   e->last_handles.clear();
@@ -264,6 +294,28 @@ bool is_pinned_host(const void* p) {
   }
   return at.type == cudaMemoryTypeHost;
 #endif
+}
+
+// SincResampler::InitializeKernel (sinc_resampler.cc:212-246): 33 sub-sample offsets of a 32-tap
+// Blackman-windowed sinc, evaluated like the reference (float index arithmetic, double
+// trigonometry, float storage) so that the table is the reference's bit for bit.
+void build_sinc_kernel(double io_ratio, float* table) {
+  const double alpha = 0.16;
+  const double a0 = 0.5 * (1.0 - alpha), a1 = 0.5, a2 = 0.5 * alpha;
+  const double pi = 3.14159265358979323846;
+  double scale = io_ratio > 1.0 ? 1.0 / io_ratio : 1.0;  // SincScaleFactor: low-pass when downsampling
+  scale *= 0.9;                                          // ... with some roll-off margin
+  const int taps = wap::kRsKernelSize;
+  for (int o = 0; o <= wap::kRsOffsetCount; ++o) {
+    const float frac = static_cast<float>(o) / wap::kRsOffsetCount;
+    for (int i = 0; i < taps; ++i) {
+      const float arg = static_cast<float>(pi * (static_cast<float>(i - taps / 2) - frac));
+      const float x = (static_cast<float>(i) - frac) / static_cast<float>(taps);
+      const float window = static_cast<float>(a0 - a1 * cos(2.0 * pi * x) + a2 * cos(4.0 * pi * x));
+      const double sinc = arg == 0 ? scale : sin(scale * arg) / arg;
+      table[o * taps + i] = static_cast<float>(window * sinc);
+    }
+  }
 }
 
 int grid_for(int n_streams) {
@@ -289,7 +341,25 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   const int wpb = 4;
   const bool timing = e->timing;
   if (timing) cudaEventRecord(e->ev[0], e->stream);
-  WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
+  if (e->cfg.resample) {
+    // API-rate frames -> processing-rate frames; k_front then reads those (already FloatS16).
+    a.rs = e->d_rs;
+    a.rs_render = e->d_rs_render;
+    a.rs_capture = e->d_rs_capture;
+    a.rs_kernel_in = e->d_rs_kernels;
+    a.rs_kernel_out = e->d_rs_kernels + wap::kRsTableFloats;
+    a.rs_ratio_in = e->rs_ratio_in;
+    a.rs_ratio_out = e->rs_ratio_out;
+    WAP_LAUNCH(wap::k_resample, grid_for(n), wpb * 32, (size_t)wpb * 2 * wap::kRsMaxRequest * sizeof(float), e->stream, a);
+    e->launches++;
+    wap::TickArgs af = a;
+    af.render = d_render ? e->d_rs_render : nullptr;
+    af.capture = d_capture ? e->d_rs_capture : nullptr;
+    af.fmt = 2;
+    WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, af);
+  } else {
+    WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
+  }
   e->launches++;
   if (timing) cudaEventRecord(e->ev[1], e->stream);
   if (e->cfg.aec_enabled && d_capture) {
@@ -397,6 +467,18 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
     const size_t ub = (size_t)max_streams * sizeof(wap::UpperBandState);
     ok = cudaMalloc((void**)&e->d_upper, ub) == cudaSuccess && cudaMemset(e->d_upper, 0, ub) == cudaSuccess;
   }
+  if (ok && cfg.resample) {
+    const size_t rb = (size_t)max_streams * wap::kRsPerLeg * sizeof(wap::ResamplerState);
+    const int pf = wap::kFrame * cfg.num_bands;
+    e->rs_ratio_in = (double)cfg.api_frame * 1.0 / pf;  // source_frames * 1.0 / destination_frames
+    e->rs_ratio_out = (double)pf * 1.0 / cfg.api_frame;
+    std::vector<float> tables(2 * wap::kRsTableFloats);
+    build_sinc_kernel(e->rs_ratio_in, tables.data());
+    build_sinc_kernel(e->rs_ratio_out, tables.data() + wap::kRsTableFloats);
+    ok = cudaMalloc((void**)&e->d_rs, rb) == cudaSuccess && cudaMemset(e->d_rs, 0, rb) == cudaSuccess &&
+         cudaMalloc((void**)&e->d_rs_kernels, tables.size() * sizeof(float)) == cudaSuccess &&
+         cudaMemcpy(e->d_rs_kernels, tables.data(), tables.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
   if (ok) {
     StreamState* tmpl = new StreamState;
     wap::init_stream_state(*tmpl);
@@ -427,6 +509,10 @@ void wap_engine_destroy(WapEngine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_states);
   cudaFree(e->d_upper);
+  cudaFree(e->d_rs);
+  cudaFree(e->d_rs_kernels);
+  cudaFree(e->d_rs_render);
+  cudaFree(e->d_rs_capture);
   cudaFree(e->d_template);
   cudaFree(e->d_render);
   cudaFree(e->d_capture);
@@ -463,6 +549,9 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
              (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
   if (e->d_upper)
     for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
+  if (e->d_rs)
+    for (int i = 0; i < n; ++i)
+      WAP_CUDA(cudaMemsetAsync(&e->d_rs[(size_t)slots[i] * wap::kRsPerLeg], 0, wap::kRsPerLeg * sizeof(wap::ResamplerState), e->stream));
   e->launches++;
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(d_slots);

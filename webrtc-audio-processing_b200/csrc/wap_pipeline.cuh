@@ -58,6 +58,43 @@ WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
   aec3_delay_frame(st.aec, st.tick, sc);
 }
 
+// k_resample body (engines whose API rate differs from the processing rate): AudioBuffer::CopyFrom
+// with an input resampler for the render and the capture frame of one leg (audio_buffer.cc:116-160,
+// 234-300).  `scratch`: 2 * kRsMaxRequest floats.
+WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
+  const EngineConfig& cfg = a.cfg;
+  const int lane = lane_id();
+  const int slot = a.slots ? a.slots[idx] : idx;
+  const StreamState& st = a.states[slot];
+  const int pf = kFrame * cfg.num_bands, af = cfg.api_frame;
+  const ResamplerParams p{af, pf, a.rs_ratio_in, a.rs_kernel_in};
+  float* src = scratch;
+  float* dst = scratch + kRsMaxRequest;
+  // Render frames in front of the first capture frame are lost to the re-initialisation
+  // (EngineConfig::reinit_on_first_capture), and so is the resampler state they left.
+  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
+  for (int which = 0; which < 2; ++which) {
+    const void* in = which == 0 ? a.render : a.capture;
+    if (!in || (which == 0 && (!cfg.aec_enabled || !render_live))) continue;
+    __syncwarp();
+    for (int i = lane; i < af; i += 32)
+      src[i] = a.fmt == 0 ? (float)(reinterpret_cast<const int16_t*>(in)[(size_t)idx * af + i])
+                          : reinterpret_cast<const float*>(in)[(size_t)idx * af + i];
+    __syncwarp();
+    rs_push(a.rs[slot * kRsPerLeg + which], p, src, dst);
+    float* out = (which == 0 ? a.rs_render : a.rs_capture) + (size_t)idx * pf;
+    for (int i = lane; i < pf; i += 32) {
+      float v = dst[i];
+      if (a.fmt == 1) {  // FloatToFloatS16 after the resampler (audio_buffer.cc:150-155)
+        v = fminr(v, 1.f);
+        v = fmaxr(v, -1.f);
+        v = v * 32768.f;
+      }
+      out[i] = v;
+    }
+  }
+}
+
 // k_echo body: everything after the front end for one leg (reference
 // audio_processing_impl.cc:1359-1448 for the enabled submodules).
 WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
@@ -115,13 +152,30 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     else two_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), &st.capture_bands.synthesis[0][0]);
   }
   __syncwarp();
+  const int slot_rs = slot * kRsPerLeg;
+  float* tmp = reinterpret_cast<float*>(dsp);
+  int olen = flen;  // samples in `full` from here on
+  if (cfg.fullband_out) {
+    // capture_fullband_audio (audio_processing_impl.cc:1245-1253,1451-1460): a 48 kHz buffer that is
+    // refreshed from the processed frame (resampled, AudioBuffer::CopyTo(AudioBuffer*)) only while
+    // the output is used; otherwise it still holds the unprocessed input frame.
+    olen = cfg.api_frame;
+    if (output_used) {
+      const ResamplerParams p{flen, olen, a.rs_ratio_out, a.rs_kernel_out};
+      rs_push(a.rs[slot_rs + 2], p, full, tmp);
+      for (int i = lane_id(); i < olen; i += 32) full[i] = tmp[i];
+    } else {
+      for (int i = lane_id(); i < olen; i += 32) full[i] = front_load_sample(a.capture, idx, olen, a.fmt, i);
+    }
+    __syncwarp();
+  }
   // GainController2 runs on the merged full-band frame, only while the output is used
   // (audio_processing_impl.cc:1450-1477), before the PostFilter.
-  if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, flen, reinterpret_cast<float*>(dsp));
+  if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, olen, tmp);
   // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
   const bool post = up && B == 3;  // 48 kHz AEC3: PostFilter + output conversion in k_post
   if (!post && !output_used_last_frame && output_used) {
-    for (int i = lane_id(); i < flen; i += 32) full[i] = 0.f;
+    for (int i = lane_id(); i < olen; i += 32) full[i] = 0.f;
     __syncwarp();
   }
   if (lane_id() == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
@@ -131,7 +185,29 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     if (lane_id() == 0) st.tick.pad_[0] = (!output_used_last_frame && output_used) ? 1 : 0;
     return;
   }
-  store_frame(a.out, idx, flen, a.fmt, full);
+  if (cfg.resample && !cfg.fullband_out) {
+    // AudioBuffer::CopyTo with an output resampler (audio_buffer.cc:156-176,314-372): the int16
+    // interface resamples FloatS16 data and then rounds, the float interface scales first.
+    const int alen = cfg.api_frame;
+    __syncwarp();
+    if (a.fmt == 1) {
+      for (int i = lane_id(); i < flen; i += 32) {  // FloatS16ToFloat (audio_util.h:71-76)
+        float v = fminr(full[i], 32768.f);
+        v = fmaxr(v, -32768.f);
+        full[i] = v * (1.f / 32768.f);
+      }
+    }
+    const ResamplerParams p{flen, alen, a.rs_ratio_out, a.rs_kernel_out};
+    rs_push(a.rs[slot_rs + 2], p, full, tmp);
+    if (a.fmt == 0) {
+      store_frame(a.out, idx, alen, 0, tmp);
+    } else {
+      float* o = reinterpret_cast<float*>(a.out) + (size_t)idx * alen;
+      for (int i = lane_id(); i < alen; i += 32) o[i] = tmp[i];
+    }
+    return;
+  }
+  store_frame(a.out, idx, olen, a.fmt, full);
 }
 
 }  // namespace wap

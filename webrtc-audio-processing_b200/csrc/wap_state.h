@@ -310,7 +310,7 @@ struct alignas(16) StreamState {
 
 // Engine-wide (config class) constants uploaded once.
 struct EngineConfig {
-  int sample_rate_hz;   // 16000 or 48000
+  int sample_rate_hz;   // processing rate: 16000, 32000 or 48000
   int num_bands;        // 1 (16 kHz), 2 (32 kHz) or 3 (48 kHz)
   int aec_enabled;
   int ns_enabled;
@@ -338,6 +338,12 @@ struct EngineConfig {
   // SubmoduleStates::CaptureMultiBandProcessingPresent (audio_processing_impl.cc:399-412): the
   // 48 kHz frame is only split into bands when a multi-band submodule is active.
   int split_bands;
+  // API rate != processing rate (audio_processing_impl.cc:632-692, audio_buffer.cc:79-94): the
+  // frames are resampled on the way in and out.
+  int api_frame;        // samples per 10 ms at the API rate
+  int resample;         // 1: API rate differs from the processing rate
+  int fullband_out;     // 1: processing rate < 48 kHz output: capture_fullband_audio path (:598-611,1451-1460)
+  int hpf_rate;         // rate whose high-pass coefficients are used (proc_fullband_sample_rate_hz, :1892)
 };
 
 }  // namespace wap

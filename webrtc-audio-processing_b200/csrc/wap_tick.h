@@ -1,5 +1,6 @@
 // Arguments of one 10 ms tick, shared by the three tick kernels.
 #pragma once
+#include "dsp_resampler.cuh"
 #include "wap_state.h"
 
 namespace wap {
@@ -14,8 +15,16 @@ struct TickArgs {
   const void* render;     // [n][frame] or nullptr
   const void* capture;    // [n][frame] or nullptr
   void* out;              // [n][frame]
-  int fmt;                // 0 = int16, 1 = float [-1,1]
+  int fmt;                // 0 = int16, 1 = float [-1,1]  (k_front of a resampled engine: 2 = FloatS16 floats)
   EngineConfig cfg;
+  // Resampled engines only (cfg.resample): per-leg resampler states [slot][kRsPerLeg], the
+  // processing-rate frames k_resample leaves for k_front (FloatS16 floats), kernels and ratios.
+  ResamplerState* rs;
+  float* rs_render;       // [n][proc frame]
+  float* rs_capture;      // [n][proc frame]
+  const float* rs_kernel_in;
+  const float* rs_kernel_out;
+  double rs_ratio_in, rs_ratio_out;
 };
 
 }  // namespace wap
