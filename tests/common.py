@@ -142,3 +142,25 @@ def loud_bursty_signal(rate, n_frames, seed=3):
     env = 1500 + 14000 * (np.sin(2 * np.pi * 1.3 * t) > 0.2) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.37 * t) ** 2)
     x = rng.uniform(-1, 1, n) * env + 9000 * np.sin(2 * np.pi * 440 * t) * (t % 0.7 < 0.3)
     return x.clip(-32768, 32767).astype(np.int16)
+
+
+def float_interface_max_diff(lib, oracle, rate, n_frames, max_rate=32000, leg=3, **kw):
+    """Drive one leg through the float interface of both implementations; returns (number of output
+    samples whose float32 bits differ, max |delta| in FloatS16 units)."""
+    import wap_b200
+    fl = rate // 100
+    far, near = synthetic_leg_48k(leg, n_frames, 2.0, rate=rate)
+    eng = wap_b200.Engine(1, rate, lib=lib, max_rate=max_rate, **kw)
+    ref = oracle.RefApm(max_rate=max_rate, **kw)
+    differing, worst = 0, 0.0
+    for f in range(n_frames):
+        c = (near[f * fl:(f + 1) * fl].astype(np.float32) / 32768.0).reshape(1, fl)
+        r = (far[f * fl:(f + 1) * fl].astype(np.float32) / 32768.0).reshape(1, fl) if kw.get("aec") else None
+        eng.set_stream_delay_ms(0)
+        o = eng.process(r, c).reshape(-1)
+        ro, err = ref.tick_f32(rate, None if r is None else r.reshape(-1), c.reshape(-1))
+        assert err == 0
+        differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
+        worst = max(worst, float(np.abs(o - ro).max()) * 32768.0)
+    eng.close()
+    return differing, worst

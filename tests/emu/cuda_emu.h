@@ -186,6 +186,8 @@ static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 
 static inline unsigned __float_as_uint(float f) { return emu::from_bits<unsigned>(emu::to_bits(f)); }
 static inline int __float_as_int(float f) { return emu::from_bits<int>(emu::to_bits(f)); }
+static inline long long __double_as_longlong(double d) { return emu::from_bits<long long>(emu::to_bits(d)); }
+static inline double __longlong_as_double(long long v) { return emu::from_bits<double>(emu::to_bits(v)); }
 static inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(emu::to_bits(u)); }
 static inline float __int_as_float(int u) { return emu::from_bits<float>(emu::to_bits(u)); }
 template <class T>

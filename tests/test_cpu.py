@@ -337,3 +337,30 @@ def test_emu_full_chain_aec3_ns_agc2(emu_lib, oracle):
                                                 agc2_fixed_gain_db=6.0).run_i16(16000, far, near, stats_every=50)
         assert err == 0
         _check_aec(out[k], stats[k], ref_out, ref_stats)
+
+
+def test_emu_libm_restatement(emu_lib):
+    """csrc/wap_libm.cuh restates glibc's powf(2, p) and tanhf (neither is correctly rounded, and the
+    NS calls both): identical bits on 60 k random arguments each."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_libm_restatement as chk
+    for which in (0, 1):
+        bad, tot = chk.mismatches(emu_lib, which, 60000)
+        assert bad == 0, (which, bad, tot)
+
+
+@pytest.mark.parametrize("rate,max_rate,kw", [
+    (16000, 32000, dict(aec=False, ns=True, ns_level=1)),
+    (16000, 32000, dict(aec=True, ns=True, ns_level=2)),
+    (32000, 32000, dict(aec=False, ns=True, ns_level=3)),
+    (48000, 48000, dict(aec=False, ns=True, ns_level=1)),
+    (48000, 32000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),
+    (44100, 32000, dict(aec=False, ns=True, ns_level=0)),
+])
+def test_emu_float_interface_is_bit_identical(emu_lib, oracle, rate, max_rate, kw):
+    """Through the float interface nothing is rounded to int16 at the end, so this compares the
+    float32 bits of every output sample: zero differing samples."""
+    from common import float_interface_max_diff
+    differing, worst = float_interface_max_diff(emu_lib, oracle, rate, 120, max_rate=max_rate, **kw)
+    assert differing == 0, (differing, worst)

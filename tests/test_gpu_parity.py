@@ -211,3 +211,27 @@ def test_resampled_rates(gpu_lib, oracle, rate, kw):
         assert d <= TOL_FS * 32768, (k, int(d))
         if kw["aec"]:
             assert np.abs(stats[k][:, 1] - ref_stats[:, 3]).max() <= 0.1, k
+
+
+def test_libm_restatement_on_device(gpu_lib):
+    """powf(2, p) / tanhf as glibc evaluates them, on the device: identical bits."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import check_libm_restatement as chk
+    for which in (0, 1):
+        bad, tot = chk.mismatches(gpu_lib, which, 100000)
+        assert bad == 0, (which, bad, tot)
+
+
+@pytest.mark.parametrize("rate,max_rate,kw", [
+    (16000, 32000, dict(aec=True, ns=True, ns_level=1)),
+    (32000, 32000, dict(aec=False, ns=True, ns_level=3)),
+    (48000, 48000, dict(aec=True, ns=True, ns_level=1)),
+    (48000, 32000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),
+])
+def test_float_interface_is_bit_identical(gpu_lib, oracle, rate, max_rate, kw):
+    """Float interface, 5 s: every output sample has the reference's float32 bits."""
+    from common import float_interface_max_diff
+    differing, worst = float_interface_max_diff(gpu_lib, oracle, rate, 500, max_rate=max_rate, **kw)
+    assert differing == 0, (differing, worst)

@@ -8,6 +8,7 @@
 
 #include "dsp_fft.cuh"
 #include "wap_dev.cuh"
+#include "wap_libm.cuh"
 #include "wap_state.h"
 
 namespace wap {
@@ -30,9 +31,8 @@ WAP_DEV float ns_fast_log2(float in) {
   return out;
 }
 WAP_DEV float ns_pow2(float p) {
-  // reference: powf(2.f, p) (glibc, ~correctly rounded); evaluated in double
-  // and rounded once.
-  return (float)exp2((double)p);
+  // reference: powf(2.f, p), the glibc routine restated (wap_libm.cuh)
+  return libm_pow2f(p);
 }
 WAP_DEV float ns_pow_approx(float x, float p) { return ns_pow2(p * ns_fast_log2(x)); }
 WAP_DEV float ns_log_approx(float x) { return ns_fast_log2(x) * 0.693147180559945309f; }
@@ -546,8 +546,9 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
     float avg_prob_speech = sc.red[0] * (1.f / 32.f);
     const float avg_filter_gain = sc.red[1] * (1.f / 32.f);
     avg_prob_speech *= sc.red[3] / sc.red[2];
-    // reference calls tanhf here (noise_suppressor.cc:231)
-    float gain = 0.5f * (1.f + (float)tanh((double)(2.f * avg_prob_speech - 1.f)));
+    // GCC narrows static_cast<float>(tanh(float)) to tanhf (noise_suppressor.cc:231); glibc's
+    // routine restated in wap_libm.cuh
+    float gain = 0.5f * (1.f + libm_tanhf(2.f * avg_prob_speech - 1.f));
     if (avg_prob_speech >= 0.5f) gain = 0.25f * gain + 0.75f * avg_filter_gain;
     else gain = 0.5f * gain + 0.5f * avg_filter_gain;
     upper_band_gain = fminr(fmaxr(gain, cfg.ns_minimum_attenuating_gain), 1.f);

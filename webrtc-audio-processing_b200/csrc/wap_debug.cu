@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "dsp_fft.cuh"
+#include "wap_libm.cuh"
 #include "wap_launch.h"
 
 namespace wap {
@@ -35,6 +36,12 @@ __global__ void k_dbg_fft256(float* data, int count, int inverse) {
   for (int i = lane; i < 256; i += 32) data[(size_t)idx * 256 + i] = a[i];
 }
 
+// which: 0 = powf(2, x), 1 = tanhf(x); in place.
+__global__ void k_dbg_libm(float* data, int count, int which) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) data[i] = which == 0 ? libm_pow2f(data[i]) : libm_tanhf(data[i]);
+}
+
 }  // namespace wap
 
 #define WAPDBG_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -63,6 +70,19 @@ int wapdbg_fft256(float* host, int count, int inverse) {
   WAPDBG_CHECK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
   int wpb = 4, blocks = (count + wpb - 1) / wpb;
   WAP_LAUNCH(wap::k_dbg_fft256, blocks, wpb * 32, wpb * 256 * sizeof(float), 0, d, count, inverse);
+  WAPDBG_CHECK(cudaDeviceSynchronize());
+  WAPDBG_CHECK(cudaGetLastError());
+  WAPDBG_CHECK(cudaMemcpy(host, d, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
+int wapdbg_libm(float* host, int count, int which) {
+  float* d = nullptr;
+  size_t bytes = (size_t)count * sizeof(float);
+  WAPDBG_CHECK(cudaMalloc((void**)&d, bytes));
+  WAPDBG_CHECK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  WAP_LAUNCH(wap::k_dbg_libm, (count + 127) / 128, 128, 0, 0, d, count, which);
   WAPDBG_CHECK(cudaDeviceSynchronize());
   WAPDBG_CHECK(cudaGetLastError());
   WAPDBG_CHECK(cudaMemcpy(host, d, bytes, cudaMemcpyDeviceToHost));
