@@ -164,3 +164,30 @@ def float_interface_max_diff(lib, oracle, rate, n_frames, max_rate=32000, leg=3,
         worst = max(worst, float(np.abs(o - ro).max()) * 32768.0)
     eng.close()
     return differing, worst
+
+
+def stereo_leg(rate, n_frames, seed, right_gain=0.6):
+    """Interleaved stereo (render, capture) int16: two different synthetic legs mixed per channel.
+    right_gain > 2 clips the right capture channel while the left one stays moderate -- AEC3's
+    saturation test looks at both channels although only the left one is processed."""
+    f1, n1 = synthetic_leg_48k(seed, n_frames, 1.5, rate=rate)
+    f2, n2 = synthetic_leg_48k(seed + 40, n_frames, 1.0, rate=rate)
+    right = np.clip(n1.astype(np.float64) * right_gain + n2 * 0.4, -32768, 32767).astype(np.int16)
+    return np.stack([f1, f2], 1).reshape(-1), np.stack([n1, right], 1).reshape(-1)
+
+
+def run_stereo_i16(lib, oracle, rate, n_frames, seed, max_rate=32000, right_gain=0.6, **kw):
+    """One stereo leg through both implementations (int16 interleaved); returns (ours, reference)."""
+    import wap_b200
+    far, near = stereo_leg(rate, n_frames, seed, right_gain)
+    fl = rate // 100 * 2
+    eng = wap_b200.Engine(1, rate, channels=2, lib=lib, max_rate=max_rate, **kw)
+    ref_out, _, err = oracle.RefApm(max_rate=max_rate, **kw).run_i16(rate, far, near, render_ch=2, capture_ch=2)
+    assert err == 0
+    out = np.zeros_like(near)
+    for f in range(n_frames):
+        eng.set_stream_delay_ms(0)
+        out[f * fl:(f + 1) * fl] = eng.process(far[f * fl:(f + 1) * fl].reshape(1, fl),
+                                               near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
+    eng.close()
+    return out, ref_out

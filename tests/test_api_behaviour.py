@@ -212,7 +212,7 @@ def test_pipelined_host_tick_matches_plain(emu_lib, oracle):
 
 def test_rates_and_unsupported_formats(emu_lib):
     """Mono engines exist for every API rate up to 48 kHz that has whole 10 ms frames (native 16 / 32 /
-    48 kHz, the others through the sinc resamplers); multichannel and rates above 48 kHz are outside
+    48 kHz, the others through the sinc resamplers); true multi-channel processing and rates above 48 kHz are outside
     the built scope and are refused, not approximated."""
     import wap_b200
     for rate, max_rate in ((16000, 32000), (32000, 32000), (48000, 48000), (48000, 32000), (8000, 32000),
@@ -224,5 +224,7 @@ def test_rates_and_unsupported_formats(emu_lib):
     for rate in (96000, 22050):
         with pytest.raises(RuntimeError):
             wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
-    with pytest.raises(RuntimeError):
-        wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=True, ns=True)
+    eng = wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=True, ns=True)  # stereo in/out, mono processing
+    x = np.zeros((1, 960), np.int16)
+    assert eng.process(x, x).shape == (1, 960)
+    eng.close()

@@ -364,3 +364,34 @@ def test_emu_float_interface_is_bit_identical(emu_lib, oracle, rate, max_rate, k
     from common import float_interface_max_diff
     differing, worst = float_interface_max_diff(emu_lib, oracle, rate, 120, max_rate=max_rate, **kw)
     assert differing == 0, (differing, worst)
+
+
+@pytest.mark.parametrize("rate,max_rate,right_gain,kw", [
+    (16000, 32000, 0.6, dict(aec=True, ns=True, ns_level=1)),
+    (16000, 32000, 4.0, dict(aec=True, ns=False)),                 # right channel clips, left does not
+    (48000, 48000, 0.6, dict(aec=True, ns=True, ns_level=1)),
+    (48000, 32000, 3.0, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),
+    (44100, 32000, 0.6, dict(aec=True, ns=True, ns_level=2)),
+])
+def test_emu_stereo_default_pipeline(emu_lib, oracle, rate, max_rate, right_gain, kw):
+    """Stereo frames with multi_channel_render / _capture off (the default) and AEC3 on: render is
+    averaged to mono, capture continues with the first channel after AEC3's saturation test has seen
+    both (audio_processing_impl.cc:585-594,1343,1365-1373), output on both channels."""
+    from common import run_stereo_i16
+    out, ref_out = run_stereo_i16(emu_lib, oracle, rate, 100, 9, max_rate=max_rate, right_gain=right_gain, **kw)
+    assert np.array_equal(ref_out[0::2], ref_out[1::2])
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max()
+    assert d <= TOL_FS * 32768, d
+    if right_gain > 2 and rate == 16000:  # the saturation flag really differs from a left-only run
+        left = np.repeat(__import__("common").stereo_leg(rate, 100, 9, right_gain)[1][0::2], 2)
+        far = __import__("common").stereo_leg(rate, 100, 9, right_gain)[0]
+        alt, _, _ = oracle.RefApm(max_rate=max_rate, **kw).run_i16(rate, far, left, render_ch=2, capture_ch=2)
+        assert not np.array_equal(alt, ref_out)
+
+
+def test_emu_stereo_without_aec_is_refused(emu_lib):
+    import wap_b200
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 16000, channels=2, lib=emu_lib, aec=False, ns=True)
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 16000, channels=3, lib=emu_lib, aec=True, ns=True)

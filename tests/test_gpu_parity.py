@@ -235,3 +235,13 @@ def test_float_interface_is_bit_identical(gpu_lib, oracle, rate, max_rate, kw):
     from common import float_interface_max_diff
     differing, worst = float_interface_max_diff(gpu_lib, oracle, rate, 500, max_rate=max_rate, **kw)
     assert differing == 0, (differing, worst)
+
+
+@pytest.mark.parametrize("rate,max_rate,right_gain", [(16000, 32000, 4.0), (48000, 32000, 0.6), (48000, 48000, 3.0)])
+def test_stereo_default_pipeline(gpu_lib, oracle, rate, max_rate, right_gain):
+    """Stereo in / out with the default pipeline and AEC3+NS: 4 s, bit-identical."""
+    from common import run_stereo_i16
+    out, ref_out = run_stereo_i16(gpu_lib, oracle, rate, 400, 9, max_rate=max_rate, right_gain=right_gain,
+                                  aec=True, ns=True, ns_level=1)
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max()
+    assert d <= TOL_FS * 32768, int(d)

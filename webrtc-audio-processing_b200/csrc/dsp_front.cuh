@@ -32,10 +32,29 @@ WAP_DEV float biquad_step(const BiquadCoef& c, Biquad& m, float x) {
 }
 
 // S16ToFloatS16 / FloatToFloatS16 (audio_util.h:52-69) for sample i of leg `leg`.
-WAP_DEV float front_load_sample(const void* src, size_t leg, int len, int fmt, int i) {
-  if (fmt == 0) return (float)(reinterpret_cast<const int16_t*>(src)[leg * len + i]);
+// Sample i of leg `leg`'s API frame before any scaling (int16 interleaved / float planar; len =
+// samples per channel).  ch >= 0: that channel; ch < 0: AudioBuffer::CopyFrom's downmix by
+// averaging (audio_buffer.cc:116-140 float: sum in channel order times 1/C; :256-264 int16:
+// int32 sum, integer division).
+WAP_DEV float load_raw_sample(const void* src, size_t leg, int len, int fmt, int i, int C, int ch) {
+  if (fmt == 0) {
+    const int16_t* p = reinterpret_cast<const int16_t*>(src) + leg * (size_t)len * C + (size_t)i * C;
+    if (ch >= 0) return (float)p[ch];
+    int sum = 0;
+    for (int c = 0; c < C; ++c) sum += p[c];
+    return (float)(sum / C);
+  }
+  const float* p = reinterpret_cast<const float*>(src) + leg * (size_t)len * C + i;
+  if (ch >= 0) return p[(size_t)ch * len];
+  float v = p[0];
+  for (int c = 1; c < C; ++c) v += p[(size_t)c * len];
+  return v * (1.f / C);
+}
+// The same as a FloatS16 sample (S16ToFloatS16 / FloatToFloatS16, audio_util.h).
+WAP_DEV float front_load_sample(const void* src, size_t leg, int len, int fmt, int i, int C = 1, int ch = 0) {
   if (fmt == 2) return reinterpret_cast<const float*>(src)[leg * len + i];  // already FloatS16 (k_resample)
-  float v = reinterpret_cast<const float*>(src)[leg * len + i];
+  float v = load_raw_sample(src, leg, len, fmt, i, C, C == 1 ? 0 : ch);
+  if (fmt == 0) return v;
   v = fminr(v, 1.f);
   v = fmaxr(v, -1.f);
   return v * 32768.f;
@@ -128,12 +147,12 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
       for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
       float* full = ts.capture_frame;  // borrowed as the thread's 320/480-sample input buffer
-      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
+      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
       if (B == 3) three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
       else two_band_analysis_thread(full, frame, &st.render_bands.analysis[0][0]);
       band0 = frame;
     } else {
-      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i);
+      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
       band0 = frame;
     }
     const int L = s.render_blocker_len;
@@ -166,7 +185,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     Biquad h0 = st.hpf[0], h1 = st.hpf[1], h2 = st.hpf[2];
     int sat = 0;
     for (int i = 0; i < flen; ++i) {
-      float v = front_load_sample(a.capture, idx, flen, a.fmt, i);
+      float v = front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 0);
       if (cfg.hpf_enabled) {
         v = biquad_step(hc[0], h0, v);
         v = biquad_step(hc[1], h1, v);
@@ -176,6 +195,24 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       sat |= (v >= 32700.0f || v <= -32700.0f) ? 1 : 0;
     }
     st.hpf[0] = h0; st.hpf[1] = h1; st.hpf[2] = h2;
+    if (cfg.channels == 2 && cfg.aec_enabled) {
+      // The capture AudioBuffer keeps every channel until AEC3 has looked for saturation
+      // (audio_processing_impl.cc:1343,1365-1373): the second channel is high-pass filtered with
+      // its own state just for that test, then dropped.
+      ExtraChannelState& x = a.extra[slot];
+      Biquad g0 = x.hpf[0], g1 = x.hpf[1], g2 = x.hpf[2];
+      for (int i = 0; i < flen; ++i) {
+        float v = a.rs_capture1 ? a.rs_capture1[(size_t)idx * flen + i]
+                                : front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 1);
+        if (cfg.hpf_enabled) {
+          v = biquad_step(hc[0], g0, v);
+          v = biquad_step(hc[1], g1, v);
+          v = biquad_step(hc[2], g2, v);
+        }
+        sat |= (v >= 32700.0f || v <= -32700.0f) ? 1 : 0;
+      }
+      x.hpf[0] = g0; x.hpf[1] = g1; x.hpf[2] = g2;
+    }
     if (cfg.aec_enabled) s.saturated_microphone_signal = sat;
   }
   if (!cfg.aec_enabled) return;
@@ -249,14 +286,16 @@ WAP_DEV void post_leg(const TickArgs& a, int idx) {
       v = biquad_step(kPostFilter48k[3], p3, v);
     }
     if (zero) v = 0.f;
+    const int C = a.cfg.channels;  // the mono result goes to every output channel
     if (a.fmt == 0) {  // FloatS16ToS16 (audio_util.h:52-56)
       float w = fminr(v, 32767.f);
       w = fmaxr(w, -32768.f);
-      reinterpret_cast<int16_t*>(a.out)[(size_t)idx * flen + i] = (int16_t)(w + copysignf(0.5f, w));
+      const int16_t q = (int16_t)(w + copysignf(0.5f, w));
+      for (int c = 0; c < C; ++c) reinterpret_cast<int16_t*>(a.out)[((size_t)idx * flen + i) * C + c] = q;
     } else {           // FloatS16ToFloat (audio_util.h:71-76)
       float w = fminr(v, 32768.f);
       w = fmaxr(w, -32768.f);
-      reinterpret_cast<float*>(a.out)[(size_t)idx * flen + i] = w * (1.f / 32768.f);
+      for (int c = 0; c < C; ++c) reinterpret_cast<float*>(a.out)[((size_t)idx * C + c) * flen + i] = w * (1.f / 32768.f);
     }
   }
   up.post_filter[0] = p0; up.post_filter[1] = p1; up.post_filter[2] = p2; up.post_filter[3] = p3;

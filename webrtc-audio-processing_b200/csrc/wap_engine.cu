@@ -153,6 +153,8 @@ struct WapEngine {
   float* d_rs_kernels = nullptr;         // in | out tables
   float* d_rs_render = nullptr;          // [staged][proc frame]
   float* d_rs_capture = nullptr;
+  float* d_rs_capture1 = nullptr;        // stereo: second capture channel
+  wap::ExtraChannelState* d_extra = nullptr;  // stereo engines: [capacity]
   double rs_ratio_in = 1.0, rs_ratio_out = 1.0;
   int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
   // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
@@ -219,7 +221,13 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   e.resample = proc != f.sample_rate_hz ? 1 : 0;
   e.fullband_out = (proc < f.sample_rate_hz && f.sample_rate_hz == 48000) ? 1 : 0;
   e.hpf_rate = e.fullband_out ? 48000 : proc;
-  if (f.num_channels != 1) return WapError::UnsupportedConfig;  // multichannel: SURVEY 8 cfg4, later round
+  // Multi-channel frames are downmixed for processing and the mono result is copied to every
+  // output channel (the default pipeline); true multi-channel processing is SURVEY 8 cfg4.
+  // Stereo needs AEC3 (without it the reference runs NS / AGC2 on both channels).
+  if (f.num_channels > 2 || c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture ||
+      (f.num_channels == 2 && !c.echo_canceller_enabled))
+    return WapError::UnsupportedConfig;
+  e.channels = f.num_channels;
   if (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) return WapError::UnsupportedConfig;
   // AGC2: fixed digital gain + limiter (the default sub-configuration); the adaptive digital
   // controller and the input volume controller are SURVEY 8(f)-1.
@@ -275,6 +283,10 @@ WapError ensure_staging(WapEngine* e, size_t n) {
     const size_t pb = (size_t)wap::kFrame * e->cfg.num_bands * sizeof(float);
     WAP_CUDA(cudaMalloc((void**)&e->d_rs_render, cap * pb));
     WAP_CUDA(cudaMalloc((void**)&e->d_rs_capture, cap * pb));
+    if (e->cfg.channels == 2) {
+      if (e->d_rs_capture1) cudaFree(e->d_rs_capture1);
+      WAP_CUDA(cudaMalloc((void**)&e->d_rs_capture1, cap * pb));
+    }
   }
   e->staged_streams = cap;
   e->last_slots.clear();
@@ -341,9 +353,12 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   const int wpb = 4;
   const bool timing = e->timing;
   if (timing) cudaEventRecord(e->ev[0], e->stream);
+  a.extra = e->d_extra;
+  a.rs_capture1 = nullptr;
   if (e->cfg.resample) {
     // API-rate frames -> processing-rate frames; k_front then reads those (already FloatS16).
     a.rs = e->d_rs;
+    a.rs_capture1 = e->d_rs_capture1;
     a.rs_render = e->d_rs_render;
     a.rs_capture = e->d_rs_capture;
     a.rs_kernel_in = e->d_rs_kernels;
@@ -479,6 +494,10 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
          cudaMalloc((void**)&e->d_rs_kernels, tables.size() * sizeof(float)) == cudaSuccess &&
          cudaMemcpy(e->d_rs_kernels, tables.data(), tables.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
   }
+  if (ok && cfg.channels == 2) {
+    const size_t xb = (size_t)max_streams * sizeof(wap::ExtraChannelState);
+    ok = cudaMalloc((void**)&e->d_extra, xb) == cudaSuccess && cudaMemset(e->d_extra, 0, xb) == cudaSuccess;
+  }
   if (ok) {
     StreamState* tmpl = new StreamState;
     wap::init_stream_state(*tmpl);
@@ -513,6 +532,8 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_rs_kernels);
   cudaFree(e->d_rs_render);
   cudaFree(e->d_rs_capture);
+  cudaFree(e->d_rs_capture1);
+  cudaFree(e->d_extra);
   cudaFree(e->d_template);
   cudaFree(e->d_render);
   cudaFree(e->d_capture);
@@ -549,6 +570,8 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
              (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
   if (e->d_upper)
     for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
+  if (e->d_extra)
+    for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_extra[slots[i]], 0, sizeof(wap::ExtraChannelState), e->stream));
   if (e->d_rs)
     for (int i = 0; i < n; ++i)
       WAP_CUDA(cudaMemsetAsync(&e->d_rs[(size_t)slots[i] * wap::kRsPerLeg], 0, wap::kRsPerLeg * sizeof(wap::ResamplerState), e->stream));

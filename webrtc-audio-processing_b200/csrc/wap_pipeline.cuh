@@ -29,23 +29,27 @@ static_assert(offsetof(StreamState, aec) % 16 == 0 && offsetof(Aec3State, mf_h) 
                   sizeof(StreamState) % 16 == 0 && offsetof(AecScratch, mf) % 16 == 0,
               "128-bit accesses need 16-byte aligned state and scratch members");
 
-WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float* src) {
+// AudioBuffer::CopyTo: the mono frame `src` (FloatS16) to all C output channels of leg `stream`
+// (int16 interleaved / float planar).
+WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float* src, int C = 1) {
   const int lane = lane_id();
   if (fmt == 0) {
-    int16_t* p = reinterpret_cast<int16_t*>(dst) + stream * len;
+    int16_t* p = reinterpret_cast<int16_t*>(dst) + stream * len * C;
     for (int i = lane; i < len; i += 32) {  // FloatS16ToS16 (audio_util.h:52-56)
       float v = src[i];
       v = fminr(v, 32767.f);
       v = fmaxr(v, -32768.f);
-      p[i] = (int16_t)(v + copysignf(0.5f, v));
+      const int16_t q = (int16_t)(v + copysignf(0.5f, v));
+      for (int c = 0; c < C; ++c) p[i * C + c] = q;
     }
   } else {
-    float* p = reinterpret_cast<float*>(dst) + stream * len;
+    float* p = reinterpret_cast<float*>(dst) + stream * len * C;
     for (int i = lane; i < len; i += 32) {  // FloatS16ToFloat (audio_util.h:71-76)
       float v = src[i];
       v = fminr(v, 32768.f);
       v = fmaxr(v, -32768.f);
-      p[i] = v * (1.f / 32768.f);
+      v = v * (1.f / 32768.f);
+      for (int c = 0; c < C; ++c) p[(size_t)c * len + i] = v;
     }
   }
 }
@@ -73,16 +77,17 @@ WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
   // Render frames in front of the first capture frame are lost to the re-initialisation
   // (EngineConfig::reinit_on_first_capture), and so is the resampler state they left.
   const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
-  for (int which = 0; which < 2; ++which) {
+  const int n_in = (cfg.channels == 2 && cfg.aec_enabled) ? 3 : 2;
+  for (int which = 0; which < n_in; ++which) {
     const void* in = which == 0 ? a.render : a.capture;
     if (!in || (which == 0 && (!cfg.aec_enabled || !render_live))) continue;
     __syncwarp();
+    // render: averaged to mono; capture: first channel (which == 2: the second one, stereo only)
     for (int i = lane; i < af; i += 32)
-      src[i] = a.fmt == 0 ? (float)(reinterpret_cast<const int16_t*>(in)[(size_t)idx * af + i])
-                          : reinterpret_cast<const float*>(in)[(size_t)idx * af + i];
+      src[i] = load_raw_sample(in, idx, af, a.fmt, i, cfg.channels, which == 0 ? (cfg.channels == 1 ? 0 : -1) : which - 1);
     __syncwarp();
-    rs_push(a.rs[slot * kRsPerLeg + which], p, src, dst);
-    float* out = (which == 0 ? a.rs_render : a.rs_capture) + (size_t)idx * pf;
+    rs_push(which == 2 ? a.extra[slot].rs : a.rs[slot * kRsPerLeg + which], p, src, dst);
+    float* out = (which == 0 ? a.rs_render : (which == 1 ? a.rs_capture : a.rs_capture1)) + (size_t)idx * pf;
     for (int i = lane; i < pf; i += 32) {
       float v = dst[i];
       if (a.fmt == 1) {  // FloatToFloatS16 after the resampler (audio_buffer.cc:150-155)
@@ -165,7 +170,19 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       rs_push(a.rs[slot_rs + 2], p, full, tmp);
       for (int i = lane_id(); i < olen; i += 32) full[i] = tmp[i];
     } else {
-      for (int i = lane_id(); i < olen; i += 32) full[i] = front_load_sample(a.capture, idx, olen, a.fmt, i);
+      // Muted: the (multi-channel) input frame comes back, channel by channel.
+      const int total = olen * cfg.channels;
+      for (int i = lane_id(); i < total; i += 32) {
+        if (a.fmt == 0) {
+          reinterpret_cast<int16_t*>(a.out)[(size_t)idx * total + i] = reinterpret_cast<const int16_t*>(a.capture)[(size_t)idx * total + i];
+        } else {
+          float v = reinterpret_cast<const float*>(a.capture)[(size_t)idx * total + i];
+          v = fmaxr(fminr(v, 1.f), -1.f);
+          reinterpret_cast<float*>(a.out)[(size_t)idx * total + i] = v * 32768.f * (1.f / 32768.f);
+        }
+      }
+      if (lane_id() == 0) st.capture_output_used_last_frame = 0;
+      return;
     }
     __syncwarp();
   }
@@ -200,14 +217,15 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     const ResamplerParams p{flen, alen, a.rs_ratio_out, a.rs_kernel_out};
     rs_push(a.rs[slot_rs + 2], p, full, tmp);
     if (a.fmt == 0) {
-      store_frame(a.out, idx, alen, 0, tmp);
+      store_frame(a.out, idx, alen, 0, tmp, cfg.channels);
     } else {
-      float* o = reinterpret_cast<float*>(a.out) + (size_t)idx * alen;
-      for (int i = lane_id(); i < alen; i += 32) o[i] = tmp[i];
+      float* o = reinterpret_cast<float*>(a.out) + (size_t)idx * alen * cfg.channels;
+      for (int i = lane_id(); i < alen; i += 32)
+        for (int c = 0; c < cfg.channels; ++c) o[(size_t)c * alen + i] = tmp[i];
     }
     return;
   }
-  store_frame(a.out, idx, olen, a.fmt, full);
+  store_frame(a.out, idx, olen, a.fmt, full, cfg.channels);
 }
 
 }  // namespace wap

@@ -344,6 +344,11 @@ struct EngineConfig {
   int resample;         // 1: API rate differs from the processing rate
   int fullband_out;     // 1: processing rate < 48 kHz output: capture_fullband_audio path (:598-611,1451-1460)
   int hpf_rate;         // rate whose high-pass coefficients are used (proc_fullband_sample_rate_hz, :1892)
+  // Stereo API frames with the default pipeline (multi_channel_render / _capture off) and AEC3:
+  // render is averaged to mono (render AudioBuffer has one channel), capture keeps both channels
+  // until AEC3's saturation test and then continues with the first one only
+  // (audio_processing_impl.cc:585-594,1365-1373); the mono result goes to both output channels.
+  int channels;         // API channels of render, capture and output (1 or 2)
 };
 
 }  // namespace wap

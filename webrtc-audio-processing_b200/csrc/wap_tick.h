@@ -5,6 +5,13 @@
 
 namespace wap {
 
+// Second capture channel of a stereo leg: it only feeds AEC3's saturation test.
+struct ExtraChannelState {
+  Biquad hpf[3];
+  int pad_[4];
+  ResamplerState rs;
+};
+
 struct TickArgs {
   StreamState* states;
   UpperBandState* upper;  // [arena slot] for 48 kHz AEC3 engines, else nullptr
@@ -25,6 +32,9 @@ struct TickArgs {
   const float* rs_kernel_in;
   const float* rs_kernel_out;
   double rs_ratio_in, rs_ratio_out;
+  // Stereo engines only: second capture channel (high-pass state, input resampler, resampled frame).
+  ExtraChannelState* extra;  // [slot]
+  float* rs_capture1;        // [n][proc frame] or nullptr
 };
 
 }  // namespace wap
