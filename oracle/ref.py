@@ -54,8 +54,18 @@ class RefApm:
     """One reference webrtc::AudioProcessing instance (= one call leg)."""
 
     def __init__(self, aec=True, ns=True, ns_level=1, max_rate=48000, hpf=False,
-                 mc_render=False, mc_capture=False, agc2=False, agc2_fixed_gain_db=0.0):
-        if agc2:
+                 mc_render=False, mc_capture=False, agc2=False, agc2_fixed_gain_db=0.0,
+                 pre_amp=None, pre_gain=None, post_gain=None):
+        if pre_amp is not None or pre_gain is not None or post_gain is not None:
+            L = lib()
+            L.ref_apm_create_levels.restype = C.c_void_p
+            L.ref_apm_create_levels.argtypes = [C.c_int] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float]
+            cla = pre_gain is not None or post_gain is not None
+            self.h = L.ref_apm_create_levels(int(aec), int(ns), int(ns_level), int(max_rate), int(hpf), int(agc2),
+                                             float(agc2_fixed_gain_db), int(pre_amp is not None), float(pre_amp or 1.0),
+                                             int(cla), float(1.0 if pre_gain is None else pre_gain),
+                                             float(1.0 if post_gain is None else post_gain))
+        elif agc2:
             self.h = lib().ref_apm_create_agc2(int(aec), int(ns), int(ns_level), int(max_rate), 1,
                                                float(agc2_fixed_gain_db))
         else:
@@ -91,6 +101,18 @@ class RefApm:
 
     def set_capture_output_used(self, used):
         lib().ref_apm_set_capture_output_used(self.h, int(used))
+
+    def set_pre_gain(self, g):
+        L = lib(); L.ref_apm_set_pre_gain.argtypes = [C.c_void_p, C.c_float]; L.ref_apm_set_pre_gain(self.h, float(g))
+
+    def set_post_gain(self, g):
+        L = lib(); L.ref_apm_set_post_gain.argtypes = [C.c_void_p, C.c_float]; L.ref_apm_set_post_gain(self.h, float(g))
+
+    def set_fixed_post_gain(self, db):
+        L = lib(); L.ref_apm_set_fixed_post_gain.argtypes = [C.c_void_p, C.c_float]; L.ref_apm_set_fixed_post_gain(self.h, float(db))
+
+    def set_playout_volume(self, v):
+        L = lib(); L.ref_apm_set_playout_volume.argtypes = [C.c_void_p, C.c_int]; L.ref_apm_set_playout_volume(self.h, int(v))
 
     def stats(self):
         s = np.zeros(6, dtype=np.float32)

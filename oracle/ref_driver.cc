@@ -83,6 +83,23 @@ void* ref_apm_create_agc2(int aec, int ns, int ns_level, int max_rate, int agc2,
   return h;
 }
 
+// Everything above plus pre-amplifier / capture level adjustment, configured at construction.
+void* ref_apm_create_levels(int aec, int ns, int ns_level, int max_rate, int hpf, int agc2, float fixed_gain_db,
+                            int pre_amp_enabled, float pre_amp_gain, int cla_enabled, float cla_pre, float cla_post) {
+  auto* h = new RefApm;
+  webrtc::Environment env = webrtc::CreateEnvironment();
+  AudioProcessing::Config c = MakeConfig(aec, ns, ns_level, max_rate, hpf, 0, 0);
+  c.gain_controller2.enabled = agc2 != 0;
+  c.gain_controller2.fixed_digital.gain_db = fixed_gain_db;
+  c.pre_amplifier.enabled = pre_amp_enabled != 0;
+  c.pre_amplifier.fixed_gain_factor = pre_amp_gain;
+  c.capture_level_adjustment.enabled = cla_enabled != 0;
+  c.capture_level_adjustment.pre_gain_factor = cla_pre;
+  c.capture_level_adjustment.post_gain_factor = cla_post;
+  h->apm = webrtc::BuiltinAudioProcessingBuilder(c).Build(env);
+  return h;
+}
+
 void ref_apm_destroy(void* p) { delete static_cast<RefApm*>(p); }
 
 // One 10 ms tick on interleaved int16 frames: render then capture, exactly as
@@ -126,6 +143,20 @@ int ref_apm_tick_f32(void* p, int rate, int render_ch, int capture_ch,
   h->apm->set_stream_delay_ms(0);
   int e2 = h->apm->ProcessStream(cp.data(), cc, cc, op.data());
   return e1 ? e1 : e2;
+}
+
+// The runtime settings behind the wap_set_capture_*_gain / wap_set_playout_volume entry points.
+void ref_apm_set_pre_gain(void* p, float g) {
+  static_cast<RefApm*>(p)->apm->SetRuntimeSetting(AudioProcessing::RuntimeSetting::CreateCapturePreGain(g));
+}
+void ref_apm_set_post_gain(void* p, float g) {
+  static_cast<RefApm*>(p)->apm->SetRuntimeSetting(AudioProcessing::RuntimeSetting::CreateCapturePostGain(g));
+}
+void ref_apm_set_fixed_post_gain(void* p, float db) {
+  static_cast<RefApm*>(p)->apm->SetRuntimeSetting(AudioProcessing::RuntimeSetting::CreateCaptureFixedPostGain(db));
+}
+void ref_apm_set_playout_volume(void* p, int v) {
+  static_cast<RefApm*>(p)->apm->SetRuntimeSetting(AudioProcessing::RuntimeSetting::CreatePlayoutVolumeChange(v));
 }
 
 void ref_apm_set_capture_output_used(void* p, int used) {

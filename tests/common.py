@@ -191,3 +191,29 @@ def run_stereo_i16(lib, oracle, rate, n_frames, seed, max_rate=32000, right_gain
                                                near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
     eng.close()
     return out, ref_out
+
+
+def run_with_runtime_settings(lib, oracle, rate, n_frames, events, max_rate=32000, leg=7, **kw):
+    """One leg through the float interface of both implementations with runtime settings applied in
+    front of given frames: events = [(frame, 'pre_gain' | 'post_gain' | 'fixed_post_gain' |
+    'playout_volume', value)].  Returns the number of output samples whose float32 bits differ."""
+    import wap_b200
+    far, near = synthetic_leg(leg, n_frames) if rate == 16000 else synthetic_leg_48k(leg, n_frames, 1.0, rate=rate)
+    fl = rate // 100
+    eng = wap_b200.Engine(1, rate, lib=lib, max_rate=max_rate, **kw)
+    ref = oracle.RefApm(max_rate=max_rate, **kw)
+    differing = 0
+    for f in range(n_frames):
+        for ff, what, val in events:
+            if ff == f:
+                getattr(eng, "set_" + what)(val)
+                getattr(ref, "set_" + what)(val)
+        c = (near[f * fl:(f + 1) * fl].astype(np.float32) / 32768.0).reshape(1, fl)
+        r = (far[f * fl:(f + 1) * fl].astype(np.float32) / 32768.0).reshape(1, fl) if kw.get("aec") else None
+        eng.set_stream_delay_ms(0)
+        o = eng.process(r, c).reshape(-1)
+        ro, err = ref.tick_f32(rate, None if r is None else r.reshape(-1), c.reshape(-1))
+        assert err == 0
+        differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
+    eng.close()
+    return differing

@@ -395,3 +395,29 @@ def test_emu_stereo_without_aec_is_refused(emu_lib):
         wap_b200.Engine(1, 16000, channels=2, lib=emu_lib, aec=False, ns=True)
     with pytest.raises(RuntimeError):
         wap_b200.Engine(1, 16000, channels=3, lib=emu_lib, aec=True, ns=True)
+
+
+LEVEL_EVENTS = [(10, "pre_gain", 2.5), (20, "post_gain", 0.5), (30, "playout_volume", 100), (40, "playout_volume", 180),
+                (50, "pre_gain", 0.7), (60, "post_gain", 3.0)]
+AGC2_EVENTS = [(8, "fixed_post_gain", 12.0), (20, "fixed_post_gain", 12.0), (30, "fixed_post_gain", -3.0),
+               (50, "fixed_post_gain", 20.0)]
+
+
+@pytest.mark.parametrize("rate,max_rate,events,kw", [
+    (16000, 32000, LEVEL_EVENTS, dict(aec=True, ns=True, ns_level=1, pre_gain=1.5, post_gain=0.8)),
+    (16000, 32000, LEVEL_EVENTS, dict(aec=True, ns=False, pre_amp=3.0)),
+    (48000, 48000, LEVEL_EVENTS, dict(aec=True, ns=True, ns_level=1, pre_gain=1.0, post_gain=1.0)),
+    (48000, 32000, LEVEL_EVENTS, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=3.0,
+                                      pre_amp=2.0, pre_gain=1.2, post_gain=1.1)),
+    (32000, 32000, LEVEL_EVENTS, dict(aec=False, ns=True, ns_level=2, pre_gain=4.0, post_gain=0.9)),
+    (16000, 32000, LEVEL_EVENTS, dict(aec=True, ns=True, ns_level=1)),      # only the playout volume acts
+    (16000, 32000, AGC2_EVENTS, dict(aec=False, ns=False, agc2=True, agc2_fixed_gain_db=0.0)),
+    (48000, 32000, AGC2_EVENTS, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0)),
+])
+def test_emu_level_adjustment_and_runtime_settings(emu_lib, oracle, rate, max_rate, events, kw):
+    """Pre-amplifier / capture level adjustment (ramped pre and post gains, clamp), the runtime
+    settings kCapturePreGain / kCapturePostGain / kCaptureFixedPostGain / kPlayoutVolumeChange, and
+    the echo-path gain-change flag AEC3 gets from them (audio_processing_impl.cc:970-1038,1289-1341,
+    1526-1528; gain_controller2.cc:160-168): float32 bits identical."""
+    from common import run_with_runtime_settings
+    assert run_with_runtime_settings(emu_lib, oracle, rate, 80, events, max_rate=max_rate, **kw) == 0

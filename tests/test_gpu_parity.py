@@ -245,3 +245,13 @@ def test_stereo_default_pipeline(gpu_lib, oracle, rate, max_rate, right_gain):
                                   aec=True, ns=True, ns_level=1)
     d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max()
     assert d <= TOL_FS * 32768, int(d)
+
+
+def test_level_adjustment_and_runtime_settings(gpu_lib, oracle):
+    """Pre / post gains, AGC2 fixed gain and playout volume changed at run time, 48 kHz default config."""
+    from common import run_with_runtime_settings
+    events = [(10, "pre_gain", 2.5), (20, "post_gain", 0.5), (30, "playout_volume", 100), (40, "playout_volume", 180),
+              (50, "fixed_post_gain", 12.0), (70, "pre_gain", 0.7), (90, "fixed_post_gain", -3.0), (120, "post_gain", 3.0)]
+    kw = dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=3.0, pre_amp=2.0, pre_gain=1.2, post_gain=1.1)
+    for rate, max_rate in ((48000, 32000), (16000, 32000), (48000, 48000)):
+        assert run_with_runtime_settings(gpu_lib, oracle, rate, 200, events, max_rate=max_rate, **kw) == 0

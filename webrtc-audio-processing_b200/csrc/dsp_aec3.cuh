@@ -123,7 +123,7 @@ WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int
     rec.process = 1;
     rec.blocks_read = s.blocks_read;
     rec.spectra_read = s.spectra_read;
-    rec.gain_change = 0;  // capture_.echo_path_gain_change: analog level / playout volume changes only
+    rec.gain_change = ts.pad_[1];  // capture_.echo_path_gain_change, set by k_front
     rec.delay_change = delay_change;
     rec.clock_drift = s.cd_level != 0;
     rec.est_has = s.bp_has_estimated_delay;

@@ -59,10 +59,27 @@ WAP_DEV void agc2_process(Agc2State& st, const EngineConfig& cfg, float* frame, 
   const int lane = lane_id();
   const int sub = flen / kAgc2SubFrames;
   __syncwarp();
-  // GainApplier with a constant gain (last == current): untouched when the gain is so close to
-  // one that int16 samples cannot change (gain_applier.cc:26-29,43-57).
-  const float g = cfg.agc2_fixed_gain;
-  if (!(1.f - 1.f / 32767.f <= g && g <= 1.f + 1.f / 32767.f)) {
+  // GainApplier::ApplyGain -> ApplyGainWithRamping (gain_applier.cc:41-74,88-97): untouched when the
+  // gain is constant and so close to one that int16 samples cannot change, a plain multiply when
+  // constant, else a linear ramp from the last gain (a serial chain of additions: lane 0).
+  const float g_last = st.gain_last, g = st.gain_current;
+  if (st.reset_limiter) {  // SetFixedGainDb changed the gain: Limiter::Reset()
+    __syncwarp();
+    if (lane == 0) { st.filter_state_level = 0.f; st.reset_limiter = 0; }
+    __syncwarp();
+  }
+  if (g_last != g) {
+    const float increment = (g - g_last) * (1.f / flen);
+    if (lane == 0) {
+      float gain = g_last;
+      for (int i = 0; i < flen; ++i) { fac[i] = gain; gain += increment; }
+    }
+    __syncwarp();
+    for (int i = lane; i < flen; i += 32) frame[i] *= fac[i];
+    __syncwarp();
+    if (lane == 0) st.gain_last = g;
+    __syncwarp();
+  } else if (!(1.f - 1.f / 32767.f <= g && g <= 1.f + 1.f / 32767.f)) {
     for (int i = lane; i < flen; i += 32) frame[i] *= g;
     __syncwarp();
   }

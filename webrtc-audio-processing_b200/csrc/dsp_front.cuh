@@ -118,6 +118,33 @@ WAP_DEV void front_slice_band(const float* band, float* blocker, int L, int nb, 
   for (int j = 0; j < rem; ++j) blocker[j] = band[kFrame - rem + j];
 }
 
+// AudioSamplesScaler::Process for one sample: `mode` 0 = gain 1 throughout (nothing, not even the
+// clamp), 1 = constant gain, 2 = rising ramp, 3 = falling ramp (audio_samples_scaler.cc:25-90).
+struct ScalerRun {
+  int mode;
+  float gain, increment, target;
+};
+WAP_DEV ScalerRun scaler_begin(float prev, float target, int samples) {
+  ScalerRun r;
+  r.gain = prev;
+  r.target = target;
+  r.increment = 0.f;
+  if (target == 1.f && prev == target) r.mode = 0;
+  else if (prev == target) r.mode = 1;
+  else {
+    r.increment = (target - prev) * (1.f / samples);
+    r.mode = r.increment > 0.f ? 2 : 3;
+  }
+  return r;
+}
+WAP_DEV float scaler_step(ScalerRun& r, float v) {
+  if (r.mode == 0) return v;
+  if (r.mode == 2) r.gain = fminr(r.gain + r.increment, r.target);
+  else if (r.mode == 3) r.gain = fmaxr(r.gain + r.increment, r.target);
+  v *= r.gain;
+  return fminr(fmaxr(v, -32768.f), 32767.f);  // SafeClamp
+}
+
 // The front end of one tick for leg `idx` (thread-private).
 WAP_DEV void front_leg(const TickArgs& a, int idx) {
   const EngineConfig& cfg = a.cfg;
@@ -184,6 +211,11 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     const BiquadCoef* hc = cfg.hpf_rate == 48000 ? kHpf48k : (cfg.hpf_rate == 32000 ? kHpf32k : kHpf16k);
     Biquad h0 = st.hpf[0], h1 = st.hpf[1], h2 = st.hpf[2];
     int sat = 0;
+    // CaptureLevelsAdjuster::ApplyPreLevelAdjustment follows the full-band high-pass filter
+    // (audio_processing_impl.cc:1280-1299).
+    LevelState& lv = st.levels;
+    ScalerRun pre = scaler_begin(lv.pre_prev, lv.pre_target, flen);
+    if (!cfg.levels_enabled) pre.mode = 0;
     for (int i = 0; i < flen; ++i) {
       float v = front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 0);
       if (cfg.hpf_enabled) {
@@ -191,6 +223,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
         v = biquad_step(hc[1], h1, v);
         v = biquad_step(hc[2], h2, v);
       }
+      v = scaler_step(pre, v);
       ts.capture_frame[i] = v;
       sat |= (v >= 32700.0f || v <= -32700.0f) ? 1 : 0;
     }
@@ -201,6 +234,8 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       // its own state just for that test, then dropped.
       ExtraChannelState& x = a.extra[slot];
       Biquad g0 = x.hpf[0], g1 = x.hpf[1], g2 = x.hpf[2];
+      ScalerRun pre1 = scaler_begin(lv.pre_prev, lv.pre_target, flen);
+      if (!cfg.levels_enabled) pre1.mode = 0;
       for (int i = 0; i < flen; ++i) {
         float v = a.rs_capture1 ? a.rs_capture1[(size_t)idx * flen + i]
                                 : front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 1);
@@ -209,11 +244,25 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
           v = biquad_step(hc[1], g1, v);
           v = biquad_step(hc[2], g2, v);
         }
+        v = scaler_step(pre1, v);
         sat |= (v >= 32700.0f || v <= -32700.0f) ? 1 : 0;
       }
       x.hpf[0] = g0; x.hpf[1] = g1; x.hpf[2] = g2;
     }
-    if (cfg.aec_enabled) s.saturated_microphone_signal = sat;
+    if (cfg.levels_enabled) lv.pre_prev = lv.pre_target;
+    if (cfg.aec_enabled) {
+      s.saturated_microphone_signal = sat;
+      // capture_.echo_path_gain_change (audio_processing_impl.cc:1316-1341): a changed pre-gain or
+      // playout volume; EchoCanceller3 hands it to every block of this frame.
+      int gc = 0;
+      if (cfg.levels_enabled) {
+        gc |= (lv.prev_pre_adjustment_gain != lv.pre_target && lv.prev_pre_adjustment_gain >= 0.f) ? 1 : 0;
+        lv.prev_pre_adjustment_gain = lv.pre_target;
+      }
+      gc |= (lv.prev_playout_volume != lv.playout_volume && lv.prev_playout_volume >= 0) ? 1 : 0;
+      lv.prev_playout_volume = lv.playout_volume;
+      ts.pad_[1] = gc;
+    }
   }
   if (!cfg.aec_enabled) return;
   const float* cap0 = ts.capture_frame;
@@ -277,6 +326,10 @@ WAP_DEV void post_leg(const TickArgs& a, int idx) {
   const int flen = kFrame * 3;
   Biquad p0 = up.post_filter[0], p1 = up.post_filter[1], p2 = up.post_filter[2], p3 = up.post_filter[3];
   const bool zero = st.tick.pad_[0] != 0;  // first frame after un-muting (set by k_echo)
+  // CaptureLevelsAdjuster::ApplyPostLevelAdjustment, after the PostFilter, while the output is used
+  ScalerRun post = scaler_begin(st.levels.post_prev, st.levels.post_target, flen);
+  if (!a.cfg.levels_enabled || !st.capture_output_used) post.mode = 0;
+  else st.levels.post_prev = st.levels.post_target;
   for (int i = 0; i < flen; ++i) {
     float v = st.tick.capture_frame[i];
     if (st.capture_output_used) {
@@ -285,6 +338,7 @@ WAP_DEV void post_leg(const TickArgs& a, int idx) {
       v = biquad_step(kPostFilter48k[2], p2, v);
       v = biquad_step(kPostFilter48k[3], p3, v);
     }
+    v = scaler_step(post, v);
     if (zero) v = 0.f;
     const int C = a.cfg.channels;  // the mono result goes to every output channel
     if (a.fmt == 0) {  // FloatS16ToS16 (audio_util.h:52-56)

@@ -170,6 +170,12 @@ struct WapAudioProcessing {
   bool was_stream_delay_set = false;
   bool capture_output_used = true;
   bool capture_output_used_dirty = false;  // not yet written to the leg's state slab
+  // runtime settings waiting for the next capture frame (HandleCaptureRuntimeSettings)
+  bool pre_gain_dirty = false, post_gain_dirty = false, playout_volume_dirty = false, agc2_gain_dirty = false;
+  float agc2_gain_factor = -1.f;  // < 0: the engine's configured gain
+  bool agc2_reset_limiter = false;
+  float pre_gain_target = 1.f, post_gain_target = 1.f;
+  int playout_volume = -1;
   int analog_level = 0;
   std::deque<std::vector<unsigned char>> render_queue;  // SwapQueue stand-in (aec3_common.h:41)
   WapSampleFormat render_fmt = WapSampleFormat::I16;
@@ -228,7 +234,11 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
       (f.num_channels == 2 && !c.echo_canceller_enabled))
     return WapError::UnsupportedConfig;
   e.channels = f.num_channels;
-  if (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) return WapError::UnsupportedConfig;
+  e.levels_enabled = (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) ? 1 : 0;
+  e.post_gain_enabled = c.capture_level_adjustment_enabled ? 1 : 0;
+  // capture level adjustment: pre / post gains; the analog mic gain emulation needs an input volume
+  // controller.
+  if (c.capture_level_adjustment_enabled && c.analog_mic_gain_emulation_enabled) return WapError::UnsupportedConfig;
   // AGC2: fixed digital gain + limiter (the default sub-configuration); the adaptive digital
   // controller and the input volume controller are SURVEY 8(f)-1.
   if (c.gain_controller2_enabled &&
@@ -501,6 +511,14 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   if (ok) {
     StreamState* tmpl = new StreamState;
     wap::init_stream_state(*tmpl);
+    tmpl->agc2.gain_last = tmpl->agc2.gain_current = cfg.agc2_fixed_gain;
+    if (cfg.levels_enabled) {  // InitializeCaptureLevelsAdjuster (audio_processing_impl.cc:2108-2130)
+      float pre_gain = 1.f;
+      if (config.pre_amplifier_enabled) pre_gain *= config.pre_amplifier_fixed_gain_factor;
+      if (config.capture_level_adjustment_enabled) pre_gain *= config.capture_level_adjustment_pre_gain_factor;
+      tmpl->levels.pre_prev = tmpl->levels.pre_target = pre_gain;
+      tmpl->levels.post_prev = tmpl->levels.post_target = config.capture_level_adjustment_post_gain_factor;
+    }
     ok = cudaMemcpy(e->d_template, tmpl, sizeof(StreamState), cudaMemcpyHostToDevice) == cudaSuccess;
     delete tmpl;
   }
@@ -637,12 +655,26 @@ static WapError prepare_tick(WapEngine* e, WapAudioProcessing* const* handles, i
   if (e->dirty_legs > 0) {  // rare: un/mute events
     for (int i = 0; i < n; ++i) {
       WapAudioProcessing* h = handles[i];
-      if (!h->capture_output_used_dirty) continue;
+      StreamState* slab = &e->d_states[h->slot];
+      if (h->pre_gain_dirty) WAP_CUDA(cudaMemcpyAsync(&slab->levels.pre_target, &h->pre_gain_target, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+      if (h->post_gain_dirty) WAP_CUDA(cudaMemcpyAsync(&slab->levels.post_target, &h->post_gain_target, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+      if (h->playout_volume_dirty) WAP_CUDA(cudaMemcpyAsync(&slab->levels.playout_volume, &h->playout_volume, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      if (h->agc2_gain_dirty) {
+        WAP_CUDA(cudaMemcpyAsync(&slab->agc2.gain_current, &h->agc2_gain_factor, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (h->agc2_reset_limiter) {
+          static const int one = 1;
+          WAP_CUDA(cudaMemcpyAsync(&slab->agc2.reset_limiter, &one, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+          h->agc2_reset_limiter = false;
+        }
+      }
       const int v = h->capture_output_used ? 1 : 0;
-      WAP_CUDA(cudaMemcpyAsync(&e->d_states[h->slot].capture_output_used, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      if (h->capture_output_used_dirty) WAP_CUDA(cudaMemcpyAsync(&slab->capture_output_used, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      const int n_dirty = (int)h->pre_gain_dirty + (int)h->post_gain_dirty + (int)h->playout_volume_dirty + (int)h->capture_output_used_dirty +
+                          (int)h->agc2_gain_dirty;
+      if (!n_dirty) continue;
       WAP_CUDA(cudaStreamSynchronize(e->stream));
-      h->capture_output_used_dirty = false;
-      e->dirty_legs--;
+      h->pre_gain_dirty = h->post_gain_dirty = h->playout_volume_dirty = h->capture_output_used_dirty = h->agc2_gain_dirty = false;
+      e->dirty_legs -= n_dirty;
     }
   }
   const int* d_delays = nullptr;

@@ -109,6 +109,9 @@ inline void init_stream_state(StreamState& st) {
   st.capture_output_used = 1;
   st.capture_output_used_last_frame = 1;
   st.agc2.last_scaling_factor = 1.f;  // limiter.h
+  st.levels.pre_prev = st.levels.pre_target = st.levels.post_prev = st.levels.post_target = 1.f;
+  st.levels.prev_pre_adjustment_gain = -1.f;
+  st.levels.playout_volume = st.levels.prev_playout_volume = -1;
   init_ns_state(st.ns);
   init_aec3_state(st.aec);
 }

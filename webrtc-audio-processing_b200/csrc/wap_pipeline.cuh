@@ -189,8 +189,32 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   // GainController2 runs on the merged full-band frame, only while the output is used
   // (audio_processing_impl.cc:1450-1477), before the PostFilter.
   if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, olen, tmp);
+  const bool post = up && B == 3;  // 48 kHz AEC3: PostFilter, post gain and output conversion in k_post
+  // CaptureLevelsAdjuster::ApplyPostLevelAdjustment (audio_processing_impl.cc:1526-1528), while the
+  // output is used: the gain ramp is a serial chain (lane 0), the multiply and clamp are not.
+  if (cfg.levels_enabled && output_used && !post) {
+    LevelState& lv = st.levels;
+    __syncwarp();
+    const float prev = lv.post_prev, target = lv.post_target;
+    __syncwarp();
+    ScalerRun run = scaler_begin(prev, target, olen);
+    if (run.mode >= 2) {
+      if (lane_id() == 0)
+        for (int i = 0; i < olen; ++i) {
+          run.gain = run.mode == 2 ? fminr(run.gain + run.increment, run.target) : fmaxr(run.gain + run.increment, run.target);
+          tmp[i] = run.gain;
+        }
+      __syncwarp();
+    }
+    if (run.mode != 0)
+      for (int i = lane_id(); i < olen; i += 32) {
+        const float g = run.mode >= 2 ? tmp[i] : prev;
+        full[i] = fminr(fmaxr(full[i] * g, -32768.f), 32767.f);
+      }
+    __syncwarp();
+    if (lane_id() == 0) lv.post_prev = target;
+  }
   // Output is zeroed for the first frame after un-muting (audio_processing_impl.cc:1540-1552).
-  const bool post = up && B == 3;  // 48 kHz AEC3: PostFilter + output conversion in k_post
   if (!post && !output_used_last_frame && output_used) {
     for (int i = lane_id(); i < olen; i += 32) full[i] = 0.f;
     __syncwarp();

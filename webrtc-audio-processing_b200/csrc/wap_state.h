@@ -285,6 +285,22 @@ struct alignas(16) UpperBandState {
 struct Agc2State {
   float filter_state_level;    // FixedDigitalLevelEstimator::filter_state_level_, init 0
   float last_scaling_factor;   // Limiter::last_scaling_factor_, init 1
+  // fixed GainApplier::{last_gain_factor_, current_gain_factor_} (init: the configured gain) and a
+  // pending Limiter::Reset() from GainController2::SetFixedGainDb (gain_controller2.cc:160-168)
+  float gain_last, gain_current;
+  int reset_limiter;
+  int pad_;
+};
+
+// CaptureLevelsAdjuster (capture_levels_adjuster/{capture_levels_adjuster,audio_samples_scaler}.cc)
+// and the echo-path gain-change detection around it (audio_processing_impl.cc:1316-1341).
+struct LevelState {
+  float pre_prev, pre_target;      // pre AudioSamplesScaler::{previous_gain_, target_gain_}
+  float post_prev, post_target;    // post scaler
+  float prev_pre_adjustment_gain;  // capture_.prev_pre_adjustment_gain (-1)
+  int playout_volume;              // capture_.playout_volume (-1)
+  int prev_playout_volume;         // capture_.prev_playout_volume (-1)
+  int pad_;
 };
 
 // One call leg.
@@ -301,6 +317,7 @@ struct alignas(16) StreamState {
   int pad_[1];
   Agc2State agc2;
   int pad2_[2];
+  LevelState levels;
   ThreeBandState capture_bands; // AudioBuffer's SplittingFilter (48 kHz only)
   ThreeBandState render_bands;
   NsState ns;
@@ -349,6 +366,8 @@ struct EngineConfig {
   // until AEC3's saturation test and then continues with the first one only
   // (audio_processing_impl.cc:585-594,1365-1373); the mono result goes to both output channels.
   int channels;         // API channels of render, capture and output (1 or 2)
+  int levels_enabled;   // pre_amplifier.enabled || capture_level_adjustment.enabled
+  int post_gain_enabled;  // capture_level_adjustment.enabled: kCapturePostGain is honoured
 };
 
 }  // namespace wap

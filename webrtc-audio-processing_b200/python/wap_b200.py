@@ -130,6 +130,10 @@ def load(path=None):
     L.wap_streams_set_delay_ms.argtypes = [vp, i32, C.c_int]
     L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
     L.wap_engine_set_pipeline_chunks.argtypes = [vp, i32]
+    L.wap_set_capture_pre_gain.argtypes = [vp, C.c_float]
+    L.wap_set_capture_post_gain.argtypes = [vp, C.c_float]
+    L.wap_set_playout_volume.argtypes = [vp, C.c_int]
+    L.wap_set_capture_fixed_post_gain.argtypes = [vp, C.c_float]
     L.wap_engine_read_kernel_timing.restype = C.c_int64
     L.wap_engine_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.wap_engine_algorithmic_bytes_per_kernel.argtypes = [vp, C.POINTER(C.c_double)]
@@ -139,8 +143,15 @@ def load(path=None):
 
 
 def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False, agc2=False,
-                agc2_fixed_gain_db=0.0):
+                agc2_fixed_gain_db=0.0, pre_amp=None, pre_gain=None, post_gain=None):
     c = lib.wap_config_default()
+    if pre_amp is not None:
+        c.pre_amplifier_enabled = True
+        c.pre_amplifier_fixed_gain_factor = float(pre_amp)
+    if pre_gain is not None or post_gain is not None:
+        c.capture_level_adjustment_enabled = True
+        c.capture_level_adjustment_pre_gain_factor = float(1.0 if pre_gain is None else pre_gain)
+        c.capture_level_adjustment_post_gain_factor = float(1.0 if post_gain is None else post_gain)
     c.gain_controller2_enabled = bool(agc2)
     c.gain_controller2_fixed_digital_gain_db = float(agc2_fixed_gain_db)
     c.echo_canceller_enabled = bool(aec)
@@ -179,6 +190,22 @@ class Engine:
         err = self.lib.wap_engine_set_pipeline_chunks(self.h, int(chunks))
         if err:
             raise RuntimeError("wap_engine_set_pipeline_chunks -> WapError %d" % err)
+
+    def set_pre_gain(self, gain, legs=None):
+        for i in (range(self.n) if legs is None else legs):
+            self.lib.wap_set_capture_pre_gain(self.handles[i], float(gain))
+
+    def set_post_gain(self, gain, legs=None):
+        for i in (range(self.n) if legs is None else legs):
+            self.lib.wap_set_capture_post_gain(self.handles[i], float(gain))
+
+    def set_fixed_post_gain(self, gain_db, legs=None):
+        for i in (range(self.n) if legs is None else legs):
+            self.lib.wap_set_capture_fixed_post_gain(self.handles[i], float(gain_db))
+
+    def set_playout_volume(self, volume, legs=None):
+        for i in (range(self.n) if legs is None else legs):
+            self.lib.wap_set_playout_volume(self.handles[i], int(volume))
 
     def set_capture_output_used(self, used, legs=None):
         for i in (range(self.n) if legs is None else legs):
