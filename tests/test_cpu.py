@@ -345,7 +345,7 @@ def test_emu_libm_restatement(emu_lib):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import check_libm_restatement as chk
-    for which in (0, 1):
+    for which in (0, 1, 2):
         bad, tot = chk.mismatches(emu_lib, which, 60000)
         assert bad == 0, (which, bad, tot)
 

@@ -219,7 +219,7 @@ def test_libm_restatement_on_device(gpu_lib):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import check_libm_restatement as chk
-    for which in (0, 1):
+    for which in (0, 1, 2):
         bad, tot = chk.mismatches(gpu_lib, which, 100000)
         assert bad == 0, (which, bad, tot)
 
@@ -255,3 +255,30 @@ def test_level_adjustment_and_runtime_settings(gpu_lib, oracle):
     kw = dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=3.0, pre_amp=2.0, pre_gain=1.2, post_gain=1.1)
     for rate, max_rate in ((48000, 32000), (16000, 32000), (48000, 48000)):
         assert run_with_runtime_settings(gpu_lib, oracle, rate, 200, events, max_rate=max_rate, **kw) == 0
+
+
+def test_long_run_60s_float_identity(gpu_lib, oracle):
+    """One minute of AEC3 + NS at 16 kHz through the float interface (12 NS histogram periods, ERLE
+    and reverb estimators long past start-up, several render-silence gaps): still every float32 bit."""
+    from common import float_interface_max_diff
+    differing, worst = float_interface_max_diff(gpu_lib, oracle, 16000, 6000, leg=13, aec=True, ns=True, ns_level=1)
+    assert differing == 0, (differing, worst)
+
+
+@pytest.mark.parametrize("rate", [16000, 48000])
+def test_agc2_limiter_float_identity(gpu_lib, oracle, rate):
+    """The limiter's attack interpolation (a power of 8 the reference takes from libm) at float level."""
+    import wap_b200
+    x = loud_bursty_signal(rate, 600)
+    fl = rate // 100
+    eng = wap_b200.Engine(1, rate, lib=gpu_lib, aec=False, ns=False, agc2=True, agc2_fixed_gain_db=12.0)
+    ref = oracle.RefApm(aec=False, ns=False, agc2=True, agc2_fixed_gain_db=12.0)
+    differing = 0
+    for f in range(600):
+        c = (x[f * fl:(f + 1) * fl].astype(np.float32) / 32768.0).reshape(1, fl)
+        o = eng.process(None, c).reshape(-1)
+        ro, err = ref.tick_f32(rate, None, c.reshape(-1))
+        assert err == 0
+        differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
+    eng.close()
+    assert differing == 0

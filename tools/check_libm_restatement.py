@@ -19,18 +19,26 @@ def libm_reference(which, x):
     m.powf.argtypes = [C.c_float, C.c_float]
     m.tanhf.restype = C.c_float
     m.tanhf.argtypes = [C.c_float]
+    m.tanh.restype = C.c_double
+    m.tanh.argtypes = [C.c_double]
     if which == 0:
         return np.array([m.powf(2.0, float(v)) for v in x], np.float32)
-    return np.array([m.tanhf(float(v)) for v in x], np.float32)
+    if which == 1:
+        return np.array([m.tanhf(float(v)) for v in x], np.float32)
+    # the NS prior-model indicator: (float)(0.5 * (tanh((double)x) + 1)); the sum magnifies last-bit
+    # differences of tanh near -1
+    return np.array([np.float32(0.5 * (np.float64(m.tanh(float(v))) + 1.0)) for v in x], np.float32)
 
 
 def arguments(which, n, seed=7):
     rng = np.random.default_rng(seed + which)
     if which == 0:
         parts = [rng.uniform(-30, 30, n // 2), rng.uniform(-2, 2, n // 4), rng.uniform(-125, 125, n // 4)]
-    else:
+    elif which == 1:
         parts = [rng.uniform(-1.2, 1.2, n // 2), rng.uniform(-9, 9, n // 4), rng.uniform(-1e-3, 1e-3, n // 8),
                  rng.uniform(-30, 30, n // 8)]
+    else:
+        parts = [rng.uniform(-1.2, 1.2, n // 4), rng.uniform(-20, 0, n // 2), rng.uniform(-40, 40, n // 4)]
     return np.concatenate(parts).astype(np.float32)
 
 
@@ -52,6 +60,6 @@ if __name__ == "__main__":
     else:
         import build_emu
         lib = wap_b200.load(build_emu.build())
-    for which, name in ((0, "powf(2, p)"), (1, "tanhf")):
+    for which, name in ((0, "powf(2, p)"), (1, "tanhf"), (2, "tanh")):
         bad, tot = mismatches(lib, which, n)
         print("%-10s %d mismatches of %d" % (name, bad, tot))

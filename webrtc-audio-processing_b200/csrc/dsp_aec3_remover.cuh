@@ -670,7 +670,7 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
 WAP_DEV void gain_params(const ec3::Tuning& t, int k, float* enr_transparent, float* enr_suppress, float* emr_transparent) {
   float aa;
   if (k <= ec3::kLastLfBand) aa = 0.f;
-  else if (k < ec3::kFirstHfBand) aa = (k - ec3::kLastLfBand) / (float)(ec3::kFirstHfBand - ec3::kLastLfBand);
+  else if (k < ec3::kFirstHfBand) aa = fdiv((float)(k - ec3::kLastLfBand), (float)(ec3::kFirstHfBand - ec3::kLastLfBand));
   else aa = 1.f;
   *enr_transparent = (1 - aa) * t.lf_t + aa * t.hf_t;
   *enr_suppress = (1 - aa) * t.lf_s + aa * t.hf_s;

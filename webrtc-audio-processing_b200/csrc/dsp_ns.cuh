@@ -128,7 +128,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
     __syncwarp();
   }
   float signal_energy = sc.red[0];
-  signal_energy /= (float)kNsBins;
+  signal_energy = fdiv(signal_energy, (float)kNsBins);
   const float signal_spectral_sum = sc.red[1];
   const float noise_sum = sc.red[2];
   const float flat_log_sum = sc.red[3];
@@ -407,7 +407,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
       st.hist_diff[i] = 0;
     }
     hist_counter = 500;
-    energy_sum = energy_sum / 500.f;
+    energy_sum = fdiv(energy_sum, 500.f);
     diff_norm = 0.5f * (energy_sum + diff_norm);
     energy_sum = 0.f;
     if (lane == 0) {
@@ -436,11 +436,11 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   __syncwarp();
   {
     float width_prior = f_lrt < p_lrt ? 8.f : 4.f;
-    const float indicator0 = (float)(0.5f * (tanh((double)(width_prior * (f_lrt - p_lrt))) + 1.f));
+    const float indicator0 = (float)(0.5f * (libm_tanh((double)(width_prior * (f_lrt - p_lrt))) + 1.f));
     width_prior = f_flat > p_flat_thr ? 8.f : 4.f;
-    const float indicator1 = (float)(0.5f * (tanh((double)(1.f * width_prior * (p_flat_thr - f_flat))) + 1.f));
+    const float indicator1 = (float)(0.5f * (libm_tanh((double)(1.f * width_prior * (p_flat_thr - f_flat))) + 1.f));
     width_prior = f_diff < p_diff_thr ? 8.f : 4.f;
-    const float indicator2 = (float)(0.5f * (tanh((double)(width_prior * (f_diff - p_diff_thr))) + 1.f));
+    const float indicator2 = (float)(0.5f * (libm_tanh((double)(width_prior * (f_diff - p_diff_thr))) + 1.f));
     const float ind_prior = p_w_lrt * indicator0 + p_w_flat * indicator1 + p_w_diff * indicator2;
     prior_prob += 0.1f * (ind_prior - prior_prob);
     prior_prob = fmaxr(fminr(prior_prob, 1.f), 0.01f);

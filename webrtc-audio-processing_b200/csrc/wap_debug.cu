@@ -36,10 +36,13 @@ __global__ void k_dbg_fft256(float* data, int count, int inverse) {
   for (int i = lane; i < 256; i += 32) data[(size_t)idx * 256 + i] = a[i];
 }
 
-// which: 0 = powf(2, x), 1 = tanhf(x); in place.
+// which: 0 = powf(2, x), 1 = tanhf(x), 2 = (float)(0.5 * (tanh(x) + 1)) with the double tanh; in place.
 __global__ void k_dbg_libm(float* data, int count, int which) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) data[i] = which == 0 ? libm_pow2f(data[i]) : libm_tanhf(data[i]);
+  if (i >= count) return;
+  if (which == 3) data[i] = fdiv(data[i], 500.f);
+  else if (which == 2) data[i] = (float)(0.5f * (libm_tanh((double)data[i]) + 1.f));  // the NS prior-model indicators
+  else data[i] = which == 0 ? libm_pow2f(data[i]) : libm_tanhf(data[i]);
 }
 
 }  // namespace wap

@@ -31,6 +31,18 @@ extern __shared__ __align__(16) unsigned char wap_dyn_smem_raw[];
 
 namespace wap {
 
+// IEEE division for a divisor that is (or may become, after inlining) a compile-time constant:
+// with -ftz=true nvcc rewrites `x / c` into `x * (1 / c)` even under -prec-div=true, which is an
+// ulp off for most x.  __fdiv_rn is not rewritten.  (`tools/div_sites.sh` lists the sites: it
+// compares the number of div.rn in the PTX with and without -ftz.)
+WAP_DEV float fdiv(float a, float b) {
+#if defined(WAP_EMU)
+  return a / b;
+#else
+  return __fdiv_rn(a, b);
+#endif
+}
+
 // std::min / std::max semantics of the reference ((b < a) ? b : a etc.).
 WAP_DEV float fminr(float a, float b) { return (b < a) ? b : a; }
 WAP_DEV float fmaxr(float a, float b) { return (a < b) ? b : a; }

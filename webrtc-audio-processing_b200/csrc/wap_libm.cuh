@@ -11,8 +11,14 @@
 //               1.5*2^47 shift, 32-entry table of 2^(i/32), cubic in r, in double;
 //   tanhf       sysdeps/ieee754/flt-32/s_tanhf.c on top of s_expm1f.c (the fdlibm
 //               algorithms), in float.
-// Both restatements were checked against libm on 450 k / 340 k random arguments
-// (tools/check_libm_restatement.py) with zero mismatches.
+//   tanh        (double; the NS prior-model indicators call it on floats, speech_probability_
+//               estimator.cc:62-84, and add 1 to results near -1, which magnifies a last-bit
+//               difference 10^5-fold) sysdeps/ieee754/dbl-64/s_tanh.c on top of s_expm1.c.  On
+//               CPUs with FMA glibc 2.39 dispatches to a build of s_expm1.c with contraction
+//               enabled (sysdeps/x86_64/fpu/multiarch/s_expm1-fma.c); the fused operations below
+//               are the ones that build contracts.  Without them 3 results in 10^4 differ.
+// All restatements were checked against libm on several 100 k random arguments
+// (tools/check_libm_restatement.py) with zero mismatches, on the host and on the device.
 #pragma once
 
 #include "wap_dev.cuh"
@@ -130,6 +136,90 @@ WAP_DEV float libm_tanhf(float x) {
     }
   } else {
     z = 1.0f - 1.0e-30f;
+  }
+  return (jx & 0x80000000u) ? -z : z;
+}
+
+// expm1 (double) as the FMA build of glibc's s_expm1.c evaluates it; |x| < 700.
+WAP_DEV double libm_expm1(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+               invln2 = 1.44269504088896338700e+00;
+  const double Q1 = -3.33333333333331316428e-02, Q2 = 1.58730158725481460165e-03, Q3 = -7.93650757867487942473e-05,
+               Q4 = 4.00821782732936239552e-06, Q5 = -2.01099218183624371326e-07;
+  unsigned hx = (unsigned)((unsigned long long)__double_as_longlong(x) >> 32);
+  const unsigned xsb = hx & 0x80000000u;
+  hx &= 0x7fffffffu;
+  if (hx >= 0x4043687Au && xsb) return 1.0e-300 - 1.0;  // x <= -56 ln2
+  double c = 0.0;
+  int k = 0;
+  if (hx > 0x3fd62e42u) {        // |x| > 0.5 ln2
+    double hi, lo;
+    if (hx < 0x3FF0A2B2u) {      // |x| < 1.5 ln2
+      if (!xsb) { hi = x - ln2_hi; lo = ln2_lo; k = 1; }
+      else { hi = x + ln2_hi; lo = -ln2_lo; k = -1; }
+    } else {
+      k = (int)fma(invln2, x, xsb ? -0.5 : 0.5);
+      const double t = (double)k;
+      hi = fma(-t, ln2_hi, x);
+      lo = t * ln2_lo;
+    }
+    x = hi - lo;
+    c = (hi - x) - lo;
+  } else if (hx < 0x3c900000u) {  // |x| < 2^-54
+    return x;
+  }
+  const double hfx = 0.5 * x;
+  const double hxs = x * hfx;
+  const double R1 = fma(hxs, Q1, 1.0), h2 = hxs * hxs, R2 = fma(hxs, Q3, Q2), h4 = h2 * h2, R3 = fma(hxs, Q5, Q4);
+  const double r1 = fma(h4, R3, fma(h2, R2, R1));
+  double t = fma(-r1, hfx, 3.0);
+  double e = hxs * ((r1 - t) / fma(-x, t, 6.0));
+  if (k == 0) return x - fma(x, e, -hxs);
+  e = fma(x, e - c, -c);
+  e -= hxs;
+  if (k == -1) return fma(0.5, x - e, -0.5);
+  if (k == 1) {
+    if (x < -0.25) return -2.0 * (e - (x + 0.5));
+    return fma(2.0, x - e, 1.0);
+  }
+  double y;
+  if (k <= -2 || k > 56) {
+    y = 1.0 - (e - x);
+    y = __longlong_as_double(__double_as_longlong(y) + ((long long)k << 52));
+    return y - 1.0;
+  }
+  if (k < 20) {
+    t = __longlong_as_double((long long)(0x3ff00000u - (0x200000u >> k)) << 32);  // 1 - 2^-k
+    y = t - (e - x);
+    y = __longlong_as_double(__double_as_longlong(y) + ((long long)k << 52));
+  } else {
+    t = __longlong_as_double((long long)(0x3ff - k) << 52);  // 2^-k
+    y = x - (e + t);
+    y += 1.0;
+    y = __longlong_as_double(__double_as_longlong(y) + ((long long)k << 52));
+  }
+  return y;
+}
+
+// tanh (double, s_tanh.c), finite arguments.
+WAP_DEV double libm_tanh(double x) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+  const unsigned jx = (unsigned)(bits >> 32), lx = (unsigned)bits;
+  const unsigned ix = jx & 0x7fffffffu;
+  double z;
+  if (ix < 0x40360000u) {  // |x| < 22
+    if ((ix | lx) == 0) return x;
+    if (ix < 0x3c800000u) return x * (1.0 + x);  // |x| < 2^-55
+    const double ax = fabs(x);
+    if (ix >= 0x3ff00000u) {  // |x| >= 1
+      const double t = libm_expm1(2.0 * ax);
+      z = 1.0 - 2.0 / (t + 2.0);
+    } else {
+      const double t = libm_expm1(-2.0 * ax);
+      z = -t / (t + 2.0);
+    }
+  } else {
+    z = 1.0 - 1.0e-300;
   }
   return (jx & 0x80000000u) ? -z : z;
 }
