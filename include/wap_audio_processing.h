@@ -212,6 +212,13 @@ void* wap_engine_cuda_stream(WapEngine* engine);
 /* Number of kernel launches issued by the engine so far. */
 int64_t wap_engine_launch_count(const WapEngine* engine);
 
+/* Stream lifecycle: the complete state of a leg (device slabs + host-side settings) as an opaque
+ * blob, e.g. to move a live call to another engine or GPU.  The importing leg must belong to an
+ * engine of the same config class (else UnsupportedConfig); processing continues bit-identically. */
+size_t wap_stream_state_bytes(const WapAudioProcessing* handle);
+WapError wap_stream_export_state(WapAudioProcessing* handle, void* blob, size_t blob_bytes);
+WapError wap_stream_import_state(WapAudioProcessing* handle, const void* blob, size_t blob_bytes);
+
 const char* wap_version(void);
 
 #ifdef __cplusplus

@@ -228,3 +228,51 @@ def test_rates_and_unsupported_formats(emu_lib):
     x = np.zeros((1, 960), np.int16)
     assert eng.process(x, x).shape == (1, 960)
     eng.close()
+
+
+@pytest.mark.parametrize("rate,max_rate,kw", [
+    (16000, 32000, dict(aec=True, ns=True, ns_level=1)),
+    (48000, 32000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0, pre_gain=1.5, post_gain=0.8)),
+])
+def test_stream_state_export_import(emu_lib, oracle, rate, max_rate, kw):
+    """Stream lifecycle: a leg exported in the middle of a call and imported into a leg of another
+    engine continues bit-identically (output and statistics); a blob does not fit another config."""
+    import wap_b200
+    from common import synthetic_leg, synthetic_leg_48k
+    nf, cut = 70, 37
+    fl = rate // 100
+    far, near = synthetic_leg(4, nf) if rate == 16000 else synthetic_leg_48k(4, nf, 1.0, rate=rate)
+    ref_out, ref_stats, err = oracle.RefApm(max_rate=max_rate, **kw).run_i16(rate, far, near, stats_every=nf)
+    assert err == 0
+
+    def tick(eng, f, slot=0):
+        eng.set_stream_delay_ms(0)
+        r = np.zeros((eng.n, fl), np.int16); c = np.zeros((eng.n, fl), np.int16)
+        r[slot] = far[f * fl:(f + 1) * fl]; c[slot] = near[f * fl:(f + 1) * fl]
+        return eng.process(r, c)[slot]
+
+    a = wap_b200.Engine(1, rate, lib=emu_lib, max_rate=max_rate, **kw)
+    out = np.zeros(nf * fl, np.int16)
+    for f in range(cut):
+        out[f * fl:(f + 1) * fl] = tick(a, f)
+    a.set_playout_volume(120)           # a pending runtime setting travels with the leg
+    blob = a.export_state(0)
+    a.close()
+    b = wap_b200.Engine(3, rate, lib=emu_lib, max_rate=max_rate, **kw)   # another engine, another slot
+    b.import_state(blob, 2)
+    for f in range(cut, nf):
+        out[f * fl:(f + 1) * fl] = tick(b, f, slot=2)
+    st = b.stats(2)
+    ref2 = oracle.RefApm(max_rate=max_rate, **kw)
+    ro = np.zeros(nf * fl, np.int16)
+    for f in range(nf):
+        if f == cut:
+            ref2.set_playout_volume(120)
+        o, _, e2 = ref2.run_i16(rate, far[f * fl:(f + 1) * fl], near[f * fl:(f + 1) * fl])
+        ro[f * fl:(f + 1) * fl] = o
+    assert np.array_equal(out, ro)
+    assert abs(st.echo_return_loss_enhancement - float(ref2.stats()[3])) <= 1e-6
+    other = wap_b200.Engine(1, rate, lib=emu_lib, max_rate=max_rate, aec=True, ns=False)
+    with pytest.raises(RuntimeError):
+        other.import_state(blob, 0)
+    other.close(); b.close()

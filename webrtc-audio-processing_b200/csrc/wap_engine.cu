@@ -817,6 +817,118 @@ WapError wap_get_statistics(const WapAudioProcessing* hc, WapStats* out) {
   return WapError::None;
 }
 
+// ---- stream lifecycle: a leg's complete state as an opaque blob (move a call between engines / GPUs)
+namespace {
+struct BlobHeader {
+  uint32_t magic, version;
+  uint64_t total_bytes;
+  wap::EngineConfig cfg;  // the blob only fits an engine of the same config class
+  // host-side per-leg state
+  WapConfig config;
+  int32_t delay_ms, delay_set, capture_output_used, analog_level, playout_volume;
+  float pre_gain_target, post_gain_target, agc2_gain_factor;
+  uint8_t dirty[8];  // capture_output_used, pre, post, playout, agc2 gain, agc2 limiter reset
+  WapStats cached_stats;
+};
+constexpr uint32_t kBlobMagic = 0x57415042u;  // "WAPB"
+constexpr uint32_t kBlobVersion = 1;
+size_t blob_bytes(const WapEngine* e) {
+  size_t n = sizeof(BlobHeader) + sizeof(StreamState);
+  if (e->d_upper) n += sizeof(wap::UpperBandState);
+  if (e->d_rs) n += wap::kRsPerLeg * sizeof(wap::ResamplerState);
+  if (e->d_extra) n += sizeof(wap::ExtraChannelState);
+  return n;
+}
+}  // namespace
+
+size_t wap_stream_state_bytes(const WapAudioProcessing* h) {
+  return (h && h->engine && h->slot >= 0) ? blob_bytes(h->engine) : 0;
+}
+
+WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes) {
+  if (!h || !blob) return WapError::NullPointer;
+  if (!h->engine || h->slot < 0 || bytes < blob_bytes(h->engine)) return WapError::BadStreamParameter;
+  WapEngine* e = h->engine;
+  WAP_CUDA(cudaSetDevice(e->device));
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  BlobHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.magic = kBlobMagic;
+  hd.version = kBlobVersion;
+  hd.total_bytes = blob_bytes(e);
+  hd.cfg = e->cfg;
+  hd.config = h->config;
+  hd.delay_ms = e->leg_delay_ms[h->slot];
+  hd.delay_set = e->leg_delay_set[h->slot];
+  hd.capture_output_used = h->capture_output_used;
+  hd.analog_level = h->analog_level;
+  hd.playout_volume = h->playout_volume;
+  hd.pre_gain_target = h->pre_gain_target;
+  hd.post_gain_target = h->post_gain_target;
+  hd.agc2_gain_factor = h->agc2_gain_factor;
+  hd.dirty[0] = h->capture_output_used_dirty; hd.dirty[1] = h->pre_gain_dirty; hd.dirty[2] = h->post_gain_dirty;
+  hd.dirty[3] = h->playout_volume_dirty; hd.dirty[4] = h->agc2_gain_dirty; hd.dirty[5] = h->agc2_reset_limiter;
+  hd.cached_stats = h->cached_stats;
+  unsigned char* p = static_cast<unsigned char*>(blob);
+  memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  WAP_CUDA(cudaMemcpy(p, &e->d_states[h->slot], sizeof(StreamState), cudaMemcpyDeviceToHost));
+  p += sizeof(StreamState);
+  if (e->d_upper) {
+    WAP_CUDA(cudaMemcpy(p, &e->d_upper[h->slot], sizeof(wap::UpperBandState), cudaMemcpyDeviceToHost));
+    p += sizeof(wap::UpperBandState);
+  }
+  if (e->d_rs) {
+    WAP_CUDA(cudaMemcpy(p, &e->d_rs[(size_t)h->slot * wap::kRsPerLeg], wap::kRsPerLeg * sizeof(wap::ResamplerState), cudaMemcpyDeviceToHost));
+    p += wap::kRsPerLeg * sizeof(wap::ResamplerState);
+  }
+  if (e->d_extra) WAP_CUDA(cudaMemcpy(p, &e->d_extra[h->slot], sizeof(wap::ExtraChannelState), cudaMemcpyDeviceToHost));
+  return WapError::None;
+}
+
+WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t bytes) {
+  if (!h || !blob) return WapError::NullPointer;
+  if (!h->engine || h->slot < 0 || bytes < sizeof(BlobHeader)) return WapError::BadStreamParameter;
+  WapEngine* e = h->engine;
+  BlobHeader hd;
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kBlobMagic || hd.version != kBlobVersion || hd.total_bytes != blob_bytes(e) || bytes < hd.total_bytes ||
+      memcmp(&hd.cfg, &e->cfg, sizeof(e->cfg)) != 0)
+    return WapError::UnsupportedConfig;  // another config class (or library version)
+  WAP_CUDA(cudaSetDevice(e->device));
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  const unsigned char* p = static_cast<const unsigned char*>(blob) + sizeof(hd);
+  WAP_CUDA(cudaMemcpy(&e->d_states[h->slot], p, sizeof(StreamState), cudaMemcpyHostToDevice));
+  p += sizeof(StreamState);
+  if (e->d_upper) {
+    WAP_CUDA(cudaMemcpy(&e->d_upper[h->slot], p, sizeof(wap::UpperBandState), cudaMemcpyHostToDevice));
+    p += sizeof(wap::UpperBandState);
+  }
+  if (e->d_rs) {
+    WAP_CUDA(cudaMemcpy(&e->d_rs[(size_t)h->slot * wap::kRsPerLeg], p, wap::kRsPerLeg * sizeof(wap::ResamplerState), cudaMemcpyHostToDevice));
+    p += wap::kRsPerLeg * sizeof(wap::ResamplerState);
+  }
+  if (e->d_extra) WAP_CUDA(cudaMemcpy(&e->d_extra[h->slot], p, sizeof(wap::ExtraChannelState), cudaMemcpyHostToDevice));
+  e->dirty_legs -= (int)h->capture_output_used_dirty + (int)h->pre_gain_dirty + (int)h->post_gain_dirty +
+                   (int)h->playout_volume_dirty + (int)h->agc2_gain_dirty;
+  h->config = hd.config;
+  e->leg_delay_ms[h->slot] = hd.delay_ms;
+  e->leg_delay_set[h->slot] = (unsigned char)hd.delay_set;
+  h->stream_delay_ms = hd.delay_ms;
+  h->capture_output_used = hd.capture_output_used != 0;
+  h->analog_level = hd.analog_level;
+  h->playout_volume = hd.playout_volume;
+  h->pre_gain_target = hd.pre_gain_target;
+  h->post_gain_target = hd.post_gain_target;
+  h->agc2_gain_factor = hd.agc2_gain_factor;
+  h->capture_output_used_dirty = hd.dirty[0]; h->pre_gain_dirty = hd.dirty[1]; h->post_gain_dirty = hd.dirty[2];
+  h->playout_volume_dirty = hd.dirty[3]; h->agc2_gain_dirty = hd.dirty[4]; h->agc2_reset_limiter = hd.dirty[5];
+  e->dirty_legs += (int)h->capture_output_used_dirty + (int)h->pre_gain_dirty + (int)h->post_gain_dirty +
+                   (int)h->playout_volume_dirty + (int)h->agc2_gain_dirty;
+  h->cached_stats = hd.cached_stats;
+  return WapError::None;
+}
+
 // Test / tooling hook: raw copy of one leg's state slab (wap_state.h layout).
 int wapdbg_read_state(const WapAudioProcessing* h, void* out, size_t bytes) {
   if (!h || !h->engine || h->slot < 0 || bytes > sizeof(StreamState)) return -1;

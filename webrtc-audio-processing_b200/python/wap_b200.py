@@ -81,7 +81,7 @@ EXPORTS = [
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
     "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
-    "wap_engine_set_pipeline_chunks",
+    "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state",
 ]
 
 _libs = {}
@@ -131,6 +131,10 @@ def load(path=None):
     L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
     L.wap_engine_set_pipeline_chunks.argtypes = [vp, i32]
     L.wap_set_capture_pre_gain.argtypes = [vp, C.c_float]
+    L.wap_stream_state_bytes.restype = C.c_size_t
+    L.wap_stream_state_bytes.argtypes = [vp]
+    L.wap_stream_export_state.argtypes = [vp, vp, C.c_size_t]
+    L.wap_stream_import_state.argtypes = [vp, vp, C.c_size_t]
     L.wap_set_capture_post_gain.argtypes = [vp, C.c_float]
     L.wap_set_playout_volume.argtypes = [vp, C.c_int]
     L.wap_set_capture_fixed_post_gain.argtypes = [vp, C.c_float]
@@ -190,6 +194,19 @@ class Engine:
         err = self.lib.wap_engine_set_pipeline_chunks(self.h, int(chunks))
         if err:
             raise RuntimeError("wap_engine_set_pipeline_chunks -> WapError %d" % err)
+
+    def export_state(self, i=0):
+        n = self.lib.wap_stream_state_bytes(self.handles[i])
+        blob = np.zeros(n, np.uint8)
+        err = self.lib.wap_stream_export_state(self.handles[i], blob.ctypes.data_as(C.c_void_p), n)
+        if err:
+            raise RuntimeError("wap_stream_export_state: " + ERRORS.get(err, str(err)))
+        return blob
+
+    def import_state(self, blob, i=0):
+        err = self.lib.wap_stream_import_state(self.handles[i], blob.ctypes.data_as(C.c_void_p), blob.size)
+        if err:
+            raise RuntimeError("wap_stream_import_state: " + ERRORS.get(err, str(err)))
 
     def set_pre_gain(self, gain, legs=None):
         for i in (range(self.n) if legs is None else legs):
