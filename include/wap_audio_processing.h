@@ -219,6 +219,31 @@ size_t wap_stream_state_bytes(const WapAudioProcessing* handle);
 WapError wap_stream_export_state(WapAudioProcessing* handle, void* blob, size_t blob_bytes);
 WapError wap_stream_import_state(WapAudioProcessing* handle, const void* blob, size_t blob_bytes);
 
+/* Stage taps: internal signals of one leg as of the last processed 64-sample block / 10 ms frame,
+ * named after the reference's ApmDataDumper taps (modules/audio_processing/logging/
+ * apm_data_dumper.h; e.g. "aec3_erle" in aec3/subband_erle_estimator.cc).  Read-only snapshot of
+ * the leg's state slab; costs one small device->host copy. */
+typedef struct WapStageTaps {
+  float aec3_erle[65];                    /* "aec3_erle" */
+  float aec3_erle_onset_compensated[65];  /* "aec3_erle_onset_compensated" */
+  float aec3_erl[65];                     /* "aec3_erl" */
+  float aec3_erl_time_domain;             /* "aec3_erl_time_domain" */
+  float aec3_fullband_erle_log2;          /* "aec3_fullband_erle_log2" */
+  float aec3_suppressor_gain[65];         /* "aec3_suppressor_gain" */
+  float aec3_N2[65];                      /* "aec3_N2": comfort-noise spectrum */
+  float aec3_refined_gain_H_error[65];    /* "aec3_refined_gain_H_error" */
+  int32_t aec3_filter_delay;              /* "aec3_filter_delay": FilterAnalyzer::MinFilterDelayBlocks */
+  int32_t aec3_min_direct_path_filter_delay;  /* AecState::MinDirectPathFilterDelay, blocks */
+  int32_t aec3_render_delay_controller_buffer_delay; /* "aec3_render_delay_controller_buffer_delay", blocks (0: none) */
+  int32_t aec3_usable_linear_estimate, aec3_transparent_mode, aec3_initial_state;
+  int32_t aec3_echo_saturation, aec3_capture_saturation, aec3_dominant_nearend;
+  float ns_noise_spectrum[129];           /* NoiseEstimator::noise_spectrum_ */
+  float ns_filter[129];                   /* WienerFilter::filter_ */
+  float ns_speech_probability[129];       /* SpeechProbabilityEstimator::speech_probability_ */
+  float ns_prior_speech_probability;
+} WapStageTaps;
+WapError wap_stream_read_taps(WapAudioProcessing* handle, WapStageTaps* out);
+
 const char* wap_version(void);
 
 #ifdef __cplusplus

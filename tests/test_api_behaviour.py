@@ -3,12 +3,14 @@ error codes, delay clamp, mute / un-mute, single-leg entry points, int16 / float
 Mirrors the reference's APM API tests (tests/unit/audio_processing_unittest.cc,
 audio_processing_impl_unittest.cc) for the part of the surface the seam forwards."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
 from common import golden, synthetic_leg
 
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 TOL = 1e-4 * 32768
 
 
@@ -276,3 +278,45 @@ def test_stream_state_export_import(emu_lib, oracle, rate, max_rate, kw):
     with pytest.raises(RuntimeError):
         other.import_state(blob, 0)
     other.close(); b.close()
+
+
+def test_stage_taps_match_reference_dumps(emu_lib, tmp_path):
+    """wap_stream_read_taps against the reference's own ApmDataDumper output (the dump variant of the
+    compiled reference, -DWEBRTC_APM_DEBUG_DUMP=1, run in a helper process): the taps after the last
+    block equal the last records of the reference's tap files bit for bit."""
+    import glob
+    import subprocess
+    import sys
+    import wap_b200
+    nf, leg = 260, 6
+    dump_lib = os.path.join(ROOT, "oracle", "_ref", "libwap_ref_dump.so")
+    if not os.path.exists(dump_lib):
+        pytest.skip("dump variant of the oracle not built (python -c 'import __graft_entry__ as g; g.build()')")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dump_ref_taps.py"), str(tmp_path), str(nf), str(leg)],
+                   check=True)
+    far, near = synthetic_leg(leg, nf)
+    eng = wap_b200.Engine(1, 16000, lib=emu_lib, max_rate=32000, aec=True, ns=True, ns_level=1)
+    for f in range(nf):
+        eng.set_stream_delay_ms(0)
+        eng.process(far[f * 160:(f + 1) * 160].reshape(1, 160), near[f * 160:(f + 1) * 160].reshape(1, 160))
+    t = eng.taps(0)
+    eng.close()
+
+    def last(name, n, dtype):
+        files = sorted(glob.glob(os.path.join(str(tmp_path), name + "_[0-9]*-[0-9]*.dat")))
+        assert files, name
+        return np.fromfile(files[-1], dtype)[-n:]
+
+    for name in ("aec3_erle", "aec3_erle_onset_compensated", "aec3_erl", "aec3_suppressor_gain", "aec3_N2",
+                 "aec3_refined_gain_H_error"):
+        assert np.array_equal(np.array(getattr(t, name), np.float32), last(name, 65, np.float32)), name
+    assert t.aec3_erl_time_domain == last("aec3_erl_time_domain", 1, np.float32)[0]
+    assert t.aec3_fullband_erle_log2 == last("aec3_fullband_erle_log2", 1, np.float32)[0]
+    assert t.aec3_filter_delay == last("aec3_filter_delay", 1, np.int32)[0]
+    assert t.aec3_render_delay_controller_buffer_delay == last("aec3_render_delay_controller_buffer_delay", 1, np.int64)[0]
+    for name in ("aec3_usable_linear_estimate", "aec3_transparent_mode", "aec3_initial_state", "aec3_echo_saturation",
+                 "aec3_dominant_nearend"):   # bools are dumped as int16
+        assert getattr(t, name) == last(name, 1, np.int16)[0], name
+    assert t.aec3_capture_saturation == last("aec3_capture_saturation", 1, np.int32)[0]
+    assert np.all(np.array(t.ns_noise_spectrum) > 0) and 0.0 <= t.ns_prior_speech_probability <= 1.0
+    assert np.all((np.array(t.ns_filter) >= 0.0) & (np.array(t.ns_filter) <= 1.0))

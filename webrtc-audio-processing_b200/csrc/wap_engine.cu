@@ -929,6 +929,48 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   return WapError::None;
 }
 
+WapError wap_stream_read_taps(WapAudioProcessing* h, WapStageTaps* out) {
+  if (!h || !out) return WapError::NullPointer;
+  if (!h->engine || h->slot < 0) return WapError::BadStreamParameter;
+  WapEngine* e = h->engine;
+  WAP_CUDA(cudaSetDevice(e->device));
+  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  memset(out, 0, sizeof(*out));
+  const StreamState* slab = &e->d_states[h->slot];
+  auto fetch = [&](void* dst, const void* src, size_t n) {
+    return cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+  };
+  bool ok = true;
+  if (e->cfg.aec_enabled) {
+    wap::Aec3Scalars s;
+    ok = ok && fetch(&s, &slab->aec.s, sizeof(s)) && fetch(out->aec3_erle, slab->aec.erle, sizeof(out->aec3_erle)) &&
+         fetch(out->aec3_erle_onset_compensated, slab->aec.erle_onset_comp, sizeof(out->aec3_erle)) &&
+         fetch(out->aec3_erl, slab->aec.erl, sizeof(out->aec3_erl)) &&
+         fetch(out->aec3_suppressor_gain, slab->aec.last_gain, sizeof(out->aec3_suppressor_gain)) &&  // G^2, see below
+         fetch(out->aec3_N2, slab->aec.cng_N2, sizeof(out->aec3_N2)) &&
+         fetch(out->aec3_refined_gain_H_error, slab->aec.H_error, sizeof(out->aec3_refined_gain_H_error));
+    for (float& g : out->aec3_suppressor_gain) g = sqrtf(g);  // the reference dumps the amplitude gain
+    out->aec3_erl_time_domain = s.erl_time_domain;
+    out->aec3_fullband_erle_log2 = s.fb_erle_time_domain_log2;
+    out->aec3_filter_delay = s.fa_filter_delay_blocks;  // one capture channel: the minimum is the value
+    out->aec3_min_direct_path_filter_delay = s.fd_min_filter_delay;
+    out->aec3_render_delay_controller_buffer_delay = s.ctl_has_delay ? s.ctl_delay : 0;
+    out->aec3_usable_linear_estimate = s.fq_usable;
+    out->aec3_transparent_mode = s.tm_active;
+    out->aec3_initial_state = s.init_state;
+    out->aec3_echo_saturation = s.saturated_echo;
+    out->aec3_capture_saturation = s.capture_signal_saturation;
+    out->aec3_dominant_nearend = s.dn_nearend_state;
+  }
+  if (e->cfg.ns_enabled) {
+    ok = ok && fetch(out->ns_noise_spectrum, slab->ns.noise, sizeof(out->ns_noise_spectrum)) &&
+         fetch(out->ns_filter, slab->ns.wiener, sizeof(out->ns_filter)) &&
+         fetch(out->ns_speech_probability, slab->ns.speech_prob, sizeof(out->ns_speech_probability)) &&
+         fetch(&out->ns_prior_speech_probability, &slab->ns.prior_speech_prob, sizeof(float));
+  }
+  return ok ? WapError::None : WapError::Internal;
+}
+
 // Test / tooling hook: raw copy of one leg's state slab (wap_state.h layout).
 int wapdbg_read_state(const WapAudioProcessing* h, void* out, size_t bytes) {
   if (!h || !h->engine || h->slot < 0 || bytes > sizeof(StreamState)) return -1;

@@ -81,7 +81,7 @@ EXPORTS = [
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
     "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
-    "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state",
+    "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state", "wap_stream_read_taps",
 ]
 
 _libs = {}
@@ -170,6 +170,20 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class WapStageTaps(C.Structure):
+    _fields_ = [("aec3_erle", C.c_float * 65), ("aec3_erle_onset_compensated", C.c_float * 65),
+                ("aec3_erl", C.c_float * 65), ("aec3_erl_time_domain", C.c_float),
+                ("aec3_fullband_erle_log2", C.c_float), ("aec3_suppressor_gain", C.c_float * 65),
+                ("aec3_N2", C.c_float * 65), ("aec3_refined_gain_H_error", C.c_float * 65),
+                ("aec3_filter_delay", C.c_int32), ("aec3_min_direct_path_filter_delay", C.c_int32),
+                ("aec3_render_delay_controller_buffer_delay", C.c_int32),
+                ("aec3_usable_linear_estimate", C.c_int32), ("aec3_transparent_mode", C.c_int32),
+                ("aec3_initial_state", C.c_int32), ("aec3_echo_saturation", C.c_int32),
+                ("aec3_capture_saturation", C.c_int32), ("aec3_dominant_nearend", C.c_int32),
+                ("ns_noise_spectrum", C.c_float * 129), ("ns_filter", C.c_float * 129),
+                ("ns_speech_probability", C.c_float * 129), ("ns_prior_speech_probability", C.c_float)]
+
+
 class Engine:
     """Batched engine: `n` call legs of one config class on one GPU."""
 
@@ -194,6 +208,13 @@ class Engine:
         err = self.lib.wap_engine_set_pipeline_chunks(self.h, int(chunks))
         if err:
             raise RuntimeError("wap_engine_set_pipeline_chunks -> WapError %d" % err)
+
+    def taps(self, i=0):
+        t = WapStageTaps()
+        err = self.lib.wap_stream_read_taps(self.handles[i], C.byref(t))
+        if err:
+            raise RuntimeError("wap_stream_read_taps: " + ERRORS.get(err, str(err)))
+        return t
 
     def export_state(self, i=0):
         n = self.lib.wap_stream_state_bytes(self.handles[i])
