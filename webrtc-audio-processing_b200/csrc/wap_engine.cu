@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, 
 #ifndef WAP_ECHO_MINBLOCKS
 #define WAP_ECHO_MINBLOCKS 4
 #endif
+template <bool kMono16k>
 __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, in
 #endif
   float* scratch = sm + scratch_off;
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
-    echo_stream_tick(a, idx, scratch);
+    echo_stream_tick<kMono16k>(a, idx, scratch);
     __syncwarp();
   }
 }
@@ -148,6 +149,7 @@ struct WapEngine {
   int delay_scratch_floats = 0;
   bool is_default = false;
   int sm_count = 148;
+  bool mono16k_class = false;  // served by the specialised k_echo<true> instance
   // resampled engines (API rate != processing rate)
   wap::ResamplerState* d_rs = nullptr;   // [capacity][kRsPerLeg]
   float* d_rs_kernels = nullptr;         // in | out tables
@@ -394,7 +396,8 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   }
   if (timing) cudaEventRecord(e->ev[2], e->stream);
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
-  WAP_LAUNCH(wap::k_echo, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  if (e->mono16k_class) WAP_LAUNCH(wap::k_echo<true>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  else WAP_LAUNCH(wap::k_echo<false>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
   if (e->d_upper && e->cfg.num_bands == 3 && d_capture) {  // PostFilter: 48 kHz only (post_filter.cc:44-52)
     WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
@@ -482,6 +485,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->cfg = cfg;
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
   e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
+  e->mono16k_class = cfg.num_bands == 1 && !cfg.resample && !cfg.agc2_enabled && !cfg.levels_enabled && cfg.channels == 1;
   e->delay_scratch_floats = wap::delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&
@@ -525,7 +529,8 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
   const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
   if (ok && smem_e > 48 * 1024)
-    ok = cudaFuncSetAttribute(wap::k_echo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
+    ok = cudaFuncSetAttribute(wap::k_echo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
+         cudaFuncSetAttribute(wap::k_echo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
   if (ok && smem_d > 48 * 1024)
     ok = cudaFuncSetAttribute(wap::k_delay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d) == cudaSuccess;
   if (!ok) {
