@@ -194,27 +194,30 @@ WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* ban
   const int final_blocks_read = sc.s.blocks_read, final_spectra_read = sc.s.spectra_read;
   __syncwarp();
   // BlockFramer per band: the three framers fill in lock-step, so the upper bands work on a
-  // copy of the band-0 fill level.
-  for (int sub = 0; sub < 2; ++sub) {
-    aec3_echo_block(a, cfg, sc, ts, sub, up);
-    const int len = sc.s.output_framer_len;
-    __syncwarp();
-    if (up) {
-      int l1 = len, l2 = len;
-      framer_insert_and_extract_local(up->output_framer_hi[0], l1, sc.x, band0 + kFrame + sub * kSubFrame);
-      framer_insert_and_extract_local(up->output_framer_hi[1], l2, sc.rm.x_aligned, band0 + 2 * kFrame + sub * kSubFrame);
-    }
-    framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, band0 + sub * kSubFrame);
-  }
-  if (ts.n_capture_blocks == 3) {
-    aec3_echo_block(a, cfg, sc, ts, 2, up);
-    if (up) {
-      for (int i = lane_id(); i < kBlock; i += 32) {
-        up->output_framer_hi[0][i] = sc.x[i];
-        up->output_framer_hi[1][i] = sc.rm.x_aligned[i];
+  // copy of the band-0 fill level.  Blocks 0 and 1 each complete a sub-frame
+  // (InsertBlockAndExtractSubFrame), a third block is only buffered (InsertBlock).  One real loop:
+  // a single copy of the block code in the kernel instead of three.
+  const int nb = ts.n_capture_blocks == 3 ? 3 : 2;
+#pragma unroll 1
+  for (int b = 0; b < nb; ++b) {
+    aec3_echo_block(a, cfg, sc, ts, b, up);
+    if (b < 2) {
+      const int len = sc.s.output_framer_len;
+      __syncwarp();
+      if (up) {
+        framer_insert_and_extract_local(up->output_framer_hi[0], len, sc.x, band0 + kFrame + b * kSubFrame);
+        framer_insert_and_extract_local(up->output_framer_hi[1], len, sc.rm.x_aligned, band0 + 2 * kFrame + b * kSubFrame);
       }
+      framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, band0 + b * kSubFrame);
+    } else {
+      if (up) {
+        for (int i = lane_id(); i < kBlock; i += 32) {
+          up->output_framer_hi[0][i] = sc.x[i];
+          up->output_framer_hi[1][i] = sc.rm.x_aligned[i];
+        }
+      }
+      framer_insert(a.output_framer, &sc.s.output_framer_len, sc.y);
     }
-    framer_insert(a.output_framer, &sc.s.output_framer_len, sc.y);
   }
   __syncwarp();
   // ApmStatsReporter::UpdateStatistics (audio_processing_impl.cc:2322-2328): a
