@@ -179,13 +179,23 @@ WAP_DEV void power_spectrum(const float* re, const float* im, float* out) {
 }
 
 // Two 128-point transforms side by side: lanes 0-15 on fftA, lanes 16-31 on fftB.
-WAP_DEV void fft_pair(AecScratch& sc, bool inverse, bool second_on) {
+// The transforms are leaf routines of ~650 instructions called from a dozen places per block: one
+// shared copy of each direction keeps the kernel's instruction footprint small.
+WAP_DEV_NOINLINE void fft_pair_forward(float* fftA, float* fftB, bool second_on) {
   const int lane = lane_id();
-  float* a = (lane < 16) ? sc.fftA : sc.fftB;
-  const bool on = (lane < 16) || second_on;
+  float* a = (lane < 16) ? fftA : fftB;
   __syncwarp();
-  if (inverse) fft128_inverse(a, lane & 15, on);
-  else fft128_forward(a, lane & 15, on);
+  fft128_forward(a, lane & 15, (lane < 16) || second_on);
+}
+WAP_DEV_NOINLINE void fft_pair_inverse(float* fftA, float* fftB, bool second_on) {
+  const int lane = lane_id();
+  float* a = (lane < 16) ? fftA : fftB;
+  __syncwarp();
+  fft128_inverse(a, lane & 15, (lane < 16) || second_on);
+}
+WAP_DEV void fft_pair(AecScratch& sc, bool inverse, bool second_on) {
+  if (inverse) fft_pair_inverse(sc.fftA, sc.fftB, second_on);
+  else fft_pair_forward(sc.fftA, sc.fftB, second_on);
 }
 
 // FastApproxLog2f (aec3_common.cc:37-52)

@@ -23,6 +23,9 @@ struct NsScratch {
   float red[32];             // reduction exchange
 };
 
+// One shared copy of the forward 256-point transform for its two call sites (Analyze, Process).
+WAP_DEV_NOINLINE void ns_fft256_forward(float* buf) { fft256_forward(buf, lane_id()); }
+
 // ---- ns/fast_math.cc:25-84
 WAP_DEV float ns_fast_log2(float in) {
   float out = (float)__float_as_uint(in);
@@ -101,7 +104,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   if (lane == 0) st.num_analyzed_frames = naf;
 
   ns_form_windowed_frame(frame, st.analyze_mem, sc.buf);
-  fft256_forward(sc.buf, lane);
+  ns_fft256_forward(sc.buf);
   ns_magnitude(sc.buf, sc.spec);
 
   // signal_energy, signal_spectral_sum, conservative-noise average, and the
@@ -499,7 +502,7 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   // energies_before_filtering: serial sum over the 256 windowed samples.
   const float energy_before = serial_sum_sq_v4(sc.buf, 256);
   __syncwarp();
-  fft256_forward(sc.buf, lane);
+  ns_fft256_forward(sc.buf);
   ns_magnitude(sc.buf, sc.spec);
 
   // ---- WienerFilter::Update (wiener_filter.cc:33-84)

@@ -18,11 +18,14 @@
 // g++ build for the test-only emulator (tests/emu/cuda_emu.h is force-included).
 #define WAP_DEVCONST static const
 #define WAP_DEV static inline
+#define WAP_DEV_NOINLINE static __attribute__((noinline))
 #define WAP_DYN_SMEM() (emu::smem_ptr())
 #else
 #include <cuda_runtime.h>
 #define WAP_DEVCONST static __device__ const
 #define WAP_DEV static __device__ __forceinline__
+// one shared copy of a large leaf routine instead of one per call site (instruction-cache footprint)
+#define WAP_DEV_NOINLINE static __device__ __noinline__
 #define WAP_DYN_SMEM() (wap_dyn_smem_raw)
 extern __shared__ __align__(16) unsigned char wap_dyn_smem_raw[];
 #endif
