@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Attribute the executed warp instructions of k_tick to source lines.
-usage: tools/ncu_lines.py <report.ncu-rep> [top_n] [kernel] [profiled .so]
+usage: tools/ncu_lines.py <report.ncu-rep> [top_n] [kernel] [profiled .so] [mangled-name substring]
 Joins `ncu --page source --print-source sass --csv` (per-SASS-instruction counters) with the line
 table of the cubin inside libwap_b200.so (nvdisasm -g).  The .so must be the one that was profiled."""
 import csv, io, os, re, subprocess, sys, tempfile, collections
@@ -10,6 +10,8 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 kernel = sys.argv[3] if len(sys.argv) > 3 else "k_echo"
 so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "webrtc-audio-processing_b200", "libwap_b200.so")
+# substring of the MANGLED name selecting the function in the cubin (template instances: k_echoILb1)
+mangled = sys.argv[5] if len(sys.argv) > 5 else kernel
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)],
                cwd=tmp, capture_output=True)
@@ -20,7 +22,7 @@ cur = None
 inside = False
 for l in dis.splitlines():
     if l.startswith(".text."):
-        inside = kernel in l
+        inside = mangled in l
         continue
     if not inside:
         continue

@@ -17,7 +17,7 @@ ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("d
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = {}
 for r in rows[2:]:
-    name = r[ki].split("(")[0].replace("wap::", "")
+    name = r[ki].split("(")[0].replace("wap::", "").replace("void ", "").split("<")[0].strip()
     b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
     acc.setdefault(name, []).append(b)
 res = {}
