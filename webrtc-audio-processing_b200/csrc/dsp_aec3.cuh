@@ -70,6 +70,7 @@ WAP_DEV void framer_insert_and_extract_local(float* buffer, int n, const float* 
 }
 // BlockFramer::InsertBlock
 WAP_DEV void framer_insert(float* buffer, int* len, const float* block) {
+  #pragma unroll
   for (int i = lane_id(); i < kBlock; i += 32) buffer[i] = block[i];
   __syncwarp();
   if (lane_id() == 0) *len = kBlock;
@@ -147,10 +148,12 @@ WAP_DEV void aec3_echo_render(Aec3State& a, const TickScratch& ts, AecScratch& s
   const int lane = lane_id();
   for (int r = 0; r < ts.n_render_blocks; ++r) {
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) sc.x[i] = ts.render_blocks[r][i];
     aec3_render_insert_vector(a, sc, ts.rins[r]);
     if (up) {  // bands 1-2 of the block ring
       const int bw = ts.rins[r].blocks_write;
+      #pragma unroll
       for (int i = lane; i < 2 * kBlock; i += 32) (&up->blocks_hi[bw][0][0])[i] = (&up->render_blocks_hi[r][0][0])[i];
     }
   }
@@ -162,10 +165,12 @@ WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& 
                              UpperBandState* up) {
   const int lane = lane_id();
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) sc.y[i] = ts.capture_blocks[b][i];
   const CaptureBlockRec& rec = ts.crec[b];
   if (!rec.process) {
     if (up)
+      #pragma unroll
       for (int i = lane; i < kBlock; i += 32) {
         sc.x[i] = up->capture_blocks_hi[b][0][i];
         sc.rm.x_aligned[i] = up->capture_blocks_hi[b][1][i];
@@ -211,6 +216,7 @@ WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* ban
       framer_insert_and_extract(a.output_framer, &sc.s.output_framer_len, sc.y, band0 + b * kSubFrame);
     } else {
       if (up) {
+        #pragma unroll
         for (int i = lane_id(); i < kBlock; i += 32) {
           up->output_framer_hi[0][i] = sc.x[i];
           up->output_framer_hi[1][i] = sc.rm.x_aligned[i];

@@ -42,6 +42,7 @@ WAP_DEV float chain_sum(const float* p, int from, int to) {
 // ---- ErleEstimator::Reset / FullBandErleEstimator::Reset / SubbandErleEstimator::Reset
 WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
   const int lane = lane_id();
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     a.erle[k] = ec3::kErleMin;
     a.erle_onset_comp[k] = ec3::kErleMin;
@@ -205,6 +206,7 @@ WAP_DEV void filter_analyzer_update(Aec3State& a, AecScratch& sc) {
   __syncwarp();
   if (s.cfd_significant_peak) {
     const float* xb = a.blocks[ring_off(s.blocks_read, -delay_blocks, kRingBlocks)];
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) r.x_aligned[i] = xb[i];
     __syncwarp();
     const float x_energy = energy_serial(r.x_aligned, kBlock);
@@ -267,6 +269,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   // aligned render block, render counters
   {
     const float* xb = a.blocks[ring_off(s.blocks_read, -delay, kRingBlocks)];
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) r.x_aligned[i] = xb[i];
   }
   __syncwarp();
@@ -275,6 +278,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   const bool saturated_capture = s.capture_signal_saturation != 0;
   const bool usable_linear_before = s.fq_usable != 0;
   float max_sample_l = 0.f;
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) max_sample_l = fmaxf(max_sample_l, fabsf(r.x_aligned[i]));
   const float max_sample = warp_max(max_sample_l);
   __syncwarp();
@@ -286,6 +290,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   // ComputeAvgRenderReverb: r.v1 = avg_render_spectrum_with_reverb, r.v2 = X2 at the delay.
   const int idx_at_delay = ring_off(s.spectra_read, delay, kRingBlocks);
   const int idx_past = ring_inc(idx_at_delay, kRingBlocks);
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * ec3::kDefaultLen;
     a.avg_render_reverb[k] = rev;
@@ -313,6 +318,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     const bool restart = converged && s.erle_num_points == 6;
     const int num_points = converged ? (restart ? 1 : s.erle_num_points + 1) : s.erle_num_points;
     const bool update_bands = converged && num_points == 6;
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       float accY = a.accum_Y2[k], accE = a.accum_E2[k];
       int low = a.accum_low_render[k];
@@ -515,6 +521,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     const float average_decay = direct_path_energy == 0.f ? 0.f : tail_energy / direct_path_energy;
     const float smoothing = 0.2f * quality;
     const float avg = s.reverb_average_decay + smoothing * (average_decay - s.reverb_average_decay);
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) r.v3[k] = fmaxr(tail[k], direct[k] * avg);
     __syncwarp();
     if (lane == 0) {
@@ -525,6 +532,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
       }
     }
     __syncwarp();
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) a.tail_response[k] = r.v3[k];
   }
   __syncwarp();
@@ -545,6 +553,7 @@ WAP_DEV void cng_compute(Aec3State& a, const EngineConfig& cfg, AecScratch& sc, 
   const bool has_initial = s.cng_has_initial != 0;
   const bool drop_initial = !saturated_capture && has_initial && counter + 1 == 1000;
   const bool use_initial = has_initial && !drop_initial;
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     float N2 = a.cng_N2[k], N2i = a.cng_N2_initial[k];
     if (!saturated_capture) {
@@ -612,6 +621,7 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   const float* erle = dominant_nearend ? a.erle : a.erle_onset_comp;
   const int w0 = ring_off(s.spectra_read, imax(0, delay - 1), kRingBlocks);
   const int wn = delay + 1 - imax(0, delay - 1) + 1;  // spectra in the window
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     // UpdateRenderNoisePower
     float floor = a.X2_noise_floor[k];
@@ -727,6 +737,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   const float min_echo_power = low_noise_render ? ec3::kLowRenderLimit : ec3::kNormalRenderLimit;
   const int mem_index = s.sg_nearend_mem_index;
   // LowerBandGain
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     const float last_gain = a.last_gain[k];
     const float max_gain = fminr(fmaxr(last_gain * tun.max_inc, ec3::kFloorFirstIncrease), 1.f);
@@ -782,6 +793,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     const float min_upper_gain = fminr(1.f, r.gain[ec3::kLimitingGainBand]);
     const float g63 = limit_hf ? fminr(r.gain[63], min_upper_gain) : r.gain[63];
     __syncwarp();
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       float g = r.gain[k];
       if (k <= 1) g = g12;
@@ -848,6 +860,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   // x = render_buffer->GetBlock(0)
   {
     const float* xb = a.blocks[s.blocks_read];
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) sc.x[i] = xb[i];
   }
   if (lane == 0) s.capture_signal_saturation = capture_signal_saturation;
@@ -896,6 +909,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     }
     const float* from = s.er_refined_last_selected ? r.e_ref : r.e_coa;
     const float* to = use_refined_output ? r.e_ref : r.e_coa;
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) {
       float o = to[i];
       if (from != to && i < 30) {  // SignalTransition
@@ -908,6 +922,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     if (lane == 0) s.er_refined_last_selected = use_refined_output;
   }
   // WindowedPaddedFft of y and e (sqrt-Hanning), spectra.
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) {
     sc.fftA[i] = a.y_old[i] * kSqrtHanning128[i];
     sc.fftA[kBlock + i] = sc.y[i] * kSqrtHanning128[kBlock + i];
@@ -920,6 +935,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   packed_to_reim(sc.fftA, r.Y_re, r.Y_im);
   packed_to_reim(sc.fftB, r.E_re, r.E_im);
   __syncwarp();
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     const float dr = r.Y_re[k] - r.E_re[k], di = r.Y_im[k] - r.E_im[k];
     r.S2_lin[k] = dr * dr + di * di;  // LinearEchoPower
@@ -938,6 +954,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     residual_echo_estimate(a, sc);
     const bool usable = s.fq_usable != 0;
     if (usable) {
+      #pragma unroll
       for (int k = lane; k < kBins; k += 32) r.E2[k] = fminr(r.E2[k], r.Y2[k]);
       __syncwarp();
     }
@@ -949,6 +966,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     // SuppressionFilter::ApplyGain
     const float* Yf_re = usable ? r.E_re : r.Y_re;
     const float* Yf_im = usable ? r.E_im : r.Y_im;
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       const float g = r.gain[k];
       const float noise_gain = sqrtf(1.f - g * g);
@@ -968,6 +986,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     }
     fft_pair(sc, true, up != nullptr);
     constexpr float kIfftNormalization = 2.f / 128;
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) {
       float e0 = a.e_output_old[i] * kSqrtHanning128[kBlock + i];
       e0 += sc.fftA[i] * kSqrtHanning128[i];
@@ -981,6 +1000,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
       const float noise_scaling = 0.4f * sqrtf(1.f - high_bands_gain * high_bands_gain);
       const float ngain = noise_scaling * kIfftNormalization;
       __syncwarp();
+      #pragma unroll
       for (int i = lane; i < kBlock; i += 32) {
         float e1 = up->capture_blocks_hi[b][0][i] * high_bands_gain;
         e1 += sc.fftB[i] * ngain;
@@ -994,6 +1014,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
     }
   } else if (up) {
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) {
       sc.x[i] = up->capture_blocks_hi[b][0][i];
       r.x_aligned[i] = up->capture_blocks_hi[b][1][i];

@@ -114,12 +114,14 @@ WAP_DEV void aec3_render_insert_vector(Aec3State& a, AecScratch& sc, const Rende
   const int lane = lane_id();
   const int previous_write = rec.previous_write, bw = rec.blocks_write, sw = rec.spectra_write;
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) {
     a.blocks[bw][i] = sc.x[i];
     sc.fftA[i] = a.blocks[previous_write][i];
     sc.fftA[kBlock + i] = sc.x[i];
   }
   fft_pair(sc, false, false);
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     float re, im;
     if (k == 0) { re = sc.fftA[0]; im = 0.f; }

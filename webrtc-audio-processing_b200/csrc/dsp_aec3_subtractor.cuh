@@ -60,6 +60,7 @@ WAP_DEV void subtractor_handle_echo_path_change(Aec3State& a, AecScratch& sc, co
     __syncwarp();
     fir_zero_partitions(a.Hr_re, a.Hr_im, s.fr_current_size, kMaxPartitions);
     fir_zero_partitions(a.Hc_re, a.Hc_im, s.fc_current_size, kMaxPartitions);
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) a.H_error[k] = 10000.f;
     __syncwarp();
     if (lane == 0) {
@@ -131,8 +132,10 @@ WAP_DEV void render_signal_analyzer_update(Aec3State& a, AecScratch& sc, int del
   const float* X2_latest = a.spectra[s.spectra_read];
   const int peak_bin = warp_argmax_first(X2_latest, kBins);
   float max_abs_l = 0.f;
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) max_abs_l = fmaxf(max_abs_l, fabsf(sc.x[i]));
   if (x_band1)
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) max_abs_l = fmaxf(max_abs_l, fabsf(x_band1[i]));
   const float max_abs = warp_max(max_abs_l);
   if (lane == 0) {
@@ -158,6 +161,7 @@ WAP_DEV bool render_signal_analyzer_mask(const Aec3State& a, float* mask) {
   const int lane = lane_id();
   const int* c = a.narrow_band_counters;
   int poor = 0;
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     bool m = false;
     if (k <= 1 && c[0] > 5) m = true;
@@ -258,6 +262,7 @@ WAP_DEV void fir_filter_both(const Aec3State& a, AecScratch& sc, int P_r, int P_
 // PredictionError (subtractor.cc:49-65) from the inverse transform in `buf`.
 WAP_DEV void prediction_error(const float* buf, const float* y, float* e_out, float* s_out) {
   constexpr float kScale = 1.0f / 64;
+  #pragma unroll
   for (int i = lane_id(); i < kBlock; i += 32) {
     const float t = buf[kBlock + i];
     e_out[i] = y[i] - t * kScale;
@@ -374,6 +379,7 @@ WAP_DEV void fir_constrain_pair(AecScratch& sc, float* Hr_re_p, float* Hr_im_p, 
   if (second) reim_to_packed(Hc_re_p, Hc_im_p, sc.fftB);
   fft_pair(sc, true, second);
   constexpr float kScale = 1.0f / 64;
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) {
     const float v = sc.fftA[i] * kScale;
     sc.fftA[i] = v;
@@ -396,6 +402,7 @@ WAP_DEV void fir_constrain(AecScratch& sc, float* H_re_p, float* H_im_p) {
   reim_to_packed(H_re_p, H_im_p, sc.fftA);
   fft_pair(sc, true, false);
   constexpr float kScale = 1.0f / 64;
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) {
     sc.fftA[i] = sc.fftA[i] * kScale;
     sc.fftA[kBlock + i] = 0.f;
@@ -407,6 +414,7 @@ WAP_DEV void fir_constrain(AecScratch& sc, float* H_re_p, float* H_im_p) {
 
 // Aec3Fft::ZeroPaddedFft(x, kHanning) into the packed buffer `buf` (not transformed yet).
 WAP_DEV void stage_zero_padded_hanning(const float* x, float* buf) {
+  #pragma unroll
   for (int i = lane_id(); i < kBlock; i += 32) {
     buf[i] = 0.f;
     buf[kBlock + i] = x[i] * kHanning64[i];
@@ -511,6 +519,7 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
       (&a.Hr_im[0][0])[i] *= scale;
     }
     for (int i = lane; i < s.h_time_size * kBlock; i += 32) a.h_time[i] *= scale;
+    #pragma unroll
     for (int i = lane; i < kBlock; i += 32) {  // ScaleFilterOutput
       r.s_ref[i] *= scale;
       r.e_ref[i] = sc.y[i] - r.s_ref[i];
@@ -573,6 +582,7 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
     const float* Ecx_re = coarse_ok ? r.Ec_re : r.Er_re;
     const float* Ecx_im = coarse_ok ? r.Ec_im : r.Er_im;
     const int H2_size = s.H2_size;
+    #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       const bool masked = r.v0[k] != 0.f;
       if (!refined_filters_adjusted) {
@@ -648,6 +658,7 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
     fir_constrain(sc, a.Hc_re[pc], a.Hc_im[pc]);
   }
   // ComputeFrequencyResponse of the partition Constrain() rewrote.
+  #pragma unroll
   for (int k = lane; k < kBins; k += 32) a.H2[pr][k] = h2_bin(a.Hr_re[pr][k], a.Hr_im[pr][k], k);
   if (lane == 0) {
     s.h_time_size = P_r2;
@@ -656,6 +667,7 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
     s.fc_partition_to_constrain = pc < (P_c2 - 1) ? pc + 1 : 0;
   }
   // e_refined clamp (subtractor.cc:333-334)
+  #pragma unroll
   for (int i = lane; i < kBlock; i += 32) r.e_ref[i] = clampr(r.e_ref[i], -32768.f, 32767.f);
   __syncwarp();
 }

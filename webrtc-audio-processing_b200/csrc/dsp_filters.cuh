@@ -250,6 +250,7 @@ WAP_DEV void two_band_analysis(const float* full, float* bands, float* tmp, floa
   if (lane == 0) qmf_allpass_branch(full + 1, 2, kFrame, kQmfAllPass1, state, tmp);
   if (lane == 1) qmf_allpass_branch(full, 2, kFrame, kQmfAllPass2, state + kQmfStateFloats, tmp + kFrame);
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kFrame; i += 32) {
     const float f1 = tmp[i], f2 = tmp[kFrame + i];
     bands[i] = (f1 + f2) * 0.5f;
@@ -262,6 +263,7 @@ WAP_DEV void two_band_analysis(const float* full, float* bands, float* tmp, floa
 WAP_DEV void two_band_synthesis(const float* bands, float* full, float* tmp, float* state) {
   const int lane = lane_id();
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kFrame; i += 32) {
     const float lo = bands[i], hi = bands[kFrame + i];
     tmp[i] = lo + hi;
@@ -271,6 +273,7 @@ WAP_DEV void two_band_synthesis(const float* bands, float* full, float* tmp, flo
   if (lane == 0) qmf_allpass_branch(tmp, 1, kFrame, kQmfAllPass2, state, tmp);
   if (lane == 1) qmf_allpass_branch(tmp + kFrame, 1, kFrame, kQmfAllPass1, state + kQmfStateFloats, tmp + kFrame);
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kFrame; i += 32) {
     const float f1 = tmp[i], f2 = tmp[kFrame + i];
     full[2 * i] = f2 > -32768.0f ? (f2 < 32767.0f ? f2 : 32767.0f) : -32768.0f;

@@ -57,12 +57,15 @@ WAP_DEV float ns_exp_approx(float x) { return ns_pow_approx(10.f, x * 0.43429448
 // FormExtendedFrame + ApplyFilterBankWindow (noise_suppressor.cc:78-101).
 WAP_DEV void ns_form_windowed_frame(const float* frame, float* mem, float* buf) {
   const int lane = lane_id();
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) {
     float v = (i < kNsOverlap) ? mem[i] : frame[i - kNsOverlap];
     buf[i] = v;
   }
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kNsOverlap; i += 32) mem[i] = buf[160 + i];
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) {
     if (i < 96) buf[i] = kNsWindow96[i] * buf[i];
     else if (i >= 161) buf[i] = kNsWindow96[256 - i] * buf[i];
@@ -87,10 +90,12 @@ WAP_DEV void ns_magnitude(const float* a, float* spec) {
 WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame, NsScratch& sc) {
   const int lane = lane_id();
   // NoiseEstimator::PrepareAnalysis (noise_estimator.cc:66-69)
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) st.prev_noise[i] = st.noise[i];
   // Zero-frame detection: the reference sums v*v over memory+frame and tests
   // > 0; a sum of non-negative terms is positive iff one term is.
   int nz = 0;
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) {
     const float v = (i < kNsOverlap) ? st.analyze_mem[i] : frame[i - kNsOverlap];
     nz |= (v * v > 0.f);
@@ -113,6 +118,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   // instruction stream on four lanes (one pointer each) instead of four divergent loops.
   {
     const float* a = sc.buf;
+    #pragma unroll
     for (int i = lane; i < kNsBins; i += 32) {
       const float re = (i == 0) ? a[0] : (i == 128 ? a[1] : a[2 * i]);
       const float im = (i == 0 || i == 128) ? 0.f : a[2 * i + 1];
@@ -146,6 +152,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
     __syncwarp();
     for (int s = 0; s < 3; ++s) {
       const float one_by_counter_plus_1 = 1.f / ((float)counter[s] + 1.f);
+      #pragma unroll
       for (int i = lane; i < kNsBins; i += 32) {
         const int j = s * kNsBins + i;
         float dens = st.q_density[j];
@@ -178,9 +185,11 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
       st.q_num_updates = num_updates;
     }
     if (qidx >= 0) {
+      #pragma unroll
       for (int i = lane; i < kNsBins; i += 32) st.q_quantile[i] = ns_exp_approx(st.q_log_quantile[qidx + i]);
     }
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kNsBins; i += 32) st.noise[i] = st.q_quantile[i];
     __syncwarp();
   }
@@ -228,6 +237,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
       st.pink_noise_numerator = pink_num;
       st.pink_noise_exp = pink_exp;
     }
+    #pragma unroll
     for (int i = lane; i < kNsBins; i += 32) {
       float pn;
       if (pink_exp == 0.f) {
@@ -248,6 +258,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   }
 
   // ---- ComputeSnr (noise_suppressor.cc:167-190)
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float noise = st.noise[i];
     const float prev_estimate = st.prev_analysis_spectrum[i] / (st.prev_noise[i] + 0.0001f) * st.wiener[i];
@@ -294,6 +305,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
     float* t1 = sc.buf;
     float* t2 = sc.buf + 132;
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kNsBins; i += 32) {
       const float sd = sc.spec[i] - signal_average;
       const float nd = st.conservative_noise[i] - noise_average;
@@ -423,6 +435,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
     }
   }
   // UpdateSpectralLrt (signal_model_estimator.cc:94-118)
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float tmp1 = 1.f + 2.f * sc.prior[i];
     const float tmp2 = 2.f * sc.prior[i] / (tmp1 + 0.0001f);
@@ -458,6 +471,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
     st.spectral_diff = f_diff;
     st.prior_speech_prob = prior_prob;
   }
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float inv_lrt = ns_exp_approx(-sc.tmp[i]);
     const float p = 1.f / (1.f + gain_prior * inv_lrt);
@@ -467,6 +481,7 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   __syncwarp();
 
   // ---- NoiseEstimator::PostUpdate (noise_estimator.cc:161-205)
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float prob_speech = sc.post[i];
     const float prob_non_speech = 1.f - prob_speech;
@@ -506,6 +521,7 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   ns_magnitude(sc.buf, sc.spec);
 
   // ---- WienerFilter::Update (wiener_filter.cc:33-84)
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float spec = sc.spec[i];
     const float noise = st.noise[i];
@@ -560,6 +576,7 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   if (!cfg.capture_output_used) return;
 
   // apply filter to the packed spectrum, inverse FFT, scale 2/256
+  #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
     const float f = sc.prior[i];
     if (i == 0) sc.buf[0] *= f;
@@ -571,11 +588,13 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   }
   __syncwarp();
   fft256_inverse(sc.buf, lane);
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) sc.buf[i] *= (2.f / 256.f);
   __syncwarp();
   const float energy_after = serial_sum_sq_v4(sc.buf, 256);
   __syncwarp();
   // synthesis window
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) {
     if (i < 96) sc.buf[i] = kNsWindow96[i] * sc.buf[i];
     else if (i >= 161) sc.buf[i] = kNsWindow96[256 - i] * sc.buf[i];
@@ -599,22 +618,28 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
   }
   __syncwarp();
   // scale, overlap-add (noise_suppressor.cc:104-116) and clamp
+  #pragma unroll
   for (int i = lane; i < 256; i += 32) sc.buf[i] = gain_adjustment * sc.buf[i];
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kFrame; i += 32) {
     float v = (i < kNsOverlap) ? st.synth_mem[i] + sc.buf[i] : sc.buf[i];
     bands[i] = fminr(fmaxr(v, -32768.f), 32767.f);
   }
   __syncwarp();
+  #pragma unroll
   for (int i = lane; i < kNsOverlap; i += 32) st.synth_mem[i] = sc.buf[kFrame + i];
   // upper bands: delay by 96 samples and scale (noise_suppressor.cc:119-131,523-547)
   for (int b = 1; b < cfg.num_bands; ++b) {
     float* y = bands + b * kFrame;
     float* dm = st.delay_mem[b - 1];
+    #pragma unroll
     for (int i = lane; i < kFrame; i += 32) sc.buf[i] = (i < kNsOverlap) ? dm[i] : y[i - kNsOverlap];
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kNsOverlap; i += 32) dm[i] = y[kFrame - kNsOverlap + i];
     __syncwarp();
+    #pragma unroll
     for (int i = lane; i < kFrame; i += 32) {
       const float v = upper_band_gain * sc.buf[i];
       y[i] = fminr(fmaxr(v, -32768.f), 32767.f);
