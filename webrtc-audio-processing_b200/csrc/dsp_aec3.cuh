@@ -34,6 +34,7 @@ constexpr int kScalarWords = (int)(sizeof(Aec3Scalars) / sizeof(int));
 WAP_DEV void aec3_stage_scalars(const Aec3State& a, AecScratch& sc) {
   const int* src = reinterpret_cast<const int*>(&a.s);
   int* dst = reinterpret_cast<int*>(&sc.s);
+  #pragma unroll
   for (int i = lane_id(); i < kScalarWords; i += 32) dst[i] = src[i];
   __syncwarp();
 }
@@ -41,6 +42,7 @@ WAP_DEV void aec3_unstage_scalars(Aec3State& a, const AecScratch& sc) {
   __syncwarp();
   const int* src = reinterpret_cast<const int*>(&sc.s);
   int* dst = reinterpret_cast<int*>(&a.s);
+  #pragma unroll
   for (int i = lane_id(); i < kScalarWords; i += 32) dst[i] = src[i];
   __syncwarp();
 }

@@ -157,6 +157,7 @@ WAP_DEV int ring_off(int i, int off, int size) { return (size + i + off) % size;
 
 // FftData::CopyFromPackedArray / CopyToPackedArray (fft_data.h:77-98)
 WAP_DEV void packed_to_reim(const float* a, float* re, float* im) {
+  #pragma unroll
   for (int k = lane_id(); k < kBins; k += 32) {
     if (k == 0) { re[0] = a[0]; im[0] = 0.f; }
     else if (k == 64) { re[64] = a[1]; im[64] = 0.f; }
@@ -164,6 +165,7 @@ WAP_DEV void packed_to_reim(const float* a, float* re, float* im) {
   }
 }
 WAP_DEV void reim_to_packed(const float* re, const float* im, float* a) {
+  #pragma unroll
   for (int k = lane_id(); k < kBins; k += 32) {
     if (k == 0) a[0] = re[0];
     else if (k == 64) a[1] = re[64];
@@ -175,6 +177,7 @@ WAP_DEV float power_bin(float re, float im, int k) {
   return (k < 64) ? fmaf(re, re, im * im) : re * re + im * im;
 }
 WAP_DEV void power_spectrum(const float* re, const float* im, float* out) {
+  #pragma unroll
   for (int k = lane_id(); k < kBins; k += 32) out[k] = power_bin(re[k], im[k], k);
 }
 

@@ -28,7 +28,8 @@ constexpr float kMfX2SumThreshold = 512.f * ec3::kMfExcitationLimit * ec3::kMfEx
 WAP_DEV void mf_stage_window(const Aec3State& a, const AecScratch& sc, int n, float* dst) {
   int start = sc.s.lr_read + n * kMfShift;
   if (start >= kLowRateSize) start -= kLowRateSize;
-  for (int w = lane_id(); w < kMfWin; w += 32) {
+#pragma unroll
+  for (int w = lane_id(); w < kMfWin; w += 32) {  // 17 independent loads in flight
     int r = start + w;
     if (r >= kLowRateSize) r -= kLowRateSize;
     dst[w] = a.low_rate[r];
@@ -156,6 +157,7 @@ WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) 
   {
     int start = sc.s.lr_read + n * kMfShift;
     if (start >= kLowRateSize) start -= kLowRateSize;
+    #pragma unroll
     for (int w = lane; w < kMfWin; w += 32) {
       int r = start + w;
       if (r >= kLowRateSize) r -= kLowRateSize;
@@ -376,6 +378,7 @@ WAP_DEV int mf_max_square_peak_index(const float* h) {
   const int lane = lane_id();
   float best = -1.f;
   int bi = 0;
+  #pragma unroll
   for (int t = lane; t < kMfLen; t += 32) {  // lane parity == tap parity
     const float v = h[t] * h[t];
     if (v > best) { best = v; bi = t; }
@@ -493,12 +496,14 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
     }
     __syncwarp();
     mf_stage_window(a, sc, n, sc.mf.xp);
+    #pragma unroll
     for (int t = lane; t < kMfLen; t += 32) (sc.mf.xp + kMfHOffset)[t] = a.mf_h[n][t];
     __syncwarp();
     float error_sum;
     int updated;
     mf_core(sc, n, y, &error_sum, &updated);
     const int peak = mf_max_square_peak_index((sc.mf.xp + kMfHOffset));
+    #pragma unroll
     for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = (sc.mf.xp + kMfHOffset)[t];
     if (lane == 0) {
       sc.mf.err_sum[n] = error_sum;
@@ -552,6 +557,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
     if (sc.ired[3]) {
       // UpdateAccumulatedError (matched_filter.cc:43-58)
       const float one_over_anchor = 1.0f / error_sum_anchor;
+      #pragma unroll
       for (int k = lane; k < kAccErrLen; k += 32) {
         const float error_norm = sc.mf.inst_err[k] * one_over_anchor;
         float acc = a.mf_acc_err[winner_index][k];
