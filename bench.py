@@ -49,9 +49,14 @@ def parse():
     ap.add_argument("--aec", type=int, default=1)
     ap.add_argument("--ns", type=int, default=1)
     ap.add_argument("--ns-level", type=int, default=1)
+    ap.add_argument("--rate", type=int, default=16000, choices=[16000, 32000, 48000],
+                    help="native sample rate of the legs (BASELINE config 3: --rate 48000 --aec 0 --ns-level 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    global RATE, FL
+    RATE, FL = a.rate, a.rate // 100
+    return a
 
 
 def workload_name(a):
@@ -60,7 +65,7 @@ def workload_name(a):
         parts.append("AEC3(default EchoCanceller3Config)")
     if a.ns:
         parts.append("NS(%s)" % ["low", "moderate", "high", "veryhigh"][a.ns_level])
-    return "%d synthetic mono 16 kHz call legs per GPU, %s, 10 ms frames" % (a.streams, "+".join(parts))
+    return "%d synthetic mono %d kHz call legs per GPU, %s, 10 ms frames" % (a.streams, a.rate // 1000, "+".join(parts))
 
 
 def peaks():
