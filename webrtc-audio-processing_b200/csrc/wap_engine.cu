@@ -485,7 +485,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->cfg = cfg;
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
   e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
-  e->mono16k_class = cfg.num_bands == 1 && !cfg.resample && !cfg.agc2_enabled && !cfg.levels_enabled && cfg.channels == 1;
+  e->mono16k_class = cfg.num_bands == 1 && !cfg.resample && cfg.channels == 1;
   e->delay_scratch_floats = wap::delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&

@@ -103,8 +103,9 @@ WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
 // k_echo body: everything after the front end for one leg (reference
 // audio_processing_impl.cc:1359-1448 for the enabled submodules).
 // kMono16k: the kernel instance for the most common config class -- 16 kHz mono at its native rate
-// without AGC2 / level adjustment (the bench workload): the config fields below become compile-time
-// constants, so the band-split, resampler, stereo, AGC2 and level code is not even in the kernel.
+// (the bench workload, with or without AGC2 / level adjustment): the config fields below become
+// compile-time constants, so the band-split, upper-band, resampler and stereo code is not even in the
+// kernel.
 template <bool kMono16k>
 WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   EngineConfig cfg = a.cfg;
@@ -113,8 +114,6 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     cfg.split_bands = 0;
     cfg.resample = 0;
     cfg.fullband_out = 0;
-    cfg.agc2_enabled = 0;
-    cfg.levels_enabled = 0;
     cfg.channels = 1;
   }
   const int B = cfg.num_bands;
