@@ -145,69 +145,16 @@ WAP_DEV float scaler_step(ScalerRun& r, float v) {
   return fminr(fmaxr(v, -32768.f), 32767.f);  // SafeClamp
 }
 
-// The front end of one tick for leg `idx` (thread-private).
-WAP_DEV void front_leg(const TickArgs& a, int idx) {
+// Capture side in front of the band split: full-band high-pass filter, pre level adjustment,
+// AEC3's saturation test (both channels of a stereo leg), echo-path gain-change flag.  Writes the
+// filtered frame to ts.capture_frame.  One thread (k_front, or lane 0 of k_split).
+WAP_DEV void front_capture_prefilter(const TickArgs& a, int idx) {
   const EngineConfig& cfg = a.cfg;
-  const int B = cfg.num_bands;
-  const int flen = kFrame * B;
+  const int flen = kFrame * cfg.num_bands;
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
   TickScratch& ts = st.tick;
-  Aec3State& aec = st.aec;
-  Aec3Scalars& s = aec.s;
-  // 32 kHz legs run the upper-band code of the 3-band path with a second upper band that stays
-  // all-zero (it never raises the band-energy maximum and its output is dropped).
-  UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
-  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
-  const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
-  // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
-  // drains the render queue (audio_processing_impl.cc:1409-1415).
-  if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms);
-  float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
-  float sub[kFrame];
-
-  // ---------------- render: [band split] -> FrameBlocker -> BlockProcessor::BufferRender
-  int nrb = 0;
-  if (a.render && cfg.aec_enabled && render_live) {
-    const float* band0;
-    if (B >= 2) {
-      // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
-      for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
-      float* full = ts.capture_frame;  // borrowed as the thread's 320/480-sample input buffer
-      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
-      if (B == 3) three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
-      else two_band_analysis_thread(full, frame, &st.render_bands.analysis[0][0]);
-      band0 = frame;
-    } else {
-      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
-      band0 = frame;
-    }
-    const int L = s.render_blocker_len;
-    const int total = L + kFrame;
-    nrb = total / kBlock;
-    float x[kBlock];
-    for (int r = 0; r < nrb; ++r) {
-      for (int j = 0; j < kBlock; ++j) {
-        const int k = kBlock * r + j - L;
-        x[j] = k < 0 ? aec.render_blocker[L + k] : band0[k];
-      }
-      front_render_insert(aec, ts, r, x);
-    }
-    const int rem = total - kBlock * nrb;
-    for (int j = 0; j < rem; ++j) aec.render_blocker[j] = band0[kFrame - rem + j];
-    if (up) {
-      front_slice_band(frame + kFrame, up->render_blocker_hi[0], L, nrb, up->render_blocks_hi, 0);
-      if (B == 3) front_slice_band(frame + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
-    }
-    s.render_blocker_len = rem;
-  }
-  ts.n_render_blocks = nrb;
-  ts.n_capture_blocks = 0;
-  if (!a.capture) return;
-
-  // ---------------- capture: high-pass filter, saturation, [band split], FrameBlocker, decimator
-  st.seen_capture = 1;
-  {
+  Aec3Scalars& s = st.aec.s;
     const BiquadCoef* hc = cfg.hpf_rate == 48000 ? kHpf48k : (cfg.hpf_rate == 32000 ? kHpf32k : kHpf16k);
     Biquad h0 = st.hpf[0], h1 = st.hpf[1], h2 = st.hpf[2];
     int sat = 0;
@@ -264,9 +211,81 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       ts.pad_[1] = gc;
     }
   }
+
+// True for legs whose band split runs in k_split (warp per leg) in front of k_front: 48 kHz AEC3.
+WAP_DEV bool front_presplit(const EngineConfig& cfg) { return cfg.num_bands == 3 && cfg.aec_enabled && !cfg.resample; }
+
+// The front end of one tick for leg `idx` (thread-private).
+WAP_DEV void front_leg(const TickArgs& a, int idx) {
+  const EngineConfig& cfg = a.cfg;
+  const int B = cfg.num_bands;
+  const int flen = kFrame * B;
+  const int slot = a.slots ? a.slots[idx] : idx;
+  StreamState& st = a.states[slot];
+  TickScratch& ts = st.tick;
+  Aec3State& aec = st.aec;
+  Aec3Scalars& s = aec.s;
+  // 32 kHz legs run the upper-band code of the 3-band path with a second upper band that stays
+  // all-zero (it never raises the band-energy maximum and its output is dropped).
+  UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
+  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
+  const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
+  // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
+  // drains the render queue (audio_processing_impl.cc:1409-1415).
+  if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms);
+  float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
+  float sub[kFrame];
+
+  // ---------------- render: [band split] -> FrameBlocker -> BlockProcessor::BufferRender
+  int nrb = 0;
+  if (a.render && cfg.aec_enabled && render_live) {
+    const float* band0;
+    const float* rbands = frame;  // bands 1.. of the render frame
+    if (front_presplit(cfg)) {
+      rbands = up->render_frame;  // k_split did the three-band analysis
+      band0 = rbands;
+    } else if (B >= 2) {
+      // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
+      for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
+      float* full = ts.capture_frame;  // borrowed as the thread's 320/480-sample input buffer
+      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+      if (B == 3) three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
+      else two_band_analysis_thread(full, frame, &st.render_bands.analysis[0][0]);
+      band0 = frame;
+    } else {
+      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+      band0 = frame;
+    }
+    const int L = s.render_blocker_len;
+    const int total = L + kFrame;
+    nrb = total / kBlock;
+    float x[kBlock];
+    for (int r = 0; r < nrb; ++r) {
+      for (int j = 0; j < kBlock; ++j) {
+        const int k = kBlock * r + j - L;
+        x[j] = k < 0 ? aec.render_blocker[L + k] : band0[k];
+      }
+      front_render_insert(aec, ts, r, x);
+    }
+    const int rem = total - kBlock * nrb;
+    for (int j = 0; j < rem; ++j) aec.render_blocker[j] = band0[kFrame - rem + j];
+    if (up) {
+      front_slice_band(rbands + kFrame, up->render_blocker_hi[0], L, nrb, up->render_blocks_hi, 0);
+      if (B == 3) front_slice_band(rbands + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
+    }
+    s.render_blocker_len = rem;
+  }
+  ts.n_render_blocks = nrb;
+  ts.n_capture_blocks = 0;
+  if (!a.capture) return;
+
+  // ---------------- capture: high-pass filter, saturation, [band split], FrameBlocker, decimator
+  st.seen_capture = 1;
+  const bool presplit = front_presplit(cfg);
+  if (!presplit) front_capture_prefilter(a, idx);
   if (!cfg.aec_enabled) return;
-  const float* cap0 = ts.capture_frame;
-  if (B >= 2) {
+  const float* cap0 = ts.capture_frame;  // with k_split: already the bands of the filtered frame
+  if (B >= 2 && !presplit) {
     // AudioBuffer::SplitIntoFrequencyBands on the capture side (audio_processing_impl.cc:1359-1363);
     // k_echo finds the bands in ts.capture_frame instead of the full-band frame.
     for (int i = 0; i < flen; ++i) frame[i] = 0.f;
@@ -303,8 +322,8 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     const int rem = total - kBlock * ncb;
     for (int j = 0; j < rem; ++j) aec.capture_blocker[j] = cap0[kFrame - rem + j];
     if (up) {
-      front_slice_band(frame + kFrame, up->capture_blocker_hi[0], L, ncb, up->capture_blocks_hi, 0);
-      if (B == 3) front_slice_band(frame + 2 * kFrame, up->capture_blocker_hi[1], L, ncb, up->capture_blocks_hi, 1);
+      front_slice_band(cap0 + kFrame, up->capture_blocker_hi[0], L, ncb, up->capture_blocks_hi, 0);
+      if (B == 3) front_slice_band(cap0 + 2 * kFrame, up->capture_blocker_hi[1], L, ncb, up->capture_blocks_hi, 1);
     }
     s.capture_blocker_len = rem;
     ts.n_capture_blocks = ncb;

@@ -29,6 +29,14 @@ __global__ void __launch_bounds__(128) k_front(TickArgs a) {
   if (idx < a.n) front_leg(a, idx);
 }
 
+// 48 kHz AEC3 engines: band split of render and capture in front of k_front, one warp per leg.
+__global__ void __launch_bounds__(128) k_split(TickArgs a) {
+  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());  // 4 warps x 1120 floats
+  const int warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 4 + warp;
+  if (idx < a.n) split_tick(a, idx, sm + warp * 1120);
+}
+
 // Resampled engines: API-rate frames -> processing-rate FloatS16 frames, one warp per leg.
 __global__ void __launch_bounds__(128) k_resample(TickArgs a) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());  // 4 warps x 2 * kRsMaxRequest floats
@@ -385,6 +393,10 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     af.fmt = 2;
     WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, af);
   } else {
+    if (e->d_upper && e->cfg.num_bands == 3) {
+      WAP_LAUNCH(wap::k_split, grid_for(n), wpb * 32, (size_t)wpb * 1120 * sizeof(float), e->stream, a);
+      e->launches++;
+    }
     WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
   }
   e->launches++;

@@ -62,6 +62,38 @@ WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
   aec3_delay_frame(st.aec, st.tick, sc);
 }
 
+// k_split body (48 kHz AEC3 engines): the three-band analysis of the render and the capture frame,
+// which needs the lanes of a warp (in k_front it would be 480 outputs x 10 filters per thread and
+// dominate the tick).  Lane 0 runs the serial capture pre-filter first.  `scratch`: 1120 floats.
+WAP_DEV void split_tick(const TickArgs& a, int idx, float* scratch) {
+  const EngineConfig& cfg = a.cfg;
+  const int lane = lane_id();
+  const int slot = a.slots ? a.slots[idx] : idx;
+  StreamState& st = a.states[slot];
+  UpperBandState& up = a.upper[slot];
+  const int flen = 3 * kFrame;
+  float* full = scratch;
+  float* bands = scratch + flen;
+  float* sub = scratch + 2 * flen;
+  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
+  if (a.render && render_live) {
+    for (int i = lane; i < flen; i += 32) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+    __syncwarp();
+    three_band_analysis(full, bands, sub, st.render_bands.analysis);
+    for (int i = lane; i < flen; i += 32) up.render_frame[i] = bands[i];
+    __syncwarp();
+  }
+  if (a.capture) {
+    if (lane == 0) front_capture_prefilter(a, idx);
+    __syncwarp();
+    for (int i = lane; i < flen; i += 32) full[i] = st.tick.capture_frame[i];
+    __syncwarp();
+    three_band_analysis(full, bands, sub, st.capture_bands.analysis);
+    for (int i = lane; i < flen; i += 32) st.tick.capture_frame[i] = bands[i];
+    __syncwarp();
+  }
+}
+
 // k_resample body (engines whose API rate differs from the processing rate): AudioBuffer::CopyFrom
 // with an input resampler for the render and the capture frame of one leg (audio_buffer.cc:116-160,
 // 234-300).  `scratch`: 2 * kRsMaxRequest floats.

@@ -277,6 +277,7 @@ struct alignas(16) UpperBandState {
   float render_blocker_hi[2][kBlock], capture_blocker_hi[2][kBlock], output_framer_hi[2][kBlock];
   Biquad post_filter[4];                        // PostFilter (post_filter.cc:27-72), 48 kHz only
   // tick scratch (k_front -> k_echo -> k_post)
+  float render_frame[3 * 160];                  // bands of this tick's render frame (k_split -> k_front)
   float render_blocks_hi[3][2][kBlock];
   float capture_blocks_hi[3][2][kBlock];
 };
