@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--ns-level", type=int, default=1)
     ap.add_argument("--agc2-gain-db", type=float, default=None,
                     help="add GainController2 (fixed gain + limiter) to the chain: BASELINE config 5 (no CPU arm)")
+    ap.add_argument("--max-rate", type=int, default=48000, choices=[32000, 48000],
+                    help="pipeline.maximum_internal_processing_rate (32000 = the reference default: 48 kHz legs are resampled)")
     ap.add_argument("--rate", type=int, default=16000, choices=[16000, 32000, 48000],
                     help="native sample rate of the legs (BASELINE config 3: --rate 48000 --aec 0 --ns-level 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
@@ -69,6 +71,8 @@ def workload_name(a):
         parts.append("NS(%s)" % ["low", "moderate", "high", "veryhigh"][a.ns_level])
     if getattr(a, "agc2_gain_db", None) is not None:
         parts.append("AGC2(fixed %g dB + limiter)" % a.agc2_gain_db)
+    if getattr(a, "max_rate", 48000) == 32000 and a.rate == 48000:
+        parts.append("processed at 32 kHz (default maximum_internal_processing_rate)")
     return "%d synthetic mono %d kHz call legs per GPU, %s, 10 ms frames" % (a.streams, a.rate // 1000, "+".join(parts))
 
 
@@ -220,7 +224,7 @@ def run_b200(a):
     L = wap_b200.load()
     S = a.streams
     extra = {} if a.agc2_gain_db is None else dict(agc2=True, agc2_fixed_gain_db=a.agc2_gain_db)
-    eng = wap_b200.Engine(S, RATE, lib=L, device=local, aec=bool(a.aec), ns=bool(a.ns), ns_level=a.ns_level, **extra)
+    eng = wap_b200.Engine(S, RATE, lib=L, device=local, aec=bool(a.aec), ns=bool(a.ns), ns_level=a.ns_level, max_rate=a.max_rate, **extra)
     render, capture = make_inputs(torch, dev, S, 1234 + rank)
     out = torch.empty((S, FL), dtype=torch.int16, device=dev)
     stream = torch.cuda.ExternalStream(L.wap_engine_cuda_stream(eng.h), device=dev)
