@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, 
 #ifndef WAP_ECHO_MINBLOCKS
 #define WAP_ECHO_MINBLOCKS 4
 #endif
-template <bool kMono16k>
+template <int kClass>
 __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, in
 #endif
   float* scratch = sm + scratch_off;
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
-    echo_stream_tick<kMono16k>(a, idx, scratch);
+    echo_stream_tick<kClass>(a, idx, scratch);
     __syncwarp();
   }
 }
@@ -157,7 +157,7 @@ struct WapEngine {
   int delay_scratch_floats = 0;
   bool is_default = false;
   int sm_count = 148;
-  bool mono16k_class = false;  // served by the specialised k_echo<true> instance
+  int echo_class = 0;  // wap::EchoClass: which k_echo instance serves this engine
   // resampled engines (API rate != processing rate)
   wap::ResamplerState* d_rs = nullptr;   // [capacity][kRsPerLeg]
   float* d_rs_kernels = nullptr;         // in | out tables
@@ -408,8 +408,13 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   }
   if (timing) cudaEventRecord(e->ev[2], e->stream);
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
-  if (e->mono16k_class) WAP_LAUNCH(wap::k_echo<true>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
-  else WAP_LAUNCH(wap::k_echo<false>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  switch (e->echo_class) {
+    case wap::kEchoMono16k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono16k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
+    case wap::kEchoMono48kNative: WAP_LAUNCH(wap::k_echo<wap::kEchoMono48kNative>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
+    case wap::kEchoMono48kVia32k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono48kVia32k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
+    case wap::kEchoMono32k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono32k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
+    default: WAP_LAUNCH(wap::k_echo<wap::kEchoGeneric>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
+  }
   e->launches++;
   if (e->d_upper && e->cfg.num_bands == 3 && d_capture) {  // PostFilter: 48 kHz only (post_filter.cc:44-52)
     WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
@@ -497,7 +502,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->cfg = cfg;
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
   e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
-  e->mono16k_class = cfg.num_bands == 1 && !cfg.resample && cfg.channels == 1;
+  e->echo_class = wap::echo_class_of(cfg);
   e->delay_scratch_floats = wap::delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&
@@ -541,8 +546,11 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
   const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
   if (ok && smem_e > 48 * 1024)
-    ok = cudaFuncSetAttribute(wap::k_echo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
-         cudaFuncSetAttribute(wap::k_echo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
+    ok = cudaFuncSetAttribute(wap::k_echo<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
+         cudaFuncSetAttribute(wap::k_echo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
+         cudaFuncSetAttribute(wap::k_echo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
+         cudaFuncSetAttribute(wap::k_echo<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
+         cudaFuncSetAttribute(wap::k_echo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
   if (ok && smem_d > 48 * 1024)
     ok = cudaFuncSetAttribute(wap::k_delay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d) == cudaSuccess;
   if (!ok) {

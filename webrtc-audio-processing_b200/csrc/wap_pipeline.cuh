@@ -134,19 +134,37 @@ WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
 
 // k_echo body: everything after the front end for one leg (reference
 // audio_processing_impl.cc:1359-1448 for the enabled submodules).
-// kMono16k: the kernel instance for the most common config class -- 16 kHz mono at its native rate
-// (the bench workload, with or without AGC2 / level adjustment): the config fields below become
-// compile-time constants, so the band-split, upper-band, resampler and stereo code is not even in the
-// kernel.
-template <bool kMono16k>
+// Config classes with their own k_echo instance: the fields below become compile-time constants in
+// it, so the band-split / upper-band / resampler / stereo code a class does not use is not even in
+// the kernel (instruction footprint is what k_echo is sensitive to).  Class 0 is the generic one.
+enum EchoClass {
+  kEchoGeneric = 0,
+  kEchoMono16k = 1,      // 16 kHz mono, native (the bench workload; with or without AGC2 / levels)
+  kEchoMono48kNative = 2,  // 48 kHz mono, three bands
+  kEchoMono48kVia32k = 3,  // 48 kHz mono under the default maximum_internal_processing_rate
+  kEchoMono32k = 4,      // 32 kHz mono, two bands
+  kEchoClasses = 5
+};
+inline int echo_class_of(const EngineConfig& c) {
+  if (c.channels != 1) return kEchoGeneric;
+  if (c.num_bands == 1 && !c.resample) return kEchoMono16k;
+  if (!c.split_bands) return kEchoGeneric;
+  if (c.num_bands == 3 && !c.resample) return kEchoMono48kNative;
+  if (c.num_bands == 2 && c.resample && c.fullband_out) return kEchoMono48kVia32k;
+  if (c.num_bands == 2 && !c.resample) return kEchoMono32k;
+  return kEchoGeneric;
+}
+
+template <int kClass>
 WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   EngineConfig cfg = a.cfg;
-  if (kMono16k) {
-    cfg.num_bands = 1;
-    cfg.split_bands = 0;
-    cfg.resample = 0;
-    cfg.fullband_out = 0;
+  if (kClass != kEchoGeneric) {
     cfg.channels = 1;
+    cfg.num_bands = kClass == kEchoMono16k ? 1 : (kClass == kEchoMono48kNative ? 3 : 2);
+    cfg.split_bands = kClass == kEchoMono16k ? 0 : 1;
+    cfg.resample = kClass == kEchoMono48kVia32k ? 1 : 0;
+    cfg.fullband_out = kClass == kEchoMono48kVia32k ? 1 : 0;
+    if (kClass == kEchoMono48kVia32k) cfg.api_frame = 480;
   }
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
