@@ -196,7 +196,9 @@ WapError wap_streams_set_delay_ms(WapAudioProcessing* const* handles, int32_t n,
 WapError wap_process_streams_device(WapEngine* engine, WapAudioProcessing* const* handles, int32_t n,
                                     const void* d_render, const void* d_capture, void* d_out,
                                     WapSampleFormat fmt);
-/* One tick is three kernels (k_front, k_delay, k_echo).  While kernel timing is enabled
+/* One tick is three kernels for the 16 kHz classes (k_front, k_delay, k_echo; k_resample / k_split in
+ * front and k_post behind for the resampled and 48 kHz classes, counted with k_front / k_echo here).
+ * While kernel timing is enabled
  * every tick records CUDA events around them on the engine's stream (and waits), so a
  * bench can attribute time and algorithmic bytes per kernel; out arrays have 3 entries. */
 WapError wap_engine_enable_kernel_timing(WapEngine* engine, bool on);

@@ -10,7 +10,7 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 kernel = sys.argv[3] if len(sys.argv) > 3 else "k_echo"
 so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "webrtc-audio-processing_b200", "libwap_b200.so")
-# substring of the MANGLED name selecting the function in the cubin (template instances: k_echoILb1)
+# substring of the MANGLED name selecting the function in the cubin (template instances: k_echoILi1 = k_echo<1>)
 mangled = sys.argv[5] if len(sys.argv) > 5 else kernel
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)],

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """A short run of every kernel path (16 / 32 / 48 kHz, resampled, stereo, AGC2, level adjustment,
-mute) for compute-sanitizer on the GPU box:
-  compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python tools/sanitize_run.py"""
+mute, ragged last CTA) -- a quick smoke of all config classes on the GPU box, and the workload to put
+under compute-sanitizer where that tool is available (it is closed on this pool):
+  [compute-sanitizer --tool memcheck|racecheck|synccheck] python tools/sanitize_run.py"""
 import os
 import sys
 
