@@ -421,3 +421,22 @@ def test_emu_level_adjustment_and_runtime_settings(emu_lib, oracle, rate, max_ra
     1526-1528; gain_controller2.cc:160-168): float32 bits identical."""
     from common import run_with_runtime_settings
     assert run_with_runtime_settings(emu_lib, oracle, rate, 80, events, max_rate=max_rate, **kw) == 0
+
+
+def test_bench_reference_arm_contract(oracle):
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): exactly one JSON
+    line on stdout with the contract's keys; no CUDA device needed."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-seconds", "1.5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "real-time streams" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"]
