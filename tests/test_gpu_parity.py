@@ -282,3 +282,28 @@ def test_agc2_limiter_float_identity(gpu_lib, oracle, rate):
         differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
     eng.close()
     assert differing == 0
+
+
+def test_bench_line_contract(gpu_lib):
+    """`python bench.py` (small arguments): one JSON line with the bench contract's keys, the kernels
+    really launched, a roofline object for the dominant kernel and a bounded CPU baseline."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--streams", "512", "--steps", "6", "--warmup", "3",
+                        "--cpu-seconds", "1.5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["steps"] == 6 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["scaling"] == "weak"
+    assert d["gpu_launches"] == 18 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 512 * 160 * 2 and d["e2e"]["d2h_bytes_per_step"] == 512 * 160 * 2
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["kernel"] in ("k_echo", "k_delay") and 0 < rf["frac"] < 1 and rf["peak"] > 1000
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
