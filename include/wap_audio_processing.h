@@ -16,6 +16,17 @@
  * Audio conventions are the reference's (api/audio/audio_processing.h:66-77):
  * 10 ms frames; int16 data interleaved; float data planar in [-1, 1].
  * There is no CPU fallback: every call needs a CUDA device.
+ *
+ * Threading contract (webrtc::AudioProcessing's render / capture split,
+ * audio_processing_impl.h:199-215):
+ *  - a handle made by wap_create*() may be driven by ONE render thread
+ *    (wap_process_reverse_stream_*) and ONE capture thread (everything else)
+ *    at the same time: the reverse call only validates and enqueues, the
+ *    capture side owns the private engine; capture-side calls on one handle
+ *    serialise on a per-handle lock;
+ *  - every wap_engine_* / wap_process_streams* call and every per-leg setter on
+ *    a leg of an engine takes that engine's lock, so calls on one engine from
+ *    several threads are safe but serialise; different engines are independent.
  */
 #ifndef WAP_AUDIO_PROCESSING_H_
 #define WAP_AUDIO_PROCESSING_H_

@@ -105,5 +105,33 @@ def build(verbose=True, dump=False):
     return LIB
 
 
+def build_seam(verbose=True):
+    """oracle/_ref/libwap_seam.so: the reference's rust_audio_processing.cc, compiled UNMODIFIED with
+    -DWEBRTC_USE_RUST_APM against this repo's include/wap_audio_processing.h, plus oracle/seam_driver.cc,
+    linked against libwap_ref.so for the rest of webrtc.  Its wap_* references stay undefined: the
+    test loads libwap_b200.so (or the emulator build) first with RTLD_GLOBAL."""
+    lib = os.path.join(OUT, "libwap_seam.so")
+    seam = os.path.join(REF, "webrtc", "modules", "audio_processing", "rust_audio_processing.cc")
+    if not os.path.isdir(REF):
+        if os.path.exists(lib):
+            return lib
+        raise RuntimeError("no /root/reference and no prebuilt oracle/_ref/libwap_seam.so")
+    build(verbose=False)
+    hdr = os.path.join(HERE, "..", "include", "wap_audio_processing.h")
+    drv = os.path.join(HERE, "seam_driver.cc")
+    if os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(x) for x in (seam, hdr, drv)):
+        return lib
+    cmd = ["g++", "-std=c++23", "-shared"] + COMMON + ["-DWEBRTC_USE_RUST_APM", "-I" + os.path.join(HERE, "..", "include"),
+           seam, drv, "-o", lib, "-L" + OUT, "-lwap_ref", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stderr[-4000:])
+        raise RuntimeError("oracle/_ref: the reference seam does not compile against include/wap_audio_processing.h")
+    if verbose:
+        print("oracle/_ref: built", lib, "(reference seam, unmodified, against include/wap_audio_processing.h)")
+    return lib
+
+
 if __name__ == "__main__":
     build(dump="--dump" in sys.argv)
+    build_seam()

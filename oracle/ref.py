@@ -32,6 +32,10 @@ def lib():
         L.ref_apm_set_capture_output_used.argtypes = [C.c_void_p, C.c_int]
         L.ref_apm_bench.restype = C.c_double
         L.ref_apm_bench.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_apm_create_kv.restype = C.c_void_p
+        L.ref_apm_create_kv.argtypes = [C.c_char_p]
+        L.ref_apm_apply_kv.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_ec3_validate_kv.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
         L.ref_fft128.argtypes = [C.c_void_p, C.c_int]
         L.ref_rdft256.argtypes = [C.c_void_p, C.c_int]
         L.ref_hpf_create.restype = C.c_void_p
@@ -55,8 +59,14 @@ class RefApm:
 
     def __init__(self, aec=True, ns=True, ns_level=1, max_rate=48000, hpf=False,
                  mc_render=False, mc_capture=False, agc2=False, agc2_fixed_gain_db=0.0,
-                 pre_amp=None, pre_gain=None, post_gain=None):
-        if pre_amp is not None or pre_gain is not None or post_gain is not None:
+                 pre_amp=None, pre_gain=None, post_gain=None, kv=None):
+        if kv is not None:
+            # generic "key=value;..." configuration (ref_driver.cc: ParseKv); ec3.* keys inject an
+            # EchoCanceller3Config through BuiltinAudioProcessingBuilder::SetEchoCancellerConfig
+            self.h = lib().ref_apm_create_kv(kv_string(kv))
+            if not self.h:
+                raise ValueError("ref_apm_create_kv: unknown key in %r" % (kv,))
+        elif pre_amp is not None or pre_gain is not None or post_gain is not None:
             L = lib()
             L.ref_apm_create_levels.restype = C.c_void_p
             L.ref_apm_create_levels.argtypes = [C.c_int] * 6 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float]
@@ -99,6 +109,11 @@ class RefApm:
         err = lib().ref_apm_tick_f32(self.h, rate, render_ch, capture_ch, _p(render), _p(capture), _p(out))
         return out, err
 
+    def apply_config(self, **kv):
+        """AudioProcessing::ApplyConfig with the current config updated by the given APM keys."""
+        err = lib().ref_apm_apply_kv(self.h, kv_string(kv))
+        assert err == 0, err
+
     def set_capture_output_used(self, used):
         lib().ref_apm_set_capture_output_used(self.h, int(used))
 
@@ -118,6 +133,21 @@ class RefApm:
         s = np.zeros(6, dtype=np.float32)
         lib().ref_apm_stats(self.h, _p(s))
         return s
+
+
+def kv_string(kv):
+    if isinstance(kv, str):
+        return kv.encode()
+    return ";".join("%s=%r" % (k, float(v)) for k, v in kv.items()).encode()
+
+
+def ec3_validate(kv, probe=None):
+    """EchoCanceller3Config::Validate on default + kv; returns (was_valid, value of `probe` afterwards)."""
+    out = C.c_double(0.0)
+    r = lib().ref_ec3_validate_kv(kv_string({"ec3." + k: v for k, v in kv.items()}), probe.encode() if probe else None,
+                                  C.byref(out))
+    assert r >= 0, r
+    return bool(r), out.value
 
 
 def fft128(a, inverse=False):

@@ -14,6 +14,8 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <optional>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -101,6 +103,176 @@ void* ref_apm_create_levels(int aec, int ns, int ns_level, int max_rate, int hpf
 }
 
 void ref_apm_destroy(void* p) { delete static_cast<RefApm*>(p); }
+
+// ---- generic "key=value;key=value" configuration (tests of ApplyConfig, EchoCanceller3Config
+// injection through BuiltinAudioProcessingBuilder::SetEchoCancellerConfig and the multi-channel
+// pipeline).  Unknown keys return null / -1 so that a typo in a test cannot pass silently.
+}  // extern "C"
+namespace {
+bool SetEc3(webrtc::EchoCanceller3Config& c, const std::string& k, double v) {
+#define F(path) if (k == #path) { c.path = static_cast<decltype(c.path)>(v); return true; }
+  F(buffering.excess_render_detection_interval_blocks) F(buffering.max_allowed_excess_render_blocks)
+  F(delay.default_delay) F(delay.down_sampling_factor) F(delay.num_filters) F(delay.delay_headroom_samples)
+  F(delay.hysteresis_limit_blocks) F(delay.fixed_capture_delay_samples) F(delay.delay_estimate_smoothing)
+  F(delay.delay_estimate_smoothing_delay_found) F(delay.delay_candidate_detection_threshold)
+  F(delay.delay_selection_thresholds.initial) F(delay.delay_selection_thresholds.converged)
+  F(delay.use_external_delay_estimator) F(delay.log_warning_on_delay_changes)
+  F(delay.render_alignment_mixing.downmix) F(delay.render_alignment_mixing.adaptive_selection)
+  F(delay.render_alignment_mixing.activity_power_threshold) F(delay.render_alignment_mixing.prefer_first_two_channels)
+  F(delay.capture_alignment_mixing.downmix) F(delay.capture_alignment_mixing.adaptive_selection)
+  F(delay.capture_alignment_mixing.activity_power_threshold) F(delay.capture_alignment_mixing.prefer_first_two_channels)
+  F(delay.detect_pre_echo)
+  F(filter.refined.length_blocks) F(filter.refined.leakage_converged) F(filter.refined.leakage_diverged)
+  F(filter.refined.error_floor) F(filter.refined.error_ceil) F(filter.refined.noise_gate)
+  F(filter.coarse.length_blocks) F(filter.coarse.rate) F(filter.coarse.noise_gate)
+  F(filter.refined_initial.length_blocks) F(filter.refined_initial.leakage_converged) F(filter.refined_initial.leakage_diverged)
+  F(filter.refined_initial.error_floor) F(filter.refined_initial.error_ceil) F(filter.refined_initial.noise_gate)
+  F(filter.coarse_initial.length_blocks) F(filter.coarse_initial.rate) F(filter.coarse_initial.noise_gate)
+  F(filter.config_change_duration_blocks) F(filter.initial_state_seconds) F(filter.coarse_reset_hangover_blocks)
+  F(filter.conservative_initial_phase) F(filter.enable_coarse_filter_output_usage) F(filter.use_linear_filter)
+  F(filter.high_pass_filter_echo_reference) F(filter.export_linear_aec_output)
+  F(erle.min) F(erle.max_l) F(erle.max_h) F(erle.onset_detection) F(erle.num_sections)
+  F(erle.clamp_quality_estimate_to_zero) F(erle.clamp_quality_estimate_to_one)
+  F(ep_strength.default_gain) F(ep_strength.default_len) F(ep_strength.nearend_len) F(ep_strength.echo_can_saturate)
+  F(ep_strength.bounded_erl) F(ep_strength.erle_onset_compensation_in_dominant_nearend)
+  F(ep_strength.use_conservative_tail_frequency_response)
+  F(echo_audibility.low_render_limit) F(echo_audibility.normal_render_limit) F(echo_audibility.floor_power)
+  F(echo_audibility.audibility_threshold_lf) F(echo_audibility.audibility_threshold_mf) F(echo_audibility.audibility_threshold_hf)
+  F(echo_audibility.use_stationarity_properties) F(echo_audibility.use_stationarity_properties_at_init)
+  F(render_levels.active_render_limit) F(render_levels.poor_excitation_render_limit)
+  F(render_levels.poor_excitation_render_limit_ds8) F(render_levels.render_power_gain_db)
+  F(echo_removal_control.has_clock_drift) F(echo_removal_control.linear_and_stable_echo_path)
+  F(echo_model.noise_floor_hold) F(echo_model.min_noise_floor_power) F(echo_model.stationary_gate_slope)
+  F(echo_model.noise_gate_power) F(echo_model.noise_gate_slope) F(echo_model.render_pre_window_size)
+  F(echo_model.render_post_window_size) F(echo_model.model_reverb_in_nonlinear_mode)
+  F(comfort_noise.noise_floor_dbfs)
+  F(suppressor.nearend_average_blocks)
+  F(suppressor.normal_tuning.mask_lf.enr_transparent) F(suppressor.normal_tuning.mask_lf.enr_suppress) F(suppressor.normal_tuning.mask_lf.emr_transparent)
+  F(suppressor.normal_tuning.mask_hf.enr_transparent) F(suppressor.normal_tuning.mask_hf.enr_suppress) F(suppressor.normal_tuning.mask_hf.emr_transparent)
+  F(suppressor.normal_tuning.max_inc_factor) F(suppressor.normal_tuning.max_dec_factor_lf)
+  F(suppressor.nearend_tuning.mask_lf.enr_transparent) F(suppressor.nearend_tuning.mask_lf.enr_suppress) F(suppressor.nearend_tuning.mask_lf.emr_transparent)
+  F(suppressor.nearend_tuning.mask_hf.enr_transparent) F(suppressor.nearend_tuning.mask_hf.enr_suppress) F(suppressor.nearend_tuning.mask_hf.emr_transparent)
+  F(suppressor.nearend_tuning.max_inc_factor) F(suppressor.nearend_tuning.max_dec_factor_lf)
+  F(suppressor.lf_smoothing_during_initial_phase) F(suppressor.last_permanent_lf_smoothing_band)
+  F(suppressor.last_lf_smoothing_band) F(suppressor.last_lf_band) F(suppressor.first_hf_band)
+  F(suppressor.dominant_nearend_detection.enr_threshold) F(suppressor.dominant_nearend_detection.enr_exit_threshold)
+  F(suppressor.dominant_nearend_detection.snr_threshold) F(suppressor.dominant_nearend_detection.hold_duration)
+  F(suppressor.dominant_nearend_detection.trigger_threshold) F(suppressor.dominant_nearend_detection.use_during_initial_phase)
+  F(suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum)
+  F(suppressor.subband_nearend_detection.nearend_average_blocks)
+  F(suppressor.subband_nearend_detection.subband1.low) F(suppressor.subband_nearend_detection.subband1.high)
+  F(suppressor.subband_nearend_detection.subband2.low) F(suppressor.subband_nearend_detection.subband2.high)
+  F(suppressor.subband_nearend_detection.nearend_threshold) F(suppressor.subband_nearend_detection.snr_threshold)
+  F(suppressor.use_subband_nearend_detection)
+  F(suppressor.high_bands_suppression.enr_threshold) F(suppressor.high_bands_suppression.max_gain_during_echo)
+  F(suppressor.high_bands_suppression.anti_howling_activation_threshold) F(suppressor.high_bands_suppression.anti_howling_gain)
+  F(suppressor.high_frequency_suppression.limiting_gain_band) F(suppressor.high_frequency_suppression.bands_in_limiting_gain)
+  F(suppressor.floor_first_increase) F(suppressor.conservative_hf_suppression)
+  F(multi_channel.detect_stereo_content) F(multi_channel.stereo_detection_threshold)
+  F(multi_channel.stereo_detection_timeout_threshold_seconds) F(multi_channel.stereo_detection_hysteresis_seconds)
+#undef F
+  return false;
+}
+
+struct KvConfig {
+  AudioProcessing::Config apm;
+  webrtc::EchoCanceller3Config ec3;
+  std::optional<webrtc::EchoCanceller3Config> ec3mc;
+  bool has_ec3 = false;
+};
+
+bool ParseKv(const char* text, KvConfig* out) {
+  AudioProcessing::Config& c = out->apm;
+  std::string s(text ? text : "");
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t end = s.find(';', pos);
+    if (end == std::string::npos) end = s.size();
+    const std::string item = s.substr(pos, end - pos);
+    pos = end + 1;
+    if (item.empty()) continue;
+    const size_t eq = item.find('=');
+    if (eq == std::string::npos) return false;
+    const std::string k = item.substr(0, eq);
+    const double v = atof(item.c_str() + eq + 1);
+    if (k == "aec") c.echo_canceller.enabled = v != 0;
+    else if (k == "aec_enforce_hpf") c.echo_canceller.enforce_high_pass_filtering = v != 0;
+    else if (k == "ns") c.noise_suppression.enabled = v != 0;
+    else if (k == "ns_level") c.noise_suppression.level = static_cast<AudioProcessing::Config::NoiseSuppression::Level>((int)v);
+    else if (k == "max_rate") c.pipeline.maximum_internal_processing_rate = (int)v;
+    else if (k == "mc_render") c.pipeline.multi_channel_render = v != 0;
+    else if (k == "mc_capture") c.pipeline.multi_channel_capture = v != 0;
+    else if (k == "downmix") c.pipeline.capture_downmix_method = static_cast<AudioProcessing::Config::Pipeline::DownmixMethod>((int)v);
+    else if (k == "hpf") c.high_pass_filter.enabled = v != 0;
+    else if (k == "hpf_full_band") c.high_pass_filter.apply_in_full_band = v != 0;
+    else if (k == "agc2") c.gain_controller2.enabled = v != 0;
+    else if (k == "agc2_gain_db") c.gain_controller2.fixed_digital.gain_db = (float)v;
+    else if (k == "agc2_adaptive") c.gain_controller2.adaptive_digital.enabled = v != 0;
+    else if (k == "pre_amp") c.pre_amplifier.enabled = v != 0;
+    else if (k == "pre_amp_gain") c.pre_amplifier.fixed_gain_factor = (float)v;
+    else if (k == "cla") c.capture_level_adjustment.enabled = v != 0;
+    else if (k == "cla_pre") c.capture_level_adjustment.pre_gain_factor = (float)v;
+    else if (k == "cla_post") c.capture_level_adjustment.post_gain_factor = (float)v;
+    else if (k == "ec3mc_default") { if (v != 0) out->ec3mc = webrtc::EchoCanceller3Config::CreateDefaultMultichannelConfig(); out->has_ec3 = true; }
+    else if (k.rfind("ec3mc.", 0) == 0) {
+      if (!out->ec3mc) out->ec3mc = webrtc::EchoCanceller3Config::CreateDefaultMultichannelConfig();
+      out->has_ec3 = true;
+      if (!SetEc3(*out->ec3mc, k.substr(6), v)) return false;
+    } else if (k.rfind("ec3.", 0) == 0) {
+      out->has_ec3 = true;
+      if (!SetEc3(out->ec3, k.substr(4), v)) return false;
+    } else return false;
+  }
+  return true;
+}
+}  // namespace
+extern "C" {
+
+void* ref_apm_create_kv(const char* text) {
+  KvConfig kv;
+  kv.apm = MakeConfig(1, 1, 1, 48000, 0, 0, 0);
+  if (!ParseKv(text, &kv)) return nullptr;
+  auto* h = new RefApm;
+  webrtc::Environment env = webrtc::CreateEnvironment();
+  webrtc::BuiltinAudioProcessingBuilder b(kv.apm);
+  if (kv.has_ec3) b.SetEchoCancellerConfig(kv.ec3, kv.ec3mc);
+  h->apm = b.Build(env);
+  return h;
+}
+
+// AudioProcessing::ApplyConfig with the current config updated by the given keys (APM keys only).
+int ref_apm_apply_kv(void* p, const char* text) {
+  auto* h = static_cast<RefApm*>(p);
+  KvConfig kv;
+  kv.apm = h->apm->GetConfig();
+  if (!ParseKv(text, &kv) || kv.has_ec3) return -1;
+  h->apm->ApplyConfig(kv.apm);
+  return 0;
+}
+
+// EchoCanceller3Config::Validate on the config the keys describe; writes the (possibly clamped)
+// value of `probe` back.  Returns 1 when the config was valid as given, 0 when it was changed.
+int ref_ec3_validate_kv(const char* text, const char* probe, double* probe_out) {
+  KvConfig kv;
+  if (!ParseKv(text, &kv)) return -1;
+  const bool ok = webrtc::EchoCanceller3Config::Validate(&kv.ec3);
+  if (probe && probe_out) {
+    // read back through the setter table: find the value v with SetEc3(copy, probe, v) leaving it unchanged
+    // is not possible generically, so expose a few representative fields
+    const std::string k(probe);
+    if (k == "filter.refined.length_blocks") *probe_out = kv.ec3.filter.refined.length_blocks;
+    else if (k == "delay.down_sampling_factor") *probe_out = kv.ec3.delay.down_sampling_factor;
+    else if (k == "erle.min") *probe_out = kv.ec3.erle.min;
+    else if (k == "erle.max_l") *probe_out = kv.ec3.erle.max_l;
+    else if (k == "suppressor.normal_tuning.max_inc_factor") *probe_out = kv.ec3.suppressor.normal_tuning.max_inc_factor;
+    else if (k == "filter.coarse.rate") *probe_out = kv.ec3.filter.coarse.rate;
+    else if (k == "delay.default_delay") *probe_out = kv.ec3.delay.default_delay;
+    else if (k == "filter.initial_state_seconds") *probe_out = kv.ec3.filter.initial_state_seconds;
+    else return -2;
+  }
+  return ok ? 1 : 0;
+}
+
 
 // One 10 ms tick on interleaved int16 frames: render then capture, exactly as
 // examples/run-offline.cpp:58-59 (+ set_stream_delay_ms(0)).

@@ -61,28 +61,11 @@ def run_legs(lib, rate, legs, stats_every=0, delay_ms=0, pipeline_chunks=None, *
     return out, st
 
 
-# ---- synthetic generator of SURVEY.md section 8(d) (xorshift64* as webrtc::Random)
-class WebRtcRandom:
-    """webrtc::Random (rtc_base/random.h:71-77, random.cc:52-56) restated."""
-
-    def __init__(self, seed):
-        self.state = seed & 0xFFFFFFFFFFFFFFFF
-
-    def next_output(self):
-        s = self.state
-        s ^= s >> 12
-        s ^= (s << 25) & 0xFFFFFFFFFFFFFFFF
-        s ^= s >> 27
-        self.state = s
-        return (s * 2685821657736338717) & 0xFFFFFFFFFFFFFFFF
-
-    def rand_float(self):
-        return float(self.next_output() - 1) / float(0xFFFFFFFFFFFFFFFE + 1)
-
-
+# ---- test signals (the bench workload generator is tests/synth.py + tools/wap_synth.c)
 def synthetic_leg(i, n_frames, rate=16000):
     """Render/capture int16 for stream i: gated white-noise render, 3-tap echo path with
-    per-stream delay, noise floor + double-talk bursts."""
+    per-stream delay, noise floor + double-talk bursts (the shape of SURVEY.md section 8d, drawn
+    from numpy's generator; parity-test signal only -- bench.py uses tests/synth.py)."""
     n = n_frames * rate // 100
     rng_r = np.random.default_rng(1000 + 2 * i)
     rng_n = np.random.default_rng(1001 + 2 * i)

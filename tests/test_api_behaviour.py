@@ -1,4 +1,4 @@
-"""The seam's contract exercised on the emulator build of the product sources:
+"""The seam's contract exercised on the emulator build of the product sources and on the GPU build:
 error codes, delay clamp, mute / un-mute, single-leg entry points, int16 / float equivalence.
 Mirrors the reference's APM API tests (tests/unit/audio_processing_unittest.cc,
 audio_processing_impl_unittest.cc) for the part of the surface the seam forwards."""
@@ -10,6 +10,14 @@ import pytest
 
 from common import golden, synthetic_leg
 
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def api_lib(request):
+    """Every test of this file runs twice: on the emulator build of the product sources (CPU box) and,
+    marked gpu, on libwap_b200.so itself through the same C ABI."""
+    return request.getfixturevalue("emu_lib" if request.param == "emu" else "gpu_lib")
+
+
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 TOL = 1e-4 * 32768
 
@@ -18,9 +26,9 @@ def _sc(wap_b200, rate, ch=1):
     return wap_b200.WapStreamConfig(rate, ch)
 
 
-def test_error_codes_and_delay_clamp(emu_lib):
+def test_error_codes_and_delay_clamp(api_lib):
     import wap_b200
-    L = emu_lib
+    L = api_lib
     h = L.wap_create()
     assert h
     x = np.zeros(160, np.int16)
@@ -43,11 +51,11 @@ def test_error_codes_and_delay_clamp(emu_lib):
     L.wap_destroy(h)
 
 
-def test_single_leg_entry_points_match_the_reference(emu_lib, oracle):
+def test_single_leg_entry_points_match_the_reference(api_lib, oracle):
     """wap_process_reverse_stream_i16 + wap_set_stream_delay_ms + wap_process_stream_i16 on one
     handle (what RustAudioProcessing forwards) == the reference, including GetStatistics."""
     import wap_b200
-    L = emu_lib
+    L = api_lib
     far, near = synthetic_leg(9, 120)
     ref_out, ref_stats, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near, stats_every=40)
     assert err == 0
@@ -78,12 +86,12 @@ def test_single_leg_entry_points_match_the_reference(emu_lib, oracle):
     assert np.array_equal(stats[:, 2], ref_stats[:, 5])
 
 
-def test_float_and_int16_entry_points_agree(emu_lib):
+def test_float_and_int16_entry_points_agree(api_lib):
     import wap_b200
     far, near = synthetic_leg(4, 60)
     outs = []
     for dt in (np.int16, np.float32):
-        eng = wap_b200.Engine(1, 16000, lib=emu_lib, aec=True, ns=True, ns_level=1)
+        eng = wap_b200.Engine(1, 16000, lib=api_lib, aec=True, ns=True, ns_level=1)
         o = []
         for f in range(60):
             r = far[f * 160:(f + 1) * 160][None, :]
@@ -99,13 +107,13 @@ def test_float_and_int16_entry_points_agree(emu_lib):
     assert np.abs(outs[0] - outs[1]).max() <= 0.5 + 1e-3
 
 
-def test_mute_unmute_matches_reference(emu_lib, oracle):
+def test_mute_unmute_matches_reference(api_lib, oracle):
     """set_output_will_be_muted: AEC3 skips the suppressor, NS its synthesis, and the first frame
     after un-muting is zeroed (audio_processing_impl.cc:818-838,1450,1540-1552)."""
     import wap_b200
     far, near = synthetic_leg(2, 90)
     ref = oracle.RefApm(aec=True, ns=True, ns_level=1)
-    eng = wap_b200.Engine(2, 16000, lib=emu_lib, aec=True, ns=True, ns_level=1)
+    eng = wap_b200.Engine(2, 16000, lib=api_lib, aec=True, ns=True, ns_level=1)
     ref_out = np.zeros_like(near)
     out = np.zeros((2, near.size), np.int16)
     for f in range(90):
@@ -127,11 +135,11 @@ def test_mute_unmute_matches_reference(emu_lib, oracle):
     assert not np.array_equal(out[0], out[1])                  # the flag is per leg
 
 
-def test_legs_joining_later_and_slot_reuse(emu_lib, oracle):
+def test_legs_joining_later_and_slot_reuse(api_lib, oracle):
     """Ragged batches: legs created on different ticks run different 2/3-block cadences inside the
     same launch; a destroyed leg's arena slot is re-initialised for the next leg."""
     import wap_b200
-    L = emu_lib
+    L = api_lib
     nf = 50
     legs = [synthetic_leg(i, nf) for i in range(3)]
     refs = []
@@ -183,50 +191,50 @@ def test_legs_joining_later_and_slot_reuse(emu_lib, oracle):
 
 
 @pytest.mark.parametrize("level", [0, 3])
-def test_ns_levels_low_and_very_high(emu_lib, oracle, level):
+def test_ns_levels_low_and_very_high(api_lib, oracle, level):
     """NoiseSuppression kLow / kVeryHigh (suppression_params.cc:18-48); kModerate / kHigh are covered
     by the parity tests."""
     from common import run_engine
     near = golden("speech_16k.npz")["near"][:120 * 160]
     ref_out, _, err = oracle.RefApm(aec=False, ns=True, ns_level=level).run_i16(16000, None, near)
     assert err == 0
-    out = run_engine(emu_lib, 16000, None, near, n_streams=1, aec=False, ns=True, ns_level=level)
+    out = run_engine(api_lib, 16000, None, near, n_streams=1, aec=False, ns=True, ns_level=level)
     assert np.abs(out.reshape(-1).astype(np.int32) - ref_out.astype(np.int32)).max() <= TOL
 
 
-def test_pipelined_host_tick_matches_plain(emu_lib, oracle):
+def test_pipelined_host_tick_matches_plain(api_lib, oracle):
     """wap_engine_set_pipeline_chunks: cutting the batch into leg ranges (ragged last range)
     changes nothing in the output."""
     import wap_b200
     from common import run_legs
     legs = [synthetic_leg(i, 30) for i in range(11)]
-    ref, _ = run_legs(emu_lib, 16000, legs, pipeline_chunks=1, aec=True, ns=True, ns_level=1)
-    out, _ = run_legs(emu_lib, 16000, legs, pipeline_chunks=3, aec=True, ns=True, ns_level=1)
+    ref, _ = run_legs(api_lib, 16000, legs, pipeline_chunks=1, aec=True, ns=True, ns_level=1)
+    out, _ = run_legs(api_lib, 16000, legs, pipeline_chunks=3, aec=True, ns=True, ns_level=1)
     assert np.array_equal(ref, out)
     far, near = legs[10]
     ref_out, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)
     assert err == 0 and np.array_equal(out[10], ref_out[:out[10].size])
-    eng = wap_b200.Engine(2, 16000, lib=emu_lib, aec=True, ns=False)
+    eng = wap_b200.Engine(2, 16000, lib=api_lib, aec=True, ns=False)
     with pytest.raises(RuntimeError):
         eng.set_pipeline_chunks(99)
     eng.close()
 
 
-def test_rates_and_unsupported_formats(emu_lib):
+def test_rates_and_unsupported_formats(api_lib):
     """Mono engines exist for every API rate up to 48 kHz that has whole 10 ms frames (native 16 / 32 /
     48 kHz, the others through the sinc resamplers); true multi-channel processing and rates above 48 kHz are outside
     the built scope and are refused, not approximated."""
     import wap_b200
     for rate, max_rate in ((16000, 32000), (32000, 32000), (48000, 48000), (48000, 32000), (8000, 32000),
                            (44100, 32000), (24000, 48000)):
-        eng = wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True, max_rate=max_rate)
+        eng = wap_b200.Engine(1, rate, lib=api_lib, aec=True, ns=True, max_rate=max_rate)
         x = np.zeros((1, rate // 100), np.int16)
         assert eng.process(x, x).shape == (1, rate // 100)
         eng.close()
     for rate in (96000, 22050):
         with pytest.raises(RuntimeError):
-            wap_b200.Engine(1, rate, lib=emu_lib, aec=True, ns=True)
-    eng = wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=True, ns=True)  # stereo in/out, mono processing
+            wap_b200.Engine(1, rate, lib=api_lib, aec=True, ns=True)
+    eng = wap_b200.Engine(1, 48000, channels=2, lib=api_lib, aec=True, ns=True)  # stereo in/out, mono processing
     x = np.zeros((1, 960), np.int16)
     assert eng.process(x, x).shape == (1, 960)
     eng.close()
@@ -236,7 +244,7 @@ def test_rates_and_unsupported_formats(emu_lib):
     (16000, 32000, dict(aec=True, ns=True, ns_level=1)),
     (48000, 32000, dict(aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=6.0, pre_gain=1.5, post_gain=0.8)),
 ])
-def test_stream_state_export_import(emu_lib, oracle, rate, max_rate, kw):
+def test_stream_state_export_import(api_lib, oracle, rate, max_rate, kw):
     """Stream lifecycle: a leg exported in the middle of a call and imported into a leg of another
     engine continues bit-identically (output and statistics); a blob does not fit another config."""
     import wap_b200
@@ -253,14 +261,14 @@ def test_stream_state_export_import(emu_lib, oracle, rate, max_rate, kw):
         r[slot] = far[f * fl:(f + 1) * fl]; c[slot] = near[f * fl:(f + 1) * fl]
         return eng.process(r, c)[slot]
 
-    a = wap_b200.Engine(1, rate, lib=emu_lib, max_rate=max_rate, **kw)
+    a = wap_b200.Engine(1, rate, lib=api_lib, max_rate=max_rate, **kw)
     out = np.zeros(nf * fl, np.int16)
     for f in range(cut):
         out[f * fl:(f + 1) * fl] = tick(a, f)
     a.set_playout_volume(120)           # a pending runtime setting travels with the leg
     blob = a.export_state(0)
     a.close()
-    b = wap_b200.Engine(3, rate, lib=emu_lib, max_rate=max_rate, **kw)   # another engine, another slot
+    b = wap_b200.Engine(3, rate, lib=api_lib, max_rate=max_rate, **kw)   # another engine, another slot
     b.import_state(blob, 2)
     for f in range(cut, nf):
         out[f * fl:(f + 1) * fl] = tick(b, f, slot=2)
@@ -274,13 +282,13 @@ def test_stream_state_export_import(emu_lib, oracle, rate, max_rate, kw):
         ro[f * fl:(f + 1) * fl] = o
     assert np.array_equal(out, ro)
     assert abs(st.echo_return_loss_enhancement - float(ref2.stats()[3])) <= 1e-6
-    other = wap_b200.Engine(1, rate, lib=emu_lib, max_rate=max_rate, aec=True, ns=False)
+    other = wap_b200.Engine(1, rate, lib=api_lib, max_rate=max_rate, aec=True, ns=False)
     with pytest.raises(RuntimeError):
         other.import_state(blob, 0)
     other.close(); b.close()
 
 
-def test_stage_taps_match_reference_dumps(emu_lib, tmp_path):
+def test_stage_taps_match_reference_dumps(api_lib, tmp_path):
     """wap_stream_read_taps against the reference's own ApmDataDumper output (the dump variant of the
     compiled reference, -DWEBRTC_APM_DEBUG_DUMP=1, run in a helper process): the taps after the last
     block equal the last records of the reference's tap files bit for bit."""
@@ -295,7 +303,7 @@ def test_stage_taps_match_reference_dumps(emu_lib, tmp_path):
     subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dump_ref_taps.py"), str(tmp_path), str(nf), str(leg)],
                    check=True)
     far, near = synthetic_leg(leg, nf)
-    eng = wap_b200.Engine(1, 16000, lib=emu_lib, max_rate=32000, aec=True, ns=True, ns_level=1)
+    eng = wap_b200.Engine(1, 16000, lib=api_lib, max_rate=32000, aec=True, ns=True, ns_level=1)
     for f in range(nf):
         eng.set_stream_delay_ms(0)
         eng.process(far[f * 160:(f + 1) * 160].reshape(1, 160), near[f * 160:(f + 1) * 160].reshape(1, 160))
@@ -320,3 +328,205 @@ def test_stage_taps_match_reference_dumps(emu_lib, tmp_path):
     assert t.aec3_capture_saturation == last("aec3_capture_saturation", 1, np.int32)[0]
     assert np.all(np.array(t.ns_noise_spectrum) > 0) and 0.0 <= t.ns_prior_speech_probability <= 1.0
     assert np.all((np.array(t.ns_filter) >= 0.0) & (np.array(t.ns_filter) <= 1.0))
+
+
+def _drive_single(L, wap_b200, h, far, near, f0, f1, out):
+    """ProcessReverseStream + set_stream_delay_ms(0) + ProcessStream on one handle, frames [f0, f1)."""
+    sc = _sc(wap_b200, 16000)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    scratch = np.zeros(160, np.int16)
+    for f in range(f0, f1):
+        r = np.ascontiguousarray(far[f * 160:(f + 1) * 160])
+        c = np.ascontiguousarray(near[f * 160:(f + 1) * 160])
+        o = np.zeros(160, np.int16)
+        assert L.wap_process_reverse_stream_i16(h, p(r), 160, sc, sc, p(scratch), 160) == 0
+        assert L.wap_set_stream_delay_ms(h, 0) == 0
+        assert L.wap_process_stream_i16(h, p(c), 160, sc, sc, p(o), 160) == 0
+        out[f * 160:(f + 1) * 160] = o
+
+
+def test_apply_config_mid_call_matches_reference(api_lib, oracle):
+    """ApplyConfig in the middle of a call (audio_processing_impl.cc:694-771): a new NS level rebuilds
+    only the noise suppressor and a new AGC2 gain only GainController2 -- AEC3 keeps its converged
+    filters -- while toggling a submodule re-initialises everything.  Bit-compared with the reference
+    driven through the same ApplyConfig calls."""
+    import wap_b200
+    L = api_lib
+    nf = 260
+    far, near = synthetic_leg(5, nf)
+    ref = oracle.RefApm(kv=dict(aec=1, ns=1, ns_level=1, max_rate=48000, agc2=1, agc2_gain_db=3.0))
+    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1, agc2=True, agc2_fixed_gain_db=3.0))
+    out = np.zeros_like(near)
+    ref_out = np.zeros_like(near)
+    steps = [(0, 120, None), (120, 170, dict(ns_level=2)), (170, 215, dict(agc2_gain_db=9.0)), (215, nf, dict(ns=0))]
+    for f0, f1, change in steps:
+        if change:
+            ref.apply_config(**change)
+            cfg = wap_b200.WapConfig()
+            assert L.wap_get_config(h, C.byref(cfg)) == 0
+            if "ns_level" in change:
+                cfg.noise_suppression_level = int(change["ns_level"])
+            if "agc2_gain_db" in change:
+                cfg.gain_controller2_fixed_digital_gain_db = change["agc2_gain_db"]
+            if "ns" in change:
+                cfg.noise_suppression_enabled = bool(change["ns"])
+            assert L.wap_apply_config(h, cfg) == 0
+        _drive_single(L, wap_b200, h, far, near, f0, f1, out)
+        o, _, err = ref.run_i16(16000, far[f0 * 160:f1 * 160], near[f0 * 160:f1 * 160])
+        assert err == 0
+        ref_out[f0 * 160:f1 * 160] = o
+    L.wap_destroy(h)
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32))
+    assert d.max() == 0, (int(d.max()), int(np.argmax(d)) // 160)
+
+
+def test_apply_config_with_an_identical_config_keeps_all_state(api_lib):
+    """A logically identical WapConfig whose padding bytes differ (a C caller that fills the struct
+    field by field) must not reset anything."""
+    import wap_b200
+    L = api_lib
+    far, near = synthetic_leg(6, 100)
+    outs = []
+    for reapply in (False, True):
+        h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+        out = np.zeros_like(near)
+        _drive_single(L, wap_b200, h, far, near, 0, 60, out)
+        if reapply:
+            cur = wap_b200.WapConfig()
+            assert L.wap_get_config(h, C.byref(cur)) == 0
+            dirty = wap_b200.WapConfig()
+            C.memset(C.byref(dirty), 0xA5, C.sizeof(dirty))       # garbage in the padding
+            for name, _ in wap_b200.WapConfig._fields_:
+                setattr(dirty, name, getattr(cur, name))
+            assert bytes(dirty) != bytes(cur)
+            assert L.wap_apply_config(h, dirty) == 0
+        _drive_single(L, wap_b200, h, far, near, 60, 100, out)
+        L.wap_destroy(h)
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_render_format_differing_from_capture_is_refused_not_reinterpreted(api_lib):
+    """Render at 48 kHz with capture at 16 kHz is the reference's MaybeInitializeRender case, which this
+    engine does not build: it must be refused (UnsupportedConfig) without touching the engine -- the
+    call's AEC3 / NS state survives and nothing is copied into a buffer of another size."""
+    import wap_b200
+    L = api_lib
+    far, near = synthetic_leg(7, 80)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ref_run = np.zeros_like(near)
+    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+    _drive_single(L, wap_b200, h, far, near, 0, 80, ref_run)
+    L.wap_destroy(h)
+    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+    out = np.zeros_like(near)
+    _drive_single(L, wap_b200, h, far, near, 0, 40, out)
+    big = np.zeros(480, np.int16)
+    sc48 = _sc(wap_b200, 48000)
+    for _ in range(3):
+        assert L.wap_process_reverse_stream_i16(h, p(big), 480, sc48, sc48, p(big), 480) == 7   # UnsupportedConfig
+    _drive_single(L, wap_b200, h, far, near, 40, 80, out)
+    assert np.array_equal(out, ref_run)            # the refused calls changed nothing
+    sc16 = _sc(wap_b200, 16000)
+    assert L.wap_initialize(h, sc16, sc16, sc48, sc48) == 7
+    L.wap_destroy(h)
+    # render first, at a format the later capture stream does not have: refused at the capture call
+    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+    assert L.wap_process_reverse_stream_i16(h, p(big), 480, sc48, sc48, p(big), 480) == 0
+    o = np.zeros(160, np.int16)
+    assert L.wap_process_stream_i16(h, p(near[:160].copy()), 160, sc16, sc16, p(o), 160) == 7
+    assert L.wap_process_stream_i16(h, p(near[:160].copy()), 160, sc16, sc16, p(o), 160) == 0   # queue was dropped
+    L.wap_destroy(h)
+
+
+def test_process_streams_rejects_engine_less_and_duplicate_handles(api_lib):
+    import wap_b200
+    L = api_lib
+    h = L.wap_create()
+    hs = (C.c_void_p * 1)(h)
+    x = np.zeros(160, np.int16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.wap_process_streams(hs, 1, None, p(x), p(x), 0, None) == 5       # BadStreamParameter, no crash
+    L.wap_destroy(h)
+    eng = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=True)
+    dup = (C.c_void_p * 2)(eng.handles[0], eng.handles[0])
+    x2 = np.zeros((2, 160), np.int16)
+    assert L.wap_process_streams(dup, 2, p(x2), p(x2), p(x2.copy()), 0, None) == 5
+    assert eng.process(x2, x2).shape == (2, 160)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_render_and_capture_threads_on_one_handle(gpu_lib, oracle):
+    """The render thread (ProcessReverseStream) and the capture thread (everything else) drive one
+    handle at the same time, as webrtc::AudioProcessing allows: the reverse call only enqueues, the
+    capture side owns the engine.  Frames are handed over in lock step so the result is comparable."""
+    import threading
+    import wap_b200
+    L = gpu_lib
+    nf = 60
+    far, near = synthetic_leg(8, nf)
+    ref_out, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)
+    assert err == 0
+    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+    sc = _sc(wap_b200, 16000)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rendered = [threading.Event() for _ in range(nf)]
+    captured = [threading.Event() for _ in range(nf)]
+    errs = []
+
+    def render_thread():
+        scratch = np.zeros(160, np.int16)
+        for f in range(nf):
+            if f:
+                captured[f - 1].wait()
+            r = np.ascontiguousarray(far[f * 160:(f + 1) * 160])
+            errs.append(L.wap_process_reverse_stream_i16(h, p(r), 160, sc, sc, p(scratch), 160))
+            rendered[f].set()
+
+    out = np.zeros_like(near)
+    t = threading.Thread(target=render_thread)
+    t.start()
+    for f in range(nf):
+        rendered[f].wait()
+        c = np.ascontiguousarray(near[f * 160:(f + 1) * 160])
+        o = np.zeros(160, np.int16)
+        L.wap_set_stream_delay_ms(h, 0)
+        errs.append(L.wap_process_stream_i16(h, p(c), 160, sc, sc, p(o), 160))
+        out[f * 160:(f + 1) * 160] = o
+        captured[f].set()
+    t.join()
+    L.wap_destroy(h)
+    assert not any(errs)
+    assert np.array_equal(out, ref_out)
+
+
+def test_reference_seam_class_runs_on_this_library(api_lib, oracle):
+    """The reference's own alternate-backend class, webrtc::RustAudioProcessing
+    (modules/audio_processing/rust_audio_processing.cc, compiled unmodified against
+    include/wap_audio_processing.h by oracle/build_ref.py), linked at load time against this library's
+    wap_* symbols and driven through the loop of examples/run-offline.cpp: its output must be the
+    output of the reference's built-in implementation."""
+    import build_ref
+    seam_path = build_ref.build_seam(verbose=False)
+    # the implementation under test provides the wap_* symbols the seam library leaves undefined
+    C.CDLL(api_lib._name, mode=C.RTLD_GLOBAL)
+    glob = C.CDLL(None)
+    if C.cast(glob.wap_create, C.c_void_p).value != C.cast(api_lib.wap_create, C.c_void_p).value:
+        pytest.skip("another implementation's wap_* symbols are already global in this process "
+                    "(emulator and GPU builds in one pytest run); run with -m gpu or -m 'not gpu'")
+    S = C.CDLL(seam_path)
+    S.seam_run_offline_i16.argtypes = [C.c_int] * 5 + [C.c_float] + [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    nf = 130
+    far, near = synthetic_leg(12, nf)
+    for kw in (dict(aec=True, ns=True, ns_level=1), dict(aec=True, ns=True, ns_level=2, agc2=True, agc2_fixed_gain_db=4.0)):
+        ref_out, ref_stats, err = oracle.RefApm(**kw).run_i16(16000, far, near, stats_every=65)
+        assert err == 0
+        out = np.zeros_like(near)
+        stats = np.zeros((2, 3), np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = S.seam_run_offline_i16(1, 1, kw["ns_level"], 48000, int(kw.get("agc2", False)), float(kw.get("agc2_fixed_gain_db", 0.0)),
+                                    16000, 1, nf, p(far), p(near), p(out), 65, p(stats))
+        assert rc == 0, rc
+        assert np.array_equal(out, ref_out)
+        assert np.abs(stats[:, 1] - ref_stats[:, 3]).max() <= 0.1 and np.array_equal(stats[:, 2], ref_stats[:, 5])

@@ -440,3 +440,24 @@ def test_bench_reference_arm_contract(oracle):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_synthetic_generator_c_equals_numpy_restatement():
+    """tools/wap_synth.c (what both bench arms use) against the numpy restatement of the same
+    SURVEY 8(d) generator (xorshift64* as webrtc::Random, gated render, circular 3-tap echo path)."""
+    import synth
+    if synth._load() is None:
+        pytest.skip("no C compiler / prebuilt generator")
+    for kind, rate in ((0, 16000), (0, 48000), (1, 48000)):
+        a = synth.cycle(kind, rate, 37, 5, 110)
+        b = synth.cycle(kind, rate, 37, 5, 110, force_numpy=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    r, c = synth.cycle(0, 16000, 0, 2, 200)
+    r = r.transpose(1, 0, 2).reshape(2, -1)
+    assert np.all(r[:, 14400:16000] == 0) and np.abs(r[:, :14400]).max() > 7000   # 0.9 s on / 0.1 s off
+    assert len(np.unique(r[0, :1000])) > 900 and not np.array_equal(r[0], r[1])
+    # webrtc::Random known answers: first outputs of seed 1000 (xorshift64*, shifts 12/25/27)
+    v = synth._VecRandom([1000])
+    s = 1000
+    s ^= s >> 12; s ^= (s << 25) & (2**64 - 1); s ^= s >> 27
+    assert int(v.s[0]) == 1000 and abs(float(v.rand_float()[0]) - ((s * 2685821657736338717) % 2**64 - 1) / (2**64 - 1)) < 1e-7

@@ -307,3 +307,12 @@ def test_bench_line_contract(gpu_lib):
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["kernel"] in ("k_echo", "k_delay") and 0 < rf["frac"] < 1 and rf["peak"] > 1000
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+    # steady state by construction, and the timed batch is checked against the compiled reference
+    assert d["config"]["settle_ticks"] >= 300
+    pc = d["parity_spot_check"]
+    assert pc["legs"] == 16 and pc["pass"] and pc["max_abs_diff_lsb"] == 0, pc
+    assert "profile-derived" in (rf["traffic_source"] or "profile-derived")
+    names = [o["name"] for o in d["other_configs"]]
+    assert any("config 3" in n for n in names) and any("config 5" in n for n in names)
+    for o in d["other_configs"]:
+        assert o["value"] > 0 and o["e2e"]["value"] > 0 and o["parity_spot_check"]["pass"], o

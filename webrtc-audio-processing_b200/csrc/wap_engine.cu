@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <deque>
 #include <mutex>
 #include <new>
@@ -131,7 +132,9 @@ struct WapEngine {
   StreamState* d_template = nullptr;
   cudaStream_t stream = nullptr;
   std::vector<int> free_slots;
-  std::mutex mu;
+  // Guards every member below and the engine's stream: tick, create / destroy and the per-leg
+  // setters that touch engine state take it (recursive: the host-buffer tick calls the device tick).
+  std::recursive_mutex mu;
   // staging for the host-buffer entry points
   void* d_render = nullptr;
   void* d_capture = nullptr;
@@ -145,7 +148,7 @@ struct WapEngine {
   // per-leg host state indexed by slot, so the per-tick bookkeeping walks contiguous memory
   std::vector<int> leg_delay_ms;            // last set_stream_delay_ms value
   std::vector<unsigned char> leg_delay_set; // was_stream_delay_set (cleared by every capture frame)
-  int dirty_legs = 0;                       // handles whose capture_output_used is not yet in the slab
+  std::atomic<int> dirty_legs{0};           // handles whose capture_output_used is not yet in the slab
   int64_t launches = 0;
   int frame_len = 0;  // samples per frame (all channels)
   int echo_scratch_floats = 0;
@@ -189,7 +192,13 @@ struct WapAudioProcessing {
   int analog_level = 0;
   std::deque<std::vector<unsigned char>> render_queue;  // SwapQueue stand-in (aec3_common.h:41)
   WapSampleFormat render_fmt = WapSampleFormat::I16;
+  WapStreamConfig render_format{0, 0};  // format of the queued render frames
   std::mutex render_mu;
+  // Capture-side lock of a single-leg handle (webrtc::AudioProcessing's mutex_capture_): engine
+  // creation, ApplyConfig, Initialize, the setters and ProcessStream serialise on it; the render
+  // thread only ever takes render_mu (ProcessReverseStream enqueues and returns).
+  std::recursive_mutex mu;
+  bool skip_first_reinit = false;  // the next private engine starts "already initialised" (ApplyConfig / Initialize ran InitializeLocked)
   bool owns_engine = false;
   WapStats cached_stats{};  // ApmStatsReporter::cached_stats_
 };
@@ -255,6 +264,12 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
       (c.gain_controller2_adaptive_digital_enabled || c.gain_controller2_input_volume_controller_enabled))
     return WapError::UnsupportedConfig;
   e.sample_rate_hz = proc;
+  // high_pass_filter.apply_in_full_band = false moves the filter onto split band 0 with the 16 kHz
+  // coefficients (audio_processing_impl.cc:1283,1376,1890): not built -- refused rather than approximated.
+  if (!c.high_pass_filter_apply_in_full_band && e.num_bands > 1 &&
+      (c.high_pass_filter_enabled || c.noise_suppression_enabled ||
+       (c.echo_canceller_enabled && c.echo_canceller_enforce_high_pass_filtering)))
+    return WapError::UnsupportedConfig;
   e.aec_enabled = c.echo_canceller_enabled;
   e.ns_enabled = c.noise_suppression_enabled;
   // InitializeHighPassFilter (audio_processing_impl.cc:1883-1907)
@@ -284,29 +299,36 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
 WapError ensure_staging(WapEngine* e, size_t n) {
   if (n <= e->staged_streams) return WapError::None;
   size_t cap = std::max<size_t>(n, std::min<size_t>((size_t)e->capacity, std::max<size_t>(64, 2 * e->staged_streams)));
-  if (e->d_render) cudaFree(e->d_render);
-  if (e->d_capture) cudaFree(e->d_capture);
-  if (e->d_out) cudaFree(e->d_out);
-  if (e->d_slots) cudaFree(e->d_slots);
-  if (e->d_delays) cudaFree(e->d_delays);
-  if (e->h_pinned) cudaFreeHost(e->h_pinned);
   const size_t fb = (size_t)e->frame_len * sizeof(float);
-  WAP_CUDA(cudaMalloc(&e->d_render, cap * fb));
-  WAP_CUDA(cudaMalloc(&e->d_capture, cap * fb));
-  WAP_CUDA(cudaMalloc(&e->d_out, cap * fb));
-  WAP_CUDA(cudaMalloc((void**)&e->d_slots, cap * sizeof(int)));
-  WAP_CUDA(cudaMalloc((void**)&e->d_delays, cap * sizeof(int)));
-  WAP_CUDA(cudaMallocHost(&e->h_pinned, cap * (3 * fb + 2 * sizeof(int))));
+  const size_t pb = (size_t)wap::kFrame * e->cfg.num_bands * sizeof(float);
+  // Allocate the new buffers first and swap them in only when every allocation succeeded: a failure
+  // leaves the engine with its old (smaller) staging area instead of dangling pointers.
+  void *n_render = nullptr, *n_capture = nullptr, *n_out = nullptr, *n_pinned = nullptr;
+  int *n_slots = nullptr, *n_delays = nullptr;
+  float *n_rs_render = nullptr, *n_rs_capture = nullptr, *n_rs_capture1 = nullptr;
+  bool ok = cudaMalloc(&n_render, cap * fb) == cudaSuccess && cudaMalloc(&n_capture, cap * fb) == cudaSuccess &&
+            cudaMalloc(&n_out, cap * fb) == cudaSuccess && cudaMalloc((void**)&n_slots, cap * sizeof(int)) == cudaSuccess &&
+            cudaMalloc((void**)&n_delays, cap * sizeof(int)) == cudaSuccess &&
+            cudaMallocHost(&n_pinned, cap * (3 * fb + 2 * sizeof(int))) == cudaSuccess;
+  if (ok && e->cfg.resample) {
+    ok = cudaMalloc((void**)&n_rs_render, cap * pb) == cudaSuccess && cudaMalloc((void**)&n_rs_capture, cap * pb) == cudaSuccess;
+    if (ok && e->cfg.channels == 2) ok = cudaMalloc((void**)&n_rs_capture1, cap * pb) == cudaSuccess;
+  }
+  if (!ok) {
+    fprintf(stderr, "[wap_b200] staging allocation for %zu legs failed: %s\n", cap, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(n_render); cudaFree(n_capture); cudaFree(n_out); cudaFree(n_slots); cudaFree(n_delays);
+    if (n_pinned) cudaFreeHost(n_pinned);
+    cudaFree(n_rs_render); cudaFree(n_rs_capture); cudaFree(n_rs_capture1);
+    return WapError::Internal;
+  }
+  cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_render); cudaFree(e->d_capture); cudaFree(e->d_out); cudaFree(e->d_slots); cudaFree(e->d_delays);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  e->d_render = n_render; e->d_capture = n_capture; e->d_out = n_out; e->d_slots = n_slots; e->d_delays = n_delays;
+  e->h_pinned = n_pinned;
   if (e->cfg.resample) {
-    if (e->d_rs_render) cudaFree(e->d_rs_render);
-    if (e->d_rs_capture) cudaFree(e->d_rs_capture);
-    const size_t pb = (size_t)wap::kFrame * e->cfg.num_bands * sizeof(float);
-    WAP_CUDA(cudaMalloc((void**)&e->d_rs_render, cap * pb));
-    WAP_CUDA(cudaMalloc((void**)&e->d_rs_capture, cap * pb));
-    if (e->cfg.channels == 2) {
-      if (e->d_rs_capture1) cudaFree(e->d_rs_capture1);
-      WAP_CUDA(cudaMalloc((void**)&e->d_rs_capture1, cap * pb));
-    }
+    cudaFree(e->d_rs_render); cudaFree(e->d_rs_capture); cudaFree(e->d_rs_capture1);
+    e->d_rs_render = n_rs_render; e->d_rs_capture = n_rs_capture; e->d_rs_capture1 = n_rs_capture1;
   }
   e->staged_streams = cap;
   e->last_slots.clear();
@@ -598,7 +620,7 @@ void wap_engine_destroy(WapEngine* e) {
 
 WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing** out) {
   if (!e || !out) return WapError::NullPointer;
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   if (n <= 0 || (size_t)n > e->free_slots.size()) return WapError::BadStreamParameter;
   WAP_CUDA(cudaSetDevice(e->device));
   std::vector<int> slots(n);
@@ -607,20 +629,29 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
     e->free_slots.pop_back();
   }
   int* d_slots = nullptr;
-  WAP_CUDA(cudaMalloc((void**)&d_slots, (size_t)n * sizeof(int)));
-  WAP_CUDA(cudaMemcpy(d_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
-  WAP_LAUNCH(wap::k_init_slots, dim3(16, std::min(n, 4096)), 256, 0, e->stream, e->d_states,
-             (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
-  if (e->d_upper)
-    for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
-  if (e->d_extra)
-    for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_extra[slots[i]], 0, sizeof(wap::ExtraChannelState), e->stream));
-  if (e->d_rs)
-    for (int i = 0; i < n; ++i)
-      WAP_CUDA(cudaMemsetAsync(&e->d_rs[(size_t)slots[i] * wap::kRsPerLeg], 0, wap::kRsPerLeg * sizeof(wap::ResamplerState), e->stream));
-  e->launches++;
-  WAP_CUDA(cudaStreamSynchronize(e->stream));
+  // Any CUDA failure below hands the slots back and frees the scratch list.
+  auto init = [&]() -> WapError {
+    WAP_CUDA(cudaMalloc((void**)&d_slots, (size_t)n * sizeof(int)));
+    WAP_CUDA(cudaMemcpy(d_slots, slots.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    WAP_LAUNCH(wap::k_init_slots, dim3(16, std::min(n, 4096)), 256, 0, e->stream, e->d_states,
+               (const StreamState*)e->d_template, (const int*)d_slots, (int)n);
+    if (e->d_upper)
+      for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
+    if (e->d_extra)
+      for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_extra[slots[i]], 0, sizeof(wap::ExtraChannelState), e->stream));
+    if (e->d_rs)
+      for (int i = 0; i < n; ++i)
+        WAP_CUDA(cudaMemsetAsync(&e->d_rs[(size_t)slots[i] * wap::kRsPerLeg], 0, wap::kRsPerLeg * sizeof(wap::ResamplerState), e->stream));
+    e->launches++;
+    WAP_CUDA(cudaStreamSynchronize(e->stream));
+    return WapError::None;
+  };
+  const WapError init_err = init();
   cudaFree(d_slots);
+  if (init_err != WapError::None) {
+    for (int i = n - 1; i >= 0; --i) e->free_slots.push_back(slots[i]);
+    return init_err;
+  }
   e->last_handles.clear();
   for (int i = 0; i < n; ++i) {
     e->leg_delay_ms[slots[i]] = 0;
@@ -664,6 +695,13 @@ static WapError prepare_tick(WapEngine* e, WapAudioProcessing* const* handles, i
   if (!same) {
     for (int i = 0; i < n; ++i)
       if (!handles[i] || handles[i]->engine != e) return WapError::BadStreamParameter;
+    // Two entries for one leg would let two warps update the same state slab.
+    std::vector<unsigned char> seen(e->capacity, 0);
+    for (int i = 0; i < n; ++i) {
+      const int sl = handles[i]->slot;
+      if (sl < 0 || sl >= e->capacity || seen[sl]) return WapError::BadStreamParameter;
+      seen[sl] = 1;
+    }
     e->last_slots.resize(n);
     for (int i = 0; i < n; ++i) e->last_slots[i] = handles[i]->slot;
     e->last_handles.assign(handles, handles + n);
@@ -718,11 +756,18 @@ static WapError prepare_tick(WapEngine* e, WapAudioProcessing* const* handles, i
 WapError wap_process_streams_device(WapEngine* e, WapAudioProcessing* const* handles, int32_t n,
                                     const void* d_render, const void* d_capture, void* d_out,
                                     WapSampleFormat fmt) {
+  if (!e) return WapError::NullPointer;
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   const int* d_delays = nullptr;
   int uniform_delay = -1;
   WapError err = prepare_tick(e, handles, n, &d_delays, &uniform_delay);
   if (err != WapError::None) return err;
-  return launch_tick(e, e->d_slots, d_delays, uniform_delay, n, d_render, d_capture, d_out, fmt);
+  err = launch_tick(e, e->d_slots, d_delays, uniform_delay, n, d_render, d_capture, d_out, fmt);
+  // was_stream_delay_set is one-shot: every capture frame clears it (audio_processing_impl.cc:1556),
+  // through this entry point as through the host-buffer one.
+  if (d_capture)
+    for (int i = 0; i < n; ++i) e->leg_delay_set[e->last_slots[i]] = 0;
+  return err;
 }
 
 WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, const void* render,
@@ -730,6 +775,8 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
   if (!handles || !capture || !out) return WapError::NullPointer;
   if (n <= 0 || !handles[0]) return WapError::BadStreamParameter;
   WapEngine* e = handles[0]->engine;
+  if (!e) return WapError::BadStreamParameter;  // a wap_create() handle that has not processed yet has no engine
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   WAP_CUDA(cudaSetDevice(e->device));
   WapError err = ensure_staging(e, n);
   if (err != WapError::None) return err;
@@ -758,7 +805,6 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
     if (err != WapError::None) return err;
     WAP_CUDA(cudaMemcpyAsync(dst_o, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
-    for (int i = 0; i < n; ++i) e->leg_delay_set[e->last_slots[i]] = 0;  // audio_processing_impl.cc:1556
     WAP_CUDA(cudaStreamSynchronize(e->stream));
   } else {
     // Large batch: the legs are cut into `chunks` ranges; host->device copies run on one copy
@@ -819,6 +865,7 @@ WapError wap_get_statistics(const WapAudioProcessing* hc, WapStats* out) {
   WapAudioProcessing* h = const_cast<WapAudioProcessing*>(hc);
   if (h->engine && h->slot >= 0 && h->engine->cfg.aec_enabled) {
     WapEngine* e = h->engine;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     WAP_CUDA(cudaSetDevice(e->device));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
     wap::Aec3Scalars s;
@@ -874,6 +921,7 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
   if (!h || !blob) return WapError::NullPointer;
   if (!h->engine || h->slot < 0 || bytes < blob_bytes(h->engine)) return WapError::BadStreamParameter;
   WapEngine* e = h->engine;
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   BlobHeader hd;
@@ -915,10 +963,11 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   if (!h || !blob) return WapError::NullPointer;
   if (!h->engine || h->slot < 0 || bytes < sizeof(BlobHeader)) return WapError::BadStreamParameter;
   WapEngine* e = h->engine;
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   BlobHeader hd;
   memcpy(&hd, blob, sizeof(hd));
   if (hd.magic != kBlobMagic || hd.version != kBlobVersion || hd.total_bytes != blob_bytes(e) || bytes < hd.total_bytes ||
-      memcmp(&hd.cfg, &e->cfg, sizeof(e->cfg)) != 0)
+      !wap::same_engine_config(hd.cfg, e->cfg))
     return WapError::UnsupportedConfig;  // another config class (or library version)
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));
@@ -958,6 +1007,7 @@ WapError wap_stream_read_taps(WapAudioProcessing* h, WapStageTaps* out) {
   if (!h || !out) return WapError::NullPointer;
   if (!h->engine || h->slot < 0) return WapError::BadStreamParameter;
   WapEngine* e = h->engine;
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));
   memset(out, 0, sizeof(*out));

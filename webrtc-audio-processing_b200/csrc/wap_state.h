@@ -12,6 +12,7 @@
 // (initialisation, statistics read-back) and device code.
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 
 namespace wap {
@@ -370,5 +371,16 @@ struct EngineConfig {
   int levels_enabled;   // pre_amplifier.enabled || capture_level_adjustment.enabled
   int post_gain_enabled;  // capture_level_adjustment.enabled: kCapturePostGain is honoured
 };
+
+// Every member of EngineConfig is a 4-byte scalar, so the struct has no padding bytes and two
+// configs are equal exactly when their object representations are (export / import of leg state).
+static_assert(alignof(EngineConfig) == 4 && sizeof(EngineConfig) % 4 == 0, "EngineConfig: 4-byte members only");
+inline bool same_engine_config(const EngineConfig& a, const EngineConfig& b) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+  for (size_t i = 0; i < sizeof(EngineConfig) / 4; ++i)
+    if (pa[i] != pb[i]) return false;
+  return true;
+}
 
 }  // namespace wap
