@@ -18,6 +18,7 @@ LIB = os.path.join(OUT, "libwap_emu_O0.so" if O0 else "libwap_emu.so")
 
 
 def build(verbose=True):
+    import concurrent.futures as cf
     os.makedirs(OUT, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc")))
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
@@ -25,20 +26,42 @@ def build(verbose=True):
         glob.glob(os.path.join(ROOT, "include", "*.h"))
     if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
-    cmd = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
-           "-DWAP_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", HERE, "-I", CSRC,
-           "-I", os.path.join(ROOT, "include"), "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
-           "-Wno-unused-variable"]
+    base = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+            "-DWAP_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", HERE, "-I", CSRC,
+            "-I", os.path.join(ROOT, "include"), "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
+            "-Wno-unused-variable"]
+    # the same translation units as the product build: wap_k_echo.cu once per config class
+    tus = []
+    tag = "_O0" if O0 else ""
     for s in srcs:
-        cmd += ["-x", "c++", s]
-    cmd += ["-x", "c++", os.path.join(HERE, "cuda_emu.cc"), "-o", LIB, "-lpthread", "-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        name = os.path.basename(s).rsplit(".", 1)[0]
+        if name == "wap_k_echo":
+            tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c], os.path.join(OUT, "%s_%d%s.o" % (name, c, tag))) for c in range(5)]
+        else:
+            tus.append((s, [], os.path.join(OUT, name + tag + ".o")))
+    tus.append((os.path.join(HERE, "cuda_emu.cc"), [], os.path.join(OUT, "cuda_emu" + tag + ".o")))
+
+    def one(tu):
+        src, defs, obj = tu
+        r = subprocess.run(base + defs + ["-x", "c++", "-c", src, "-o", obj], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    objs, warn = [], []
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        for obj, rc, out in ex.map(one, tus):
+            objs.append(obj)
+            if rc:
+                sys.stderr.write(out)
+                raise RuntimeError("emu build failed")
+            if out.strip():
+                warn.append(out)
+    r = subprocess.run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread", "-ldl"], capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("emu build failed")
+        raise RuntimeError("emu link failed")
     if verbose:
-        if r.stderr.strip():
-            sys.stderr.write(r.stderr)
+        if warn:
+            sys.stderr.write("".join(warn))
         print("built", LIB)
     return LIB
 

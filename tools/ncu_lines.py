@@ -15,8 +15,13 @@ mangled = sys.argv[5] if len(sys.argv) > 5 else kernel
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)],
                cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("wap_engine") and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+# the kernels live in several translation units: take the cubin whose text sections name the kernel
+dis = ""
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    if any(l.startswith(".text.") and mangled in l for l in d.splitlines()):
+        dis = d
+        break
 line_of = {}
 cur = None
 inside = False

@@ -25,30 +25,64 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I", CSRC, "-I", os.path.join(ROOT, "include")]
 
 
-def build(verbose=True, extra=()):
-    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc")))
+ECHO_CLASSES = 5  # wap::EchoClass instances of k_echo (wap_k_echo.cu is compiled once per class)
+OBJ = os.path.join(HERE, "_obj")
+
+
+def translation_units():
+    """(source, extra defines, object name): every .cu once, wap_k_echo.cu once per config class."""
+    tus = []
+    for s in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc"))):
+        base = os.path.basename(s).rsplit(".", 1)[0]
+        if base == "wap_k_echo":
+            tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c], "%s_%d.o" % (base, c)) for c in range(ECHO_CLASSES)]
+        else:
+            tus.append((s, [], base + ".o"))
+    return tus
+
+
+def build(verbose=True, extra=(), lib=None):
+    import concurrent.futures as cf
+    lib = lib or LIB
+    tus = translation_units()
+    srcs = [t[0] for t in tus]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(CSRC, "*.inc")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [__file__]
-    if not extra and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
-        return LIB
+    if not extra and os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(d) for d in deps):
+        return lib
     if not os.path.exists(NVCC):
-        if os.path.exists(LIB):
-            return LIB
+        if os.path.exists(lib):
+            return lib
         raise RuntimeError("nvcc not found and no prebuilt libwap_b200.so")
-    cmd = [NVCC] + FLAGS + list(extra)
-    for s in srcs:
-        cmd += (["-x", "cu", s] if s.endswith(".cc") else [s])
-    cmd += ["-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    compile_flags = [f for f in FLAGS if f != "-shared"]
+
+    def one(tu):
+        src, defs, name = tu
+        obj = os.path.join(OBJ, name)
+        cmd = [NVCC] + compile_flags + list(extra) + defs + (["-x", "cu"] if src.endswith(".cc") else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, r.returncode, (r.stdout + r.stderr)
+
+    objs, log = [], []
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        for obj, rc, out in ex.map(one, tus):
+            objs.append(obj)
+            if out.strip():
+                log.append(out.strip())
+            if rc:
+                sys.stderr.write(out[-6000:])
+                raise RuntimeError("nvcc build failed")
+    r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs,
+                       capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write((r.stdout + r.stderr)[-6000:])
-        raise RuntimeError("nvcc build failed")
+        raise RuntimeError("nvcc link failed")
     if verbose:
-        tail = (r.stdout + r.stderr).strip()
-        if tail:
-            print(tail[-4000:])
-        print("built", LIB)
-    return LIB
+        if log:
+            print("\n".join(log)[-6000:])
+        print("built", lib)
+    return lib
 
 
 if __name__ == "__main__":

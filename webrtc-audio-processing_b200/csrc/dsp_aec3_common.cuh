@@ -81,8 +81,7 @@ struct EchoPathVariability {  // echo_path_variability.h:16-29
 constexpr int kMfWin = kMfLen + kSubBlock - 1;   // 527 low-rate samples one filter sees in a block
 constexpr int kMfWinPad = 544;                   // second window starts 16 banks after the first
 constexpr int kMfShiftCopy = 528;                // one shifted window copy of the accumulated-error path
-constexpr int kMfHOffset = 2 * kMfWinPad + 32;     // where mf_core keeps h inside xp
-static_assert(4 * kMfShiftCopy >= kMfHOffset + kMfLen, "pair path windows and the wrapped path's h must fit");
+static_assert(4 * kMfShiftCopy >= 2 * kMfWinPad + 32, "pair path windows must fit");
 struct AecMfScratch {
   // Linearised low-rate windows: xp[w] = low_rate[(read + n*384 + w) % size], w < 527, so that
   // tap t of capture sample i is xp[15 - i + t].  The pair path keeps two filters' windows
@@ -90,8 +89,7 @@ struct AecMfScratch {
   // The accumulated-error path keeps FOUR copies of its window, copy sh shifted by sh samples
   // (xs(sh)[w] = window[w + sh], 528 floats each), so that the 4 consecutive taps a lane owns
   // can be fetched with one aligned 128-bit load whatever the sample's offset is.
-  // The general one-filter path (mf_core) keeps its window in the first 544 floats and its taps
-  // h[512] behind the pair-path region (xp + kMfHOffset); the three paths never overlap in time.
+  // The two paths never overlap in time.
   alignas(16) float xp[4 * kMfShiftCopy];
   float inst_err[kAccErrLen];  // MatchedFilter::instantaneous_accumulated_error_
   alignas(16) float q[kAccErrLen];     // per-4-tap partial sums / prefix sums of the accumulated-error core

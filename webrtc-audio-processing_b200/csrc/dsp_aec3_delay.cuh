@@ -23,19 +23,6 @@ namespace wap {
 
 constexpr float kMfX2SumThreshold = 512.f * ec3::kMfExcitationLimit * ec3::kMfExcitationLimit;
 
-// Copies the part of the low-rate ring filter n sees during this block into shared
-// memory, linearised: dst[w] = low_rate[(read + n*shift + w) % size], w < 527.
-WAP_DEV void mf_stage_window(const Aec3State& a, const AecScratch& sc, int n, float* dst) {
-  int start = sc.s.lr_read + n * kMfShift;
-  if (start >= kLowRateSize) start -= kLowRateSize;
-#pragma unroll
-  for (int w = lane_id(); w < kMfWin; w += 32) {  // 17 independent loads in flight
-    int r = start + w;
-    if (r >= kLowRateSize) r -= kLowRateSize;
-    dst[w] = a.low_rate[r];
-  }
-}
-
 // hsum over the 8 "c" values of one accumulator group in the order of hsum_ab
 // (matched_filter_avx2.cc:35-43): ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7)),
 // c_j = chain_j + chain_{j+8}.  Works on both half-warps at once.
@@ -47,95 +34,21 @@ WAP_DEV float mf_hsum16(float acc) {
   return acc;
 }
 
-// One matched filter, 16 decimated capture samples, non-accumulating core
-// (matched_filter_avx2.cc:151-270), general version for blocks in which the window crosses
-// the end of the reference's ring: per sample the 512 taps split at the wrap into two
-// chunks; in each chunk the first floor(len/16)*16 taps feed the 16 fused chains (lane =
-// tap index mod 16 WITHIN the chunk), the remaining len%16 taps are added to the scalar
-// sums with separate multiply and add, in order.  Lanes 0-15 run the h*x chains, lanes
-// 16-31 the x*x chains -- the same code on a per-lane operand pointer (h or x).
-// h lives in (sc.mf.xp + kMfHOffset), the window in sc.mf.xp.
-WAP_DEV void mf_core(AecScratch& sc, int n, const float* y, float* error_sum_out, int* updated_out) {
-  const int lane = lane_id();
-  const int half = lane >> 4, L = lane & 15;
-  float* h = (sc.mf.xp + kMfHOffset);
-  float error_sum = 0.f;
-  int updated = 0;
-#pragma unroll 1
-  for (int i = 0; i < kSubBlock; ++i) {
-    int x_start = sc.s.lr_read + n * kMfShift + kSubBlock - 1 - i;  // position in the reference's ring
-    if (x_start >= kLowRateSize) x_start -= kLowRateSize;
-    const float* x = sc.mf.xp + (kSubBlock - 1 - i);                // tap 0 of sample i
-    const float* pa = half ? x : h;                                  // first operand of this lane's chain
-    const int chunk1 = imin(kMfLen, kLowRateSize - x_start);
-    const int chunk2 = kMfLen - chunk1;
-    const int v1 = chunk1 >> 4, v2 = chunk2 >> 4;
-    float acc = 0.f;
-    {
-      const float* qa = pa + L;
-      const float* qx = x + L;
-      int k = 0;
-      for (; k + 4 <= v1; k += 4, qa += 64, qx += 64) {
-        acc = fmaf(qa[0], qx[0], acc);
-        acc = fmaf(qa[16], qx[16], acc);
-        acc = fmaf(qa[32], qx[32], acc);
-        acc = fmaf(qa[48], qx[48], acc);
-      }
-      for (; k < v1; ++k, qa += 16, qx += 16) acc = fmaf(qa[0], qx[0], acc);
-      qa = pa + chunk1 + L;
-      qx = x + chunk1 + L;
-      for (k = 0; k + 4 <= v2; k += 4, qa += 64, qx += 64) {
-        acc = fmaf(qa[0], qx[0], acc);
-        acc = fmaf(qa[16], qx[16], acc);
-        acc = fmaf(qa[32], qx[32], acc);
-        acc = fmaf(qa[48], qx[48], acc);
-      }
-      for (; k < v2; ++k, qa += 16, qx += 16) acc = fmaf(qa[0], qx[0], acc);
-    }
-    acc = mf_hsum16(acc);   // uniform within each half: h*x on lanes 0-15, x*x on lanes 16-31
-    // Scalar tails: r1 taps after chunk 1's groups, then r2 after chunk 2's (r1 + r2 is 0 or 16).
-    // One product per lane, then the additions in tap order through shuffles.
-    const int r1 = chunk1 & 15, r2 = chunk2 & 15;
-    float tail = 0.f;
-    if (r1 + r2) {
-      const int t = L < r1 ? 16 * v1 + L : chunk1 + 16 * v2 + (L - r1);
-      const float p = pa[t] * x[t];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) tail += __shfl_sync(WAP_FULL, p, (lane & 16) | j);
-    }
-    const float mine = tail + acc;                      // reference: s += vec (x2_sum += vec)
-    const float s = __shfl_sync(WAP_FULL, mine, 0);
-    const float x2_sum = __shfl_sync(WAP_FULL, mine, 16);
-    const float yi = y[i];
-    const float e = yi - s;
-    const bool saturation = yi >= 32000.f || yi <= -32000.f;
-    error_sum += e * e;
-    __syncwarp();
-    if (x2_sum > kMfX2SumThreshold && !saturation) {
-      const float alpha = ec3::kMfSmoothing * e / x2_sum;
-      // The groups of 8 of each chunk are fused, the (< 8 tap) ends are not: those few taps are
-      // computed unfused from the old h first and written over the fused result afterwards.
-      const int f1 = chunk1 & ~7, n1 = chunk1 - f1;
-      const int f2 = chunk1 + (chunk2 & ~7), n2 = kMfLen - f2;
-      int tn = -1;
-      float hn = 0.f;
-      if (lane < n1) tn = f1 + lane;
-      else if (lane - n1 < n2) tn = f2 + (lane - n1);
-      if (tn >= 0) hn = h[tn] + alpha * x[tn];
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < kMfLen / 32; ++k) {
-        const int t = lane + 32 * k;
-        h[t] = fmaf(x[t], alpha, h[t]);
-      }
-      __syncwarp();
-      if (tn >= 0) h[tn] = hn;
-      updated = 1;
-    }
-    __syncwarp();
-  }
-  *error_sum_out = error_sum;
-  *updated_out = updated;
+// h[k], h[k+1] += alpha * x[k], x[k+1] as ONE packed fused multiply-add (sm_100 FFMA2): the
+// reference's NLMS update is an explicit _mm256_fmadd_ps (matched_filter_avx2.cc:251), and each
+// half of fma.rn.f32x2 is the same correctly rounded single-precision FMA.
+WAP_DEV void mf_fma2(float& h0, float& h1, float x0, float x1, float alpha) {
+#if defined(WAP_EMU)
+  h0 = fmaf(x0, alpha, h0);
+  h1 = fmaf(x1, alpha, h1);
+#else
+  unsigned long long hh, xx, aa;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(hh) : "f"(h0), "f"(h1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(alpha));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(hh) : "l"(xx), "l"(aa));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(hh));
+#endif
 }
 
 // The filter that won the previous block, with the accumulated-error side output
@@ -239,7 +152,7 @@ WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) 
     if (x2_sum > kMfX2SumThreshold && !saturation) {
       const float alpha = ec3::kMfSmoothing * e / x2_sum;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h[j] = fmaf(xv[j], alpha, h[j]);
+      for (int j = 0; j < 16; j += 2) mf_fma2(h[j], h[j + 1], xv[j], xv[j + 1], alpha);
       updated = 1;
     }
   }
@@ -272,78 +185,249 @@ WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) 
   __syncwarp();
 }
 
-// Two matched filters side by side, one per half-warp, for blocks in which neither
-// window crosses the end of the reference's ring (chunk1 == 512 for all 16 capture
-// samples, no scalar tails): the non-accumulating core of matched_filter_avx2.cc:
-// 151-270 with
+// ---- window table of the pair path -------------------------------------------------------
+// One filter sees 527 consecutive low-rate samples w[0..526] during a block (tap t of capture
+// sample i is w[15 - i + t]).  Lane L of a half-warp owns taps t = L + 16k, k = 0..31, so for
+// sample i it needs w[m + 16k] with m = 15 - i + L in 0..30.  The table stores the window
+// "transposed": T[g][m][j] = w[m + 16 (4g + j)], g < 8, m < 31, j < 4 -- a lane fetches its 32 taps of
+// one sample with 8 aligned 128-bit loads (consecutive lanes read consecutive 16-byte chunks, so
+// the loads are bank-conflict free) instead of 32 scalar ones.  Most samples are stored twice.
+constexpr int kMfTabGroup = 31 * 4;          // floats per k-group
+constexpr int kMfTab = 8 * kMfTabGroup;      // 992 floats per filter
+constexpr int kMfTabStride = 1024;           // second filter's table
+static_assert(kMfTabStride + kMfTab <= 4 * kMfShiftCopy, "pair-path tables must fit the matched-filter scratch");
+WAP_DEV int mf_tab_index(int m, int k) { return ((k >> 2) * 31 + m) * 4 + (k & 3); }
+
+WAP_DEV void mf_stage_table(const Aec3State& a, const AecScratch& sc, int n, float* T) {
+  int start = sc.s.lr_read + n * kMfShift;
+  if (start >= kLowRateSize) start -= kLowRateSize;
+#pragma unroll
+  for (int w = lane_id(); w < kMfWin; w += 32) {  // 17 independent loads in flight
+    int r = start + w;
+    if (r >= kLowRateSize) r -= kLowRateSize;
+    const float v = a.low_rate[r];
+    const int m = w & 15, k = w >> 4;
+    if (k < 32) T[mf_tab_index(m, k)] = v;
+    if (m < 15 && k >= 1) T[mf_tab_index(m + 16, k - 1)] = v;
+  }
+}
+
+// The 32 taps lane L sees for the sample whose table row is m (= 15 - i + L).
+WAP_DEV void mf_load_row(const float* T, int m, float (&xv)[32]) {
+  const float4* row = reinterpret_cast<const float4*>(T + 4 * m);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 v = row[g * 31];
+    xv[4 * g] = v.x; xv[4 * g + 1] = v.y; xv[4 * g + 2] = v.z; xv[4 * g + 3] = v.w;
+  }
+}
+
+// a == b, opaque to the optimiser.  Inside `if (k == v1w)` with k unrolled the compiler would
+// otherwise rewrite h[k] / xv[k] as h[v1w] / xv[v1w] -- a dynamically indexed register array, i.e.
+// both arrays would move to local memory (measured: 3x the kernel's global traffic in spills).
+WAP_DEV bool mf_opaque_eq(int a, int b) {
+#if defined(WAP_EMU)
+  return a == b;
+#else
+  int r;
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(a), "r"(b));
+  return r != 0;
+#endif
+}
+
+// Two matched filters side by side, one per half-warp: the non-accumulating core of
+// matched_filter_avx2.cc:151-270 with
 //  * the 32 taps of chain L (t = L + 16k) and their h in REGISTERS of lane L, so the
 //    NLMS update reuses the x values the dot product loaded and h never touches
 //    shared memory;
-//  * the x*x chains computed once per block instead of once per sample: chain j of
+//  * kWrap == false (neither window crosses the end of the reference's ring during the
+//    block): the x*x chains computed once per block instead of once per sample: chain j of
 //    sample i runs over x[s - i + j + 16k], k = 0..31, i.e. it is chain 0 of "sample
 //    i - j".  The block therefore has only 31 distinct chains (E[m], m = -15..15, each
-//    the same fused 32-term recursion the reference evaluates), and x2_sum of sample i
-//    is the reference's hsum tree over E[i - j].
+//    the same fused 32-term recursion the reference evaluates), and x2_sum of every sample is
+//    the reference's hsum tree over E[i - j];
+//  * kWrap == true (filter nA's window crosses the ring end; nB's does not): for a sample whose
+//    512 taps split into chunk1 | chunk2 at a position that is not a multiple of 16 the reference
+//    runs its 16 fused chains over the first 16*floor(chunk1/16) taps, adds the r1 = chunk1 % 16
+//    left-over taps unfused to the scalar sums, CONTINUES the same 16 accumulators over chunk 2
+//    (chain = tap offset within the chunk mod 16) and adds the last r2 = 16 - r1 taps unfused.
+//    With v1 = floor(chunk1/16): lane L's tap L + 16k belongs to chain L for k < v1, is a
+//    chunk-1 left-over for k == v1 && L < r1, belongs to chain (L - r1) mod 16 for the taps
+//    after that, and is a chunk-2 left-over for k == 31 && L >= r1.  So the accumulators are
+//    rotated by r1 lanes once (one shuffle) at k == v1, lanes skip the one FMA their left-over
+//    tap would be, and the 16 left-over products are added in tap order -- which is lane
+//    order.  The NLMS update is fused except for the < 8 taps at the end of each chunk
+//    (k == v1 and k == 31 again).  x*x runs per sample through the same structure.
 // nA / nB: filter indices (nB < 0: second half idle).
-WAP_DEV void mf_pair_fast(Aec3State& a, AecScratch& sc, int nA, int nB, const float* y) {
+template <bool kWrap>
+WAP_DEV void mf_pair(Aec3State& a, AecScratch& sc, int nA, int nB, const float* y) {
   const int lane = lane_id();
   const int hw = lane >> 4, L = lane & 15;
   const int n = hw ? nB : nA;
   const bool on = n >= 0;
   const int nn = on ? n : nA;
-  float* xp = sc.mf.xp + hw * (kMfWinPad + 16);
+  const float* T = sc.mf.xp + hw * kMfTabStride;
   __syncwarp();
-  mf_stage_window(a, sc, nA, sc.mf.xp);
-  if (nB >= 0) mf_stage_window(a, sc, nB, sc.mf.xp + kMfWinPad + 16);
+  mf_stage_table(a, sc, nA, sc.mf.xp);
+  if (nB >= 0) mf_stage_table(a, sc, nB, sc.mf.xp + kMfTabStride);
   float h[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) h[k] = a.mf_h[nn][L + 16 * k];
   __syncwarp();
-  // ---- the 31 x*x chains of this block: E[15 - L] = chain L of sample 0, E[15 + L] = chain 0 of sample L
-  {
-    float c_init = 0.f, c_new = 0.f;
-    const float* x0 = xp + (kSubBlock - 1) + L;  // tap L of sample 0
-    const float* x1 = xp + (kSubBlock - 1) - L;  // tap 0 of sample L
+  if (!kWrap) {
+    // ---- the 31 x*x chains of this block: E[15 - L] = chain L of sample 0, E[15 + L] = chain 0 of sample L
+    {
+      float u[32], v[32];
+      mf_load_row(T, 15 + L, u);   // tap L of sample 0 onwards
+      mf_load_row(T, 15 - L, v);   // tap 0 of sample L onwards
+      float c_init = 0.f, c_new = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float u = x0[16 * k], v = x1[16 * k];
-      c_init = fmaf(u, u, c_init);
-      c_new = fmaf(v, v, c_new);
+      for (int k = 0; k < 32; ++k) {
+        c_init = fmaf(u[k], u[k], c_init);
+        c_new = fmaf(v[k], v[k], c_new);
+      }
+      sc.mf.x2chain[hw][15 - L] = c_init;
+      if (L > 0) sc.mf.x2chain[hw][15 + L] = c_new;
     }
-    sc.mf.x2chain[hw][15 - L] = c_init;
-    if (L > 0) sc.mf.x2chain[hw][15 + L] = c_new;
+    __syncwarp();
+    {
+      // x2_sum of sample i = L: c_j = chain_j + chain_{j+8}; ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7))  (hsum_ab)
+      const float* E = sc.mf.x2chain[hw] + 15 + L;  // E[-j] = chain j of sample L
+      const float c0 = E[0] + E[-8], c1 = E[-1] + E[-9], c2 = E[-2] + E[-10], c3 = E[-3] + E[-11];
+      const float c4 = E[-4] + E[-12], c5 = E[-5] + E[-13], c6 = E[-6] + E[-14], c7 = E[-7] + E[-15];
+      sc.mf.x2sum[hw][L] = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  {
-    // x2_sum of sample i = L: c_j = chain_j + chain_{j+8}; ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7))  (hsum_ab)
-    const float* E = sc.mf.x2chain[hw] + 15 + L;  // E[-j] = chain j of sample L
-    const float c0 = E[0] + E[-8], c1 = E[-1] + E[-9], c2 = E[-2] + E[-10], c3 = E[-3] + E[-11];
-    const float c4 = E[-4] + E[-12], c5 = E[-5] + E[-13], c6 = E[-6] + E[-14], c7 = E[-7] + E[-15];
-    sc.mf.x2sum[hw][L] = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
-  }
-  __syncwarp();
+  // position of tap 0 of sample 0 of filter nA in the reference's ring (kWrap only)
+  const int x_start0 = sc.s.lr_read + nA * kMfShift + kSubBlock - 1;
   float error_sum = 0.f;
   int updated = 0;
 #pragma unroll 1
   for (int i = 0; i < kSubBlock; ++i) {
-    const float* x = xp + (kSubBlock - 1 - i) + L;
     float xv[32];
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      xv[k] = x[16 * k];
-      acc = fmaf(h[k], xv[k], acc);
+    mf_load_row(T, kSubBlock - 1 - i + L, xv);
+    float acc = 0.f, accx = 0.f;
+    float s, x2_sum;
+    // kWrap: where filter nA wraps for this sample (warp-uniform; r1 == 0: the chains are unaffected)
+    int v1w = 99, r1 = 0, chunk1 = kMfLen;
+    if (kWrap) {
+      int xs = x_start0 - i;
+      if (xs >= kLowRateSize) xs -= kLowRateSize;
+      chunk1 = imin(kMfLen, kLowRateSize - xs);
+      r1 = chunk1 & 15;
+      v1w = r1 ? (chunk1 >> 4) : 99;
     }
-    const float s = mf_hsum16(acc);     // uniform within the half-warp; reference: s = 0 + hsum
-    const float x2_sum = sc.mf.x2sum[hw][i];
+    const bool wrapped_half = kWrap && hw == 0;
+    const bool tail1 = wrapped_half && L < r1;             // my tap at k == v1w is a chunk-1 left-over
+    const bool tail2 = wrapped_half && r1 > 0 && L >= r1;  // my tap at k == 31 is a chunk-2 left-over
+    float p_h = 0.f, p_x = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (kWrap && mf_opaque_eq(v1w >> 3, g)) {   // warp-uniform: the wrap step is among these eight k
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = 8 * g + kk;
+          const bool at_wrap = mf_opaque_eq(k, v1w);
+          if (at_wrap) {
+            // the accumulators move to the lane that owns their chain's taps from here on (one
+            // convergent shuffle: the half-warp whose filter does not wrap reads itself)
+            const int src = wrapped_half ? ((L - r1) & 15) : lane;
+            acc = __shfl_sync(WAP_FULL, acc, src);
+            accx = __shfl_sync(WAP_FULL, accx, src);
+          }
+          if (at_wrap || k == 31) {   // warp-uniform
+            const bool left_over = (at_wrap && tail1) || (k == 31 && tail2);
+            const float ph = h[k] * xv[k], px = xv[k] * xv[k];
+            const float a1 = fmaf(h[k], xv[k], acc), a2 = fmaf(xv[k], xv[k], accx);
+            acc = left_over ? acc : a1;
+            accx = left_over ? accx : a2;
+            p_h = left_over ? ph : p_h;
+            p_x = left_over ? px : p_x;
+          } else {
+            acc = fmaf(h[k], xv[k], acc);
+            accx = fmaf(xv[k], xv[k], accx);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = 8 * g + kk;
+          if (kWrap && k == 31) {
+            const float a1 = fmaf(h[k], xv[k], acc), a2 = fmaf(xv[k], xv[k], accx);
+            p_h = tail2 ? h[k] * xv[k] : p_h;
+            p_x = tail2 ? xv[k] * xv[k] : p_x;
+            acc = tail2 ? acc : a1;
+            accx = tail2 ? accx : a2;
+          } else {
+            acc = fmaf(h[k], xv[k], acc);
+            if (kWrap) accx = fmaf(xv[k], xv[k], accx);
+          }
+        }
+      }
+    }
+    if (kWrap) {
+      float t_h = 0.f, t_x = 0.f;
+      if (r1 > 0) {   // warp-uniform
+        // back to chain order for the combine tree
+        const int src = wrapped_half ? ((L + r1) & 15) : lane;
+        acc = __shfl_sync(WAP_FULL, acc, src);
+        accx = __shfl_sync(WAP_FULL, accx, src);
+        // the 16 left-over products in tap (= lane) order: lane 0 adds the h*x ones, lane 1 the x*x ones
+        __syncwarp();
+        if (wrapped_half) { sc.mf.q[L] = p_h; sc.mf.q[16 + L] = p_x; }
+        __syncwarp();
+        const float4* q = reinterpret_cast<const float4*>(sc.mf.q + 16 * (lane & 1));
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = q[j];
+          t += v.x; t += v.y; t += v.z; t += v.w;
+        }
+        t_h = __shfl_sync(WAP_FULL, t, 0);
+        t_x = __shfl_sync(WAP_FULL, t, 1);
+        if (!wrapped_half) { t_h = 0.f; t_x = 0.f; }
+      }
+      s = t_h + mf_hsum16(acc);        // reference: s (left-overs) += hsum(vector accumulators)
+      x2_sum = t_x + mf_hsum16(accx);
+    } else {
+      s = mf_hsum16(acc);     // uniform within the half-warp; reference: s = 0 + hsum
+      x2_sum = sc.mf.x2sum[hw][i];
+    }
     const float yi = y[i];
     const float e = yi - s;
     const bool saturation = yi >= 32000.f || yi <= -32000.f;
     error_sum += e * e;
     if (on && x2_sum > kMfX2SumThreshold && !saturation) {
       const float alpha = ec3::kMfSmoothing * e / x2_sum;
+      if (kWrap) {
+        // groups of 8 of each chunk are fused; the < 8 taps at the end of each chunk are not
+        const int c1 = wrapped_half ? chunk1 : kMfLen;
+        const int f1 = c1 & ~7, f2 = c1 + ((kMfLen - c1) & ~7);
 #pragma unroll
-      for (int k = 0; k < 32; ++k) h[k] = fmaf(xv[k], alpha, h[k]);
+        for (int g = 0; g < 4; ++g) {
+          if (mf_opaque_eq(v1w >> 3, g) || g == 3) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const int k = 8 * g + kk;
+              if (mf_opaque_eq(k, v1w) || k == 31) {   // warp-uniform: the only steps that can hold unfused taps
+                const int t = L + 16 * k;
+                const bool unfused = (t >= f1 && t < c1) || t >= f2;
+                const float hf = fmaf(xv[k], alpha, h[k]), hu = h[k] + alpha * xv[k];
+                h[k] = unfused ? hu : hf;
+              } else {
+                h[k] = fmaf(xv[k], alpha, h[k]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 2) mf_fma2(h[8 * g + kk], h[8 * g + kk + 1], xv[8 * g + kk], xv[8 * g + kk + 1], alpha);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) mf_fma2(h[k], h[k + 1], xv[k], xv[k + 1], alpha);
+      }
       updated = 1;
     }
   }
@@ -369,28 +453,6 @@ WAP_DEV void mf_pair_fast(Aec3State& a, AecScratch& sc, int nA, int nB, const fl
     sc.mf.peak[n] = (odd_v > best) ? odd_i : bi;
   }
   __syncwarp();
-}
-
-// aec3::MaxSquarePeakIndex (matched_filter.cc:558-591) for a 512-tap filter:
-// first maximum among even taps, first maximum among odd taps, odd wins only
-// when strictly larger.
-WAP_DEV int mf_max_square_peak_index(const float* h) {
-  const int lane = lane_id();
-  float best = -1.f;
-  int bi = 0;
-  #pragma unroll
-  for (int t = lane; t < kMfLen; t += 32) {  // lane parity == tap parity
-    const float v = h[t] * h[t];
-    if (v > best) { best = v; bi = t; }
-  }
-  for (int m = 2; m < 32; m <<= 1) {
-    const float ov = __shfl_xor_sync(WAP_FULL, best, m);
-    const int oi = __shfl_xor_sync(WAP_FULL, bi, m);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-  }
-  const float even_v = __shfl_sync(WAP_FULL, best, 0), odd_v = __shfl_sync(WAP_FULL, best, 1);
-  const int even_i = __shfl_sync(WAP_FULL, bi, 0), odd_i = __shfl_sync(WAP_FULL, bi, 1);
-  return (odd_v > even_v) ? odd_i : even_i;
 }
 
 // MatchedFilter::Reset (matched_filter.cc:641-655)
@@ -475,43 +537,32 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   float error_sum_anchor = 0.f;
   for (int k = 0; k < kSubBlock; ++k) error_sum_anchor += y[k] * y[k];
   const int last_best = s.mf_last_detected_best_lag_filter;
-  // Filters whose window does not wrap in the reference's ring during this block (and
-  // that do not need the accumulated-error side output) go through the pair path.
-  int fast[kNumMatchedFilters];
-  int nfast = 0;
-  unsigned slow_mask = 0;
+  // The filter that won the previous block needs the accumulated-error side output and goes through
+  // its own path; the others are processed two at a time, one per half-warp.  A filter whose window
+  // crosses the end of the reference's ring during this block is paired with one that does not
+  // (adjacent filters can wrap together: they go into different passes).
+  unsigned plain = 0, wrapped = 0;   // bit n: filter n (no arrays: the kernel keeps no stack frame)
   for (int n = 0; n < kNumMatchedFilters; ++n) {
+    if (n == last_best) continue;
     int x_start0 = s.lr_read + n * kMfShift + kSubBlock - 1;
     if (x_start0 >= kLowRateSize) x_start0 -= kLowRateSize;
     const bool no_wrap = x_start0 >= kSubBlock - 1 && x_start0 + kMfLen <= kLowRateSize;
-    if (no_wrap && n != last_best) fast[nfast++] = n;
-    else slow_mask |= 1u << n;
+    if (no_wrap) plain |= 1u << n;
+    else wrapped |= 1u << n;
   }
-  for (int p = 0; p < nfast; p += 2) mf_pair_fast(a, sc, fast[p], p + 1 < nfast ? fast[p + 1] : -1, y);
-  for (int n = 0; n < kNumMatchedFilters; ++n) {
-    if (!((slow_mask >> n) & 1u)) continue;
-    if (n == last_best) {
-      mf_acc_filter(a, sc, n, y);
-      continue;
-    }
-    __syncwarp();
-    mf_stage_window(a, sc, n, sc.mf.xp);
-    #pragma unroll
-    for (int t = lane; t < kMfLen; t += 32) (sc.mf.xp + kMfHOffset)[t] = a.mf_h[n][t];
-    __syncwarp();
-    float error_sum;
-    int updated;
-    mf_core(sc, n, y, &error_sum, &updated);
-    const int peak = mf_max_square_peak_index((sc.mf.xp + kMfHOffset));
-    #pragma unroll
-    for (int t = lane; t < kMfLen; t += 32) a.mf_h[n][t] = (sc.mf.xp + kMfHOffset)[t];
-    if (lane == 0) {
-      sc.mf.err_sum[n] = error_sum;
-      sc.mf.updated[n] = updated;
-      sc.mf.peak[n] = peak;
-    }
-    __syncwarp();
+  // One call site per variant inside one loop: each is inlined exactly once (instruction-cache
+  // footprint), and nothing is passed through local memory.
+#pragma unroll 1
+  while (plain | wrapped) {
+    const bool wrap = wrapped != 0;
+    int nA, nB = -1;
+    if (wrap) { nA = __ffs((int)wrapped) - 1; wrapped &= wrapped - 1; }
+    else { nA = __ffs((int)plain) - 1; plain &= plain - 1; }
+    if (plain) { nB = __ffs((int)plain) - 1; plain &= plain - 1; }
+    if (wrap) mf_pair<true>(a, sc, nA, nB, y);
+    else mf_pair<false>(a, sc, nA, nB, y);
   }
+  if (last_best >= 0) mf_acc_filter(a, sc, last_best, y);
   // winner selection (matched_filter.cc:729-776), lane 0
   if (lane == 0) {
     float winner_error_sum = error_sum_anchor;

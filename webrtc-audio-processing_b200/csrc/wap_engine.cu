@@ -20,6 +20,7 @@
 #include "wap_audio_processing.h"
 #include "wap_init.h"
 #include "wap_launch.h"
+#include "wap_kernels.h"
 #include "wap_pipeline.cuh"
 
 namespace wap {
@@ -44,47 +45,6 @@ __global__ void __launch_bounds__(128) k_resample(TickArgs a) {
   const int warp = threadIdx.x >> 5;
   const int idx = blockIdx.x * 4 + warp;
   if (idx < a.n) resample_in_tick(a, idx, sm + warp * 2 * kRsMaxRequest);
-}
-
-#ifndef WAP_DELAY_MINBLOCKS
-#define WAP_DELAY_MINBLOCKS 5
-#endif
-__global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, int scratch_floats) {
-  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  unsigned scratch_off = (unsigned)warp * (unsigned)scratch_floats;
-#if !defined(WAP_EMU)
-  // Opaque to the optimiser: keeps the per-warp offset in one register instead of
-  // re-deriving it from tid / the kernel parameter at every shared-memory access.
-  asm volatile("" : "+r"(scratch_off));
-#endif
-  float* scratch = sm + scratch_off;
-  for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
-    delay_stream_tick(a, idx, scratch);
-    __syncwarp();
-  }
-}
-
-#ifndef WAP_ECHO_MINBLOCKS
-#define WAP_ECHO_MINBLOCKS 4
-#endif
-template <int kClass>
-__global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
-  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
-  const int warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  unsigned scratch_off = (unsigned)warp * (unsigned)scratch_floats;
-#if !defined(WAP_EMU)
-  // Opaque to the optimiser: keeps the per-warp offset in one register instead of
-  // re-deriving it from tid / the kernel parameter at every shared-memory access.
-  asm volatile("" : "+r"(scratch_off));
-#endif
-  float* scratch = sm + scratch_off;
-  for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
-    echo_stream_tick<kClass>(a, idx, scratch);
-    __syncwarp();
-  }
 }
 
 // 48 kHz AEC3 legs only: PostFilter + output conversion, one thread per leg.
@@ -425,18 +385,12 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   if (timing) cudaEventRecord(e->ev[1], e->stream);
   if (e->cfg.aec_enabled && d_capture) {
     const size_t smem_d = (size_t)wpb * e->delay_scratch_floats * sizeof(float);
-    WAP_LAUNCH(wap::k_delay, grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
+    wap::launch_k_delay(grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
     e->launches++;
   }
   if (timing) cudaEventRecord(e->ev[2], e->stream);
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
-  switch (e->echo_class) {
-    case wap::kEchoMono16k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono16k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
-    case wap::kEchoMono48kNative: WAP_LAUNCH(wap::k_echo<wap::kEchoMono48kNative>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
-    case wap::kEchoMono48kVia32k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono48kVia32k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
-    case wap::kEchoMono32k: WAP_LAUNCH(wap::k_echo<wap::kEchoMono32k>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
-    default: WAP_LAUNCH(wap::k_echo<wap::kEchoGeneric>, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats); break;
-  }
+  wap::launch_k_echo(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
   if (e->d_upper && e->cfg.num_bands == 3 && d_capture) {  // PostFilter: 48 kHz only (post_filter.cc:44-52)
     WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
@@ -482,7 +436,7 @@ extern "C" {
 const char* wap_version(void) {
   static char v[160];
   snprintf(v, sizeof(v), "wap_b200 0.2 (sm_100a; per-warp smem: k_delay %d B, k_echo %d B at 16 kHz; k_echo min blocks/SM %d)",
-           wap::delay_scratch_floats() * 4, wap::echo_scratch_floats(1) * 4, WAP_ECHO_MINBLOCKS);
+           wap::delay_scratch_floats() * 4, wap::echo_scratch_floats(1) * 4, wap::k_echo_min_blocks());
   return v;
 }
 
@@ -567,14 +521,8 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   }
   const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
   const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
-  if (ok && smem_e > 48 * 1024)
-    ok = cudaFuncSetAttribute(wap::k_echo<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
-         cudaFuncSetAttribute(wap::k_echo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
-         cudaFuncSetAttribute(wap::k_echo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
-         cudaFuncSetAttribute(wap::k_echo<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess &&
-         cudaFuncSetAttribute(wap::k_echo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e) == cudaSuccess;
-  if (ok && smem_d > 48 * 1024)
-    ok = cudaFuncSetAttribute(wap::k_delay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d) == cudaSuccess;
+  if (ok && smem_e > 48 * 1024) ok = wap::set_k_echo_smem((int)smem_e) == cudaSuccess;
+  if (ok && smem_d > 48 * 1024) ok = wap::set_k_delay_smem((int)smem_d) == cudaSuccess;
   if (!ok) {
     fprintf(stderr, "[wap_b200] engine allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     wap_engine_destroy(e);

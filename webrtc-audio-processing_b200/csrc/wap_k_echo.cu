@@ -1,0 +1,68 @@
+// k_echo<class>: everything after the front end for one leg (wap_pipeline.cuh: echo_stream_tick), one
+// warp per call leg.  This file is compiled once per config class (-DWAP_ECHO_CLASS=0..4, see
+// build.py): each instance has the band-split / upper-band / resampler / stereo code it does not
+// need compiled out, and the instances build in parallel.
+#include "wap_kernels.h"
+#include "wap_launch.h"
+#include "wap_pipeline.cuh"
+
+#ifndef WAP_ECHO_CLASS
+#error "compile with -DWAP_ECHO_CLASS=<0..4>"
+#endif
+#ifndef WAP_ECHO_MINBLOCKS
+#define WAP_ECHO_MINBLOCKS 4
+#endif
+#define WAP_CAT2(a, b) a##b
+#define WAP_CAT(a, b) WAP_CAT2(a, b)
+
+namespace wap {
+
+template <int kClass>
+__global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
+  float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  unsigned scratch_off = (unsigned)warp * (unsigned)scratch_floats;
+#if !defined(WAP_EMU)
+  // Opaque to the optimiser: keeps the per-warp offset in one register instead of
+  // re-deriving it from tid / the kernel parameter at every shared-memory access.
+  asm volatile("" : "+r"(scratch_off));
+#endif
+  float* scratch = sm + scratch_off;
+  for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
+    echo_stream_tick<kClass>(a, idx, scratch);
+    __syncwarp();
+  }
+}
+
+cudaError_t WAP_CAT(launch_k_echo_, WAP_ECHO_CLASS)(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,
+                                                     int scratch_floats) {
+  WAP_LAUNCH(k_echo<WAP_ECHO_CLASS>, grid, block, smem, stream, a, scratch_floats);
+  return cudaSuccess;
+}
+cudaError_t WAP_CAT(set_k_echo_smem_, WAP_ECHO_CLASS)(int bytes) {
+  return cudaFuncSetAttribute(k_echo<WAP_ECHO_CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+#if WAP_ECHO_CLASS == 0
+cudaError_t launch_k_echo(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats) {
+  switch (cls) {
+    case kEchoMono16k: return launch_k_echo_1(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono48kNative: return launch_k_echo_2(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono48kVia32k: return launch_k_echo_3(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono32k: return launch_k_echo_4(grid, block, smem, stream, a, scratch_floats);
+    default: return launch_k_echo_0(grid, block, smem, stream, a, scratch_floats);
+  }
+}
+cudaError_t set_k_echo_smem(int bytes) {
+  cudaError_t e = set_k_echo_smem_0(bytes);
+  if (e == cudaSuccess) e = set_k_echo_smem_1(bytes);
+  if (e == cudaSuccess) e = set_k_echo_smem_2(bytes);
+  if (e == cudaSuccess) e = set_k_echo_smem_3(bytes);
+  if (e == cudaSuccess) e = set_k_echo_smem_4(bytes);
+  return e;
+}
+int k_echo_min_blocks() { return WAP_ECHO_MINBLOCKS; }
+#endif
+
+}  // namespace wap
