@@ -257,6 +257,156 @@ typedef struct WapStageTaps {
 } WapStageTaps;
 WapError wap_stream_read_taps(WapAudioProcessing* handle, WapStageTaps* out);
 
+/* ---- EXT: EchoCanceller3Config through the boundary -----------------------------------------
+ * The reference injects a non-default AEC3 configuration when the instance is built
+ * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig, api/audio/
+ * builtin_audio_processing_builder.h:51-58); the seam has no entry point for it, so these are
+ * extensions.  WapEchoCanceller3Config mirrors webrtc::EchoCanceller3Config member for member
+ * (api/audio/echo_canceller3_config.h:21-275; size_t members are int32_t here).
+ * wap_echo_canceller3_config_validate restates EchoCanceller3Config::Validate
+ * (echo_canceller3_config.cc:101-286): it clamps in place and returns true when nothing changed.
+ * Engines run the default config on compile-time constants; any other config selects kernel
+ * instances that read the parameters at run time.  Members that would change the structure of
+ * the engine (see wap_echo_canceller3_config_supported) must keep their default value. */
+typedef struct WapEc3MaskingThresholds {
+  float enr_transparent, enr_suppress, emr_transparent;
+} WapEc3MaskingThresholds;
+typedef struct WapEc3Tuning {
+  WapEc3MaskingThresholds mask_lf, mask_hf;
+  float max_inc_factor, max_dec_factor_lf;
+} WapEc3Tuning;
+typedef struct WapEc3AlignmentMixing {
+  bool downmix, adaptive_selection;
+  float activity_power_threshold;
+  bool prefer_first_two_channels;
+} WapEc3AlignmentMixing;
+typedef struct WapEc3RefinedConfiguration {
+  int32_t length_blocks;
+  float leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate;
+} WapEc3RefinedConfiguration;
+typedef struct WapEc3CoarseConfiguration {
+  int32_t length_blocks;
+  float rate, noise_gate;
+} WapEc3CoarseConfiguration;
+typedef struct WapEc3SubbandRegion {
+  int32_t low, high;
+} WapEc3SubbandRegion;
+typedef struct WapEchoCanceller3Config {
+  struct {
+    int32_t excess_render_detection_interval_blocks, max_allowed_excess_render_blocks;
+  } buffering;
+  struct {
+    int32_t default_delay, down_sampling_factor, num_filters, delay_headroom_samples, hysteresis_limit_blocks,
+        fixed_capture_delay_samples;
+    float delay_estimate_smoothing, delay_estimate_smoothing_delay_found, delay_candidate_detection_threshold;
+    struct {
+      int32_t initial, converged;
+    } delay_selection_thresholds;
+    bool use_external_delay_estimator, log_warning_on_delay_changes;
+    WapEc3AlignmentMixing render_alignment_mixing, capture_alignment_mixing;
+    bool detect_pre_echo;
+  } delay;
+  struct {
+    WapEc3RefinedConfiguration refined;
+    WapEc3CoarseConfiguration coarse;
+    WapEc3RefinedConfiguration refined_initial;
+    WapEc3CoarseConfiguration coarse_initial;
+    int32_t config_change_duration_blocks;
+    float initial_state_seconds;
+    int32_t coarse_reset_hangover_blocks;
+    bool conservative_initial_phase, enable_coarse_filter_output_usage, use_linear_filter,
+        high_pass_filter_echo_reference, export_linear_aec_output;
+  } filter;
+  struct {
+    float min, max_l, max_h;
+    bool onset_detection;
+    int32_t num_sections;
+    bool clamp_quality_estimate_to_zero, clamp_quality_estimate_to_one;
+  } erle;
+  struct {
+    float default_gain, default_len, nearend_len;
+    bool echo_can_saturate, bounded_erl, erle_onset_compensation_in_dominant_nearend,
+        use_conservative_tail_frequency_response;
+  } ep_strength;
+  struct {
+    float low_render_limit, normal_render_limit, floor_power, audibility_threshold_lf, audibility_threshold_mf,
+        audibility_threshold_hf;
+    bool use_stationarity_properties, use_stationarity_properties_at_init;
+  } echo_audibility;
+  struct {
+    float active_render_limit, poor_excitation_render_limit, poor_excitation_render_limit_ds8, render_power_gain_db;
+  } render_levels;
+  struct {
+    bool has_clock_drift, linear_and_stable_echo_path;
+  } echo_removal_control;
+  struct {
+    int32_t noise_floor_hold;
+    float min_noise_floor_power, stationary_gate_slope, noise_gate_power, noise_gate_slope;
+    int32_t render_pre_window_size, render_post_window_size;
+    bool model_reverb_in_nonlinear_mode;
+  } echo_model;
+  struct {
+    float noise_floor_dbfs;
+  } comfort_noise;
+  struct {
+    int32_t nearend_average_blocks;
+    WapEc3Tuning normal_tuning, nearend_tuning;
+    bool lf_smoothing_during_initial_phase;
+    int32_t last_permanent_lf_smoothing_band, last_lf_smoothing_band, last_lf_band, first_hf_band;
+    struct {
+      float enr_threshold, enr_exit_threshold, snr_threshold;
+      int32_t hold_duration, trigger_threshold;
+      bool use_during_initial_phase, use_unbounded_echo_spectrum;
+    } dominant_nearend_detection;
+    struct {
+      int32_t nearend_average_blocks;
+      WapEc3SubbandRegion subband1, subband2;
+      float nearend_threshold, snr_threshold;
+    } subband_nearend_detection;
+    bool use_subband_nearend_detection;
+    struct {
+      float enr_threshold, max_gain_during_echo, anti_howling_activation_threshold, anti_howling_gain;
+    } high_bands_suppression;
+    struct {
+      int32_t limiting_gain_band, bands_in_limiting_gain;
+    } high_frequency_suppression;
+    float floor_first_increase;
+    bool conservative_hf_suppression;
+  } suppressor;
+  struct {
+    bool detect_stereo_content;
+    float stereo_detection_threshold;
+    int32_t stereo_detection_timeout_threshold_seconds;
+    float stereo_detection_hysteresis_seconds;
+  } multi_channel;
+} WapEchoCanceller3Config;
+
+/* EchoCanceller3Config() / ::CreateDefaultMultichannelConfig() (echo_canceller3_config.cc:288-301) */
+WapEchoCanceller3Config wap_echo_canceller3_config_default(void);
+WapEchoCanceller3Config wap_echo_canceller3_config_default_multichannel(void);
+size_t wap_echo_canceller3_config_sizeof(void);
+/* EchoCanceller3Config::Validate: clamps *config, returns true iff it was valid as given. */
+bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
+/* None when this library can run `config` (after Validate); UnsupportedConfig when a member that
+ * fixes the engine's structure differs from its default: delay.down_sampling_factor (4),
+ * delay.num_filters (5), delay.fixed_capture_delay_samples (0), delay.use_external_delay_estimator,
+ * delay.detect_pre_echo, filter lengths above 13 blocks, the filter.* / erle.* / ep_strength.* /
+ * echo_audibility.* / echo_removal_control.* / echo_model.* switches, erle.num_sections (1),
+ * echo_model.render_pre/post_window_size (1), suppressor.nearend_average_blocks (4),
+ * suppressor.use_subband_nearend_detection, suppressor.conservative_hf_suppression,
+ * render_levels.render_power_gain_db (0). */
+WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config);
+/* wap_create_with_config / wap_engine_create with an injected AEC3 config
+ * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig(config, multichannel_config)).
+ * multichannel_config may be NULL: the reference then derives it from `config`
+ * (echo_canceller3.cc:107-118); it applies to legs with more than one render or capture channel. */
+WapAudioProcessing* wap_create_with_aec3_config(WapConfig config, const WapEchoCanceller3Config* aec3_config,
+                                                const WapEchoCanceller3Config* aec3_multichannel_config);
+WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_streams, WapConfig config,
+                                              WapStreamConfig stream_format,
+                                              const WapEchoCanceller3Config* aec3_config,
+                                              const WapEchoCanceller3Config* aec3_multichannel_config);
+
 const char* wap_version(void);
 
 #ifdef __cplusplus

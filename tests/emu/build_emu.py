@@ -36,7 +36,11 @@ def build(verbose=True):
     for s in srcs:
         name = os.path.basename(s).rsplit(".", 1)[0]
         if name == "wap_k_echo":
-            tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c], os.path.join(OUT, "%s_%d%s.o" % (name, c, tag))) for c in range(5)]
+            for rt in (0, 1):
+                tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c, "-DWAP_EC3_RUNTIME=%d" % rt],
+                         os.path.join(OUT, "%s_%d%s%s.o" % (name, c, "_rt" if rt else "", tag))) for c in range(5)]
+        elif name == "wap_k_delay":
+            tus += [(s, ["-DWAP_EC3_RUNTIME=%d" % rt], os.path.join(OUT, name + ("_rt" if rt else "") + tag + ".o")) for rt in (0, 1)]
         else:
             tus.append((s, [], os.path.join(OUT, name + tag + ".o")))
     tus.append((os.path.join(HERE, "cuda_emu.cc"), [], os.path.join(OUT, "cuda_emu" + tag + ".o")))

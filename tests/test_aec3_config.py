@@ -1,0 +1,175 @@
+"""EchoCanceller3Config through the C ABI (SURVEY.md 8(b) EXT (i)): WapEchoCanceller3Config mirrors
+webrtc::EchoCanceller3Config, Validate restates EchoCanceller3Config::Validate, and engines created with
+a non-default config (wap_engine_create_with_aec3_config / wap_create_with_aec3_config) match the
+reference built through BuiltinAudioProcessingBuilder::SetEchoCancellerConfig bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import synthetic_leg, synthetic_leg_48k
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def api_lib(request):
+    return request.getfixturevalue("emu_lib" if request.param == "emu" else "gpu_lib")
+
+
+CONFIGS = {
+    # filter geometry: shorter refined / coarse filters, faster config changes, shorter initial state
+    "filter_lengths": {
+        "filter.refined.length_blocks": 10, "filter.coarse.length_blocks": 8,
+        "filter.refined_initial.length_blocks": 9, "filter.coarse_initial.length_blocks": 7,
+        "filter.config_change_duration_blocks": 100, "filter.initial_state_seconds": 1.0,
+        "filter.coarse_reset_hangover_blocks": 10,
+        "filter.refined.leakage_converged": 0.0001, "filter.refined.leakage_diverged": 0.1,
+        "filter.refined.error_floor": 0.002, "filter.refined.error_ceil": 3.0, "filter.refined.noise_gate": 1.0e7,
+        "filter.coarse.rate": 0.6, "filter.coarse.noise_gate": 1.0e7,
+        "filter.refined_initial.leakage_converged": 0.01, "filter.coarse_initial.rate": 0.8,
+    },
+    # suppressor tuning, ERLE limits, audibility weighting, high-frequency limiting
+    "suppressor_tuning": {
+        "suppressor.normal_tuning.mask_lf.enr_transparent": 0.2, "suppressor.normal_tuning.mask_lf.enr_suppress": 0.3,
+        "suppressor.normal_tuning.mask_lf.emr_transparent": 0.25, "suppressor.normal_tuning.mask_hf.enr_transparent": 0.05,
+        "suppressor.normal_tuning.mask_hf.enr_suppress": 0.15, "suppressor.normal_tuning.max_inc_factor": 1.5,
+        "suppressor.normal_tuning.max_dec_factor_lf": 0.35,
+        "suppressor.nearend_tuning.mask_lf.enr_transparent": 0.9, "suppressor.nearend_tuning.mask_lf.enr_suppress": 1.2,
+        "suppressor.nearend_tuning.max_inc_factor": 1.8,
+        "suppressor.last_lf_band": 4, "suppressor.first_hf_band": 10, "suppressor.last_lf_smoothing_band": 7,
+        "suppressor.last_permanent_lf_smoothing_band": 1,
+        "suppressor.dominant_nearend_detection.enr_threshold": 0.5, "suppressor.dominant_nearend_detection.enr_exit_threshold": 5.0,
+        "suppressor.dominant_nearend_detection.snr_threshold": 20.0, "suppressor.dominant_nearend_detection.hold_duration": 25,
+        "suppressor.dominant_nearend_detection.trigger_threshold": 6,
+        "suppressor.high_frequency_suppression.limiting_gain_band": 20,
+        "suppressor.high_frequency_suppression.bands_in_limiting_gain": 3, "suppressor.floor_first_increase": 0.0001,
+        "erle.min": 1.5, "erle.max_l": 6.0, "erle.max_h": 2.5,
+        "echo_audibility.low_render_limit": 192.0, "echo_audibility.normal_render_limit": 48.0,
+        "echo_audibility.floor_power": 100.0, "echo_audibility.audibility_threshold_lf": 8.0,
+        "echo_audibility.audibility_threshold_mf": 12.0, "echo_audibility.audibility_threshold_hf": 14.0,
+    },
+    # delay estimation, render levels, echo model, echo path strength, buffering, comfort noise
+    "delay_and_model": {
+        "delay.default_delay": 7, "delay.delay_headroom_samples": 64, "delay.hysteresis_limit_blocks": 2,
+        "delay.delay_selection_thresholds.initial": 3, "delay.delay_selection_thresholds.converged": 15,
+        "delay.delay_estimate_smoothing": 0.5, "delay.delay_estimate_smoothing_delay_found": 0.3,
+        "delay.delay_candidate_detection_threshold": 0.3,
+        "render_levels.active_render_limit": 80.0, "render_levels.poor_excitation_render_limit": 120.0,
+        "echo_model.noise_floor_hold": 30, "echo_model.min_noise_floor_power": 1.0e6, "echo_model.stationary_gate_slope": 8.0,
+        "echo_model.noise_gate_power": 20000.0, "echo_model.noise_gate_slope": 0.4,
+        "ep_strength.default_gain": 0.8, "ep_strength.default_len": 0.7, "ep_strength.nearend_len": 0.6,
+        "buffering.excess_render_detection_interval_blocks": 100, "buffering.max_allowed_excess_render_blocks": 4,
+        "comfort_noise.noise_floor_dbfs": -90.0,
+    },
+}
+
+
+def _ref_kv(overrides, **apm):
+    kv = dict(apm)
+    kv.update({"ec3." + k: v for k, v in overrides.items()})
+    return kv
+
+
+def test_config_struct_defaults_match_the_reference(api_lib, oracle):
+    import wap_b200
+    L = api_lib
+    assert L.wap_echo_canceller3_config_sizeof() == C.sizeof(wap_b200.WapEchoCanceller3Config)
+    d = L.wap_echo_canceller3_config_default()
+    assert L.wap_echo_canceller3_config_supported(C.byref(d)) == 0
+    valid = L.wap_echo_canceller3_config_validate(C.byref(d))
+    assert valid and oracle.ec3_validate({})[0]
+    # the reference's defaults, read back through its own Validate probe
+    for path in ("filter.refined.length_blocks", "delay.down_sampling_factor", "erle.min", "erle.max_l",
+                 "suppressor.normal_tuning.max_inc_factor", "filter.coarse.rate", "delay.default_delay",
+                 "filter.initial_state_seconds"):
+        assert wap_b200.ec3_get(d, path) == pytest.approx(oracle.ec3_validate({}, path)[1], rel=1e-7), path
+    m = L.wap_echo_canceller3_config_default_multichannel()
+    assert (m.filter.coarse.length_blocks, m.filter.coarse_initial.length_blocks) == (11, 11)
+    assert m.filter.coarse.rate == pytest.approx(0.95) and m.suppressor.normal_tuning.max_inc_factor == pytest.approx(1.5)
+    # structural members must keep their defaults
+    for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
+                    ("filter.use_linear_filter", False), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
+                    ("suppressor.use_subband_nearend_detection", True)):
+        c = L.wap_echo_canceller3_config_default()
+        wap_b200.ec3_set(c, path, v)
+        assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 7, path
+    c = L.wap_echo_canceller3_config_default()
+    c.delay.down_sampling_factor = 8
+    assert not L.wap_engine_create_with_aec3_config(0, 1, wap_b200.make_config(L), wap_b200.WapStreamConfig(16000, 1), C.byref(c), None)
+
+
+@pytest.mark.parametrize("probe,value", [
+    ("filter.refined.length_blocks", 0), ("delay.down_sampling_factor", 5), ("erle.min", 0.5), ("erle.max_l", 2.0e5),
+    ("suppressor.normal_tuning.max_inc_factor", 250.0), ("filter.coarse.rate", 1.5), ("delay.default_delay", 6000),
+    ("filter.initial_state_seconds", -1.0), ("erle.min", 5.0),
+])
+def test_validate_clamps_like_the_reference(api_lib, oracle, probe, value):
+    """wap_echo_canceller3_config_validate == EchoCanceller3Config::Validate (echo_canceller3_config.cc:101-286)."""
+    import wap_b200
+    L = api_lib
+    c = L.wap_echo_canceller3_config_default()
+    wap_b200.ec3_set(c, probe, value)
+    ok = L.wap_echo_canceller3_config_validate(C.byref(c))
+    ref_ok, ref_value = oracle.ec3_validate({probe: value}, probe)
+    assert ok == ref_ok
+    assert wap_b200.ec3_get(c, probe) == pytest.approx(ref_value, rel=1e-7)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_non_default_config_matches_the_reference(api_lib, oracle, name):
+    """A batched engine created with a non-default EchoCanceller3Config against the reference built with
+    SetEchoCancellerConfig: int16 output identical, ERLE within 0.1 dB, reported delay equal."""
+    import wap_b200
+    over = CONFIGS[name]
+    nf = 500
+    legs = [synthetic_leg(i, nf) for i in (3, 21)]
+    eng = wap_b200.Engine(2, 16000, lib=api_lib, aec=True, ns=True, ns_level=1, aec3=over)
+    out = np.zeros((2, nf * 160), np.int16)
+    stats = []
+    for f in range(nf):
+        sl = slice(f * 160, (f + 1) * 160)
+        eng.set_stream_delay_ms(0)
+        out[:, sl] = eng.process(np.stack([l[0][sl] for l in legs]), np.stack([l[1][sl] for l in legs]))
+        if (f + 1) % 100 == 0:
+            stats.append([(eng.stats(i).echo_return_loss_enhancement, eng.stats(i).delay_ms) for i in range(2)])
+    eng.close()
+    stats = np.array(stats)
+    for i, (far, near) in enumerate(legs):
+        ro, rs, err = oracle.RefApm(kv=_ref_kv(over, aec=1, ns=1, ns_level=1, max_rate=48000)).run_i16(16000, far, near, stats_every=100)
+        assert err == 0
+        d = np.abs(out[i].astype(np.int32) - ro.astype(np.int32))
+        assert d.max() == 0, (name, i, int(d.max()), int(np.argmax(d)) // 160)
+        assert np.abs(stats[:, i, 0] - rs[:, 3]).max() <= 0.1 and np.array_equal(stats[:, i, 1], rs[:, 5])
+    # the config really changes the result
+    ro_default, _, _ = oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, legs[0][0], legs[0][1])
+    assert not np.array_equal(ro_default, out[0])
+
+
+def test_non_default_config_through_the_single_leg_seam(api_lib, oracle):
+    """wap_create_with_aec3_config + the seam's per-frame entry points, 48 kHz three-band leg (upper-band
+    anti-howling parameters are part of the config)."""
+    import wap_b200
+    L = api_lib
+    over = dict(CONFIGS["filter_lengths"])
+    over.update({"suppressor.high_bands_suppression.anti_howling_activation_threshold": 25.0,
+                 "suppressor.high_bands_suppression.anti_howling_gain": 0.01})
+    nf = 150
+    far, near = synthetic_leg_48k(4, nf, 2.0)
+    ro, _, err = oracle.RefApm(kv=_ref_kv(over, aec=1, ns=1, ns_level=1, max_rate=48000)).run_i16(48000, far, near)
+    assert err == 0
+    cfg = wap_b200.make_aec3_config(L, over)
+    h = L.wap_create_with_aec3_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1, max_rate=48000), C.byref(cfg), None)
+    assert h
+    sc = wap_b200.WapStreamConfig(48000, 1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = np.zeros_like(near)
+    scratch = np.zeros(480, np.int16)
+    for f in range(nf):
+        r = np.ascontiguousarray(far[f * 480:(f + 1) * 480])
+        c = np.ascontiguousarray(near[f * 480:(f + 1) * 480])
+        o = np.zeros(480, np.int16)
+        assert L.wap_process_reverse_stream_i16(h, p(r), 480, sc, sc, p(scratch), 480) == 0
+        L.wap_set_stream_delay_ms(h, 0)
+        assert L.wap_process_stream_i16(h, p(c), 480, sc, sc, p(o), 480) == 0
+        out[f * 480:(f + 1) * 480] = o
+    L.wap_destroy(h)
+    assert np.array_equal(out, ro)

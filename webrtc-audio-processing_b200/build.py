@@ -35,7 +35,12 @@ def translation_units():
     for s in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc"))):
         base = os.path.basename(s).rsplit(".", 1)[0]
         if base == "wap_k_echo":
-            tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c], "%s_%d.o" % (base, c)) for c in range(ECHO_CLASSES)]
+            # per config class, default EchoCanceller3Config (compile-time constants) and run-time parameters
+            for rt in (0, 1):
+                tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c, "-DWAP_EC3_RUNTIME=%d" % rt], "%s_%d%s.o" % (base, c, "_rt" if rt else ""))
+                        for c in range(ECHO_CLASSES)]
+        elif base == "wap_k_delay":
+            tus += [(s, ["-DWAP_EC3_RUNTIME=%d" % rt], base + ("_rt.o" if rt else ".o")) for rt in (0, 1)]
         else:
             tus.append((s, [], base + ".o"))
     return tus

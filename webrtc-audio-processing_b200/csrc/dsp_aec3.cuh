@@ -99,7 +99,7 @@ WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int
   if (first_capture) {
     if (lane == 0) {
       s.capture_properly_started = 1;
-      rdb_reset(s);
+      rdb_reset(s, WAP_EC3(default_delay));
     }
     __syncwarp();
     delay_controller_reset(a, sc, true);
@@ -112,7 +112,8 @@ WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int
   __syncwarp();
   if (lane == 0) {
     s.render_event = kEventNone;
-    sc.ired[0] = rdb_prepare_capture_processing(s);
+    sc.ired[0] = rdb_prepare_capture_processing(s, WAP_EC3(default_delay), WAP_EC3(excess_render_detection_interval_blocks),
+                                                WAP_EC3(max_allowed_excess_render_blocks));
   }
   __syncwarp();
   if (sc.ired[0] == kEventRenderUnderrun) delay_controller_reset(a, sc, false);

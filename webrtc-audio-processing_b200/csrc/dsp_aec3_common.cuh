@@ -13,53 +13,24 @@
 #include "dsp_fft.cuh"
 #include "dsp_filters.cuh"
 #include "wap_dev.cuh"
+#include "wap_ec3_params.h"
 #include "wap_state.h"
 
 namespace wap {
 
-// Default EchoCanceller3Config (reference api/audio/echo_canceller3_config.h:21-275);
-// the engine accepts only this config class (wap_engine.cu validates).
-namespace ec3 {
-constexpr int kDefaultDelay = 5;               // delay.default_delay
-constexpr int kHeadroomSamples = 32;           // delay.delay_headroom_samples
-constexpr int kHysteresisLimitBlocks = 1;      // delay.hysteresis_limit_blocks
-constexpr int kThrInitial = 5, kThrConverged = 20;  // delay.delay_selection_thresholds
-constexpr float kMfSmoothing = 0.7f;           // delay_estimate_smoothing (both variants)
-constexpr float kMfThreshold = 0.2f;           // delay_candidate_detection_threshold
-constexpr float kMfExcitationLimit = 150.f;    // render_levels.poor_excitation_render_limit
-constexpr float kActiveRenderLimit = 100.f;    // render_levels.active_render_limit
-constexpr int kExcessRenderInterval = 250;     // buffering.excess_render_detection_interval_blocks
-constexpr int kMaxExcessRenderBlocks = 8;      // buffering.max_allowed_excess_render_blocks
-constexpr int kConfigChangeDuration = 250;     // filter.config_change_duration_blocks
-constexpr float kInitialStateSeconds = 2.5f;   // filter.initial_state_seconds
-constexpr int kCoarseResetHangover = 25;       // filter.coarse_reset_hangover_blocks
-// filter.refined / refined_initial: leakage_converged, leakage_diverged, error_floor, error_ceil, noise_gate
-#define WAP_EC3_REFINED {0.00005f, 0.05f, 0.001f, 2.f, 20075344.f}
-#define WAP_EC3_REFINED_INITIAL {0.005f, 0.5f, 0.001f, 2.f, 20075344.f}
-#define WAP_EC3_COARSE {0.7f, 20075344.f}
-#define WAP_EC3_COARSE_INITIAL {0.9f, 20075344.f}
-constexpr float kErleMin = 1.f, kErleMaxL = 4.f, kErleMaxH = 1.5f;  // erle
-constexpr float kDefaultGain = 1.f;            // ep_strength.default_gain
-constexpr float kDefaultLen = 0.83f;           // ep_strength.default_len (= nearend_len)
-constexpr float kNoiseFloorHold = 50;          // echo_model.noise_floor_hold
-constexpr float kMinNoiseFloorPower = 1638400.f;
-constexpr float kStationaryGateSlope = 10.f;
-constexpr float kNoiseGatePower = 27509.42f;
-constexpr float kNoiseGateSlope = 0.3f;
-constexpr float kLowRenderLimit = 4 * 64.f, kNormalRenderLimit = 64.f, kFloorPower = 2 * 64.f;
-constexpr float kAudibilityThreshold = 10.f;   // lf = mf = hf
-constexpr float kFloorFirstIncrease = 0.00001f;
-constexpr int kLastLfSmoothingBand = 5, kLastPermanentLfSmoothingBand = 0;
-constexpr int kLastLfBand = 5, kFirstHfBand = 8;
-constexpr int kLimitingGainBand = 16;          // high_frequency_suppression (bands_in_limiting_gain = 1)
-// dominant_nearend_detection
-constexpr float kDnEnrThreshold = .25f, kDnEnrExitThreshold = 10.f, kDnSnrThreshold = 30.f;
-constexpr int kDnHoldDuration = 50, kDnTriggerThreshold = 12;
-// suppressor tunings: {lf.enr_transparent, lf.enr_suppress, lf.emr_transparent, hf..., max_inc, max_dec_lf}
-struct Tuning { float lf_t, lf_s, lf_e, hf_t, hf_s, hf_e, max_inc, max_dec_lf; };
-#define WAP_EC3_NORMAL_TUNING {.3f, .4f, .3f, .07f, .1f, .3f, 2.0f, 0.25f}
-#define WAP_EC3_NEAREND_TUNING {1.09f, 1.1f, .3f, .1f, .3f, .3f, 2.0f, 0.25f}
-}  // namespace ec3
+// EchoCanceller3Config parameters: wap_ec3_params.h (compile-time constants for the default config,
+// a run-time Ec3Params copy in `sc.ep` for the instances that serve other configs).
+#if WAP_EC3_RUNTIME
+#define WAP_EC3_ARR(name) (sc.ep.name)
+#else
+WAP_DEVCONST float ec3d_refined[5] = WAP_EC3D_REFINED;
+WAP_DEVCONST float ec3d_refined_initial[5] = WAP_EC3D_REFINED_INITIAL;
+WAP_DEVCONST float ec3d_coarse[2] = WAP_EC3D_COARSE;
+WAP_DEVCONST float ec3d_coarse_initial[2] = WAP_EC3D_COARSE_INITIAL;
+WAP_DEVCONST Ec3Tuning ec3d_normal_tuning = WAP_EC3D_NORMAL_TUNING;
+WAP_DEVCONST Ec3Tuning ec3d_nearend_tuning = WAP_EC3D_NEAREND_TUNING;
+#define WAP_EC3_ARR(name) (::wap::ec3d_##name)
+#endif
 
 constexpr int kNumBlocksPerSecond = 250;
 constexpr int kMaxRingDelay = kRingBlocks - 1 - kMaxPartitions;  // RenderDelayBufferImpl::MaxDelay(): 153
@@ -133,6 +104,9 @@ struct AecScratch {
   float ds[kSubBlock];     // decimated capture sub-block
   float red[32];           // reduction / broadcast exchange
   int ired[32];
+#if WAP_EC3_RUNTIME
+  Ec3Params ep;            // this engine's EchoCanceller3Config parameters (copied from TickArgs per tick)
+#endif
   union {
     AecMfScratch mf;       // k_delay
     struct {               // k_echo (same members as AecEchoScratch)

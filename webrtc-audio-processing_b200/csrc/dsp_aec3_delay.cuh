@@ -21,7 +21,20 @@
 
 namespace wap {
 
-constexpr float kMfX2SumThreshold = 512.f * ec3::kMfExcitationLimit * ec3::kMfExcitationLimit;
+// x2_sum_threshold = filters_[0].size() * excitation_limit^2 (matched_filter.cc:667-668)
+#define kMfX2SumThreshold (512.f * WAP_EC3(poor_excitation_render_limit) * WAP_EC3(poor_excitation_render_limit))
+
+// MatchedFilter::Update(use_slow_smoothing = MatchedFilterLagAggregator::ReliableDelayFound()):
+// delay_estimate_smoothing until a significant candidate was found, then ..._delay_found
+// (echo_path_delay_estimator.cc:49-50,85-86; matched_filter.cc:662-663).
+WAP_DEV float mf_smoothing(const AecScratch& sc) {
+#if WAP_EC3_RUNTIME
+  return sc.s.agg_significant_candidate_found ? sc.ep.delay_estimate_smoothing_delay_found : sc.ep.delay_estimate_smoothing;
+#else
+  static_assert(ec3d::delay_estimate_smoothing == ec3d::delay_estimate_smoothing_delay_found, "default config: one smoothing");
+  return ec3d::delay_estimate_smoothing;
+#endif
+}
 
 // hsum over the 8 "c" values of one accumulator group in the order of hsum_ab
 // (matched_filter_avx2.cc:35-43): ((c0+c1)+(c2+c3)) + ((c4+c5)+(c6+c7)),
@@ -150,7 +163,7 @@ WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) 
     error_sum += e * e;
     __syncwarp();
     if (x2_sum > kMfX2SumThreshold && !saturation) {
-      const float alpha = ec3::kMfSmoothing * e / x2_sum;
+      const float alpha = mf_smoothing(sc) * e / x2_sum;
 #pragma unroll
       for (int j = 0; j < 16; j += 2) mf_fma2(h[j], h[j + 1], xv[j], xv[j + 1], alpha);
       updated = 1;
@@ -399,7 +412,7 @@ WAP_DEV void mf_pair(Aec3State& a, AecScratch& sc, int nA, int nB, const float* 
     const bool saturation = yi >= 32000.f || yi <= -32000.f;
     error_sum += e * e;
     if (on && x2_sum > kMfX2SumThreshold && !saturation) {
-      const float alpha = ec3::kMfSmoothing * e / x2_sum;
+      const float alpha = mf_smoothing(sc) * e / x2_sum;
       if (kWrap) {
         // groups of 8 of each chunk are fused; the < 8 taps at the end of each chunk are not
         const int c1 = wrapped_half ? chunk1 : kMfLen;
@@ -572,7 +585,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
       const int lag_estimate = sc.mf.peak[n];
       const float error_sum = sc.mf.err_sum[n];
       const bool reliable = lag_estimate > 2 && lag_estimate < (kMfLen - 10) &&
-                            error_sum < ec3::kMfThreshold * error_sum_anchor;
+                            error_sum < WAP_EC3(delay_candidate_detection_threshold) * error_sum_anchor;
       const int lag = lag_estimate + alignment_shift;
       if (sc.mf.updated[n] && reliable && error_sum < winner_error_sum) {
         winner_error_sum = error_sum;
@@ -639,7 +652,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   // ---- MatchedFilterLagAggregator::Aggregate
   int has_agg = 0, agg_quality = 0, agg_delay = 0;
   if (winner_index != -1) {
-    const int headroom = ec3::kHeadroomSamples / kDownSampling;
+    const int headroom = WAP_EC3(delay_headroom_samples) / kDownSampling;
     // PreEchoLagAggregator::Aggregate (:139-183)
     {
       int blk = imax(0, pre_echo_lag - headroom) >> 4;
@@ -707,8 +720,8 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
         cand = (v > vmax || (v == vmax && lag < prev_cand)) ? lag : prev_cand;
       }
       const int count = a.lag_hist[cand];
-      const int sig = s.agg_significant_candidate_found || count > ec3::kThrConverged;
-      if (count > ec3::kThrConverged || (count > ec3::kThrInitial && !sig)) {
+      const int sig = s.agg_significant_candidate_found || count > WAP_EC3(thr_converged);
+      if (count > WAP_EC3(thr_converged) || (count > WAP_EC3(thr_initial) && !sig)) {
         has_agg = 1;
         agg_quality = sig ? kQualityRefined : kQualityCoarse;
         agg_delay = s.pre_candidate;
@@ -747,7 +760,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
       const bool use_hysteresis =
           s.ctl_last_quality == kQualityRefined && s.ctl_delay_samples_quality == kQualityRefined;
       // ComputeBufferDelay (render_delay_controller.cc:65-82)
-      const int hysteresis = use_hysteresis ? ec3::kHysteresisLimitBlocks : 0;
+      const int hysteresis = use_hysteresis ? WAP_EC3(hysteresis_limit_blocks) : 0;
       int new_delay_blocks = s.ctl_delay_samples >> 6;
       if (s.ctl_has_delay) {
         const int current = s.ctl_delay;

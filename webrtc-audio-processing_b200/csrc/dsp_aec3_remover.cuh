@@ -26,11 +26,10 @@
 
 namespace wap {
 
-WAP_DEVCONST ec3::Tuning kNormalTuning = WAP_EC3_NORMAL_TUNING;
-WAP_DEVCONST ec3::Tuning kNearendTuning = WAP_EC3_NEAREND_TUNING;
 
 constexpr float kX2BandEnergyThreshold = 44015068.0f;  // subband/fullband ERLE, ERL kX2Min
-constexpr float kActiveRenderEnergy = ec3::kActiveRenderLimit * ec3::kActiveRenderLimit * 64.f;
+// (active_render_limit^2) * kFftLengthBy2 (aec_state.cc:235-237)
+#define kActiveRenderEnergy ((WAP_EC3(active_render_limit) * WAP_EC3(active_render_limit)) * 64.f)
 
 // Left-to-right sum of p[from..to) -- the order std::accumulate uses.
 WAP_DEV float chain_sum(const float* p, int from, int to) {
@@ -44,9 +43,9 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
   const int lane = lane_id();
   #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
-    a.erle[k] = ec3::kErleMin;
-    a.erle_onset_comp[k] = ec3::kErleMin;
-    a.erle_unbounded[k] = ec3::kErleMin;
+    a.erle[k] = WAP_EC3(erle_min);
+    a.erle_onset_comp[k] = WAP_EC3(erle_min);
+    a.erle_unbounded[k] = WAP_EC3(erle_min);
     a.coming_onset[k] = 1;
     a.erle_hold_counters[k] = 0;
     a.accum_Y2[k] = 0.f;
@@ -64,7 +63,7 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
     s.fb_Y2_acum = 0.f;
     s.fb_max_erle_log2 = -10.f;
     s.fb_min_erle_log2 = 33.f;
-    s.fb_erle_time_domain_log2 = fast_approx_log2f(ec3::kErleMin + 1e-3f);
+    s.fb_erle_time_domain_log2 = fast_approx_log2f(WAP_EC3(erle_min) + 1e-3f);
     s.fb_hold_counter = 0;
     if (delay_change) s.erle_blocks_since_reset = 0;
   }
@@ -72,12 +71,13 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
 }
 
 // ---- FilterAnalyzer::Reset (filter_analyzer.cc:71-78), lane 0
-WAP_DEV void filter_analyzer_reset(Aec3Scalars& s) {
+WAP_DEV void filter_analyzer_reset(AecScratch& sc) {
+  Aec3Scalars& s = sc.s;
   s.fa_blocks_since_reset = 0;
   s.fa_region_start = 0;
   s.fa_region_end = 0;
   s.fa_peak_index = 0;
-  s.fa_gain = ec3::kDefaultGain;
+  s.fa_gain = WAP_EC3(default_gain);
   s.cfd_significant_peak = 0;
   s.cfd_floor_accum = 0.f;
   s.cfd_secondary_peak = 0.f;
@@ -94,7 +94,7 @@ WAP_DEV void aec_state_handle_echo_path_change(Aec3State& a, AecScratch& sc, con
   __syncwarp();
   if (v.delay_change != kDelayAdjNone) {
     if (lane_id() == 0) {
-      filter_analyzer_reset(s);
+      filter_analyzer_reset(sc);
       s.capture_signal_saturation = 0;
       s.strong_not_saturated_render_blocks = 0;
       s.blocks_with_active_render = 0;
@@ -259,7 +259,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
       s.fd_external_delay = ext_delay;
     }
     const bool may_not_have_converged = s.strong_not_saturated_render_blocks < 2 * kNumBlocksPerSecond;
-    if (may_not_have_converged && s.fd_has_external) s.fd_filter_delay = ec3::kHeadroomSamples / kBlock;
+    if (may_not_have_converged && s.fd_has_external) s.fd_filter_delay = WAP_EC3(delay_headroom_samples) / kBlock;
     else s.fd_filter_delay = s.fa_filter_delay_blocks;
     s.fd_min_filter_delay = s.fd_filter_delay;
   }
@@ -292,7 +292,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   const int idx_past = ring_inc(idx_at_delay, kRingBlocks);
   #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
-    const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * ec3::kDefaultLen;
+    const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * WAP_EC3(default_len);   // ReverbDecay(mild = false)
     a.avg_render_reverb[k] = rev;
     const float x2 = a.spectra[idx_at_delay][k];
     r.v2[k] = x2;
@@ -340,21 +340,21 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
             if (onset) onset = 0;
             hold = 250;  // kBlocksForOnsetDetection
           }
-          const float max_erle = k < 32 ? ec3::kErleMaxL : ec3::kErleMaxH;
+          const float max_erle = k < 32 ? WAP_EC3(erle_max_l) : WAP_EC3(erle_max_h);
           float alpha = 0.05f;
           if (new_erle < erle) alpha = low ? 0.f : 0.1f;
-          erle = clampr(erle + alpha * (new_erle - erle), ec3::kErleMin, max_erle);
+          erle = clampr(erle + alpha * (new_erle - erle), WAP_EC3(erle_min), max_erle);
           alpha = 0.05f;
           if (new_erle < erle_oc) alpha = low ? 0.f : 0.1f;
-          erle_oc = clampr(erle_oc + alpha * (new_erle - erle_oc), ec3::kErleMin, max_erle);
+          erle_oc = clampr(erle_oc + alpha * (new_erle - erle_oc), WAP_EC3(erle_min), max_erle);
           alpha = 0.05f;
           if (new_erle < erle_u) alpha = low ? 0.f : 0.1f;
-          erle_u = clampr(erle_u + alpha * (new_erle - erle_u), ec3::kErleMin, 100000.0f);
+          erle_u = clampr(erle_u + alpha * (new_erle - erle_u), WAP_EC3(erle_min), 100000.0f);
         }
         // DecreaseErlePerBandForLowRenderSignals (erle_during_onsets_ stays at min_erle)
         --hold;
         if (hold <= 250 - 100) {
-          if (erle_oc > ec3::kErleMin) erle_oc = fmaxr(ec3::kErleMin, 0.97f * erle_oc);
+          if (erle_oc > WAP_EC3(erle_min)) erle_oc = fmaxr(WAP_EC3(erle_min), 0.97f * erle_oc);
           if (hold <= 0) { onset = 1; hold = 0; }
         }
         a.erle[k] = erle;
@@ -397,7 +397,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
           else s.fb_inst_quality += 0.07f * (quality_estimate - s.fb_inst_quality);
           s.fb_hold_counter = 100;  // kBlocksToHoldErle
           s.fb_erle_time_domain_log2 += 0.05f * (s.fb_erle_log2 - s.fb_erle_time_domain_log2);
-          s.fb_erle_time_domain_log2 = fmaxr(s.fb_erle_time_domain_log2, fast_approx_log2f(ec3::kErleMin + 1e-3f));
+          s.fb_erle_time_domain_log2 = fmaxr(s.fb_erle_time_domain_log2, fast_approx_log2f(WAP_EC3(erle_min) + 1e-3f));
         }
       }
       --s.fb_hold_counter;
@@ -465,7 +465,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     // InitialState::Update
     s.init_strong_blocks += (active_render && !saturated_capture) ? 1 : 0;
     const int prev_initial_state = s.init_state;
-    s.init_state = (float)s.init_strong_blocks < ec3::kInitialStateSeconds * kNumBlocksPerSecond;
+    s.init_state = (float)s.init_strong_blocks < WAP_EC3(initial_state_seconds) * kNumBlocksPerSecond;
     s.init_transition_triggered = !s.init_state && prev_initial_state;
     // LegacyTransparentModeImpl::Update
     ++s.tm_capture_block_counter;
@@ -613,9 +613,11 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   const bool saturated_echo = s.saturated_echo != 0;
   const bool transparent = s.tm_active != 0;
   const float* X2_latest = a.spectra[s.spectra_read];
-  const float echo_path_gain = transparent ? 0.01f * 0.01f : ec3::kDefaultGain * ec3::kDefaultGain;
+  const float echo_path_gain = transparent ? 0.01f * 0.01f : WAP_EC3(default_gain) * WAP_EC3(default_gain);
   const int delay = s.fd_min_filter_delay;
   const bool add_reverb = usable || !transparent;
+  // AecState::ReverbDecay(mild = dominant_nearend) (residual_echo_estimator.cc:384, aec_state.h:127)
+  const float reverb_decay = dominant_nearend ? WAP_EC3(nearend_len) : WAP_EC3(default_len);
   const int first_reverb_partition = usable ? s.fa_filter_length_blocks + 1 : delay + 1;
   const float* X2_reverb_src = a.spectra[ring_off(s.spectra_read, first_reverb_partition, kRingBlocks)];
   const float* erle = dominant_nearend ? a.erle : a.erle_onset_comp;
@@ -631,8 +633,8 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
       if (p < floor) {
         floor = p;
         cnt = 0;
-      } else if (cnt >= (int)ec3::kNoiseFloorHold) {
-        floor = fmaxr(floor * 1.1f, ec3::kMinNoiseFloorPower);
+      } else if (cnt >= (int)WAP_EC3(noise_floor_hold)) {
+        floor = fmaxr(floor * 1.1f, WAP_EC3(min_noise_floor_power));
       } else {
         ++cnt;
       }
@@ -657,15 +659,15 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
         X2 = fmaxr(X2, a.spectra[idx][k]);
         idx = ring_inc(idx, kRingBlocks);
       }
-      if (ec3::kNoiseGatePower > X2) X2 = fmaxr(0.f, X2 - ec3::kNoiseGateSlope * (ec3::kNoiseGatePower - X2));
-      X2 -= ec3::kStationaryGateSlope * floor;
+      if (WAP_EC3(noise_gate_power) > X2) X2 = fmaxr(0.f, X2 - WAP_EC3(noise_gate_slope) * (WAP_EC3(noise_gate_power) - X2));
+      X2 -= WAP_EC3(stationary_gate_slope) * floor;
       X2 = fmaxr(0.f, X2);
       R2 = R2u = X2 * echo_path_gain;
     }
     if (add_reverb) {
       // UpdateReverb + AddReverb
       const float scaling = usable ? a.tail_response[k] : echo_path_gain;
-      const float rev = (a.echo_reverb[k] + X2_reverb_src[k] * scaling) * ec3::kDefaultLen;
+      const float rev = (a.echo_reverb[k] + X2_reverb_src[k] * scaling) * reverb_decay;
       a.echo_reverb[k] = rev;
       R2 += rev;
       R2u += rev;
@@ -677,10 +679,10 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
 }
 
 // GainParameters thresholds for bin k (suppression_gain.cc:452-477).
-WAP_DEV void gain_params(const ec3::Tuning& t, int k, float* enr_transparent, float* enr_suppress, float* emr_transparent) {
+WAP_DEV void gain_params(const AecScratch& sc, const Ec3Tuning& t, int k, float* enr_transparent, float* enr_suppress, float* emr_transparent) {
   float aa;
-  if (k <= ec3::kLastLfBand) aa = 0.f;
-  else if (k < ec3::kFirstHfBand) aa = fdiv((float)(k - ec3::kLastLfBand), (float)(ec3::kFirstHfBand - ec3::kLastLfBand));
+  if (k <= WAP_EC3(last_lf_band)) aa = 0.f;
+  else if (k < WAP_EC3(first_hf_band)) aa = fdiv((float)(k - WAP_EC3(last_lf_band)), (float)(WAP_EC3(first_hf_band) - WAP_EC3(last_lf_band)));
   else aa = 1.f;
   *enr_transparent = (1 - aa) * t.lf_t + aa * t.hf_t;
   *enr_suppress = (1 - aa) * t.lf_s + aa * t.hf_s;
@@ -712,15 +714,15 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   __syncwarp();
   if (lane == 0) {
     const float ne_sum = sc.red[16], echo_sum = sc.red[17], noise_sum = sc.red[18];
-    if (echo_sum < ec3::kDnEnrThreshold * ne_sum && ne_sum > ec3::kDnSnrThreshold * noise_sum) {
-      if (++s.dn_trigger_counter >= ec3::kDnTriggerThreshold) {
-        s.dn_hold_counter = ec3::kDnHoldDuration;
-        s.dn_trigger_counter = ec3::kDnTriggerThreshold;
+    if (echo_sum < WAP_EC3(dn_enr_threshold) * ne_sum && ne_sum > WAP_EC3(dn_snr_threshold) * noise_sum) {
+      if (++s.dn_trigger_counter >= WAP_EC3(dn_trigger_threshold)) {
+        s.dn_hold_counter = WAP_EC3(dn_hold_duration);
+        s.dn_trigger_counter = WAP_EC3(dn_trigger_threshold);
       }
     } else {
       s.dn_trigger_counter = imax(0, s.dn_trigger_counter - 1);
     }
-    if (echo_sum > ec3::kDnEnrExitThreshold * ne_sum && echo_sum > ec3::kDnSnrThreshold * noise_sum) s.dn_hold_counter = 0;
+    if (echo_sum > WAP_EC3(dn_enr_exit_threshold) * ne_sum && echo_sum > WAP_EC3(dn_snr_threshold) * noise_sum) s.dn_hold_counter = 0;
     s.dn_hold_counter = imax(0, s.dn_hold_counter - 1);
     s.dn_nearend_state = s.dn_hold_counter > 0;
     // LowNoiseRenderDetector
@@ -733,14 +735,14 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   const bool low_noise_render = sc.ired[8] != 0;
   const bool nearend_state = s.dn_nearend_state != 0;
   const bool saturated_echo = s.saturated_echo != 0;
-  const ec3::Tuning& tun = nearend_state ? kNearendTuning : kNormalTuning;
-  const float min_echo_power = low_noise_render ? ec3::kLowRenderLimit : ec3::kNormalRenderLimit;
+  const Ec3Tuning& tun = nearend_state ? WAP_EC3_ARR(nearend_tuning) : WAP_EC3_ARR(normal_tuning);
+  const float min_echo_power = low_noise_render ? WAP_EC3(low_render_limit) : WAP_EC3(normal_render_limit);
   const int mem_index = s.sg_nearend_mem_index;
   // LowerBandGain
   #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     const float last_gain = a.last_gain[k];
-    const float max_gain = fminr(fmaxr(last_gain * tun.max_inc, ec3::kFloorFirstIncrease), 1.f);
+    const float max_gain = fminr(fmaxr(last_gain * tun.max_inc, WAP_EC3(floor_first_increase)), 1.f);
     // MovingAverage::Average (mem_len 4 -> 3 stored blocks, scaling 1/4)
     const float in = nearend[k];
     float ne = in;
@@ -749,9 +751,10 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     ne = a.nearend_mem[2][k] + ne;
     ne *= 0.25f;
     a.nearend_mem[mem_index][k] = in;
-    // WeightEchoForAudibility (the three ranges share threshold and normaliser)
-    const float threshold = ec3::kFloorPower * ec3::kAudibilityThreshold;
-    const float normalizer = 1.f / (threshold - ec3::kFloorPower);
+    // WeightEchoForAudibility: bins [0,3) / [3,7) / [7,65) (suppression_gain.cc:104-118)
+    const float audibility = k < 3 ? WAP_EC3(audibility_threshold_lf) : (k < 7 ? WAP_EC3(audibility_threshold_mf) : WAP_EC3(audibility_threshold_hf));
+    const float threshold = WAP_EC3(floor_power) * audibility;
+    const float normalizer = 1.f / (threshold - WAP_EC3(floor_power));
     const float echo = r.R2[k];
     float weighted = echo;
     if (echo < threshold) {
@@ -763,8 +766,8 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     if (!saturated_echo) {
       min_gain = weighted > 0.f ? min_echo_power / weighted : 1.f;
       min_gain = fminr(min_gain, 1.f);
-      if (k <= ec3::kLastLfSmoothingBand) {  // lf_smoothing_during_initial_phase = true
-        if (a.last_nearend[k] > a.last_echo[k] || k <= ec3::kLastPermanentLfSmoothingBand) {
+      if (k <= WAP_EC3(last_lf_smoothing_band)) {  // lf_smoothing_during_initial_phase = true
+        if (a.last_nearend[k] > a.last_echo[k] || k <= WAP_EC3(last_permanent_lf_smoothing_band)) {
           min_gain = fmaxr(min_gain, last_gain * tun.max_dec_lf);
           min_gain = fminr(min_gain, 1.f);
         }
@@ -772,7 +775,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     }
     // GainToNoAudibleEcho (masker = comfort noise spectrum N2)
     float enr_t, enr_s, emr_t;
-    gain_params(tun, k, &enr_t, &enr_s, &emr_t);
+    gain_params(sc, tun, k, &enr_t, &enr_s, &emr_t);
     const float enr = weighted / (ne + 1.f);
     const float emr = weighted / (a.cng_N2[k] + 1.f);
     float g = 1.0f;
@@ -790,15 +793,19 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     // LimitLowFrequencyGains / LimitHighFrequencyGains
     const float g12 = fminr(r.gain[1], r.gain[2]);
     const bool limit_hf = !nearend_state || clock_drift;
-    const float min_upper_gain = fminr(1.f, r.gain[ec3::kLimitingGainBand]);
-    const float g63 = limit_hf ? fminr(r.gain[63], min_upper_gain) : r.gain[63];
+    // min over bands [limiting_gain_band, + bands_in_limiting_gain) (suppression_gain.cc:44-62)
+    float min_upper_gain = 1.f;
+    for (int band = WAP_EC3(limiting_gain_band); band < WAP_EC3(limiting_gain_band) + WAP_EC3(bands_in_limiting_gain); ++band)
+      min_upper_gain = fminr(min_upper_gain, r.gain[band]);
+    const bool limit_bands = WAP_EC3(bands_in_limiting_gain) > 0;
+    const float g63 = limit_hf ? (limit_bands ? fminr(r.gain[63], min_upper_gain) : r.gain[63]) : r.gain[63];
     __syncwarp();
     #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       float g = r.gain[k];
       if (k <= 1) g = g12;
       if (limit_hf) {
-        if (k > ec3::kLimitingGainBand) g = fminr(g, min_upper_gain);
+        if (limit_bands && k > WAP_EC3(limiting_gain_band)) g = fminr(g, min_upper_gain);
         if (k == 64) g = g63;
       }
       a.last_gain[k] = g;
@@ -834,10 +841,10 @@ WAP_DEV float upper_bands_gain(const Aec3State& a, AecScratch& sc, const UpperBa
   const float low_band_energy = sc.red[16];
   const float high_band_energy = fmaxr(fmaxr(0.f, sc.red[17]), sc.red[18]);
   float anti_howling_gain;
-  const float activation_threshold = kBlock * 400.f;  // anti_howling_activation_threshold
+  const float activation_threshold = kBlock * WAP_EC3(hb_anti_howling_activation_threshold);
   if (high_band_energy < fmaxr(low_band_energy, activation_threshold)) anti_howling_gain = 1.f;
-  else anti_howling_gain = 1.f * sqrtf(low_band_energy / high_band_energy);  // anti_howling_gain = 1
-  // gain_bound: max_gain_during_echo == 1 in the default config, so the echo/noise test cannot lower it.
+  else anti_howling_gain = WAP_EC3(hb_anti_howling_gain) * sqrtf(low_band_energy / high_band_energy);
+  // gain_bound: max_gain_during_echo must be 1 (the default; checked by the host), so the echo/noise test cannot lower it.
   const float gain_bound = 1.f;
   (void)echo_spectrum;
   __syncwarp();
@@ -889,7 +896,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
 
   if (s.init_transition_triggered) {
     if (lane == 0) {
-      subtractor_exit_initial_state(s);
+      subtractor_exit_initial_state(sc);
       s.sg_initial_state = 0;
     }
     __syncwarp();

@@ -25,7 +25,7 @@ WAP_DEV int rdb_compute_delay(const Aec3Scalars& s) {
   return internal_delay - latency_blocks;
 }
 // Reset (:161-197)
-WAP_DEV void rdb_reset(Aec3Scalars& s) {
+WAP_DEV void rdb_reset(Aec3Scalars& s, int default_delay) {
   s.last_call_was_render = 0;
   s.num_api_calls_in_a_row = 1;
   s.min_latency_blocks = 0;
@@ -40,7 +40,7 @@ WAP_DEV void rdb_reset(Aec3Scalars& s) {
     s.has_delay = 1;
     s.external_delay_verified = 0;
   } else {
-    rdb_apply_total_delay(s, ec3::kDefaultDelay);
+    rdb_apply_total_delay(s, default_delay);
     s.has_delay = 0;
   }
 }
@@ -68,7 +68,9 @@ WAP_DEV void rdb_set_audio_buffer_delay(Aec3Scalars& s, int delay_ms) {
   s.has_external_delay = 1;
 }
 // PrepareCaptureProcessing (:249-301)
-WAP_DEV int rdb_prepare_capture_processing(Aec3Scalars& s) {
+// default_delay / interval / max_excess: delay.default_delay, buffering.excess_render_detection_interval_blocks,
+// buffering.max_allowed_excess_render_blocks
+WAP_DEV int rdb_prepare_capture_processing(Aec3Scalars& s, int default_delay, int interval, int max_excess) {
   int event = kEventNone;
   if (s.has_delay) {
     if (s.last_call_was_render) {
@@ -82,13 +84,13 @@ WAP_DEV int rdb_prepare_capture_processing(Aec3Scalars& s) {
   bool excess = false;
   const int latency_blocks = rdb_buffer_latency(s);
   s.min_latency_blocks = imin(s.min_latency_blocks, latency_blocks);
-  if (++s.excess_render_detection_counter >= ec3::kExcessRenderInterval) {
-    excess = s.min_latency_blocks > ec3::kMaxExcessRenderBlocks;
+  if (++s.excess_render_detection_counter >= interval) {
+    excess = s.min_latency_blocks > max_excess;
     s.min_latency_blocks = latency_blocks;
     s.excess_render_detection_counter = 0;
   }
   if (excess) {
-    rdb_reset(s);
+    rdb_reset(s, default_delay);
     event = kEventRenderOverrun;
   } else if (s.lr_read == s.lr_write) {  // RenderUnderrun
     rdb_increment_read_indices(s);

@@ -15,11 +15,6 @@
 
 namespace wap {
 
-WAP_DEVCONST float kRefinedCfg[5] = WAP_EC3_REFINED;
-WAP_DEVCONST float kRefinedInitialCfg[5] = WAP_EC3_REFINED_INITIAL;
-WAP_DEVCONST float kCoarseCfg[2] = WAP_EC3_COARSE;
-WAP_DEVCONST float kCoarseInitialCfg[2] = WAP_EC3_COARSE_INITIAL;
-
 // ZeroFilter (adaptive_fir_filter.cc:464-476)
 WAP_DEV void fir_zero_partitions(float (*H_re)[kBinsPad], float (*H_im)[kBinsPad], int from, int to) {
   for (int p = from; p < to; ++p)
@@ -27,8 +22,8 @@ WAP_DEV void fir_zero_partitions(float (*H_re)[kBinsPad], float (*H_im)[kBinsPad
 }
 
 // AdaptiveFirFilter::SetSizePartitions(size, immediate_effect = true) scalars; returns the old size.
-WAP_DEV int fir_set_size_immediate(int* cur, int* target, int* old_target, int* counter, int* ptc, int size) {
-  *target = imin(kMaxPartitions, size);
+WAP_DEV int fir_set_size_immediate(int* cur, int* target, int* old_target, int* counter, int* ptc, int size, int max_size) {
+  *target = imin(max_size, size);
   const int old = *cur;
   *cur = *old_target = *target;
   *ptc = imin(*ptc, *cur - 1);
@@ -37,11 +32,11 @@ WAP_DEV int fir_set_size_immediate(int* cur, int* target, int* old_target, int* 
 }
 
 // AdaptiveFirFilter::UpdateSize scalars (:542-565); returns the old size.
-WAP_DEV int fir_update_size(int* cur, int* target, int* old_target, int* counter, int* ptc) {
+WAP_DEV int fir_update_size(const AecScratch& sc, int* cur, int* target, int* old_target, int* counter, int* ptc) {
   const int old = *cur;
   if (*counter > 0) {
     --*counter;
-    const float one_by = 1.f / ec3::kConfigChangeDuration;
+    const float one_by = 1.f / WAP_EC3(config_change_duration_blocks);
     const float change_factor = *counter * one_by;
     const float v = (float)*old_target * change_factor + (float)*target * (1.f - change_factor);
     *cur = (int)v;
@@ -58,8 +53,8 @@ WAP_DEV void subtractor_handle_echo_path_change(Aec3State& a, AecScratch& sc, co
   Aec3Scalars& s = sc.s;
   if (v.delay_change != kDelayAdjNone) {
     __syncwarp();
-    fir_zero_partitions(a.Hr_re, a.Hr_im, s.fr_current_size, kMaxPartitions);
-    fir_zero_partitions(a.Hc_re, a.Hc_im, s.fc_current_size, kMaxPartitions);
+    fir_zero_partitions(a.Hr_re, a.Hr_im, s.fr_current_size, WAP_EC3(refined_len));
+    fir_zero_partitions(a.Hc_re, a.Hc_im, s.fc_current_size, WAP_EC3(coarse_len));
     #pragma unroll
     for (int k = lane; k < kBins; k += 32) a.H_error[k] = 10000.f;
     __syncwarp();
@@ -70,14 +65,16 @@ WAP_DEV void subtractor_handle_echo_path_change(Aec3State& a, AecScratch& sc, co
       }
       s.cg_poor_excitation_counter = 0;
       s.cg_call_counter = 0;
-      for (int i = 0; i < 5; ++i) s.rg_cur[i] = s.rg_old[i] = s.rg_tgt[i] = kRefinedInitialCfg[i];
+      for (int i = 0; i < 5; ++i) s.rg_cur[i] = s.rg_old[i] = s.rg_tgt[i] = WAP_EC3_ARR(refined_initial)[i];
       s.rg_config_change_counter = 0;
-      for (int i = 0; i < 2; ++i) s.cg_cur[i] = s.cg_old[i] = s.cg_tgt[i] = kCoarseInitialCfg[i];
+      for (int i = 0; i < 2; ++i) s.cg_cur[i] = s.cg_old[i] = s.cg_tgt[i] = WAP_EC3_ARR(coarse_initial)[i];
       s.cg_config_change_counter = 0;
       sc.ired[0] = fir_set_size_immediate(&s.fr_current_size, &s.fr_target_size, &s.fr_old_target_size,
-                                          &s.fr_size_change_counter, &s.fr_partition_to_constrain, kInitPartitions);
+                                          &s.fr_size_change_counter, &s.fr_partition_to_constrain, WAP_EC3(refined_initial_len),
+                                          WAP_EC3(refined_len));
       sc.ired[1] = fir_set_size_immediate(&s.fc_current_size, &s.fc_target_size, &s.fc_old_target_size,
-                                          &s.fc_size_change_counter, &s.fc_partition_to_constrain, kInitPartitions);
+                                          &s.fc_size_change_counter, &s.fc_partition_to_constrain, WAP_EC3(coarse_initial_len),
+                                          WAP_EC3(coarse_len));
     }
     __syncwarp();
     fir_zero_partitions(a.Hr_re, a.Hr_im, sc.ired[0], s.fr_current_size);
@@ -89,22 +86,23 @@ WAP_DEV void subtractor_handle_echo_path_change(Aec3State& a, AecScratch& sc, co
 }
 
 // Subtractor::ExitInitialState (subtractor.cc:185-194), lane 0.
-WAP_DEV void subtractor_exit_initial_state(Aec3Scalars& s) {
-  for (int i = 0; i < 5; ++i) { s.rg_old[i] = s.rg_cur[i]; s.rg_tgt[i] = kRefinedCfg[i]; }
-  s.rg_config_change_counter = ec3::kConfigChangeDuration;
-  for (int i = 0; i < 2; ++i) { s.cg_old[i] = s.cg_cur[i]; s.cg_tgt[i] = kCoarseCfg[i]; }
-  s.cg_config_change_counter = ec3::kConfigChangeDuration;
-  s.fr_target_size = imin(kMaxPartitions, kMaxPartitions);
-  s.fr_size_change_counter = ec3::kConfigChangeDuration;
-  s.fc_target_size = imin(kMaxPartitions, kMaxPartitions);
-  s.fc_size_change_counter = ec3::kConfigChangeDuration;
+WAP_DEV void subtractor_exit_initial_state(AecScratch& sc) {
+  Aec3Scalars& s = sc.s;
+  for (int i = 0; i < 5; ++i) { s.rg_old[i] = s.rg_cur[i]; s.rg_tgt[i] = WAP_EC3_ARR(refined)[i]; }
+  s.rg_config_change_counter = WAP_EC3(config_change_duration_blocks);
+  for (int i = 0; i < 2; ++i) { s.cg_old[i] = s.cg_cur[i]; s.cg_tgt[i] = WAP_EC3_ARR(coarse)[i]; }
+  s.cg_config_change_counter = WAP_EC3(config_change_duration_blocks);
+  s.fr_target_size = WAP_EC3(refined_len);
+  s.fr_size_change_counter = WAP_EC3(config_change_duration_blocks);
+  s.fc_target_size = WAP_EC3(coarse_len);
+  s.fc_size_change_counter = WAP_EC3(config_change_duration_blocks);
 }
 
 // UpdateCurrentConfig of both gain classes, lane 0.
-WAP_DEV void gain_update_current_config(float* cur, float* old, const float* tgt, int n, int* counter) {
+WAP_DEV void gain_update_current_config(const AecScratch& sc, float* cur, float* old, const float* tgt, int n, int* counter) {
   if (*counter > 0) {
     if (--*counter > 0) {
-      const float one_by = 1.f / ec3::kConfigChangeDuration;
+      const float one_by = 1.f / WAP_EC3(config_change_duration_blocks);
       const float change_factor = *counter * one_by;
       for (int i = 0; i < n; ++i) cur[i] = old[i] * change_factor + tgt[i] * (1.f - change_factor);
     } else {
@@ -139,7 +137,7 @@ WAP_DEV void render_signal_analyzer_update(Aec3State& a, AecScratch& sc, int del
     for (int i = lane; i < kBlock; i += 32) max_abs_l = fmaxf(max_abs_l, fabsf(x_band1[i]));
   const float max_abs = warp_max(max_abs_l);
   if (lane == 0) {
-    if (s.rsa_has_narrow_peak && ++s.rsa_narrow_peak_counter > kMaxPartitions) s.rsa_has_narrow_peak = 0;
+    if (s.rsa_has_narrow_peak && ++s.rsa_narrow_peak_counter > WAP_EC3(refined_len)) s.rsa_has_narrow_peak = 0;
     float non_peak_power = 0.f;
     for (int k = imax(0, peak_bin - 14); k < peak_bin - 4; ++k) non_peak_power = fmaxr(X2_latest[k], non_peak_power);
     for (int k = peak_bin + 5; k < imin(peak_bin + 15, kBins); ++k) non_peak_power = fmaxr(X2_latest[k], non_peak_power);
@@ -544,14 +542,14 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
     sc.ired[1] = 1;  // refined G == 0 ?
     if (!refined_filters_adjusted) {
       ++s.rg_call_counter;
-      gain_update_current_config(s.rg_cur, s.rg_old, s.rg_tgt, 5, &s.rg_config_change_counter);
+      gain_update_current_config(sc, s.rg_cur, s.rg_old, s.rg_tgt, 5, &s.rg_config_change_counter);
       if (poor_excitation) s.rg_poor_excitation_counter = 0;
       const bool zero = (unsigned)(++s.rg_poor_excitation_counter) < (unsigned)P_r || saturated_capture ||
                         (unsigned)s.rg_call_counter <= (unsigned)P_r;
       sc.ired[1] = zero;
     }
     sc.ired[2] = s.coarse_filter_reset_hangover > 0;  // disallow_leakage_diverged
-    sc.ired[3] = fir_update_size(&s.fr_current_size, &s.fr_target_size, &s.fr_old_target_size,
+    sc.ired[3] = fir_update_size(sc, &s.fr_current_size, &s.fr_target_size, &s.fr_old_target_size,
                                  &s.fr_size_change_counter, &s.fr_partition_to_constrain);
     s.poor_coarse_filter_counter = e2_refined < e2_coarse ? s.poor_coarse_filter_counter + 1 : 0;
     sc.ired[4] = s.poor_coarse_filter_counter < 5;
@@ -559,14 +557,14 @@ WAP_DEV void subtractor_process(Aec3State& a, AecScratch& sc, bool saturated_cap
       s.coarse_filter_reset_hangover = imax(s.coarse_filter_reset_hangover - 1, 0);
     } else {
       s.poor_coarse_filter_counter = 0;
-      s.coarse_filter_reset_hangover = ec3::kCoarseResetHangover;
+      s.coarse_filter_reset_hangover = WAP_EC3(coarse_reset_hangover_blocks);
     }
     ++s.cg_call_counter;
-    gain_update_current_config(s.cg_cur, s.cg_old, s.cg_tgt, 2, &s.cg_config_change_counter);
+    gain_update_current_config(sc, s.cg_cur, s.cg_old, s.cg_tgt, 2, &s.cg_config_change_counter);
     if (poor_excitation) s.cg_poor_excitation_counter = 0;
     sc.ired[5] = (unsigned)(++s.cg_poor_excitation_counter) < (unsigned)P_c || saturated_capture ||
                  (unsigned)s.cg_call_counter <= (unsigned)P_c;
-    sc.ired[6] = fir_update_size(&s.fc_current_size, &s.fc_target_size, &s.fc_old_target_size,
+    sc.ired[6] = fir_update_size(sc, &s.fc_current_size, &s.fc_target_size, &s.fc_old_target_size,
                                  &s.fc_size_change_counter, &s.fc_partition_to_constrain);
   }
   __syncwarp();

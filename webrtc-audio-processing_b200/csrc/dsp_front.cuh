@@ -63,7 +63,7 @@ WAP_DEV float front_load_sample(const void* src, size_t leg, int len, int fmt, i
 // RenderDelayBufferImpl::Insert for render block `x` (64 samples, thread-local):
 // scalar bookkeeping, decimation into the low-rate ring, and the record that tells
 // k_echo where the block, its FFT and its spectrum go.
-WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const float* x) {
+WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const float* x, const Ec3Params& ep) {
   Aec3Scalars& s = a.s;
   float x_energy = 0.f;  // DetectActiveRender: std::inner_product
   for (int i = 0; i < kBlock; ++i) x_energy += x[i] * x[i];
@@ -83,7 +83,7 @@ WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const flo
   // RenderOverrun (:481-483); BlockProcessorImpl::BufferRender keeps the last event.
   s.render_event = (s.lr_read == s.lr_write || s.blocks_read == s.blocks_write) ? kEventRenderOverrun : kEventNone;
   if (!s.render_activity) {
-    s.render_activity_counter += (x_energy > (ec3::kActiveRenderLimit * ec3::kActiveRenderLimit) * 64.f) ? 1 : 0;
+    s.render_activity_counter += (x_energy > (ep.active_render_limit * ep.active_render_limit) * 64.f) ? 1 : 0;
     s.render_activity = s.render_activity_counter >= 20;
   }
   ts.rins[r].blocks_write = s.blocks_write;
@@ -102,7 +102,7 @@ WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const flo
     if ((i & (kDownSampling - 1)) == 0) a.low_rate[lw + kSubBlock - 1 - (i >> 2)] = v;
   }
   a.render_decimator[0] = d0; a.render_decimator[1] = d1; a.render_decimator[2] = d2; a.render_decimator[3] = d3;
-  if (s.render_event != kEventNone) rdb_reset(s);
+  if (s.render_event != kEventNone) rdb_reset(s, ep.default_delay);
   s.render_properly_started = 1;
 }
 
@@ -265,7 +265,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
         const int k = kBlock * r + j - L;
         x[j] = k < 0 ? aec.render_blocker[L + k] : band0[k];
       }
-      front_render_insert(aec, ts, r, x);
+      front_render_insert(aec, ts, r, x, a.ep);
     }
     const int rem = total - kBlock * nrb;
     for (int j = 0; j < rem; ++j) aec.render_blocker[j] = band0[kFrame - rem + j];

@@ -6,6 +6,7 @@
 // (:1689-1707), statistics (:1509-1518).  The DSP itself runs only on the GPU:
 // there is no CPU fallback and creation fails loudly without a CUDA device.
 #include <math.h>
+#include <cmath>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -121,6 +122,11 @@ struct WapEngine {
   bool is_default = false;
   int sm_count = 148;
   int echo_class = 0;  // wap::EchoClass: which k_echo instance serves this engine
+  // EchoCanceller3Config: the default config runs on compile-time constants, anything else on the
+  // run-time-parameter kernel instances (wap_ec3_params.h)
+  wap::Ec3Params ep = wap::ec3_default_params();
+  bool ec3_runtime = false;
+  WapEchoCanceller3Config aec3_config{};
   // resampled engines (API rate != processing rate)
   wap::ResamplerState* d_rs = nullptr;   // [capacity][kRsPerLeg]
   float* d_rs_kernels = nullptr;         // in | out tables
@@ -160,6 +166,8 @@ struct WapAudioProcessing {
   std::recursive_mutex mu;
   bool skip_first_reinit = false;  // the next private engine starts "already initialised" (ApplyConfig / Initialize ran InitializeLocked)
   bool owns_engine = false;
+  bool has_aec3_config = false;            // wap_create_with_aec3_config: injected EchoCanceller3Config
+  WapEchoCanceller3Config aec3_config{};
   WapStats cached_stats{};  // ApmStatsReporter::cached_stats_
 };
 
@@ -332,6 +340,281 @@ void build_sinc_kernel(double io_ratio, float* table) {
   }
 }
 
+// ---- EchoCanceller3Config (api/audio/echo_canceller3_config.h:21-275) ------------------------
+WapEchoCanceller3Config ec3_config_default() {
+  WapEchoCanceller3Config c{};
+  c.buffering = {250, 8};
+  c.delay.default_delay = 5; c.delay.down_sampling_factor = 4; c.delay.num_filters = 5;
+  c.delay.delay_headroom_samples = 32; c.delay.hysteresis_limit_blocks = 1; c.delay.fixed_capture_delay_samples = 0;
+  c.delay.delay_estimate_smoothing = 0.7f; c.delay.delay_estimate_smoothing_delay_found = 0.7f;
+  c.delay.delay_candidate_detection_threshold = 0.2f;
+  c.delay.delay_selection_thresholds = {5, 20};
+  c.delay.use_external_delay_estimator = false; c.delay.log_warning_on_delay_changes = false;
+  c.delay.render_alignment_mixing = {false, true, 10000.f, true};
+  c.delay.capture_alignment_mixing = {false, true, 10000.f, false};
+  c.delay.detect_pre_echo = true;
+  c.filter.refined = {13, 0.00005f, 0.05f, 0.001f, 2.f, 20075344.f};
+  c.filter.coarse = {13, 0.7f, 20075344.f};
+  c.filter.refined_initial = {12, 0.005f, 0.5f, 0.001f, 2.f, 20075344.f};
+  c.filter.coarse_initial = {12, 0.9f, 20075344.f};
+  c.filter.config_change_duration_blocks = 250; c.filter.initial_state_seconds = 2.5f;
+  c.filter.coarse_reset_hangover_blocks = 25;
+  c.filter.conservative_initial_phase = false; c.filter.enable_coarse_filter_output_usage = true;
+  c.filter.use_linear_filter = true; c.filter.high_pass_filter_echo_reference = false;
+  c.filter.export_linear_aec_output = false;
+  c.erle = {1.f, 4.f, 1.5f, true, 1, true, true};
+  c.ep_strength = {1.f, 0.83f, 0.83f, true, false, false, true};
+  c.echo_audibility = {4 * 64.f, 64.f, 2 * 64.f, 10.f, 10.f, 10.f, false, false};
+  c.render_levels = {100.f, 150.f, 20.f, 0.f};
+  c.echo_removal_control = {false, false};
+  c.echo_model = {50, 1638400.f, 10.f, 27509.42f, 0.3f, 1, 1, true};
+  c.comfort_noise.noise_floor_dbfs = -96.03406f;
+  c.suppressor.nearend_average_blocks = 4;
+  c.suppressor.normal_tuning = {{.3f, .4f, .3f}, {.07f, .1f, .3f}, 2.0f, 0.25f};
+  c.suppressor.nearend_tuning = {{1.09f, 1.1f, .3f}, {.1f, .3f, .3f}, 2.0f, 0.25f};
+  c.suppressor.lf_smoothing_during_initial_phase = true;
+  c.suppressor.last_permanent_lf_smoothing_band = 0; c.suppressor.last_lf_smoothing_band = 5;
+  c.suppressor.last_lf_band = 5; c.suppressor.first_hf_band = 8;
+  c.suppressor.dominant_nearend_detection = {.25f, 10.f, 30.f, 50, 12, true, true};
+  c.suppressor.subband_nearend_detection = {1, {1, 1}, {1, 1}, 1.f, 1.f};
+  c.suppressor.use_subband_nearend_detection = false;
+  c.suppressor.high_bands_suppression = {1.f, 1.f, 400.f, 1.f};
+  c.suppressor.high_frequency_suppression = {16, 1};
+  c.suppressor.floor_first_increase = 0.00001f;
+  c.suppressor.conservative_hf_suppression = false;
+  c.multi_channel = {true, 0.0f, 300, 2.0f};
+  return c;
+}
+
+// Members that fix the structure of the engine must keep their default value (see the header).
+WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
+  const WapEchoCanceller3Config d = ec3_config_default();
+  const bool ok =
+      c.delay.down_sampling_factor == 4 && c.delay.num_filters == 5 && c.delay.fixed_capture_delay_samples == 0 &&
+      !c.delay.use_external_delay_estimator && c.delay.detect_pre_echo && c.delay.default_delay >= 0 &&
+      c.delay.default_delay <= wap::kMaxRingDelay &&
+      c.filter.refined.length_blocks >= 1 && c.filter.refined.length_blocks <= wap::kMaxPartitions &&
+      c.filter.coarse.length_blocks >= 1 && c.filter.coarse.length_blocks <= wap::kMaxPartitions &&
+      c.filter.refined_initial.length_blocks >= 1 && c.filter.refined_initial.length_blocks <= c.filter.refined.length_blocks &&
+      c.filter.coarse_initial.length_blocks >= 1 && c.filter.coarse_initial.length_blocks <= c.filter.coarse.length_blocks &&
+      c.filter.config_change_duration_blocks >= 1 &&
+      c.filter.conservative_initial_phase == d.filter.conservative_initial_phase &&
+      c.filter.enable_coarse_filter_output_usage == d.filter.enable_coarse_filter_output_usage &&
+      c.filter.use_linear_filter == d.filter.use_linear_filter &&
+      c.filter.high_pass_filter_echo_reference == d.filter.high_pass_filter_echo_reference &&
+      c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
+      c.erle.onset_detection == d.erle.onset_detection && c.erle.num_sections == 1 &&
+      c.erle.clamp_quality_estimate_to_zero && c.erle.clamp_quality_estimate_to_one &&
+      c.ep_strength.default_len >= 0.f && c.ep_strength.nearend_len >= 0.f &&   // negative: adaptive reverb decay
+      c.ep_strength.echo_can_saturate && !c.ep_strength.bounded_erl &&
+      !c.ep_strength.erle_onset_compensation_in_dominant_nearend && c.ep_strength.use_conservative_tail_frequency_response &&
+      !c.echo_audibility.use_stationarity_properties && !c.echo_audibility.use_stationarity_properties_at_init &&
+      c.render_levels.render_power_gain_db == 0.f &&
+      !c.echo_removal_control.has_clock_drift && !c.echo_removal_control.linear_and_stable_echo_path &&
+      c.echo_model.render_pre_window_size == 1 && c.echo_model.render_post_window_size == 1 &&
+      c.echo_model.model_reverb_in_nonlinear_mode &&
+      c.suppressor.nearend_average_blocks == 4 && c.suppressor.lf_smoothing_during_initial_phase &&
+      c.suppressor.dominant_nearend_detection.use_during_initial_phase &&
+      c.suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum &&
+      !c.suppressor.use_subband_nearend_detection && !c.suppressor.conservative_hf_suppression &&
+      c.suppressor.high_bands_suppression.max_gain_during_echo == 1.f &&
+      c.suppressor.high_frequency_suppression.limiting_gain_band >= 0 &&
+      c.suppressor.high_frequency_suppression.bands_in_limiting_gain >= 0 &&
+      c.suppressor.high_frequency_suppression.limiting_gain_band +
+              c.suppressor.high_frequency_suppression.bands_in_limiting_gain <= wap::kBins &&
+      c.suppressor.last_lf_band >= 0 && c.suppressor.first_hf_band > c.suppressor.last_lf_band;
+  return ok ? WapError::None : WapError::UnsupportedConfig;
+}
+
+wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
+  wap::Ec3Params p{};
+  p.excess_render_detection_interval_blocks = c.buffering.excess_render_detection_interval_blocks;
+  p.max_allowed_excess_render_blocks = c.buffering.max_allowed_excess_render_blocks;
+  p.default_delay = c.delay.default_delay;
+  p.delay_headroom_samples = c.delay.delay_headroom_samples;
+  p.hysteresis_limit_blocks = c.delay.hysteresis_limit_blocks;
+  p.thr_initial = c.delay.delay_selection_thresholds.initial;
+  p.thr_converged = c.delay.delay_selection_thresholds.converged;
+  p.delay_estimate_smoothing = c.delay.delay_estimate_smoothing;
+  p.delay_estimate_smoothing_delay_found = c.delay.delay_estimate_smoothing_delay_found;
+  p.delay_candidate_detection_threshold = c.delay.delay_candidate_detection_threshold;
+  p.active_render_limit = c.render_levels.active_render_limit;
+  p.poor_excitation_render_limit = c.render_levels.poor_excitation_render_limit;
+  p.refined_len = c.filter.refined.length_blocks;
+  p.coarse_len = c.filter.coarse.length_blocks;
+  p.refined_initial_len = c.filter.refined_initial.length_blocks;
+  p.coarse_initial_len = c.filter.coarse_initial.length_blocks;
+  const WapEc3RefinedConfiguration* rc[2] = {&c.filter.refined, &c.filter.refined_initial};
+  float* rd[2] = {p.refined, p.refined_initial};
+  for (int i = 0; i < 2; ++i) {
+    rd[i][0] = rc[i]->leakage_converged; rd[i][1] = rc[i]->leakage_diverged; rd[i][2] = rc[i]->error_floor;
+    rd[i][3] = rc[i]->error_ceil; rd[i][4] = rc[i]->noise_gate;
+  }
+  p.coarse[0] = c.filter.coarse.rate; p.coarse[1] = c.filter.coarse.noise_gate;
+  p.coarse_initial[0] = c.filter.coarse_initial.rate; p.coarse_initial[1] = c.filter.coarse_initial.noise_gate;
+  p.config_change_duration_blocks = c.filter.config_change_duration_blocks;
+  p.coarse_reset_hangover_blocks = c.filter.coarse_reset_hangover_blocks;
+  p.initial_state_seconds = c.filter.initial_state_seconds;
+  p.erle_min = c.erle.min; p.erle_max_l = c.erle.max_l; p.erle_max_h = c.erle.max_h;
+  p.default_gain = c.ep_strength.default_gain; p.default_len = c.ep_strength.default_len;
+  p.nearend_len = c.ep_strength.nearend_len;
+  p.low_render_limit = c.echo_audibility.low_render_limit; p.normal_render_limit = c.echo_audibility.normal_render_limit;
+  p.floor_power = c.echo_audibility.floor_power;
+  p.audibility_threshold_lf = c.echo_audibility.audibility_threshold_lf;
+  p.audibility_threshold_mf = c.echo_audibility.audibility_threshold_mf;
+  p.audibility_threshold_hf = c.echo_audibility.audibility_threshold_hf;
+  p.noise_floor_hold = c.echo_model.noise_floor_hold; p.min_noise_floor_power = c.echo_model.min_noise_floor_power;
+  p.stationary_gate_slope = c.echo_model.stationary_gate_slope; p.noise_gate_power = c.echo_model.noise_gate_power;
+  p.noise_gate_slope = c.echo_model.noise_gate_slope;
+  const WapEc3Tuning* tc[2] = {&c.suppressor.normal_tuning, &c.suppressor.nearend_tuning};
+  wap::Ec3Tuning* td[2] = {&p.normal_tuning, &p.nearend_tuning};
+  for (int i = 0; i < 2; ++i)
+    *td[i] = {tc[i]->mask_lf.enr_transparent, tc[i]->mask_lf.enr_suppress, tc[i]->mask_lf.emr_transparent,
+              tc[i]->mask_hf.enr_transparent, tc[i]->mask_hf.enr_suppress, tc[i]->mask_hf.emr_transparent,
+              tc[i]->max_inc_factor, tc[i]->max_dec_factor_lf};
+  p.last_permanent_lf_smoothing_band = c.suppressor.last_permanent_lf_smoothing_band;
+  p.last_lf_smoothing_band = c.suppressor.last_lf_smoothing_band;
+  p.last_lf_band = c.suppressor.last_lf_band; p.first_hf_band = c.suppressor.first_hf_band;
+  p.dn_enr_threshold = c.suppressor.dominant_nearend_detection.enr_threshold;
+  p.dn_enr_exit_threshold = c.suppressor.dominant_nearend_detection.enr_exit_threshold;
+  p.dn_snr_threshold = c.suppressor.dominant_nearend_detection.snr_threshold;
+  p.dn_hold_duration = c.suppressor.dominant_nearend_detection.hold_duration;
+  p.dn_trigger_threshold = c.suppressor.dominant_nearend_detection.trigger_threshold;
+  p.hb_enr_threshold = c.suppressor.high_bands_suppression.enr_threshold;
+  p.hb_max_gain_during_echo = c.suppressor.high_bands_suppression.max_gain_during_echo;
+  p.hb_anti_howling_activation_threshold = c.suppressor.high_bands_suppression.anti_howling_activation_threshold;
+  p.hb_anti_howling_gain = c.suppressor.high_bands_suppression.anti_howling_gain;
+  p.limiting_gain_band = c.suppressor.high_frequency_suppression.limiting_gain_band;
+  p.bands_in_limiting_gain = c.suppressor.high_frequency_suppression.bands_in_limiting_gain;
+  p.floor_first_increase = c.suppressor.floor_first_increase;
+  return p;
+}
+
+// EchoCanceller3Config::Validate (echo_canceller3_config.cc:101-286).
+template <class T>
+bool ec3_limit(T* v, T lo, T hi) {
+  T c = *v < lo ? lo : (*v > hi ? hi : *v);
+  bool res = *v == c;
+  *v = c;
+  return res;
+}
+bool ec3_limit(float* v, float lo, float hi) {
+  float c = *v < lo ? lo : (*v > hi ? hi : *v);   // SafeClamp; NaN compares false and falls through
+  if (!std::isfinite(c)) c = lo;
+  bool res = *v == c;
+  *v = c;
+  return res;
+}
+bool ec3_floor(int32_t* v, int32_t lo) {
+  bool res = *v >= lo;
+  if (!res) *v = lo;
+  return res;
+}
+bool ec3_validate(WapEchoCanceller3Config* c) {
+  bool res = true;
+  if (c->delay.down_sampling_factor != 4 && c->delay.down_sampling_factor != 8) { c->delay.down_sampling_factor = 4; res = false; }
+  res &= ec3_limit(&c->delay.default_delay, 0, 5000);
+  res &= ec3_limit(&c->delay.num_filters, 0, 5000);
+  res &= ec3_limit(&c->delay.delay_headroom_samples, 0, 5000);
+  res &= ec3_limit(&c->delay.hysteresis_limit_blocks, 0, 5000);
+  res &= ec3_limit(&c->delay.fixed_capture_delay_samples, 0, 5000);
+  res &= ec3_limit(&c->delay.delay_estimate_smoothing, 0.f, 1.f);
+  res &= ec3_limit(&c->delay.delay_candidate_detection_threshold, 0.f, 1.f);
+  res &= ec3_limit(&c->delay.delay_selection_thresholds.initial, 1, 250);
+  res &= ec3_limit(&c->delay.delay_selection_thresholds.converged, 1, 250);
+  WapEc3RefinedConfiguration* rc[2] = {&c->filter.refined, &c->filter.refined_initial};
+  for (int i = 0; i < 2; ++i) {
+    res &= ec3_floor(&rc[i]->length_blocks, 1);
+    res &= ec3_limit(&rc[i]->leakage_converged, 0.f, 1000.f);
+    res &= ec3_limit(&rc[i]->leakage_diverged, 0.f, 1000.f);
+    res &= ec3_limit(&rc[i]->error_floor, 0.f, 1000.f);
+    res &= ec3_limit(&rc[i]->error_ceil, 0.f, 100000000.f);
+    res &= ec3_limit(&rc[i]->noise_gate, 0.f, 100000000.f);
+  }
+  if (c->filter.refined.length_blocks < c->filter.refined_initial.length_blocks) {
+    c->filter.refined_initial.length_blocks = c->filter.refined.length_blocks;
+    res = false;
+  }
+  WapEc3CoarseConfiguration* cc[2] = {&c->filter.coarse, &c->filter.coarse_initial};
+  for (int i = 0; i < 2; ++i) {
+    res &= ec3_floor(&cc[i]->length_blocks, 1);
+    res &= ec3_limit(&cc[i]->rate, 0.f, 1.f);
+    res &= ec3_limit(&cc[i]->noise_gate, 0.f, 100000000.f);
+  }
+  if (c->filter.coarse.length_blocks < c->filter.coarse_initial.length_blocks) {
+    c->filter.coarse_initial.length_blocks = c->filter.coarse.length_blocks;
+    res = false;
+  }
+  res &= ec3_limit(&c->filter.config_change_duration_blocks, 0, 100000);
+  res &= ec3_limit(&c->filter.initial_state_seconds, 0.f, 100.f);
+  res &= ec3_limit(&c->filter.coarse_reset_hangover_blocks, 0, 250000);
+  res &= ec3_limit(&c->erle.min, 1.f, 100000.f);
+  res &= ec3_limit(&c->erle.max_l, 1.f, 100000.f);
+  res &= ec3_limit(&c->erle.max_h, 1.f, 100000.f);
+  if (c->erle.min > c->erle.max_l || c->erle.min > c->erle.max_h) {
+    c->erle.min = std::min(c->erle.max_l, c->erle.max_h);
+    res = false;
+  }
+  res &= ec3_limit(&c->erle.num_sections, 1, c->filter.refined.length_blocks);
+  res &= ec3_limit(&c->ep_strength.default_gain, 0.f, 1000000.f);
+  res &= ec3_limit(&c->ep_strength.default_len, -1.f, 1.f);
+  res &= ec3_limit(&c->ep_strength.nearend_len, -1.0f, 1.0f);
+  const float kMaxPower = 32768.f * 32768.f;
+  res &= ec3_limit(&c->echo_audibility.low_render_limit, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_audibility.normal_render_limit, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_audibility.floor_power, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_audibility.audibility_threshold_lf, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_audibility.audibility_threshold_mf, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_audibility.audibility_threshold_hf, 0.f, kMaxPower);
+  res &= ec3_limit(&c->render_levels.active_render_limit, 0.f, kMaxPower);
+  res &= ec3_limit(&c->render_levels.poor_excitation_render_limit, 0.f, kMaxPower);
+  res &= ec3_limit(&c->render_levels.poor_excitation_render_limit_ds8, 0.f, kMaxPower);
+  res &= ec3_limit(&c->echo_model.noise_floor_hold, 0, 1000);
+  res &= ec3_limit(&c->echo_model.min_noise_floor_power, 0.f, 2000000.f);
+  res &= ec3_limit(&c->echo_model.stationary_gate_slope, 0.f, 1000000.f);
+  res &= ec3_limit(&c->echo_model.noise_gate_power, 0.f, 1000000.f);
+  res &= ec3_limit(&c->echo_model.noise_gate_slope, 0.f, 1000000.f);
+  res &= ec3_limit(&c->echo_model.render_pre_window_size, 0, 100);
+  res &= ec3_limit(&c->echo_model.render_post_window_size, 0, 100);
+  res &= ec3_limit(&c->comfort_noise.noise_floor_dbfs, -200.f, 0.f);
+  res &= ec3_limit(&c->suppressor.nearend_average_blocks, 1, 5000);
+  WapEc3Tuning* tc[2] = {&c->suppressor.normal_tuning, &c->suppressor.nearend_tuning};
+  for (int i = 0; i < 2; ++i) {
+    res &= ec3_limit(&tc[i]->mask_lf.enr_transparent, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->mask_lf.enr_suppress, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->mask_lf.emr_transparent, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->mask_hf.enr_transparent, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->mask_hf.enr_suppress, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->mask_hf.emr_transparent, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->max_inc_factor, 0.f, 100.f);
+    res &= ec3_limit(&tc[i]->max_dec_factor_lf, 0.f, 100.f);
+  }
+  res &= ec3_limit(&c->suppressor.last_permanent_lf_smoothing_band, 0, 64);
+  res &= ec3_limit(&c->suppressor.last_lf_smoothing_band, 0, 64);
+  res &= ec3_limit(&c->suppressor.last_lf_band, 0, 63);
+  res &= ec3_limit(&c->suppressor.first_hf_band, c->suppressor.last_lf_band + 1, 64);
+  res &= ec3_limit(&c->suppressor.dominant_nearend_detection.enr_threshold, 0.f, 1000000.f);
+  res &= ec3_limit(&c->suppressor.dominant_nearend_detection.snr_threshold, 0.f, 1000000.f);
+  res &= ec3_limit(&c->suppressor.dominant_nearend_detection.hold_duration, 0, 10000);
+  res &= ec3_limit(&c->suppressor.dominant_nearend_detection.trigger_threshold, 0, 10000);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.nearend_average_blocks, 1, 1024);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.subband1.low, 0, 65);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.subband1.high, c->suppressor.subband_nearend_detection.subband1.low, 65);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.subband2.low, 0, 65);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.subband2.high, c->suppressor.subband_nearend_detection.subband2.low, 65);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.nearend_threshold, 0.f, 1.e24f);
+  res &= ec3_limit(&c->suppressor.subband_nearend_detection.snr_threshold, 0.f, 1.e24f);
+  res &= ec3_limit(&c->suppressor.high_bands_suppression.enr_threshold, 0.f, 1000000.f);
+  res &= ec3_limit(&c->suppressor.high_bands_suppression.max_gain_during_echo, 0.f, 1.f);
+  res &= ec3_limit(&c->suppressor.high_bands_suppression.anti_howling_activation_threshold, 0.f, kMaxPower);
+  res &= ec3_limit(&c->suppressor.high_bands_suppression.anti_howling_gain, 0.f, 1.f);
+  res &= ec3_limit(&c->suppressor.high_frequency_suppression.limiting_gain_band, 1, 64);
+  res &= ec3_limit(&c->suppressor.high_frequency_suppression.bands_in_limiting_gain, 0,
+                   64 - c->suppressor.high_frequency_suppression.limiting_gain_band);
+  res &= ec3_limit(&c->suppressor.floor_first_increase, 0.f, 1000000.f);
+  return res;
+}
+
 int grid_for(int n_streams) {
   const int wpb = 4;
   int blocks = (n_streams + wpb - 1) / wpb;
@@ -352,6 +635,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   a.out = d_out;
   a.fmt = (int)fmt;
   a.cfg = e->cfg;
+  a.ep = e->ep;
   const int wpb = 4;
   const bool timing = e->timing;
   if (timing) cudaEventRecord(e->ev[0], e->stream);
@@ -385,12 +669,14 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   if (timing) cudaEventRecord(e->ev[1], e->stream);
   if (e->cfg.aec_enabled && d_capture) {
     const size_t smem_d = (size_t)wpb * e->delay_scratch_floats * sizeof(float);
-    wap::launch_k_delay(grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
+    if (e->ec3_runtime) wap::launch_k_delay_rt(grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
+    else wap::launch_k_delay(grid_for(n), wpb * 32, smem_d, e->stream, a, e->delay_scratch_floats);
     e->launches++;
   }
   if (timing) cudaEventRecord(e->ev[2], e->stream);
   const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
-  wap::launch_k_echo(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  if (e->ec3_runtime) wap::launch_k_echo_rt(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
+  else wap::launch_k_echo(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
   if (e->d_upper && e->cfg.num_bands == 3 && d_capture) {  // PostFilter: 48 kHz only (post_filter.cc:44-52)
     WAP_LAUNCH(wap::k_post, (n + 127) / 128, 128, 0, e->stream, a);
@@ -460,14 +746,43 @@ WapConfig wap_config_default(void) {
   return c;
 }
 
+WapEchoCanceller3Config wap_echo_canceller3_config_default(void) { return ec3_config_default(); }
+WapEchoCanceller3Config wap_echo_canceller3_config_default_multichannel(void) {
+  // EchoCanceller3Config::CreateDefaultMultichannelConfig (echo_canceller3_config.cc:288-301)
+  WapEchoCanceller3Config c = ec3_config_default();
+  c.filter.coarse.length_blocks = 11;
+  c.filter.coarse.rate = 0.95f;
+  c.filter.coarse_initial.length_blocks = 11;
+  c.filter.coarse_initial.rate = 0.95f;
+  c.suppressor.normal_tuning.max_dec_factor_lf = 0.35f;
+  c.suppressor.normal_tuning.max_inc_factor = 1.5f;
+  return c;
+}
+size_t wap_echo_canceller3_config_sizeof(void) { return sizeof(WapEchoCanceller3Config); }
+bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config) { return config ? ec3_validate(config) : false; }
+WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config) {
+  return config ? ec3_config_supported(*config) : WapError::NullPointer;
+}
+
 WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig config, WapStreamConfig fmt) {
+  return wap_engine_create_with_aec3_config(cuda_device, max_streams, config, fmt, nullptr, nullptr);
+}
+
+WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_streams, WapConfig config, WapStreamConfig fmt,
+                                              const WapEchoCanceller3Config* aec3_config,
+                                              const WapEchoCanceller3Config* aec3_multichannel_config) {
   if (check_device() != WapError::None) return nullptr;
   EngineConfig cfg{};
   WapError err = resolve_config(config, fmt, &cfg);
+  (void)aec3_multichannel_config;  // applies to legs with more than one render / capture channel (not built: resolve_config refuses them)
+  const WapEchoCanceller3Config aec3 = aec3_config ? *aec3_config : ec3_config_default();
+  if (err == WapError::None && config.echo_canceller_enabled) err = ec3_config_supported(aec3);
   if (err != WapError::None) {
     fprintf(stderr, "[wap_b200] unsupported engine config (error %d)\n", (int)err);
     return nullptr;
   }
+  // ComfortNoiseGenerator: GetNoiseFloorFactor(comfort_noise.noise_floor_dbfs) (comfort_noise_generator.cc:41-45)
+  cfg.cng_noise_floor = 64.f * powf(10.f, (90.30899869919436f + aec3.comfort_noise.noise_floor_dbfs) * 0.1f);
   if (max_streams <= 0) return nullptr;
   WapEngine* e = new (std::nothrow) WapEngine;
   if (!e) return nullptr;
@@ -477,9 +792,12 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   e->format = fmt;
   e->cfg = cfg;
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
-  e->echo_scratch_floats = wap::echo_scratch_floats(cfg.num_bands);
+  e->aec3_config = aec3;
+  e->ep = ec3_params_from_config(aec3);
+  e->ec3_runtime = config.echo_canceller_enabled && !wap::same_ec3_params(e->ep, wap::ec3_default_params());
+  e->echo_scratch_floats = e->ec3_runtime ? wap::k_echo_scratch_floats_rt(cfg.num_bands) : wap::k_echo_scratch_floats(cfg.num_bands);
   e->echo_class = wap::echo_class_of(cfg);
-  e->delay_scratch_floats = wap::delay_scratch_floats();
+  e->delay_scratch_floats = e->ec3_runtime ? wap::k_delay_scratch_floats_rt() : wap::k_delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -507,7 +825,7 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   }
   if (ok) {
     StreamState* tmpl = new StreamState;
-    wap::init_stream_state(*tmpl);
+    wap::init_stream_state(*tmpl, e->ep);
     tmpl->agc2.gain_last = tmpl->agc2.gain_current = cfg.agc2_fixed_gain;
     if (cfg.levels_enabled) {  // InitializeCaptureLevelsAdjuster (audio_processing_impl.cc:2108-2130)
       float pre_gain = 1.f;
@@ -521,8 +839,8 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
   }
   const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
   const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
-  if (ok && smem_e > 48 * 1024) ok = wap::set_k_echo_smem((int)smem_e) == cudaSuccess;
-  if (ok && smem_d > 48 * 1024) ok = wap::set_k_delay_smem((int)smem_d) == cudaSuccess;
+  if (ok && smem_e > 48 * 1024) ok = (e->ec3_runtime ? wap::set_k_echo_smem_rt((int)smem_e) : wap::set_k_echo_smem((int)smem_e)) == cudaSuccess;
+  if (ok && smem_d > 48 * 1024) ok = (e->ec3_runtime ? wap::set_k_delay_smem_rt((int)smem_d) : wap::set_k_delay_smem((int)smem_d)) == cudaSuccess;
   if (!ok) {
     fprintf(stderr, "[wap_b200] engine allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     wap_engine_destroy(e);
@@ -843,6 +1161,7 @@ struct BlobHeader {
   uint32_t magic, version;
   uint64_t total_bytes;
   wap::EngineConfig cfg;  // the blob only fits an engine of the same config class
+  wap::Ec3Params ep;      // ... and the same EchoCanceller3Config
   // host-side per-leg state
   WapConfig config;
   int32_t delay_ms, delay_set, capture_output_used, analog_level, playout_volume;
@@ -851,7 +1170,7 @@ struct BlobHeader {
   WapStats cached_stats;
 };
 constexpr uint32_t kBlobMagic = 0x57415042u;  // "WAPB"
-constexpr uint32_t kBlobVersion = 1;
+constexpr uint32_t kBlobVersion = 2;
 size_t blob_bytes(const WapEngine* e) {
   size_t n = sizeof(BlobHeader) + sizeof(StreamState);
   if (e->d_upper) n += sizeof(wap::UpperBandState);
@@ -878,6 +1197,7 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
   hd.version = kBlobVersion;
   hd.total_bytes = blob_bytes(e);
   hd.cfg = e->cfg;
+  hd.ep = e->ep;
   hd.config = h->config;
   hd.delay_ms = e->leg_delay_ms[h->slot];
   hd.delay_set = e->leg_delay_set[h->slot];
@@ -915,7 +1235,7 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   BlobHeader hd;
   memcpy(&hd, blob, sizeof(hd));
   if (hd.magic != kBlobMagic || hd.version != kBlobVersion || hd.total_bytes != blob_bytes(e) || bytes < hd.total_bytes ||
-      !wap::same_engine_config(hd.cfg, e->cfg))
+      !wap::same_engine_config(hd.cfg, e->cfg) || !wap::same_ec3_params(hd.ep, e->ep))
     return WapError::UnsupportedConfig;  // another config class (or library version)
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));

@@ -3,6 +3,7 @@
 #pragma once
 #include <string.h>
 
+#include "wap_ec3_params.h"
 #include "wap_state.h"
 
 namespace wap {
@@ -33,7 +34,7 @@ inline void init_ns_state(NsState& s) {
 
 // Initial AEC3 state: what the reference's constructors and the Reset() calls
 // they make leave behind (citations per group).
-inline void init_aec3_state(Aec3State& a) {
+inline void init_aec3_state(Aec3State& a, const Ec3Params& ep) {
   memset(&a, 0, sizeof(a));
   Aec3Scalars& s = a.s;
   // BlockFramer starts with one block of zeros buffered (block_framer.cc:24-33).
@@ -42,8 +43,8 @@ inline void init_aec3_state(Aec3State& a) {
   // (render_delay_buffer.cc:118-197): indices 0, low-rate read one sub-block
   // ahead of write, total delay = default_delay (5), delay_ unset.
   s.lr_read = kSubBlock;
-  s.blocks_read = kRingBlocks - 5;
-  s.spectra_read = 5;
+  s.blocks_read = kRingBlocks - ep.default_delay;
+  s.spectra_read = ep.default_delay;
   s.num_api_calls_in_a_row = 1;
   s.max_observed_jitter = 1;
   // MatchedFilter / lag aggregators (matched_filter.h:156-164, matched_filter_lag_aggregator.h:61-98)
@@ -55,39 +56,37 @@ inline void init_aec3_state(Aec3State& a) {
   // EchoRemoverImpl (echo_remover.cc:168-176)
   s.er_refined_last_selected = 1;
   // AdaptiveFirFilter x2: initial sizes (echo_canceller3_config.h:76-120)
-  s.fr_current_size = s.fr_target_size = s.fr_old_target_size = kInitPartitions;
-  s.fc_current_size = s.fc_target_size = s.fc_old_target_size = kInitPartitions;
+  s.fr_current_size = s.fr_target_size = s.fr_old_target_size = ep.refined_initial_len;
+  s.fc_current_size = s.fc_target_size = s.fc_old_target_size = ep.coarse_initial_len;
   // Subtractor ctor: impulse/frequency responses sized for the longest filter (subtractor.cc:99-112)
-  s.h_time_size = kMaxPartitions;
-  s.H2_size = kMaxPartitions;
+  s.h_time_size = ep.refined_len;   // max(refined_initial, refined) = refined (Validate keeps initial <= main)
+  s.H2_size = ep.refined_len;
   // RefinedFilterUpdateGain / CoarseFilterUpdateGain with the *_initial configs
   s.rg_poor_excitation_counter = 1000;
-  const float rg[5] = {0.005f, 0.5f, 0.001f, 2.f, 20075344.f};
-  const float cg[2] = {0.9f, 20075344.f};
-  for (int i = 0; i < 5; ++i) s.rg_cur[i] = s.rg_old[i] = s.rg_tgt[i] = rg[i];
-  for (int i = 0; i < 2; ++i) s.cg_cur[i] = s.cg_old[i] = s.cg_tgt[i] = cg[i];
+  for (int i = 0; i < 5; ++i) s.rg_cur[i] = s.rg_old[i] = s.rg_tgt[i] = ep.refined_initial[i];
+  for (int i = 0; i < 2; ++i) s.cg_cur[i] = s.cg_old[i] = s.cg_tgt[i] = ep.coarse_initial[i];
   for (int k = 0; k < kBins; ++k) a.H_error[k] = 10000.f;
   // AecState and members (aec_state.h:170-305)
   s.init_state = 1;
-  s.fa_gain = 1.f;                       // ep_strength.default_gain
-  s.fa_filter_length_blocks = kInitPartitions;
-  s.fa_hp_size = kMaxPartitions * kBlock;
+  s.fa_gain = ep.default_gain;           // ep_strength.default_gain
+  s.fa_filter_length_blocks = ep.refined_initial_len;
+  s.fa_hp_size = ep.refined_len * kBlock;
   s.cfd_consistent_delay_reference = -10;
   s.tm_active_blocks_since_sane_filter = 10000;  // LegacyTransparentModeImpl (transparent_mode.cc:132-140)
   s.tm_non_converged_sequence_size = 10000;
   // ErleEstimator::Reset(true) (erle_estimator.cc:46-56, fullband_erle_estimator.cc:50-62,150-155)
   for (int k = 0; k < kBins; ++k) {
-    a.erle[k] = a.erle_onset_comp[k] = a.erle_unbounded[k] = 1.f;
+    a.erle[k] = a.erle_onset_comp[k] = a.erle_unbounded[k] = ep.erle_min;
     a.coming_onset[k] = 1;
     a.erl[k] = 1000.f;                   // ErlEstimator ctor (erl_estimator.cc:33-39)
-    a.X2_noise_floor[k] = 1638400.f;     // ResidualEchoEstimator::Reset (residual_echo_estimator.cc:317-321)
-    a.X2_noise_floor_counter[k] = 50;
+    a.X2_noise_floor[k] = ep.min_noise_floor_power;  // ResidualEchoEstimator::Reset (residual_echo_estimator.cc:317-321)
+    a.X2_noise_floor_counter[k] = ep.noise_floor_hold;
     a.cng_N2[k] = 1.0e6f;                // ComfortNoiseGenerator ctor (comfort_noise_generator.cc:106-123)
     a.last_gain[k] = 1.f;                // SuppressionGain ctor (suppression_gain.cc:351)
   }
   {
     // FastApproxLog2f(erle.min + 1e-3) (aec3_common.cc:37-52)
-    const float in = 1.f + 1e-3f;
+    const float in = ep.erle_min + 1e-3f;
     uint32_t bits;
     memcpy(&bits, &in, 4);
     float out = (float)bits;
@@ -104,7 +103,7 @@ inline void init_aec3_state(Aec3State& a) {
   s.sg_average_power = 32768.f * 32768.f;  // LowNoiseRenderDetector (suppression_gain.h:106)
 }
 
-inline void init_stream_state(StreamState& st) {
+inline void init_stream_state(StreamState& st, const Ec3Params& ep = ec3_default_params()) {
   memset(&st, 0, sizeof(st));
   st.capture_output_used = 1;
   st.capture_output_used_last_frame = 1;
@@ -113,7 +112,7 @@ inline void init_stream_state(StreamState& st) {
   st.levels.prev_pre_adjustment_gain = -1.f;
   st.levels.playout_volume = st.levels.prev_playout_volume = -1;
   init_ns_state(st.ns);
-  init_aec3_state(st.aec);
+  init_aec3_state(st.aec, ep);
 }
 
 }  // namespace wap

@@ -4,12 +4,18 @@
 #include "wap_launch.h"
 #include "wap_pipeline.cuh"
 
+#if WAP_EC3_RUNTIME
+#define WAP_KSUF(x) x##_rt
+#else
+#define WAP_KSUF(x) x
+#endif
+
 namespace wap {
 
 #ifndef WAP_DELAY_MINBLOCKS
 #define WAP_DELAY_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, int scratch_floats) {
+__global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) WAP_KSUF(k_delay)(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -26,12 +32,14 @@ __global__ void __launch_bounds__(128, WAP_DELAY_MINBLOCKS) k_delay(TickArgs a, 
   }
 }
 
-cudaError_t launch_k_delay(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats) {
-  WAP_LAUNCH(k_delay, grid, block, smem, stream, a, scratch_floats);
+cudaError_t WAP_KSUF(launch_k_delay)(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats) {
+  WAP_LAUNCH(WAP_KSUF(k_delay), grid, block, smem, stream, a, scratch_floats);
   return cudaSuccess;
 }
-cudaError_t set_k_delay_smem(int bytes) {
-  return cudaFuncSetAttribute(k_delay, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+cudaError_t WAP_KSUF(set_k_delay_smem)(int bytes) {
+  return cudaFuncSetAttribute(WAP_KSUF(k_delay), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
+
+int WAP_KSUF(k_delay_scratch_floats)() { return delay_scratch_floats(); }
 
 }  // namespace wap

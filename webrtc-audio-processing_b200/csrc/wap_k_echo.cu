@@ -12,13 +12,18 @@
 #ifndef WAP_ECHO_MINBLOCKS
 #define WAP_ECHO_MINBLOCKS 4
 #endif
+#if WAP_EC3_RUNTIME
+#define WAP_KSUF(x) x##_rt
+#else
+#define WAP_KSUF(x) x
+#endif
 #define WAP_CAT2(a, b) a##b
 #define WAP_CAT(a, b) WAP_CAT2(a, b)
 
 namespace wap {
 
 template <int kClass>
-__global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, int scratch_floats) {
+__global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) WAP_KSUF(k_echo)(TickArgs a, int scratch_floats) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -35,34 +40,39 @@ __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) k_echo(TickArgs a, in
   }
 }
 
-cudaError_t WAP_CAT(launch_k_echo_, WAP_ECHO_CLASS)(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,
+cudaError_t WAP_CAT(WAP_KSUF(launch_k_echo), WAP_CAT(_, WAP_ECHO_CLASS))(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,
                                                      int scratch_floats) {
-  WAP_LAUNCH(k_echo<WAP_ECHO_CLASS>, grid, block, smem, stream, a, scratch_floats);
+  WAP_LAUNCH(WAP_KSUF(k_echo)<WAP_ECHO_CLASS>, grid, block, smem, stream, a, scratch_floats);
   return cudaSuccess;
 }
-cudaError_t WAP_CAT(set_k_echo_smem_, WAP_ECHO_CLASS)(int bytes) {
-  return cudaFuncSetAttribute(k_echo<WAP_ECHO_CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+cudaError_t WAP_CAT(WAP_KSUF(set_k_echo_smem), WAP_CAT(_, WAP_ECHO_CLASS))(int bytes) {
+  return cudaFuncSetAttribute(WAP_KSUF(k_echo)<WAP_ECHO_CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 #if WAP_ECHO_CLASS == 0
-cudaError_t launch_k_echo(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats) {
+#define WAP_L(N) WAP_CAT(WAP_KSUF(launch_k_echo), _##N)
+#define WAP_S(N) WAP_CAT(WAP_KSUF(set_k_echo_smem), _##N)
+cudaError_t WAP_KSUF(launch_k_echo)(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats) {
   switch (cls) {
-    case kEchoMono16k: return launch_k_echo_1(grid, block, smem, stream, a, scratch_floats);
-    case kEchoMono48kNative: return launch_k_echo_2(grid, block, smem, stream, a, scratch_floats);
-    case kEchoMono48kVia32k: return launch_k_echo_3(grid, block, smem, stream, a, scratch_floats);
-    case kEchoMono32k: return launch_k_echo_4(grid, block, smem, stream, a, scratch_floats);
-    default: return launch_k_echo_0(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono16k: return WAP_L(1)(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono48kNative: return WAP_L(2)(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono48kVia32k: return WAP_L(3)(grid, block, smem, stream, a, scratch_floats);
+    case kEchoMono32k: return WAP_L(4)(grid, block, smem, stream, a, scratch_floats);
+    default: return WAP_L(0)(grid, block, smem, stream, a, scratch_floats);
   }
 }
-cudaError_t set_k_echo_smem(int bytes) {
-  cudaError_t e = set_k_echo_smem_0(bytes);
-  if (e == cudaSuccess) e = set_k_echo_smem_1(bytes);
-  if (e == cudaSuccess) e = set_k_echo_smem_2(bytes);
-  if (e == cudaSuccess) e = set_k_echo_smem_3(bytes);
-  if (e == cudaSuccess) e = set_k_echo_smem_4(bytes);
+cudaError_t WAP_KSUF(set_k_echo_smem)(int bytes) {
+  cudaError_t e = WAP_S(0)(bytes);
+  if (e == cudaSuccess) e = WAP_S(1)(bytes);
+  if (e == cudaSuccess) e = WAP_S(2)(bytes);
+  if (e == cudaSuccess) e = WAP_S(3)(bytes);
+  if (e == cudaSuccess) e = WAP_S(4)(bytes);
   return e;
 }
+int WAP_KSUF(k_echo_scratch_floats)(int bands) { return echo_scratch_floats(bands); }
+#if !WAP_EC3_RUNTIME
 int k_echo_min_blocks() { return WAP_ECHO_MINBLOCKS; }
+#endif
 #endif
 
 }  // namespace wap

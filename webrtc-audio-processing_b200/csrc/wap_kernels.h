@@ -9,21 +9,29 @@
 
 namespace wap {
 
-cudaError_t launch_k_delay(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats);
-cudaError_t set_k_delay_smem(int bytes);
-// cls: wap::EchoClass (wap_pipeline.cuh)
-cudaError_t launch_k_echo(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats);
-cudaError_t set_k_echo_smem(int bytes);
+// Two instances of every heavy kernel: the default EchoCanceller3Config on compile-time constants
+// (no suffix) and the run-time-parameter build (_rt, -DWAP_EC3_RUNTIME=1) for engines created with
+// another config.  cls: wap::EchoClass (wap_pipeline.cuh).
+#define WAP_DECLARE_ECHO_CLASS(S, N)                                                                              \
+  cudaError_t launch_k_echo##S##_##N(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, \
+                                     int scratch_floats);                                                         \
+  cudaError_t set_k_echo_smem##S##_##N(int bytes);
+#define WAP_DECLARE_KERNELS(S)                                                                                          \
+  cudaError_t launch_k_delay##S(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,             \
+                                int scratch_floats);                                                                    \
+  cudaError_t set_k_delay_smem##S(int bytes);                                                                           \
+  int k_delay_scratch_floats##S();                                                                                      \
+  cudaError_t launch_k_echo##S(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,     \
+                               int scratch_floats);                                                                     \
+  cudaError_t set_k_echo_smem##S(int bytes);                                                                            \
+  int k_echo_scratch_floats##S(int bands);                                                                              \
+  WAP_DECLARE_ECHO_CLASS(S, 0)                                                                                          \
+  WAP_DECLARE_ECHO_CLASS(S, 1)                                                                                          \
+  WAP_DECLARE_ECHO_CLASS(S, 2)                                                                                          \
+  WAP_DECLARE_ECHO_CLASS(S, 3)                                                                                          \
+  WAP_DECLARE_ECHO_CLASS(S, 4)
+WAP_DECLARE_KERNELS()
+WAP_DECLARE_KERNELS(_rt)
 int k_echo_min_blocks();
-
-#define WAP_DECLARE_ECHO_CLASS(N)                                                                            \
-  cudaError_t launch_k_echo_##N(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, \
-                                int scratch_floats);                                                         \
-  cudaError_t set_k_echo_smem_##N(int bytes);
-WAP_DECLARE_ECHO_CLASS(0)
-WAP_DECLARE_ECHO_CLASS(1)
-WAP_DECLARE_ECHO_CLASS(2)
-WAP_DECLARE_ECHO_CLASS(3)
-WAP_DECLARE_ECHO_CLASS(4)
 
 }  // namespace wap

@@ -54,11 +54,26 @@ WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float
   }
 }
 
+// Run-time config instances: the engine's Ec3Params into the warp's scratch (kernel parameters live in
+// constant memory; the DSP stages read them through `sc.ep`).
+WAP_DEV void stage_ec3_params(const TickArgs& a, AecScratch& sc) {
+#if WAP_EC3_RUNTIME
+  const int* src = reinterpret_cast<const int*>(&a.ep);
+  int* dst = reinterpret_cast<int*>(&sc.ep);
+  __syncwarp();
+  for (int i = lane_id(); i < (int)(sizeof(Ec3Params) / 4); i += 32) dst[i] = src[i];
+  __syncwarp();
+#else
+  (void)a; (void)sc;
+#endif
+}
+
 // k_delay body: AEC3 delay estimation of one leg for the capture blocks of this tick.
 WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
   AecScratch& sc = *reinterpret_cast<AecScratch*>(scratch);
+  stage_ec3_params(a, sc);
   aec3_delay_frame(st.aec, st.tick, sc);
 }
 
@@ -196,7 +211,10 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   }
   // ---------------- render side: ring / FFT / spectrum writes for the blocks k_front sliced
   UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
-  if (cfg.aec_enabled && ts.n_render_blocks > 0) aec3_echo_render(st.aec, ts, aec_sc, up);
+  if (cfg.aec_enabled && ts.n_render_blocks > 0) {
+    stage_ec3_params(a, aec_sc);
+    aec3_echo_render(st.aec, ts, aec_sc, up);
+  }
   if (!a.capture) return;
 
   // ---------------- capture side (the frame is already high-pass filtered)
@@ -212,7 +230,10 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     }
   }
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
-  if (cfg.aec_enabled) aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
+  if (cfg.aec_enabled) {
+    stage_ec3_params(a, aec_sc);   // the noise suppressor's scratch overlays the AEC3 scratch
+    aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
+  }
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
   if (cfg.split_bands) {
     if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);

@@ -1,6 +1,7 @@
 // Arguments of one 10 ms tick, shared by the three tick kernels.
 #pragma once
 #include "dsp_resampler.cuh"
+#include "wap_ec3_params.h"
 #include "wap_state.h"
 
 namespace wap {
@@ -24,6 +25,7 @@ struct TickArgs {
   void* out;              // [n][frame]
   int fmt;                // 0 = int16, 1 = float [-1,1]  (k_front of a resampled engine: 2 = FloatS16 floats)
   EngineConfig cfg;
+  Ec3Params ep;           // the engine's EchoCanceller3Config parameters (the default config for default engines)
   // Resampled engines only (cfg.resample): per-leg resampler states [slot][kRsPerLeg], the
   // processing-rate frames k_resample leaves for k_front (FloatS16 floats), kernels and ratios.
   ResamplerState* rs;

@@ -69,6 +69,104 @@ class WapStats(C.Structure):
     ]
 
 
+def _struct(name, fields):
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+_f, _i, _b = C.c_float, C.c_int32, C.c_bool
+WapEc3MaskingThresholds = _struct("WapEc3MaskingThresholds", [("enr_transparent", _f), ("enr_suppress", _f), ("emr_transparent", _f)])
+WapEc3Tuning = _struct("WapEc3Tuning", [("mask_lf", WapEc3MaskingThresholds), ("mask_hf", WapEc3MaskingThresholds),
+                                        ("max_inc_factor", _f), ("max_dec_factor_lf", _f)])
+WapEc3AlignmentMixing = _struct("WapEc3AlignmentMixing", [("downmix", _b), ("adaptive_selection", _b),
+                                                          ("activity_power_threshold", _f), ("prefer_first_two_channels", _b)])
+WapEc3RefinedConfiguration = _struct("WapEc3RefinedConfiguration", [
+    ("length_blocks", _i), ("leakage_converged", _f), ("leakage_diverged", _f), ("error_floor", _f), ("error_ceil", _f),
+    ("noise_gate", _f)])
+WapEc3CoarseConfiguration = _struct("WapEc3CoarseConfiguration", [("length_blocks", _i), ("rate", _f), ("noise_gate", _f)])
+WapEc3SubbandRegion = _struct("WapEc3SubbandRegion", [("low", _i), ("high", _i)])
+
+
+class WapEchoCanceller3Config(C.Structure):
+    """Mirror of include/wap_audio_processing.h: WapEchoCanceller3Config (= webrtc::EchoCanceller3Config)."""
+    _fields_ = [
+        ("buffering", _struct("Buffering", [("excess_render_detection_interval_blocks", _i), ("max_allowed_excess_render_blocks", _i)])),
+        ("delay", _struct("Delay", [
+            ("default_delay", _i), ("down_sampling_factor", _i), ("num_filters", _i), ("delay_headroom_samples", _i),
+            ("hysteresis_limit_blocks", _i), ("fixed_capture_delay_samples", _i), ("delay_estimate_smoothing", _f),
+            ("delay_estimate_smoothing_delay_found", _f), ("delay_candidate_detection_threshold", _f),
+            ("delay_selection_thresholds", _struct("DelaySelectionThresholds", [("initial", _i), ("converged", _i)])),
+            ("use_external_delay_estimator", _b), ("log_warning_on_delay_changes", _b),
+            ("render_alignment_mixing", WapEc3AlignmentMixing), ("capture_alignment_mixing", WapEc3AlignmentMixing),
+            ("detect_pre_echo", _b)])),
+        ("filter", _struct("Filter", [
+            ("refined", WapEc3RefinedConfiguration), ("coarse", WapEc3CoarseConfiguration),
+            ("refined_initial", WapEc3RefinedConfiguration), ("coarse_initial", WapEc3CoarseConfiguration),
+            ("config_change_duration_blocks", _i), ("initial_state_seconds", _f), ("coarse_reset_hangover_blocks", _i),
+            ("conservative_initial_phase", _b), ("enable_coarse_filter_output_usage", _b), ("use_linear_filter", _b),
+            ("high_pass_filter_echo_reference", _b), ("export_linear_aec_output", _b)])),
+        ("erle", _struct("Erle", [("min", _f), ("max_l", _f), ("max_h", _f), ("onset_detection", _b), ("num_sections", _i),
+                                  ("clamp_quality_estimate_to_zero", _b), ("clamp_quality_estimate_to_one", _b)])),
+        ("ep_strength", _struct("EpStrength", [
+            ("default_gain", _f), ("default_len", _f), ("nearend_len", _f), ("echo_can_saturate", _b), ("bounded_erl", _b),
+            ("erle_onset_compensation_in_dominant_nearend", _b), ("use_conservative_tail_frequency_response", _b)])),
+        ("echo_audibility", _struct("EchoAudibility", [
+            ("low_render_limit", _f), ("normal_render_limit", _f), ("floor_power", _f), ("audibility_threshold_lf", _f),
+            ("audibility_threshold_mf", _f), ("audibility_threshold_hf", _f), ("use_stationarity_properties", _b),
+            ("use_stationarity_properties_at_init", _b)])),
+        ("render_levels", _struct("RenderLevels", [("active_render_limit", _f), ("poor_excitation_render_limit", _f),
+                                                   ("poor_excitation_render_limit_ds8", _f), ("render_power_gain_db", _f)])),
+        ("echo_removal_control", _struct("EchoRemovalControl", [("has_clock_drift", _b), ("linear_and_stable_echo_path", _b)])),
+        ("echo_model", _struct("EchoModel", [
+            ("noise_floor_hold", _i), ("min_noise_floor_power", _f), ("stationary_gate_slope", _f), ("noise_gate_power", _f),
+            ("noise_gate_slope", _f), ("render_pre_window_size", _i), ("render_post_window_size", _i),
+            ("model_reverb_in_nonlinear_mode", _b)])),
+        ("comfort_noise", _struct("ComfortNoise", [("noise_floor_dbfs", _f)])),
+        ("suppressor", _struct("Suppressor", [
+            ("nearend_average_blocks", _i), ("normal_tuning", WapEc3Tuning), ("nearend_tuning", WapEc3Tuning),
+            ("lf_smoothing_during_initial_phase", _b), ("last_permanent_lf_smoothing_band", _i), ("last_lf_smoothing_band", _i),
+            ("last_lf_band", _i), ("first_hf_band", _i),
+            ("dominant_nearend_detection", _struct("DominantNearendDetection", [
+                ("enr_threshold", _f), ("enr_exit_threshold", _f), ("snr_threshold", _f), ("hold_duration", _i),
+                ("trigger_threshold", _i), ("use_during_initial_phase", _b), ("use_unbounded_echo_spectrum", _b)])),
+            ("subband_nearend_detection", _struct("SubbandNearendDetection", [
+                ("nearend_average_blocks", _i), ("subband1", WapEc3SubbandRegion), ("subband2", WapEc3SubbandRegion),
+                ("nearend_threshold", _f), ("snr_threshold", _f)])),
+            ("use_subband_nearend_detection", _b),
+            ("high_bands_suppression", _struct("HighBandsSuppression", [
+                ("enr_threshold", _f), ("max_gain_during_echo", _f), ("anti_howling_activation_threshold", _f),
+                ("anti_howling_gain", _f)])),
+            ("high_frequency_suppression", _struct("HighFrequencySuppression", [("limiting_gain_band", _i), ("bands_in_limiting_gain", _i)])),
+            ("floor_first_increase", _f), ("conservative_hf_suppression", _b)])),
+        ("multi_channel", _struct("MultiChannel", [
+            ("detect_stereo_content", _b), ("stereo_detection_threshold", _f),
+            ("stereo_detection_timeout_threshold_seconds", _i), ("stereo_detection_hysteresis_seconds", _f)])),
+    ]
+
+
+def ec3_set(cfg, path, value):
+    """cfg.<a.b.c> = value with the reference's member names, e.g. "filter.refined.length_blocks"."""
+    obj = cfg
+    parts = path.split(".")
+    for p in parts[:-1]:
+        obj = getattr(obj, p)
+    cur = getattr(obj, parts[-1])
+    setattr(obj, parts[-1], type(cur)(value) if not isinstance(cur, float) else float(value))
+
+
+def ec3_get(cfg, path):
+    obj = cfg
+    for p in path.split("."):
+        obj = getattr(obj, p)
+    return obj
+
+
+def make_aec3_config(lib, overrides=None, multichannel=False):
+    c = lib.wap_echo_canceller3_config_default_multichannel() if multichannel else lib.wap_echo_canceller3_config_default()
+    for k, v in (overrides or {}).items():
+        ec3_set(c, k, v)
+    return c
+
+
 # Every symbol include/wap_audio_processing.h declares.
 EXPORTS = [
     "wap_create", "wap_create_with_config", "wap_destroy", "wap_config_default", "wap_get_config",
@@ -82,6 +180,9 @@ EXPORTS = [
     "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
     "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
     "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state", "wap_stream_read_taps",
+    "wap_echo_canceller3_config_default", "wap_echo_canceller3_config_default_multichannel", "wap_echo_canceller3_config_sizeof",
+    "wap_echo_canceller3_config_validate", "wap_echo_canceller3_config_supported", "wap_create_with_aec3_config",
+    "wap_engine_create_with_aec3_config",
 ]
 
 _libs = {}
@@ -141,6 +242,17 @@ def load(path=None):
     L.wap_engine_read_kernel_timing.restype = C.c_int64
     L.wap_engine_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double)]
     L.wap_engine_algorithmic_bytes_per_kernel.argtypes = [vp, C.POINTER(C.c_double)]
+    ec3 = WapEchoCanceller3Config
+    L.wap_echo_canceller3_config_default.restype = ec3
+    L.wap_echo_canceller3_config_default_multichannel.restype = ec3
+    L.wap_echo_canceller3_config_sizeof.restype = C.c_size_t
+    L.wap_echo_canceller3_config_validate.restype = C.c_bool
+    L.wap_echo_canceller3_config_validate.argtypes = [C.POINTER(ec3)]
+    L.wap_echo_canceller3_config_supported.argtypes = [C.POINTER(ec3)]
+    L.wap_create_with_aec3_config.restype = vp
+    L.wap_create_with_aec3_config.argtypes = [cfg, C.POINTER(ec3), C.POINTER(ec3)]
+    L.wap_engine_create_with_aec3_config.restype = vp
+    L.wap_engine_create_with_aec3_config.argtypes = [C.c_int, i32, cfg, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_version.restype = C.c_char_p
     _libs[path] = L
     return L
@@ -187,13 +299,20 @@ class WapStageTaps(C.Structure):
 class Engine:
     """Batched engine: `n` call legs of one config class on one GPU."""
 
-    def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, **cfg):
+    def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, aec3=None, **cfg):
+        """aec3: None (default EchoCanceller3Config), a dict of overrides keyed by the reference's member
+        paths ("filter.refined.length_blocks": 10, ...) or a WapEchoCanceller3Config."""
         self.lib = lib or load()
         self.rate, self.channels, self.n = rate, channels, n_streams
         self.frame = rate // 100 * channels
         self.config = make_config(self.lib, **cfg)
-        self.h = self.lib.wap_engine_create(device, capacity or n_streams, self.config,
-                                            WapStreamConfig(rate, channels))
+        if aec3 is None:
+            self.h = self.lib.wap_engine_create(device, capacity or n_streams, self.config,
+                                                WapStreamConfig(rate, channels))
+        else:
+            self.aec3 = aec3 if isinstance(aec3, WapEchoCanceller3Config) else make_aec3_config(self.lib, aec3)
+            self.h = self.lib.wap_engine_create_with_aec3_config(device, capacity or n_streams, self.config,
+                                                                 WapStreamConfig(rate, channels), C.byref(self.aec3), None)
         if not self.h:
             raise RuntimeError("wap_engine_create failed (no CUDA device or unsupported config)")
         self.handles = (C.c_void_p * n_streams)()
