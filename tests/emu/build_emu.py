@@ -14,7 +14,9 @@ CSRC = os.path.join(ROOT, "webrtc-audio-processing_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 # WAP_EMU_O0=1: unoptimised variant (no code cloning), for WAP_EMU_CHECK_DIVERGENCE runs.
 O0 = bool(os.environ.get("WAP_EMU_O0"))
-LIB = os.path.join(OUT, "libwap_emu_O0.so" if O0 else "libwap_emu.so")
+# WAP_EMU_EXTRA="-DWAP_ECHO_LOCKSTEP=1": experiment variants of the kernel source (separate library name)
+EXTRA = os.environ.get("WAP_EMU_EXTRA", "").split()
+LIB = os.path.join(OUT, "libwap_emu_O0.so" if O0 else ("libwap_emu_x.so" if EXTRA else "libwap_emu.so"))
 
 
 def build(verbose=True):
@@ -29,10 +31,10 @@ def build(verbose=True):
     base = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
             "-DWAP_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", HERE, "-I", CSRC,
             "-I", os.path.join(ROOT, "include"), "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
-            "-Wno-unused-variable"]
+            "-Wno-unused-variable"] + EXTRA
     # the same translation units as the product build: wap_k_echo.cu once per config class
     tus = []
-    tag = "_O0" if O0 else ""
+    tag = "_O0" if O0 else ("_x" if EXTRA else "")
     for s in srcs:
         name = os.path.basename(s).rsplit(".", 1)[0]
         if name == "wap_k_echo":

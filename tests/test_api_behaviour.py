@@ -530,3 +530,23 @@ def test_reference_seam_class_runs_on_this_library(api_lib, oracle):
         assert rc == 0, rc
         assert np.array_equal(out, ref_out)
         assert np.abs(stats[:, 1] - ref_stats[:, 3]).max() <= 0.1 and np.array_equal(stats[:, 2], ref_stats[:, 5])
+
+
+def test_multi_channel_pipeline_flags_on_mono_legs(api_lib, oracle):
+    """pipeline.multi_channel_render / _capture with mono frames: the reference runs its mono configuration
+    (config_selector.cc:44-58, one render and one capture channel), so the flags are accepted and change
+    nothing; with stereo frames they select true multi-channel processing, which is refused."""
+    import wap_b200
+    far, near = synthetic_leg(10, 100)
+    ro, _, err = oracle.RefApm(aec=True, ns=True, ns_level=1, mc_render=True, mc_capture=True).run_i16(16000, far, near)
+    assert err == 0
+    eng = wap_b200.Engine(1, 16000, lib=api_lib, aec=True, ns=True, ns_level=1, mc_render=True, mc_capture=True)
+    out = np.zeros_like(near)
+    for f in range(100):
+        sl = slice(f * 160, (f + 1) * 160)
+        eng.set_stream_delay_ms(0)
+        out[sl] = eng.process(far[sl][None, :], near[sl][None, :])[0]
+    eng.close()
+    assert np.array_equal(out, ro)
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 16000, channels=2, lib=api_lib, aec=True, ns=True, mc_render=True, mc_capture=True)

@@ -208,6 +208,7 @@ WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* ban
   const int nb = ts.n_capture_blocks == 3 ? 3 : 2;
 #pragma unroll 1
   for (int b = 0; b < nb; ++b) {
+    WAP_PHASE_SYNC();
     aec3_echo_block(a, cfg, sc, ts, b, up);
     if (b < 2) {
       const int len = sc.s.output_framer_len;
@@ -228,6 +229,7 @@ WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* ban
       framer_insert(a.output_framer, &sc.s.output_framer_len, sc.y);
     }
   }
+  if (nb == 2) WAP_PHASE_SYNC();   // the third block slot of the tick
   __syncwarp();
   // ApmStatsReporter::UpdateStatistics (audio_processing_impl.cc:2322-2328): a
   // one-slot queue -- while the slot is full (nobody called GetStatistics) the

@@ -139,7 +139,7 @@ WAP_DEV void mf_acc_filter(Aec3State& a, AecScratch& sc, int n, const float* y) 
     __syncwarp();
     if (lane == 0) {  // the one dependent chain of the block: 128 additions in order
       float s_acum = 0.f;
-#pragma unroll 4
+#pragma unroll
       for (int g = 0; g < kAccErrLen; g += 4) {
         float4 v = *reinterpret_cast<const float4*>(&sc.mf.q[g]);
         s_acum += v.x; v.x = s_acum;

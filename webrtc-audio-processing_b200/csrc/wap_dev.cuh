@@ -32,6 +32,18 @@ extern __shared__ __align__(16) unsigned char wap_dyn_smem_raw[];
 
 #define WAP_FULL 0xffffffffu
 
+// Experiment (-DWAP_ECHO_LOCKSTEP=1): the warps of a k_echo CTA meet at a fixed sequence of points of
+// a tick, so that they walk the same stretch of the kernel's (~375 KB) code at about the same time and
+// share instruction-cache lines.  Every warp of the CTA passes every point exactly once per tick.
+#ifndef WAP_ECHO_LOCKSTEP
+#define WAP_ECHO_LOCKSTEP 0
+#endif
+#if WAP_ECHO_LOCKSTEP
+#define WAP_PHASE_SYNC() __syncthreads()
+#else
+#define WAP_PHASE_SYNC() ((void)0)
+#endif
+
 namespace wap {
 
 // IEEE division for a divisor that is (or may become, after inlining) a compile-time constant:

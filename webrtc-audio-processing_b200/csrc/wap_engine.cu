@@ -217,8 +217,10 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   // Multi-channel frames are downmixed for processing and the mono result is copied to every
   // output channel (the default pipeline); true multi-channel processing is SURVEY 8 cfg4.
   // Stereo needs AEC3 (without it the reference runs NS / AGC2 on both channels).
-  if (f.num_channels > 2 || c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture ||
-      (f.num_channels == 2 && !c.echo_canceller_enabled))
+  // pipeline.multi_channel_render / _capture only matter for frames with more than one channel (mono
+  // legs run the mono EchoCanceller3Config whatever the flags say: config_selector.cc:44-58).
+  if (f.num_channels > 2 ||
+      (f.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture || !c.echo_canceller_enabled)))
     return WapError::UnsupportedConfig;
   e.channels = f.num_channels;
   e.levels_enabled = (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) ? 1 : 0;
@@ -1079,12 +1081,29 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     const size_t leg_bytes = (size_t)e->frame_len * esz;
     WAP_CUDA(cudaEventRecord(e->ev_start, e->stream));
     WAP_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
-    // Range length: a whole number of full-occupancy waves of both warp-per-leg kernels
-    // (4 and 5 CTAs of 4 legs per SM), so cutting the batch adds no partial waves.
+    // Range boundaries.  Only two copies are ever exposed: the host->device copy of the FIRST range
+    // (nothing to compute yet) and the device->host copy of the LAST one (nothing left to compute), so
+    // those two ranges are one full-occupancy wave of the warp-per-leg kernels (4 and 5 CTAs of 4 legs
+    // per SM) and the middle takes the rest in at most `chunks - 3` (>= 1) ranges of whole waves: every extra
+    // range costs the tail of two kernels, so there are as few as the overlap needs.
     const int wave = e->forced_chunks ? 4 : e->sm_count * 80;
-    const int per = ((n + chunks - 1) / chunks + wave - 1) / wave * wave;
-    for (int c = 0, off = 0; off < n; ++c, off += per) {
-      const int cnt = std::min(per, n - off);
+    int bounds[kMaxChunks + 1];
+    int nr = 0;
+    bounds[0] = 0;
+    if (e->forced_chunks || n < 3 * wave) {
+      const int per = ((n + chunks - 1) / chunks + wave - 1) / wave * wave;
+      for (int off = per; off < n && nr < kMaxChunks - 1; off += per) bounds[++nr] = off;
+    } else {
+      bounds[++nr] = wave;
+      const int mid = n - 2 * wave;
+      const int parts = std::max(1, std::min(chunks - 3, mid / wave));
+      const int per = ((mid + parts - 1) / parts + wave - 1) / wave * wave;
+      for (int off = wave + per; off < n - wave && nr < kMaxChunks - 2; off += per) bounds[++nr] = off;
+      bounds[++nr] = n - wave;
+    }
+    bounds[++nr] = n;
+    for (int c = 0; c < nr; ++c) {
+      const int off = bounds[c], cnt = bounds[c + 1] - off;
       const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
       if (render)
         WAP_CUDA(cudaMemcpyAsync((char*)e->d_render + bo, (const char*)src_r + bo, bc, cudaMemcpyHostToDevice, e->copy_in));
@@ -1096,8 +1115,8 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     int uniform_delay = -1;
     err = prepare_tick(e, handles, n, &d_delays, &uniform_delay);
     if (err != WapError::None) return err;
-    for (int c = 0, off = 0; off < n; ++c, off += per) {
-      const int cnt = std::min(per, n - off);
+    for (int c = 0; c < nr; ++c) {
+      const int off = bounds[c], cnt = bounds[c + 1] - off;
       const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
       WAP_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in[c], 0));
       err = launch_tick(e, e->d_slots + off, d_delays ? d_delays + off : nullptr, uniform_delay, cnt,

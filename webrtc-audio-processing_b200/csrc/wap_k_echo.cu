@@ -34,10 +34,19 @@ __global__ void __launch_bounds__(128, WAP_ECHO_MINBLOCKS) WAP_KSUF(k_echo)(Tick
   asm volatile("" : "+r"(scratch_off));
 #endif
   float* scratch = sm + scratch_off;
+#if WAP_ECHO_LOCKSTEP
+  // every warp of the CTA makes the same number of trips; a warp without a leg only keeps the phase points
+  for (int base = blockIdx.x * wpb; base < a.n; base += gridDim.x * wpb) {
+    const int idx = base + warp;
+    echo_stream_tick<kClass>(a, idx < a.n ? idx : -1, scratch);
+    __syncwarp();
+  }
+#else
   for (int idx = blockIdx.x * wpb + warp; idx < a.n; idx += gridDim.x * wpb) {
     echo_stream_tick<kClass>(a, idx, scratch);
     __syncwarp();
   }
+#endif
 }
 
 cudaError_t WAP_CAT(WAP_KSUF(launch_k_echo), WAP_CAT(_, WAP_ECHO_CLASS))(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,

@@ -183,6 +183,16 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   }
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
+#if WAP_ECHO_LOCKSTEP
+  WAP_PHASE_SYNC();
+  if (idx < 0) {  // no leg for this warp in this trip: pass the same phase points
+    if (!a.capture) return;
+    WAP_PHASE_SYNC();
+    if (cfg.aec_enabled) { WAP_PHASE_SYNC(); WAP_PHASE_SYNC(); WAP_PHASE_SYNC(); WAP_PHASE_SYNC(); }
+    WAP_PHASE_SYNC();
+    return;
+  }
+#endif
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
   const TickScratch& ts = st.tick;
@@ -216,6 +226,7 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     aec3_echo_render(st.aec, ts, aec_sc, up);
   }
   if (!a.capture) return;
+  WAP_PHASE_SYNC();
 
   // ---------------- capture side (the frame is already high-pass filtered)
   if (up) {  // k_front already split the capture frame (it needs band 0 for the blocks)
@@ -231,9 +242,11 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   }
   if (cfg.ns_enabled) ns_analyze(st.ns, cfg, bands, ns_sc);
   if (cfg.aec_enabled) {
+    WAP_PHASE_SYNC();
     stage_ec3_params(a, aec_sc);   // the noise suppressor's scratch overlays the AEC3 scratch
-    aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);
+    aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);   // three more phase points, one per block slot
   }
+  WAP_PHASE_SYNC();
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
   if (cfg.split_bands) {
     if (B == 3) three_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), st.capture_bands.synthesis);

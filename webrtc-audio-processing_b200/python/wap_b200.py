@@ -259,8 +259,10 @@ def load(path=None):
 
 
 def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False, agc2=False,
-                agc2_fixed_gain_db=0.0, pre_amp=None, pre_gain=None, post_gain=None):
+                agc2_fixed_gain_db=0.0, pre_amp=None, pre_gain=None, post_gain=None, mc_render=False, mc_capture=False):
     c = lib.wap_config_default()
+    c.pipeline_multi_channel_render = bool(mc_render)
+    c.pipeline_multi_channel_capture = bool(mc_capture)
     if pre_amp is not None:
         c.pre_amplifier_enabled = True
         c.pre_amplifier_fixed_gain_factor = float(pre_amp)
