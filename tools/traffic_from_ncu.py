@@ -24,6 +24,6 @@ res = {}
 for k, v in acc.items():
     m = sum(v) / len(v)
     res[k] = {"dram_bytes_per_launch_mean": m, "launches": len(v), "legs": legs, "dram_bytes_per_leg_frame": m / legs}
-res["_source"] = "ncu --set full (%s), %d legs, early ticks (2- and 3-block); tools/traffic_from_ncu.py" % (rep, legs)
+res["_source"] = "ncu --set full (%s), %d legs, steady state (ticks >= 300; 2- and 3-block); tools/traffic_from_ncu.py" % (rep, legs)
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))
