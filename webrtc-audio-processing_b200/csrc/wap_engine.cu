@@ -65,6 +65,26 @@ __global__ void k_init_slots(StreamState* states, const StreamState* tmpl, const
   }
 }
 
+// Multi-channel engines: a fresh McState (zeros, the channel templates, BlockFramer holding one block of
+// zeros, the content detector's start state) into `n` arena slots.  which: 1 when the legs start with
+// persistent multichannel content (detect_stereo_content off), else 0.
+__global__ void k_mc_init_slots(McState* mcs, const McTemplates* t, const int* slots, int n, int which) {
+  const size_t words = sizeof(McState) / 4;
+  const size_t chan0 = offsetof(McState, chan) / 4, chan_words = sizeof(McChan) / 4;
+  const uint32_t* tc = reinterpret_cast<const uint32_t*>(&t->chan[which]);
+  for (int i = blockIdx.y; i < n; i += gridDim.y) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&mcs[slots[i]]);
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) {
+      uint32_t v = 0;
+      if (w >= chan0 && w < chan0 + kMcCh * chan_words) v = tc[(w - chan0) % chan_words];
+      else if (w == offsetof(McState, output_framer_len) / 4) v = kBlock;
+      else if (w == (offsetof(McState, det) + offsetof(McDetector, persistent)) / 4) v = (uint32_t)which;
+      else if (w == (offsetof(McState, det) + offsetof(McDetector, render_channels_to_aec)) / 4) v = which ? 2u : 1u;
+      dst[w] = v;
+    }
+  }
+}
+
 }  // namespace wap
 
 using wap::EngineConfig;
@@ -134,6 +154,12 @@ struct WapEngine {
   float* d_rs_capture = nullptr;
   float* d_rs_capture1 = nullptr;        // stereo: second capture channel
   wap::ExtraChannelState* d_extra = nullptr;  // stereo engines: [capacity]
+  // multi-channel engines (EngineConfig::mc)
+  wap::McState* d_mc = nullptr;             // [capacity]
+  wap::McTemplates* d_mc_templates = nullptr;
+  wap::Ec3Params ep_mc = wap::ec3_default_params();
+  wap::McParams mcp[2] = {};
+  int mc_front_floats = 0, mc_echo_floats = 0;
   double rs_ratio_in = 1.0, rs_ratio_out = 1.0;
   int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
   // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
@@ -219,9 +245,16 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   // Stereo needs AEC3 (without it the reference runs NS / AGC2 on both channels).
   // pipeline.multi_channel_render / _capture only matter for frames with more than one channel (mono
   // legs run the mono EchoCanceller3Config whatever the flags say: config_selector.cc:44-58).
-  if (f.num_channels > 2 ||
-      (f.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture || !c.echo_canceller_enabled)))
-    return WapError::UnsupportedConfig;
+  if (f.num_channels > 2 || (f.num_channels == 2 && !c.echo_canceller_enabled)) return WapError::UnsupportedConfig;
+  if (f.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture)) {
+    // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) only,
+    // at a native rate of 16 or 48 kHz.
+    if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) || c.noise_suppression_enabled ||
+        c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.resample ||
+        e.num_bands == 2)
+      return WapError::UnsupportedConfig;
+    e.mc = 1;
+  }
   e.channels = f.num_channels;
   e.levels_enabled = (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) ? 1 : 0;
   e.post_gain_enabled = c.capture_level_adjustment_enabled ? 1 : 0;
@@ -643,6 +676,41 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   if (timing) cudaEventRecord(e->ev[0], e->stream);
   a.extra = e->d_extra;
   a.rs_capture1 = nullptr;
+  a.mc = e->d_mc;
+  a.mc_templates = e->d_mc_templates;
+  a.ep_mc = e->ep_mc;
+  a.mcp[0] = e->mcp[0];
+  a.mcp[1] = e->mcp[1];
+  if (e->cfg.mc) {
+    // multi-channel legs: k_mc_front -> k_delay_rt -> k_mc_echo [-> k_mc_post]
+    wap::launch_k_mc_front(grid_for(n), wpb * 32, (size_t)wpb * e->mc_front_floats * sizeof(float), e->stream, a, e->mc_front_floats);
+    e->launches++;
+    if (timing) cudaEventRecord(e->ev[1], e->stream);
+    if (d_capture) {
+      wap::launch_k_delay_rt(grid_for(n), wpb * 32, (size_t)wpb * e->delay_scratch_floats * sizeof(float), e->stream, a,
+                             e->delay_scratch_floats);
+      e->launches++;
+    }
+    if (timing) cudaEventRecord(e->ev[2], e->stream);
+    wap::launch_k_mc_echo(grid_for(n), wpb * 32, (size_t)wpb * e->mc_echo_floats * sizeof(float), e->stream, a, e->mc_echo_floats);
+    e->launches++;
+    if (e->cfg.num_bands == 3 && d_capture) {
+      wap::launch_k_mc_post(e->stream, a);
+      e->launches++;
+    }
+    if (timing) {
+      cudaEventRecord(e->ev[3], e->stream);
+      WAP_CUDA(cudaEventSynchronize(e->ev[3]));
+      for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev[k], e->ev[k + 1]);
+        e->kernel_ms[k] += ms;
+      }
+      e->timed_ticks++;
+    }
+    WAP_CUDA(cudaGetLastError());
+    return WapError::None;
+  }
   if (e->cfg.resample) {
     // API-rate frames -> processing-rate frames; k_front then reads those (already FloatS16).
     a.rs = e->d_rs;
@@ -776,9 +844,27 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
   if (check_device() != WapError::None) return nullptr;
   EngineConfig cfg{};
   WapError err = resolve_config(config, fmt, &cfg);
-  (void)aec3_multichannel_config;  // applies to legs with more than one render / capture channel (not built: resolve_config refuses them)
   const WapEchoCanceller3Config aec3 = aec3_config ? *aec3_config : ec3_config_default();
+  // AudioProcessingImpl::InitializeEchoController (audio_processing_impl.cc:1928-1943): the default
+  // multichannel config only when the user set neither; a mono config alone serves both.
+  const WapEchoCanceller3Config aec3_mc = aec3_multichannel_config ? *aec3_multichannel_config
+                                          : (aec3_config ? *aec3_config : wap_echo_canceller3_config_default_multichannel());
   if (err == WapError::None && config.echo_canceller_enabled) err = ec3_config_supported(aec3);
+  if (err == WapError::None && cfg.mc) {
+    err = ec3_config_supported(aec3_mc);
+    // ConfigSelector's CompatibleConfigs (config_selector.cc:23-48), plus what the engine fixes per engine
+    // rather than per leg state: the delay-estimation and buffering parameters and the comfort-noise floor.
+    if (err == WapError::None &&
+        (aec3.multi_channel.detect_stereo_content != aec3_mc.multi_channel.detect_stereo_content ||
+         aec3.multi_channel.stereo_detection_timeout_threshold_seconds !=
+             aec3_mc.multi_channel.stereo_detection_timeout_threshold_seconds ||
+         aec3.comfort_noise.noise_floor_dbfs != aec3_mc.comfort_noise.noise_floor_dbfs ||
+         (aec3.delay.render_alignment_mixing.downmix && aec3.delay.render_alignment_mixing.adaptive_selection) ||
+         (aec3_mc.delay.render_alignment_mixing.downmix && aec3_mc.delay.render_alignment_mixing.adaptive_selection) ||
+         (aec3.delay.capture_alignment_mixing.downmix && aec3.delay.capture_alignment_mixing.adaptive_selection) ||
+         (aec3_mc.delay.capture_alignment_mixing.downmix && aec3_mc.delay.capture_alignment_mixing.adaptive_selection)))
+      err = WapError::UnsupportedConfig;
+  }
   if (err != WapError::None) {
     fprintf(stderr, "[wap_b200] unsupported engine config (error %d)\n", (int)err);
     return nullptr;
@@ -796,7 +882,29 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
   e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
   e->aec3_config = aec3;
   e->ep = ec3_params_from_config(aec3);
-  e->ec3_runtime = config.echo_canceller_enabled && !wap::same_ec3_params(e->ep, wap::ec3_default_params());
+  e->ec3_runtime = config.echo_canceller_enabled && (cfg.mc || !wap::same_ec3_params(e->ep, wap::ec3_default_params()));
+  if (cfg.mc) {
+    e->ep_mc = ec3_params_from_config(aec3_mc);
+    const WapEchoCanceller3Config* cc[2] = {&aec3, &aec3_mc};
+    // The detector is built from the config that is active at construction (echo_canceller3.cc:765-775).
+    const WapEchoCanceller3Config& dc = aec3.multi_channel.detect_stereo_content ? aec3 : aec3_mc;
+    for (int i = 0; i < 2; ++i) {
+      wap::McParams& m = e->mcp[i];
+      m.detect_stereo_content = dc.multi_channel.detect_stereo_content ? 1 : 0;
+      m.detection_threshold = dc.multi_channel.stereo_detection_threshold;
+      m.timeout_frames = dc.multi_channel.stereo_detection_timeout_threshold_seconds > 0
+                             ? dc.multi_channel.stereo_detection_timeout_threshold_seconds * 100 : 0;
+      m.hysteresis_frames = (int)(dc.multi_channel.stereo_detection_hysteresis_seconds * 100);
+      const WapEc3AlignmentMixing& rm = cc[i]->delay.render_alignment_mixing;
+      const WapEc3AlignmentMixing& cm = cc[i]->delay.capture_alignment_mixing;
+      m.render_mix_downmix = rm.downmix; m.render_mix_adaptive = rm.adaptive_selection;
+      m.render_mix_prefer_first_two = rm.prefer_first_two_channels; m.render_mix_threshold = rm.activity_power_threshold;
+      m.capture_mix_downmix = cm.downmix; m.capture_mix_adaptive = cm.adaptive_selection;
+      m.capture_mix_prefer_first_two = cm.prefer_first_two_channels; m.capture_mix_threshold = cm.activity_power_threshold;
+    }
+    e->mc_front_floats = wap::k_mc_front_scratch_floats();
+    e->mc_echo_floats = wap::k_mc_echo_scratch_floats();
+  }
   e->echo_scratch_floats = e->ec3_runtime ? wap::k_echo_scratch_floats_rt(cfg.num_bands) : wap::k_echo_scratch_floats(cfg.num_bands);
   e->echo_class = wap::echo_class_of(cfg);
   e->delay_scratch_floats = e->ec3_runtime ? wap::k_delay_scratch_floats_rt() : wap::k_delay_scratch_floats();
@@ -821,13 +929,23 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
          cudaMalloc((void**)&e->d_rs_kernels, tables.size() * sizeof(float)) == cudaSuccess &&
          cudaMemcpy(e->d_rs_kernels, tables.data(), tables.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
   }
-  if (ok && cfg.channels == 2) {
+  if (ok && cfg.mc) {
+    wap::McTemplates* t = new wap::McTemplates;
+    wap::init_mc_templates(*t, e->ep, e->ep_mc);
+    ok = cudaMalloc((void**)&e->d_mc, (size_t)max_streams * sizeof(wap::McState)) == cudaSuccess &&
+         cudaMalloc((void**)&e->d_mc_templates, sizeof(wap::McTemplates)) == cudaSuccess &&
+         cudaMemcpy(e->d_mc_templates, t, sizeof(wap::McTemplates), cudaMemcpyHostToDevice) == cudaSuccess &&
+         wap::set_k_mc_smem(4 * e->mc_front_floats * (int)sizeof(float), 4 * e->mc_echo_floats * (int)sizeof(float)) == cudaSuccess;
+    delete t;
+  }
+  if (ok && cfg.channels == 2 && !cfg.mc) {
     const size_t xb = (size_t)max_streams * sizeof(wap::ExtraChannelState);
     ok = cudaMalloc((void**)&e->d_extra, xb) == cudaSuccess && cudaMemset(e->d_extra, 0, xb) == cudaSuccess;
   }
   if (ok) {
     StreamState* tmpl = new StreamState;
-    wap::init_stream_state(*tmpl, e->ep);
+    // legs of a multi-channel engine without stereo detection start on the multichannel config
+    wap::init_stream_state(*tmpl, (cfg.mc && !e->mcp[0].detect_stereo_content) ? e->ep_mc : e->ep);
     tmpl->agc2.gain_last = tmpl->agc2.gain_current = cfg.agc2_fixed_gain;
     if (cfg.levels_enabled) {  // InitializeCaptureLevelsAdjuster (audio_processing_impl.cc:2108-2130)
       float pre_gain = 1.f;
@@ -867,6 +985,8 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_rs_capture);
   cudaFree(e->d_rs_capture1);
   cudaFree(e->d_extra);
+  cudaFree(e->d_mc);
+  cudaFree(e->d_mc_templates);
   cudaFree(e->d_template);
   cudaFree(e->d_render);
   cudaFree(e->d_capture);
@@ -907,6 +1027,12 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
       for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
     if (e->d_extra)
       for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_extra[slots[i]], 0, sizeof(wap::ExtraChannelState), e->stream));
+    if (e->d_mc) {
+      WAP_LAUNCH(wap::k_mc_init_slots, dim3(32, std::min(n, 2048)), 256, 0, e->stream, e->d_mc,
+                 (const wap::McTemplates*)e->d_mc_templates, (const int*)d_slots, (int)n,
+                 e->mcp[0].detect_stereo_content ? 0 : 1);
+      e->launches++;
+    }
     if (e->d_rs)
       for (int i = 0; i < n; ++i)
         WAP_CUDA(cudaMemsetAsync(&e->d_rs[(size_t)slots[i] * wap::kRsPerLeg], 0, wap::kRsPerLeg * sizeof(wap::ResamplerState), e->stream));
@@ -1181,6 +1307,7 @@ struct BlobHeader {
   uint64_t total_bytes;
   wap::EngineConfig cfg;  // the blob only fits an engine of the same config class
   wap::Ec3Params ep;      // ... and the same EchoCanceller3Config
+  wap::Ec3Params ep_mc;   // ... and multichannel EchoCanceller3Config
   // host-side per-leg state
   WapConfig config;
   int32_t delay_ms, delay_set, capture_output_used, analog_level, playout_volume;
@@ -1189,12 +1316,13 @@ struct BlobHeader {
   WapStats cached_stats;
 };
 constexpr uint32_t kBlobMagic = 0x57415042u;  // "WAPB"
-constexpr uint32_t kBlobVersion = 2;
+constexpr uint32_t kBlobVersion = 3;
 size_t blob_bytes(const WapEngine* e) {
   size_t n = sizeof(BlobHeader) + sizeof(StreamState);
   if (e->d_upper) n += sizeof(wap::UpperBandState);
   if (e->d_rs) n += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   if (e->d_extra) n += sizeof(wap::ExtraChannelState);
+  if (e->d_mc) n += sizeof(wap::McState);
   return n;
 }
 }  // namespace
@@ -1217,6 +1345,7 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
   hd.total_bytes = blob_bytes(e);
   hd.cfg = e->cfg;
   hd.ep = e->ep;
+  hd.ep_mc = e->ep_mc;
   hd.config = h->config;
   hd.delay_ms = e->leg_delay_ms[h->slot];
   hd.delay_set = e->leg_delay_set[h->slot];
@@ -1242,7 +1371,11 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
     WAP_CUDA(cudaMemcpy(p, &e->d_rs[(size_t)h->slot * wap::kRsPerLeg], wap::kRsPerLeg * sizeof(wap::ResamplerState), cudaMemcpyDeviceToHost));
     p += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   }
-  if (e->d_extra) WAP_CUDA(cudaMemcpy(p, &e->d_extra[h->slot], sizeof(wap::ExtraChannelState), cudaMemcpyDeviceToHost));
+  if (e->d_extra) {
+    WAP_CUDA(cudaMemcpy(p, &e->d_extra[h->slot], sizeof(wap::ExtraChannelState), cudaMemcpyDeviceToHost));
+    p += sizeof(wap::ExtraChannelState);
+  }
+  if (e->d_mc) WAP_CUDA(cudaMemcpy(p, &e->d_mc[h->slot], sizeof(wap::McState), cudaMemcpyDeviceToHost));
   return WapError::None;
 }
 
@@ -1254,7 +1387,8 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   BlobHeader hd;
   memcpy(&hd, blob, sizeof(hd));
   if (hd.magic != kBlobMagic || hd.version != kBlobVersion || hd.total_bytes != blob_bytes(e) || bytes < hd.total_bytes ||
-      !wap::same_engine_config(hd.cfg, e->cfg) || !wap::same_ec3_params(hd.ep, e->ep))
+      !wap::same_engine_config(hd.cfg, e->cfg) || !wap::same_ec3_params(hd.ep, e->ep) ||
+      !wap::same_ec3_params(hd.ep_mc, e->ep_mc))
     return WapError::UnsupportedConfig;  // another config class (or library version)
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1269,7 +1403,11 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
     WAP_CUDA(cudaMemcpy(&e->d_rs[(size_t)h->slot * wap::kRsPerLeg], p, wap::kRsPerLeg * sizeof(wap::ResamplerState), cudaMemcpyHostToDevice));
     p += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   }
-  if (e->d_extra) WAP_CUDA(cudaMemcpy(&e->d_extra[h->slot], p, sizeof(wap::ExtraChannelState), cudaMemcpyHostToDevice));
+  if (e->d_extra) {
+    WAP_CUDA(cudaMemcpy(&e->d_extra[h->slot], p, sizeof(wap::ExtraChannelState), cudaMemcpyHostToDevice));
+    p += sizeof(wap::ExtraChannelState);
+  }
+  if (e->d_mc) WAP_CUDA(cudaMemcpy(&e->d_mc[h->slot], p, sizeof(wap::McState), cudaMemcpyHostToDevice));
   e->dirty_legs -= (int)h->capture_output_used_dirty + (int)h->pre_gain_dirty + (int)h->post_gain_dirty +
                    (int)h->playout_volume_dirty + (int)h->agc2_gain_dirty;
   h->config = hd.config;
@@ -1294,6 +1432,7 @@ WapError wap_stream_read_taps(WapAudioProcessing* h, WapStageTaps* out) {
   if (!h || !out) return WapError::NullPointer;
   if (!h->engine || h->slot < 0) return WapError::BadStreamParameter;
   WapEngine* e = h->engine;
+  if (e->cfg.mc) return WapError::UnsupportedConfig;  // the stage taps describe a single capture channel
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   WAP_CUDA(cudaSetDevice(e->device));
   WAP_CUDA(cudaStreamSynchronize(e->stream));

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "wap_ec3_params.h"
+#include "wap_mc_state.h"
 #include "wap_state.h"
 
 namespace wap {
@@ -101,6 +102,24 @@ inline void init_aec3_state(Aec3State& a, const Ec3Params& ep) {
   s.cng_seed = 42;
   s.sg_initial_state = 1;
   s.sg_average_power = 32768.f * 32768.f;  // LowNoiseRenderDetector (suppression_gain.h:106)
+}
+
+// The per-capture-channel part of a freshly constructed AEC3 state (wap_mc_state.h).
+inline void init_mc_chan(McChan& c, const Aec3State& a) {
+  memset(&c, 0, sizeof(c));
+  memcpy(c.H_error, a.H_error, sizeof(c.H_error));
+  memcpy(c.erle, a.erle, sizeof(c.erle));
+  memcpy(c.erle_onset_comp, a.erle_onset_comp, sizeof(c.erle_onset_comp));
+  memcpy(c.erle_unbounded, a.erle_unbounded, sizeof(c.erle_unbounded));
+  memcpy(c.cng_N2, a.cng_N2, sizeof(c.cng_N2));
+  memcpy(c.coming_onset, a.coming_onset, sizeof(c.coming_onset));
+  c.s = a.s;
+}
+inline void init_mc_templates(McTemplates& t, const Ec3Params& ep_mono, const Ec3Params& ep_multichannel) {
+  init_aec3_state(t.aec[0], ep_mono);
+  init_aec3_state(t.aec[1], ep_multichannel);
+  init_mc_chan(t.chan[0], t.aec[0]);
+  init_mc_chan(t.chan[1], t.aec[1]);
 }
 
 inline void init_stream_state(StreamState& st, const Ec3Params& ep = ec3_default_params()) {

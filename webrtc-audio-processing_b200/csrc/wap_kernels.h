@@ -34,4 +34,12 @@ WAP_DECLARE_KERNELS()
 WAP_DECLARE_KERNELS(_rt)
 int k_echo_min_blocks();
 
+// Multi-channel legs (wap_k_mc.cu)
+int k_mc_front_scratch_floats();
+int k_mc_echo_scratch_floats();
+cudaError_t set_k_mc_smem(int front_bytes, int echo_bytes);
+cudaError_t launch_k_mc_front(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats);
+cudaError_t launch_k_mc_echo(int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a, int scratch_floats);
+cudaError_t launch_k_mc_post(cudaStream_t stream, const TickArgs& a);
+
 }  // namespace wap

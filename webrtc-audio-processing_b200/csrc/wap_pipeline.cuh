@@ -56,15 +56,15 @@ WAP_DEV void store_frame(void* dst, size_t stream, int len, int fmt, const float
 
 // Run-time config instances: the engine's Ec3Params into the warp's scratch (kernel parameters live in
 // constant memory; the DSP stages read them through `sc.ep`).
-WAP_DEV void stage_ec3_params(const TickArgs& a, AecScratch& sc) {
+WAP_DEV void stage_ec3_params(const TickArgs& a, AecScratch& sc, bool multichannel = false) {
 #if WAP_EC3_RUNTIME
-  const int* src = reinterpret_cast<const int*>(&a.ep);
+  const int* src = reinterpret_cast<const int*>(multichannel ? &a.ep_mc : &a.ep);
   int* dst = reinterpret_cast<int*>(&sc.ep);
   __syncwarp();
   for (int i = lane_id(); i < (int)(sizeof(Ec3Params) / 4); i += 32) dst[i] = src[i];
   __syncwarp();
 #else
-  (void)a; (void)sc;
+  (void)a; (void)sc; (void)multichannel;
 #endif
 }
 
@@ -73,7 +73,8 @@ WAP_DEV void delay_stream_tick(const TickArgs& a, int idx, float* scratch) {
   const int slot = a.slots ? a.slots[idx] : idx;
   StreamState& st = a.states[slot];
   AecScratch& sc = *reinterpret_cast<AecScratch*>(scratch);
-  stage_ec3_params(a, sc);
+  // multi-channel legs run the multichannel EchoCanceller3Config once stereo content has been detected
+  stage_ec3_params(a, sc, a.mc != nullptr && a.mc[slot].det.persistent != 0);
   aec3_delay_frame(st.aec, st.tick, sc);
 }
 

@@ -370,6 +370,9 @@ struct EngineConfig {
   int channels;         // API channels of render, capture and output (1 or 2)
   int levels_enabled;   // pre_amplifier.enabled || capture_level_adjustment.enabled
   int post_gain_enabled;  // capture_level_adjustment.enabled: kCapturePostGain is honoured
+  // Stereo frames with pipeline.multi_channel_render and _capture on and AEC3: every channel is processed
+  // (EchoCanceller3 with 2 capture and 1 or 2 render channels, wap_mc_state.h) -- BASELINE config 4.
+  int mc;
 };
 
 // Every member of EngineConfig is a 4-byte scalar, so the struct has no padding bytes and two

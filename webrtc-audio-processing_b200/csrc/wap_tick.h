@@ -2,6 +2,7 @@
 #pragma once
 #include "dsp_resampler.cuh"
 #include "wap_ec3_params.h"
+#include "wap_mc_state.h"
 #include "wap_state.h"
 
 namespace wap {
@@ -37,6 +38,14 @@ struct TickArgs {
   // Stereo engines only: second capture channel (high-pass state, input resampler, resampled frame).
   ExtraChannelState* extra;  // [slot]
   float* rs_capture1;        // [n][proc frame] or nullptr
+  // Multi-channel engines only (stereo frames with pipeline.multi_channel_render / _capture, BASELINE config 4):
+  // the per-leg multi-channel arena, the freshly constructed state EchoCanceller3::Initialize copies in, the
+  // multichannel EchoCanceller3Config (`ep` is the mono one) and the parameters outside Ec3Params ([0]: of the
+  // mono config, [1]: of the multichannel config; the detector reads [0]).
+  McState* mc;               // [slot] or nullptr
+  const McTemplates* mc_templates;
+  Ec3Params ep_mc;
+  McParams mcp[2];
 };
 
 }  // namespace wap
