@@ -1,0 +1,188 @@
+"""Multi-channel AEC3 (BASELINE config 4): stereo frames with
+pipeline.multi_channel_render and _capture on.  The reference then runs EchoCanceller3 with two capture
+channels and one (downmixed) or two render channels, switching when MultiChannelContentDetector sees
+persistent stereo content; the engine must follow it bit for bit: int16 output identical, float output
+identical in every bit.  Runs on the CPU warp emulator and (marked gpu) on the product library."""
+import numpy as np
+import pytest
+
+from common import stereo_leg
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def api_lib(request):
+    return request.getfixturevalue("emu_lib" if request.param == "emu" else "gpu_lib")
+
+
+MC = dict(aec=True, ns=False, mc_render=True, mc_capture=True, max_rate=48000)
+
+
+def render_variant(far, kind, rate):
+    """far: interleaved stereo render.  'stereo': as is (persistent stereo content after 2 s); 'mono': both
+    channels identical (the AEC keeps one downmixed render channel); 'burst': 0.5 s of stereo content, then
+    identical channels (temporary stereo: average downmix + echo_path_gain_change, never persistent)."""
+    far = far.copy()
+    if kind == "mono":
+        far[1::2] = far[0::2]
+    elif kind == "burst":
+        n = rate // 100 * 2 * 50
+        far[n + 1::2] = far[n::2]
+    return far
+
+
+def run_pair(lib, oracle, rate, n_frames, kind, seed=9, right_gain=0.6, delay_ms=0, engine_kw=None, ref_kv=None):
+    import wap_b200
+    far, near = stereo_leg(rate, n_frames, seed, right_gain)
+    far = render_variant(far, kind, rate)
+    fl = rate // 100 * 2
+    eng = wap_b200.Engine(1, rate, channels=2, lib=lib, **MC, **(engine_kw or {}))
+    if ref_kv is None:
+        refapm = oracle.RefApm(**MC)
+    else:
+        kv = dict(aec=1, ns=0, mc_render=1, mc_capture=1, max_rate=48000)
+        kv.update(ref_kv)
+        refapm = oracle.RefApm(kv=kv)
+    ref_out, _, err = refapm.run_i16(rate, far, near, render_ch=2, capture_ch=2)
+    assert err == 0
+    out = np.zeros_like(near)
+    for f in range(n_frames):
+        eng.set_stream_delay_ms(delay_ms)
+        out[f * fl:(f + 1) * fl] = eng.process(far[f * fl:(f + 1) * fl].reshape(1, fl),
+                                               near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
+    eng.close()
+    return out, ref_out
+
+
+def first_bad_frame(out, ref_out, fl):
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).reshape(-1, fl).max(1)
+    bad = np.nonzero(d)[0]
+    return (int(bad[0]), int(d.max())) if bad.size else None
+
+
+@pytest.mark.parametrize("rate,n_frames,kind", [
+    (16000, 420, "stereo"),   # crosses the detector's 2 s hysteresis: Initialize() with 2 render channels + multichannel config
+    (16000, 150, "mono"),
+    (16000, 150, "burst"),
+    (48000, 300, "stereo"),
+    (48000, 100, "mono"),
+    (48000, 100, "burst"),
+])
+def test_multichannel_matches_reference(api_lib, oracle, rate, n_frames, kind):
+    out, ref_out = run_pair(api_lib, oracle, rate, n_frames, kind)
+    assert first_bad_frame(out, ref_out, rate // 100 * 2) is None
+    # the second channel is really processed on its own (not a copy of the first)
+    assert np.any(out[0::2] != out[1::2])
+
+
+def test_multichannel_saturated_capture_channel(api_lib, oracle):
+    # the right capture channel clips: AnalyzeCapture's saturation flag covers every channel
+    out, ref_out = run_pair(api_lib, oracle, 16000, 260, "stereo", right_gain=2.6)
+    assert first_bad_frame(out, ref_out, 320) is None
+
+
+def test_multichannel_float_interface_and_statistics(api_lib, oracle):
+    import wap_b200
+    rate, n_frames = 16000, 330
+    far, near = stereo_leg(rate, n_frames, 11, 0.6)
+    fl = rate // 100
+    eng = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **MC)
+    refapm = oracle.RefApm(**MC)
+    differing = 0
+    for f in range(n_frames):
+        # planar float frames [channel][sample]
+        r = (far[f * 2 * fl:(f + 1) * 2 * fl].reshape(fl, 2).T.astype(np.float32) / 32768.0).copy()
+        c = (near[f * 2 * fl:(f + 1) * 2 * fl].reshape(fl, 2).T.astype(np.float32) / 32768.0).copy()
+        eng.set_stream_delay_ms(0)
+        o = eng.process(r.reshape(1, -1), c.reshape(1, -1)).reshape(-1)
+        ro, err = refapm.tick_f32(rate, r.reshape(-1), c.reshape(-1), render_ch=2, capture_ch=2)
+        assert err == 0
+        differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
+        if f % 110 == 109:
+            ours, theirs = eng.stats(0), refapm.stats()
+            # (has_erl, erl, has_erle, erle, has_delay, delay_ms)
+            assert ours.has_echo_return_loss and theirs[0] and ours.has_echo_return_loss_enhancement and theirs[2]
+            assert ours.echo_return_loss == pytest.approx(float(theirs[1]), abs=1e-4)
+            assert ours.echo_return_loss_enhancement == pytest.approx(float(theirs[3]), abs=1e-4)
+            assert ours.delay_ms == int(theirs[5])
+    eng.close()
+    assert differing == 0
+
+
+def test_multichannel_batch_legs_switch_independently(api_lib, oracle):
+    """Three legs in one batch: stereo content, identical channels, a stereo burst.  Each leg's content
+    detector re-initialises its own state; the others must not notice."""
+    import wap_b200
+    rate, n_frames, fl = 16000, 260, 320
+    kinds = ["stereo", "mono", "burst"]
+    legs = []
+    for i, kind in enumerate(kinds):
+        far, near = stereo_leg(rate, n_frames, 20 + i, 0.6)
+        legs.append((render_variant(far, kind, rate), near))
+    eng = wap_b200.Engine(len(kinds), rate, channels=2, lib=api_lib, **MC)
+    outs = [np.zeros(n_frames * fl, np.int16) for _ in kinds]
+    for f in range(n_frames):
+        eng.set_stream_delay_ms(0)
+        r = np.stack([l[0][f * fl:(f + 1) * fl] for l in legs])
+        c = np.stack([l[1][f * fl:(f + 1) * fl] for l in legs])
+        o = eng.process(r, c)
+        for i in range(len(kinds)):
+            outs[i][f * fl:(f + 1) * fl] = o[i]
+    eng.close()
+    for i, kind in enumerate(kinds):
+        ref_out, _, err = oracle.RefApm(**MC).run_i16(rate, legs[i][0], legs[i][1], render_ch=2, capture_ch=2)
+        assert err == 0
+        assert first_bad_frame(outs[i], ref_out, fl) is None, kind
+
+
+def test_multichannel_custom_configs(api_lib, oracle):
+    """A mono config and a multichannel config of the user's own (SetEchoCancellerConfig(config,
+    multichannel_config)): shorter detector hysteresis so that the switch happens early, a fixed-downmix
+    capture mixer, other filter lengths for the multichannel AEC."""
+    mono = {"multi_channel.stereo_detection_hysteresis_seconds": 0.5, "filter.refined.length_blocks": 11,
+            "filter.refined_initial.length_blocks": 10}
+    mc = {"filter.refined.length_blocks": 12, "filter.coarse.length_blocks": 9, "filter.coarse_initial.length_blocks": 8,
+          "delay.capture_alignment_mixing.downmix": True, "delay.capture_alignment_mixing.adaptive_selection": False,
+          "suppressor.normal_tuning.max_inc_factor": 1.7}
+    ref_kv = {"ec3." + k: v for k, v in mono.items()}
+    ref_kv.update({"ec3mc." + k: v for k, v in mc.items()})
+    out, ref_out = run_pair(api_lib, oracle, 16000, 200, "stereo", engine_kw=dict(aec3=mono, aec3_multichannel=mc), ref_kv=ref_kv)
+    assert first_bad_frame(out, ref_out, 320) is None
+
+
+def test_multichannel_without_stereo_detection(api_lib, oracle):
+    # detect_stereo_content off: two render channels and the multichannel config from the first frame
+    mono = {"multi_channel.detect_stereo_content": False}
+    ref_kv = {"ec3.multi_channel.detect_stereo_content": 0, "ec3mc.multi_channel.detect_stereo_content": 0}
+    out, ref_out = run_pair(api_lib, oracle, 16000, 120, "mono", engine_kw=dict(aec3=mono, aec3_multichannel=mono), ref_kv=ref_kv)
+    assert first_bad_frame(out, ref_out, 320) is None
+
+
+def test_multichannel_state_moves_between_engines(api_lib, oracle):
+    """Export a multi-channel leg after the switch to two render channels and continue it on another engine."""
+    import wap_b200
+    rate, n_frames, fl, cut = 16000, 300, 320, 240
+    far, near = stereo_leg(rate, n_frames, 31, 0.6)
+    ref_out, _, err = oracle.RefApm(**MC).run_i16(rate, far, near, render_ch=2, capture_ch=2)
+    assert err == 0
+    a = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **MC)
+    b = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **MC)
+    out = np.zeros_like(near)
+    eng = a
+    for f in range(n_frames):
+        if f == cut:
+            b.import_state(a.export_state(0), 0)
+            eng = b
+        eng.set_stream_delay_ms(0)
+        out[f * fl:(f + 1) * fl] = eng.process(far[f * fl:(f + 1) * fl].reshape(1, fl), near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
+    a.close()
+    b.close()
+    assert first_bad_frame(out, ref_out, fl) is None
+
+
+def test_multichannel_unsupported_combinations_are_refused(api_lib):
+    import wap_b200
+    for kw in (dict(MC, ns=True), dict(MC, agc2=True), dict(MC, mc_capture=False), dict(MC, mc_render=False),
+               dict(MC, max_rate=32000)):
+        rate = 48000 if kw.get("max_rate") == 32000 else 16000
+        with pytest.raises(RuntimeError):
+            wap_b200.Engine(1, rate, channels=2, lib=api_lib, **kw)

@@ -301,20 +301,29 @@ class WapStageTaps(C.Structure):
 class Engine:
     """Batched engine: `n` call legs of one config class on one GPU."""
 
-    def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, aec3=None, **cfg):
+    def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, aec3=None,
+                 aec3_multichannel=None, **cfg):
         """aec3: None (default EchoCanceller3Config), a dict of overrides keyed by the reference's member
-        paths ("filter.refined.length_blocks": 10, ...) or a WapEchoCanceller3Config."""
+        paths ("filter.refined.length_blocks": 10, ...) or a WapEchoCanceller3Config.  aec3_multichannel: the
+        same for the multichannel config (overrides apply to CreateDefaultMultichannelConfig)."""
         self.lib = lib or load()
         self.rate, self.channels, self.n = rate, channels, n_streams
         self.frame = rate // 100 * channels
         self.config = make_config(self.lib, **cfg)
-        if aec3 is None:
+        if aec3 is None and aec3_multichannel is None:
             self.h = self.lib.wap_engine_create(device, capacity or n_streams, self.config,
                                                 WapStreamConfig(rate, channels))
         else:
-            self.aec3 = aec3 if isinstance(aec3, WapEchoCanceller3Config) else make_aec3_config(self.lib, aec3)
-            self.h = self.lib.wap_engine_create_with_aec3_config(device, capacity or n_streams, self.config,
-                                                                 WapStreamConfig(rate, channels), C.byref(self.aec3), None)
+            def conv(c, mc):
+                if c is None:
+                    return None
+                return c if isinstance(c, WapEchoCanceller3Config) else make_aec3_config(self.lib, c, multichannel=mc)
+            self.aec3, self.aec3_mc = conv(aec3, False), conv(aec3_multichannel, True)
+            if self.aec3 is None:   # BuiltinAudioProcessingBuilder::SetEchoCancellerConfig needs the mono config
+                self.aec3 = make_aec3_config(self.lib, {})
+            self.h = self.lib.wap_engine_create_with_aec3_config(
+                device, capacity or n_streams, self.config, WapStreamConfig(rate, channels), C.byref(self.aec3),
+                C.byref(self.aec3_mc) if self.aec3_mc is not None else None)
         if not self.h:
             raise RuntimeError("wap_engine_create failed (no CUDA device or unsupported config)")
         self.handles = (C.c_void_p * n_streams)()
