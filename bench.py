@@ -46,6 +46,7 @@ for p in (os.path.join(ROOT, "webrtc-audio-processing_b200", "python"), os.path.
 
 CYCLE = 200        # frames per leg before the input repeats: 2 s = one double-talk period, two render gates
 SETTLE_MIN = 300   # ticks every leg is advanced before anything is timed
+MC_SETTLE = 520    # the same for multichannel legs: 201 frames until the stereo detector switches + 3 s
 
 
 def parse():
@@ -67,12 +68,15 @@ def parse():
                     help="pipeline.maximum_internal_processing_rate (32000 = the reference default: 48 kHz legs are resampled)")
     ap.add_argument("--rate", type=int, default=16000, choices=[16000, 32000, 48000],
                     help="native sample rate of the legs (BASELINE config 3: --rate 48000 --aec 0 --ns-level 2)")
+    ap.add_argument("--mc", type=int, default=0,
+                    help="1: stereo legs with pipeline.multi_channel_render/_capture (multichannel AEC3, BASELINE config 4: "
+                         "--mc 1 --rate 48000 --ns 0)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE config 3 / 5 side lines")
     ap.add_argument("--check-legs", type=int, default=16, help="legs of the parity spot check (0: off)")
     a = ap.parse_args()
-    a.settle = max(a.settle, SETTLE_MIN)
+    a.settle = max(a.settle, MC_SETTLE if a.mc else SETTLE_MIN)
     return a
 
 
@@ -86,6 +90,9 @@ def workload_name(a):
         parts.append("AGC2(fixed %g dB + limiter)" % a.agc2_gain_db)
     if getattr(a, "max_rate", 48000) == 32000 and a.rate == 48000:
         parts.append("processed at 32 kHz (default maximum_internal_processing_rate)")
+    if getattr(a, "mc", 0):
+        return "%d synthetic stereo %d kHz call legs per GPU (multi_channel_render + _capture: 2 render / 2 capture channels), " \
+               "%s, 10 ms frames" % (a.streams, a.rate // 1000, "+".join(parts).replace("default EchoCanceller3Config", "default mono + multichannel EchoCanceller3Config"))
     return "%d synthetic mono %d kHz call legs per GPU, %s, 10 ms frames" % (a.streams, a.rate // 1000, "+".join(parts))
 
 
@@ -98,11 +105,19 @@ def peaks():
 
 
 def synth_kind(a):
+    if getattr(a, "mc", 0):
+        return 2
     return 0 if a.aec else 1
+
+
+def channels(a):
+    return 2 if getattr(a, "mc", 0) else 1
 
 
 def ref_kwargs(a):
     kw = dict(aec=bool(a.aec), ns=bool(a.ns), ns_level=a.ns_level, max_rate=a.max_rate)
+    if getattr(a, "mc", 0):
+        kw.update(mc_render=True, mc_capture=True)
     if a.agc2_gain_db is not None:
         kw.update(agc2=True, agc2_fixed_gain_db=a.agc2_gain_db)
     return kw
@@ -116,18 +131,25 @@ def cpu_reference(a, seconds):
     import ref
     import synth
     cores = os.cpu_count() or 1
-    fl = a.rate // 100
-    warm, timed = SETTLE_MIN, 300
+    fl = a.rate // 100 * channels(a)
+    # multichannel legs: persistent stereo content is detected after 201 frames (Initialize() with two render
+    # channels); warm up well past it
+    warm, timed = (MC_SETTLE if getattr(a, "mc", 0) else SETTLE_MIN), 300
     per_leg_frames = warm + timed
-    # ~65-150 us per leg-frame per core: size the sample to `seconds`.
-    legs_per_thread = max(1, int(seconds / (per_leg_frames * 160e-6)))
+    # ~65-150 us per leg-frame per core (~400 us for the multichannel 48 kHz shape): size the
+    # sample to `seconds`.
+    legs_per_thread = max(1, int(seconds / (per_leg_frames * (400e-6 if getattr(a, "mc", 0) else 160e-6))))
     legs = cores * legs_per_thread
     r, c = synth.cycle(synth_kind(a), a.rate, 0, legs, CYCLE)          # [CYCLE][legs][fl]
     idx = np.arange(per_leg_frames) % CYCLE
     r = np.ascontiguousarray(r[idx].transpose(1, 0, 2)).reshape(legs, -1)   # [leg][frame*fl]
     c = np.ascontiguousarray(c[idx].transpose(1, 0, 2)).reshape(legs, -1)
-    secs = ref.cpu_bench(a.aec, a.ns, a.ns_level, a.rate, legs, cores, warm, per_leg_frames, r, c,
-                         stride=r.shape[1])
+    if getattr(a, "mc", 0):
+        kv = dict(aec=int(a.aec), ns=int(a.ns), ns_level=a.ns_level, max_rate=a.max_rate, mc_render=1, mc_capture=1)
+        secs = ref.cpu_bench_kv(kv, a.rate, 2, legs, cores, warm, per_leg_frames, r, c, stride=r.shape[1])
+    else:
+        secs = ref.cpu_bench(a.aec, a.ns, a.ns_level, a.rate, legs, cores, warm, per_leg_frames, r, c,
+                             stride=r.shape[1])
     frames = legs * timed
     streams_rt = frames / secs / 100.0
     return {"value": streams_rt, "unit": "real-time streams", "cores": cores, "kind": "reference",
@@ -204,7 +226,7 @@ def make_inputs(torch, dev, a, first_leg, cycle):
     """Pinned host copies [cycle][S][fl] int16 of this rank's legs (the e2e arm feeds them through the
     host-buffer ABI) and their device copies (the device-resident arm)."""
     import synth
-    S, fl = a.streams, a.rate // 100
+    S, fl = a.streams, a.rate // 100 * channels(a)
     h_r = torch.empty((cycle, S, fl), dtype=torch.int16).pin_memory()
     h_c = torch.empty((cycle, S, fl), dtype=torch.int16).pin_memory()
     synth.cycle(synth_kind(a), a.rate, first_leg, S, cycle, h_r.numpy(), h_c.numpy())
@@ -221,7 +243,7 @@ def spot_check(a, L, eng, tick_host, h_o, t_now, h_r, h_c, first_leg, n_legs, n_
         ref.lib()
     except Exception as e:
         return {"legs": 0, "unavailable": "oracle/_ref not loadable: %s" % e}, t_now
-    S, fl = a.streams, a.rate // 100
+    S, fl = a.streams, a.rate // 100 * channels(a)
     rng = np.random.default_rng(seed)
     legs = sorted(int(x) for x in rng.choice(S, size=min(n_legs, S), replace=False))
     got = np.zeros((len(legs), n_ticks, fl), np.int16)
@@ -237,7 +259,7 @@ def spot_check(a, L, eng, tick_host, h_o, t_now, h_r, h_c, first_leg, n_legs, n_
     for j, leg in enumerate(legs):
         cap = np.ascontiguousarray(c_np[idx, leg]).reshape(-1)
         ren = np.ascontiguousarray(r_np[idx, leg]).reshape(-1) if a.aec else None
-        o, _, err = ref.RefApm(**ref_kwargs(a)).run_i16(a.rate, ren, cap)
+        o, _, err = ref.RefApm(**ref_kwargs(a)).run_i16(a.rate, ren, cap, render_ch=channels(a), capture_ch=channels(a))
         assert err == 0
         d = np.abs(o.reshape(t, fl)[t_now:].astype(np.int32) - got[j].astype(np.int32))
         worst = max(worst, int(d.max()))
@@ -251,11 +273,13 @@ def spot_check(a, L, eng, tick_host, h_o, t_now, h_r, h_c, first_leg, n_legs, n_
 def measure(a, torch, dist, L, wap_b200, dev, local, rank, world, headline):
     """Everything measured for one config class; returns the fields of its (sub-)line."""
     import numpy as np
-    S, fl = a.streams, a.rate // 100
+    S, fl = a.streams, a.rate // 100 * channels(a)
     cycle = CYCLE if a.aec else 100
     extra = {} if a.agc2_gain_db is None else dict(agc2=True, agc2_fixed_gain_db=a.agc2_gain_db)
-    eng = wap_b200.Engine(S, a.rate, lib=L, device=local, aec=bool(a.aec), ns=bool(a.ns), ns_level=a.ns_level,
-                          max_rate=a.max_rate, **extra)
+    if getattr(a, "mc", 0):
+        extra.update(mc_render=True, mc_capture=True)
+    eng = wap_b200.Engine(S, a.rate, channels=channels(a), lib=L, device=local, aec=bool(a.aec), ns=bool(a.ns),
+                          ns_level=a.ns_level, max_rate=a.max_rate, **extra)
     first_leg = rank * S
     h_r, h_c, render, capture = make_inputs(torch, dev, a, first_leg, cycle)
     out = torch.empty((S, fl), dtype=torch.int16, device=dev)
@@ -323,7 +347,8 @@ def measure(a, torch, dist, L, wap_b200, dev, local, rank, world, headline):
     L.wap_engine_algorithmic_bytes_per_kernel(eng.h, kbytes)
     L.wap_engine_enable_kernel_timing(eng.h, False)
     kernels = []
-    for name, m, bts in zip(("k_front", "k_delay", "k_echo"), kms, kbytes):
+    knames = ("k_mc_front", "k_delay", "k_mc_echo(+k_mc_post)") if getattr(a, "mc", 0) else ("k_front", "k_delay", "k_echo")
+    for name, m, bts in zip(knames, kms, kbytes):
         per = m / max(1, n_timed)
         kernels.append({"name": name, "ms_per_launch": per, "algorithmic_bytes_per_leg_frame": bts,
                         "achieved_gbs": (bts * S / (per * 1e-3) / 1e9) if per > 0 else 0.0})
@@ -423,6 +448,8 @@ def run_b200(a):
         # BASELINE config 3: NS-only, level high, 48 kHz three-band; config 5: the full chain with AGC2.
         for name, upd in (("BASELINE config 3: NS-only (kHigh) 48 kHz three-band",
                            dict(rate=48000, aec=0, ns=1, ns_level=2, streams=min(a.streams, 16384), settle=SETTLE_MIN)),
+                          ("BASELINE config 4: stereo 48 kHz multichannel AEC3 (2 render / 2 capture channels)",
+                           dict(rate=48000, aec=1, ns=0, mc=1, streams=min(a.streams, 8192), settle=MC_SETTLE)),
                           ("BASELINE config 5: full chain AEC3+NS+AGC2",
                            dict(agc2_gain_db=6.0))):
             b = copy.copy(a)

@@ -32,6 +32,8 @@ def lib():
         L.ref_apm_set_capture_output_used.argtypes = [C.c_void_p, C.c_int]
         L.ref_apm_bench.restype = C.c_double
         L.ref_apm_bench.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_apm_bench_kv.restype = C.c_double
+        L.ref_apm_bench_kv.argtypes = [C.c_char_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_size_t]
         L.ref_apm_create_kv.restype = C.c_void_p
         L.ref_apm_create_kv.argtypes = [C.c_char_p]
         L.ref_apm_apply_kv.argtypes = [C.c_void_p, C.c_char_p]
@@ -160,6 +162,15 @@ def rdft256(a, isgn=1):
     a = np.array(a, dtype=np.float32).copy()
     lib().ref_rdft256(_p(a), int(isgn))
     return a
+
+
+def cpu_bench_kv(kv, rate, channels, streams, threads, warm, nframes, render, capture, stride=0):
+    """ref_apm_bench for any configuration ref_apm_create_kv understands; frames interleaved per channel."""
+    render = np.ascontiguousarray(render, dtype=np.int16)
+    capture = np.ascontiguousarray(capture, dtype=np.int16)
+    secs = lib().ref_apm_bench_kv(kv_string(kv), rate, channels, streams, threads, warm, nframes, _p(render), _p(capture), stride)
+    assert secs > 0, "ref_apm_bench_kv: bad configuration"
+    return secs
 
 
 def cpu_bench(aec, ns, ns_level, rate, streams, threads, warm, nframes, render, capture, stride=0):

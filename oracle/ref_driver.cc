@@ -413,6 +413,53 @@ double ref_apm_bench(int aec, int ns, int ns_level, int rate, int streams,
   return mx;
 }
 
+// `kv`: configuration text as for ref_apm_create_kv (e.g. "aec=1;ns=0;mc_render=1;mc_capture=1"); `ch`: channels
+// of the interleaved render / capture frames.
+double ref_apm_bench_kv(const char* kv, int rate, int ch, int streams,
+                        int threads, int warm, int nframes, const int16_t* render,
+                        const int16_t* capture, size_t stride) {
+  const int n = rate / 100 * ch;
+  std::vector<void*> h(streams);
+  for (auto& x : h) {
+    x = ref_apm_create_kv(kv);
+    if (!x) return -1.0;
+  }
+  std::atomic<int> ready{0};
+  std::atomic<bool> go{false};
+  std::vector<double> secs(threads, 0.0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    th.emplace_back([&, t] {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      CPU_SET(t % std::thread::hardware_concurrency(), &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+      std::vector<int16_t> out(n), ro(n);
+      for (int s = t; s < streams; s += threads)
+        for (int f = 0; f < warm; ++f)
+          ref_apm_tick_i16(h[s], rate, ch, ch, render + s * stride + (size_t)f * n,
+                           capture + s * stride + (size_t)f * n, out.data(), ro.data());
+      ready++;
+      while (!go.load()) std::this_thread::yield();
+      auto t0 = std::chrono::steady_clock::now();
+      for (int s = t; s < streams; s += threads)
+        for (int f = warm; f < nframes; ++f)
+          ref_apm_tick_i16(h[s], rate, ch, ch, render + s * stride + (size_t)f * n,
+                           capture + s * stride + (size_t)f * n, out.data(), ro.data());
+      secs[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+  }
+  while (ready.load() < threads) std::this_thread::yield();
+  go = true;
+  double mx = 0;
+  for (int t = 0; t < threads; ++t) {
+    th[t].join();
+    if (secs[t] > mx) mx = secs[t];
+  }
+  for (auto x : h) ref_apm_destroy(x);
+  return mx;
+}
+
 // ------------------------------------------------------------ stage level
 // Ooura 128-point real FFT as AEC3 uses it (reference
 // common_audio/third_party/ooura/fft_size_128/ooura_fft.cc:334-349); the

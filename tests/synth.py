@@ -50,7 +50,7 @@ def cycle(kind, rate, first_leg, legs, frames, render=None, capture=None, force_
     """int16 render / capture [frames][legs][rate // 100] of legs first_leg .. first_leg + legs - 1:
     one seamless cycle (see tools/wap_synth.c).  Pre-allocated (e.g. pinned) output arrays may be
     passed in."""
-    fl = rate // 100
+    fl = rate // 100 * (2 if kind == 2 else 1)   # kind 2: interleaved stereo frames
     if render is None:
         render = np.zeros((frames, legs, fl), np.int16)
     if capture is None:
@@ -113,6 +113,36 @@ def cycle_numpy(kind, rate, first_leg, legs, frames):
                 y[:, t] += floor_
                 if (t % (2 * rate)) >= (rate // 10) * 17:
                     y[:, t] += burst
+        elif kind == 2:
+            rr2 = _VecRandom(1000 + 2 * i + 7919)
+            rn2 = _VecRandom(1001 + 2 * i + 7919)
+            xr = np.zeros((legs, n), np.float32)
+            for t in range(n):
+                v, w = rr.sample(8000.0), rr2.sample(8000.0)
+                on = (t % rate) < (rate // 10) * 9
+                x[:, t] = v if on else 0.0
+                xr[:, t] = w if on else 0.0
+            D = (rate // 16000) * (64 * (1 + (i % 48)) + (7 * i) % 64)
+            rows = np.arange(legs)[:, None]
+            xd, xrd = x.astype(np.float64), xr.astype(np.float64)
+            at = lambda a, d: a[rows, (k[None, :] - d[:, None]) % n]
+            ys = []
+            for c in range(2):
+                Dc = D + 3 * c
+                ys.append(0.5 * at(xd, Dc) + 0.25 * at(xd, Dc + 37) + 0.1 * at(xd, Dc + 160) +
+                          0.35 * at(xrd, Dc + 11) + 0.15 * at(xrd, Dc + 53))
+            for t in range(n):
+                floor0 = rn.sample(50.0)
+                burst = rn.sample(3000.0)
+                floor1 = rn2.sample(50.0)
+                ys[0][:, t] += floor0
+                ys[1][:, t] += floor1
+                if (t % (2 * rate)) >= (rate // 10) * 17:
+                    ys[0][:, t] += burst
+                    ys[1][:, t] += burst
+            q = lambda a: np.clip(np.rint(a), -32768, 32767).astype(np.int16)
+            il = lambda a, b: np.stack([a, b], 2).reshape(legs, frames, fl * 2).transpose(1, 0, 2).copy()
+            return il(q(x), q(xr)), il(q(ys[0]), q(ys[1]))
         else:
             for t in range(n):
                 y[:, t] = rn.sample(300.0)

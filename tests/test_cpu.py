@@ -448,7 +448,7 @@ def test_synthetic_generator_c_equals_numpy_restatement():
     import synth
     if synth._load() is None:
         pytest.skip("no C compiler / prebuilt generator")
-    for kind, rate in ((0, 16000), (0, 48000), (1, 48000)):
+    for kind, rate in ((0, 16000), (0, 48000), (1, 48000), (2, 16000), (2, 48000)):
         a = synth.cycle(kind, rate, 37, 5, 110)
         b = synth.cycle(kind, rate, 37, 5, 110, force_numpy=True)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

@@ -15,7 +15,13 @@
 //     0.3 s of every 2 s).
 //   kind 1 (BASELINE config 3, near end only): noise amplitude 300 + 1 kHz and 2.3 kHz tones of
 //     amplitude 4000 gated 0.5 s on / 0.5 s off; render = 0.
-// Output layout: [frame][leg][samples per frame] int16 (what wap_process_streams takes per tick).
+//   kind 2 (BASELINE config 4, stereo render and capture): render L / R = independent white noise
+//     (seeds seed_r, seed_r + 7919), amplitude 8000, gated like kind 0; capture channel c =
+//     0.5 L[n-Dc] + 0.25 L[n-Dc-37] + 0.1 L[n-Dc-160] + 0.35 R[n-Dc-11] + 0.15 R[n-Dc-53], D0 = D,
+//     D1 = D + 3, + an independent noise floor per channel (seeds seed_n, seed_n + 7919, amplitude 50)
+//     + the same double-talk bursts on both channels.  Frames are interleaved stereo.
+// Output layout: [frame][leg][samples per frame (x 2 interleaved channels for kind 2)] int16 (what
+// wap_process_streams takes per tick).
 //
 // build: gcc -O2 -shared -fPIC -fopenmp tools/wap_synth.c -o tools/_build/libwap_synth.so -lm
 #include <math.h>
@@ -75,6 +81,34 @@ int wap_synth_cycle(int kind, int rate, int first_leg, int legs, int frames, int
           render[o] = q16(x[k]);
           capture[o] = q16(y);
         }
+      } else if (kind == 2) {
+        float* xr = (float*)malloc(sizeof(float) * (size_t)n);
+        if (!xr) { ok = 0; continue; }
+        Rng rr2 = {(uint64_t)(1000 + 2 * (int64_t)i + 7919)}, rn2 = {(uint64_t)(1001 + 2 * (int64_t)i + 7919)};
+        for (int k = 0; k < n; ++k) {
+          const float v = sample(&rr, 8000.f), w = sample(&rr2, 8000.f);
+          const int on = (k % rate) < (rate / 10) * 9;
+          x[k] = on ? v : 0.f;
+          xr[k] = on ? w : 0.f;
+        }
+        const int D = (rate / 16000) * (64 * (1 + (i % 48)) + (7 * i) % 64);
+#define WAP_AT(a, d) (a)[(((k - (d)) % n) + n) % n]
+        for (int k = 0; k < n; ++k) {
+          const float floor0 = sample(&rn, 50.f), burst = sample(&rn, 3000.f), floor1 = sample(&rn2, 50.f);
+          const size_t o = (((size_t)(k / fl) * legs + l) * fl + (k % fl)) * 2;
+          for (int c = 0; c < 2; ++c) {
+            const int Dc = D + 3 * c;
+            double y = 0.5 * WAP_AT(x, Dc) + 0.25 * WAP_AT(x, Dc + 37) + 0.1 * WAP_AT(x, Dc + 160) +
+                       0.35 * WAP_AT(xr, Dc + 11) + 0.15 * WAP_AT(xr, Dc + 53);
+            y += c ? floor1 : floor0;
+            if ((k % (2 * rate)) >= (rate / 10) * 17) y += burst;
+            capture[o + c] = q16(y);
+          }
+          render[o] = q16(x[k]);
+          render[o + 1] = q16(xr[k]);
+        }
+#undef WAP_AT
+        free(xr);
       } else {
         for (int k = 0; k < n; ++k) {
           double y = sample(&rn, 300.f);

@@ -1059,7 +1059,9 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
   return WapError::None;
 }
 
-size_t wap_engine_state_bytes_per_stream(const WapEngine*) { return sizeof(StreamState); }
+size_t wap_engine_state_bytes_per_stream(const WapEngine* e) {
+  return sizeof(StreamState) + ((e && e->d_mc) ? sizeof(wap::McState) : 0);
+}
 
 WapError wap_engine_synchronize(WapEngine* e) {
   if (!e) return WapError::NullPointer;
@@ -1499,6 +1501,7 @@ int64_t wap_engine_read_kernel_timing(const WapEngine* e, double* out_ms) {
   for (int k = 0; k < 3; ++k) out_ms[k] = e->kernel_ms[k];
   return e->timed_ticks;
 }
+static const double kBlockBytesHi = 2 * 64;  // floats of bands 1-2 per block
 // Algorithmic HBM bytes per leg-frame attributed to each tick kernel (SURVEY.md 8(d) groups):
 // k_front: audio in + HPF state; k_delay: the "delay estimation" group; k_echo: the rest.
 void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* e, double* out_bytes) {
@@ -1511,12 +1514,29 @@ void wap_engine_algorithmic_bytes_per_kernel(const WapEngine* e, double* out_byt
   out_bytes[2] = total - front - delay;
 }
 
-static const double kBlockBytesHi = 2 * 64;  // floats of bands 1-2 per block
 double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
   if (!e) return 0.0;
   // SURVEY.md section 8(d) byte model.
   const int B = e->cfg.num_bands;
   double bytes = 0.0;
+  if (e->cfg.mc) {
+    // Multi-channel legs after stereo detection (R = 2 render, C = 2 capture channels, multichannel config:
+    // refined 13 / coarse 11 partitions), per 64-sample block:
+    //   delay estimation (on the mixed channels)                          40256   (as mono)
+    //   adaptive filters  C x (13 + 11) x R x 65 bins x re,im x 4 B x r/w  99840
+    //   render FFT partitions  13 x R x 65 x re,im x 4 B x {filter, adapt}  27040   (shared by the capture channels)
+    //   render spectra  13 x R x 65 x 4 B                                    6760
+    //   H2  C x 13 x 65 x 4 B x r/w                                          13520
+    //   estimators, comfort noise, suppressor state  C x 16504               33008   (mono: 16504)
+    bytes += 2.5 * (40256.0 + 99840.0 + 27040.0 + 6760.0 + 13520.0 + 33008.0);
+    bytes += 2 * 96.0;                                   // high-pass filter state, both channels
+    if (B == 3) {
+      bytes += (2 * 2 + 2) * 150 * 4.0;                  // capture analysis + synthesis and render analysis state, x2 channels
+      bytes += 2 * (2.5 * (4.0 * kBlockBytesHi * 5) + 128.0);  // upper-band ring / delay / framers, PostFilter state
+    }
+    bytes += e->frame_len * 4.0 * 3;                     // render + capture in, output
+    return bytes;
+  }
   if (e->cfg.aec_enabled) bytes += 2.5 * 107460.0;
   if (e->cfg.ns_enabled) bytes += 2223.0 * 8.0 + 24.0;
   if (e->cfg.hpf_enabled) bytes += 96.0;
