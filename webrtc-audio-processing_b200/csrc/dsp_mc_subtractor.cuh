@@ -140,26 +140,46 @@ WAP_DEV void mc_render_signal_analyzer_update(Aec3State& sh, const McRender& rb,
 
 // RenderBuffer::SpectralSum(s): X2 summed over partitions (outer) and render channels (inner), with the
 // running sum captured after P_r and after P_c partitions -> r.X2_ref / r.X2_coa.
-WAP_DEV void mc_spectral_sums(const McRender& rb, AecScratch& sc, int P_r, int P_c, int R) {
+template <int R>
+WAP_DEV void mc_spectral_sums_r(const McRender& rb, AecScratch& sc, int P_r, int P_c) {
   AecRemoverScratch& r = sc.rm;
   const int pos = sc.s.spectra_read;
   const int pmax = imax(P_r, P_c);
   __syncwarp();
   for (int k = lane_id(); k < kBins; k += 32) {
     float x2 = 0.f;
-    for (int j = 0; j < pmax; ++j) {
-      const int row = ring_row(pos, j);
-      for (int rc = 0; rc < R; ++rc) x2 += rb.spectra[row][rc][k];
-      if (j + 1 == P_r) r.X2_ref[k] = x2;
-      if (j + 1 == P_c) r.X2_coa[k] = x2;
+#pragma unroll 1
+    for (int j0 = 0; j0 < pmax; j0 += 4) {
+      float v[4][R];   // one batch of loads, then the additions in the reference's order
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int row = ring_row(pos, imin(j0 + jj, pmax - 1));
+#pragma unroll
+        for (int rc = 0; rc < R; ++rc) v[jj][rc] = rb.spectra[row][rc][k];
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj;
+        if (j < pmax) {
+#pragma unroll
+          for (int rc = 0; rc < R; ++rc) x2 += v[jj][rc];
+          if (j + 1 == P_r) r.X2_ref[k] = x2;
+          if (j + 1 == P_c) r.X2_coa[k] = x2;
+        }
+      }
     }
   }
   __syncwarp();
 }
+WAP_DEV void mc_spectral_sums(const McRender& rb, AecScratch& sc, int P_r, int P_c, int R) {
+  if (R == 2) mc_spectral_sums_r<2>(rb, sc, P_r, P_c);
+  else mc_spectral_sums_r<1>(rb, sc, P_r, P_c);
+}
 
 // Both filters of one capture channel: S = sum over virtual partitions of X * H (ApplyFilter_Avx2's
 // operations per bin) -> sc.fftA (refined, packed) / sc.fftB (coarse).
-WAP_DEV void mc_fir_filter_both(const McRender& rb, const McFilters& f, AecScratch& sc, int P_r, int P_c, int R) {
+template <int R>
+WAP_DEV void mc_fir_filter_both_r(const McRender& rb, const McFilters& f, AecScratch& sc, int P_r, int P_c) {
   const int lane = lane_id();
   const int pos = sc.s.spectra_read;
   const int pmax = imax(P_r, P_c);
@@ -177,23 +197,42 @@ WAP_DEV void mc_fir_filter_both(const McRender& rb, const McFilters& f, AecScrat
   }
   for (int k = lane; k < 64; k += 32) {
     float Sr_re = 0.f, Sr_im = 0.f, Sc_re = 0.f, Sc_im = 0.f;
-#pragma unroll 2
-    for (int p = 0; p < pmax; ++p) {
-      const int row = ring_row(pos, p);
-      for (int rc = 0; rc < R; ++rc) {
-        const int v = p * R + rc;
-        const float Xr = rb.fft_re[row][rc][k], Xi = rb.fft_im[row][rc][k];
-        if (p < P_r) {
-          const float Hre = f.Hr_re[v][k], Him = f.Hr_im[v][k];
-          const float aa = Xr * Hre, bb = Xi * Him, cc = Xr * Him, dd = Xi * Hre;
-          Sr_re = Sr_re + (aa - bb);
-          Sr_im = Sr_im + (cc + dd);
+#pragma unroll 1
+    for (int p0 = 0; p0 < pmax; p0 += 2) {
+      // one batch of loads (2 partitions x R channels x {X, Hr, Hc} x {re, im}), then the arithmetic in order
+      float Xr[2][R], Xi[2][R], Ar[2][R], Ai[2][R], Cr[2][R], Ci[2][R];
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const int p = imin(p0 + pp, pmax - 1);
+        const int row = ring_row(pos, p);
+#pragma unroll
+        for (int rc = 0; rc < R; ++rc) {
+          const int v = p * R + rc;
+          Xr[pp][rc] = rb.fft_re[row][rc][k];
+          Xi[pp][rc] = rb.fft_im[row][rc][k];
+          Ar[pp][rc] = f.Hr_re[v][k];
+          Ai[pp][rc] = f.Hr_im[v][k];
+          Cr[pp][rc] = f.Hc_re[v][k];
+          Ci[pp][rc] = f.Hc_im[v][k];
         }
-        if (p < P_c) {
-          const float Hre = f.Hc_re[v][k], Him = f.Hc_im[v][k];
-          const float aa = Xr * Hre, bb = Xi * Him, cc = Xr * Him, dd = Xi * Hre;
-          Sc_re = Sc_re + (aa - bb);
-          Sc_im = Sc_im + (cc + dd);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const int p = p0 + pp;
+#pragma unroll
+        for (int rc = 0; rc < R; ++rc) {
+          if (p < P_r) {
+            const float aa = Xr[pp][rc] * Ar[pp][rc], bb = Xi[pp][rc] * Ai[pp][rc], cc = Xr[pp][rc] * Ai[pp][rc],
+                        dd = Xi[pp][rc] * Ar[pp][rc];
+            Sr_re = Sr_re + (aa - bb);
+            Sr_im = Sr_im + (cc + dd);
+          }
+          if (p < P_c) {
+            const float aa = Xr[pp][rc] * Cr[pp][rc], bb = Xi[pp][rc] * Ci[pp][rc], cc = Xr[pp][rc] * Ci[pp][rc],
+                        dd = Xi[pp][rc] * Cr[pp][rc];
+            Sc_re = Sc_re + (aa - bb);
+            Sc_im = Sc_im + (cc + dd);
+          }
         }
       }
     }
@@ -203,7 +242,8 @@ WAP_DEV void mc_fir_filter_both(const McRender& rb, const McFilters& f, AecScrat
   {
     float S_ref = 0.f, S_coa = 0.f;
     const int nv_r = P_r * R, nv_c = P_c * R;
-    for (int v = 0; v < kMcVParts; ++v) {
+#pragma unroll
+    for (int v = 0; v < kMaxPartitions * R; ++v) {
       const float tr = __shfl_sync(WAP_FULL, t_ref, v), tc = __shfl_sync(WAP_FULL, t_coa, v);
       if (v < nv_r) S_ref = S_ref + tr;
       if (v < nv_c) S_coa = S_coa + tc;
@@ -214,32 +254,59 @@ WAP_DEV void mc_fir_filter_both(const McRender& rb, const McFilters& f, AecScrat
     }
   }
 }
+WAP_DEV void mc_fir_filter_both(const McRender& rb, const McFilters& f, AecScratch& sc, int P_r, int P_c, int R) {
+  if (R == 2) mc_fir_filter_both_r<2>(rb, f, sc, P_r, P_c);
+  else mc_fir_filter_both_r<1>(rb, f, sc, P_r, P_c);
+}
 
 // AdaptPartitions_Avx2 for one filter: H_v += conj(X) * G over P partitions x R channels.  h2 != nullptr:
 // also ComputeFrequencyResponse_Avx2 (max over the render channels, from 0) for every partition.
-WAP_DEV void mc_fir_adapt(const McRender& rb, AecScratch& sc, float (*H_re)[kBinsPad], float (*H_im)[kBinsPad], int P,
-                          int R, const float* G_re, const float* G_im, float (*h2)[kBinsPad]) {
+template <int R>
+WAP_DEV void mc_fir_adapt_r(const McRender& rb, AecScratch& sc, float (*H_re)[kBinsPad], float (*H_im)[kBinsPad], int P,
+                            const float* G_re, const float* G_im, float (*h2)[kBinsPad]) {
   const int pos = sc.s.spectra_read;
   for (int k = lane_id(); k < kBins; k += 32) {
     const float Gre = G_re[k], Gim = G_im[k];
-#pragma unroll 2
-    for (int p = 0; p < P; ++p) {
-      const int row = ring_row(pos, p);
-      float m = 0.f;
-      for (int rc = 0; rc < R; ++rc) {
-        const int v = p * R + rc;
-        const float X_re = rb.fft_re[row][rc][k], X_im = rb.fft_im[row][rc][k];
-        const float aa = X_re * Gre, bb = X_im * Gim, cc = X_re * Gim, dd = X_im * Gre;
-        const float re = H_re[v][k] + (aa + bb), im = H_im[v][k] + (cc - dd);
-        H_re[v][k] = re;
-        H_im[v][k] = im;
-        const float p2 = (k < 64) ? fmaf(im, im, re * re) : re * re + im * im;
-        m = fmaxr(m, p2);
+#pragma unroll 1
+    for (int p0 = 0; p0 < P; p0 += 2) {
+      float Xr[2][R], Xi[2][R], Hr[2][R], Hi[2][R];
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const int p = imin(p0 + pp, P - 1);
+        const int row = ring_row(pos, p);
+#pragma unroll
+        for (int rc = 0; rc < R; ++rc) {
+          Xr[pp][rc] = rb.fft_re[row][rc][k];
+          Xi[pp][rc] = rb.fft_im[row][rc][k];
+          Hr[pp][rc] = H_re[p * R + rc][k];
+          Hi[pp][rc] = H_im[p * R + rc][k];
+        }
       }
-      if (h2) h2[p][k] = m;
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const int p = p0 + pp;
+        if (p < P) {
+          float m = 0.f;
+#pragma unroll
+          for (int rc = 0; rc < R; ++rc) {
+            const float aa = Xr[pp][rc] * Gre, bb = Xi[pp][rc] * Gim, cc = Xr[pp][rc] * Gim, dd = Xi[pp][rc] * Gre;
+            const float re = Hr[pp][rc] + (aa + bb), im = Hi[pp][rc] + (cc - dd);
+            H_re[p * R + rc][k] = re;
+            H_im[p * R + rc][k] = im;
+            const float p2 = (k < 64) ? fmaf(im, im, re * re) : re * re + im * im;
+            m = fmaxr(m, p2);
+          }
+          if (h2) h2[p][k] = m;
+        }
+      }
     }
   }
   __syncwarp();
+}
+WAP_DEV void mc_fir_adapt(const McRender& rb, AecScratch& sc, float (*H_re)[kBinsPad], float (*H_im)[kBinsPad], int P,
+                          int R, const float* G_re, const float* G_im, float (*h2)[kBinsPad]) {
+  if (R == 2) mc_fir_adapt_r<2>(rb, sc, H_re, H_im, P, G_re, G_im, h2);
+  else mc_fir_adapt_r<1>(rb, sc, H_re, H_im, P, G_re, G_im, h2);
 }
 
 // Subtractor::Process for capture channel c (subtractor.cc:226-342).  In: cv.y, r.X2_ref / r.X2_coa (the

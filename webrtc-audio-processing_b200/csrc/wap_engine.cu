@@ -159,7 +159,7 @@ struct WapEngine {
   wap::McTemplates* d_mc_templates = nullptr;
   wap::Ec3Params ep_mc = wap::ec3_default_params();
   wap::McParams mcp[2] = {};
-  int mc_front_floats = 0, mc_echo_floats = 0;
+  int mc_front_floats = 0, mc_echo_floats = 0, mc_echo_wpb = 4;
   double rs_ratio_in = 1.0, rs_ratio_out = 1.0;
   int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
   // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
@@ -692,7 +692,9 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
       e->launches++;
     }
     if (timing) cudaEventRecord(e->ev[2], e->stream);
-    wap::launch_k_mc_echo(grid_for(n), wpb * 32, (size_t)wpb * e->mc_echo_floats * sizeof(float), e->stream, a, e->mc_echo_floats);
+    // k_mc_echo: ~18 KB of scratch per warp (12 warps per SM whatever the CTA size; 4-warp CTAs measured best)
+    const int ew = e->mc_echo_wpb;
+    wap::launch_k_mc_echo((n + ew - 1) / ew, ew * 32, (size_t)ew * e->mc_echo_floats * sizeof(float), e->stream, a, e->mc_echo_floats);
     e->launches++;
     if (e->cfg.num_bands == 3 && d_capture) {
       wap::launch_k_mc_post(e->stream, a);
@@ -904,6 +906,7 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
     }
     e->mc_front_floats = wap::k_mc_front_scratch_floats();
     e->mc_echo_floats = wap::k_mc_echo_scratch_floats();
+    if (const char* w = getenv("WAP_MC_ECHO_WPB")) e->mc_echo_wpb = std::max(1, std::min(4, atoi(w)));   // tuning knob
   }
   e->echo_scratch_floats = e->ec3_runtime ? wap::k_echo_scratch_floats_rt(cfg.num_bands) : wap::k_echo_scratch_floats(cfg.num_bands);
   e->echo_class = wap::echo_class_of(cfg);

@@ -25,7 +25,9 @@ namespace wap {
 // Shared-memory footprint of one warp.
 constexpr int kMcEchoBase = (int)((kAecEchoScratchBytes + 15) / 16 * 16);
 constexpr int kMcEchoBytes = kMcEchoBase + (int)((sizeof(McExtra) + 15) / 16 * 16);
-constexpr int kMcEchoFloats = kMcEchoBytes / 4 + 3 * kFrame * kMaxBands;   // + bands | full | filter-bank scratch
+// The band merge after the echo remover (bands | full | filter-bank scratch: 3 x 480 floats) overlays the
+// echo-remover scratch, which is dead by then.
+constexpr int kMcEchoFloats = kMcEchoBytes / 4 > 3 * kFrame * kMaxBands ? kMcEchoBytes / 4 : 3 * kFrame * kMaxBands;
 constexpr int kMcFrontFloats = (int)((sizeof(McFrontScratch) + 15) / 16 * 4);
 
 WAP_DEV void mc_stage_scalars(const Aec3Scalars& src_s, Aec3Scalars& dst_s) {
@@ -81,7 +83,7 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   McTick& mt = mc.tick;
   AecScratch& sc = *reinterpret_cast<AecScratch*>(scratch);
   McExtra& mx = *reinterpret_cast<McExtra*>(reinterpret_cast<char*>(scratch) + kMcEchoBase);
-  float* fb = scratch + kMcEchoBytes / 4;   // 3 x flen floats for the band merge
+  float* fb = scratch;   // 3 x flen floats for the band merge (overlay: used after the scalars are unstaged)
   const bool output_used = st.capture_output_used != 0;
   const bool output_used_last_frame = st.capture_output_used_last_frame != 0;
   cfg.capture_output_used = output_used ? 1 : 0;
