@@ -398,8 +398,12 @@ bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
 WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config);
 /* wap_create_with_config / wap_engine_create with an injected AEC3 config
  * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig(config, multichannel_config)).
- * multichannel_config may be NULL: the reference then derives it from `config`
- * (echo_canceller3.cc:107-118); it applies to legs with more than one render or capture channel. */
+ * multichannel_config may be NULL: `config` then serves both (audio_processing_impl.cc:1928-1943; with no
+ * injected config at all the multichannel one is CreateDefaultMultichannelConfig()).  It is what legs
+ * with stereo frames and pipeline_multi_channel_render + _capture run once MultiChannelContentDetector
+ * has seen persistent stereo content (echo_canceller3.cc:790-811, config_selector.cc:51-72).  The two
+ * configs must agree in multi_channel.detect_stereo_content / stereo_detection_timeout_threshold_seconds
+ * (ConfigSelector) and in comfort_noise.noise_floor_dbfs. */
 WapAudioProcessing* wap_create_with_aec3_config(WapConfig config, const WapEchoCanceller3Config* aec3_config,
                                                 const WapEchoCanceller3Config* aec3_multichannel_config);
 WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_streams, WapConfig config,

@@ -186,3 +186,37 @@ def test_multichannel_unsupported_combinations_are_refused(api_lib):
         rate = 48000 if kw.get("max_rate") == 32000 else 16000
         with pytest.raises(RuntimeError):
             wap_b200.Engine(1, rate, channels=2, lib=api_lib, **kw)
+
+
+def test_multichannel_single_leg_entry_points(api_lib, oracle):
+    """The seam's own calls (wap_create_with_aec3_config + ProcessReverseStream / ProcessStream) on stereo
+    frames with both multi_channel flags: same engine underneath, user configs for both variants."""
+    import ctypes as C
+    import wap_b200
+    L = api_lib
+    rate, n_frames, fl = 16000, 150, 320
+    mono = {"multi_channel.stereo_detection_hysteresis_seconds": 0.3}
+    mc = {"filter.coarse.length_blocks": 10, "filter.coarse_initial.length_blocks": 9}
+    far, near = stereo_leg(rate, n_frames, 41, 0.6)
+    kv = dict(aec=1, ns=0, mc_render=1, mc_capture=1, max_rate=48000)
+    kv.update({"ec3." + k: v for k, v in mono.items()})
+    kv.update({"ec3mc." + k: v for k, v in mc.items()})
+    ref_out, _, err = oracle.RefApm(kv=kv).run_i16(rate, far, near, render_ch=2, capture_ch=2)
+    assert err == 0
+    cfg = wap_b200.make_config(L, **MC)
+    c_mono, c_mc = wap_b200.make_aec3_config(L, mono), wap_b200.make_aec3_config(L, mc, multichannel=True)
+    h = L.wap_create_with_aec3_config(cfg, C.byref(c_mono), C.byref(c_mc))
+    assert h
+    sc = wap_b200.WapStreamConfig(rate, 2)
+    out = np.zeros_like(near)
+    tmp = np.zeros(fl, np.int16)
+    for f in range(n_frames):
+        r = np.ascontiguousarray(far[f * fl:(f + 1) * fl])
+        c = np.ascontiguousarray(near[f * fl:(f + 1) * fl])
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert L.wap_process_reverse_stream_i16(h, p(r), fl, sc, sc, p(tmp), fl) == 0
+        L.wap_set_stream_delay_ms(h, 0)
+        assert L.wap_process_stream_i16(h, p(c), fl, sc, sc, p(tmp), fl) == 0
+        out[f * fl:(f + 1) * fl] = tmp
+    L.wap_destroy(h)
+    assert first_bad_frame(out, ref_out, fl) is None

@@ -194,6 +194,8 @@ struct WapAudioProcessing {
   bool owns_engine = false;
   bool has_aec3_config = false;            // wap_create_with_aec3_config: injected EchoCanceller3Config
   WapEchoCanceller3Config aec3_config{};
+  bool has_aec3_mc_config = false;         // ... and multichannel EchoCanceller3Config
+  WapEchoCanceller3Config aec3_mc_config{};
   WapStats cached_stats{};  // ApmStatsReporter::cached_stats_
 };
 
