@@ -548,5 +548,6 @@ def test_multi_channel_pipeline_flags_on_mono_legs(api_lib, oracle):
         out[sl] = eng.process(far[sl][None, :], near[sl][None, :])[0]
     eng.close()
     assert np.array_equal(out, ro)
+    # stereo frames with the flags are the multi-channel class (tests/test_multichannel.py); with one flag only: refused
     with pytest.raises(RuntimeError):
-        wap_b200.Engine(1, 16000, channels=2, lib=api_lib, aec=True, ns=True, mc_render=True, mc_capture=True)
+        wap_b200.Engine(1, 16000, channels=2, lib=api_lib, aec=True, ns=True, mc_render=True, mc_capture=False)

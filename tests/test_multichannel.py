@@ -74,6 +74,59 @@ def test_multichannel_matches_reference(api_lib, oracle, rate, n_frames, kind):
     assert np.any(out[0::2] != out[1::2])
 
 
+@pytest.mark.parametrize("rate,n_frames,kind,level", [
+    (16000, 330, "stereo", 1),    # NS moderate, crosses the switch to two render channels and NS's 200-frame start-up
+    (16000, 120, "mono", 3),      # NS very high
+    (48000, 260, "stereo", 2),    # NS high, three bands: upper-band gains and delays per channel, minimum over channels
+    (48000, 90, "burst", 0),      # NS low
+])
+def test_multichannel_with_noise_suppressor(api_lib, oracle, rate, n_frames, kind, level):
+    """NoiseSuppressor with two channels (noise_suppressor.cc:278-292,294-559): per-channel state, one frame
+    counter and zero-frame test, Wiener filter / gain adjustment / upper-band gain = minimum over the channels."""
+    import wap_b200
+    far, near = stereo_leg(rate, n_frames, 13, 0.6)
+    far = render_variant(far, kind, rate)
+    fl = rate // 100 * 2
+    kw = dict(MC, ns=True, ns_level=level)
+    eng = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **kw)
+    ref_out, _, err = oracle.RefApm(**kw).run_i16(rate, far, near, render_ch=2, capture_ch=2)
+    assert err == 0
+    out = np.zeros_like(near)
+    for f in range(n_frames):
+        eng.set_stream_delay_ms(0)
+        out[f * fl:(f + 1) * fl] = eng.process(far[f * fl:(f + 1) * fl].reshape(1, fl), near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
+    eng.close()
+    assert first_bad_frame(out, ref_out, fl) is None
+
+
+def test_multichannel_noise_suppressor_muted_output_and_silence(api_lib, oracle):
+    """Silent stretches (the zero-frame rule looks at every channel) and a muted output (Process stops after the
+    per-channel filter update) with NS on two channels, float interface."""
+    import wap_b200
+    rate, n_frames, fl = 16000, 160, 160
+    far, near = stereo_leg(rate, n_frames, 17, 0.6)
+    near = near.copy()
+    near[0:2 * fl * 6] = 0                      # six silent frames at the start (both channels)
+    near[2 * fl * 40:2 * fl * 44:2] = 0         # left channel silent, right one not
+    kw = dict(MC, ns=True, ns_level=1)
+    eng = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **kw)
+    refapm = oracle.RefApm(**kw)
+    differing = 0
+    for f in range(n_frames):
+        if f in (60, 90):
+            eng.set_capture_output_used(f == 90)
+            refapm.set_capture_output_used(f == 90)
+        r = (far[f * 2 * fl:(f + 1) * 2 * fl].reshape(fl, 2).T.astype(np.float32) / 32768.0).copy()
+        c = (near[f * 2 * fl:(f + 1) * 2 * fl].reshape(fl, 2).T.astype(np.float32) / 32768.0).copy()
+        eng.set_stream_delay_ms(0)
+        o = eng.process(r.reshape(1, -1), c.reshape(1, -1)).reshape(-1)
+        ro, err = refapm.tick_f32(rate, r.reshape(-1), c.reshape(-1), render_ch=2, capture_ch=2)
+        assert err == 0
+        differing += int(np.count_nonzero(o.view(np.uint32) != ro.view(np.uint32)))
+    eng.close()
+    assert differing == 0
+
+
 def test_multichannel_saturated_capture_channel(api_lib, oracle):
     # the right capture channel clips: AnalyzeCapture's saturation flag covers every channel
     out, ref_out = run_pair(api_lib, oracle, 16000, 260, "stereo", right_gain=2.6)
@@ -181,7 +234,7 @@ def test_multichannel_state_moves_between_engines(api_lib, oracle):
 
 def test_multichannel_unsupported_combinations_are_refused(api_lib):
     import wap_b200
-    for kw in (dict(MC, ns=True), dict(MC, agc2=True), dict(MC, mc_capture=False), dict(MC, mc_render=False),
+    for kw in (dict(MC, agc2=True), dict(MC, pre_gain=2.0), dict(MC, mc_capture=False), dict(MC, mc_render=False),
                dict(MC, max_rate=32000)):
         rate = 48000 if kw.get("max_rate") == 32000 else 16000
         with pytest.raises(RuntimeError):

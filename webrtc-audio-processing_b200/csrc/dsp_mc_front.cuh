@@ -342,6 +342,9 @@ WAP_DEV void mc_front_tick(const TickArgs& a, int idx, McFrontScratch& fs) {
     __syncwarp();
     if (B == 3) three_band_analysis(fs.full, fs.bands[c], fs.sub, mc.cio[c].bands.analysis);
     __syncwarp();
+    // NoiseSuppressor::Analyze (k_mc_echo) looks at band 0 of the capture frame in front of the echo canceller
+    if (cfg.ns_enabled)
+      for (int i = lane; i < kFrame; i += 32) mt.capture_frame[c][i] = fs.bands[c][i];
   }
   const bool saturated = __any_sync(WAP_FULL, sat);
   __syncwarp();

@@ -85,29 +85,42 @@ WAP_DEV void ns_magnitude(const float* a, float* spec) {
   __syncwarp();
 }
 
-// NoiseSuppressor::Analyze (noise_suppressor.cc:294-386), one channel.
-// `frame`: band-0 samples (160) in shared memory.
-WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame, NsScratch& sc) {
-  const int lane = lane_id();
-  // NoiseEstimator::PrepareAnalysis (noise_estimator.cc:66-69)
+// NoiseSuppressor::Analyze (noise_suppressor.cc:294-386) in the pieces the reference's channel loops cut it
+// into: ns_analyze_prepare and ns_frame_nonzero for every channel, then (unless all channels are silent) the
+// shared frame counter and ns_analyze_channel for every channel.  `frame`: band-0 samples (160) in shared memory.
+// NoiseEstimator::PrepareAnalysis (noise_estimator.cc:66-69)
+WAP_DEV void ns_analyze_prepare(NsState& st) {
   #pragma unroll
-  for (int i = lane; i < kNsBins; i += 32) st.prev_noise[i] = st.noise[i];
-  // Zero-frame detection: the reference sums v*v over memory+frame and tests
-  // > 0; a sum of non-negative terms is positive iff one term is.
+  for (int i = lane_id(); i < kNsBins; i += 32) st.prev_noise[i] = st.noise[i];
+}
+// Zero-frame detection: the reference sums v*v over memory+frame and tests
+// > 0; a sum of non-negative terms is positive iff one term is.
+WAP_DEV bool ns_frame_nonzero(const NsState& st, const float* frame) {
   int nz = 0;
   #pragma unroll
-  for (int i = lane; i < 256; i += 32) {
+  for (int i = lane_id(); i < 256; i += 32) {
     const float v = (i < kNsOverlap) ? st.analyze_mem[i] : frame[i - kNsOverlap];
     nz |= (v * v > 0.f);
   }
   __syncwarp();
-  if (!__any_sync(WAP_FULL, nz)) return;
+  return __any_sync(WAP_FULL, nz) != 0;
+}
+WAP_DEV void ns_analyze_channel(NsState& st, const EngineConfig& cfg, const float* frame, NsScratch& sc, int naf);
 
+// One channel (mono legs).
+WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame, NsScratch& sc) {
+  ns_analyze_prepare(st);
+  if (!ns_frame_nonzero(st, frame)) return;
   int naf = st.num_analyzed_frames + 1;
   if (naf < 0) naf = 0;
   __syncwarp();
-  if (lane == 0) st.num_analyzed_frames = naf;
+  if (lane_id() == 0) st.num_analyzed_frames = naf;
+  ns_analyze_channel(st, cfg, frame, sc, naf);
+}
 
+// The per-channel body; naf: num_analyzed_frames_ after this frame's increment.
+WAP_DEV void ns_analyze_channel(NsState& st, const EngineConfig& cfg, const float* frame, NsScratch& sc, int naf) {
+  const int lane = lane_id();
   ns_form_windowed_frame(frame, st.analyze_mem, sc.buf);
   ns_fft256_forward(sc.buf);
   ns_magnitude(sc.buf, sc.spec);
@@ -508,9 +521,17 @@ WAP_DEV void ns_analyze(NsState& st, const EngineConfig& cfg, const float* frame
   __syncwarp();
 }
 
-// NoiseSuppressor::Process (noise_suppressor.cc:388-559), one channel.
+// NoiseSuppressor::Process (noise_suppressor.cc:388-559) in the three pieces the reference's channel loops
+// cut it into (the Wiener filters, the gain adjustments and the upper-band gains of the channels are each
+// reduced to their minimum in between):
+//   ns_process_front   extended frame, FFT, WienerFilter::Update, ComputeUpperBandsGain
+//                      -> spectrum in sc.buf, this channel's filter in sc.prior, *energy_before, *upper_band_gain
+//   ns_process_filter  filter (sc.prior, possibly replaced by the minimum over the channels) applied, inverse
+//                      FFT, synthesis window -> windowed frame in sc.buf; returns ComputeOverallScalingFactor
+//   ns_process_finish  gain adjustment, overlap-add, upper bands delayed and scaled, clamp -> bands
 // `bands`: [num_bands][160] in shared memory, processed in place.
-WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsScratch& sc) {
+WAP_DEV void ns_process_front(NsState& st, const EngineConfig& cfg, const float* bands, NsScratch& sc,
+                              float* energy_before_out, float* upper_band_gain_out) {
   const int lane = lane_id();
   const int naf = st.num_analyzed_frames;
   ns_form_windowed_frame(bands, st.process_mem, sc.buf);
@@ -573,8 +594,13 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
     upper_band_gain = fminr(fmaxr(gain, cfg.ns_minimum_attenuating_gain), 1.f);
     __syncwarp();
   }
-  if (!cfg.capture_output_used) return;
+  *energy_before_out = energy_before;
+  *upper_band_gain_out = upper_band_gain;
+}
 
+WAP_DEV float ns_process_filter(const NsState& st, const EngineConfig& cfg, NsScratch& sc, float energy_before) {
+  const int lane = lane_id();
+  const int naf = st.num_analyzed_frames;
   // apply filter to the packed spectrum, inverse FFT, scale 2/256
   #pragma unroll
   for (int i = lane; i < kNsBins; i += 32) {
@@ -617,6 +643,12 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
     gain_adjustment = prior_speech_probability * scale_factor1 + (1.f - prior_speech_probability) * scale_factor2;
   }
   __syncwarp();
+  return gain_adjustment;
+}
+
+WAP_DEV void ns_process_finish(NsState& st, const EngineConfig& cfg, float* bands, NsScratch& sc, float gain_adjustment,
+                               float upper_band_gain) {
+  const int lane = lane_id();
   // scale, overlap-add (noise_suppressor.cc:104-116) and clamp
   #pragma unroll
   for (int i = lane; i < 256; i += 32) sc.buf[i] = gain_adjustment * sc.buf[i];
@@ -646,6 +678,15 @@ WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsSc
     }
     __syncwarp();
   }
+}
+
+// One channel (mono legs).
+WAP_DEV void ns_process(NsState& st, const EngineConfig& cfg, float* bands, NsScratch& sc) {
+  float energy_before, upper_band_gain;
+  ns_process_front(st, cfg, bands, sc, &energy_before, &upper_band_gain);
+  if (!cfg.capture_output_used) return;
+  const float gain_adjustment = ns_process_filter(st, cfg, sc, energy_before);
+  ns_process_finish(st, cfg, bands, sc, gain_adjustment, upper_band_gain);
 }
 
 }  // namespace wap

@@ -157,6 +157,8 @@ struct WapEngine {
   // multi-channel engines (EngineConfig::mc)
   wap::McState* d_mc = nullptr;             // [capacity]
   wap::McTemplates* d_mc_templates = nullptr;
+  wap::NsState* d_mc_ns = nullptr;          // [capacity][kMcCh] when NS is enabled
+  wap::NsState* d_mc_ns_template = nullptr;
   wap::Ec3Params ep_mc = wap::ec3_default_params();
   wap::McParams mcp[2] = {};
   int mc_front_floats = 0, mc_echo_floats = 0, mc_echo_wpb = 4;
@@ -249,9 +251,9 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   // legs run the mono EchoCanceller3Config whatever the flags say: config_selector.cc:44-58).
   if (f.num_channels > 2 || (f.num_channels == 2 && !c.echo_canceller_enabled)) return WapError::UnsupportedConfig;
   if (f.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture)) {
-    // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) only,
-    // at a native rate of 16 or 48 kHz.
-    if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) || c.noise_suppression_enabled ||
+    // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) with or
+    // without the noise suppressor, at a native rate of 16 or 48 kHz.
+    if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) ||
         c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.resample ||
         e.num_bands == 2)
       return WapError::UnsupportedConfig;
@@ -680,6 +682,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   a.rs_capture1 = nullptr;
   a.mc = e->d_mc;
   a.mc_templates = e->d_mc_templates;
+  a.mc_ns = e->d_mc_ns;
   a.ep_mc = e->ep_mc;
   a.mcp[0] = e->mcp[0];
   a.mcp[1] = e->mcp[1];
@@ -942,6 +945,14 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
          cudaMemcpy(e->d_mc_templates, t, sizeof(wap::McTemplates), cudaMemcpyHostToDevice) == cudaSuccess &&
          wap::set_k_mc_smem(4 * e->mc_front_floats * (int)sizeof(float), 4 * e->mc_echo_floats * (int)sizeof(float)) == cudaSuccess;
     delete t;
+    if (ok && cfg.ns_enabled) {
+      wap::NsState* nt = new wap::NsState;
+      wap::init_ns_state(*nt);
+      ok = cudaMalloc((void**)&e->d_mc_ns, (size_t)max_streams * wap::kMcCh * sizeof(wap::NsState)) == cudaSuccess &&
+           cudaMalloc((void**)&e->d_mc_ns_template, sizeof(wap::NsState)) == cudaSuccess &&
+           cudaMemcpy(e->d_mc_ns_template, nt, sizeof(wap::NsState), cudaMemcpyHostToDevice) == cudaSuccess;
+      delete nt;
+    }
   }
   if (ok && cfg.channels == 2 && !cfg.mc) {
     const size_t xb = (size_t)max_streams * sizeof(wap::ExtraChannelState);
@@ -992,6 +1003,8 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_extra);
   cudaFree(e->d_mc);
   cudaFree(e->d_mc_templates);
+  cudaFree(e->d_mc_ns);
+  cudaFree(e->d_mc_ns_template);
   cudaFree(e->d_template);
   cudaFree(e->d_render);
   cudaFree(e->d_capture);
@@ -1037,6 +1050,10 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
                  (const wap::McTemplates*)e->d_mc_templates, (const int*)d_slots, (int)n,
                  e->mcp[0].detect_stereo_content ? 0 : 1);
       e->launches++;
+      if (e->d_mc_ns)
+        for (int i = 0; i < n * wap::kMcCh; ++i)
+          WAP_CUDA(cudaMemcpyAsync(&e->d_mc_ns[(size_t)slots[i / wap::kMcCh] * wap::kMcCh + i % wap::kMcCh], e->d_mc_ns_template,
+                                   sizeof(wap::NsState), cudaMemcpyDeviceToDevice, e->stream));
     }
     if (e->d_rs)
       for (int i = 0; i < n; ++i)
@@ -1065,7 +1082,8 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
 }
 
 size_t wap_engine_state_bytes_per_stream(const WapEngine* e) {
-  return sizeof(StreamState) + ((e && e->d_mc) ? sizeof(wap::McState) : 0);
+  return sizeof(StreamState) + ((e && e->d_mc) ? sizeof(wap::McState) : 0) +
+         ((e && e->d_mc_ns) ? wap::kMcCh * sizeof(wap::NsState) : 0);
 }
 
 WapError wap_engine_synchronize(WapEngine* e) {
@@ -1330,6 +1348,7 @@ size_t blob_bytes(const WapEngine* e) {
   if (e->d_rs) n += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   if (e->d_extra) n += sizeof(wap::ExtraChannelState);
   if (e->d_mc) n += sizeof(wap::McState);
+  if (e->d_mc_ns) n += wap::kMcCh * sizeof(wap::NsState);
   return n;
 }
 }  // namespace
@@ -1382,7 +1401,12 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
     WAP_CUDA(cudaMemcpy(p, &e->d_extra[h->slot], sizeof(wap::ExtraChannelState), cudaMemcpyDeviceToHost));
     p += sizeof(wap::ExtraChannelState);
   }
-  if (e->d_mc) WAP_CUDA(cudaMemcpy(p, &e->d_mc[h->slot], sizeof(wap::McState), cudaMemcpyDeviceToHost));
+  if (e->d_mc) {
+    WAP_CUDA(cudaMemcpy(p, &e->d_mc[h->slot], sizeof(wap::McState), cudaMemcpyDeviceToHost));
+    p += sizeof(wap::McState);
+  }
+  if (e->d_mc_ns)
+    WAP_CUDA(cudaMemcpy(p, &e->d_mc_ns[(size_t)h->slot * wap::kMcCh], wap::kMcCh * sizeof(wap::NsState), cudaMemcpyDeviceToHost));
   return WapError::None;
 }
 
@@ -1414,7 +1438,12 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
     WAP_CUDA(cudaMemcpy(&e->d_extra[h->slot], p, sizeof(wap::ExtraChannelState), cudaMemcpyHostToDevice));
     p += sizeof(wap::ExtraChannelState);
   }
-  if (e->d_mc) WAP_CUDA(cudaMemcpy(&e->d_mc[h->slot], p, sizeof(wap::McState), cudaMemcpyHostToDevice));
+  if (e->d_mc) {
+    WAP_CUDA(cudaMemcpy(&e->d_mc[h->slot], p, sizeof(wap::McState), cudaMemcpyHostToDevice));
+    p += sizeof(wap::McState);
+  }
+  if (e->d_mc_ns)
+    WAP_CUDA(cudaMemcpy(&e->d_mc_ns[(size_t)h->slot * wap::kMcCh], p, wap::kMcCh * sizeof(wap::NsState), cudaMemcpyHostToDevice));
   e->dirty_legs -= (int)h->capture_output_used_dirty + (int)h->pre_gain_dirty + (int)h->post_gain_dirty +
                    (int)h->playout_volume_dirty + (int)h->agc2_gain_dirty;
   h->config = hd.config;
@@ -1535,6 +1564,7 @@ double wap_engine_algorithmic_bytes_per_frame(const WapEngine* e) {
     //   estimators, comfort noise, suppressor state  C x 16504               33008   (mono: 16504)
     bytes += 2.5 * (40256.0 + 99840.0 + 27040.0 + 6760.0 + 13520.0 + 33008.0);
     bytes += 2 * 96.0;                                   // high-pass filter state, both channels
+    if (e->cfg.ns_enabled) bytes += 2 * (2223.0 * 8.0 + 24.0);   // noise suppressor state, both channels
     if (B == 3) {
       bytes += (2 * 2 + 2) * 150 * 4.0;                  // capture analysis + synthesis and render analysis state, x2 channels
       bytes += 2 * (2.5 * (4.0 * kBlockBytesHi * 5) + 128.0);  // upper-band ring / delay / framers, PostFilter state

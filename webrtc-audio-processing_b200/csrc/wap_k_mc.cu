@@ -25,9 +25,13 @@ namespace wap {
 // Shared-memory footprint of one warp.
 constexpr int kMcEchoBase = (int)((kAecEchoScratchBytes + 15) / 16 * 16);
 constexpr int kMcEchoBytes = kMcEchoBase + (int)((sizeof(McExtra) + 15) / 16 * 16);
-// The band merge after the echo remover (bands | full | filter-bank scratch: 3 x 480 floats) overlays the
-// echo-remover scratch, which is dead by then.
-constexpr int kMcEchoFloats = kMcEchoBytes / 4 > 3 * kFrame * kMaxBands ? kMcEchoBytes / 4 : 3 * kFrame * kMaxBands;
+// Noise suppression and the band merge behind the echo remover overlay its scratch, which is dead by then:
+// the bands of both channels | one NsScratch per channel, or the full-band frame + filter-bank scratch.
+constexpr int kMcNsScratchFloats = (int)((sizeof(NsScratch) + 15) / 16 * 4);
+static_assert(sizeof(NsScratch) % 16 == 0, "per-channel NS scratch must stay 16-byte aligned");
+constexpr int kMcTailFloats = kMcCh * kFrame * kMaxBands +
+                              (kMcCh * kMcNsScratchFloats > 2 * kFrame * kMaxBands ? kMcCh * kMcNsScratchFloats : 2 * kFrame * kMaxBands);
+constexpr int kMcEchoFloats = kMcEchoBytes / 4 > kMcTailFloats ? kMcEchoBytes / 4 : kMcTailFloats;
 constexpr int kMcFrontFloats = (int)((sizeof(McFrontScratch) + 15) / 16 * 4);
 
 WAP_DEV void mc_stage_scalars(const Aec3Scalars& src_s, Aec3Scalars& dst_s) {
@@ -83,7 +87,6 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   McTick& mt = mc.tick;
   AecScratch& sc = *reinterpret_cast<AecScratch*>(scratch);
   McExtra& mx = *reinterpret_cast<McExtra*>(reinterpret_cast<char*>(scratch) + kMcEchoBase);
-  float* fb = scratch;   // 3 x flen floats for the band merge (overlay: used after the scalars are unstaged)
   const bool output_used = st.capture_output_used != 0;
   const bool output_used_last_frame = st.capture_output_used_last_frame != 0;
   cfg.capture_output_used = output_used ? 1 : 0;
@@ -95,6 +98,32 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   // ---------------- render side
   for (int r = 0; r < ts.n_render_blocks; ++r) mc_render_insert_vector(mc, sc, ts.rins[r], r, R, B);
   if (!a.capture) return;
+
+  // ---------------- NoiseSuppressor::Analyze on the capture frame in front of the echo canceller
+  // (noise_suppressor.cc:294-386): every channel prepared, one zero-frame test and one frame counter
+  // for all channels, then the per-channel analysis.  The NS scratch overlays the echo-remover scratch.
+  NsState* ns = cfg.ns_enabled ? a.mc_ns + (size_t)slot * kMcCh : nullptr;
+  if (ns) {
+    NsScratch& nsc = *reinterpret_cast<NsScratch*>(scratch);
+    float* frame = scratch + (sizeof(NsScratch) + 15) / 16 * 4;   // kMcCh x 160 floats behind the scratch
+    bool nonzero = false;
+    for (int c = 0; c < C; ++c) {
+      ns_analyze_prepare(ns[c]);
+      for (int i = lane; i < kFrame; i += 32) frame[c * kFrame + i] = mt.capture_frame[c][i];
+    }
+    __syncwarp();
+    for (int c = 0; c < C && !nonzero; ++c) nonzero = ns_frame_nonzero(ns[c], frame + c * kFrame);
+    if (nonzero) {
+      int naf = ns[0].num_analyzed_frames + 1;
+      if (naf < 0) naf = 0;
+      __syncwarp();
+      if (lane < C) ns[lane].num_analyzed_frames = naf;
+      __syncwarp();
+      for (int c = 0; c < C; ++c) ns_analyze_channel(ns[c], cfg, frame + c * kFrame, nsc, naf);
+    }
+    __syncwarp();
+    stage_ec3_params(a, sc, persistent);   // the NS scratch overlaid them
+  }
 
   // ---------------- capture side: EchoCanceller3::ProcessCapture
   aec3_stage_scalars(st.aec, sc);
@@ -159,17 +188,46 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   for (int c = 0; c < C; ++c) mc_stage_scalars(mx.cs[c], mc.chan[c].s);
   __syncwarp();
 
-  // ---------------- band merge and output
+  // ---------------- NoiseSuppressor::Process (noise_suppressor.cc:388-559), band merge and output
+  // shared memory from here on (the echo-remover scratch is dead): bands of both channels | NS scratch per
+  // channel, or full-band frame + filter-bank scratch for the merge
+  float* bands_all = scratch;                                  // [C][flen]
+  float* work = scratch + C * flen;
+  __syncwarp();
+  for (int c = 0; c < C; ++c)
+    for (int i = lane; i < flen; i += 32) bands_all[c * flen + i] = mt.capture_frame[c][i];
+  __syncwarp();
+  if (ns) {
+    NsScratch* nsc = reinterpret_cast<NsScratch*>(work);      // one per channel
+    float energy_before[kMcCh], upper_gain[kMcCh];
+    for (int c = 0; c < C; ++c) ns_process_front(ns[c], cfg, bands_all + c * flen, nsc[c], &energy_before[c], &upper_gain[c]);
+    if (cfg.capture_output_used) {
+      // AggregateWienerFilters: the minimum over the channels, applied to every channel
+      __syncwarp();
+      for (int i = lane; i < kNsBins; i += 32) {
+        float f = nsc[0].prior[i];
+        for (int c = 1; c < C; ++c) f = fminr(f, nsc[c].prior[i]);
+        for (int c = 0; c < C; ++c) nsc[c].prior[i] = f;
+      }
+      __syncwarp();
+      float gain_adjustment = 0.f, upper = upper_gain[0];
+      for (int c = 0; c < C; ++c) {
+        const float g = ns_process_filter(ns[c], cfg, nsc[c], energy_before[c]);
+        gain_adjustment = c == 0 ? g : fminr(gain_adjustment, g);
+        if (c) upper = fminr(upper, upper_gain[c]);
+      }
+      for (int c = 0; c < C; ++c) ns_process_finish(ns[c], cfg, bands_all + c * flen, nsc[c], gain_adjustment, upper);
+    }
+    __syncwarp();
+  }
   const bool zero_out = !output_used_last_frame && output_used;   // first frame after un-muting
   if (lane == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
   for (int c = 0; c < C; ++c) {
-    float* bands = fb;
-    float* full = fb + flen;
-    __syncwarp();
-    for (int i = lane; i < flen; i += 32) bands[i] = mt.capture_frame[c][i];
+    const float* bands = bands_all + c * flen;
+    float* full = work;
     __syncwarp();
     if (B == 3) {
-      three_band_synthesis(bands, full, fb + 2 * flen, mc.cio[c].bands.synthesis);
+      three_band_synthesis(bands, full, work + flen, mc.cio[c].bands.synthesis);
       __syncwarp();
       // 48 kHz: PostFilter and the output conversion are serial work for k_mc_post
       for (int i = lane; i < flen; i += 32) mt.capture_frame[c][i] = zero_out ? 0.f : full[i];

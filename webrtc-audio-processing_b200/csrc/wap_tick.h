@@ -43,6 +43,7 @@ struct TickArgs {
   // multichannel EchoCanceller3Config (`ep` is the mono one) and the parameters outside Ec3Params ([0]: of the
   // mono config, [1]: of the multichannel config; the detector reads [0]).
   McState* mc;               // [slot] or nullptr
+  NsState* mc_ns;            // [slot][kMcCh]: per-channel NoiseSuppressor::ChannelState when NS is enabled, else nullptr
   const McTemplates* mc_templates;
   Ec3Params ep_mc;
   McParams mcp[2];
