@@ -53,6 +53,9 @@ struct float2 {
 struct float4 {
   float x, y, z, w;
 };
+struct uchar4 {
+  unsigned char x, y, z, w;
+};
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) {
   return float4{x, y, z, w};

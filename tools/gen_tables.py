@@ -143,14 +143,14 @@ def flit(v):
 
 
 def farr(name, vals, per=6):
-    s = "WAP_DEVCONST float %s[%d] = {\n" % (name, len(vals))
+    s = "alignas(16) WAP_DEVCONST float %s[%d] = {\n" % (name, len(vals))
     for i in range(0, len(vals), per):
         s += "    " + ", ".join(flit(v) for v in vals[i:i + per]) + ",\n"
     return s + "};\n"
 
 
 def iarr(name, vals, ctype="unsigned char", per=16):
-    s = "WAP_DEVCONST %s %s[%d] = {\n" % (ctype, name, len(vals))
+    s = "alignas(16) WAP_DEVCONST %s %s[%d] = {\n" % (ctype, name, len(vals))
     for i in range(0, len(vals), per):
         s += "    " + ", ".join(str(int(v)) for v in vals[i:i + per]) + ",\n"
     return s + "};\n"

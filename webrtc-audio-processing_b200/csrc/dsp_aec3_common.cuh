@@ -118,6 +118,8 @@ struct AecScratch {
     };
   };
 };
+static_assert(offsetof(AecScratch, fftA) % 8 == 0 && offsetof(AecScratch, fftB) % 8 == 0,
+              "the transforms access (re, im) pairs with 64-bit loads / stores");
 // Each kernel allocates the common head plus its own member of the union.
 constexpr size_t kAecScratchHead = offsetof(AecScratch, mf);
 constexpr size_t kAecDelayScratchBytes = kAecScratchHead + sizeof(AecMfScratch);
