@@ -215,17 +215,8 @@ WAP_DEV void front_capture_prefilter(const TickArgs& a, int idx) {
 // True for legs whose band split runs in k_split (warp per leg) in front of k_front: 48 kHz AEC3.
 WAP_DEV bool front_presplit(const EngineConfig& cfg) { return cfg.num_bands == 3 && cfg.aec_enabled && !cfg.resample; }
 
-// The render side and the capture side of the front end touch disjoint state, except that the
-// capture side marks the leg as started (`seen_capture`, read by the render side: k_front passes
-// the value from before the tick) and the multi-band render path borrows ts.capture_frame.  Single
-// band legs therefore run the two sides on two threads (k_front: warps 0-1 / warps 2-3 of a CTA):
-// twice the threads for a kernel whose only parallelism is the number of legs.
-WAP_DEV bool front_two_sided(const EngineConfig& cfg) { return cfg.num_bands == 1; }
-enum { kFrontRender = 1, kFrontCapture = 2, kFrontBoth = 3 };
-
-// The front end of one tick for leg `idx` (thread-private); `sides`: which half this thread runs,
-// `seen_capture`: StreamState::seen_capture before the tick.
-WAP_DEV void front_leg(const TickArgs& a, int idx, int sides, int seen_capture) {
+// The front end of one tick for leg `idx` (thread-private).
+WAP_DEV void front_leg(const TickArgs& a, int idx) {
   const EngineConfig& cfg = a.cfg;
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
@@ -237,19 +228,17 @@ WAP_DEV void front_leg(const TickArgs& a, int idx, int sides, int seen_capture) 
   // 32 kHz legs run the upper-band code of the 3-band path with a second upper band that stays
   // all-zero (it never raises the band-energy maximum and its output is dropped).
   UpperBandState* up = (B >= 2 && cfg.aec_enabled) ? &a.upper[slot] : nullptr;
-  const bool render_live = !(cfg.reinit_on_first_capture && !seen_capture);
-  const bool render_now = a.render && cfg.aec_enabled && render_live;
-  float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
-  float sub[kFrame];
-
-  // ---------------- render: [band split] -> FrameBlocker -> BlockProcessor::BufferRender
-  if (sides & kFrontRender) {
+  const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
   const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
   // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
   // drains the render queue (audio_processing_impl.cc:1409-1415).
   if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms);
+  float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
+  float sub[kFrame];
+
+  // ---------------- render: [band split] -> FrameBlocker -> BlockProcessor::BufferRender
   int nrb = 0;
-  if (render_now) {
+  if (a.render && cfg.aec_enabled && render_live) {
     const float* band0;
     const float* rbands = frame;  // bands 1.. of the render frame
     if (front_presplit(cfg)) {
@@ -287,8 +276,6 @@ WAP_DEV void front_leg(const TickArgs& a, int idx, int sides, int seen_capture) 
     s.render_blocker_len = rem;
   }
   ts.n_render_blocks = nrb;
-  }
-  if (!(sides & kFrontCapture)) return;
   ts.n_capture_blocks = 0;
   if (!a.capture) return;
 
@@ -311,9 +298,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx, int sides, int seen_capture) 
     const int L = s.capture_blocker_len;
     const int total = L + kFrame;
     const int ncb = total / kBlock;
-    // blocks are only processed once render has started: a render frame of this tick always yields at
-    // least two blocks, each of which sets render_properly_started (front_render_insert)
-    const bool decimate = s.render_properly_started != 0 || render_now;
+    const bool decimate = s.render_properly_started != 0;  // blocks are only processed once render has started
     Biquad d0 = aec.capture_decimator[0], d1 = aec.capture_decimator[1], d2 = aec.capture_decimator[2],
            d3 = aec.capture_decimator[3];
     for (int b = 0; b < ncb; ++b) {

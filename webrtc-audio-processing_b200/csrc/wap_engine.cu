@@ -27,19 +27,9 @@
 namespace wap {
 
 // One 10 ms tick = k_front -> (k_delay) -> k_echo on the engine's stream.
-// One thread per leg and side: warps 0-1 of a CTA run the render side of 64 legs, warps 2-3 the
-// capture side of the same legs (dsp_front.cuh: front_two_sided); classes whose sides share scratch
-// run both on the capture thread.
 __global__ void __launch_bounds__(128) k_front(TickArgs a) {
-  const int idx = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int side = threadIdx.x >> 6;
-  const bool on = idx < a.n;
-  int seen = 1;
-  if (on) seen = a.states[a.slots ? a.slots[idx] : idx].seen_capture;
-  __syncthreads();  // the capture side sets seen_capture: every thread has read it
-  if (!on) return;
-  if (front_two_sided(a.cfg)) front_leg(a, idx, side == 0 ? kFrontRender : kFrontCapture, seen);
-  else if (side == 1) front_leg(a, idx, kFrontBoth, seen);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.n) front_leg(a, idx);
 }
 
 // 48 kHz AEC3 engines: band split of render and capture in front of k_front, one warp per leg.
@@ -744,13 +734,13 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     af.render = d_render ? e->d_rs_render : nullptr;
     af.capture = d_capture ? e->d_rs_capture : nullptr;
     af.fmt = 2;
-    WAP_LAUNCH(wap::k_front, (n + 63) / 64, 128, 0, e->stream, af);
+    WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, af);
   } else {
     if (e->d_upper && e->cfg.num_bands == 3) {
       WAP_LAUNCH(wap::k_split, grid_for(n), wpb * 32, (size_t)wpb * 1120 * sizeof(float), e->stream, a);
       e->launches++;
     }
-    WAP_LAUNCH(wap::k_front, (n + 63) / 64, 128, 0, e->stream, a);
+    WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
   }
   e->launches++;
   if (timing) cudaEventRecord(e->ev[1], e->stream);
