@@ -196,7 +196,8 @@ WAP_DEV void aec3_echo_block(Aec3State& a, const EngineConfig& cfg, AecScratch& 
 // EchoCanceller3::ProcessCapture for one capture frame (band 0 in place): the echo
 // remover on the 2-3 blocks k_front sliced, BlockFramer back into the frame.
 WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* band0, const TickScratch& ts,
-                               AecScratch& sc, UpperBandState* up) {
+                               AecScratch& sc, UpperBandState* up, const void* ns_prefetch = nullptr,
+                               int ns_prefetch_bytes = 0) {
   aec3_stage_scalars(a, sc);
   // The staged read indices are the ones after the last block; blocks see their own.
   const int final_blocks_read = sc.s.blocks_read, final_spectra_read = sc.s.spectra_read;
@@ -210,6 +211,8 @@ WAP_DEV void aec3_echo_capture(Aec3State& a, const EngineConfig& cfg, float* ban
   for (int b = 0; b < nb; ++b) {
     WAP_PHASE_SYNC();
     aec3_echo_block(a, cfg, sc, ts, b, up);
+    // the noise suppressor's Process half follows the last block
+    if (b == nb - 1 && cfg.ns_enabled && ns_prefetch) warp_prefetch_l1(ns_prefetch, ns_prefetch_bytes);
     if (b < 2) {
       const int len = sc.s.output_framer_len;
       __syncwarp();

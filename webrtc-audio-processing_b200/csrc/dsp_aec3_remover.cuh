@@ -903,6 +903,10 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   }
 
   subtractor_process(a, sc, s.capture_signal_saturation != 0);
+  // The filter passes have streamed ~28 KB through the L1 since the prefetch at the top of the block
+  // (which brought the lines into the L2): ask again now that the stages reading these vectors are next.
+  // Measured on B200: k_echo -3.3 %.
+  warp_prefetch_l1(a.H_error, (int)(reinterpret_cast<const char*>(a.render_decimator) - reinterpret_cast<const char*>(a.H_error)));
 
   // FormLinearFilterOutput (echo_remover.cc:497-529)
   {

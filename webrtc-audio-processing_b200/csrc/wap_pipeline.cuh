@@ -245,7 +245,7 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   if (cfg.aec_enabled) {
     WAP_PHASE_SYNC();
     stage_ec3_params(a, aec_sc);   // the noise suppressor's scratch overlays the AEC3 scratch
-    aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up);   // three more phase points, one per block slot
+    aec3_echo_capture(st.aec, cfg, bands, ts, aec_sc, up, &st.ns, (int)offsetof(NsState, hist_lrt));   // three more phase points, one per block slot
   }
   WAP_PHASE_SYNC();
   if (cfg.ns_enabled) ns_process(st.ns, cfg, bands, ns_sc);
