@@ -224,6 +224,9 @@ WapError wap_engine_set_pipeline_chunks(WapEngine* engine, int32_t chunks);
 void* wap_engine_cuda_stream(WapEngine* engine);
 /* Number of kernel launches issued by the engine so far. */
 int64_t wap_engine_launch_count(const WapEngine* engine);
+/* 1 when the engine runs the kernel instances that read the EchoCanceller3Config parameters at run
+ * time (a non-default config, or multi-channel legs), 0 for the default-config instances. */
+int32_t wap_engine_uses_runtime_aec3_parameters(const WapEngine* engine);
 
 /* Stream lifecycle: the complete state of a leg (device slabs + host-side settings) as an opaque
  * blob, e.g. to move a live call to another engine or GPU.  The importing leg must belong to an

@@ -28,7 +28,7 @@ def build(verbose=True):
         glob.glob(os.path.join(ROOT, "include", "*.h"))
     if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
-    base = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+    base = ["g++", "-std=c++17", "-O0" if O0 else "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-fPIC",
             "-DWAP_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"), "-I", HERE, "-I", CSRC,
             "-I", os.path.join(ROOT, "include"), "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
             "-Wno-unused-variable"] + EXTRA

@@ -173,3 +173,24 @@ def test_non_default_config_through_the_single_leg_seam(api_lib, oracle):
         out[f * 480:(f + 1) * 480] = o
     L.wap_destroy(h)
     assert np.array_equal(out, ro)
+
+
+def test_default_engines_run_the_compile_time_config_instances(api_lib):
+    """A default EchoCanceller3Config -- given explicitly or not -- selects the kernel instances with the
+    config folded into constants; any other config, and multi-channel legs, the run-time-parameter ones.
+    (A type-punned comparison of the parameter blocks once made the default compare unequal to itself.)"""
+    import wap_b200
+    L = api_lib
+    for _ in range(3):
+        e = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=True)
+        assert L.wap_engine_uses_runtime_aec3_parameters(e.h) == 0
+        e.close()
+    e = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=True, aec3={"delay.default_delay": 5})
+    assert L.wap_engine_uses_runtime_aec3_parameters(e.h) == 0
+    e.close()
+    e = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=True, aec3={"filter.coarse.rate": 0.6})
+    assert L.wap_engine_uses_runtime_aec3_parameters(e.h) == 1
+    e.close()
+    e = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=False, agc2=True)
+    assert L.wap_engine_uses_runtime_aec3_parameters(e.h) == 0
+    e.close()

@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-ftz=true", "-prec-div=true", "-prec-sqrt=true",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-shared",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-fno-strict-aliasing", "-shared",
          "-I", CSRC, "-I", os.path.join(ROOT, "include")]
 
 

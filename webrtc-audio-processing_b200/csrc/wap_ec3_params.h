@@ -9,6 +9,7 @@
 // Device code spells a parameter WAP_EC3(name) / WAP_EC3_ARR(name) with `sc` (AecScratch&) in scope.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 namespace wap {
 
@@ -118,11 +119,10 @@ inline Ec3Params ec3_default_params() {
 // Every member is a 4-byte scalar: equality of the object representations is equality of the configs.
 static_assert(sizeof(Ec3Params) % 4 == 0 && alignof(Ec3Params) == 4, "Ec3Params: 4-byte members only");
 inline bool same_ec3_params(const Ec3Params& a, const Ec3Params& b) {
-  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
-  for (unsigned i = 0; i < sizeof(Ec3Params) / 4; ++i)
-    if (pa[i] != pb[i]) return false;
-  return true;
+  // memcmp, not a walk over uint32_t words: reading the float members through another type is undefined
+  // behaviour and g++ -O2 did reorder it (the default config then compared unequal to itself and every
+  // default engine ran the run-time-parameter kernels).
+  return memcmp(&a, &b, sizeof(Ec3Params)) == 0;
 }
 
 }  // namespace wap

@@ -1099,6 +1099,7 @@ WapError wap_engine_set_pipeline_chunks(WapEngine* e, int32_t chunks) {
 }
 void* wap_engine_cuda_stream(WapEngine* e) { return e ? (void*)e->stream : nullptr; }
 int64_t wap_engine_launch_count(const WapEngine* e) { return e ? e->launches : 0; }
+int32_t wap_engine_uses_runtime_aec3_parameters(const WapEngine* e) { return e && e->ec3_runtime ? 1 : 0; }
 
 // Per-tick host bookkeeping in front of the launches: slot list, un/mute flags, stream delays.
 static WapError prepare_tick(WapEngine* e, WapAudioProcessing* const* handles, int32_t n, const int** d_delays_out,

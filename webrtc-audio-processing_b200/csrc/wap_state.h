@@ -14,6 +14,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace wap {
 
@@ -379,11 +380,7 @@ struct EngineConfig {
 // configs are equal exactly when their object representations are (export / import of leg state).
 static_assert(alignof(EngineConfig) == 4 && sizeof(EngineConfig) % 4 == 0, "EngineConfig: 4-byte members only");
 inline bool same_engine_config(const EngineConfig& a, const EngineConfig& b) {
-  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
-  for (size_t i = 0; i < sizeof(EngineConfig) / 4; ++i)
-    if (pa[i] != pb[i]) return false;
-  return true;
+  return memcmp(&a, &b, sizeof(EngineConfig)) == 0;  // see same_ec3_params: no type-punned reads
 }
 
 }  // namespace wap

@@ -177,7 +177,7 @@ EXPORTS = [
     "wap_process_reverse_stream_i16", "wap_process_reverse_stream_f32", "wap_get_statistics",
     "wap_engine_create", "wap_engine_destroy", "wap_engine_create_streams", "wap_engine_state_bytes_per_stream",
     "wap_engine_algorithmic_bytes_per_frame", "wap_process_streams", "wap_process_streams_device",
-    "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_version",
+    "wap_engine_synchronize", "wap_engine_cuda_stream", "wap_engine_launch_count", "wap_engine_uses_runtime_aec3_parameters", "wap_version",
     "wap_streams_set_delay_ms", "wap_engine_enable_kernel_timing", "wap_engine_read_kernel_timing", "wap_engine_algorithmic_bytes_per_kernel",
     "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state", "wap_stream_read_taps",
     "wap_echo_canceller3_config_default", "wap_echo_canceller3_config_default_multichannel", "wap_echo_canceller3_config_sizeof",
@@ -228,6 +228,8 @@ def load(path=None):
     L.wap_engine_cuda_stream.argtypes = [vp]
     L.wap_engine_launch_count.restype = C.c_int64
     L.wap_engine_launch_count.argtypes = [vp]
+    L.wap_engine_uses_runtime_aec3_parameters.restype = C.c_int32
+    L.wap_engine_uses_runtime_aec3_parameters.argtypes = [vp]
     L.wap_streams_set_delay_ms.argtypes = [vp, i32, C.c_int]
     L.wap_engine_enable_kernel_timing.argtypes = [vp, C.c_bool]
     L.wap_engine_set_pipeline_chunks.argtypes = [vp, i32]
