@@ -414,6 +414,23 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
                                               const WapEchoCanceller3Config* aec3_config,
                                               const WapEchoCanceller3Config* aec3_multichannel_config);
 
+/* ---- EXT: legs whose three streams have different formats ---------------------
+ * The reference negotiates one format per stream (ProcessStream(src, input_config, output_config, dest),
+ * ProcessReverseStream(src, input_config, ...): audio_processing_impl.cc:527-612,632-692,894-940): the
+ * processing rate follows the lower of the capture input and output rates, every stream gets its own
+ * PushSincResampler, a capture input with more channels than the output is downmixed on the way in
+ * (average, or first channel with pipeline_capture_downmix_method).  The single-leg entry points take
+ * the formats per call like the reference; a batched engine fixes them when it is created.
+ * aec3_config / aec3_multichannel_config may be NULL (defaults).  Rates: multiples of 100 Hz up to
+ * 96 kHz.  Refused (UnsupportedConfig), never approximated: an output of 48 kHz above the processing
+ * rate whose input has another format (capture_fullband_audio), 48 kHz AEC3 with another output rate,
+ * multi-channel processing with differing formats, a rate conversion of the render pass-through output. */
+WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, WapConfig config,
+                                          WapStreamConfig input, WapStreamConfig output,
+                                          WapStreamConfig reverse_input,
+                                          const WapEchoCanceller3Config* aec3_config,
+                                          const WapEchoCanceller3Config* aec3_multichannel_config);
+
 const char* wap_version(void);
 
 #ifdef __cplusplus

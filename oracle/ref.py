@@ -111,6 +111,37 @@ class RefApm:
         err = lib().ref_apm_tick_f32(self.h, rate, render_ch, capture_ch, _p(render), _p(capture), _p(out))
         return out, err
 
+    def run_formats(self, render_fmt, in_fmt, out_fmt, render, capture):
+        """One format (rate, channels) per stream.  render / capture: whole signals, int16 interleaved or
+        float32 planar per frame ([frames][ch][samples]); returns the output frames stacked the same way."""
+        L = lib()
+        (rr, rc), (ir, ic), (orate, oc) = render_fmt, in_fmt, out_fmt
+        capture = np.ascontiguousarray(capture)
+        i16 = capture.dtype == np.int16
+        fn = L.ref_apm_tick_fmt_i16 if i16 else L.ref_apm_tick_fmt_f32
+        fn.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3
+        nr, ni, no = rr // 100 * rc, ir // 100 * ic, orate // 100 * oc
+        frames = capture.size // ni
+        render = None if render is None else np.ascontiguousarray(render, dtype=capture.dtype)
+        out = np.zeros(frames * no, capture.dtype)
+        cap = capture.reshape(-1)
+        for f in range(frames):
+            r = None if render is None else render.reshape(-1)[f * nr:(f + 1) * nr]
+            c = cap[f * ni:(f + 1) * ni]
+            o = out[f * no:(f + 1) * no]
+            err = fn(self.h, rr, rc, ir, ic, orate, oc, _p(r), _p(c), _p(o))
+            assert err == 0, err
+        return out
+
+    def reverse_f32(self, in_fmt, out_fmt, render):
+        L = lib()
+        L.ref_apm_reverse_f32.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
+        (rr, rc), (orr, orc) = in_fmt, out_fmt
+        render = np.ascontiguousarray(render, dtype=np.float32)
+        out = np.zeros(orr // 100 * orc, np.float32)
+        err = L.ref_apm_reverse_f32(self.h, rr, rc, orr, orc, _p(render), _p(out))
+        return out, err
+
     def apply_config(self, **kv):
         """AudioProcessing::ApplyConfig with the current config updated by the given APM keys."""
         err = lib().ref_apm_apply_kv(self.h, kv_string(kv))

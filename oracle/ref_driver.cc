@@ -317,6 +317,52 @@ int ref_apm_tick_f32(void* p, int rate, int render_ch, int capture_ch,
   return e1 ? e1 : e2;
 }
 
+// One tick with a format of its own per stream: render (rr Hz, rc channels), capture
+// input (ir, ic), capture output (orate, oc).  Interleaved int16.
+int ref_apm_tick_fmt_i16(void* p, int rr, int rc, int ir, int ic, int orate, int oc, const int16_t* render,
+                         const int16_t* capture, int16_t* out) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::StreamConfig rcfg(rr, rc), icfg(ir, ic), ocfg(orate, oc);
+  std::vector<int16_t> scratch(rcfg.num_frames() * rc);
+  int e1 = 0;
+  if (render) e1 = h->apm->ProcessReverseStream(render, rcfg, rcfg, scratch.data());
+  h->apm->set_stream_delay_ms(0);
+  int e2 = h->apm->ProcessStream(capture, icfg, ocfg, out);
+  return e1 ? e1 : e2;
+}
+// Same with planar float [-1,1] ([ch][frame] per stream).
+int ref_apm_tick_fmt_f32(void* p, int rr, int rc, int ir, int ic, int orate, int oc, const float* render,
+                         const float* capture, float* out) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::StreamConfig rcfg(rr, rc), icfg(ir, ic), ocfg(orate, oc);
+  const int nr = rr / 100, ni = ir / 100, no = orate / 100;
+  std::vector<const float*> rp(rc), cp(ic);
+  std::vector<float*> op(oc), rop(rc);
+  std::vector<float> rscratch((size_t)nr * rc);
+  for (int i = 0; i < rc; ++i) {
+    rp[i] = render ? render + (size_t)i * nr : nullptr;
+    rop[i] = rscratch.data() + (size_t)i * nr;
+  }
+  for (int i = 0; i < ic; ++i) cp[i] = capture + (size_t)i * ni;
+  for (int i = 0; i < oc; ++i) op[i] = out + (size_t)i * no;
+  int e1 = 0;
+  if (render) e1 = h->apm->ProcessReverseStream(rp.data(), rcfg, rcfg, rop.data());
+  h->apm->set_stream_delay_ms(0);
+  int e2 = h->apm->ProcessStream(cp.data(), icfg, ocfg, op.data());
+  return e1 ? e1 : e2;
+}
+// ProcessReverseStream alone, float, with an output format of its own: the render pass-through output.
+int ref_apm_reverse_f32(void* p, int rr, int rc, int orr, int orc, const float* render, float* render_out) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::StreamConfig rcfg(rr, rc), ocfg(orr, orc);
+  const int nr = rr / 100, no = orr / 100;
+  std::vector<const float*> rp(rc);
+  std::vector<float*> rop(orc);
+  for (int i = 0; i < rc; ++i) rp[i] = render + (size_t)i * nr;
+  for (int i = 0; i < orc; ++i) rop[i] = render_out + (size_t)i * no;
+  return h->apm->ProcessReverseStream(rp.data(), rcfg, ocfg, rop.data());
+}
+
 // The runtime settings behind the wap_set_capture_*_gain / wap_set_playout_volume entry points.
 void ref_apm_set_pre_gain(void* p, float g) {
   static_cast<RefApm*>(p)->apm->SetRuntimeSetting(AudioProcessing::RuntimeSetting::CreateCapturePreGain(g));

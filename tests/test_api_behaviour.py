@@ -406,10 +406,11 @@ def test_apply_config_with_an_identical_config_keeps_all_state(api_lib):
     assert np.array_equal(outs[0], outs[1])
 
 
-def test_render_format_differing_from_capture_is_refused_not_reinterpreted(api_lib):
-    """Render at 48 kHz with capture at 16 kHz is the reference's MaybeInitializeRender case, which this
-    engine does not build: it must be refused (UnsupportedConfig) without touching the engine -- the
-    call's AEC3 / NS state survives and nothing is copied into a buffer of another size."""
+def test_render_format_of_a_shared_engine_is_fixed_and_never_reinterpreted(api_lib):
+    """Legs of a batched engine have the formats the engine was created with: a render frame of another
+    format is refused (UnsupportedConfig) without touching the leg -- its AEC3 / NS state survives and
+    nothing is copied into a buffer of another size.  (A private single-leg handle follows the reference's
+    MaybeInitializeRender instead: tests/test_formats.py.)"""
     import wap_b200
     L = api_lib
     far, near = synthetic_leg(7, 80)
@@ -418,7 +419,8 @@ def test_render_format_differing_from_capture_is_refused_not_reinterpreted(api_l
     h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
     _drive_single(L, wap_b200, h, far, near, 0, 80, ref_run)
     L.wap_destroy(h)
-    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
+    e = wap_b200.Engine(1, 16000, lib=L, aec=True, ns=True, ns_level=1)
+    h = e.handles[0]
     out = np.zeros_like(near)
     _drive_single(L, wap_b200, h, far, near, 0, 40, out)
     big = np.zeros(480, np.int16)
@@ -427,16 +429,9 @@ def test_render_format_differing_from_capture_is_refused_not_reinterpreted(api_l
         assert L.wap_process_reverse_stream_i16(h, p(big), 480, sc48, sc48, p(big), 480) == 7   # UnsupportedConfig
     _drive_single(L, wap_b200, h, far, near, 40, 80, out)
     assert np.array_equal(out, ref_run)            # the refused calls changed nothing
-    sc16 = _sc(wap_b200, 16000)
-    assert L.wap_initialize(h, sc16, sc16, sc48, sc48) == 7
-    L.wap_destroy(h)
-    # render first, at a format the later capture stream does not have: refused at the capture call
-    h = L.wap_create_with_config(wap_b200.make_config(L, aec=True, ns=True, ns_level=1))
-    assert L.wap_process_reverse_stream_i16(h, p(big), 480, sc48, sc48, p(big), 480) == 0
-    o = np.zeros(160, np.int16)
-    assert L.wap_process_stream_i16(h, p(near[:160].copy()), 160, sc16, sc16, p(o), 160) == 7
-    assert L.wap_process_stream_i16(h, p(near[:160].copy()), 160, sc16, sc16, p(o), 160) == 0   # queue was dropped
-    L.wap_destroy(h)
+    o = np.zeros(480, np.int16)
+    assert L.wap_process_stream_i16(h, p(big), 480, sc48, sc48, p(o), 480) == 5   # BadStreamParameter: fixed formats
+    e.close()
 
 
 def test_process_streams_rejects_engine_less_and_duplicate_handles(api_lib):

@@ -60,6 +60,13 @@ WAP_DEV float front_load_sample(const void* src, size_t leg, int len, int fmt, i
   return v * 32768.f;
 }
 
+// Channel selection for the first channel of the capture AudioBuffer (audio_buffer.cc:116-140,234-300):
+// an input with more channels than the buffer is downmixed on the way in -- the average of all input
+// channels, or the first one with capture_downmix_method = UseFirstChannel; otherwise channel 0.
+WAP_DEV int capture_first_channel(const EngineConfig& cfg) {
+  return (cfg.in_channels > cfg.channels && !cfg.downmix_first) ? -1 : 0;
+}
+
 // RenderDelayBufferImpl::Insert for render block `x` (64 samples, thread-local):
 // scalar bookkeeping, decimation into the low-rate ring, and the record that tells
 // k_echo where the block, its FFT and its spectrum go.
@@ -164,7 +171,7 @@ WAP_DEV void front_capture_prefilter(const TickArgs& a, int idx) {
     ScalerRun pre = scaler_begin(lv.pre_prev, lv.pre_target, flen);
     if (!cfg.levels_enabled) pre.mode = 0;
     for (int i = 0; i < flen; ++i) {
-      float v = front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 0);
+      float v = front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.in_channels, capture_first_channel(cfg));
       if (cfg.hpf_enabled) {
         v = biquad_step(hc[0], h0, v);
         v = biquad_step(hc[1], h1, v);
@@ -185,7 +192,7 @@ WAP_DEV void front_capture_prefilter(const TickArgs& a, int idx) {
       if (!cfg.levels_enabled) pre1.mode = 0;
       for (int i = 0; i < flen; ++i) {
         float v = a.rs_capture1 ? a.rs_capture1[(size_t)idx * flen + i]
-                                : front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.channels, 1);
+                                : front_load_sample(a.capture, idx, flen, a.fmt, i, cfg.in_channels, 1);
         if (cfg.hpf_enabled) {
           v = biquad_step(hc[0], g0, v);
           v = biquad_step(hc[1], g1, v);
@@ -213,7 +220,7 @@ WAP_DEV void front_capture_prefilter(const TickArgs& a, int idx) {
   }
 
 // True for legs whose band split runs in k_split (warp per leg) in front of k_front: 48 kHz AEC3.
-WAP_DEV bool front_presplit(const EngineConfig& cfg) { return cfg.num_bands == 3 && cfg.aec_enabled && !cfg.resample; }
+WAP_DEV bool front_presplit(const EngineConfig& cfg) { return cfg.num_bands == 3 && cfg.aec_enabled && !cfg.pre_stage; }
 
 // The front end of one tick for leg `idx` (thread-private).
 WAP_DEV void front_leg(const TickArgs& a, int idx) {
@@ -248,12 +255,12 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
       // AudioBuffer::SplitIntoFrequencyBands on the render side (audio_processing_impl.cc:1660-1664)
       for (int i = 0; i < flen; ++i) sub[i % kFrame] = 0.f, frame[i] = 0.f;
       float* full = ts.capture_frame;  // borrowed as the thread's 320/480-sample input buffer
-      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+      for (int i = 0; i < flen; ++i) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.render_channels, -1);
       if (B == 3) three_band_analysis_thread(full, frame, sub, st.render_bands.analysis);
       else two_band_analysis_thread(full, frame, &st.render_bands.analysis[0][0]);
       band0 = frame;
     } else {
-      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+      for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.render_channels, -1);
       band0 = frame;
     }
     const int L = s.render_blocker_len;

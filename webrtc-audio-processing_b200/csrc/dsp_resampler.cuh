@@ -23,7 +23,7 @@ namespace wap {
 constexpr int kRsKernelSize = 32;    // SincResampler::kKernelSize
 constexpr int kRsOffsetCount = 32;   // SincResampler::kKernelOffsetCount
 constexpr int kRsTableFloats = kRsKernelSize * (kRsOffsetCount + 1);
-constexpr int kRsMaxRequest = 480;   // API / processing rates up to 48 kHz
+constexpr int kRsMaxRequest = 960;   // API rates up to 96 kHz (processing rates up to 48 kHz)
 
 // One PushSincResampler (+ its SincResampler).
 struct alignas(16) ResamplerState {

@@ -102,11 +102,21 @@ using wap::StreamState;
 
 constexpr int kMaxChunks = 8;
 
+// The three API formats of a leg: capture input, capture output, render (reverse) input.
+struct WapFormats {
+  WapStreamConfig in, out, render;
+};
+inline bool same_format(const WapStreamConfig& a, const WapStreamConfig& b) {
+  return a.sample_rate_hz == b.sample_rate_hz && a.num_channels == b.num_channels;
+}
+inline WapFormats uniform_formats(const WapStreamConfig& f) { return WapFormats{f, f, f}; }
+
 struct WapEngine {
   int device = 0;
   int capacity = 0;
   WapConfig config{};
-  WapStreamConfig format{};
+  WapStreamConfig format{};   // capture input format
+  WapFormats formats{};       // capture input, capture output, render input
   EngineConfig cfg{};
   StreamState* d_states = nullptr;
   wap::UpperBandState* d_upper = nullptr;  // 32 / 48 kHz AEC3 engines only
@@ -131,7 +141,9 @@ struct WapEngine {
   std::vector<unsigned char> leg_delay_set; // was_stream_delay_set (cleared by every capture frame)
   std::atomic<int> dirty_legs{0};           // handles whose capture_output_used is not yet in the slab
   int64_t launches = 0;
-  int frame_len = 0;  // samples per frame (all channels)
+  int frame_len = 0;   // samples per capture input frame (all channels)
+  int out_len = 0;     // ... per output frame
+  int render_len = 0;  // ... per render frame
   int echo_scratch_floats = 0;
   // optional per-kernel timing (bench roofline): events around the three tick kernels
   bool timing = false;
@@ -149,7 +161,7 @@ struct WapEngine {
   WapEchoCanceller3Config aec3_config{};
   // resampled engines (API rate != processing rate)
   wap::ResamplerState* d_rs = nullptr;   // [capacity][kRsPerLeg]
-  float* d_rs_kernels = nullptr;         // in | out tables
+  float* d_rs_kernels = nullptr;         // in | out | render tables
   float* d_rs_render = nullptr;          // [staged][proc frame]
   float* d_rs_capture = nullptr;
   float* d_rs_capture1 = nullptr;        // stereo: second capture channel
@@ -162,7 +174,7 @@ struct WapEngine {
   wap::Ec3Params ep_mc = wap::ec3_default_params();
   wap::McParams mcp[2] = {};
   int mc_front_floats = 0, mc_echo_floats = 0, mc_echo_wpb = 4;
-  double rs_ratio_in = 1.0, rs_ratio_out = 1.0;
+  double rs_ratio_in = 1.0, rs_ratio_out = 1.0, rs_ratio_render = 1.0;
   int forced_chunks = 0;  // wap_engine_set_pipeline_chunks; 0 = automatic
   // host-buffer entry point, large batches: copies of one half overlap the kernels of the other
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -220,46 +232,77 @@ WapError check_device() {
   return WapError::None;
 }
 
-// SuitableProcessRate (audio_processing_impl.cc:92-107) restricted to the
-// native-rate config classes of SURVEY.md section 8.
-WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConfig* out) {
-  if (f.sample_rate_hz < 8000 || f.sample_rate_hz > 384000) return WapError::BadSampleRate;
-  if (f.num_channels <= 0) return WapError::BadNumberChannels;
+// API rates the resamplers are sized for (kRsMaxRequest samples per 10 ms).
+constexpr int kMaxApiRate = wap::kRsMaxRequest * 100;
+
+// SuitableProcessRate / InitializeLocked (audio_processing_impl.cc:92-107,527-692) for the config
+// classes of SURVEY.md section 8.
+WapError resolve_config(const WapConfig& c, const WapFormats& fm, EngineConfig* out) {
+  const WapStreamConfig& f = fm.in;
+  for (const WapStreamConfig* s : {&fm.in, &fm.out, &fm.render}) {
+    if (s->sample_rate_hz < 8000 || s->sample_rate_hz > 384000) return WapError::BadSampleRate;
+    if (s->num_channels <= 0) return WapError::BadNumberChannels;
+  }
+  if (fm.out.num_channels != 1 && fm.out.num_channels != fm.in.num_channels) return WapError::BadNumberChannels;
   EngineConfig e{};
   // InitializeLocked (audio_processing_impl.cc:632-692): the processing rate is the lowest native
-  // rate that covers the API rate, capped by maximum_internal_processing_rate when a multi-band
-  // submodule is active.
-  if (f.sample_rate_hz % 100 != 0 || f.sample_rate_hz > 48000) return WapError::UnsupportedConfig;
+  // rate that covers the lower of the capture input and output rates, capped by
+  // maximum_internal_processing_rate when a multi-band submodule is active; with AEC3 the render
+  // stream is processed at the same rate.
+  for (const WapStreamConfig* s : {&fm.in, &fm.out, &fm.render})
+    if (s->sample_rate_hz % 100 != 0 || s->sample_rate_hz > kMaxApiRate) return WapError::UnsupportedConfig;
   if (c.pipeline_maximum_internal_processing_rate != 32000 && c.pipeline_maximum_internal_processing_rate != 48000)
     return WapError::UnsupportedConfig;
   const bool multi_band = c.high_pass_filter_enabled || c.noise_suppression_enabled || c.echo_canceller_enabled;
   const int uppermost = multi_band ? c.pipeline_maximum_internal_processing_rate : 48000;
+  const int min_rate = std::min(fm.in.sample_rate_hz, fm.out.sample_rate_hz);
   int proc = uppermost;
   for (int rate : {16000, 32000, 48000}) {
     if (rate >= uppermost) { proc = uppermost; break; }
-    if (rate >= f.sample_rate_hz) { proc = rate; break; }
+    if (rate >= min_rate) { proc = rate; break; }
   }
   e.num_bands = proc / 16000;
-  e.api_frame = f.sample_rate_hz / 100;
-  e.resample = proc != f.sample_rate_hz ? 1 : 0;
-  e.fullband_out = (proc < f.sample_rate_hz && f.sample_rate_hz == 48000) ? 1 : 0;
+  e.api_frame = fm.in.sample_rate_hz / 100;
+  e.out_frame = fm.out.sample_rate_hz / 100;
+  e.render_frame = fm.render.sample_rate_hz / 100;
+  e.resample = proc != fm.in.sample_rate_hz ? 1 : 0;
+  e.resample_render = (c.echo_canceller_enabled && proc != fm.render.sample_rate_hz) ? 1 : 0;
+  e.pre_stage = (e.resample || e.resample_render) ? 1 : 0;
+  e.fullband_out = (proc < fm.out.sample_rate_hz && fm.out.sample_rate_hz == 48000) ? 1 : 0;
+  e.resample_out = (proc != fm.out.sample_rate_hz && !e.fullband_out) ? 1 : 0;
   e.hpf_rate = e.fullband_out ? 48000 : proc;
-  // Multi-channel frames are downmixed for processing and the mono result is copied to every
-  // output channel (the default pipeline); true multi-channel processing is SURVEY 8 cfg4.
-  // Stereo needs AEC3 (without it the reference runs NS / AGC2 on both channels).
-  // pipeline.multi_channel_render / _capture only matter for frames with more than one channel (mono
-  // legs run the mono EchoCanceller3Config whatever the flags say: config_selector.cc:44-58).
-  if (f.num_channels > 2 || (f.num_channels == 2 && !c.echo_canceller_enabled)) return WapError::UnsupportedConfig;
-  if (f.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture)) {
+  e.in_channels = fm.in.num_channels;
+  e.render_channels = fm.render.num_channels;
+  e.downmix_first = c.pipeline_capture_downmix_method == WapDownmixMethod::UseFirstChannel ? 1 : 0;
+  // The capture_fullband_audio buffer is filled from the capture input (resampled to 48 kHz when the
+  // input has another rate) and comes back unprocessed while the output is muted: only built for an
+  // input that already has the output's format.
+  if (e.fullband_out && !same_format(fm.in, fm.out)) return WapError::UnsupportedConfig;
+  // 48 kHz AEC3 runs the PostFilter and the output conversion in k_post: the output must be 48 kHz too.
+  if (e.num_bands == 3 && c.echo_canceller_enabled && e.resample_out) return WapError::UnsupportedConfig;
+  // The capture AudioBuffer has the OUTPUT's channel count (an input with more channels is downmixed on
+  // the way in).  Two-channel buffers are processed as the default pipeline does -- first channel
+  // only, mono result copied to both output channels -- or, with pipeline.multi_channel_render /
+  // _capture, truly multi-channel.  Stereo buffers need AEC3 (without it the reference
+  // runs NS / AGC2 on both channels).  The flags only matter for frames with more than one channel
+  // (mono legs run the mono EchoCanceller3Config whatever they say: config_selector.cc:44-58).
+  const int buf_channels = fm.out.num_channels;
+  if (buf_channels > 2 || fm.in.num_channels > 8 || fm.render.num_channels > 8 ||
+      (buf_channels == 2 && !c.echo_canceller_enabled))
+    return WapError::UnsupportedConfig;
+  if (buf_channels == 2 && fm.render.num_channels != 2 && c.echo_canceller_enabled &&
+      (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture))
+    return WapError::UnsupportedConfig;
+  if (buf_channels == 2 && fm.render.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture)) {
     // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) with or
-    // without the noise suppressor, at a native rate of 16 or 48 kHz.
+    // without the noise suppressor, at a native rate of 16 or 48 kHz, one format for all three streams.
     if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) ||
-        c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.resample ||
-        e.num_bands == 2)
+        c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.pre_stage ||
+        e.resample_out || e.num_bands == 2 || !same_format(fm.in, fm.out) || !same_format(fm.in, fm.render))
       return WapError::UnsupportedConfig;
     e.mc = 1;
   }
-  e.channels = f.num_channels;
+  e.channels = buf_channels;
   e.levels_enabled = (c.pre_amplifier_enabled || c.capture_level_adjustment_enabled) ? 1 : 0;
   e.post_gain_enabled = c.capture_level_adjustment_enabled ? 1 : 0;
   // capture level adjustment: pre / post gains; the analog mic gain emulation needs an input volume
@@ -296,28 +339,43 @@ WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConf
   e.agc2_enabled = c.gain_controller2_enabled ? 1 : 0;
   e.split_bands = (e.num_bands >= 2 && (c.high_pass_filter_enabled || e.ns_enabled || e.aec_enabled)) ? 1 : 0;
   e.agc2_fixed_gain = powf(10.0f, c.gain_controller2_fixed_digital_gain_db / 20.0f);  // DbToRatio (audio_util.h:85-87)
-  e.reinit_on_first_capture = (c.noise_suppression_enabled || c.gain_controller2_enabled ||
-                               f.sample_rate_hz != 16000 || f.num_channels != 1) ? 1 : 0;
+  // The constructor's api_format is 16 kHz mono for every stream.  MaybeInitializeCapture re-initialises
+  // when the capture input / output formats differ from it, or when UpdateActiveSubmoduleStates() sees
+  // the submodules the constructor created for the first time (audio_processing_impl.cc:894-925) --
+  // unless a render call with another format came first: MaybeInitializeRender's InitializeLocked() has
+  // then already taken note of them (:543-556,632-633), and render audio queued before the first
+  // capture call survives.
+  const bool capture_default = fm.in.sample_rate_hz == 16000 && fm.in.num_channels == 1 &&
+                               fm.out.sample_rate_hz == 16000 && fm.out.num_channels == 1;
+  const bool render_default = fm.render.sample_rate_hz == 16000 && fm.render.num_channels == 1;
+  e.reinit_on_first_capture =
+      (!capture_default || ((c.noise_suppression_enabled || c.gain_controller2_enabled) && render_default)) ? 1 : 0;
   e.cng_noise_floor = 64.f * powf(10.f, (90.30899869919436f + -96.03406f) * 0.1f);
   *out = e;
   return WapError::None;
 }
 
+WapError resolve_config(const WapConfig& c, const WapStreamConfig& f, EngineConfig* out) {
+  return resolve_config(c, uniform_formats(f), out);
+}
+
 WapError ensure_staging(WapEngine* e, size_t n) {
   if (n <= e->staged_streams) return WapError::None;
   size_t cap = std::max<size_t>(n, std::min<size_t>((size_t)e->capacity, std::max<size_t>(64, 2 * e->staged_streams)));
-  const size_t fb = (size_t)e->frame_len * sizeof(float);
+  const size_t fb = (size_t)e->frame_len * sizeof(float);     // capture input
+  const size_t rfb = (size_t)e->render_len * sizeof(float);   // render
+  const size_t ofb = (size_t)e->out_len * sizeof(float);      // output
   const size_t pb = (size_t)wap::kFrame * e->cfg.num_bands * sizeof(float);
   // Allocate the new buffers first and swap them in only when every allocation succeeded: a failure
   // leaves the engine with its old (smaller) staging area instead of dangling pointers.
   void *n_render = nullptr, *n_capture = nullptr, *n_out = nullptr, *n_pinned = nullptr;
   int *n_slots = nullptr, *n_delays = nullptr;
   float *n_rs_render = nullptr, *n_rs_capture = nullptr, *n_rs_capture1 = nullptr;
-  bool ok = cudaMalloc(&n_render, cap * fb) == cudaSuccess && cudaMalloc(&n_capture, cap * fb) == cudaSuccess &&
-            cudaMalloc(&n_out, cap * fb) == cudaSuccess && cudaMalloc((void**)&n_slots, cap * sizeof(int)) == cudaSuccess &&
+  bool ok = cudaMalloc(&n_render, cap * rfb) == cudaSuccess && cudaMalloc(&n_capture, cap * fb) == cudaSuccess &&
+            cudaMalloc(&n_out, cap * ofb) == cudaSuccess && cudaMalloc((void**)&n_slots, cap * sizeof(int)) == cudaSuccess &&
             cudaMalloc((void**)&n_delays, cap * sizeof(int)) == cudaSuccess &&
-            cudaMallocHost(&n_pinned, cap * (3 * fb + 2 * sizeof(int))) == cudaSuccess;
-  if (ok && e->cfg.resample) {
+            cudaMallocHost(&n_pinned, cap * (rfb + fb + ofb + 2 * sizeof(int))) == cudaSuccess;
+  if (ok && e->cfg.pre_stage) {
     ok = cudaMalloc((void**)&n_rs_render, cap * pb) == cudaSuccess && cudaMalloc((void**)&n_rs_capture, cap * pb) == cudaSuccess;
     if (ok && e->cfg.channels == 2) ok = cudaMalloc((void**)&n_rs_capture1, cap * pb) == cudaSuccess;
   }
@@ -333,7 +391,7 @@ WapError ensure_staging(WapEngine* e, size_t n) {
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   e->d_render = n_render; e->d_capture = n_capture; e->d_out = n_out; e->d_slots = n_slots; e->d_delays = n_delays;
   e->h_pinned = n_pinned;
-  if (e->cfg.resample) {
+  if (e->cfg.pre_stage) {
     cudaFree(e->d_rs_render); cudaFree(e->d_rs_capture); cudaFree(e->d_rs_capture1);
     e->d_rs_render = n_rs_render; e->d_rs_capture = n_rs_capture; e->d_rs_capture1 = n_rs_capture1;
   }
@@ -718,16 +776,20 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     WAP_CUDA(cudaGetLastError());
     return WapError::None;
   }
-  if (e->cfg.resample) {
-    // API-rate frames -> processing-rate frames; k_front then reads those (already FloatS16).
+  if (e->d_rs) {   // some stream of the leg is resampled
     a.rs = e->d_rs;
+    a.rs_kernel_in = e->d_rs_kernels;
+    a.rs_kernel_out = e->d_rs_kernels + wap::kRsTableFloats;
+    a.rs_kernel_render = e->d_rs_kernels + 2 * wap::kRsTableFloats;
+    a.rs_ratio_in = e->rs_ratio_in;
+    a.rs_ratio_out = e->rs_ratio_out;
+    a.rs_ratio_render = e->rs_ratio_render;
+  }
+  if (e->cfg.pre_stage) {
+    // API-rate frames -> processing-rate frames; k_front then reads those (already FloatS16).
     a.rs_capture1 = e->d_rs_capture1;
     a.rs_render = e->d_rs_render;
     a.rs_capture = e->d_rs_capture;
-    a.rs_kernel_in = e->d_rs_kernels;
-    a.rs_kernel_out = e->d_rs_kernels + wap::kRsTableFloats;
-    a.rs_ratio_in = e->rs_ratio_in;
-    a.rs_ratio_out = e->rs_ratio_out;
     WAP_LAUNCH(wap::k_resample, grid_for(n), wpb * 32, (size_t)wpb * 2 * wap::kRsMaxRequest * sizeof(float), e->stream, a);
     e->launches++;
     wap::TickArgs af = a;
@@ -848,9 +910,19 @@ WapEngine* wap_engine_create(int cuda_device, int32_t max_streams, WapConfig con
 WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_streams, WapConfig config, WapStreamConfig fmt,
                                               const WapEchoCanceller3Config* aec3_config,
                                               const WapEchoCanceller3Config* aec3_multichannel_config) {
+  return wap_engine_create_with_formats(cuda_device, max_streams, config, fmt, fmt, fmt, aec3_config,
+                                        aec3_multichannel_config);
+}
+
+WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, WapConfig config, WapStreamConfig input,
+                                          WapStreamConfig output, WapStreamConfig reverse_input,
+                                          const WapEchoCanceller3Config* aec3_config,
+                                          const WapEchoCanceller3Config* aec3_multichannel_config) {
   if (check_device() != WapError::None) return nullptr;
   EngineConfig cfg{};
-  WapError err = resolve_config(config, fmt, &cfg);
+  const WapFormats formats{input, output, reverse_input};
+  const WapStreamConfig fmt = input;
+  WapError err = resolve_config(config, formats, &cfg);
   const WapEchoCanceller3Config aec3 = aec3_config ? *aec3_config : ec3_config_default();
   // AudioProcessingImpl::InitializeEchoController (audio_processing_impl.cc:1928-1943): the default
   // multichannel config only when the user set neither; a mono config alone serves both.
@@ -885,8 +957,11 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
   e->capacity = max_streams;
   e->config = config;
   e->format = fmt;
+  e->formats = formats;
   e->cfg = cfg;
-  e->frame_len = fmt.sample_rate_hz / 100 * fmt.num_channels;
+  e->frame_len = input.sample_rate_hz / 100 * input.num_channels;
+  e->out_len = output.sample_rate_hz / 100 * output.num_channels;
+  e->render_len = reverse_input.sample_rate_hz / 100 * reverse_input.num_channels;
   e->aec3_config = aec3;
   e->ep = ec3_params_from_config(aec3);
   e->ec3_runtime = config.echo_canceller_enabled && (cfg.mc || !wap::same_ec3_params(e->ep, wap::ec3_default_params()));
@@ -925,14 +1000,16 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
     const size_t ub = (size_t)max_streams * sizeof(wap::UpperBandState);
     ok = cudaMalloc((void**)&e->d_upper, ub) == cudaSuccess && cudaMemset(e->d_upper, 0, ub) == cudaSuccess;
   }
-  if (ok && cfg.resample) {
+  if (ok && (cfg.pre_stage || cfg.resample_out || cfg.fullband_out)) {
     const size_t rb = (size_t)max_streams * wap::kRsPerLeg * sizeof(wap::ResamplerState);
     const int pf = wap::kFrame * cfg.num_bands;
     e->rs_ratio_in = (double)cfg.api_frame * 1.0 / pf;  // source_frames * 1.0 / destination_frames
-    e->rs_ratio_out = (double)pf * 1.0 / cfg.api_frame;
-    std::vector<float> tables(2 * wap::kRsTableFloats);
+    e->rs_ratio_out = (double)pf * 1.0 / cfg.out_frame;
+    e->rs_ratio_render = (double)cfg.render_frame * 1.0 / pf;
+    std::vector<float> tables(3 * wap::kRsTableFloats);
     build_sinc_kernel(e->rs_ratio_in, tables.data());
     build_sinc_kernel(e->rs_ratio_out, tables.data() + wap::kRsTableFloats);
+    build_sinc_kernel(e->rs_ratio_render, tables.data() + 2 * wap::kRsTableFloats);
     ok = cudaMalloc((void**)&e->d_rs, rb) == cudaSuccess && cudaMemset(e->d_rs, 0, rb) == cudaSuccess &&
          cudaMalloc((void**)&e->d_rs_kernels, tables.size() * sizeof(float)) == cudaSuccess &&
          cudaMemcpy(e->d_rs_kernels, tables.data(), tables.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -1201,36 +1278,41 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
   WapError err = ensure_staging(e, n);
   if (err != WapError::None) return err;
   const size_t esz = fmt == WapSampleFormat::I16 ? sizeof(int16_t) : sizeof(float);
-  const size_t bytes = (size_t)n * e->frame_len * esz;
+  // the three streams of a leg may have different formats (wap_engine_create_with_formats)
+  const size_t bytes = (size_t)n * e->frame_len * esz;        // capture input
+  const size_t rbytes = (size_t)n * e->render_len * esz;      // render
+  const size_t obytes = (size_t)n * e->out_len * esz;         // output
   unsigned char* hp = static_cast<unsigned char*>(e->h_pinned);
-  const size_t stride = e->staged_streams * e->frame_len * sizeof(float);
+  unsigned char* hp_capture = hp + e->staged_streams * e->render_len * sizeof(float);
+  unsigned char* hp_out = hp_capture + e->staged_streams * e->frame_len * sizeof(float);
   // Page-locked caller buffers are copied from / to directly; pageable ones go through the
   // engine's pinned staging area.
   const void* src_r = render;
   const void* src_c = capture;
   if (render && !is_pinned_host(render)) {
-    memcpy(hp, render, bytes);
+    memcpy(hp, render, rbytes);
     src_r = hp;
   }
   if (!is_pinned_host(capture)) {
-    memcpy(hp + stride, capture, bytes);
-    src_c = hp + stride;
+    memcpy(hp_capture, capture, bytes);
+    src_c = hp_capture;
   }
   const bool out_pinned = is_pinned_host(out);
-  void* dst_o = out_pinned ? out : (void*)(hp + 2 * stride);
+  void* dst_o = out_pinned ? out : (void*)hp_out;
   const int chunks = pipeline_chunks(e, n);
   if (chunks <= 1) {
-    if (render) WAP_CUDA(cudaMemcpyAsync(e->d_render, src_r, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (render) WAP_CUDA(cudaMemcpyAsync(e->d_render, src_r, rbytes, cudaMemcpyHostToDevice, e->stream));
     WAP_CUDA(cudaMemcpyAsync(e->d_capture, src_c, bytes, cudaMemcpyHostToDevice, e->stream));
     err = wap_process_streams_device(e, handles, n, render ? e->d_render : nullptr, e->d_capture, e->d_out, fmt);
     if (err != WapError::None) return err;
-    WAP_CUDA(cudaMemcpyAsync(dst_o, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    WAP_CUDA(cudaMemcpyAsync(dst_o, e->d_out, obytes, cudaMemcpyDeviceToHost, e->stream));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
   } else {
     // Large batch: the legs are cut into `chunks` ranges; host->device copies run on one copy
     // stream, the tick kernels of each range on the engine stream, device->host copies on a
     // second copy stream, so the PCIe traffic of one range hides behind the kernels of another.
-    const size_t leg_bytes = (size_t)e->frame_len * esz;
+    const size_t leg_bytes = (size_t)e->frame_len * esz, rleg_bytes = (size_t)e->render_len * esz,
+                 oleg_bytes = (size_t)e->out_len * esz;
     WAP_CUDA(cudaEventRecord(e->ev_start, e->stream));
     WAP_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
     // Range boundaries.  Only two copies are ever exposed: the host->device copy of the FIRST range
@@ -1258,7 +1340,8 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
       const int off = bounds[c], cnt = bounds[c + 1] - off;
       const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
       if (render)
-        WAP_CUDA(cudaMemcpyAsync((char*)e->d_render + bo, (const char*)src_r + bo, bc, cudaMemcpyHostToDevice, e->copy_in));
+        WAP_CUDA(cudaMemcpyAsync((char*)e->d_render + (size_t)off * rleg_bytes, (const char*)src_r + (size_t)off * rleg_bytes,
+                                 (size_t)cnt * rleg_bytes, cudaMemcpyHostToDevice, e->copy_in));
       WAP_CUDA(cudaMemcpyAsync((char*)e->d_capture + bo, (const char*)src_c + bo, bc, cudaMemcpyHostToDevice, e->copy_in));
       WAP_CUDA(cudaEventRecord(e->ev_in[c], e->copy_in));
     }
@@ -1269,21 +1352,22 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     if (err != WapError::None) return err;
     for (int c = 0; c < nr; ++c) {
       const int off = bounds[c], cnt = bounds[c + 1] - off;
-      const size_t bo = (size_t)off * leg_bytes, bc = (size_t)cnt * leg_bytes;
+      const size_t bo = (size_t)off * leg_bytes, ro = (size_t)off * rleg_bytes, oo = (size_t)off * oleg_bytes;
       WAP_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in[c], 0));
       err = launch_tick(e, e->d_slots + off, d_delays ? d_delays + off : nullptr, uniform_delay, cnt,
-                        render ? (const void*)((const char*)e->d_render + bo) : nullptr, (const char*)e->d_capture + bo,
-                        (char*)e->d_out + bo, fmt);
+                        render ? (const void*)((const char*)e->d_render + ro) : nullptr, (const char*)e->d_capture + bo,
+                        (char*)e->d_out + oo, fmt);
       if (err != WapError::None) return err;
       WAP_CUDA(cudaEventRecord(e->ev_done[c], e->stream));
       WAP_CUDA(cudaStreamWaitEvent(e->copy_out, e->ev_done[c], 0));
-      WAP_CUDA(cudaMemcpyAsync((char*)dst_o + bo, (const char*)e->d_out + bo, bc, cudaMemcpyDeviceToHost, e->copy_out));
+      WAP_CUDA(cudaMemcpyAsync((char*)dst_o + oo, (const char*)e->d_out + oo, (size_t)cnt * oleg_bytes, cudaMemcpyDeviceToHost,
+                               e->copy_out));
     }
     for (int i = 0; i < n; ++i) e->leg_delay_set[e->last_slots[i]] = 0;  // audio_processing_impl.cc:1556
     WAP_CUDA(cudaStreamSynchronize(e->copy_out));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
   }
-  if (!out_pinned) memcpy(out, hp + 2 * stride, bytes);
+  if (!out_pinned) memcpy(out, hp_out, obytes);
   if (per_stream_err) for (int i = 0; i < n; ++i) per_stream_err[i] = WapError::None;
   return WapError::None;
 }

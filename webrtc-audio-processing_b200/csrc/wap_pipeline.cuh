@@ -93,7 +93,7 @@ WAP_DEV void split_tick(const TickArgs& a, int idx, float* scratch) {
   float* sub = scratch + 2 * flen;
   const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
   if (a.render && render_live) {
-    for (int i = lane; i < flen; i += 32) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.channels, -1);
+    for (int i = lane; i < flen; i += 32) full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.render_channels, -1);
     __syncwarp();
     three_band_analysis(full, bands, sub, st.render_bands.analysis);
     for (int i = lane; i < flen; i += 32) up.render_frame[i] = bands[i];
@@ -118,8 +118,7 @@ WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
   const int lane = lane_id();
   const int slot = a.slots ? a.slots[idx] : idx;
   const StreamState& st = a.states[slot];
-  const int pf = kFrame * cfg.num_bands, af = cfg.api_frame;
-  const ResamplerParams p{af, pf, a.rs_ratio_in, a.rs_kernel_in};
+  const int pf = kFrame * cfg.num_bands;
   float* src = scratch;
   float* dst = scratch + kRsMaxRequest;
   // Render frames in front of the first capture frame are lost to the re-initialisation
@@ -129,13 +128,23 @@ WAP_DEV void resample_in_tick(const TickArgs& a, int idx, float* scratch) {
   for (int which = 0; which < n_in; ++which) {
     const void* in = which == 0 ? a.render : a.capture;
     if (!in || (which == 0 && (!cfg.aec_enabled || !render_live))) continue;
+    // render: its own rate and channel count, averaged to mono; capture: the first buffer channel
+    // (downmixed when the input has more channels than the buffer); which == 2: the second channel of
+    // a stereo buffer.  A stream that already has the processing rate is only converted to FloatS16.
+    const int af = which == 0 ? cfg.render_frame : cfg.api_frame;
+    const int C = which == 0 ? cfg.render_channels : cfg.in_channels;
+    const int ch = which == 0 ? (C == 1 ? 0 : -1) : (which == 1 ? (C == 1 ? 0 : capture_first_channel(cfg)) : 1);
+    const bool resampled = which == 0 ? cfg.resample_render != 0 : cfg.resample != 0;
+    float* out = (which == 0 ? a.rs_render : (which == 1 ? a.rs_capture : a.rs_capture1)) + (size_t)idx * pf;
     __syncwarp();
-    // render: averaged to mono; capture: first channel (which == 2: the second one, stereo only)
-    for (int i = lane; i < af; i += 32)
-      src[i] = load_raw_sample(in, idx, af, a.fmt, i, cfg.channels, which == 0 ? (cfg.channels == 1 ? 0 : -1) : which - 1);
+    if (!resampled) {
+      for (int i = lane; i < pf; i += 32) out[i] = front_load_sample(in, idx, pf, a.fmt, i, C, ch);
+      continue;
+    }
+    const ResamplerParams p{af, pf, which == 0 ? a.rs_ratio_render : a.rs_ratio_in, which == 0 ? a.rs_kernel_render : a.rs_kernel_in};
+    for (int i = lane; i < af; i += 32) src[i] = load_raw_sample(in, idx, af, a.fmt, i, C, ch);
     __syncwarp();
     rs_push(which == 2 ? a.extra[slot].rs : a.rs[slot * kRsPerLeg + which], p, src, dst);
-    float* out = (which == 0 ? a.rs_render : (which == 1 ? a.rs_capture : a.rs_capture1)) + (size_t)idx * pf;
     for (int i = lane; i < pf; i += 32) {
       float v = dst[i];
       if (a.fmt == 1) {  // FloatToFloatS16 after the resampler (audio_buffer.cc:150-155)
@@ -162,12 +171,13 @@ enum EchoClass {
   kEchoClasses = 5
 };
 inline int echo_class_of(const EngineConfig& c) {
-  if (c.channels != 1) return kEchoGeneric;
-  if (c.num_bands == 1 && !c.resample) return kEchoMono16k;
+  // (k_echo starts behind the front end: only the output side of the formats matters to it)
+  if (c.channels != 1 || c.in_channels != 1) return kEchoGeneric;
+  if (c.num_bands == 1 && !c.resample_out) return kEchoMono16k;
   if (!c.split_bands) return kEchoGeneric;
-  if (c.num_bands == 3 && !c.resample) return kEchoMono48kNative;
-  if (c.num_bands == 2 && c.resample && c.fullband_out) return kEchoMono48kVia32k;
-  if (c.num_bands == 2 && !c.resample) return kEchoMono32k;
+  if (c.num_bands == 3 && !c.resample_out) return kEchoMono48kNative;
+  if (c.num_bands == 2 && c.fullband_out) return kEchoMono48kVia32k;
+  if (c.num_bands == 2 && !c.resample_out && !c.fullband_out) return kEchoMono32k;
   return kEchoGeneric;
 }
 
@@ -176,11 +186,12 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   EngineConfig cfg = a.cfg;
   if (kClass != kEchoGeneric) {
     cfg.channels = 1;
+    cfg.in_channels = 1;
     cfg.num_bands = kClass == kEchoMono16k ? 1 : (kClass == kEchoMono48kNative ? 3 : 2);
     cfg.split_bands = kClass == kEchoMono16k ? 0 : 1;
-    cfg.resample = kClass == kEchoMono48kVia32k ? 1 : 0;
+    cfg.resample_out = 0;
     cfg.fullband_out = kClass == kEchoMono48kVia32k ? 1 : 0;
-    if (kClass == kEchoMono48kVia32k) cfg.api_frame = 480;
+    if (kClass == kEchoMono48kVia32k) cfg.out_frame = 480;
   }
   const int B = cfg.num_bands;
   const int flen = kFrame * B;
@@ -261,14 +272,14 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     // capture_fullband_audio (audio_processing_impl.cc:1245-1253,1451-1460): a 48 kHz buffer that is
     // refreshed from the processed frame (resampled, AudioBuffer::CopyTo(AudioBuffer*)) only while
     // the output is used; otherwise it still holds the unprocessed input frame.
-    olen = cfg.api_frame;
+    olen = cfg.out_frame;
     if (output_used) {
       const ResamplerParams p{flen, olen, a.rs_ratio_out, a.rs_kernel_out};
       rs_push(a.rs[slot_rs + 2], p, full, tmp);
       for (int i = lane_id(); i < olen; i += 32) full[i] = tmp[i];
     } else {
       // Muted: the (multi-channel) input frame comes back, channel by channel.
-      const int total = olen * cfg.channels;
+      const int total = olen * cfg.channels;   // (this path requires input format == output format)
       for (int i = lane_id(); i < total; i += 32) {
         if (a.fmt == 0) {
           reinterpret_cast<int16_t*>(a.out)[(size_t)idx * total + i] = reinterpret_cast<const int16_t*>(a.capture)[(size_t)idx * total + i];
@@ -323,10 +334,10 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     if (lane_id() == 0) st.tick.pad_[0] = (!output_used_last_frame && output_used) ? 1 : 0;
     return;
   }
-  if (cfg.resample && !cfg.fullband_out) {
+  if (cfg.resample_out) {
     // AudioBuffer::CopyTo with an output resampler (audio_buffer.cc:156-176,314-372): the int16
     // interface resamples FloatS16 data and then rounds, the float interface scales first.
-    const int alen = cfg.api_frame;
+    const int alen = cfg.out_frame;
     __syncwarp();
     if (a.fmt == 1) {
       for (int i = lane_id(); i < flen; i += 32) {  // FloatS16ToFloat (audio_util.h:71-76)

@@ -368,12 +368,25 @@ struct EngineConfig {
   // render is averaged to mono (render AudioBuffer has one channel), capture keeps both channels
   // until AEC3's saturation test and then continues with the first one only
   // (audio_processing_impl.cc:585-594,1365-1373); the mono result goes to both output channels.
-  int channels;         // API channels of render, capture and output (1 or 2)
+  int channels;         // channels of the capture AudioBuffer = of the output stream (1 or 2)
   int levels_enabled;   // pre_amplifier.enabled || capture_level_adjustment.enabled
   int post_gain_enabled;  // capture_level_adjustment.enabled: kCapturePostGain is honoured
   // Stereo frames with pipeline.multi_channel_render and _capture on and AEC3: every channel is processed
   // (EchoCanceller3 with 2 capture and 1 or 2 render channels, wap_mc_state.h) -- BASELINE config 4.
   int mc;
+  // Formats that differ between the three streams of a leg (audio_processing_impl.cc:527-612,632-692;
+  // SURVEY 8(f)-2).  api_frame / resample describe the capture input, `channels` the capture buffer
+  // (= output) channels; the capture AudioBuffer downmixes an input with more channels on the way in
+  // (audio_buffer.cc:116-140,234-300: average, or the first channel with
+  // pipeline.capture_downmix_method = UseFirstChannel).
+  int in_channels;      // API channels of the capture input
+  int out_frame;        // samples per channel and 10 ms at the output rate
+  int resample_out;     // output rate != processing rate (not the capture_fullband_audio path)
+  int render_frame;     // samples per channel and 10 ms of the render (reverse) stream
+  int render_channels;  // API channels of the render stream (averaged to mono unless `mc`)
+  int resample_render;  // render rate != processing rate
+  int pre_stage;        // resample || resample_render: k_resample hands k_front processing-rate frames
+  int downmix_first;    // capture downmix takes the first channel instead of the average
 };
 
 // Every member of EngineConfig is a 4-byte scalar, so the struct has no padding bytes and two

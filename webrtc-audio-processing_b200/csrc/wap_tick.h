@@ -27,14 +27,15 @@ struct TickArgs {
   int fmt;                // 0 = int16, 1 = float [-1,1]  (k_front of a resampled engine: 2 = FloatS16 floats)
   EngineConfig cfg;
   Ec3Params ep;           // the engine's EchoCanceller3Config parameters (the default config for default engines)
-  // Resampled engines only (cfg.resample): per-leg resampler states [slot][kRsPerLeg], the
+  // Resampled engines only (cfg.pre_stage / resample_out / fullband_out): per-leg resampler states [slot][kRsPerLeg], the
   // processing-rate frames k_resample leaves for k_front (FloatS16 floats), kernels and ratios.
   ResamplerState* rs;
   float* rs_render;       // [n][proc frame]
   float* rs_capture;      // [n][proc frame]
-  const float* rs_kernel_in;
-  const float* rs_kernel_out;
-  double rs_ratio_in, rs_ratio_out;
+  const float* rs_kernel_in;      // capture input -> processing rate
+  const float* rs_kernel_out;     // processing rate -> output
+  const float* rs_kernel_render;  // render input -> processing rate
+  double rs_ratio_in, rs_ratio_out, rs_ratio_render;
   // Stereo engines only: second capture channel (high-pass state, input resampler, resampled frame).
   ExtraChannelState* extra;  // [slot]
   float* rs_capture1;        // [n][proc frame] or nullptr

@@ -182,7 +182,7 @@ EXPORTS = [
     "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state", "wap_stream_read_taps",
     "wap_echo_canceller3_config_default", "wap_echo_canceller3_config_default_multichannel", "wap_echo_canceller3_config_sizeof",
     "wap_echo_canceller3_config_validate", "wap_echo_canceller3_config_supported", "wap_create_with_aec3_config",
-    "wap_engine_create_with_aec3_config",
+    "wap_engine_create_with_aec3_config", "wap_engine_create_with_formats",
 ]
 
 _libs = {}
@@ -255,14 +255,18 @@ def load(path=None):
     L.wap_create_with_aec3_config.argtypes = [cfg, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_engine_create_with_aec3_config.restype = vp
     L.wap_engine_create_with_aec3_config.argtypes = [C.c_int, i32, cfg, sc, C.POINTER(ec3), C.POINTER(ec3)]
+    L.wap_engine_create_with_formats.restype = vp
+    L.wap_engine_create_with_formats.argtypes = [C.c_int, i32, cfg, sc, sc, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_version.restype = C.c_char_p
     _libs[path] = L
     return L
 
 
 def make_config(lib, aec=True, ns=True, ns_level=NS_MODERATE, max_rate=48000, hpf=False, agc2=False,
-                agc2_fixed_gain_db=0.0, pre_amp=None, pre_gain=None, post_gain=None, mc_render=False, mc_capture=False):
+                agc2_fixed_gain_db=0.0, pre_amp=None, pre_gain=None, post_gain=None, mc_render=False, mc_capture=False,
+                downmix=0):
     c = lib.wap_config_default()
+    c.pipeline_capture_downmix_method = int(downmix)   # 0: AverageChannels, 1: UseFirstChannel
     c.pipeline_multi_channel_render = bool(mc_render)
     c.pipeline_multi_channel_capture = bool(mc_capture)
     if pre_amp is not None:
@@ -304,7 +308,7 @@ class Engine:
     """Batched engine: `n` call legs of one config class on one GPU."""
 
     def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, aec3=None,
-                 aec3_multichannel=None, **cfg):
+                 aec3_multichannel=None, out_format=None, render_format=None, **cfg):
         """aec3: None (default EchoCanceller3Config), a dict of overrides keyed by the reference's member
         paths ("filter.refined.length_blocks": 10, ...) or a WapEchoCanceller3Config.  aec3_multichannel: the
         same for the multichannel config (overrides apply to CreateDefaultMultichannelConfig)."""
@@ -312,7 +316,23 @@ class Engine:
         self.rate, self.channels, self.n = rate, channels, n_streams
         self.frame = rate // 100 * channels
         self.config = make_config(self.lib, **cfg)
-        if aec3 is None and aec3_multichannel is None:
+        # out_format / render_format: (rate, channels) of the output / render stream when they differ from
+        # the capture input's (wap_engine_create_with_formats)
+        self.out_rate, self.out_channels = out_format or (rate, channels)
+        self.render_rate, self.render_channels = render_format or (rate, channels)
+        self.out_frame = self.out_rate // 100 * self.out_channels
+        if out_format is not None or render_format is not None:
+            def conv(c, mc):
+                if c is None:
+                    return None
+                return c if isinstance(c, WapEchoCanceller3Config) else make_aec3_config(self.lib, c, multichannel=mc)
+            self.aec3, self.aec3_mc = conv(aec3, False), conv(aec3_multichannel, True)
+            self.h = self.lib.wap_engine_create_with_formats(
+                device, capacity or n_streams, self.config, WapStreamConfig(rate, channels),
+                WapStreamConfig(self.out_rate, self.out_channels), WapStreamConfig(self.render_rate, self.render_channels),
+                C.byref(self.aec3) if self.aec3 is not None else None,
+                C.byref(self.aec3_mc) if self.aec3_mc is not None else None)
+        elif aec3 is None and aec3_multichannel is None:
             self.h = self.lib.wap_engine_create(device, capacity or n_streams, self.config,
                                                 WapStreamConfig(rate, channels))
         else:
@@ -387,7 +407,7 @@ class Engine:
         fmt = 0 if capture.dtype == np.int16 else 1
         if render is not None:
             render = np.ascontiguousarray(render, dtype=capture.dtype)
-        out = np.empty_like(capture)
+        out = np.empty_like(capture) if self.out_frame == self.frame else np.empty((self.n, self.out_frame), capture.dtype)
         err = self.lib.wap_process_streams(self.handles, self.n, _ptr(render), _ptr(capture), _ptr(out), fmt, None)
         if err:
             raise RuntimeError("wap_process_streams: " + ERRORS.get(err, str(err)))
