@@ -950,6 +950,12 @@ WAP_DEV void mc_echo_remover_process_capture(Aec3State& sh, McState& mc, const E
     McChan& ch = mc.chan[c];
     McChanVec& cv = mx.cv[c];
     mc_subtractor_process_channel(sh, rb, mc.filt[c], ch, mx.cs[c], sc, cv, R, s.capture_signal_saturation != 0);
+    // The estimator vectors the stages behind the linear filters read (per channel: H_error .. the
+    // time-domain memories; once per leg: StreamState::aec's), asked for now that the filter passes no
+    // longer stream through the L1 (same placement as the mono kernel, dsp_aec3_remover.cuh).
+    warp_prefetch_l1(ch.H_error, (int)(reinterpret_cast<const char*>(&ch + 1) - reinterpret_cast<const char*>(ch.H_error)));
+    if (c == C - 1)
+      warp_prefetch_l1(sh.H_error, (int)(reinterpret_cast<const char*>(sh.render_decimator) - reinterpret_cast<const char*>(sh.H_error)));
     // FormLinearFilterOutput (refined_filter_output_last_selected_ is one flag for all channels)
     {
       const float y2 = cv.metrics[0], e2_refined = cv.metrics[1], e2_coarse = cv.metrics[2], s2_refined = cv.metrics[3],

@@ -145,6 +145,7 @@ struct WapEngine {
   int out_len = 0;     // ... per output frame
   int render_len = 0;  // ... per render frame
   int echo_scratch_floats = 0;
+  int echo_smem_pad = 0;   // WAP_ECHO_SMEM_PAD_KB (occupancy experiments)
   // optional per-kernel timing (bench roofline): events around the three tick kernels
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -813,7 +814,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     e->launches++;
   }
   if (timing) cudaEventRecord(e->ev[2], e->stream);
-  const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float);
+  const size_t smem_e = (size_t)wpb * e->echo_scratch_floats * sizeof(float) + (size_t)e->echo_smem_pad;
   if (e->ec3_runtime) wap::launch_k_echo_rt(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   else wap::launch_k_echo(e->echo_class, grid_for(n), wpb * 32, smem_e, e->stream, a, e->echo_scratch_floats);
   e->launches++;
@@ -1050,7 +1051,9 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
     ok = cudaMemcpy(e->d_template, tmpl, sizeof(StreamState), cudaMemcpyHostToDevice) == cudaSuccess;
     delete tmpl;
   }
-  const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float);
+  // tuning knob: extra dynamic shared memory per k_echo CTA = fewer CTAs (legs in flight) per SM
+  if (const char* pad = getenv("WAP_ECHO_SMEM_PAD_KB")) e->echo_smem_pad = std::max(0, std::min(160, atoi(pad))) * 1024;
+  const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float) + (size_t)e->echo_smem_pad;
   const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
   if (ok && smem_e > 48 * 1024) ok = (e->ec3_runtime ? wap::set_k_echo_smem_rt((int)smem_e) : wap::set_k_echo_smem((int)smem_e)) == cudaSuccess;
   if (ok && smem_d > 48 * 1024) ok = (e->ec3_runtime ? wap::set_k_delay_smem_rt((int)smem_d) : wap::set_k_delay_smem((int)smem_d)) == cudaSuccess;
