@@ -88,8 +88,11 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
                     ("filter.use_linear_filter", False), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
-                    ("suppressor.use_subband_nearend_detection", True)):
+                    ("echo_audibility.use_stationarity_properties", True),
+                    ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
+        c.suppressor.use_subband_nearend_detection = True   # built with a smoother of at most three past blocks
+        assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 0
         wap_b200.ec3_set(c, path, v)
         assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 7, path
     c = L.wap_echo_canceller3_config_default()
@@ -194,3 +197,56 @@ def test_default_engines_run_the_compile_time_config_instances(api_lib):
     e = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=False, agc2=True)
     assert L.wap_engine_uses_runtime_aec3_parameters(e.h) == 0
     e.close()
+
+
+STRUCTURAL = {
+    # RenderWriter's high-pass filter on the echo reference (echo_canceller3.cc:718-737)
+    "render_high_pass": ({"filter.high_pass_filter_echo_reference": 1}, 16000),
+    "render_high_pass_48k": ({"filter.high_pass_filter_echo_reference": 1}, 48000),
+    # BlockDelayBuffer in front of ProcessCapture + its share of the external delay (block_delay_buffer.cc)
+    "fixed_capture_delay": ({"delay.fixed_capture_delay_samples": 200}, 16000),
+    "fixed_capture_delay_48k": ({"delay.fixed_capture_delay_samples": 333, "filter.high_pass_filter_echo_reference": 1}, 48000),
+    # SubbandNearendDetector in place of DominantNearendDetector (suppression_gain.cc:365-371)
+    "subband_nearend_detector": ({"suppressor.use_subband_nearend_detection": 1,
+                                  "suppressor.subband_nearend_detection.nearend_average_blocks": 3,
+                                  "suppressor.subband_nearend_detection.subband1.low": 1,
+                                  "suppressor.subband_nearend_detection.subband1.high": 12,
+                                  "suppressor.subband_nearend_detection.subband2.low": 20,
+                                  "suppressor.subband_nearend_detection.subband2.high": 44,
+                                  "suppressor.subband_nearend_detection.nearend_threshold": 3.0,
+                                  "suppressor.subband_nearend_detection.snr_threshold": 4.0}, 16000),
+    "subband_nearend_detector_no_smoothing_48k": ({"suppressor.use_subband_nearend_detection": 1,
+                                                   "suppressor.subband_nearend_detection.subband1.low": 2,
+                                                   "suppressor.subband_nearend_detection.subband1.high": 8,
+                                                   "suppressor.subband_nearend_detection.subband2.low": 9,
+                                                   "suppressor.subband_nearend_detection.subband2.high": 30,
+                                                   "suppressor.subband_nearend_detection.nearend_threshold": 50.0,
+                                                   "suppressor.subband_nearend_detection.snr_threshold": 2.0}, 48000),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STRUCTURAL))
+def test_optional_aec3_stages_match_the_reference(api_lib, oracle, name):
+    """EchoCanceller3Config members that add a stage to the path (dead by default in the reference:
+    SURVEY.md 8(a) 'deferred' list): the render high-pass filter and the fixed capture delay."""
+    import wap_b200
+    over, rate = STRUCTURAL[name]
+    nf = 300
+    n = rate // 100
+    legs = [(synthetic_leg(i, nf) if rate == 16000 else synthetic_leg_48k(i, nf, 1.5)) for i in (2, 9)]
+    eng = wap_b200.Engine(2, rate, lib=api_lib, aec=True, ns=True, ns_level=1, max_rate=48000, aec3=over)
+    out = np.zeros((2, nf * n), np.int16)
+    for f in range(nf):
+        sl = slice(f * n, (f + 1) * n)
+        eng.set_stream_delay_ms(0)
+        out[:, sl] = eng.process(np.stack([l[0][sl] for l in legs]), np.stack([l[1][sl] for l in legs]))
+    blob = eng.export_state(0)
+    assert blob.size == api_lib.wap_stream_state_bytes(eng.handles[0])
+    eng.close()
+    for i, (far, near) in enumerate(legs):
+        ro, _, err = oracle.RefApm(kv=_ref_kv(over, aec=1, ns=1, ns_level=1, max_rate=48000)).run_i16(rate, far, near)
+        assert err == 0
+        d = np.abs(out[i].astype(np.int32) - ro.astype(np.int32))
+        assert d.max() == 0, (name, i, int(d.max()), int(np.argmax(d)) // n)
+    ro_default, _, _ = oracle.RefApm(aec=True, ns=True, ns_level=1, max_rate=48000).run_i16(rate, legs[0][0], legs[0][1])
+    assert not np.array_equal(ro_default, out[0])

@@ -698,9 +698,35 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   __syncwarp();
   // DominantNearendDetector::Update on (nearend, R2_unbounded, N2): three 15-term
   // chains; LowNoiseRenderDetector::Detect: one 64-term chain with running maximum.
+  const bool subband_detector = WAP_EC3(use_subband_nearend_detection) != 0;
+  if (subband_detector) {
+    // SubbandNearendDetector::Update (subband_nearend_detector.cc:37-75): its own MovingAverage of the
+    // nearend spectrum (moving_average.cc:36-59; r.gain is free until the gains are formed), then the
+    // band powers below as left-to-right chains.
+    const int n_mem = WAP_EC3(snd_average_blocks) - 1;
+    const float scaling = fdiv(1.f, (float)WAP_EC3(snd_average_blocks));
+    const int snd_index = s.snd_mem_index;
+    #pragma unroll
+    for (int k = lane; k < kBins; k += 32) {
+      const float in = nearend[k];
+      float o = in;
+      for (int j = 0; j < n_mem; ++j) o = a.snd_mem[j][k] + o;
+      r.gain[k] = o * scaling;
+      if (n_mem > 0) a.snd_mem[snd_index][k] = in;
+    }
+    __syncwarp();
+  }
   if (lane < 3) {
-    const float* p = lane == 0 ? nearend : lane == 1 ? r.R2_unb : a.cng_N2;
-    sc.red[16 + lane] = chain_sum(p, 1, 16);
+    if (subband_detector) {
+      // noise power of region 1, nearend power of region 1, nearend power of region 2
+      const float* p = lane == 0 ? a.cng_N2 : r.gain;
+      const int lo = lane == 2 ? WAP_EC3(snd_sub2_low) : WAP_EC3(snd_sub1_low);
+      const int hi = lane == 2 ? WAP_EC3(snd_sub2_high) : WAP_EC3(snd_sub1_high);
+      sc.red[16 + lane] = chain_sum(p, lo, hi + 1);
+    } else {
+      const float* p = lane == 0 ? nearend : lane == 1 ? r.R2_unb : a.cng_N2;
+      sc.red[16 + lane] = chain_sum(p, 1, 16);
+    }
   } else if (lane == 3) {
     float x2_sum = 0.f, x2_max = 0.f;
     for (int i = 0; i < kBlock; ++i) {
@@ -712,19 +738,30 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     sc.red[20] = x2_max;
   }
   __syncwarp();
+  if (lane == 0 && subband_detector) {
+    const float one_over1 = fdiv(1.f, (float)(WAP_EC3(snd_sub1_high) - WAP_EC3(snd_sub1_low) + 1));
+    const float one_over2 = fdiv(1.f, (float)(WAP_EC3(snd_sub2_high) - WAP_EC3(snd_sub2_low) + 1));
+    const float noise_power = sc.red[16] * one_over1;
+    const float nearend_power_subband1 = sc.red[17] * one_over1, nearend_power_subband2 = sc.red[18] * one_over2;
+    s.dn_nearend_state = (nearend_power_subband1 < WAP_EC3(snd_nearend_threshold) * nearend_power_subband2 &&
+                          nearend_power_subband1 > WAP_EC3(snd_snr_threshold) * noise_power) ? 1 : 0;
+    if (WAP_EC3(snd_average_blocks) > 1) s.snd_mem_index = (s.snd_mem_index + 1) % (WAP_EC3(snd_average_blocks) - 1);
+  }
   if (lane == 0) {
     const float ne_sum = sc.red[16], echo_sum = sc.red[17], noise_sum = sc.red[18];
-    if (echo_sum < WAP_EC3(dn_enr_threshold) * ne_sum && ne_sum > WAP_EC3(dn_snr_threshold) * noise_sum) {
-      if (++s.dn_trigger_counter >= WAP_EC3(dn_trigger_threshold)) {
-        s.dn_hold_counter = WAP_EC3(dn_hold_duration);
-        s.dn_trigger_counter = WAP_EC3(dn_trigger_threshold);
+    if (!subband_detector) {   // (with the subband detector the dominant-nearend detector does not exist)
+      if (echo_sum < WAP_EC3(dn_enr_threshold) * ne_sum && ne_sum > WAP_EC3(dn_snr_threshold) * noise_sum) {
+        if (++s.dn_trigger_counter >= WAP_EC3(dn_trigger_threshold)) {
+          s.dn_hold_counter = WAP_EC3(dn_hold_duration);
+          s.dn_trigger_counter = WAP_EC3(dn_trigger_threshold);
+        }
+      } else {
+        s.dn_trigger_counter = imax(0, s.dn_trigger_counter - 1);
       }
-    } else {
-      s.dn_trigger_counter = imax(0, s.dn_trigger_counter - 1);
+      if (echo_sum > WAP_EC3(dn_enr_exit_threshold) * ne_sum && echo_sum > WAP_EC3(dn_snr_threshold) * noise_sum) s.dn_hold_counter = 0;
+      s.dn_hold_counter = imax(0, s.dn_hold_counter - 1);
+      s.dn_nearend_state = s.dn_hold_counter > 0;
     }
-    if (echo_sum > WAP_EC3(dn_enr_exit_threshold) * ne_sum && echo_sum > WAP_EC3(dn_snr_threshold) * noise_sum) s.dn_hold_counter = 0;
-    s.dn_hold_counter = imax(0, s.dn_hold_counter - 1);
-    s.dn_nearend_state = s.dn_hold_counter > 0;
     // LowNoiseRenderDetector
     const float x2_sum = sc.red[19] / 1, x2_max = sc.red[20];
     constexpr float kThreshold = 50.f * 50.f * 64.f;

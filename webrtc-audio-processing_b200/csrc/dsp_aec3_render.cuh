@@ -63,8 +63,8 @@ WAP_DEV bool rdb_align_from_delay(Aec3Scalars& s, int delay) {
   return true;
 }
 // SetAudioBufferDelay (:330-344): ms -> blocks (rounded down).
-WAP_DEV void rdb_set_audio_buffer_delay(Aec3Scalars& s, int delay_ms) {
-  s.external_delay = (delay_ms * 16) / (4 * 16);
+WAP_DEV void rdb_set_audio_buffer_delay(Aec3Scalars& s, int delay_ms, int fixed_capture_delay_samples = 0) {
+  s.external_delay = (delay_ms * 16 + fixed_capture_delay_samples) / (4 * 16);
   s.has_external_delay = 1;
 }
 // PrepareCaptureProcessing (:249-301)

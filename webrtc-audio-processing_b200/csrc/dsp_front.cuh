@@ -239,7 +239,7 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
   const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
   // AudioProcessingImpl forwards set_stream_delay_ms() before EchoCanceller3::ProcessCapture
   // drains the render queue (audio_processing_impl.cc:1409-1415).
-  if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms);
+  if (cfg.aec_enabled && delay_ms >= 0) rdb_set_audio_buffer_delay(s, delay_ms, a.ep.fixed_capture_delay_samples);
   float frame[kFrame * kMaxBands];  // full-band frame, then its bands [B][160]
   float sub[kFrame];
 
@@ -262,6 +262,19 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     } else {
       for (int i = 0; i < kFrame; ++i) frame[i] = front_load_sample(a.render, idx, flen, a.fmt, i, cfg.render_channels, -1);
       band0 = frame;
+    }
+    float rb0[kFrame];
+    if (a.ep.high_pass_filter_echo_reference) {
+      // RenderWriter::Insert (echo_canceller3.cc:733-737): band 0 through HighPassFilter(16000) before
+      // the frame is queued for the block processor.
+      Biquad h0 = aec.render_hpf[0], h1 = aec.render_hpf[1], h2 = aec.render_hpf[2];
+      for (int i = 0; i < kFrame; ++i) {
+        float v = biquad_step(kHpf16k[0], h0, band0[i]);
+        v = biquad_step(kHpf16k[1], h1, v);
+        rb0[i] = biquad_step(kHpf16k[2], h2, v);
+      }
+      aec.render_hpf[0] = h0; aec.render_hpf[1] = h1; aec.render_hpf[2] = h2;
+      band0 = rb0;
     }
     const int L = s.render_blocker_len;
     const int total = L + kFrame;
@@ -300,6 +313,31 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     else two_band_analysis_thread(ts.capture_frame, frame, &st.capture_bands.analysis[0][0]);
     for (int i = 0; i < flen; ++i) ts.capture_frame[i] = frame[i];
     cap0 = frame;
+  }
+  if (a.cap_delay) {
+    // BlockDelayBuffer::DelaySignal (block_delay_buffer.cc:35-67) on every band of the frame AEC3 is
+    // about to process; the noise suppressor's analysis (k_echo, from ts.capture_frame) saw the frame
+    // before the delay, like the reference's.
+    float* ring = a.cap_delay + (size_t)slot * a.cap_delay_stride;
+    const int delay = a.ep.fixed_capture_delay_samples;
+    int* last_insert = reinterpret_cast<int*>(ring + (size_t)B * delay);
+    const int i_start = *last_insert;
+    int i = i_start;
+    if (cap0 != frame) {
+      for (int k = 0; k < flen; ++k) frame[k] = cap0[k];
+      cap0 = frame;
+    }
+    for (int band = 0; band < B; ++band) {
+      float* rb = ring + (size_t)band * delay;
+      i = i_start;
+      for (int k = 0; k < kFrame; ++k) {
+        const float tmp = rb[i];
+        rb[i] = frame[band * kFrame + k];
+        frame[band * kFrame + k] = tmp;
+        i = i < delay - 1 ? i + 1 : 0;
+      }
+    }
+    *last_insert = i;
   }
   {
     const int L = s.capture_blocker_len;

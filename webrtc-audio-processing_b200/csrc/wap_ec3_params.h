@@ -48,6 +48,16 @@ struct Ec3Params {
   float hb_enr_threshold, hb_max_gain_during_echo, hb_anti_howling_activation_threshold, hb_anti_howling_gain;
   int limiting_gain_band, bands_in_limiting_gain;
   float floor_first_increase;
+  // filter.high_pass_filter_echo_reference: the render frames' band 0 passes the 16 kHz high-pass filter
+  // before it is queued (echo_canceller3.cc:718-720,735-737); read by k_front only
+  int high_pass_filter_echo_reference;
+  // delay.fixed_capture_delay_samples: BlockDelayBuffer in front of ProcessCapture (echo_canceller3.cc:
+  // 796-800,902-905) and its share of the external delay (render_delay_buffer.cc:338-343); k_front only
+  int fixed_capture_delay_samples;
+  // suppressor.use_subband_nearend_detection + subband_nearend_detection (SubbandNearendDetector in place
+  // of DominantNearendDetector, suppression_gain.cc:365-371)
+  int use_subband_nearend_detection, snd_average_blocks, snd_sub1_low, snd_sub1_high, snd_sub2_low, snd_sub2_high;
+  float snd_nearend_threshold, snd_snr_threshold;
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -81,6 +91,10 @@ constexpr float hb_enr_threshold = 1.f, hb_max_gain_during_echo = 1.f, hb_anti_h
                 hb_anti_howling_gain = 1.f;
 constexpr int limiting_gain_band = 16, bands_in_limiting_gain = 1;
 constexpr float floor_first_increase = 0.00001f;
+constexpr int high_pass_filter_echo_reference = 0, fixed_capture_delay_samples = 0;
+constexpr int use_subband_nearend_detection = 0, snd_average_blocks = 1, snd_sub1_low = 1, snd_sub1_high = 1, snd_sub2_low = 1,
+              snd_sub2_high = 1;
+constexpr float snd_nearend_threshold = 1.f, snd_snr_threshold = 1.f;
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -112,6 +126,9 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(hb_enr_threshold); WAP_SET(hb_max_gain_during_echo); WAP_SET(hb_anti_howling_activation_threshold);
   WAP_SET(hb_anti_howling_gain);
   WAP_SET(limiting_gain_band); WAP_SET(bands_in_limiting_gain); WAP_SET(floor_first_increase);
+  WAP_SET(high_pass_filter_echo_reference); WAP_SET(fixed_capture_delay_samples);
+  WAP_SET(use_subband_nearend_detection); WAP_SET(snd_average_blocks); WAP_SET(snd_sub1_low); WAP_SET(snd_sub1_high);
+  WAP_SET(snd_sub2_low); WAP_SET(snd_sub2_high); WAP_SET(snd_nearend_threshold); WAP_SET(snd_snr_threshold);
 #undef WAP_SET
   return p;
 }

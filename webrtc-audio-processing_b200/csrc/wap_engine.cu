@@ -167,6 +167,8 @@ struct WapEngine {
   float* d_rs_capture = nullptr;
   float* d_rs_capture1 = nullptr;        // stereo: second capture channel
   wap::ExtraChannelState* d_extra = nullptr;  // stereo engines: [capacity]
+  float* d_cap_delay = nullptr;               // delay.fixed_capture_delay_samples > 0: [capacity][cap_delay_stride]
+  int cap_delay_stride = 0;                   // floats per leg: bands * delay + 4 (insert position, padding)
   // multi-channel engines (EngineConfig::mc)
   wap::McState* d_mc = nullptr;             // [capacity]
   wap::McTemplates* d_mc_templates = nullptr;
@@ -488,7 +490,8 @@ WapEchoCanceller3Config ec3_config_default() {
 WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
   const WapEchoCanceller3Config d = ec3_config_default();
   const bool ok =
-      c.delay.down_sampling_factor == 4 && c.delay.num_filters == 5 && c.delay.fixed_capture_delay_samples == 0 &&
+      c.delay.down_sampling_factor == 4 && c.delay.num_filters == 5 && c.delay.fixed_capture_delay_samples >= 0 &&
+      c.delay.fixed_capture_delay_samples <= 5000 &&
       !c.delay.use_external_delay_estimator && c.delay.detect_pre_echo && c.delay.default_delay >= 0 &&
       c.delay.default_delay <= wap::kMaxRingDelay &&
       c.filter.refined.length_blocks >= 1 && c.filter.refined.length_blocks <= wap::kMaxPartitions &&
@@ -499,7 +502,6 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.filter.conservative_initial_phase == d.filter.conservative_initial_phase &&
       c.filter.enable_coarse_filter_output_usage == d.filter.enable_coarse_filter_output_usage &&
       c.filter.use_linear_filter == d.filter.use_linear_filter &&
-      c.filter.high_pass_filter_echo_reference == d.filter.high_pass_filter_echo_reference &&
       c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
       c.erle.onset_detection == d.erle.onset_detection && c.erle.num_sections == 1 &&
       c.erle.clamp_quality_estimate_to_zero && c.erle.clamp_quality_estimate_to_one &&
@@ -514,7 +516,15 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.suppressor.nearend_average_blocks == 4 && c.suppressor.lf_smoothing_during_initial_phase &&
       c.suppressor.dominant_nearend_detection.use_during_initial_phase &&
       c.suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum &&
-      !c.suppressor.use_subband_nearend_detection && !c.suppressor.conservative_hf_suppression &&
+      // SubbandNearendDetector: its smoother holds at most three past blocks here
+      (!c.suppressor.use_subband_nearend_detection ||
+       (c.suppressor.subband_nearend_detection.nearend_average_blocks >= 1 &&
+        c.suppressor.subband_nearend_detection.nearend_average_blocks <= 4 &&
+        c.suppressor.subband_nearend_detection.subband1.low >= 0 && c.suppressor.subband_nearend_detection.subband1.high < wap::kBins &&
+        c.suppressor.subband_nearend_detection.subband1.low <= c.suppressor.subband_nearend_detection.subband1.high &&
+        c.suppressor.subband_nearend_detection.subband2.low >= 0 && c.suppressor.subband_nearend_detection.subband2.high < wap::kBins &&
+        c.suppressor.subband_nearend_detection.subband2.low <= c.suppressor.subband_nearend_detection.subband2.high)) &&
+      !c.suppressor.conservative_hf_suppression &&
       c.suppressor.high_bands_suppression.max_gain_during_echo == 1.f &&
       c.suppressor.high_frequency_suppression.limiting_gain_band >= 0 &&
       c.suppressor.high_frequency_suppression.bands_in_limiting_gain >= 0 &&
@@ -585,6 +595,16 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   p.limiting_gain_band = c.suppressor.high_frequency_suppression.limiting_gain_band;
   p.bands_in_limiting_gain = c.suppressor.high_frequency_suppression.bands_in_limiting_gain;
   p.floor_first_increase = c.suppressor.floor_first_increase;
+  p.high_pass_filter_echo_reference = c.filter.high_pass_filter_echo_reference ? 1 : 0;
+  p.fixed_capture_delay_samples = c.delay.fixed_capture_delay_samples;
+  p.use_subband_nearend_detection = c.suppressor.use_subband_nearend_detection ? 1 : 0;
+  p.snd_average_blocks = c.suppressor.subband_nearend_detection.nearend_average_blocks;
+  p.snd_sub1_low = c.suppressor.subband_nearend_detection.subband1.low;
+  p.snd_sub1_high = c.suppressor.subband_nearend_detection.subband1.high;
+  p.snd_sub2_low = c.suppressor.subband_nearend_detection.subband2.low;
+  p.snd_sub2_high = c.suppressor.subband_nearend_detection.subband2.high;
+  p.snd_nearend_threshold = c.suppressor.subband_nearend_detection.nearend_threshold;
+  p.snd_snr_threshold = c.suppressor.subband_nearend_detection.snr_threshold;
   return p;
 }
 
@@ -738,6 +758,8 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   const bool timing = e->timing;
   if (timing) cudaEventRecord(e->ev[0], e->stream);
   a.extra = e->d_extra;
+  a.cap_delay = e->d_cap_delay;
+  a.cap_delay_stride = e->cap_delay_stride;
   a.rs_capture1 = nullptr;
   a.mc = e->d_mc;
   a.mc_templates = e->d_mc_templates;
@@ -932,6 +954,11 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
   if (err == WapError::None && config.echo_canceller_enabled) err = ec3_config_supported(aec3);
   if (err == WapError::None && cfg.mc) {
     err = ec3_config_supported(aec3_mc);
+    // the render high-pass filter and the fixed capture delay are built for the mono kernels only
+    if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||
+        aec3.filter.high_pass_filter_echo_reference || aec3_mc.filter.high_pass_filter_echo_reference ||
+        aec3.delay.fixed_capture_delay_samples || aec3_mc.delay.fixed_capture_delay_samples)
+      err = WapError::UnsupportedConfig;
     // ConfigSelector's CompatibleConfigs (config_selector.cc:23-48), plus what the engine fixes per engine
     // rather than per leg state: the delay-estimation and buffering parameters and the comfort-noise floor.
     if (err == WapError::None &&
@@ -1032,6 +1059,12 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
       delete nt;
     }
   }
+  if (ok && cfg.aec_enabled && e->ep.fixed_capture_delay_samples > 0) {
+    // BlockDelayBuffer (block_delay_buffer.cc:22-31): num_bands rings of `delay` samples, zero
+    e->cap_delay_stride = cfg.num_bands * e->ep.fixed_capture_delay_samples + 4;
+    const size_t cb = (size_t)max_streams * e->cap_delay_stride * sizeof(float);
+    ok = cudaMalloc((void**)&e->d_cap_delay, cb) == cudaSuccess && cudaMemset(e->d_cap_delay, 0, cb) == cudaSuccess;
+  }
   if (ok && cfg.channels == 2 && !cfg.mc) {
     const size_t xb = (size_t)max_streams * sizeof(wap::ExtraChannelState);
     ok = cudaMalloc((void**)&e->d_extra, xb) == cudaSuccess && cudaMemset(e->d_extra, 0, xb) == cudaSuccess;
@@ -1081,6 +1114,7 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_rs_capture);
   cudaFree(e->d_rs_capture1);
   cudaFree(e->d_extra);
+  cudaFree(e->d_cap_delay);
   cudaFree(e->d_mc);
   cudaFree(e->d_mc_templates);
   cudaFree(e->d_mc_ns);
@@ -1125,6 +1159,9 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
       for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_upper[slots[i]], 0, sizeof(wap::UpperBandState), e->stream));
     if (e->d_extra)
       for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_extra[slots[i]], 0, sizeof(wap::ExtraChannelState), e->stream));
+    if (e->d_cap_delay)
+      for (int i = 0; i < n; ++i)
+        WAP_CUDA(cudaMemsetAsync(e->d_cap_delay + (size_t)slots[i] * e->cap_delay_stride, 0, e->cap_delay_stride * sizeof(float), e->stream));
     if (e->d_mc) {
       WAP_LAUNCH(wap::k_mc_init_slots, dim3(32, std::min(n, 2048)), 256, 0, e->stream, e->d_mc,
                  (const wap::McTemplates*)e->d_mc_templates, (const int*)d_slots, (int)n,
@@ -1429,12 +1466,13 @@ struct BlobHeader {
   WapStats cached_stats;
 };
 constexpr uint32_t kBlobMagic = 0x57415042u;  // "WAPB"
-constexpr uint32_t kBlobVersion = 3;
+constexpr uint32_t kBlobVersion = 4;
 size_t blob_bytes(const WapEngine* e) {
   size_t n = sizeof(BlobHeader) + sizeof(StreamState);
   if (e->d_upper) n += sizeof(wap::UpperBandState);
   if (e->d_rs) n += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   if (e->d_extra) n += sizeof(wap::ExtraChannelState);
+  if (e->d_cap_delay) n += (size_t)e->cap_delay_stride * sizeof(float);
   if (e->d_mc) n += sizeof(wap::McState);
   if (e->d_mc_ns) n += wap::kMcCh * sizeof(wap::NsState);
   return n;
@@ -1489,6 +1527,10 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
     WAP_CUDA(cudaMemcpy(p, &e->d_extra[h->slot], sizeof(wap::ExtraChannelState), cudaMemcpyDeviceToHost));
     p += sizeof(wap::ExtraChannelState);
   }
+  if (e->d_cap_delay) {
+    WAP_CUDA(cudaMemcpy(p, e->d_cap_delay + (size_t)h->slot * e->cap_delay_stride, (size_t)e->cap_delay_stride * sizeof(float), cudaMemcpyDeviceToHost));
+    p += (size_t)e->cap_delay_stride * sizeof(float);
+  }
   if (e->d_mc) {
     WAP_CUDA(cudaMemcpy(p, &e->d_mc[h->slot], sizeof(wap::McState), cudaMemcpyDeviceToHost));
     p += sizeof(wap::McState);
@@ -1525,6 +1567,10 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   if (e->d_extra) {
     WAP_CUDA(cudaMemcpy(&e->d_extra[h->slot], p, sizeof(wap::ExtraChannelState), cudaMemcpyHostToDevice));
     p += sizeof(wap::ExtraChannelState);
+  }
+  if (e->d_cap_delay) {
+    WAP_CUDA(cudaMemcpy(e->d_cap_delay + (size_t)h->slot * e->cap_delay_stride, p, (size_t)e->cap_delay_stride * sizeof(float), cudaMemcpyHostToDevice));
+    p += (size_t)e->cap_delay_stride * sizeof(float);
   }
   if (e->d_mc) {
     WAP_CUDA(cudaMemcpy(&e->d_mc[h->slot], p, sizeof(wap::McState), cudaMemcpyHostToDevice));

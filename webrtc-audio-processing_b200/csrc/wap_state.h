@@ -193,6 +193,7 @@ struct Aec3Scalars {
   int sg_initial_state, sg_nearend_mem_index;
   float sg_average_power;
   int dn_nearend_state, dn_trigger_counter, dn_hold_counter;
+  int snd_mem_index;                      // SubbandNearendDetector's MovingAverage::mem_index_
   // ApmStatsReporter one-slot queue (audio_processing_impl.cc:2312-2327)
   int stats_slot_full;
   float stats_erl_time_domain, stats_erle_log2;
@@ -234,6 +235,7 @@ struct alignas(16) Aec3State {
   float cng_Y2_smoothed[kBinsPad], cng_N2[kBinsPad], cng_N2_initial[kBinsPad];
   float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
   float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (mem_len 4 -> 3 slots)
+  float snd_mem[3][kBinsPad];               // SubbandNearendDetector::nearend_smoothers_ (nearend_average_blocks <= 4)
   int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used, index k-1)
   int erle_hold_counters[kBinsPad];
   int erl_hold_counters[kBinsPad];          // 63 used, index k-1
@@ -244,6 +246,8 @@ struct alignas(16) Aec3State {
   float e_old[kBlock], y_old[kBlock], e_output_old[kBlock];
   float render_blocker[kBlock], capture_blocker[kBlock], output_framer[kBlock];
   Biquad render_decimator[4], capture_decimator[4];
+  Biquad render_hpf[3];                     // RenderWriter::high_pass_filter_ (filter.high_pass_filter_echo_reference)
+  int pad_hpf_[4];
   Aec3Scalars s;
 };
 

@@ -36,6 +36,10 @@ struct TickArgs {
   const float* rs_kernel_out;     // processing rate -> output
   const float* rs_kernel_render;  // render input -> processing rate
   double rs_ratio_in, rs_ratio_out, rs_ratio_render;
+  // Engines with delay.fixed_capture_delay_samples > 0 only: BlockDelayBuffer rings, per leg
+  // [band][delay] floats followed by the insert position (one int), `cap_delay_stride` floats per leg.
+  float* cap_delay;
+  int cap_delay_stride;
   // Stereo engines only: second capture channel (high-pass state, input resampler, resampled frame).
   ExtraChannelState* extra;  // [slot]
   float* rs_capture1;        // [n][proc frame] or nullptr
