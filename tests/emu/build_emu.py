@@ -40,7 +40,7 @@ def build(verbose=True):
         if name == "wap_k_echo":
             for rt in (0, 1):
                 tus += [(s, ["-DWAP_ECHO_CLASS=%d" % c, "-DWAP_EC3_RUNTIME=%d" % rt],
-                         os.path.join(OUT, "%s_%d%s%s.o" % (name, c, "_rt" if rt else "", tag))) for c in range(5)]
+                         os.path.join(OUT, "%s_%d%s%s.o" % (name, c, "_rt" if rt else "", tag))) for c in range(6)]
         elif name == "wap_k_delay":
             tus += [(s, ["-DWAP_EC3_RUNTIME=%d" % rt], os.path.join(OUT, name + ("_rt" if rt else "") + tag + ".o")) for rt in (0, 1)]
         else:

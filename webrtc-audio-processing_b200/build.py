@@ -25,7 +25,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I", CSRC, "-I", os.path.join(ROOT, "include")]
 
 
-ECHO_CLASSES = 5  # wap::EchoClass instances of k_echo (wap_k_echo.cu is compiled once per class)
+ECHO_CLASSES = 6  # wap::EchoClass instances of k_echo (wap_k_echo.cu is compiled once per class)
 OBJ = os.path.join(HERE, "_obj")
 
 

@@ -745,7 +745,8 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     const float nearend_power_subband1 = sc.red[17] * one_over1, nearend_power_subband2 = sc.red[18] * one_over2;
     s.dn_nearend_state = (nearend_power_subband1 < WAP_EC3(snd_nearend_threshold) * nearend_power_subband2 &&
                           nearend_power_subband1 > WAP_EC3(snd_snr_threshold) * noise_power) ? 1 : 0;
-    if (WAP_EC3(snd_average_blocks) > 1) s.snd_mem_index = (s.snd_mem_index + 1) % (WAP_EC3(snd_average_blocks) - 1);
+    const int snd_mem_len = imax(1, WAP_EC3(snd_average_blocks) - 1);
+    if (WAP_EC3(snd_average_blocks) > 1) s.snd_mem_index = (s.snd_mem_index + 1) % snd_mem_len;
   }
   if (lane == 0) {
     const float ne_sum = sc.red[16], echo_sum = sc.red[17], noise_sum = sc.red[18];

@@ -1016,8 +1016,9 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
     e->mc_echo_floats = wap::k_mc_echo_scratch_floats();
     if (const char* w = getenv("WAP_MC_ECHO_WPB")) e->mc_echo_wpb = std::max(1, std::min(4, atoi(w)));   // tuning knob
   }
-  e->echo_scratch_floats = e->ec3_runtime ? wap::k_echo_scratch_floats_rt(cfg.num_bands) : wap::k_echo_scratch_floats(cfg.num_bands);
   e->echo_class = wap::echo_class_of(cfg);
+  e->echo_scratch_floats = e->ec3_runtime ? wap::k_echo_scratch_floats_rt(cfg.num_bands, e->echo_class)
+                                          : wap::k_echo_scratch_floats(cfg.num_bands, e->echo_class);
   e->delay_scratch_floats = e->ec3_runtime ? wap::k_delay_scratch_floats_rt() : wap::k_delay_scratch_floats();
   bool ok = cudaSetDevice(cuda_device) == cudaSuccess &&
             cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cuda_device) == cudaSuccess &&

@@ -7,10 +7,14 @@
 #include "wap_pipeline.cuh"
 
 #ifndef WAP_ECHO_CLASS
-#error "compile with -DWAP_ECHO_CLASS=<0..4>"
+#error "compile with -DWAP_ECHO_CLASS=<0..5>"
 #endif
 #ifndef WAP_ECHO_MINBLOCKS
+#if WAP_ECHO_CLASS == 5
+#define WAP_ECHO_MINBLOCKS 6   // no AEC3: the noise suppressor and the band filters fit 80 registers
+#else
 #define WAP_ECHO_MINBLOCKS 4
+#endif
 #endif
 #if WAP_EC3_RUNTIME
 #define WAP_KSUF(x) x##_rt
@@ -67,6 +71,7 @@ cudaError_t WAP_KSUF(launch_k_echo)(int cls, int grid, int block, size_t smem, c
     case kEchoMono48kNative: return WAP_L(2)(grid, block, smem, stream, a, scratch_floats);
     case kEchoMono48kVia32k: return WAP_L(3)(grid, block, smem, stream, a, scratch_floats);
     case kEchoMono32k: return WAP_L(4)(grid, block, smem, stream, a, scratch_floats);
+    case kEchoNoAec: return WAP_L(5)(grid, block, smem, stream, a, scratch_floats);
     default: return WAP_L(0)(grid, block, smem, stream, a, scratch_floats);
   }
 }
@@ -76,9 +81,12 @@ cudaError_t WAP_KSUF(set_k_echo_smem)(int bytes) {
   if (e == cudaSuccess) e = WAP_S(2)(bytes);
   if (e == cudaSuccess) e = WAP_S(3)(bytes);
   if (e == cudaSuccess) e = WAP_S(4)(bytes);
+  if (e == cudaSuccess) e = WAP_S(5)(bytes);
   return e;
 }
-int WAP_KSUF(k_echo_scratch_floats)(int bands) { return echo_scratch_floats(bands); }
+int WAP_KSUF(k_echo_scratch_floats)(int bands, int cls) {
+  return cls == kEchoNoAec ? echo_scratch_floats_no_aec(bands) : echo_scratch_floats(bands);
+}
 #if !WAP_EC3_RUNTIME
 int k_echo_min_blocks() { return WAP_ECHO_MINBLOCKS; }
 #endif

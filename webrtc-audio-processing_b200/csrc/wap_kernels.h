@@ -24,12 +24,13 @@ namespace wap {
   cudaError_t launch_k_echo##S(int cls, int grid, int block, size_t smem, cudaStream_t stream, const TickArgs& a,     \
                                int scratch_floats);                                                                     \
   cudaError_t set_k_echo_smem##S(int bytes);                                                                            \
-  int k_echo_scratch_floats##S(int bands);                                                                              \
+  int k_echo_scratch_floats##S(int bands, int cls);                                                                              \
   WAP_DECLARE_ECHO_CLASS(S, 0)                                                                                          \
   WAP_DECLARE_ECHO_CLASS(S, 1)                                                                                          \
   WAP_DECLARE_ECHO_CLASS(S, 2)                                                                                          \
   WAP_DECLARE_ECHO_CLASS(S, 3)                                                                                          \
-  WAP_DECLARE_ECHO_CLASS(S, 4)
+  WAP_DECLARE_ECHO_CLASS(S, 4)                                                                                          \
+  WAP_DECLARE_ECHO_CLASS(S, 5)
 WAP_DECLARE_KERNELS()
 WAP_DECLARE_KERNELS(_rt)
 int k_echo_min_blocks();

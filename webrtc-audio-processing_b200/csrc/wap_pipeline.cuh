@@ -24,6 +24,11 @@ constexpr int kScratchFloatsDsp =
 // (rounded to 16 bytes: the scratch structs hold 128-bit aligned members)
 // (a 2-band leg is laid out like a 3-band one: AEC3 writes an unused third band)
 inline int echo_scratch_floats(int bands) { return (2 * kFrame * (bands == 2 ? 3 : bands) + kScratchFloatsDsp + 3) & ~3; }
+// Engines without AEC3 (k_echo class kEchoNoAec): the DSP scratch only holds the noise suppressor's buffers
+// or one output frame at the API rate (AGC2 / level ramps / output resampler).
+constexpr int kScratchFloatsDspNoAec =
+    (int)((sizeof(NsScratch) / sizeof(float) > (size_t)kRsMaxRequest ? sizeof(NsScratch) / sizeof(float) : (size_t)kRsMaxRequest)) + 4;
+inline int echo_scratch_floats_no_aec(int bands) { return (2 * kFrame * (bands == 2 ? 3 : bands) + kScratchFloatsDspNoAec + 3) & ~3; }
 inline int delay_scratch_floats() { return ((int)(kAecDelayScratchBytes / sizeof(float)) + 4 + 3) & ~3; }
 static_assert(offsetof(StreamState, aec) % 16 == 0 && offsetof(Aec3State, mf_h) % 16 == 0 &&
                   sizeof(StreamState) % 16 == 0 && offsetof(AecScratch, mf) % 16 == 0,
@@ -168,11 +173,13 @@ enum EchoClass {
   kEchoMono48kNative = 2,  // 48 kHz mono, three bands
   kEchoMono48kVia32k = 3,  // 48 kHz mono under the default maximum_internal_processing_rate
   kEchoMono32k = 4,      // 32 kHz mono, two bands
-  kEchoClasses = 5
+  kEchoNoAec = 5,        // mono legs without AEC3 (BASELINE config 3: NS-only): no AEC3 code, registers or scratch
+  kEchoClasses = 6
 };
 inline int echo_class_of(const EngineConfig& c) {
   // (k_echo starts behind the front end: only the output side of the formats matters to it)
   if (c.channels != 1 || c.in_channels != 1) return kEchoGeneric;
+  if (!c.aec_enabled) return kEchoNoAec;
   if (c.num_bands == 1 && !c.resample_out) return kEchoMono16k;
   if (!c.split_bands) return kEchoGeneric;
   if (c.num_bands == 3 && !c.resample_out) return kEchoMono48kNative;
@@ -184,7 +191,11 @@ inline int echo_class_of(const EngineConfig& c) {
 template <int kClass>
 WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
   EngineConfig cfg = a.cfg;
-  if (kClass != kEchoGeneric) {
+  if (kClass == kEchoNoAec) {
+    cfg.channels = 1;
+    cfg.in_channels = 1;
+    cfg.aec_enabled = 0;
+  } else if (kClass != kEchoGeneric) {
     cfg.channels = 1;
     cfg.in_channels = 1;
     cfg.num_bands = kClass == kEchoMono16k ? 1 : (kClass == kEchoMono48kNative ? 3 : 2);
