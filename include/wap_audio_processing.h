@@ -234,6 +234,12 @@ int32_t wap_engine_uses_runtime_aec3_parameters(const WapEngine* engine);
 size_t wap_stream_state_bytes(const WapAudioProcessing* handle);
 WapError wap_stream_export_state(WapAudioProcessing* handle, void* blob, size_t blob_bytes);
 WapError wap_stream_import_state(WapAudioProcessing* handle, const void* blob, size_t blob_bytes);
+/* Live migration: moves the leg to a free slot of `destination` -- an engine of the same config class
+ * on the same or another GPU of the box -- with device-to-device copies of its state slabs
+ * (cudaMemcpyPeer: NVLink between GPUs); the handle stays valid and belongs to `destination`
+ * afterwards.  Neither engine may be inside a tick.  BadStreamParameter: the destination is full or
+ * the handle owns a private engine; UnsupportedConfig: another config class. */
+WapError wap_stream_migrate(WapAudioProcessing* handle, WapEngine* destination);
 
 /* Stage taps: internal signals of one leg as of the last processed 64-sample block / 10 ms frame,
  * named after the reference's ApmDataDumper taps (modules/audio_processing/logging/

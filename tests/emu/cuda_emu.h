@@ -221,6 +221,7 @@ static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
 static inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyPeer(void* d, int, const void* s, int, size_t n) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }

@@ -288,6 +288,56 @@ def test_stream_state_export_import(api_lib, oracle, rate, max_rate, kw):
     other.close(); b.close()
 
 
+def test_stream_migrates_between_engines_device_to_device(api_lib, oracle, request):
+    """wap_stream_migrate: a live leg moves to a free slot of another engine of the same config class with
+    device-to-device copies (another GPU of the box when there is one) and continues bit-identically next to
+    the legs that were already there; the source slot is free again; engines of another class refuse."""
+    import wap_b200
+    L = api_lib
+    nf, cut, fl = 90, 41, 160
+    legs = [synthetic_leg(i, nf) for i in (5, 8)]
+    refs = [oracle.RefApm(aec=True, ns=True, ns_level=1).run_i16(16000, far, near)[0] for far, near in legs]
+    dst_device = 0
+    if request.node.callspec.params["api_lib"] == "gpu":
+        import torch
+        dst_device = 1 if torch.cuda.device_count() > 1 else 0
+    a = wap_b200.Engine(2, 16000, lib=L, aec=True, ns=True, ns_level=1)
+    b = wap_b200.Engine(1, 16000, lib=L, aec=True, ns=True, ns_level=1, capacity=3, device=dst_device)
+    out = [np.zeros(nf * fl, np.int16) for _ in legs]
+
+    def tick(handles, which, f):
+        n = len(handles)
+        arr = (C.c_void_p * n)(*handles)
+        L.wap_streams_set_delay_ms(arr, n, 0)
+        r = np.zeros((n, fl), np.int16); c = np.zeros((n, fl), np.int16); o = np.zeros((n, fl), np.int16)
+        for k, w in enumerate(which):
+            if w is not None:
+                r[k] = legs[w][0][f * fl:(f + 1) * fl]; c[k] = legs[w][1][f * fl:(f + 1) * fl]
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        assert L.wap_process_streams(arr, n, p(r), p(c), p(o), 0, None) == 0
+        for k, w in enumerate(which):
+            if w is not None:
+                out[w][f * fl:(f + 1) * fl] = o[k]
+
+    ha = [a.handles[0], a.handles[1]]
+    for f in range(cut):
+        tick(ha, [0, 1], f)
+    other = wap_b200.Engine(1, 16000, lib=L, aec=True, ns=False)
+    assert L.wap_stream_migrate(ha[1], other.h) == 7          # UnsupportedConfig: another config class
+    assert L.wap_stream_migrate(ha[1], b.h) == 0              # leg 1 of engine a -> engine b
+    for f in range(cut, nf):
+        tick([ha[0]], [0], f)                                  # engine a goes on with leg 0
+        tick([b.handles[0], ha[1]], [None, 1], f)              # engine b: its own (idle) leg + the migrated one
+    assert np.array_equal(out[0], refs[0]) and np.array_equal(out[1], refs[1])
+    # the source slot is free again, the destination has two legs left to hand out
+    extra = (C.c_void_p * 1)()
+    assert L.wap_engine_create_streams(a.h, 1, extra) == 0
+    L.wap_destroy(extra[0])
+    L.wap_destroy(ha[1]); a.handles[1] = None
+    a.handles = (C.c_void_p * 1)(ha[0]); a.n = 1
+    other.close(); a.close(); b.close()
+
+
 def test_stage_taps_match_reference_dumps(api_lib, tmp_path):
     """wap_stream_read_taps against the reference's own ApmDataDumper output (the dump variant of the
     compiled reference, -DWEBRTC_APM_DEBUG_DUMP=1, run in a helper process): the taps after the last

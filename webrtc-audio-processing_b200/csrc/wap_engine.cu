@@ -16,6 +16,7 @@
 #include <deque>
 #include <mutex>
 #include <new>
+#include <functional>
 #include <vector>
 
 #include "wap_audio_processing.h"
@@ -1538,6 +1539,62 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
   }
   if (e->d_mc_ns)
     WAP_CUDA(cudaMemcpy(p, &e->d_mc_ns[(size_t)h->slot * wap::kMcCh], wap::kMcCh * sizeof(wap::NsState), cudaMemcpyDeviceToHost));
+  return WapError::None;
+}
+
+namespace {
+// Every device slab that belongs to slot `slot` of engine `e` (pointer, bytes), in blob order.
+void for_each_slab(WapEngine* e, int slot, const std::function<void(void*, size_t)>& fn) {
+  fn(&e->d_states[slot], sizeof(StreamState));
+  if (e->d_upper) fn(&e->d_upper[slot], sizeof(wap::UpperBandState));
+  if (e->d_rs) fn(&e->d_rs[(size_t)slot * wap::kRsPerLeg], wap::kRsPerLeg * sizeof(wap::ResamplerState));
+  if (e->d_extra) fn(&e->d_extra[slot], sizeof(wap::ExtraChannelState));
+  if (e->d_cap_delay) fn(e->d_cap_delay + (size_t)slot * e->cap_delay_stride, (size_t)e->cap_delay_stride * sizeof(float));
+  if (e->d_mc) fn(&e->d_mc[slot], sizeof(wap::McState));
+  if (e->d_mc_ns) fn(&e->d_mc_ns[(size_t)slot * wap::kMcCh], wap::kMcCh * sizeof(wap::NsState));
+}
+}  // namespace
+
+// Live migration of a leg between two engines of the same config class (the same or another GPU): the
+// state slabs go device to device (cudaMemcpyPeer: over NVLink between GPUs of one box), the handle stays
+// valid and belongs to `dst` afterwards; the call continues bit-identically.
+WapError wap_stream_migrate(WapAudioProcessing* h, WapEngine* dst) {
+  if (!h || !dst) return WapError::NullPointer;
+  WapEngine* src = h->engine;
+  if (!src || h->slot < 0 || h->owns_engine) return WapError::BadStreamParameter;
+  if (src == dst) return WapError::None;
+  // both engines, always in the same order
+  std::unique_lock<std::recursive_mutex> l1(src < dst ? src->mu : dst->mu);
+  std::unique_lock<std::recursive_mutex> l2(src < dst ? dst->mu : src->mu);
+  if (!wap::same_engine_config(src->cfg, dst->cfg) || !wap::same_ec3_params(src->ep, dst->ep) ||
+      !wap::same_ec3_params(src->ep_mc, dst->ep_mc) || blob_bytes(src) != blob_bytes(dst))
+    return WapError::UnsupportedConfig;
+  if (dst->free_slots.empty()) return WapError::BadStreamParameter;  // destination engine is full
+  WAP_CUDA(cudaSetDevice(src->device));
+  WAP_CUDA(cudaStreamSynchronize(src->stream));
+  WAP_CUDA(cudaSetDevice(dst->device));
+  WAP_CUDA(cudaStreamSynchronize(dst->stream));
+  const int to = dst->free_slots.back();
+  std::vector<std::pair<void*, size_t>> from_slabs, to_slabs;
+  for_each_slab(src, h->slot, [&](void* p, size_t n) { from_slabs.emplace_back(p, n); });
+  for_each_slab(dst, to, [&](void* p, size_t n) { to_slabs.emplace_back(p, n); });
+  if (from_slabs.size() != to_slabs.size()) return WapError::UnsupportedConfig;
+  for (size_t i = 0; i < from_slabs.size(); ++i) {
+    if (from_slabs[i].second != to_slabs[i].second) return WapError::UnsupportedConfig;
+    WAP_CUDA(cudaMemcpyPeer(to_slabs[i].first, dst->device, from_slabs[i].first, src->device, from_slabs[i].second));
+  }
+  dst->free_slots.pop_back();
+  const int dirty = (int)h->capture_output_used_dirty + (int)h->pre_gain_dirty + (int)h->post_gain_dirty +
+                    (int)h->playout_volume_dirty + (int)h->agc2_gain_dirty;
+  dst->leg_delay_ms[to] = src->leg_delay_ms[h->slot];
+  dst->leg_delay_set[to] = src->leg_delay_set[h->slot];
+  src->dirty_legs -= dirty;
+  dst->dirty_legs += dirty;
+  src->free_slots.push_back(h->slot);
+  src->last_slots.clear(); src->last_handles.clear();
+  dst->last_slots.clear(); dst->last_handles.clear();
+  h->engine = dst;
+  h->slot = to;
   return WapError::None;
 }
 

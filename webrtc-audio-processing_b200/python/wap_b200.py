@@ -182,7 +182,7 @@ EXPORTS = [
     "wap_engine_set_pipeline_chunks", "wap_stream_state_bytes", "wap_stream_export_state", "wap_stream_import_state", "wap_stream_read_taps",
     "wap_echo_canceller3_config_default", "wap_echo_canceller3_config_default_multichannel", "wap_echo_canceller3_config_sizeof",
     "wap_echo_canceller3_config_validate", "wap_echo_canceller3_config_supported", "wap_create_with_aec3_config",
-    "wap_engine_create_with_aec3_config", "wap_engine_create_with_formats",
+    "wap_engine_create_with_aec3_config", "wap_engine_create_with_formats", "wap_stream_migrate",
 ]
 
 _libs = {}
@@ -255,6 +255,8 @@ def load(path=None):
     L.wap_create_with_aec3_config.argtypes = [cfg, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_engine_create_with_aec3_config.restype = vp
     L.wap_engine_create_with_aec3_config.argtypes = [C.c_int, i32, cfg, sc, C.POINTER(ec3), C.POINTER(ec3)]
+    L.wap_stream_migrate.restype = C.c_int
+    L.wap_stream_migrate.argtypes = [vp, vp]
     L.wap_engine_create_with_formats.restype = vp
     L.wap_engine_create_with_formats.argtypes = [C.c_int, i32, cfg, sc, sc, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_version.restype = C.c_char_p
