@@ -104,6 +104,8 @@ WAP_DEV void aec_state_handle_echo_path_change(Aec3State& a, AecScratch& sc, con
       s.tm_non_converged_sequence_size = 10000;
       s.tm_diverged_sequence_size = 0;
       s.tm_strong_not_saturated_render_blocks = 0;
+      // echo_removal_control.linear_and_stable_echo_path (transparent_mode.cc:142-149)
+      if (WAP_EC3(linear_and_stable_echo_path)) s.tm_recent_convergence = 0;
       s.erl_blocks_since_reset = 0;  // ErlEstimator::Reset
       // FilteringQualityAnalyzer::Reset
       s.fq_usable = 0;
@@ -176,6 +178,7 @@ WAP_DEV void filter_analyzer_update(Aec3State& a, AecScratch& sc) {
     } else if (s.fa_gain) {
       s.fa_gain = fmaxr(s.fa_gain, fabsf(h_peak));
     }
+    if (WAP_EC3(bounded_erl) && s.fa_gain) s.fa_gain = fmaxr(s.fa_gain, 0.01f);   // filter_analyzer.cc:156-158
     s.fa_filter_length_blocks = (int)((float)size * (1.f / kBlock));
     // ConsistentFilterDetector::Detect, first part
     if (start == 0) {
@@ -336,7 +339,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
         int hold = a.erle_hold_counters[k], onset = a.coming_onset[k];
         if (update_bands && accE > 0.f) {  // UpdateBands
           const float new_erle = accY / accE;
-          if (!low) {
+          if (WAP_EC3(erle_onset_detection) && !low) {
             if (onset) onset = 0;
             hold = 250;  // kBlocksForOnsetDetection
           }
@@ -344,18 +347,22 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
           float alpha = 0.05f;
           if (new_erle < erle) alpha = low ? 0.f : 0.1f;
           erle = clampr(erle + alpha * (new_erle - erle), WAP_EC3(erle_min), max_erle);
-          alpha = 0.05f;
-          if (new_erle < erle_oc) alpha = low ? 0.f : 0.1f;
-          erle_oc = clampr(erle_oc + alpha * (new_erle - erle_oc), WAP_EC3(erle_min), max_erle);
+          if (WAP_EC3(erle_onset_detection)) {
+            alpha = 0.05f;
+            if (new_erle < erle_oc) alpha = low ? 0.f : 0.1f;
+            erle_oc = clampr(erle_oc + alpha * (new_erle - erle_oc), WAP_EC3(erle_min), max_erle);
+          }
           alpha = 0.05f;
           if (new_erle < erle_u) alpha = low ? 0.f : 0.1f;
           erle_u = clampr(erle_u + alpha * (new_erle - erle_u), WAP_EC3(erle_min), 100000.0f);
         }
         // DecreaseErlePerBandForLowRenderSignals (erle_during_onsets_ stays at min_erle)
-        --hold;
-        if (hold <= 250 - 100) {
-          if (erle_oc > WAP_EC3(erle_min)) erle_oc = fmaxr(WAP_EC3(erle_min), 0.97f * erle_oc);
-          if (hold <= 0) { onset = 1; hold = 0; }
+        if (WAP_EC3(erle_onset_detection)) {
+          --hold;
+          if (hold <= 250 - 100) {
+            if (erle_oc > WAP_EC3(erle_min)) erle_oc = fmaxr(WAP_EC3(erle_min), 0.97f * erle_oc);
+            if (hold <= 0) { onset = 1; hold = 0; }
+          }
         }
         a.erle[k] = erle;
         a.erle_onset_comp[k] = erle_oc;
@@ -453,8 +460,8 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   // ---- scalar state machines, lane 0
   if (lane == 0) {
     // SaturationDetector::Update
-    s.saturated_echo = 0;
-    if (saturated_capture) {
+    if (WAP_EC3(echo_can_saturate)) s.saturated_echo = 0;   // aec_state.cc:273-280: else the detector is never updated
+    if (WAP_EC3(echo_can_saturate) && saturated_capture) {
       if (usable_linear_before) {
         s.saturated_echo = s_refined_max_abs > 20000.f || s_coarse_max_abs > 20000.f;
       } else {
@@ -496,6 +503,8 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     if (s.tm_finite_erl_recently_detected) s.tm_active = 0;
     else if (sane_filter_recently_seen && s.tm_recent_convergence) s.tm_active = 0;
     else s.tm_active = s.tm_strong_not_saturated_render_blocks > 6 * kNumBlocksPerSecond;
+    // ep_strength.bounded_erl: no TransparentMode object at all (transparent_mode.cc:239-243): never transparent
+    if (WAP_EC3(bounded_erl)) s.tm_active = 0;
     // FilteringQualityAnalyzer::Update
     const bool filter_update = active_render && !saturated_capture;
     s.fq_blocks_since_reset += filter_update ? 1 : 0;
@@ -512,7 +521,9 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
 
   // ---- ReverbModelEstimator::Update -> ReverbFrequencyResponse::Update
   if (s.fb_has_erle_log2) {
-    const float quality = fminr(1.f, fmaxr(0.f, s.fb_inst_quality));
+    float quality = s.fb_inst_quality;   // ErleInstantaneous::GetQualityEstimate
+    if (WAP_EC3(clamp_quality_estimate_to_zero)) quality = fmaxr(0.f, quality);
+    if (WAP_EC3(clamp_quality_estimate_to_one)) quality = fminr(1.f, quality);
     const float* tail = a.H2[s.H2_size - 1];
     const float* direct = a.H2[s.fd_filter_delay];
     if (lane < 2) sc.red[16 + lane] = chain_sum(lane == 0 ? direct : tail, 1, kBins);
@@ -522,7 +533,8 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     const float smoothing = 0.2f * quality;
     const float avg = s.reverb_average_decay + smoothing * (average_decay - s.reverb_average_decay);
     #pragma unroll
-    for (int k = lane; k < kBins; k += 32) r.v3[k] = fmaxr(tail[k], direct[k] * avg);
+    for (int k = lane; k < kBins; k += 32)
+      r.v3[k] = WAP_EC3(use_conservative_tail_frequency_response) ? fmaxr(tail[k], direct[k] * avg) : direct[k] * avg;
     __syncwarp();
     if (lane == 0) {
       s.reverb_average_decay = avg;
@@ -620,7 +632,10 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   const float reverb_decay = dominant_nearend ? WAP_EC3(nearend_len) : WAP_EC3(default_len);
   const int first_reverb_partition = usable ? s.fa_filter_length_blocks + 1 : delay + 1;
   const float* X2_reverb_src = a.spectra[ring_off(s.spectra_read, first_reverb_partition, kRingBlocks)];
-  const float* erle = dominant_nearend ? a.erle : a.erle_onset_comp;
+  // LinearEstimate uses Erle(onset_compensated), which only differs from erle_ with onset detection
+  // (residual_echo_estimator.cc:249-251, subband_erle_estimator.h:46-50)
+  const bool onset_compensated = WAP_EC3(erle_onset_compensation_in_dominant_nearend) || !dominant_nearend;
+  const float* erle = (onset_compensated && WAP_EC3(erle_onset_detection)) ? a.erle_onset_comp : a.erle;
   const int w0 = ring_off(s.spectra_read, imax(0, delay - 1), kRingBlocks);
   const int wn = delay + 1 - imax(0, delay - 1) + 1;  // spectra in the window
   #pragma unroll
@@ -724,7 +739,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
       const int hi = lane == 2 ? WAP_EC3(snd_sub2_high) : WAP_EC3(snd_sub1_high);
       sc.red[16 + lane] = chain_sum(p, lo, hi + 1);
     } else {
-      const float* p = lane == 0 ? nearend : lane == 1 ? r.R2_unb : a.cng_N2;
+      const float* p = lane == 0 ? nearend : lane == 1 ? (WAP_EC3(dn_use_unbounded_echo_spectrum) ? r.R2_unb : r.R2) : a.cng_N2;
       sc.red[16 + lane] = chain_sum(p, 1, 16);
     }
   } else if (lane == 3) {
@@ -751,7 +766,8 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   if (lane == 0) {
     const float ne_sum = sc.red[16], echo_sum = sc.red[17], noise_sum = sc.red[18];
     if (!subband_detector) {   // (with the subband detector the dominant-nearend detector does not exist)
-      if (echo_sum < WAP_EC3(dn_enr_threshold) * ne_sum && ne_sum > WAP_EC3(dn_snr_threshold) * noise_sum) {
+      if ((!s.sg_initial_state || WAP_EC3(dn_use_during_initial_phase)) &&
+          echo_sum < WAP_EC3(dn_enr_threshold) * ne_sum && ne_sum > WAP_EC3(dn_snr_threshold) * noise_sum) {
         if (++s.dn_trigger_counter >= WAP_EC3(dn_trigger_threshold)) {
           s.dn_hold_counter = WAP_EC3(dn_hold_duration);
           s.dn_trigger_counter = WAP_EC3(dn_trigger_threshold);
@@ -804,7 +820,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     if (!saturated_echo) {
       min_gain = weighted > 0.f ? min_echo_power / weighted : 1.f;
       min_gain = fminr(min_gain, 1.f);
-      if (k <= WAP_EC3(last_lf_smoothing_band)) {  // lf_smoothing_during_initial_phase = true
+      if (k <= WAP_EC3(last_lf_smoothing_band) && (!s.sg_initial_state || WAP_EC3(lf_smoothing_during_initial_phase))) {
         if (a.last_nearend[k] > a.last_echo[k] || k <= WAP_EC3(last_permanent_lf_smoothing_band)) {
           min_gain = fmaxr(min_gain, last_gain * tun.max_dec_lf);
           min_gain = fminr(min_gain, 1.f);
@@ -830,7 +846,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
   {
     // LimitLowFrequencyGains / LimitHighFrequencyGains
     const float g12 = fminr(r.gain[1], r.gain[2]);
-    const bool limit_hf = !nearend_state || clock_drift;
+    const bool limit_hf = !nearend_state || clock_drift || WAP_EC3(conservative_hf_suppression);
     // min over bands [limiting_gain_band, + bands_in_limiting_gain) (suppression_gain.cc:44-62)
     float min_upper_gain = 1.f;
     for (int band = WAP_EC3(limiting_gain_band); band < WAP_EC3(limiting_gain_band) + WAP_EC3(bands_in_limiting_gain); ++band)
@@ -838,6 +854,23 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     const bool limit_bands = WAP_EC3(bands_in_limiting_gain) > 0;
     const float g63 = limit_hf ? (limit_bands ? fminr(r.gain[63], min_upper_gain) : r.gain[63]) : r.gain[63];
     __syncwarp();
+    float hf_gain_bound = 0.f;
+    const bool hf_bound = limit_hf && WAP_EC3(conservative_hf_suppression);
+    if (hf_bound) {
+      // LimitHighFrequencyGains, conservative part (suppression_gain.cc:66-83): the mean of the limited
+      // gains of bins 20..28 (a left-to-right sum) bounds every bin from 29 up
+      #pragma unroll
+      for (int k = lane; k < kBins; k += 32) {
+        float g = r.gain[k];
+        if (limit_bands && k > WAP_EC3(limiting_gain_band)) g = fminr(g, min_upper_gain);
+        if (k == 64) g = g63;
+        if (k >= 20 && k < 29) r.v0[k] = g;
+      }
+      __syncwarp();
+      constexpr float kOneByBandsInSum = 1 / static_cast<float>(29 - 20);
+      hf_gain_bound = chain_sum(r.v0, 20, 29) * kOneByBandsInSum;
+      __syncwarp();
+    }
     #pragma unroll
     for (int k = lane; k < kBins; k += 32) {
       float g = r.gain[k];
@@ -845,6 +878,7 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
       if (limit_hf) {
         if (limit_bands && k > WAP_EC3(limiting_gain_band)) g = fminr(g, min_upper_gain);
         if (k == 64) g = g63;
+        if (hf_bound && k >= 29) g = fminr(g, hf_gain_bound);
       }
       a.last_gain[k] = g;
       r.gain[k] = sqrtf(g);
@@ -882,9 +916,13 @@ WAP_DEV float upper_bands_gain(const Aec3State& a, AecScratch& sc, const UpperBa
   const float activation_threshold = kBlock * WAP_EC3(hb_anti_howling_activation_threshold);
   if (high_band_energy < fmaxr(low_band_energy, activation_threshold)) anti_howling_gain = 1.f;
   else anti_howling_gain = WAP_EC3(hb_anti_howling_gain) * sqrtf(low_band_energy / high_band_energy);
-  // gain_bound: max_gain_during_echo must be 1 (the default; checked by the host), so the echo/noise test cannot lower it.
-  const float gain_bound = 1.f;
-  (void)echo_spectrum;
+  // Bound the upper gain during significant echo activity (suppression_gain.cc:190-204).
+  float gain_bound = 1.f;
+  if (!s.dn_nearend_state && WAP_EC3(hb_max_gain_during_echo) != 1.f) {   // (at the default bound of 1 the test is moot)
+    if (lane < 2) sc.red[19 + lane] = chain_sum(lane == 0 ? echo_spectrum : a.cng_N2, 1, 16);
+    __syncwarp();
+    if (sc.red[19] > WAP_EC3(hb_enr_threshold) * sc.red[20]) gain_bound = WAP_EC3(hb_max_gain_during_echo);
+  }
   __syncwarp();
   return fminr(fminr(gain_below_8_khz, anti_howling_gain), gain_bound);
 }
@@ -1007,7 +1045,7 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
       for (int k = lane; k < kBins; k += 32) r.E2[k] = fminr(r.E2[k], r.Y2[k]);
       __syncwarp();
     }
-    suppression_gain_get_gain(a, sc, nearend, v.clock_drift != 0);
+    suppression_gain_get_gain(a, sc, nearend, v.clock_drift != 0 || WAP_EC3(has_clock_drift));
     // SuppressionGain::UpperBandsGain (suppression_gain.cc:124-217); echo_spectrum = S2_linear or R2.
     float high_bands_gain = 1.f;
     if (up) high_bands_gain = upper_bands_gain(a, sc, *up, usable ? r.S2_lin : r.R2);

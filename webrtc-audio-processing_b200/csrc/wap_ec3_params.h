@@ -58,6 +58,11 @@ struct Ec3Params {
   // of DominantNearendDetector, suppression_gain.cc:365-371)
   int use_subband_nearend_detection, snd_average_blocks, snd_sub1_low, snd_sub1_high, snd_sub2_low, snd_sub2_high;
   float snd_nearend_threshold, snd_snr_threshold;
+  // boolean switches of the echo remover (reference defaults in ec3d below)
+  int echo_can_saturate, bounded_erl, erle_onset_compensation_in_dominant_nearend, use_conservative_tail_frequency_response;
+  int erle_onset_detection, clamp_quality_estimate_to_zero, clamp_quality_estimate_to_one;
+  int has_clock_drift, linear_and_stable_echo_path;
+  int lf_smoothing_during_initial_phase, dn_use_during_initial_phase, dn_use_unbounded_echo_spectrum, conservative_hf_suppression;
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -95,6 +100,12 @@ constexpr int high_pass_filter_echo_reference = 0, fixed_capture_delay_samples =
 constexpr int use_subband_nearend_detection = 0, snd_average_blocks = 1, snd_sub1_low = 1, snd_sub1_high = 1, snd_sub2_low = 1,
               snd_sub2_high = 1;
 constexpr float snd_nearend_threshold = 1.f, snd_snr_threshold = 1.f;
+constexpr int echo_can_saturate = 1, bounded_erl = 0, erle_onset_compensation_in_dominant_nearend = 0,
+              use_conservative_tail_frequency_response = 1;
+constexpr int erle_onset_detection = 1, clamp_quality_estimate_to_zero = 1, clamp_quality_estimate_to_one = 1;
+constexpr int has_clock_drift = 0, linear_and_stable_echo_path = 0;
+constexpr int lf_smoothing_during_initial_phase = 1, dn_use_during_initial_phase = 1, dn_use_unbounded_echo_spectrum = 1,
+              conservative_hf_suppression = 0;
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -129,6 +140,11 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(high_pass_filter_echo_reference); WAP_SET(fixed_capture_delay_samples);
   WAP_SET(use_subband_nearend_detection); WAP_SET(snd_average_blocks); WAP_SET(snd_sub1_low); WAP_SET(snd_sub1_high);
   WAP_SET(snd_sub2_low); WAP_SET(snd_sub2_high); WAP_SET(snd_nearend_threshold); WAP_SET(snd_snr_threshold);
+  WAP_SET(echo_can_saturate); WAP_SET(bounded_erl); WAP_SET(erle_onset_compensation_in_dominant_nearend);
+  WAP_SET(use_conservative_tail_frequency_response); WAP_SET(erle_onset_detection);
+  WAP_SET(clamp_quality_estimate_to_zero); WAP_SET(clamp_quality_estimate_to_one); WAP_SET(has_clock_drift);
+  WAP_SET(linear_and_stable_echo_path); WAP_SET(lf_smoothing_during_initial_phase); WAP_SET(dn_use_during_initial_phase);
+  WAP_SET(dn_use_unbounded_echo_spectrum); WAP_SET(conservative_hf_suppression);
 #undef WAP_SET
   return p;
 }

@@ -504,19 +504,15 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.filter.enable_coarse_filter_output_usage == d.filter.enable_coarse_filter_output_usage &&
       c.filter.use_linear_filter == d.filter.use_linear_filter &&
       c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
-      c.erle.onset_detection == d.erle.onset_detection && c.erle.num_sections == 1 &&
-      c.erle.clamp_quality_estimate_to_zero && c.erle.clamp_quality_estimate_to_one &&
+      c.erle.num_sections == 1 &&
       c.ep_strength.default_len >= 0.f && c.ep_strength.nearend_len >= 0.f &&   // negative: adaptive reverb decay
-      c.ep_strength.echo_can_saturate && !c.ep_strength.bounded_erl &&
-      !c.ep_strength.erle_onset_compensation_in_dominant_nearend && c.ep_strength.use_conservative_tail_frequency_response &&
+
       !c.echo_audibility.use_stationarity_properties && !c.echo_audibility.use_stationarity_properties_at_init &&
       c.render_levels.render_power_gain_db == 0.f &&
-      !c.echo_removal_control.has_clock_drift && !c.echo_removal_control.linear_and_stable_echo_path &&
+
       c.echo_model.render_pre_window_size == 1 && c.echo_model.render_post_window_size == 1 &&
       c.echo_model.model_reverb_in_nonlinear_mode &&
-      c.suppressor.nearend_average_blocks == 4 && c.suppressor.lf_smoothing_during_initial_phase &&
-      c.suppressor.dominant_nearend_detection.use_during_initial_phase &&
-      c.suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum &&
+      c.suppressor.nearend_average_blocks == 4 &&
       // SubbandNearendDetector: its smoother holds at most three past blocks here
       (!c.suppressor.use_subband_nearend_detection ||
        (c.suppressor.subband_nearend_detection.nearend_average_blocks >= 1 &&
@@ -525,8 +521,7 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
         c.suppressor.subband_nearend_detection.subband1.low <= c.suppressor.subband_nearend_detection.subband1.high &&
         c.suppressor.subband_nearend_detection.subband2.low >= 0 && c.suppressor.subband_nearend_detection.subband2.high < wap::kBins &&
         c.suppressor.subband_nearend_detection.subband2.low <= c.suppressor.subband_nearend_detection.subband2.high)) &&
-      !c.suppressor.conservative_hf_suppression &&
-      c.suppressor.high_bands_suppression.max_gain_during_echo == 1.f &&
+
       c.suppressor.high_frequency_suppression.limiting_gain_band >= 0 &&
       c.suppressor.high_frequency_suppression.bands_in_limiting_gain >= 0 &&
       c.suppressor.high_frequency_suppression.limiting_gain_band +
@@ -606,6 +601,19 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   p.snd_sub2_high = c.suppressor.subband_nearend_detection.subband2.high;
   p.snd_nearend_threshold = c.suppressor.subband_nearend_detection.nearend_threshold;
   p.snd_snr_threshold = c.suppressor.subband_nearend_detection.snr_threshold;
+  p.echo_can_saturate = c.ep_strength.echo_can_saturate;
+  p.bounded_erl = c.ep_strength.bounded_erl;
+  p.erle_onset_compensation_in_dominant_nearend = c.ep_strength.erle_onset_compensation_in_dominant_nearend;
+  p.use_conservative_tail_frequency_response = c.ep_strength.use_conservative_tail_frequency_response;
+  p.erle_onset_detection = c.erle.onset_detection;
+  p.clamp_quality_estimate_to_zero = c.erle.clamp_quality_estimate_to_zero;
+  p.clamp_quality_estimate_to_one = c.erle.clamp_quality_estimate_to_one;
+  p.has_clock_drift = c.echo_removal_control.has_clock_drift;
+  p.linear_and_stable_echo_path = c.echo_removal_control.linear_and_stable_echo_path;
+  p.lf_smoothing_during_initial_phase = c.suppressor.lf_smoothing_during_initial_phase;
+  p.dn_use_during_initial_phase = c.suppressor.dominant_nearend_detection.use_during_initial_phase;
+  p.dn_use_unbounded_echo_spectrum = c.suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum;
+  p.conservative_hf_suppression = c.suppressor.conservative_hf_suppression;
   return p;
 }
 
@@ -956,6 +964,18 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
   if (err == WapError::None && cfg.mc) {
     err = ec3_config_supported(aec3_mc);
     // the render high-pass filter and the fixed capture delay are built for the mono kernels only
+    // (the boolean switches of the echo remover below are built for the mono kernels only)
+    for (const WapEchoCanceller3Config* c : {&aec3, &aec3_mc}) {
+      const WapEchoCanceller3Config d = ec3_config_default();
+      if (c->ep_strength.echo_can_saturate != d.ep_strength.echo_can_saturate || c->ep_strength.bounded_erl ||
+          c->ep_strength.erle_onset_compensation_in_dominant_nearend || !c->ep_strength.use_conservative_tail_frequency_response ||
+          !c->erle.onset_detection || !c->erle.clamp_quality_estimate_to_zero || !c->erle.clamp_quality_estimate_to_one ||
+          c->echo_removal_control.has_clock_drift || c->echo_removal_control.linear_and_stable_echo_path ||
+          !c->suppressor.lf_smoothing_during_initial_phase || !c->suppressor.dominant_nearend_detection.use_during_initial_phase ||
+          !c->suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum || c->suppressor.conservative_hf_suppression ||
+          c->suppressor.high_bands_suppression.max_gain_during_echo != 1.f)
+        err = WapError::UnsupportedConfig;
+    }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||
         aec3.filter.high_pass_filter_echo_reference || aec3_mc.filter.high_pass_filter_echo_reference ||
         aec3.delay.fixed_capture_delay_samples || aec3_mc.delay.fixed_capture_delay_samples)
