@@ -87,7 +87,7 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     assert m.filter.coarse.rate == pytest.approx(0.95) and m.suppressor.normal_tuning.max_inc_factor == pytest.approx(1.5)
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
-                    ("filter.use_linear_filter", False), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
+                    ("filter.export_linear_aec_output", True), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
                     ("echo_audibility.use_stationarity_properties", True),
                     ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
@@ -267,6 +267,15 @@ SWITCHES = {
     "conservative_hf_suppression": {"suppressor.conservative_hf_suppression": 1},
     "max_gain_during_echo": {"suppressor.high_bands_suppression.max_gain_during_echo": 0.25,
                              "suppressor.high_bands_suppression.enr_threshold": 0.5},
+    "conservative_initial_phase": {"filter.conservative_initial_phase": 1},
+    "no_coarse_filter_output": {"filter.enable_coarse_filter_output_usage": 0},
+    "no_linear_filter": {"filter.use_linear_filter": 0},
+    "render_windows": {"echo_model.render_pre_window_size": 3, "echo_model.render_post_window_size": 2},
+    "no_reverb_in_nonlinear_mode": {"echo_model.model_reverb_in_nonlinear_mode": 0},
+    "nearend_average_2_blocks": {"suppressor.nearend_average_blocks": 2},
+    "nearend_average_1_block": {"suppressor.nearend_average_blocks": 1},
+    "render_power_gain": {"render_levels.render_power_gain_db": 6.0},
+    "render_power_gain_48k": {"render_levels.render_power_gain_db": -4.5},
 }
 
 
@@ -327,7 +336,7 @@ def test_boolean_switches_of_the_echo_remover_match_the_reference(api_lib, oracl
     its default, on legs that reach the branch (16 kHz; the upper-band gain bound at 48 kHz)."""
     import wap_b200
     over = SWITCHES[name]
-    rate = 48000 if name == "max_gain_during_echo" else 16000
+    rate = 48000 if name in ("max_gain_during_echo", "render_power_gain_48k") else 16000
     n = rate // 100
     if name in SWITCH_LEGS:
         legs = SWITCH_LEGS[name]()

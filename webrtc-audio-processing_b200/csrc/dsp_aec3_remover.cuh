@@ -261,10 +261,12 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
       s.fd_has_external = 1;
       s.fd_external_delay = ext_delay;
     }
-    const bool may_not_have_converged = s.strong_not_saturated_render_blocks < 2 * kNumBlocksPerSecond;
-    if (may_not_have_converged && s.fd_has_external) s.fd_filter_delay = WAP_EC3(delay_headroom_samples) / kBlock;
-    else s.fd_filter_delay = s.fa_filter_delay_blocks;
-    s.fd_min_filter_delay = s.fd_filter_delay;
+    if (WAP_EC3(use_linear_filter)) {   // aec_state.cc:220-223
+      const bool may_not_have_converged = s.strong_not_saturated_render_blocks < 2 * kNumBlocksPerSecond;
+      if (may_not_have_converged && s.fd_has_external) s.fd_filter_delay = WAP_EC3(delay_headroom_samples) / kBlock;
+      else s.fd_filter_delay = s.fa_filter_delay_blocks;
+      s.fd_min_filter_delay = s.fd_filter_delay;
+    }
   }
   __syncwarp();
   const int delay = s.fd_min_filter_delay;
@@ -472,7 +474,8 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     // InitialState::Update
     s.init_strong_blocks += (active_render && !saturated_capture) ? 1 : 0;
     const int prev_initial_state = s.init_state;
-    s.init_state = (float)s.init_strong_blocks < WAP_EC3(initial_state_seconds) * kNumBlocksPerSecond;
+    if (WAP_EC3(conservative_initial_phase)) s.init_state = s.init_strong_blocks < 5 * kNumBlocksPerSecond;   // aec_state.cc:360-366
+    else s.init_state = (float)s.init_strong_blocks < WAP_EC3(initial_state_seconds) * kNumBlocksPerSecond;
     s.init_transition_triggered = !s.init_state && prev_initial_state;
     // LegacyTransparentModeImpl::Update
     ++s.tm_capture_block_counter;
@@ -515,7 +518,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     bool usable = sufficient_at_startup && sufficient_at_reset;
     usable = usable && (ext_has || s.fq_convergence_seen);
     usable = usable && !s.tm_active;
-    s.fq_usable = usable;
+    s.fq_usable = usable && WAP_EC3(use_linear_filter);   // UsableLinearEstimate() (aec_state.h) / :457-461
   }
   __syncwarp();
 
@@ -627,7 +630,7 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   const float* X2_latest = a.spectra[s.spectra_read];
   const float echo_path_gain = transparent ? 0.01f * 0.01f : WAP_EC3(default_gain) * WAP_EC3(default_gain);
   const int delay = s.fd_min_filter_delay;
-  const bool add_reverb = usable || !transparent;
+  const bool add_reverb = usable || (WAP_EC3(model_reverb_in_nonlinear_mode) && !transparent);
   // AecState::ReverbDecay(mild = dominant_nearend) (residual_echo_estimator.cc:384, aec_state.h:127)
   const float reverb_decay = dominant_nearend ? WAP_EC3(nearend_len) : WAP_EC3(default_len);
   const int first_reverb_partition = usable ? s.fa_filter_length_blocks + 1 : delay + 1;
@@ -636,8 +639,10 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   // (residual_echo_estimator.cc:249-251, subband_erle_estimator.h:46-50)
   const bool onset_compensated = WAP_EC3(erle_onset_compensation_in_dominant_nearend) || !dominant_nearend;
   const float* erle = (onset_compensated && WAP_EC3(erle_onset_detection)) ? a.erle_onset_comp : a.erle;
-  const int w0 = ring_off(s.spectra_read, imax(0, delay - 1), kRingBlocks);
-  const int wn = delay + 1 - imax(0, delay - 1) + 1;  // spectra in the window
+  // GetRenderIndexesToAnalyze (residual_echo_estimator.cc:70-86): echo_model.render_pre / _post_window_size
+  const int w_first = imax(0, delay - WAP_EC3(render_pre_window_size));
+  const int w0 = ring_off(s.spectra_read, w_first, kRingBlocks);
+  const int wn = delay + WAP_EC3(render_post_window_size) - w_first + 1;  // spectra in the window
   #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
     // UpdateRenderNoisePower
@@ -800,11 +805,19 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
     // MovingAverage::Average (mem_len 4 -> 3 stored blocks, scaling 1/4)
     const float in = nearend[k];
     float ne = in;
-    ne = a.nearend_mem[0][k] + ne;
-    ne = a.nearend_mem[1][k] + ne;
-    ne = a.nearend_mem[2][k] + ne;
-    ne *= 0.25f;
-    a.nearend_mem[mem_index][k] = in;
+    constexpr bool kFourBlocks = !WAP_EC3_RUNTIME;   // the default: mem_len 4 -> 3 stored blocks, scaling 1/4
+    if (kFourBlocks || WAP_EC3(nearend_average_blocks) == 4) {
+      ne = a.nearend_mem[0][k] + ne;
+      ne = a.nearend_mem[1][k] + ne;
+      ne = a.nearend_mem[2][k] + ne;
+      ne *= 0.25f;
+      a.nearend_mem[mem_index][k] = in;
+    } else {
+      const int n_mem = WAP_EC3(nearend_average_blocks) - 1;   // 0..2 stored blocks
+      for (int j = 0; j < n_mem; ++j) ne = a.nearend_mem[j][k] + ne;
+      ne *= fdiv(1.f, (float)WAP_EC3(nearend_average_blocks));
+      if (n_mem > 0) a.nearend_mem[mem_index][k] = in;
+    }
     // WeightEchoForAudibility: bins [0,3) / [3,7) / [7,65) (suppression_gain.cc:104-118)
     const float audibility = k < 3 ? WAP_EC3(audibility_threshold_lf) : (k < 7 ? WAP_EC3(audibility_threshold_mf) : WAP_EC3(audibility_threshold_hf));
     const float threshold = WAP_EC3(floor_power) * audibility;
@@ -884,7 +897,10 @@ WAP_DEV void suppression_gain_get_gain(Aec3State& a, AecScratch& sc, const float
       r.gain[k] = sqrtf(g);
     }
   }
-  if (lane == 0) s.sg_nearend_mem_index = (mem_index + 1) % 3;
+  if (lane == 0) {
+    const int n_mem = imax(1, WAP_EC3(nearend_average_blocks) - 1);
+    s.sg_nearend_mem_index = WAP_EC3(nearend_average_blocks) > 1 ? (mem_index + 1) % n_mem : 0;
+  }
   __syncwarp();
 }
 
@@ -988,7 +1004,9 @@ WAP_DEV void echo_remover_process_capture(Aec3State& a, const EngineConfig& cfg,
   {
     const float y2 = sc.red[0], e2_refined = sc.red[1], e2_coarse = sc.red[2], s2_refined = sc.red[3], s2_coarse = sc.red[4];
     bool use_refined_output = true;
-    if (e2_coarse < 0.9f * e2_refined && y2 > 30.f * 30.f * kBlock &&
+    if (!WAP_EC3(enable_coarse_filter_output_usage)) {
+      // filter.enable_coarse_filter_output_usage = false: always the refined filter's output
+    } else if (e2_coarse < 0.9f * e2_refined && y2 > 30.f * 30.f * kBlock &&
         (s2_refined > 60.f * 60.f * kBlock || s2_coarse > 60.f * 60.f * kBlock)) {
       use_refined_output = false;
     } else if (e2_coarse < e2_refined && y2 < e2_refined) {

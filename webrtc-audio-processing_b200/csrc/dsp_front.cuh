@@ -99,8 +99,11 @@ WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const flo
   // InsertBlock: decimate and store the sub-block reversed at the low-rate write index.
   Biquad d0 = a.render_decimator[0], d1 = a.render_decimator[1], d2 = a.render_decimator[2], d3 = a.render_decimator[3];
   const int lw = s.lr_write;
+  // render_levels.render_power_gain_db (render_delay_buffer.cc:124-125,405-414): the stored block, and
+  // everything derived from it, is scaled; the activity detection above saw the block as it came
+  const float rgain = ep.render_linear_amplitude_gain;
   for (int i = 0; i < kBlock; ++i) {
-    const float xi = x[i];
+    const float xi = rgain != 1.f ? x[i] * rgain : x[i];
     ts.render_blocks[r][i] = xi;
     float v = biquad_step(kDecimator4[0], d0, xi);
     v = biquad_step(kDecimator4[1], d1, v);
@@ -292,6 +295,10 @@ WAP_DEV void front_leg(const TickArgs& a, int idx) {
     if (up) {
       front_slice_band(rbands + kFrame, up->render_blocker_hi[0], L, nrb, up->render_blocks_hi, 0);
       if (B == 3) front_slice_band(rbands + 2 * kFrame, up->render_blocker_hi[1], L, nrb, up->render_blocks_hi, 1);
+      if (a.ep.render_linear_amplitude_gain != 1.f)
+        for (int b = 0; b < nrb; ++b)
+          for (int bi = 0; bi < B - 1; ++bi)
+            for (int j = 0; j < kBlock; ++j) up->render_blocks_hi[b][bi][j] *= a.ep.render_linear_amplitude_gain;
     }
     s.render_blocker_len = rem;
   }

@@ -63,6 +63,12 @@ struct Ec3Params {
   int erle_onset_detection, clamp_quality_estimate_to_zero, clamp_quality_estimate_to_one;
   int has_clock_drift, linear_and_stable_echo_path;
   int lf_smoothing_during_initial_phase, dn_use_during_initial_phase, dn_use_unbounded_echo_spectrum, conservative_hf_suppression;
+  // filter.conservative_initial_phase / enable_coarse_filter_output_usage / use_linear_filter,
+  // echo_model.render_pre_window_size / render_post_window_size / model_reverb_in_nonlinear_mode,
+  // suppressor.nearend_average_blocks (1..4), render_levels.render_power_gain_db as a linear amplitude gain (k_front)
+  int conservative_initial_phase, enable_coarse_filter_output_usage, use_linear_filter;
+  int render_pre_window_size, render_post_window_size, model_reverb_in_nonlinear_mode, nearend_average_blocks;
+  float render_linear_amplitude_gain;
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -106,6 +112,9 @@ constexpr int erle_onset_detection = 1, clamp_quality_estimate_to_zero = 1, clam
 constexpr int has_clock_drift = 0, linear_and_stable_echo_path = 0;
 constexpr int lf_smoothing_during_initial_phase = 1, dn_use_during_initial_phase = 1, dn_use_unbounded_echo_spectrum = 1,
               conservative_hf_suppression = 0;
+constexpr int conservative_initial_phase = 0, enable_coarse_filter_output_usage = 1, use_linear_filter = 1;
+constexpr int render_pre_window_size = 1, render_post_window_size = 1, model_reverb_in_nonlinear_mode = 1, nearend_average_blocks = 4;
+constexpr float render_linear_amplitude_gain = 1.f;
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -145,6 +154,9 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(clamp_quality_estimate_to_zero); WAP_SET(clamp_quality_estimate_to_one); WAP_SET(has_clock_drift);
   WAP_SET(linear_and_stable_echo_path); WAP_SET(lf_smoothing_during_initial_phase); WAP_SET(dn_use_during_initial_phase);
   WAP_SET(dn_use_unbounded_echo_spectrum); WAP_SET(conservative_hf_suppression);
+  WAP_SET(conservative_initial_phase); WAP_SET(enable_coarse_filter_output_usage); WAP_SET(use_linear_filter);
+  WAP_SET(render_pre_window_size); WAP_SET(render_post_window_size); WAP_SET(model_reverb_in_nonlinear_mode);
+  WAP_SET(nearend_average_blocks); WAP_SET(render_linear_amplitude_gain);
 #undef WAP_SET
   return p;
 }

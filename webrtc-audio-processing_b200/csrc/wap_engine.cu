@@ -500,19 +500,15 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.filter.refined_initial.length_blocks >= 1 && c.filter.refined_initial.length_blocks <= c.filter.refined.length_blocks &&
       c.filter.coarse_initial.length_blocks >= 1 && c.filter.coarse_initial.length_blocks <= c.filter.coarse.length_blocks &&
       c.filter.config_change_duration_blocks >= 1 &&
-      c.filter.conservative_initial_phase == d.filter.conservative_initial_phase &&
-      c.filter.enable_coarse_filter_output_usage == d.filter.enable_coarse_filter_output_usage &&
-      c.filter.use_linear_filter == d.filter.use_linear_filter &&
       c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
       c.erle.num_sections == 1 &&
       c.ep_strength.default_len >= 0.f && c.ep_strength.nearend_len >= 0.f &&   // negative: adaptive reverb decay
 
       !c.echo_audibility.use_stationarity_properties && !c.echo_audibility.use_stationarity_properties_at_init &&
-      c.render_levels.render_power_gain_db == 0.f &&
 
-      c.echo_model.render_pre_window_size == 1 && c.echo_model.render_post_window_size == 1 &&
-      c.echo_model.model_reverb_in_nonlinear_mode &&
-      c.suppressor.nearend_average_blocks == 4 &&
+      c.echo_model.render_pre_window_size >= 0 && c.echo_model.render_pre_window_size <= 100 &&
+      c.echo_model.render_post_window_size >= 0 && c.echo_model.render_post_window_size <= 100 &&
+      c.suppressor.nearend_average_blocks >= 1 && c.suppressor.nearend_average_blocks <= 4 &&
       // SubbandNearendDetector: its smoother holds at most three past blocks here
       (!c.suppressor.use_subband_nearend_detection ||
        (c.suppressor.subband_nearend_detection.nearend_average_blocks >= 1 &&
@@ -614,6 +610,15 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   p.dn_use_during_initial_phase = c.suppressor.dominant_nearend_detection.use_during_initial_phase;
   p.dn_use_unbounded_echo_spectrum = c.suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum;
   p.conservative_hf_suppression = c.suppressor.conservative_hf_suppression;
+  p.conservative_initial_phase = c.filter.conservative_initial_phase;
+  p.enable_coarse_filter_output_usage = c.filter.enable_coarse_filter_output_usage;
+  p.use_linear_filter = c.filter.use_linear_filter;
+  p.render_pre_window_size = c.echo_model.render_pre_window_size;
+  p.render_post_window_size = c.echo_model.render_post_window_size;
+  p.model_reverb_in_nonlinear_mode = c.echo_model.model_reverb_in_nonlinear_mode;
+  p.nearend_average_blocks = c.suppressor.nearend_average_blocks;
+  // RenderDelayBufferImpl: std::pow(10.0f, render_power_gain_db / 20.f) (render_delay_buffer.cc:124-125)
+  p.render_linear_amplitude_gain = powf(10.0f, c.render_levels.render_power_gain_db / 20.f);
   return p;
 }
 
@@ -973,7 +978,11 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
           c->echo_removal_control.has_clock_drift || c->echo_removal_control.linear_and_stable_echo_path ||
           !c->suppressor.lf_smoothing_during_initial_phase || !c->suppressor.dominant_nearend_detection.use_during_initial_phase ||
           !c->suppressor.dominant_nearend_detection.use_unbounded_echo_spectrum || c->suppressor.conservative_hf_suppression ||
-          c->suppressor.high_bands_suppression.max_gain_during_echo != 1.f)
+          c->suppressor.high_bands_suppression.max_gain_during_echo != 1.f ||
+          c->filter.conservative_initial_phase || !c->filter.enable_coarse_filter_output_usage || !c->filter.use_linear_filter ||
+          c->echo_model.render_pre_window_size != 1 || c->echo_model.render_post_window_size != 1 ||
+          !c->echo_model.model_reverb_in_nonlinear_mode || c->suppressor.nearend_average_blocks != 4 ||
+          c->render_levels.render_power_gain_db != 0.f)
         err = WapError::UnsupportedConfig;
     }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||
