@@ -17,6 +17,11 @@ def api_lib(request):
 MC = dict(aec=True, ns=False, mc_render=True, mc_capture=True, max_rate=48000)
 
 
+def _kw_without_ns(kw):
+    """engine kwargs on top of MC (which already fixes ns=False): an `ns` entry replaces it."""
+    return kw
+
+
 def render_variant(far, kind, rate):
     """far: interleaved stereo render.  'stereo': as is (persistent stereo content after 2 s); 'mono': both
     channels identical (the AEC keeps one downmixed render channel); 'burst': 0.5 s of stereo content, then
@@ -35,7 +40,9 @@ def run_pair(lib, oracle, rate, n_frames, kind, seed=9, right_gain=0.6, delay_ms
     far, near = stereo_leg(rate, n_frames, seed, right_gain)
     far = render_variant(far, kind, rate)
     fl = rate // 100 * 2
-    eng = wap_b200.Engine(1, rate, channels=2, lib=lib, **MC, **(engine_kw or {}))
+    ekw = dict(MC)
+    ekw.update(engine_kw or {})
+    eng = wap_b200.Engine(1, rate, channels=2, lib=lib, **ekw)
     if ref_kv is None:
         refapm = oracle.RefApm(**MC)
     else:
@@ -234,7 +241,7 @@ def test_multichannel_state_moves_between_engines(api_lib, oracle):
 
 def test_multichannel_unsupported_combinations_are_refused(api_lib):
     import wap_b200
-    for kw in (dict(MC, agc2=True), dict(MC, pre_gain=2.0), dict(MC, mc_capture=False), dict(MC, mc_render=False),
+    for kw in (dict(MC, pre_gain=2.0), dict(MC, mc_capture=False), dict(MC, mc_render=False),
                dict(MC, max_rate=32000)):
         rate = 48000 if kw.get("max_rate") == 32000 else 16000
         with pytest.raises(RuntimeError):
@@ -273,3 +280,20 @@ def test_multichannel_single_leg_entry_points(api_lib, oracle):
         out[f * fl:(f + 1) * fl] = tmp
     L.wap_destroy(h)
     assert first_bad_frame(out, ref_out, fl) is None
+
+
+@pytest.mark.parametrize("rate,n_frames,ns,gain_db", [
+    (16000, 260, False, 30.0),   # +30 dB: the limiter works on the loud passages of both channels
+    (48000, 230, True, 27.0),    # three bands, NS on both channels, AGC2 in front of the PostFilter
+])
+def test_multichannel_with_agc2_fixed_gain_and_limiter(api_lib, oracle, rate, n_frames, ns, gain_db):
+    """GainController2 (fixed digital gain + limiter) on multi-channel legs: one level estimate over the
+    channels (maximum envelope), one set of scaling factors for both."""
+    kw = dict(agc2=True, agc2_fixed_gain_db=gain_db)
+    ref = dict(agc2=1, agc2_gain_db=gain_db)
+    if ns:
+        kw.update(ns=True, ns_level=1)
+        ref.update(ns=1, ns_level=1)
+    out, ref_out = run_pair(api_lib, oracle, rate, n_frames, "stereo", seed=5, engine_kw=_kw_without_ns(kw), ref_kv=ref)
+    assert first_bad_frame(out, ref_out, rate // 100 * 2) is None
+    assert np.abs(ref_out.astype(np.int32)).max() > 15000      # loud enough for the limiter to matter

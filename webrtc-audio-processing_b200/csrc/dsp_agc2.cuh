@@ -133,4 +133,78 @@ WAP_DEV void agc2_process(Agc2State& st, const EngineConfig& cfg, float* frame, 
   __syncwarp();
 }
 
+// The same for the C channels of a multi-channel leg (frames[c]: flen samples each): one gain applier
+// ramp, one level estimate -- the envelope is the maximum over the channels
+// (fixed_digital_level_estimator.cc:62-75) -- and one set of per-sample factors for every channel.
+WAP_DEV void agc2_process_channels(Agc2State& st, const EngineConfig& cfg, float* const* frames, int C, int flen, float* fac) {
+  const int lane = lane_id();
+  const int sub = flen / kAgc2SubFrames;
+  __syncwarp();
+  const float g_last = st.gain_last, g = st.gain_current;
+  if (st.reset_limiter) {
+    __syncwarp();
+    if (lane == 0) { st.filter_state_level = 0.f; st.reset_limiter = 0; }
+    __syncwarp();
+  }
+  if (g_last != g) {
+    const float increment = (g - g_last) * (1.f / flen);
+    if (lane == 0) {
+      float gain = g_last;
+      for (int i = 0; i < flen; ++i) { fac[i] = gain; gain += increment; }
+    }
+    __syncwarp();
+    for (int c = 0; c < C; ++c)
+      for (int i = lane; i < flen; i += 32) frames[c][i] *= fac[i];
+    __syncwarp();
+    if (lane == 0) st.gain_last = g;
+    __syncwarp();
+  } else if (!(1.f - 1.f / 32767.f <= g && g <= 1.f + 1.f / 32767.f)) {
+    for (int c = 0; c < C; ++c)
+      for (int i = lane; i < flen; i += 32) frames[c][i] *= g;
+    __syncwarp();
+  }
+  float env = 0.f;
+  if (lane < kAgc2SubFrames)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < sub; ++j) env = fmaxr(env, fabsf(frames[c][lane * sub + j]));
+  const float next = __shfl_down_sync(WAP_FULL, env, 1);
+  if (lane < kAgc2SubFrames - 1 && env < next) env = next;
+  float level = st.filter_state_level;
+  float mine = 0.f;
+  for (int sf = 0; sf < kAgc2SubFrames; ++sf) {
+    const float v = __shfl_sync(WAP_FULL, env, sf);
+    float out;
+    if (v > level) out = v * (1 - 0.0f) + level * 0.0f;
+    else out = v * (1 - 0.9971259f) + level * 0.9971259f;
+    level = out;
+    if (lane == sf + 1) mine = out;
+  }
+  float factor = (lane == 0) ? st.last_scaling_factor : agc2_lookup_gain(mine);
+  if (lane > kAgc2SubFrames) factor = 0.f;
+  const float f_next = __shfl_down_sync(WAP_FULL, factor, 1);
+  const float f0 = __shfl_sync(WAP_FULL, factor, 0), f1 = __shfl_sync(WAP_FULL, factor, 1);
+  const bool is_attack = f0 > f1;
+  if (lane < kAgc2SubFrames) {
+    if (lane == 0 && is_attack) {
+      for (int i = 0; i < sub; ++i) {
+        const float t = (float)i / sub;
+        const double b = (double)(1.f - t), b2 = b * b, b4 = b2 * b2;
+        fac[i] = (float)(b4 * b4) * (factor - f_next) + f_next;
+      }
+    } else {
+      const float diff = (f_next - factor) / sub;
+      for (int j = 0; j < sub; ++j) fac[lane * sub + j] = factor + diff * j;
+    }
+  }
+  __syncwarp();
+  for (int c = 0; c < C; ++c)
+    for (int i = lane; i < flen; i += 32) frames[c][i] = clampr(frames[c][i] * fac[i], -32768.f, 32767.f);
+  const float last = __shfl_sync(WAP_FULL, factor, kAgc2SubFrames);
+  if (lane == 0) {
+    st.filter_state_level = level;
+    st.last_scaling_factor = last;
+  }
+  __syncwarp();
+}
+
 }  // namespace wap

@@ -301,7 +301,7 @@ WapError resolve_config(const WapConfig& c, const WapFormats& fm, EngineConfig* 
     // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) with or
     // without the noise suppressor, at a native rate of 16 or 48 kHz, one format for all three streams.
     if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) ||
-        c.gain_controller2_enabled || c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.pre_stage ||
+        c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.pre_stage ||
         e.resample_out || e.num_bands == 2 || !same_format(fm.in, fm.out) || !same_format(fm.in, fm.render))
       return WapError::UnsupportedConfig;
     e.mc = 1;

@@ -14,6 +14,7 @@
 #endif
 #define WAP_EC3_RUNTIME 1
 
+#include "dsp_agc2.cuh"
 #include "dsp_mc_front.cuh"
 #include "dsp_mc_remover.cuh"
 #include "wap_kernels.h"
@@ -222,19 +223,35 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   }
   const bool zero_out = !output_used_last_frame && output_used;   // first frame after un-muting
   if (lane == 0) st.capture_output_used_last_frame = output_used ? 1 : 0;
-  for (int c = 0; c < C; ++c) {
-    const float* bands = bands_all + c * flen;
-    float* full = work;
-    __syncwarp();
-    if (B == 3) {
+  // Band merge per channel: the merged frame of channel c replaces its bands in `bands_all`.
+  if (B == 3) {
+    for (int c = 0; c < C; ++c) {
+      float* bands = bands_all + c * flen;
+      float* full = work;
+      __syncwarp();
       three_band_synthesis(bands, full, work + flen, mc.cio[c].bands.synthesis);
       __syncwarp();
+      for (int i = lane; i < flen; i += 32) bands[i] = full[i];
+    }
+    __syncwarp();
+  }
+  // GainController2 (fixed gain + limiter) on the merged frames of all channels, while the output is used
+  // (audio_processing_impl.cc:1450-1477), in front of the PostFilter
+  if (cfg.agc2_enabled && output_used) {
+    float* frames[kMcCh];
+    for (int c = 0; c < C; ++c) frames[c] = bands_all + c * flen;
+    agc2_process_channels(st.agc2, cfg, frames, C, flen, work);
+  }
+  for (int c = 0; c < C; ++c) {
+    const float* full = bands_all + c * flen;
+    __syncwarp();
+    if (B == 3) {
       // 48 kHz: PostFilter and the output conversion are serial work for k_mc_post
       for (int i = lane; i < flen; i += 32) mt.capture_frame[c][i] = zero_out ? 0.f : full[i];
       if (lane == 0) mt.gain_change = zero_out ? 1 : 0;   // reused as k_mc_post's "zero this frame" flag
     } else {
       for (int i = lane; i < flen; i += 32) {
-        float v = zero_out ? 0.f : bands[i];
+        float v = zero_out ? 0.f : full[i];
         if (a.fmt == 0) {
           v = fminr(v, 32767.f);
           v = fmaxr(v, -32768.f);
