@@ -7,4 +7,4 @@ SMALL="--streams 16384 --steps 4 --warmup 2 --settle 300 --no-cpu-baseline --no-
 python bench.py $SMALL > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 310 -c $CNT -o gpurun_out/prof_$TAG python bench.py $SMALL > gpurun_out/ncu_f_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_f_$TAG.log
-cp webrtc-audio-processing_b200/libwap_b200.so gpurun_out/libwap_b200_$TAG.so
+ls -la gpurun_out/prof_$TAG.ncu-rep

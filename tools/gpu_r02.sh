@@ -21,6 +21,6 @@ if [ "$2" = "ncu" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 60 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py $SMALL > gpurun_out/ncu_l_$TAG.log 2>&1
   python bench.py $SMALL > gpurun_out/plain2_$TAG.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:"k_front|k_delay|k_echo" -s 915 -c 6 -o gpurun_out/prof_$TAG python bench.py $SMALL > gpurun_out/ncu_f_$TAG.log 2>&1
-  cp webrtc-audio-processing_b200/libwap_b200.so gpurun_out/libwap_b200_$TAG.so
+  ls -la gpurun_out/prof_$TAG.ncu-rep   # (the profiled library is the snapshot's own build: not copied back, gpurun_out is capped at 64 MiB)
 fi
 ls -la gpurun_out | tail -20
