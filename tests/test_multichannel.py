@@ -241,7 +241,7 @@ def test_multichannel_state_moves_between_engines(api_lib, oracle):
 
 def test_multichannel_unsupported_combinations_are_refused(api_lib):
     import wap_b200
-    for kw in (dict(MC, pre_gain=2.0), dict(MC, mc_capture=False), dict(MC, mc_render=False),
+    for kw in (dict(MC, mc_capture=False), dict(MC, mc_render=False),
                dict(MC, max_rate=32000)):
         rate = 48000 if kw.get("max_rate") == 32000 else 16000
         with pytest.raises(RuntimeError):
@@ -297,3 +297,35 @@ def test_multichannel_with_agc2_fixed_gain_and_limiter(api_lib, oracle, rate, n_
     out, ref_out = run_pair(api_lib, oracle, rate, n_frames, "stereo", seed=5, engine_kw=_kw_without_ns(kw), ref_kv=ref)
     assert first_bad_frame(out, ref_out, rate // 100 * 2) is None
     assert np.abs(ref_out.astype(np.int32)).max() > 15000      # loud enough for the limiter to matter
+
+
+@pytest.mark.parametrize("rate,n_frames", [(16000, 200), (48000, 160)])
+def test_multichannel_level_adjustment_and_runtime_settings(api_lib, oracle, rate, n_frames):
+    """CaptureLevelsAdjuster on multi-channel legs (pre gain behind the high-pass filters, post gain behind AGC2 /
+    the PostFilter, ramped, the same for both channels) and the echo-path gain-change flag a changed pre gain or
+    playout volume raises -- with runtime changes in the middle of the call."""
+    import wap_b200
+    far, near = stereo_leg(rate, n_frames, 7, 0.6)
+    fl = rate // 100 * 2
+    kw = dict(MC)
+    kw.update(pre_gain=1.5, post_gain=0.8, agc2=True, agc2_fixed_gain_db=3.0)
+    eng = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **kw)
+    ref = oracle.RefApm(kv=dict(aec=1, ns=0, mc_render=1, mc_capture=1, max_rate=48000, cla=1, cla_pre=1.5, cla_post=0.8,
+                                agc2=1, agc2_gain_db=3.0))
+    events = {40: ("pre_gain", 2.5), 70: ("playout_volume", 90), 71: ("playout_volume", 140), 100: ("post_gain", 1.7),
+              130: ("pre_gain", 0.6)}
+    out = np.zeros_like(near)
+    ref_out = np.zeros_like(near)
+    for f in range(n_frames):
+        if f in events:
+            what, val = events[f]
+            getattr(eng, "set_" + what)(val)
+            getattr(ref, "set_" + what)(val)
+        sl = slice(f * fl, (f + 1) * fl)
+        eng.set_stream_delay_ms(0)
+        out[sl] = eng.process(far[sl].reshape(1, fl), near[sl].reshape(1, fl)).reshape(-1)
+        ro, _, err = ref.run_i16(rate, far[sl], near[sl], render_ch=2, capture_ch=2)
+        assert err == 0
+        ref_out[sl] = ro
+    eng.close()
+    assert first_bad_frame(out, ref_out, fl) is None

@@ -321,18 +321,30 @@ WAP_DEV void mc_front_tick(const TickArgs& a, int idx, McFrontScratch& fs) {
   for (int c = 0; c < C; ++c)
     for (int i = lane; i < flen; i += 32) fs.bands[c][i] = front_load_sample(a.capture, idx, flen, a.fmt, i, C, c);
   __syncwarp();
-  if (lane < C && cfg.hpf_enabled) {   // HighPassFilter: one lane per channel
+  // HighPassFilter, then CaptureLevelsAdjuster::ApplyPreLevelAdjustment (audio_processing_impl.cc:1280-1299):
+  // serial recurrences, one lane per channel; every channel sees the same gain ramp
+  LevelState& lv = st.levels;
+  const float pre_prev = lv.pre_prev, pre_target = lv.pre_target;
+  __syncwarp();
+  if (lane < C && (cfg.hpf_enabled || cfg.levels_enabled)) {
     const int c = lane;
     float* x = fs.bands[c];
     Biquad h0 = mc.cio[c].hpf[0], h1 = mc.cio[c].hpf[1], h2 = mc.cio[c].hpf[2];
+    ScalerRun pre = scaler_begin(pre_prev, pre_target, flen);
+    if (!cfg.levels_enabled) pre.mode = 0;
     for (int i = 0; i < flen; ++i) {
-      float v = biquad_step(hc[0], h0, x[i]);
-      v = biquad_step(hc[1], h1, v);
-      x[i] = biquad_step(hc[2], h2, v);
+      float v = x[i];
+      if (cfg.hpf_enabled) {
+        v = biquad_step(hc[0], h0, v);
+        v = biquad_step(hc[1], h1, v);
+        v = biquad_step(hc[2], h2, v);
+      }
+      x[i] = scaler_step(pre, v);
     }
     mc.cio[c].hpf[0] = h0; mc.cio[c].hpf[1] = h1; mc.cio[c].hpf[2] = h2;
   }
   __syncwarp();
+  if (lane == 0 && cfg.levels_enabled) lv.pre_prev = pre_target;
   for (int c = 0; c < C; ++c) {
     for (int i = lane; i < flen; i += 32) {
       const float v = fs.bands[c][i];
@@ -350,8 +362,16 @@ WAP_DEV void mc_front_tick(const TickArgs& a, int idx, McFrontScratch& fs) {
   __syncwarp();
   if (lane == 0) {
     st.aec.s.saturated_microphone_signal = saturated ? 1 : 0;
-    // echo_path_gain_change = level_change || aec_reference_is_downmixed_stereo (echo_canceller3.cc:168-170)
-    mt.gain_change = mc.det.temporary ? 1 : 0;
+    // echo_path_gain_change = level_change || aec_reference_is_downmixed_stereo (echo_canceller3.cc:168-170);
+    // level_change: a changed pre-gain or playout volume (audio_processing_impl.cc:1316-1341)
+    int gc = 0;
+    if (cfg.levels_enabled) {
+      gc |= (lv.prev_pre_adjustment_gain != lv.pre_target && lv.prev_pre_adjustment_gain >= 0.f) ? 1 : 0;
+      lv.prev_pre_adjustment_gain = lv.pre_target;
+    }
+    gc |= (lv.prev_playout_volume != lv.playout_volume && lv.prev_playout_volume >= 0) ? 1 : 0;
+    lv.prev_playout_volume = lv.playout_volume;
+    mt.gain_change = (gc || mc.det.temporary) ? 1 : 0;
     ts.pad_[1] = mt.gain_change;
   }
   {

@@ -300,8 +300,7 @@ WapError resolve_config(const WapConfig& c, const WapFormats& fm, EngineConfig* 
   if (buf_channels == 2 && fm.render.num_channels == 2 && (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture)) {
     // True multi-channel processing (BASELINE config 4): both flags, AEC3 (+ its high-pass filter) with or
     // without the noise suppressor, at a native rate of 16 or 48 kHz, one format for all three streams.
-    if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) ||
-        c.pre_amplifier_enabled || c.capture_level_adjustment_enabled || e.pre_stage ||
+    if (!(c.pipeline_multi_channel_render && c.pipeline_multi_channel_capture) || e.pre_stage ||
         e.resample_out || e.num_bands == 2 || !same_format(fm.in, fm.out) || !same_format(fm.in, fm.render))
       return WapError::UnsupportedConfig;
     e.mc = 1;

@@ -242,6 +242,40 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
     for (int c = 0; c < C; ++c) frames[c] = bands_all + c * flen;
     agc2_process_channels(st.agc2, cfg, frames, C, flen, work);
   }
+  // CaptureLevelsAdjuster::ApplyPostLevelAdjustment (audio_processing_impl.cc:1526-1528) at 16 kHz; at
+  // 48 kHz it follows the PostFilter in k_mc_post.  The ramp is a serial chain (lane 0), the same for
+  // every channel.
+  if (cfg.levels_enabled && output_used && B != 3) {
+    LevelState& lv = st.levels;
+    __syncwarp();
+    const float prev = lv.post_prev, target = lv.post_target;
+    __syncwarp();
+    ScalerRun run = scaler_begin(prev, target, flen);
+    if (run.mode >= 2) {
+      if (lane == 0)
+        for (int i = 0; i < flen; ++i) {
+          run.gain = run.mode == 2 ? fminr(run.gain + run.increment, run.target) : fmaxr(run.gain + run.increment, run.target);
+          work[i] = run.gain;
+        }
+      __syncwarp();
+    }
+    if (run.mode != 0)
+      for (int c = 0; c < C; ++c)
+        for (int i = lane; i < flen; i += 32) {
+          const float g = run.mode >= 2 ? work[i] : prev;
+          bands_all[c * flen + i] = fminr(fmaxr(bands_all[c * flen + i] * g, -32768.f), 32767.f);
+        }
+    __syncwarp();
+    if (lane == 0) lv.post_prev = target;
+  }
+  if (B == 3 && lane == 0) {   // the ramp k_mc_post applies behind the PostFilter
+    LevelState& lv = st.levels;
+    const bool on = cfg.levels_enabled && output_used;
+    mt.post_gain_on = on ? 1 : 0;
+    mt.post_gain_prev = lv.post_prev;
+    mt.post_gain_target = lv.post_target;
+    if (on) lv.post_prev = lv.post_target;
+  }
   for (int c = 0; c < C; ++c) {
     const float* full = bands_all + c * flen;
     __syncwarp();
@@ -277,6 +311,10 @@ WAP_DEV void mc_post_leg(const TickArgs& a, int idx, int c) {
   Biquad p0 = mc.post_filter[c][0], p1 = mc.post_filter[c][1], p2 = mc.post_filter[c][2], p3 = mc.post_filter[c][3];
   const bool zero = mc.tick.gain_change != 0;
   const bool used = st.capture_output_used != 0;
+  // post level adjustment behind the PostFilter: both channel threads of the leg run the ramp k_mc_echo
+  // recorded for this frame
+  ScalerRun post = scaler_begin(mc.tick.post_gain_prev, mc.tick.post_gain_target, flen);
+  if (!mc.tick.post_gain_on) post.mode = 0;
   for (int i = 0; i < flen; ++i) {
     float v = mc.tick.capture_frame[c][i];
     if (used) {
@@ -285,6 +323,7 @@ WAP_DEV void mc_post_leg(const TickArgs& a, int idx, int c) {
       v = biquad_step(kPostFilter48k[2], p2, v);
       v = biquad_step(kPostFilter48k[3], p3, v);
     }
+    v = scaler_step(post, v);
     if (zero) v = 0.f;
     if (a.fmt == 0) {
       float w = fminr(v, 32767.f);
@@ -323,6 +362,7 @@ __global__ void __launch_bounds__(128) k_mc_echo(TickArgs a, int scratch_floats)
 
 __global__ void k_mc_post(TickArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // (the two channel threads of a leg are neighbouring lanes of one warp: both exist or neither)
   if (t < a.n * 2) mc_post_leg(a, t >> 1, t & 1);
 }
 

@@ -101,6 +101,9 @@ struct alignas(16) McTick {
   float capture_frame[kMcCh][kFrame * kMaxBands];   // k_mc_echo: the processed bands; then the merged full-band frame
   int render_channels[3];    // channels of render block r (1: downmixed, 2: as is)
   int gain_change;           // echo_path_gain_change of this tick's capture blocks
+  // k_mc_echo -> k_mc_post (48 kHz): the post level adjustment's gain ramp of this frame (mode 0: none)
+  float post_gain_prev, post_gain_target;
+  int post_gain_on, pad_post_;
 };
 
 struct alignas(16) McState {
