@@ -389,10 +389,16 @@ def test_emu_stereo_default_pipeline(emu_lib, oracle, rate, max_rate, right_gain
         assert not np.array_equal(alt, ref_out)
 
 
-def test_emu_stereo_without_aec_is_refused(emu_lib):
+def test_emu_unbuilt_channel_layouts_are_refused(emu_lib):
+    """Stereo without AEC3 is built (tests/test_multichannel.py) at 16 / 48 kHz native; through the resamplers,
+    at 32 kHz, or with more than two channels it is refused, not approximated."""
     import wap_b200
     with pytest.raises(RuntimeError):
-        wap_b200.Engine(1, 16000, channels=2, lib=emu_lib, aec=False, ns=True)
+        wap_b200.Engine(1, 32000, channels=2, lib=emu_lib, aec=False, ns=True)
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=False, ns=True, max_rate=32000)
+    with pytest.raises(RuntimeError):
+        wap_b200.Engine(1, 48000, channels=2, lib=emu_lib, aec=False, ns=False, hpf=False, agc2=True)
     with pytest.raises(RuntimeError):
         wap_b200.Engine(1, 16000, channels=3, lib=emu_lib, aec=True, ns=True)
 

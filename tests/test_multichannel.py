@@ -329,3 +329,33 @@ def test_multichannel_level_adjustment_and_runtime_settings(api_lib, oracle, rat
         ref_out[sl] = ro
     eng.close()
     assert first_bad_frame(out, ref_out, fl) is None
+
+
+@pytest.mark.parametrize("rate,n_frames,kw,ref", [
+    (16000, 260, dict(ns=True, ns_level=1), dict(ns=1, ns_level=1)),
+    (48000, 240, dict(ns=True, ns_level=2, agc2=True, agc2_fixed_gain_db=24.0), dict(ns=1, ns_level=2, agc2=1, agc2_gain_db=24.0)),
+    (16000, 120, dict(ns=False, hpf=True, agc2=True, agc2_fixed_gain_db=30.0, pre_gain=1.3, post_gain=0.9),
+     dict(ns=0, hpf=1, agc2=1, agc2_gain_db=30.0, cla=1, cla_pre=1.3, cla_post=0.9)),
+])
+def test_stereo_without_echo_canceller(api_lib, oracle, rate, n_frames, kw, ref):
+    """Stereo capture without AEC3: the reference keeps both channels (the reduction to one channel only happens
+    next to an echo controller) -- high-pass filter per channel, noise suppressor with its minima over the
+    channels, AGC2 with one level estimate, level adjustment -- whatever the pipeline flags say."""
+    import wap_b200
+    _, near = stereo_leg(rate, n_frames, 11, 0.7)
+    fl = rate // 100 * 2
+    for flags in (dict(mc_render=False, mc_capture=False), dict(mc_render=True, mc_capture=True)):
+        ekw = dict(aec=False, max_rate=48000)
+        ekw.update(kw)
+        ekw.update(flags)
+        eng = wap_b200.Engine(1, rate, channels=2, lib=api_lib, **ekw)
+        rkv = dict(aec=0, max_rate=48000, mc_render=int(flags["mc_render"]), mc_capture=int(flags["mc_capture"]))
+        rkv.update(ref)
+        ref_out, _, err = oracle.RefApm(kv=rkv).run_i16(rate, None, near, render_ch=2, capture_ch=2)
+        assert err == 0
+        out = np.zeros_like(near)
+        for f in range(n_frames):
+            out[f * fl:(f + 1) * fl] = eng.process(None, near[f * fl:(f + 1) * fl].reshape(1, fl)).reshape(-1)
+        eng.close()
+        assert first_bad_frame(out, ref_out, fl) is None, flags
+        assert np.any(out[0::2] != out[1::2])

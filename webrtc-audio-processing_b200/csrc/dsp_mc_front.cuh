@@ -211,12 +211,12 @@ WAP_DEV void mc_front_tick(const TickArgs& a, int idx, McFrontScratch& fs) {
   const bool render_live = !(cfg.reinit_on_first_capture && !st.seen_capture);
   const int delay_ms = a.capture ? (a.delays_ms ? a.delays_ms[idx] : a.uniform_delay_ms) : -1;
   __syncwarp();
-  if (lane == 0 && delay_ms >= 0) rdb_set_audio_buffer_delay(st.aec.s, delay_ms);
+  if (lane == 0 && delay_ms >= 0 && cfg.aec_enabled) rdb_set_audio_buffer_delay(st.aec.s, delay_ms);
   __syncwarp();
 
-  // ---------------- render
+  // ---------------- render (stereo legs without AEC3 have no render side)
   int nrb = 0;
-  if (a.render && render_live) {
+  if (a.render && render_live && cfg.aec_enabled) {
     for (int c = 0; c < RI; ++c) {
       for (int i = lane; i < flen; i += 32) fs.full[i] = front_load_sample(a.render, idx, flen, a.fmt, i, RI, c);
       __syncwarp();
@@ -354,9 +354,17 @@ WAP_DEV void mc_front_tick(const TickArgs& a, int idx, McFrontScratch& fs) {
     __syncwarp();
     if (B == 3) three_band_analysis(fs.full, fs.bands[c], fs.sub, mc.cio[c].bands.analysis);
     __syncwarp();
-    // NoiseSuppressor::Analyze (k_mc_echo) looks at band 0 of the capture frame in front of the echo canceller
-    if (cfg.ns_enabled)
+    // NoiseSuppressor::Analyze (k_mc_echo) looks at band 0 of the capture frame in front of the echo canceller;
+    // without AEC3 the bands go to k_mc_echo as they are
+    if (!cfg.aec_enabled)
+      for (int i = lane; i < flen; i += 32) mt.capture_frame[c][i] = fs.bands[c][i];
+    else if (cfg.ns_enabled)
       for (int i = lane; i < kFrame; i += 32) mt.capture_frame[c][i] = fs.bands[c][i];
+  }
+  if (!cfg.aec_enabled) {
+    if (lane == 0 && cfg.levels_enabled) st.levels.prev_pre_adjustment_gain = st.levels.pre_target;
+    __syncwarp();
+    return;
   }
   const bool saturated = __any_sync(WAP_FULL, sat);
   __syncwarp();

@@ -291,9 +291,18 @@ WapError resolve_config(const WapConfig& c, const WapFormats& fm, EngineConfig* 
   // runs NS / AGC2 on both channels).  The flags only matter for frames with more than one channel
   // (mono legs run the mono EchoCanceller3Config whatever they say: config_selector.cc:44-58).
   const int buf_channels = fm.out.num_channels;
-  if (buf_channels > 2 || fm.in.num_channels > 8 || fm.render.num_channels > 8 ||
-      (buf_channels == 2 && !c.echo_canceller_enabled))
-    return WapError::UnsupportedConfig;
+  if (buf_channels > 2 || fm.in.num_channels > 8 || fm.render.num_channels > 8) return WapError::UnsupportedConfig;
+  if (buf_channels == 2 && !c.echo_canceller_enabled) {
+    // Stereo capture without an echo controller: both channels run through the high-pass filter, the noise
+    // suppressor (minima over the channels) and AGC2 whatever the pipeline flags say (the reduction to one
+    // channel only happens next to an echo controller, audio_processing_impl.cc:1365-1373).  Served by the
+    // multi-channel kernels with their AEC3 half switched off; native 16 / 48 kHz, stereo input.
+    // (48 kHz frames are only split into bands next to a multi-band submodule: AGC2 alone is not one)
+    if (e.pre_stage || e.resample_out || e.fullband_out || e.num_bands == 2 || fm.in.num_channels != 2 ||
+        (e.num_bands == 3 && !multi_band))
+      return WapError::UnsupportedConfig;
+    e.mc = 1;
+  }
   if (buf_channels == 2 && fm.render.num_channels != 2 && c.echo_canceller_enabled &&
       (c.pipeline_multi_channel_render || c.pipeline_multi_channel_capture))
     return WapError::UnsupportedConfig;
@@ -785,7 +794,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     wap::launch_k_mc_front(grid_for(n), wpb * 32, (size_t)wpb * e->mc_front_floats * sizeof(float), e->stream, a, e->mc_front_floats);
     e->launches++;
     if (timing) cudaEventRecord(e->ev[1], e->stream);
-    if (d_capture) {
+    if (d_capture && e->cfg.aec_enabled) {
       wap::launch_k_delay_rt(grid_for(n), wpb * 32, (size_t)wpb * e->delay_scratch_floats * sizeof(float), e->stream, a,
                              e->delay_scratch_floats);
       e->launches++;
@@ -795,7 +804,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     const int ew = e->mc_echo_wpb;
     wap::launch_k_mc_echo((n + ew - 1) / ew, ew * 32, (size_t)ew * e->mc_echo_floats * sizeof(float), e->stream, a, e->mc_echo_floats);
     e->launches++;
-    if (e->cfg.num_bands == 3 && d_capture) {
+    if (e->cfg.num_bands == 3 && d_capture && e->cfg.aec_enabled) {
       wap::launch_k_mc_post(e->stream, a);
       e->launches++;
     }

@@ -93,11 +93,13 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   cfg.capture_output_used = output_used ? 1 : 0;
   const bool persistent = mc.det.persistent != 0;
   const int R = persistent ? 2 : 1;
+  const bool aec = cfg.aec_enabled != 0;   // stereo legs without AEC3: high-pass filter, NS, AGC2, levels only
   __syncwarp();
-  stage_ec3_params(a, sc, persistent);
+  if (aec) stage_ec3_params(a, sc, persistent);
 
   // ---------------- render side
-  for (int r = 0; r < ts.n_render_blocks; ++r) mc_render_insert_vector(mc, sc, ts.rins[r], r, R, B);
+  if (aec)
+    for (int r = 0; r < ts.n_render_blocks; ++r) mc_render_insert_vector(mc, sc, ts.rins[r], r, R, B);
   if (!a.capture) return;
 
   // ---------------- NoiseSuppressor::Analyze on the capture frame in front of the echo canceller
@@ -123,10 +125,11 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
       for (int c = 0; c < C; ++c) ns_analyze_channel(ns[c], cfg, frame + c * kFrame, nsc, naf);
     }
     __syncwarp();
-    stage_ec3_params(a, sc, persistent);   // the NS scratch overlaid them
+    if (aec) stage_ec3_params(a, sc, persistent);   // the NS scratch overlaid them
   }
 
   // ---------------- capture side: EchoCanceller3::ProcessCapture
+  if (aec) {
   aec3_stage_scalars(st.aec, sc);
   for (int c = 0; c < C; ++c) mc_stage_scalars(mc.chan[c].s, mx.cs[c]);
   __syncwarp();
@@ -187,6 +190,7 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   }
   aec3_unstage_scalars(st.aec, sc);
   for (int c = 0; c < C; ++c) mc_stage_scalars(mx.cs[c], mc.chan[c].s);
+  }
   __syncwarp();
 
   // ---------------- NoiseSuppressor::Process (noise_suppressor.cc:388-559), band merge and output
@@ -245,7 +249,7 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   // CaptureLevelsAdjuster::ApplyPostLevelAdjustment (audio_processing_impl.cc:1526-1528) at 16 kHz; at
   // 48 kHz it follows the PostFilter in k_mc_post.  The ramp is a serial chain (lane 0), the same for
   // every channel.
-  if (cfg.levels_enabled && output_used && B != 3) {
+  if (cfg.levels_enabled && output_used && !(B == 3 && aec)) {
     LevelState& lv = st.levels;
     __syncwarp();
     const float prev = lv.post_prev, target = lv.post_target;
@@ -268,7 +272,7 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
     __syncwarp();
     if (lane == 0) lv.post_prev = target;
   }
-  if (B == 3 && lane == 0) {   // the ramp k_mc_post applies behind the PostFilter
+  if (B == 3 && aec && lane == 0) {   // the ramp k_mc_post applies behind the PostFilter
     LevelState& lv = st.levels;
     const bool on = cfg.levels_enabled && output_used;
     mt.post_gain_on = on ? 1 : 0;
@@ -279,7 +283,7 @@ WAP_DEV void mc_echo_tick(const TickArgs& a, int idx, float* scratch) {
   for (int c = 0; c < C; ++c) {
     const float* full = bands_all + c * flen;
     __syncwarp();
-    if (B == 3) {
+    if (B == 3 && aec) {
       // 48 kHz: PostFilter and the output conversion are serial work for k_mc_post
       for (int i = lane; i < flen; i += 32) mt.capture_frame[c][i] = zero_out ? 0.f : full[i];
       if (lane == 0) mt.gain_change = zero_out ? 1 : 0;   // reused as k_mc_post's "zero this frame" flag
