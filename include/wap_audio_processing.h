@@ -429,7 +429,7 @@ WapEngine* wap_engine_create_with_aec3_config(int cuda_device, int32_t max_strea
  * the formats per call like the reference; a batched engine fixes them when it is created.
  * aec3_config / aec3_multichannel_config may be NULL (defaults).  Rates: multiples of 100 Hz up to
  * 96 kHz.  Refused (UnsupportedConfig), never approximated: an output of 48 kHz above the processing
- * rate whose input has another format (capture_fullband_audio), 48 kHz AEC3 with another output rate,
+ * rate whose input has another rate (capture_fullband_audio), 48 kHz AEC3 with another output rate,
  * multi-channel processing with differing formats, a rate conversion of the render pass-through output. */
 WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, WapConfig config,
                                           WapStreamConfig input, WapStreamConfig output,

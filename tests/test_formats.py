@@ -94,6 +94,9 @@ CASES = {
     "ns_only_in48k_out32k": ((48000, 1), (48000, 1), (32000, 1), dict(aec=False, ns=True, max_rate=48000)),
     "agc2_in48k_out8k": ((48000, 1), (48000, 1), (8000, 1), dict(aec=True, ns=True, agc2=True, agc2_fixed_gain_db=6.0)),
     "stereo_default_pipeline_render_mono": ((16000, 1), (16000, 2), (16000, 2), dict(aec=True, ns=True)),
+    # the reference's default routing of a 48 kHz client (processing at 32 kHz, 48 kHz full-band side buffer) with a
+    # stereo microphone and a mono uplink
+    "stereo48k_in_mono48k_out_default_max_rate": ((48000, 2), (48000, 2), (48000, 1), dict(aec=True, ns=True, max_rate=32000)),
 }
 
 
@@ -198,3 +201,26 @@ def test_single_leg_seam_with_differing_formats(api_lib, oracle):
     # a rate conversion of the pass-through output is refused, not approximated
     assert L.wap_process_reverse_stream_f32(h, src, _sc(48000, 2), _sc(16000, 2), dst2) == 7
     L.wap_destroy(h)
+
+
+def test_fullband_side_buffer_with_channel_downmix_while_muted(api_lib, oracle):
+    """48 kHz stereo in, 48 kHz mono out under the default maximum_internal_processing_rate: while the output is
+    muted the capture_fullband_audio buffer -- the downmixed, otherwise unprocessed input -- comes back."""
+    L = api_lib
+    render_fmt, in_fmt, out_fmt = (48000, 1), (48000, 2), (48000, 1)
+    cfg = dict(aec=True, ns=True, max_rate=32000)
+    frames = 60
+    r, c = _leg(8, frames, render_fmt, in_fmt)
+    ref = RefApm(kv=_ref_kv(cfg))
+    e = wap_b200.Engine(1, 48000, channels=2, lib=L, out_format=out_fmt, render_format=render_fmt, **cfg)
+    for f in range(frames):
+        if f == 20:
+            e.set_capture_output_used(False); ref.set_capture_output_used(False)
+        if f == 40:
+            e.set_capture_output_used(True); ref.set_capture_output_used(True)
+        rr, cc = r[f * 480:(f + 1) * 480], c[f * 960:(f + 1) * 960]
+        e.set_stream_delay_ms(0)
+        got = e.process(rr.reshape(1, -1), cc.reshape(1, -1)).reshape(-1)
+        want = ref.run_formats(render_fmt, in_fmt, out_fmt, rr, cc)
+        assert np.array_equal(got, want), f
+    e.close()

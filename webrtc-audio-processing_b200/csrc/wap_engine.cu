@@ -280,8 +280,10 @@ WapError resolve_config(const WapConfig& c, const WapFormats& fm, EngineConfig* 
   e.downmix_first = c.pipeline_capture_downmix_method == WapDownmixMethod::UseFirstChannel ? 1 : 0;
   // The capture_fullband_audio buffer is filled from the capture input (resampled to 48 kHz when the
   // input has another rate) and comes back unprocessed while the output is muted: only built for an
-  // input that already has the output's format.
-  if (e.fullband_out && !same_format(fm.in, fm.out)) return WapError::UnsupportedConfig;
+  // input that already has the output's rate (a channel downmix on the way in is).
+  if (e.fullband_out && (fm.in.sample_rate_hz != fm.out.sample_rate_hz ||
+                         (fm.in.num_channels != fm.out.num_channels && fm.out.num_channels != 1)))
+    return WapError::UnsupportedConfig;
   // 48 kHz AEC3 runs the PostFilter and the output conversion in k_post: the output must be 48 kHz too.
   if (e.num_bands == 3 && c.echo_canceller_enabled && e.resample_out) return WapError::UnsupportedConfig;
   // The capture AudioBuffer has the OUTPUT's channel count (an input with more channels is downmixed on

@@ -289,8 +289,23 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       rs_push(a.rs[slot_rs + 2], p, full, tmp);
       for (int i = lane_id(); i < olen; i += 32) full[i] = tmp[i];
     } else {
-      // Muted: the (multi-channel) input frame comes back, channel by channel.
-      const int total = olen * cfg.channels;   // (this path requires input format == output format)
+      // Muted: the (multi-channel) input frame comes back, channel by channel -- downmixed like the
+      // capture_fullband_audio buffer's CopyFrom when the output has fewer channels than the input
+      // (this path requires input rate == output rate).
+      if (cfg.in_channels != cfg.channels) {
+        for (int i = lane_id(); i < olen; i += 32) {
+          float v = load_raw_sample(a.capture, idx, olen, a.fmt, i, cfg.in_channels, capture_first_channel(cfg));
+          if (a.fmt == 0) {
+            reinterpret_cast<int16_t*>(a.out)[(size_t)idx * olen + i] = (int16_t)v;   // an integer already
+          } else {
+            v = fmaxr(fminr(v, 1.f), -1.f);
+            reinterpret_cast<float*>(a.out)[(size_t)idx * olen + i] = v * 32768.f * (1.f / 32768.f);
+          }
+        }
+        if (lane_id() == 0) st.capture_output_used_last_frame = 0;
+        return;
+      }
+      const int total = olen * cfg.channels;
       for (int i = lane_id(); i < total; i += 32) {
         if (a.fmt == 0) {
           reinterpret_cast<int16_t*>(a.out)[(size_t)idx * total + i] = reinterpret_cast<const int16_t*>(a.capture)[(size_t)idx * total + i];
