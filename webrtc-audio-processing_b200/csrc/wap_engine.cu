@@ -883,8 +883,14 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
 }
 
 // Number of leg ranges the host-buffer tick is pipelined over (1 = plain copy/compute/copy).
+// Legs of one full-occupancy wave of the tick's heavy kernel: 20 warps per SM for the AEC3 kernels (k_delay),
+// 24 for the kernel class without AEC3 (6 CTAs of 4 warps), whose ticks are short enough for the PCIe copies
+// to dominate the host-buffer path from much smaller batches on.
+int wave_legs(const WapEngine* e) { return e->sm_count * (e->cfg.aec_enabled ? 80 : 24); }
+
 int pipeline_chunks(WapEngine* e, int n) {
-  int chunks = e->forced_chunks ? e->forced_chunks : (n >= 4 * e->sm_count * 80 ? 4 : 1);
+  int chunks = e->forced_chunks ? e->forced_chunks : (n >= 4 * wave_legs(e) ? 4 : 1);
+
   if (e->timing || n < 2 * chunks) chunks = 1;
   if (chunks > 1 && !e->copy_in) {
     bool ok = cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1401,7 +1407,11 @@ WapError wap_process_streams(WapAudioProcessing* const* handles, int32_t n, cons
     // those two ranges are one full-occupancy wave of the warp-per-leg kernels (4 and 5 CTAs of 4 legs
     // per SM) and the middle takes the rest in at most `chunks - 3` (>= 1) ranges of whole waves: every extra
     // range costs the tail of two kernels, so there are as few as the overlap needs.
-    const int wave = e->forced_chunks ? 4 : e->sm_count * 80;
+    // (engines without AEC3 are copy-bound: first / last range of a fifth of the batch when that is more than
+    // one wave -- measured on B200 at 16,384 and 65,536 NS-only 48 kHz legs against equal ranges and against
+    // one-wave edges: 175 k / 210 k legs through host buffers instead of 137 k / 156 k)
+    int wave = e->forced_chunks ? 4 : wave_legs(e);
+    if (!e->forced_chunks && !e->cfg.aec_enabled) wave = std::max(wave, n / 5 / 128 * 128);
     int bounds[kMaxChunks + 1];
     int nr = 0;
     bounds[0] = 0;
