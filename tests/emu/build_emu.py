@@ -61,7 +61,9 @@ def build(verbose=True):
                 raise RuntimeError("emu build failed")
             if out.strip():
                 warn.append(out)
-    r = subprocess.run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread", "-ldl"], capture_output=True, text=True)
+    # (sanitizer flags in WAP_EMU_EXTRA must reach the link as well)
+    r = subprocess.run(["g++", "-shared", "-o", LIB] + [f for f in EXTRA if f.startswith("-fsanitize")] + objs +
+                       ["-lpthread", "-ldl"], capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("emu link failed")

@@ -88,7 +88,7 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
                     ("filter.export_linear_aec_output", True), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
-                    ("echo_audibility.use_stationarity_properties", True),
+                    ("delay.use_external_delay_estimator", True),
                     ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
         c.suppressor.use_subband_nearend_detection = True   # built with a smoother of at most three past blocks
@@ -276,6 +276,9 @@ SWITCHES = {
     "nearend_average_1_block": {"suppressor.nearend_average_blocks": 1},
     "render_power_gain": {"render_levels.render_power_gain_db": 6.0},
     "render_power_gain_48k": {"render_levels.render_power_gain_db": -4.5},
+    "stationarity_properties": {"echo_audibility.use_stationarity_properties": 1},
+    "stationarity_properties_at_init": {"echo_audibility.use_stationarity_properties": 1,
+                                        "echo_audibility.use_stationarity_properties_at_init": 1},
 }
 
 
@@ -325,6 +328,8 @@ SWITCH_LEGS = {
     "dominant_nearend_not_during_initial_phase": lambda: [_early_nearend_leg(700)],
     "erle_onset_compensation_in_dominant_nearend": lambda: [_render_gap_leg(1500)],
     "no_erle_onset_detection": lambda: [_render_gap_leg(1500)],
+    "stationarity_properties": lambda: [_render_gap_leg(900)],
+    "stationarity_properties_at_init": lambda: [_no_echo_leg(500)],
 }
 # reached too rarely to pin with a short leg (restated line by line, run for identity only)
 SWITCHES_NOT_EXERCISED = {"unclamped_quality_estimate", "linear_and_stable_echo_path"}

@@ -228,6 +228,122 @@ WAP_DEV void filter_analyzer_update(Aec3State& a, AecScratch& sc) {
   __syncwarp();
 }
 
+// ---- EchoAudibility / StationarityEstimator (echo_audibility.cc:37-119, stationarity_estimator.cc:41-241):
+// only with echo_audibility.use_stationarity_properties.  `delay_blocks`: MinDirectPathFilterDelay();
+// the render noise estimator walks the spectra written since the previous capture block, the
+// stationarity flags sum a window of 13 spectra around the delay (plus the render reverb).
+WAP_DEV bool sta_band_stationary(const Aec3State& a, int k) { return a.sta_flags[k] != 0 && a.sta_hangovers[k] == 0; }
+
+WAP_DEV void echo_audibility_update(Aec3State& a, AecScratch& sc, int delay_blocks, bool external_delay_seen) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  __syncwarp();
+  // UpdateRenderNoiseEstimator
+  if (!s.ea_has_write_prev) {
+    __syncwarp();
+    if (lane == 0) {
+      s.ea_has_write_prev = 1;
+      s.ea_spectrum_write_prev = s.spectra_write;
+      s.ea_block_write_prev = s.blocks_write;
+    }
+    __syncwarp();
+  } else {
+    const int write_current = s.spectra_write;
+    if (!s.ea_non_zero_render_seen && !external_delay_seen) {
+      // IsRenderTooLow: every block written since the last look must reach 10 in magnitude
+      bool too_low = false;
+      const int block_write_current = s.blocks_write;
+      if (block_write_current == s.ea_block_write_prev) {
+        too_low = true;
+      } else {
+        for (int idx = s.ea_block_write_prev; idx != block_write_current; idx = ring_inc(idx, kRingBlocks)) {
+          float m = 0.f;
+          for (int i = lane; i < kBlock; i += 32) m = fmaxf(m, fabsf(a.blocks[idx][i]));
+          m = warp_max(m);
+          if (m < 10.f) { too_low = true; break; }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s.ea_block_write_prev = block_write_current;
+        s.ea_non_zero_render_seen = too_low ? 0 : 1;
+      }
+      __syncwarp();
+    }
+    if (s.ea_non_zero_render_seen) {
+      for (int idx = s.ea_spectrum_write_prev; idx != write_current; idx = ring_dec(idx, kRingBlocks)) {
+        // NoiseSpectrum::Update
+        const int block_counter = s.sta_block_counter + 1;
+        constexpr float kAlpha = 0.004f, kAlphaInit = 0.04f;
+        constexpr float kTiltAlpha = (kAlphaInit - kAlpha) / 500;
+        const float alpha = block_counter > 520 ? kAlpha : kAlphaInit - kTiltAlpha * (block_counter - 20);
+        #pragma unroll
+        for (int k = lane; k < kBins; k += 32) {
+          const float power_band = a.spectra[idx][k];
+          float noise = a.sta_noise[k];
+          if (block_counter <= 20) {
+            noise += (1.f / 20) * power_band;
+          } else if (noise < power_band) {
+            float alpha_inc = alpha * (noise / power_band);
+            if (block_counter > 500 && 10.f * noise < power_band) alpha_inc *= 0.1f;
+            noise += alpha_inc * (power_band - noise);
+          } else {
+            noise += alpha * (power_band - noise);
+            noise = fmaxr(noise, 10.f);
+          }
+          a.sta_noise[k] = noise;
+        }
+        __syncwarp();
+        if (lane == 0) s.sta_block_counter = block_counter;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    if (lane == 0) s.ea_spectrum_write_prev = write_current;
+    __syncwarp();
+  }
+  if (!(external_delay_seen || WAP_EC3(use_stationarity_properties_at_init))) return;
+  // UpdateRenderStationarityFlags -> StationarityEstimator::UpdateStationarityFlags
+  const int idx_at_delay = ring_off(s.spectra_read, delay_blocks, kRingBlocks);
+  const int headroom = s.spectra_write < s.spectra_read ? s.spectra_read - s.spectra_write
+                                                        : kRingBlocks - s.spectra_write + s.spectra_read;
+  const int num_lookahead_bounded = imin(imax(0, headroom - delay_blocks + 1), 13 - 1);
+  int idx0 = idx_at_delay;
+  if (num_lookahead_bounded < 13 - 1) idx0 = ring_off(idx_at_delay, (13 - 1) - num_lookahead_bounded, kRingBlocks);
+  #pragma unroll
+  for (int k = lane; k < kBins; k += 32) {
+    float acum_power = 0.f;
+    int idx = idx0;
+    for (int j = 0; j < 13; ++j) {
+      acum_power += a.spectra[idx][k] * 1.f;   // one render channel
+      idx = ring_dec(idx, kRingBlocks);
+    }
+    acum_power += a.avg_render_reverb[k];
+    const float noise = 13 * a.sta_noise[k];
+    a.sta_flags[k] = acum_power < 10.f * noise ? 1 : 0;
+  }
+  __syncwarp();
+  // UpdateHangover, SmoothStationaryPerFreq
+  int all_l = 1;
+  #pragma unroll
+  for (int k = lane; k < kBins; k += 32) all_l &= a.sta_flags[k];
+  const bool reduce_hangover = __all_sync(WAP_FULL, all_l);
+  int smooth[3] = {0, 0, 0};
+  #pragma unroll
+  for (int k = lane, j = 0; k < kBins; k += 32, ++j) {
+    const int kk = k == 0 ? 1 : (k == 64 ? 63 : k);   // bins 0 and 64 copy their neighbours' result
+    smooth[j] = a.sta_flags[kk - 1] && a.sta_flags[kk] && a.sta_flags[kk + 1];
+    int h = a.sta_hangovers[k];
+    if (!a.sta_flags[k]) h = 12;   // kHangoverBlocks = kNumBlocksPerSecond / 20
+    else if (reduce_hangover) h = imax(h - 1, 0);
+    a.sta_hangovers[k] = h;
+  }
+  __syncwarp();
+  #pragma unroll
+  for (int k = lane, j = 0; k < kBins; k += 32, ++j) a.sta_flags[k] = smooth[j];
+  __syncwarp();
+}
+
 // ---- AecState::Update (aec_state.cc:190-342).  Inputs in sc.rm: Y2, E2 (spectrum of the
 // formed linear output), sc.red[0..6] subtractor metrics.  `ext_has/ext_delay` is
 // the block processor's estimated delay.
@@ -304,6 +420,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     r.v1[k] = x2 + rev;
   }
   __syncwarp();
+  if (WAP_EC3(use_stationarity_properties)) echo_audibility_update(a, sc, delay, s.fd_has_external != 0);
   if (s.init_transition_triggered) erle_reset(a, sc, false);
 
   // Four 65-term chains side by side: X2_reverb, Y2, E2, X2.
@@ -522,8 +639,16 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   }
   __syncwarp();
 
-  // ---- ReverbModelEstimator::Update -> ReverbFrequencyResponse::Update
-  if (s.fb_has_erle_log2) {
+  // ---- ReverbModelEstimator::Update -> ReverbFrequencyResponse::Update (not on a stationary render block)
+  bool stationary_block = false;
+  if (WAP_EC3(use_stationarity_properties)) {
+    int cnt = 0;
+    #pragma unroll
+    for (int k = lane; k < kBins; k += 32) cnt += sta_band_stationary(a, k) ? 1 : 0;
+    for (int m = 16; m; m >>= 1) cnt += __shfl_xor_sync(WAP_FULL, cnt, m);
+    stationary_block = ((float)cnt * (1.f / kBins)) > 0.75f;   // IsBlockStationary
+  }
+  if (s.fb_has_erle_log2 && !stationary_block) {
     float quality = s.fb_inst_quality;   // ErleInstantaneous::GetQualityEstimate
     if (WAP_EC3(clamp_quality_estimate_to_zero)) quality = fmaxr(0.f, quality);
     if (WAP_EC3(clamp_quality_estimate_to_one)) quality = fminr(1.f, quality);
@@ -679,7 +804,8 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
         X2 = fmaxr(X2, a.spectra[idx][k]);
         idx = ring_inc(idx, kRingBlocks);
       }
-      if (WAP_EC3(noise_gate_power) > X2) X2 = fmaxr(0.f, X2 - WAP_EC3(noise_gate_slope) * (WAP_EC3(noise_gate_power) - X2));
+      if (!WAP_EC3(use_stationarity_properties) && WAP_EC3(noise_gate_power) > X2)
+        X2 = fmaxr(0.f, X2 - WAP_EC3(noise_gate_slope) * (WAP_EC3(noise_gate_power) - X2));
       X2 -= WAP_EC3(stationary_gate_slope) * floor;
       X2 = fmaxr(0.f, X2);
       R2 = R2u = X2 * echo_path_gain;
@@ -691,6 +817,15 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
       a.echo_reverb[k] = rev;
       R2 += rev;
       R2u += rev;
+    }
+    if (WAP_EC3(use_stationarity_properties)) {
+      // AecState::GetResidualEchoScaling (aec_state.cc:115-126, echo_audibility.h:40-51)
+      const float converge_blocks = (WAP_EC3(conservative_initial_phase) ? 1.5f : 0.8f) * kNumBlocksPerSecond;
+      const bool filter_has_had_time_to_converge = (float)s.strong_not_saturated_render_blocks >= converge_blocks;
+      const float scaling = (sta_band_stationary(a, k) &&
+                             (filter_has_had_time_to_converge || WAP_EC3(use_stationarity_properties_at_init))) ? 0.f : 1.0f;
+      R2 *= scaling;
+      R2u *= scaling;
     }
     r.R2[k] = R2;
     r.R2_unb[k] = R2u;

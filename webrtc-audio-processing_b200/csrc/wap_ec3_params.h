@@ -69,6 +69,8 @@ struct Ec3Params {
   int conservative_initial_phase, enable_coarse_filter_output_usage, use_linear_filter;
   int render_pre_window_size, render_post_window_size, model_reverb_in_nonlinear_mode, nearend_average_blocks;
   float render_linear_amplitude_gain;
+  // echo_audibility.use_stationarity_properties / use_stationarity_properties_at_init (EchoAudibility)
+  int use_stationarity_properties, use_stationarity_properties_at_init;
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -115,6 +117,7 @@ constexpr int lf_smoothing_during_initial_phase = 1, dn_use_during_initial_phase
 constexpr int conservative_initial_phase = 0, enable_coarse_filter_output_usage = 1, use_linear_filter = 1;
 constexpr int render_pre_window_size = 1, render_post_window_size = 1, model_reverb_in_nonlinear_mode = 1, nearend_average_blocks = 4;
 constexpr float render_linear_amplitude_gain = 1.f;
+constexpr int use_stationarity_properties = 0, use_stationarity_properties_at_init = 0;
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -157,6 +160,7 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(conservative_initial_phase); WAP_SET(enable_coarse_filter_output_usage); WAP_SET(use_linear_filter);
   WAP_SET(render_pre_window_size); WAP_SET(render_post_window_size); WAP_SET(model_reverb_in_nonlinear_mode);
   WAP_SET(nearend_average_blocks); WAP_SET(render_linear_amplitude_gain);
+  WAP_SET(use_stationarity_properties); WAP_SET(use_stationarity_properties_at_init);
 #undef WAP_SET
   return p;
 }

@@ -514,7 +514,6 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.erle.num_sections == 1 &&
       c.ep_strength.default_len >= 0.f && c.ep_strength.nearend_len >= 0.f &&   // negative: adaptive reverb decay
 
-      !c.echo_audibility.use_stationarity_properties && !c.echo_audibility.use_stationarity_properties_at_init &&
 
       c.echo_model.render_pre_window_size >= 0 && c.echo_model.render_pre_window_size <= 100 &&
       c.echo_model.render_post_window_size >= 0 && c.echo_model.render_post_window_size <= 100 &&
@@ -629,6 +628,8 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   p.nearend_average_blocks = c.suppressor.nearend_average_blocks;
   // RenderDelayBufferImpl: std::pow(10.0f, render_power_gain_db / 20.f) (render_delay_buffer.cc:124-125)
   p.render_linear_amplitude_gain = powf(10.0f, c.render_levels.render_power_gain_db / 20.f);
+  p.use_stationarity_properties = c.echo_audibility.use_stationarity_properties;
+  p.use_stationarity_properties_at_init = c.echo_audibility.use_stationarity_properties_at_init;
   return p;
 }
 
@@ -998,7 +999,8 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
           c->filter.conservative_initial_phase || !c->filter.enable_coarse_filter_output_usage || !c->filter.use_linear_filter ||
           c->echo_model.render_pre_window_size != 1 || c->echo_model.render_post_window_size != 1 ||
           !c->echo_model.model_reverb_in_nonlinear_mode || c->suppressor.nearend_average_blocks != 4 ||
-          c->render_levels.render_power_gain_db != 0.f)
+          c->render_levels.render_power_gain_db != 0.f || c->echo_audibility.use_stationarity_properties ||
+          c->echo_audibility.use_stationarity_properties_at_init)
         err = WapError::UnsupportedConfig;
     }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||

@@ -84,6 +84,7 @@ inline void init_aec3_state(Aec3State& a, const Ec3Params& ep) {
     a.X2_noise_floor_counter[k] = ep.noise_floor_hold;
     a.cng_N2[k] = 1.0e6f;                // ComfortNoiseGenerator ctor (comfort_noise_generator.cc:106-123)
     a.last_gain[k] = 1.f;                // SuppressionGain ctor (suppression_gain.cc:351)
+    a.sta_noise[k] = 10.f;               // StationarityEstimator::NoiseSpectrum::Reset (kMinNoisePower)
   }
   {
     // FastApproxLog2f(erle.min + 1e-3) (aec3_common.cc:37-52)

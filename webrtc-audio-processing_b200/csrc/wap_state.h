@@ -194,6 +194,8 @@ struct Aec3Scalars {
   float sg_average_power;
   int dn_nearend_state, dn_trigger_counter, dn_hold_counter;
   int snd_mem_index;                      // SubbandNearendDetector's MovingAverage::mem_index_
+  // EchoAudibility (echo_audibility.h:70-75) + StationarityEstimator::NoiseSpectrum::block_counter_
+  int ea_has_write_prev, ea_spectrum_write_prev, ea_block_write_prev, ea_non_zero_render_seen, sta_block_counter;
   // ApmStatsReporter one-slot queue (audio_processing_impl.cc:2312-2327)
   int stats_slot_full;
   float stats_erl_time_domain, stats_erle_log2;
@@ -236,6 +238,8 @@ struct alignas(16) Aec3State {
   float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
   float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (mem_len 4 -> 3 slots)
   float snd_mem[3][kBinsPad];               // SubbandNearendDetector::nearend_smoothers_ (nearend_average_blocks <= 4)
+  float sta_noise[kBinsPad];                // StationarityEstimator::NoiseSpectrum::noise_spectrum_, init 10 (kMinNoisePower)
+  int sta_flags[kBinsPad], sta_hangovers[kBinsPad];   // stationarity_flags_, hangovers_
   int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used, index k-1)
   int erle_hold_counters[kBinsPad];
   int erl_hold_counters[kBinsPad];          // 63 used, index k-1

@@ -260,6 +260,20 @@ def load(path=None):
     L.wap_engine_create_with_formats.restype = vp
     L.wap_engine_create_with_formats.argtypes = [C.c_int, i32, cfg, sc, sc, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_version.restype = C.c_char_p
+    L.wap_version.argtypes = []
+    L.wap_config_default.argtypes = []
+    L.wap_create.argtypes = []
+    L.wap_echo_canceller3_config_default.argtypes = []
+    L.wap_echo_canceller3_config_default_multichannel.argtypes = []
+    L.wap_echo_canceller3_config_sizeof.argtypes = []
+    L.wap_set_playout_audio_device.argtypes = [vp, C.c_int, C.c_int]
+    L.wap_set_stream_analog_level.argtypes = [vp, C.c_int]
+    L.wap_recommended_stream_analog_level.argtypes = [vp]
+    L.wap_stream_read_taps.argtypes = [vp, C.POINTER(WapStageTaps)]
+    # a handle passed without argtypes would be truncated to a C int: every export must be declared
+    missing = [n for n in EXPORTS if getattr(L, n).argtypes is None]
+    if missing:
+        raise RuntimeError("wap_b200: no argtypes for " + ", ".join(missing))
     _libs[path] = L
     return L
 
