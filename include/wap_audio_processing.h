@@ -397,13 +397,16 @@ size_t wap_echo_canceller3_config_sizeof(void);
 /* EchoCanceller3Config::Validate: clamps *config, returns true iff it was valid as given. */
 bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
 /* None when this library can run `config` (after Validate); UnsupportedConfig when a member that
- * fixes the engine's structure differs from its default: delay.down_sampling_factor (4),
- * delay.num_filters (5), delay.fixed_capture_delay_samples (0), delay.use_external_delay_estimator,
- * delay.detect_pre_echo, filter lengths above 13 blocks, the filter.* / erle.* / ep_strength.* /
- * echo_audibility.* / echo_removal_control.* / echo_model.* switches, erle.num_sections (1),
- * echo_model.render_pre/post_window_size (1), suppressor.nearend_average_blocks (4),
- * suppressor.use_subband_nearend_detection, suppressor.conservative_hf_suppression,
- * render_levels.render_power_gain_db (0). */
+ * fixes the engine's structure differs from what is built: delay.down_sampling_factor (4),
+ * delay.num_filters (5), delay.fixed_capture_delay_samples (0..5000), delay.use_external_delay_estimator
+ * (false), delay.detect_pre_echo (true), filter lengths (1..13 blocks, the initial ones not above the
+ * final ones), filter.export_linear_aec_output (false), erle.num_sections (1),
+ * ep_strength.default_len < 0 (adaptive reverb decay) with fewer than 10 refined filter blocks,
+ * echo_model.render_pre/post_window_size (0..100), suppressor.nearend_average_blocks (1..4) and the
+ * same bound for the subband nearend detector.  Every other member, the boolean switches of the
+ * echo remover included, is a run-time parameter.  Multi-channel engines additionally need the
+ * defaults of the boolean switches, the render high-pass filter, the fixed capture delay, the subband
+ * nearend detector and non-negative ep_strength lengths (wap_engine_create* reports it). */
 WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config);
 /* wap_create_with_config / wap_engine_create with an injected AEC3 config
  * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig(config, multichannel_config)).

@@ -87,7 +87,7 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     assert m.filter.coarse.rate == pytest.approx(0.95) and m.suppressor.normal_tuning.max_inc_factor == pytest.approx(1.5)
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
-                    ("filter.export_linear_aec_output", True), ("erle.num_sections", 2), ("ep_strength.default_len", -0.5),
+                    ("filter.export_linear_aec_output", True), ("erle.num_sections", 2),
                     ("delay.use_external_delay_estimator", True),
                     ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
@@ -95,6 +95,12 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
         assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 0
         wap_b200.ec3_set(c, path, v)
         assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 7, path
+    # the adaptive reverb decay (default_len < 0) needs a refined filter of 10 blocks or more, as in the reference
+    c = L.wap_echo_canceller3_config_default()
+    c.ep_strength.default_len = -0.5
+    assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 0
+    c.filter.refined.length_blocks = c.filter.refined_initial.length_blocks = 9
+    assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 7
     c = L.wap_echo_canceller3_config_default()
     c.delay.down_sampling_factor = 8
     assert not L.wap_engine_create_with_aec3_config(0, 1, wap_b200.make_config(L), wap_b200.WapStreamConfig(16000, 1), C.byref(c), None)
@@ -279,6 +285,12 @@ SWITCHES = {
     "stationarity_properties": {"echo_audibility.use_stationarity_properties": 1},
     "stationarity_properties_at_init": {"echo_audibility.use_stationarity_properties": 1,
                                         "echo_audibility.use_stationarity_properties_at_init": 1},
+    # ep_strength.default_len < 0: ReverbDecayEstimator adapts the decay from the refined filter's tail
+    "adaptive_reverb_decay": {"ep_strength.default_len": -0.83},
+    "adaptive_reverb_decay_long_room": {"ep_strength.default_len": -0.5, "ep_strength.nearend_len": -0.5},
+    "adaptive_reverb_decay_stationarity": {"ep_strength.default_len": -0.9,
+                                           "echo_audibility.use_stationarity_properties": 1},
+    "negative_nearend_len": {"ep_strength.nearend_len": -0.4},
 }
 
 
@@ -322,8 +334,27 @@ def _render_gap_leg(nf, seed=4):
     return q(x), q(y)
 
 
+def _reverberant_leg(nf, seed=21, rt_samples=500, delay=150):
+    """Echo through a room with an exponentially decaying tail that spans most of the 13-block filter."""
+    rng = np.random.default_rng(seed)
+    n = nf * 160
+    t = np.arange(n) / 16000.0
+    x = rng.uniform(-9000, 9000, n) * ((t % 4.0) < 3.4)
+    h = np.zeros(delay + 700)
+    h[delay] = 0.5
+    k = np.arange(1, 700)
+    h[delay + 1:] = 0.03 * rng.standard_normal(699) * np.exp(-k / rt_samples)
+    y = np.convolve(x, h)[:n] + rng.uniform(-30, 30, n) + rng.uniform(-3000, 3000, n) * ((t % 2.7) > 2.3)
+    q = lambda v: np.clip(np.round(v), -32768, 32767).astype(np.int16)
+    return q(x), q(y)
+
+
 # legs on which the reference's output provably depends on the switch (asserted below)
 SWITCH_LEGS = {
+    "adaptive_reverb_decay": lambda: [_reverberant_leg(1500)],
+    "adaptive_reverb_decay_long_room": lambda: [_reverberant_leg(1200, seed=22, rt_samples=900, delay=90)],
+    "adaptive_reverb_decay_stationarity": lambda: [_reverberant_leg(900, seed=23, rt_samples=250)],
+    "negative_nearend_len": lambda: [_early_nearend_leg(700)],
     "bounded_erl": lambda: [_no_echo_leg(1000)],
     "dominant_nearend_not_during_initial_phase": lambda: [_early_nearend_leg(700)],
     "erle_onset_compensation_in_dominant_nearend": lambda: [_render_gap_leg(1500)],

@@ -23,6 +23,7 @@
 
 #include "dsp_aec3_common.cuh"
 #include "dsp_aec3_subtractor.cuh"
+#include "wap_libm.cuh"
 
 namespace wap {
 
@@ -66,6 +67,125 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
     s.fb_erle_time_domain_log2 = fast_approx_log2f(WAP_EC3(erle_min) + 1e-3f);
     s.fb_hold_counter = 0;
     if (delay_change) s.erle_blocks_since_reset = 0;
+  }
+  __syncwarp();
+}
+
+// ---- AecState::ReverbDecay(mild) -> ReverbDecayEstimator::Decay (reverb_decay_estimator.h:37-43)
+WAP_DEV float aec_reverb_decay(const AecScratch& sc, bool mild) {
+  if (WAP_EC3(default_len) < 0.f) return sc.s.rd_decay;   // use_adaptive_echo_decay_
+  return mild ? fabsf(WAP_EC3(nearend_len)) : WAP_EC3(default_len);
+}
+
+// ---- ReverbDecayEstimator::Update (reverb_decay_estimator.cc:104-143) with the adaptive decay
+// (ep_strength.default_len < 0), on a block that is not stationary.  `filter` is the FilterAnalyzer's
+// high-passed impulse response, the peak block the direct-path filter delay.
+// The EarlyReverbLengthEstimator is not restated: with filter.refined.length_blocks <= 17 it holds fewer
+// than the kNumSectionsToAnalyze = 9 sections its Estimate() needs (:374-376), so the early reverb size is
+// always 0 and its accumulators are never read.
+static_assert(kMaxPartitions - 3 - 6 < 9, "EarlyReverbLengthEstimator::Estimate would become reachable");
+WAP_DEV void reverb_decay_update(Aec3State& a, AecScratch& sc, bool has_quality, float quality) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  const int L = WAP_EC3(refined_len);
+  const int delay = s.fd_filter_delay;
+  const float* h = a.h_highpass;
+  __syncwarp();
+  const bool feasible = delay <= L - 3 - 1 && s.fa_hp_size == L * kBlock && delay > 0 && s.fq_usable_filter;
+  const float smoothing = fmaxr(has_quality ? quality * 0.2f : 0.f, s.rd_smoothing);
+  const int b = s.rd_block_to_analyze;
+  __syncwarp();
+  if (!feasible) {
+    if (lane == 0) {   // ResetDecayEstimation (:145-154); LateReverbLinearRegressor::Reset(0)
+      s.rd_late_nz = 0.f; s.rd_late_nn = 0.f; s.rd_late_count = 0.f; s.rd_late_N = 0; s.rd_late_n = 0;
+      s.rd_block_to_analyze = 0; s.rd_candidate_size = 0; s.rd_region_identified = 0;
+      s.rd_smoothing = 0.f; s.rd_late_start = 0; s.rd_late_end = 0;
+    }
+    __syncwarp();
+    return;
+  }
+  if (lane == 0) s.rd_smoothing = smoothing;
+  if (smoothing == 0.f) { __syncwarp(); return; }
+  if (b < L) {
+    // ---- AnalyzeFilter (:212-247)
+    const float* hb = h + b * kBlock;
+    float h2_log2[kBlock / 32];
+    #pragma unroll
+    for (int j = 0; j < kBlock / 32; ++j) {
+      const float h2 = hb[lane + 32 * j] * hb[lane + 32 * j];
+      r.v3[lane + 32 * j] = h2;
+      h2_log2[j] = fast_approx_log2f((float)((double)h2 + 1e-10));
+    }
+    __syncwarp();
+    float gain = 0.f;
+    if (lane == 0) gain = fmaxr(chain_sum(r.v3, 0, kBlock) * (1.f / kBlock), 1e-32f);   // AnalyzeBlockGain
+    __syncwarp();
+    #pragma unroll
+    for (int j = 0; j < kBlock / 32; ++j) r.v3[lane + 32 * j] = h2_log2[j];
+    __syncwarp();
+    if (lane == 0) {
+      const float previous = a.rd_previous_gains[b];
+      const bool adapting = previous > 1.1f * gain || previous < 0.9f * gain;
+      const bool above_noise_floor = gain > s.rd_tail_gain;
+      a.rd_previous_gains[b] = gain;
+      s.rd_region_identified = s.rd_region_identified || adapting || !above_noise_floor;
+      if (!s.rd_region_identified) ++s.rd_candidate_size;
+      if (b <= s.rd_late_end && b >= s.rd_late_start) {
+        float nz = s.rd_late_nz, count = s.rd_late_count;   // LateReverbLinearRegressor::Accumulate
+        for (int i = 0; i < kBlock; ++i) {
+          nz += count * r.v3[i];
+          count += 1.f;
+        }
+        s.rd_late_nz = nz; s.rd_late_count = count; s.rd_late_n += kBlock;
+      }
+      s.rd_block_to_analyze = b + 1;
+    }
+  } else {
+    // ---- EstimateDecay (:156-210)
+    const int first_block = imin(delay + 3, L);
+    if (lane < 3) {
+      const float* blk = h + (lane == 0 ? first_block : lane == 1 ? L - 1 : delay) * kBlock;
+      float acc = 0.f;
+      if (lane < 2) {   // BlockEnergyAverage
+        for (int i = 0; i < kBlock; ++i) acc = acc + blk[i] * blk[i];
+        acc *= (1.f / kBlock);
+      } else {          // BlockEnergyPeak: the first largest square
+        for (int i = 0; i < kBlock; ++i) acc = (acc < blk[i] * blk[i]) ? blk[i] * blk[i] : acc;
+      }
+      sc.red[16 + lane] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const float first_reverb_gain = sc.red[16], tail_gain = sc.red[17], peak_energy = sc.red[18];
+      s.rd_tail_gain = tail_gain;
+      const bool sufficient_reverb_decay = first_reverb_gain > 4.f * tail_gain;
+      const bool valid_filter = first_reverb_gain > 2.f * tail_gain && peak_energy < 100.f;
+      const int size_late_reverb = imax(s.rd_candidate_size, 0);   // early reverb size 0, see above
+      if (size_late_reverb >= 5) {
+        if (valid_filter && s.rd_late_n == s.rd_late_N && s.rd_late_N != 0) {
+          float decay = libm_pow2f((s.rd_late_nz / s.rd_late_nn) * (float)kBlock);
+          decay = fmaxr(.97f * s.rd_decay, decay);
+          decay = fminr(decay, 0.95f);
+          decay = fmaxr(decay, 0.02f);
+          s.rd_decay += smoothing * (decay - s.rd_decay);
+        }
+        const int N = size_late_reverb * kBlock;   // LateReverbLinearRegressor::Reset(N)
+        s.rd_late_nz = 0.f;
+        s.rd_late_nn = (float)N * ((float)(N * N) - 1.0f) * (1.f / 12.f);
+        s.rd_late_count = -(float)N * 0.5f + 0.5f;
+        s.rd_late_N = N; s.rd_late_n = 0;
+        s.rd_late_start = delay + 3;
+        s.rd_late_end = first_block + s.rd_candidate_size - 1;
+      } else {
+        s.rd_late_nz = 0.f; s.rd_late_nn = 0.f; s.rd_late_count = 0.f; s.rd_late_N = 0; s.rd_late_n = 0;
+        s.rd_late_start = 0; s.rd_late_end = 0;
+      }
+      s.rd_block_to_analyze = first_block;
+      s.rd_region_identified = !(valid_filter && sufficient_reverb_decay);
+      s.rd_candidate_size = 0;
+      s.rd_smoothing = 0.f;
+    }
   }
   __syncwarp();
 }
@@ -413,7 +533,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
   const int idx_past = ring_inc(idx_at_delay, kRingBlocks);
   #pragma unroll
   for (int k = lane; k < kBins; k += 32) {
-    const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * WAP_EC3(default_len);   // ReverbDecay(mild = false)
+    const float rev = (a.avg_render_reverb[k] + a.spectra[idx_past][k] * 1.0f) * aec_reverb_decay(sc, false);
     a.avg_render_reverb[k] = rev;
     const float x2 = a.spectra[idx_at_delay][k];
     r.v2[k] = x2;
@@ -636,6 +756,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     usable = usable && (ext_has || s.fq_convergence_seen);
     usable = usable && !s.tm_active;
     s.fq_usable = usable && WAP_EC3(use_linear_filter);   // UsableLinearEstimate() (aec_state.h) / :457-461
+    s.fq_usable_filter = usable;                          // UsableLinearFilterOutputs()
   }
   __syncwarp();
 
@@ -648,10 +769,11 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     for (int m = 16; m; m >>= 1) cnt += __shfl_xor_sync(WAP_FULL, cnt, m);
     stationary_block = ((float)cnt * (1.f / kBins)) > 0.75f;   // IsBlockStationary
   }
-  if (s.fb_has_erle_log2 && !stationary_block) {
-    float quality = s.fb_inst_quality;   // ErleInstantaneous::GetQualityEstimate
-    if (WAP_EC3(clamp_quality_estimate_to_zero)) quality = fmaxr(0.f, quality);
-    if (WAP_EC3(clamp_quality_estimate_to_one)) quality = fminr(1.f, quality);
+  float quality = s.fb_inst_quality;   // ErleInstantaneous::GetQualityEstimate
+  if (WAP_EC3(clamp_quality_estimate_to_zero)) quality = fmaxr(0.f, quality);
+  if (WAP_EC3(clamp_quality_estimate_to_one)) quality = fminr(1.f, quality);
+  const bool has_quality = s.fb_has_erle_log2 != 0;
+  if (has_quality && !stationary_block) {
     const float* tail = a.H2[s.H2_size - 1];
     const float* direct = a.H2[s.fd_filter_delay];
     if (lane < 2) sc.red[16 + lane] = chain_sum(lane == 0 ? direct : tail, 1, kBins);
@@ -676,6 +798,9 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
     for (int k = lane; k < kBins; k += 32) a.tail_response[k] = r.v3[k];
   }
   __syncwarp();
+  // ---- ReverbModelEstimator::Update -> ReverbDecayEstimator::Update; without the adaptive decay it only
+  // maintains state that nothing reads
+  if (WAP_EC3(default_len) < 0.f && !stationary_block) reverb_decay_update(a, sc, has_quality, quality);
 }
 
 // ---- ComfortNoiseGenerator::Compute.  `nearend` = capture spectrum chosen by the caller.
@@ -757,7 +882,7 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   const int delay = s.fd_min_filter_delay;
   const bool add_reverb = usable || (WAP_EC3(model_reverb_in_nonlinear_mode) && !transparent);
   // AecState::ReverbDecay(mild = dominant_nearend) (residual_echo_estimator.cc:384, aec_state.h:127)
-  const float reverb_decay = dominant_nearend ? WAP_EC3(nearend_len) : WAP_EC3(default_len);
+  const float reverb_decay = aec_reverb_decay(sc, dominant_nearend);
   const int first_reverb_partition = usable ? s.fa_filter_length_blocks + 1 : delay + 1;
   const float* X2_reverb_src = a.spectra[ring_off(s.spectra_read, first_reverb_partition, kRingBlocks)];
   // LinearEstimate uses Erle(onset_compensated), which only differs from erle_ with onset detection

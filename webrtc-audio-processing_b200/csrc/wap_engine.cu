@@ -512,7 +512,9 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.filter.config_change_duration_blocks >= 1 &&
       c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
       c.erle.num_sections == 1 &&
-      c.ep_strength.default_len >= 0.f && c.ep_strength.nearend_len >= 0.f &&   // negative: adaptive reverb decay
+      // default_len < 0: the adaptive reverb decay (ReverbDecayEstimator); its EarlyReverbLengthEstimator holds
+      // length_blocks - 9 sections, so the reference itself needs 10 blocks or more
+      (c.ep_strength.default_len >= 0.f || c.filter.refined.length_blocks >= 10) &&
 
 
       c.echo_model.render_pre_window_size >= 0 && c.echo_model.render_pre_window_size <= 100 &&
@@ -1000,7 +1002,8 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
           c->echo_model.render_pre_window_size != 1 || c->echo_model.render_post_window_size != 1 ||
           !c->echo_model.model_reverb_in_nonlinear_mode || c->suppressor.nearend_average_blocks != 4 ||
           c->render_levels.render_power_gain_db != 0.f || c->echo_audibility.use_stationarity_properties ||
-          c->echo_audibility.use_stationarity_properties_at_init)
+          c->echo_audibility.use_stationarity_properties_at_init ||
+          c->ep_strength.default_len < 0.f || c->ep_strength.nearend_len < 0.f)
         err = WapError::UnsupportedConfig;
     }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||
@@ -1519,7 +1522,7 @@ struct BlobHeader {
   WapStats cached_stats;
 };
 constexpr uint32_t kBlobMagic = 0x57415042u;  // "WAPB"
-constexpr uint32_t kBlobVersion = 4;
+constexpr uint32_t kBlobVersion = 5;
 size_t blob_bytes(const WapEngine* e) {
   size_t n = sizeof(BlobHeader) + sizeof(StreamState);
   if (e->d_upper) n += sizeof(wap::UpperBandState);

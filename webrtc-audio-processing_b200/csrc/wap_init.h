@@ -75,6 +75,9 @@ inline void init_aec3_state(Aec3State& a, const Ec3Params& ep) {
   s.cfd_consistent_delay_reference = -10;
   s.tm_active_blocks_since_sane_filter = 10000;  // LegacyTransparentModeImpl (transparent_mode.cc:132-140)
   s.tm_non_converged_sequence_size = 10000;
+  // ReverbDecayEstimator ctor (reverb_decay_estimator.cc:89-102): kEarlyReverbMinSizeBlocks, |default_len|
+  s.rd_late_start = s.rd_late_end = 3;
+  s.rd_decay = fabsf(ep.default_len);
   // ErleEstimator::Reset(true) (erle_estimator.cc:46-56, fullband_erle_estimator.cc:50-62,150-155)
   for (int k = 0; k < kBins; ++k) {
     a.erle[k] = a.erle_onset_comp[k] = a.erle_unbounded[k] = ep.erle_min;

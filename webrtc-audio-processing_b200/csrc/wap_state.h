@@ -196,6 +196,14 @@ struct Aec3Scalars {
   int snd_mem_index;                      // SubbandNearendDetector's MovingAverage::mem_index_
   // EchoAudibility (echo_audibility.h:70-75) + StationarityEstimator::NoiseSpectrum::block_counter_
   int ea_has_write_prev, ea_spectrum_write_prev, ea_block_write_prev, ea_non_zero_render_seen, sta_block_counter;
+  // ReverbDecayEstimator with the adaptive decay (ep_strength.default_len < 0; reverb_decay_estimator.h:95-108)
+  // and its LateReverbLinearRegressor (:56-61).  fq_usable_filter: FilteringQualityAnalyzer::LinearFilterUsable()
+  // before the filter.use_linear_filter gate of fq_usable.
+  int fq_usable_filter;
+  int rd_late_start, rd_late_end, rd_block_to_analyze, rd_candidate_size, rd_region_identified;
+  int rd_late_N, rd_late_n;
+  float rd_late_nz, rd_late_nn, rd_late_count;
+  float rd_decay, rd_tail_gain, rd_smoothing;
   // ApmStatsReporter one-slot queue (audio_processing_impl.cc:2312-2327)
   int stats_slot_full;
   float stats_erl_time_domain, stats_erle_log2;
@@ -238,6 +246,7 @@ struct alignas(16) Aec3State {
   float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
   float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (mem_len 4 -> 3 slots)
   float snd_mem[3][kBinsPad];               // SubbandNearendDetector::nearend_smoothers_ (nearend_average_blocks <= 4)
+  float rd_previous_gains[kMaxPartitions + 3];   // ReverbDecayEstimator::previous_gains_
   float sta_noise[kBinsPad];                // StationarityEstimator::NoiseSpectrum::noise_spectrum_, init 10 (kMinNoisePower)
   int sta_flags[kBinsPad], sta_hangovers[kBinsPad];   // stationarity_flags_, hangovers_
   int narrow_band_counters[kBinsPad];       // RenderSignalAnalyzer (63 used, index k-1)
