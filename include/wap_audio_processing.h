@@ -400,13 +400,15 @@ bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
  * fixes the engine's structure differs from what is built: delay.down_sampling_factor (4),
  * delay.num_filters (5), delay.fixed_capture_delay_samples (0..5000), delay.use_external_delay_estimator
  * (false), delay.detect_pre_echo (true), filter lengths (1..13 blocks, the initial ones not above the
- * final ones), filter.export_linear_aec_output (false), erle.num_sections (1),
+ * final ones), filter.export_linear_aec_output (false), erle.num_sections (1 .. refined filter blocks
+ * behind the delay headroom),
  * ep_strength.default_len < 0 (adaptive reverb decay) with fewer than 10 refined filter blocks,
  * echo_model.render_pre/post_window_size (0..100), suppressor.nearend_average_blocks (1..4) and the
  * same bound for the subband nearend detector.  Every other member, the boolean switches of the
  * echo remover included, is a run-time parameter.  Multi-channel engines additionally need the
  * defaults of the boolean switches, the render high-pass filter, the fixed capture delay, the subband
- * nearend detector and non-negative ep_strength lengths (wap_engine_create* reports it). */
+ * nearend detector, non-negative ep_strength lengths and erle.num_sections 1 (wap_engine_create*
+ * reports it). */
 WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config);
 /* wap_create_with_config / wap_engine_create with an injected AEC3 config
  * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig(config, multichannel_config)).

@@ -87,7 +87,7 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     assert m.filter.coarse.rate == pytest.approx(0.95) and m.suppressor.normal_tuning.max_inc_factor == pytest.approx(1.5)
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
-                    ("filter.export_linear_aec_output", True), ("erle.num_sections", 2),
+                    ("filter.export_linear_aec_output", True), ("erle.num_sections", 14),
                     ("delay.use_external_delay_estimator", True),
                     ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
@@ -291,6 +291,11 @@ SWITCHES = {
     "adaptive_reverb_decay_stationarity": {"ep_strength.default_len": -0.9,
                                            "echo_audibility.use_stationarity_properties": 1},
     "negative_nearend_len": {"ep_strength.nearend_len": -0.4},
+    # erle.num_sections > 1: SignalDependentErleEstimator
+    "erle_2_sections": {"erle.num_sections": 2},
+    "erle_4_sections": {"erle.num_sections": 4},
+    "erle_6_sections_long_room": {"erle.num_sections": 6, "delay.delay_headroom_samples": 64},
+    "erle_12_sections_no_onset_detection": {"erle.num_sections": 12, "erle.onset_detection": 0},
 }
 
 
@@ -355,6 +360,10 @@ SWITCH_LEGS = {
     "adaptive_reverb_decay_long_room": lambda: [_reverberant_leg(1200, seed=22, rt_samples=900, delay=90)],
     "adaptive_reverb_decay_stationarity": lambda: [_reverberant_leg(900, seed=23, rt_samples=250)],
     "negative_nearend_len": lambda: [_early_nearend_leg(700)],
+    "erle_2_sections": lambda: [_reverberant_leg(1000, seed=31)],
+    "erle_4_sections": lambda: [_reverberant_leg(1000, seed=32, rt_samples=300)],
+    "erle_6_sections_long_room": lambda: [_reverberant_leg(1000, seed=33, rt_samples=900, delay=90)],
+    "erle_12_sections_no_onset_detection": lambda: [_reverberant_leg(800, seed=34)],
     "bounded_erl": lambda: [_no_echo_leg(1000)],
     "dominant_nearend_not_during_initial_phase": lambda: [_early_nearend_leg(700)],
     "erle_onset_compensation_in_dominant_nearend": lambda: [_render_gap_leg(1500)],

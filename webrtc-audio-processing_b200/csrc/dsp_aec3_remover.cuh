@@ -47,6 +47,7 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
     a.erle[k] = WAP_EC3(erle_min);
     a.erle_onset_comp[k] = WAP_EC3(erle_min);
     a.erle_unbounded[k] = WAP_EC3(erle_min);
+    if (WAP_EC3(erle_num_sections) > 1) { a.sd_erle[k] = WAP_EC3(erle_min); a.sd_erle_onset[k] = WAP_EC3(erle_min); }
     a.coming_onset[k] = 1;
     a.erle_hold_counters[k] = 0;
     a.accum_Y2[k] = 0.f;
@@ -68,8 +69,122 @@ WAP_DEV void erle_reset(Aec3State& a, AecScratch& sc, bool delay_change) {
     s.fb_hold_counter = 0;
     if (delay_change) s.erle_blocks_since_reset = 0;
   }
+  if (WAP_EC3(erle_num_sections) > 1) {   // SignalDependentErleEstimator::Reset
+    for (int i = lane; i < kMaxPartitions * 8; i += 32) {
+      a.sd_estimators[i >> 3][i & 7] = WAP_EC3(erle_min);
+      a.sd_correction[i >> 3][i & 7] = 1.0f;
+    }
+    if (lane < 8) { a.sd_erle_ref[lane] = WAP_EC3(erle_min); a.sd_num_updates[lane] = 0; }
+  }
   __syncwarp();
 }
+
+// ---- SignalDependentErleEstimator::Update (signal_dependent_erle_estimator.cc:177-372), erle.num_sections > 1.
+// The refined filter is cut into sections (boundaries computed on the host); per bin, the number of leading
+// sections that carry 90 % of the echo estimate selects a correction factor per (section count, subband) that
+// scales the subband estimator's ERLE.  In: r.v1 = X2 with reverb, r.Y2, r.E2, the subband estimator's a.erle /
+// a.erle_onset_comp of this block.  Scratch: r.R2 (active sections per bin), r.R2_unb (subband sums).
+#if WAP_EC3_RUNTIME
+WAP_DEV int sd_subband_of_bin(int k) { return k < 8 ? 0 : k < 16 ? 1 : k < 24 ? 2 : k < 32 ? 3 : k < 48 ? 4 : 5; }
+WAP_DEV int sd_band_boundary(int i) { return i == 0 ? 1 : i < 5 ? 8 * i : i == 5 ? 48 : kBins; }   // kBandBoundaries
+WAP_DEV float sd_safe_clamp(float x, float lo, float hi) { return x <= lo ? lo : x >= hi ? hi : x; }
+WAP_DEV void signal_dependent_erle_update(Aec3State& a, AecScratch& sc, bool converged) {
+  const int lane = lane_id();
+  Aec3Scalars& s = sc.s;
+  AecRemoverScratch& r = sc.rm;
+  const int num_sections = sc.ep.erle_num_sections;
+  const int* bounds = sc.ep.sd_boundaries;
+  const int H2_size = s.H2_size;
+  __syncwarp();
+  // ComputeEchoEstimatePerFilterSection + ComputeActiveFilterSections: the accumulated section estimates of a
+  // bin never decrease, so the first section that reaches 0.9 of the total is where the reference's downward
+  // scan stops; two passes over the sections (total, then the first hit) with the same operations in the
+  // same order
+  const int idx_first = ring_off(s.spectra_read, bounds[0], kRingBlocks);
+  for (int k = lane; k < kBins; k += 32) {
+    float target = 0.f;
+    int n_active = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      int idx = idx_first;
+      float accum = 0.f;
+      bool found = false;
+      for (int sec = 0; sec < num_sections; ++sec) {
+        float X2_section = 0.f, H2_section = 0.f;
+        const int limit = imin(bounds[sec + 1], H2_size);
+        for (int block = bounds[sec]; block < limit; ++block) {
+          X2_section += a.spectra[idx][k] * 1.f;
+          H2_section = H2_section + a.H2[block][k];
+          idx = ring_inc(idx, kRingBlocks);
+        }
+        const float S2 = X2_section * H2_section;
+        accum = sec == 0 ? S2 : accum + S2;
+        if (pass == 1 && !found && accum >= target) { found = true; n_active = sec; }
+      }
+      target = 0.9f * accum;
+    }
+    r.R2[k] = (float)n_active;
+  }
+  __syncwarp();
+  // UpdateCorrectionFactors
+  if (converged) {
+    if (lane < 18) {   // subband powers of X2, E2, Y2: left-to-right sums from 0
+      const int sb = lane % 6;
+      const float* p = lane < 6 ? r.v1 : lane < 12 ? r.E2 : r.Y2;
+      r.R2_unb[lane] = chain_sum(p, sd_band_boundary(sb), sd_band_boundary(sb + 1));
+    } else if (lane < 24) {   // the fewest active sections of the subband's bins
+      const int sb = lane - 18;
+      float m = r.R2[sd_band_boundary(sb)];
+      for (int k = sd_band_boundary(sb) + 1; k < sd_band_boundary(sb + 1); ++k) m = fminr(m, r.R2[k]);
+      r.R2_unb[lane] = m;
+    }
+    __syncwarp();
+    if (lane < 6) {
+      const int sb = lane;
+      const float X2_sb = r.R2_unb[sb], E2_sb = r.R2_unb[6 + sb], Y2_sb = r.R2_unb[12 + sb];
+      const int idx = (int)r.R2_unb[18 + sb];
+      const float max_erle = sb < 4 ? WAP_EC3(erle_max_l) : WAP_EC3(erle_max_h);
+      float new_erle = 0.f;
+      bool updated = false;
+      int num_updates = a.sd_num_updates[sb];
+      if (X2_sb > kX2BandEnergyThreshold && E2_sb > 0.f) {
+        new_erle = Y2_sb / E2_sb;
+        updated = true;
+        ++num_updates;
+      }
+      float est = a.sd_estimators[idx][sb];
+      float alpha = new_erle > est ? 0.05f : 0.1f;
+      alpha = (updated ? 1.f : 0.f) * alpha;
+      est += alpha * (new_erle - est);
+      est = sd_safe_clamp(est, WAP_EC3(erle_min), max_erle);
+      float ref = a.sd_erle_ref[sb];
+      alpha = new_erle > ref ? 0.05f : 0.1f;
+      alpha = (updated ? 1.f : 0.f) * alpha;
+      ref += alpha * (new_erle - ref);
+      ref = sd_safe_clamp(ref, WAP_EC3(erle_min), max_erle);
+      if (updated && num_updates > 50) {
+        const float new_correction_factor = est / ref;
+        const float cf = a.sd_correction[idx][sb];
+        a.sd_correction[idx][sb] = cf + 0.1f * (new_correction_factor - cf);
+      }
+      a.sd_estimators[idx][sb] = est;
+      a.sd_erle_ref[sb] = ref;
+      a.sd_num_updates[sb] = num_updates;
+    }
+    __syncwarp();
+  }
+  for (int k = lane; k < kBlock; k += 32) {   // bins 0..63; bin 64 keeps the value of the last Reset
+    const int sb = sd_subband_of_bin(k);
+    const float max_erle = sb < 4 ? WAP_EC3(erle_max_l) : WAP_EC3(erle_max_h);
+    const float correction_factor = a.sd_correction[(int)r.R2[k]][sb];
+    a.sd_erle[k] = sd_safe_clamp(a.erle[k] * correction_factor, WAP_EC3(erle_min), max_erle);
+    if (WAP_EC3(erle_onset_detection))
+      a.sd_erle_onset[k] = sd_safe_clamp(a.erle_onset_comp[k] * correction_factor, WAP_EC3(erle_min), max_erle);
+  }
+  __syncwarp();
+}
+#else
+WAP_DEV void signal_dependent_erle_update(Aec3State&, AecScratch&, bool) {}
+#endif
 
 // ---- AecState::ReverbDecay(mild) -> ReverbDecayEstimator::Decay (reverb_decay_estimator.h:37-43)
 WAP_DEV float aec_reverb_decay(const AecScratch& sc, bool mild) {
@@ -613,6 +728,7 @@ WAP_DEV void aec_state_update(Aec3State& a, AecScratch& sc, int ext_has, int ext
       }
     }
     __syncwarp();
+    if (WAP_EC3(erle_num_sections) > 1) signal_dependent_erle_update(a, sc, converged);
     if (lane == 0) {
       s.erle_num_points = num_points;
       // FullBandErleEstimator::Update
@@ -888,7 +1004,11 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
   // LinearEstimate uses Erle(onset_compensated), which only differs from erle_ with onset detection
   // (residual_echo_estimator.cc:249-251, subband_erle_estimator.h:46-50)
   const bool onset_compensated = WAP_EC3(erle_onset_compensation_in_dominant_nearend) || !dominant_nearend;
-  const float* erle = (onset_compensated && WAP_EC3(erle_onset_detection)) ? a.erle_onset_comp : a.erle;
+  // ErleEstimator::Erle / ErleUnbounded (erle_estimator.h:58-74): the signal-dependent estimator's when it exists
+  const bool sd_erle = WAP_EC3(erle_num_sections) > 1;
+  const float* erle = (onset_compensated && WAP_EC3(erle_onset_detection)) ? (sd_erle ? a.sd_erle_onset : a.erle_onset_comp)
+                                                                            : (sd_erle ? a.sd_erle : a.erle);
+  const float* erle_unbounded = sd_erle ? a.sd_erle : a.erle_unbounded;
   // GetRenderIndexesToAnalyze (residual_echo_estimator.cc:70-86): echo_model.render_pre / _post_window_size
   const int w_first = imax(0, delay - WAP_EC3(render_pre_window_size));
   const int w0 = ring_off(s.spectra_read, w_first, kRingBlocks);
@@ -917,7 +1037,7 @@ WAP_DEV void residual_echo_estimate(Aec3State& a, AecScratch& sc) {
         R2 = R2u = r.Y2[k];
       } else {
         R2 = r.S2_lin[k] / erle[k];
-        R2u = r.S2_lin[k] / a.erle_unbounded[k];
+        R2u = r.S2_lin[k] / erle_unbounded[k];
       }
     } else if (saturated_echo) {
       R2 = R2u = r.Y2[k];

@@ -71,6 +71,9 @@ struct Ec3Params {
   float render_linear_amplitude_gain;
   // echo_audibility.use_stationarity_properties / use_stationarity_properties_at_init (EchoAudibility)
   int use_stationarity_properties, use_stationarity_properties_at_init;
+  // erle.num_sections > 1: SignalDependentErleEstimator; section_boundaries_blocks_ computed on the host
+  // (signal_dependent_erle_estimator.cc:46-110), num_sections + 1 entries
+  int erle_num_sections, sd_boundaries[14];
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -118,6 +121,7 @@ constexpr int conservative_initial_phase = 0, enable_coarse_filter_output_usage 
 constexpr int render_pre_window_size = 1, render_post_window_size = 1, model_reverb_in_nonlinear_mode = 1, nearend_average_blocks = 4;
 constexpr float render_linear_amplitude_gain = 1.f;
 constexpr int use_stationarity_properties = 0, use_stationarity_properties_at_init = 0;
+constexpr int erle_num_sections = 1;   // sd_boundaries: all zero unless erle_num_sections > 1
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -161,6 +165,7 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(render_pre_window_size); WAP_SET(render_post_window_size); WAP_SET(model_reverb_in_nonlinear_mode);
   WAP_SET(nearend_average_blocks); WAP_SET(render_linear_amplitude_gain);
   WAP_SET(use_stationarity_properties); WAP_SET(use_stationarity_properties_at_init);
+  WAP_SET(erle_num_sections);
 #undef WAP_SET
   return p;
 }

@@ -511,7 +511,11 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
       c.filter.coarse_initial.length_blocks >= 1 && c.filter.coarse_initial.length_blocks <= c.filter.coarse.length_blocks &&
       c.filter.config_change_duration_blocks >= 1 &&
       c.filter.export_linear_aec_output == d.filter.export_linear_aec_output &&
-      c.erle.num_sections == 1 &&
+      // SignalDependentErleEstimator: sections of the refined filter behind the delay headroom
+      c.erle.num_sections >= 1 &&
+      (c.erle.num_sections == 1 ||
+       (c.delay.delay_headroom_samples >= 0 &&
+        c.erle.num_sections <= c.filter.refined.length_blocks - c.delay.delay_headroom_samples / (int)wap::kBlock)) &&
       // default_len < 0: the adaptive reverb decay (ReverbDecayEstimator); its EarlyReverbLengthEstimator holds
       // length_blocks - 9 sections, so the reference itself needs 10 blocks or more
       (c.ep_strength.default_len >= 0.f || c.filter.refined.length_blocks >= 10) &&
@@ -630,6 +634,35 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   p.nearend_average_blocks = c.suppressor.nearend_average_blocks;
   // RenderDelayBufferImpl: std::pow(10.0f, render_power_gain_db / 20.f) (render_delay_buffer.cc:124-125)
   p.render_linear_amplitude_gain = powf(10.0f, c.render_levels.render_power_gain_db / 20.f);
+  p.erle_num_sections = c.erle.num_sections;
+  if (c.erle.num_sections > 1) {
+    // SetSectionsBoundaries / DefineFilterSectionSizes (signal_dependent_erle_estimator.cc:46-110): sections
+    // of 2, 4, 8 ... blocks while more than that many blocks per remaining section are left, the rest split
+    // evenly, the remainder to the last one; the first section starts behind the delay headroom
+    const int num_sections = c.erle.num_sections, num_blocks = c.filter.refined.length_blocks;
+    const int headroom = c.delay.delay_headroom_samples / (int)wap::kBlock;
+    int sizes[wap::kMaxPartitions] = {};
+    int remaining_blocks = num_blocks - headroom, remaining_sections = num_sections, estimator_size = 2, idx = 0;
+    while (remaining_sections > 1 && remaining_blocks > estimator_size * remaining_sections) {
+      sizes[idx++] = estimator_size;
+      remaining_blocks -= estimator_size;
+      --remaining_sections;
+      estimator_size *= 2;
+    }
+    const int last_groups_size = remaining_blocks / remaining_sections;
+    for (; idx < num_sections; ++idx) sizes[idx] = last_groups_size;
+    sizes[num_sections - 1] += remaining_blocks - last_groups_size * remaining_sections;
+    p.sd_boundaries[0] = headroom;
+    int section = 0, current_size_block = 0;
+    for (int k = headroom; k < num_blocks; ++k) {
+      if (++current_size_block >= sizes[section]) {
+        if (++section == num_sections) break;
+        p.sd_boundaries[section] = k + 1;
+        current_size_block = 0;
+      }
+    }
+    p.sd_boundaries[num_sections] = num_blocks;
+  }
   p.use_stationarity_properties = c.echo_audibility.use_stationarity_properties;
   p.use_stationarity_properties_at_init = c.echo_audibility.use_stationarity_properties_at_init;
   return p;
@@ -1003,7 +1036,7 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
           !c->echo_model.model_reverb_in_nonlinear_mode || c->suppressor.nearend_average_blocks != 4 ||
           c->render_levels.render_power_gain_db != 0.f || c->echo_audibility.use_stationarity_properties ||
           c->echo_audibility.use_stationarity_properties_at_init ||
-          c->ep_strength.default_len < 0.f || c->ep_strength.nearend_len < 0.f)
+          c->ep_strength.default_len < 0.f || c->ep_strength.nearend_len < 0.f || c->erle.num_sections != 1)
         err = WapError::UnsupportedConfig;
     }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||

@@ -88,7 +88,11 @@ inline void init_aec3_state(Aec3State& a, const Ec3Params& ep) {
     a.cng_N2[k] = 1.0e6f;                // ComfortNoiseGenerator ctor (comfort_noise_generator.cc:106-123)
     a.last_gain[k] = 1.f;                // SuppressionGain ctor (suppression_gain.cc:351)
     a.sta_noise[k] = 10.f;               // StationarityEstimator::NoiseSpectrum::Reset (kMinNoisePower)
+    a.sd_erle[k] = a.sd_erle_onset[k] = ep.erle_min;   // SignalDependentErleEstimator::Reset
   }
+  for (int j = 0; j < kMaxPartitions; ++j)
+    for (int b = 0; b < 8; ++b) { a.sd_estimators[j][b] = ep.erle_min; a.sd_correction[j][b] = 1.f; }
+  for (int b = 0; b < 8; ++b) a.sd_erle_ref[b] = ep.erle_min;
   {
     // FastApproxLog2f(erle.min + 1e-3) (aec3_common.cc:37-52)
     const float in = ep.erle_min + 1e-3f;

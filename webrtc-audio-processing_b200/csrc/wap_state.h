@@ -246,6 +246,10 @@ struct alignas(16) Aec3State {
   float last_gain[kBinsPad], last_nearend[kBinsPad], last_echo[kBinsPad];
   float nearend_mem[3][kBinsPad];           // aec3::MovingAverage memory (mem_len 4 -> 3 slots)
   float snd_mem[3][kBinsPad];               // SubbandNearendDetector::nearend_smoothers_ (nearend_average_blocks <= 4)
+  // SignalDependentErleEstimator (erle.num_sections > 1; signal_dependent_erle_estimator.h:84-97), six subbands
+  float sd_erle[kBinsPad], sd_erle_onset[kBinsPad];
+  float sd_estimators[kMaxPartitions][8], sd_correction[kMaxPartitions][8], sd_erle_ref[8];
+  int sd_num_updates[8];
   float rd_previous_gains[kMaxPartitions + 3];   // ReverbDecayEstimator::previous_gains_
   float sta_noise[kBinsPad];                // StationarityEstimator::NoiseSpectrum::noise_spectrum_, init 10 (kMinNoisePower)
   int sta_flags[kBinsPad], sta_hangovers[kBinsPad];   // stationarity_flags_, hangovers_
