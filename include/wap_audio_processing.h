@@ -241,6 +241,14 @@ WapError wap_stream_import_state(WapAudioProcessing* handle, const void* blob, s
  * the handle owns a private engine; UnsupportedConfig: another config class. */
 WapError wap_stream_migrate(WapAudioProcessing* handle, WapEngine* destination);
 
+/* EXT: the residual echo detector.  The reference injects it when the instance is built
+ * (AudioProcessingBuilder::SetEchoDetector(CreateEchoDetector()), api/audio/echo_detector_creator.h:21,
+ * modules/audio_processing/residual_echo_detector.cc); the seam has no entry point for it.  Call on a
+ * new engine before its first leg is created: every leg then reports
+ * WapStats::residual_echo_likelihood / _recent_max (audio_processing_impl.cc:1499-1505).
+ * UnsupportedConfig: multi-channel engines and engines without AEC3; BadStreamParameter: legs exist. */
+WapError wap_engine_enable_echo_detector(WapEngine* engine);
+
 /* Stage taps: internal signals of one leg as of the last processed 64-sample block / 10 ms frame,
  * named after the reference's ApmDataDumper taps (modules/audio_processing/logging/
  * apm_data_dumper.h; e.g. "aec3_erle" in aec3/subband_erle_estimator.cc).  Read-only snapshot of

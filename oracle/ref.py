@@ -29,6 +29,7 @@ def lib():
         L.ref_apm_tick_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_apm_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_apm_stats_echo_detector.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_apm_set_capture_output_used.argtypes = [C.c_void_p, C.c_int]
         L.ref_apm_bench.restype = C.c_double
         L.ref_apm_bench.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -165,6 +166,12 @@ class RefApm:
     def stats(self):
         s = np.zeros(6, dtype=np.float32)
         lib().ref_apm_stats(self.h, _p(s))
+        return s
+
+    def stats_echo_detector(self):
+        """[has_likelihood, residual_echo_likelihood, has_recent_max, residual_echo_likelihood_recent_max]"""
+        s = np.zeros(4, dtype=np.float64)
+        lib().ref_apm_stats_echo_detector(self.h, _p(s))
         return s
 
 

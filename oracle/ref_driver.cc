@@ -21,6 +21,8 @@
 
 #include "api/audio/audio_processing.h"
 #include "api/audio/builtin_audio_processing_builder.h"
+#include "api/make_ref_counted.h"
+#include "modules/audio_processing/residual_echo_detector.h"
 #include "api/audio/echo_canceller3_config.h"
 #include "api/environment/environment_factory.h"
 #include "api/scoped_refptr.h"
@@ -179,6 +181,7 @@ struct KvConfig {
   webrtc::EchoCanceller3Config ec3;
   std::optional<webrtc::EchoCanceller3Config> ec3mc;
   bool has_ec3 = false;
+  bool echo_detector = false;   // AudioProcessingBuilder::SetEchoDetector(CreateEchoDetector())
 };
 
 bool ParseKv(const char* text, KvConfig* out) {
@@ -195,7 +198,8 @@ bool ParseKv(const char* text, KvConfig* out) {
     if (eq == std::string::npos) return false;
     const std::string k = item.substr(0, eq);
     const double v = atof(item.c_str() + eq + 1);
-    if (k == "aec") c.echo_canceller.enabled = v != 0;
+    if (k == "echo_detector") out->echo_detector = v != 0;
+    else if (k == "aec") c.echo_canceller.enabled = v != 0;
     else if (k == "aec_enforce_hpf") c.echo_canceller.enforce_high_pass_filtering = v != 0;
     else if (k == "ns") c.noise_suppression.enabled = v != 0;
     else if (k == "ns_level") c.noise_suppression.level = static_cast<AudioProcessing::Config::NoiseSuppression::Level>((int)v);
@@ -236,6 +240,7 @@ void* ref_apm_create_kv(const char* text) {
   webrtc::Environment env = webrtc::CreateEnvironment();
   webrtc::BuiltinAudioProcessingBuilder b(kv.apm);
   if (kv.has_ec3) b.SetEchoCancellerConfig(kv.ec3, kv.ec3mc);
+  if (kv.echo_detector) b.SetEchoDetector(webrtc::make_ref_counted<webrtc::ResidualEchoDetector>());   // = CreateEchoDetector(), api/audio/echo_detector_creator.cc:19-21
   h->apm = b.Build(env);
   return h;
 }
@@ -245,7 +250,7 @@ int ref_apm_apply_kv(void* p, const char* text) {
   auto* h = static_cast<RefApm*>(p);
   KvConfig kv;
   kv.apm = h->apm->GetConfig();
-  if (!ParseKv(text, &kv) || kv.has_ec3) return -1;
+  if (!ParseKv(text, &kv) || kv.has_ec3 || kv.echo_detector) return -1;
   h->apm->ApplyConfig(kv.apm);
   return 0;
 }
@@ -391,6 +396,16 @@ void ref_apm_stats(void* p, float* out6) {
   out6[3] = s.echo_return_loss_enhancement.value_or(0.0);
   out6[4] = s.delay_ms.has_value();
   out6[5] = s.delay_ms.value_or(0);
+}
+
+// residual echo detector statistics: [has_likelihood, likelihood, has_recent_max, recent_max]
+void ref_apm_stats_echo_detector(void* p, double* out4) {
+  auto* h = static_cast<RefApm*>(p);
+  webrtc::AudioProcessingStats s = h->apm->GetStatistics();
+  out4[0] = s.residual_echo_likelihood.has_value();
+  out4[1] = s.residual_echo_likelihood.value_or(0.0);
+  out4[2] = s.residual_echo_likelihood_recent_max.has_value();
+  out4[3] = s.residual_echo_likelihood_recent_max.value_or(0.0);
 }
 
 // Run nframes ticks of int16 audio laid out [frame][sample*ch]; stats every

@@ -33,6 +33,12 @@ __global__ void __launch_bounds__(128) k_front(TickArgs a) {
   if (idx < a.n) front_leg(a, idx);
 }
 
+// Engines with the residual echo detector: the power of the leg's render frame, one thread per leg.
+__global__ void __launch_bounds__(128) k_red_render(TickArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.n) red_analyze_render(a, idx);
+}
+
 // 48 kHz AEC3 engines: band split of render and capture in front of k_front, one warp per leg.
 __global__ void __launch_bounds__(128) k_split(TickArgs a) {
   float* sm = reinterpret_cast<float*>(WAP_DYN_SMEM());  // 4 warps x 1120 floats
@@ -170,6 +176,7 @@ struct WapEngine {
   wap::ExtraChannelState* d_extra = nullptr;  // stereo engines: [capacity]
   float* d_cap_delay = nullptr;               // delay.fixed_capture_delay_samples > 0: [capacity][cap_delay_stride]
   int cap_delay_stride = 0;                   // floats per leg: bands * delay + 4 (insert position, padding)
+  wap::EchoDetectorState* d_red = nullptr;    // wap_engine_enable_echo_detector: [capacity]
   // multi-channel engines (EngineConfig::mc)
   wap::McState* d_mc = nullptr;             // [capacity]
   wap::McTemplates* d_mc_templates = nullptr;
@@ -820,6 +827,7 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
   a.extra = e->d_extra;
   a.cap_delay = e->d_cap_delay;
   a.cap_delay_stride = e->cap_delay_stride;
+  a.red = e->d_red;
   a.rs_capture1 = nullptr;
   a.mc = e->d_mc;
   a.mc_templates = e->d_mc_templates;
@@ -879,10 +887,18 @@ WapError launch_tick(WapEngine* e, const int* d_slots, const int* d_delays, int 
     af.render = d_render ? e->d_rs_render : nullptr;
     af.capture = d_capture ? e->d_rs_capture : nullptr;
     af.fmt = 2;
+    if (e->d_red && d_render) {   // before k_front: it latches "a capture frame has been seen"
+      WAP_LAUNCH(wap::k_red_render, (n + 127) / 128, 128, 0, e->stream, af);
+      e->launches++;
+    }
     WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, af);
   } else {
     if (e->d_upper && e->cfg.num_bands == 3) {
       WAP_LAUNCH(wap::k_split, grid_for(n), wpb * 32, (size_t)wpb * 1120 * sizeof(float), e->stream, a);
+      e->launches++;
+    }
+    if (e->d_red && d_render) {
+      WAP_LAUNCH(wap::k_red_render, (n + 127) / 128, 128, 0, e->stream, a);
       e->launches++;
     }
     WAP_LAUNCH(wap::k_front, (n + 127) / 128, 128, 0, e->stream, a);
@@ -1200,6 +1216,7 @@ void wap_engine_destroy(WapEngine* e) {
   cudaFree(e->d_rs_capture1);
   cudaFree(e->d_extra);
   cudaFree(e->d_cap_delay);
+  cudaFree(e->d_red);
   cudaFree(e->d_mc);
   cudaFree(e->d_mc_templates);
   cudaFree(e->d_mc_ns);
@@ -1221,6 +1238,21 @@ void wap_engine_destroy(WapEngine* e) {
   if (e->copy_out) cudaStreamDestroy(e->copy_out);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
+}
+
+// EXT: AudioProcessingBuilder::SetEchoDetector(CreateEchoDetector()) for every leg of the engine.
+WapError wap_engine_enable_echo_detector(WapEngine* e) {
+  if (!e) return WapError::NullPointer;
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  if (e->d_red) return WapError::None;
+  // built for the mono AEC3 classes; before the first leg joins
+  if (e->cfg.mc || !e->cfg.aec_enabled) return WapError::UnsupportedConfig;
+  if (e->free_slots.size() != (size_t)e->capacity) return WapError::BadStreamParameter;
+  WAP_CUDA(cudaSetDevice(e->device));
+  const size_t bytes = (size_t)e->capacity * sizeof(wap::EchoDetectorState);
+  WAP_CUDA(cudaMalloc((void**)&e->d_red, bytes));
+  WAP_CUDA(cudaMemset(e->d_red, 0, bytes));
+  return WapError::None;
 }
 
 WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing** out) {
@@ -1247,6 +1279,8 @@ WapError wap_engine_create_streams(WapEngine* e, int32_t n, WapAudioProcessing**
     if (e->d_cap_delay)
       for (int i = 0; i < n; ++i)
         WAP_CUDA(cudaMemsetAsync(e->d_cap_delay + (size_t)slots[i] * e->cap_delay_stride, 0, e->cap_delay_stride * sizeof(float), e->stream));
+    if (e->d_red)
+      for (int i = 0; i < n; ++i) WAP_CUDA(cudaMemsetAsync(&e->d_red[slots[i]], 0, sizeof(wap::EchoDetectorState), e->stream));
     if (e->d_mc) {
       WAP_LAUNCH(wap::k_mc_init_slots, dim3(32, std::min(n, 2048)), 256, 0, e->stream, e->d_mc,
                  (const wap::McTemplates*)e->d_mc_templates, (const int*)d_slots, (int)n,
@@ -1530,6 +1564,22 @@ WapError wap_get_statistics(const WapAudioProcessing* hc, WapStats* out) {
       st.echo_return_loss_enhancement = (double)(float)(3.0102999566398121 * (double)s.stats_erle_log2);
       st.has_delay_ms = true;
       st.delay_ms = s.stats_delay_blocks * 4;  // block_size_ms = 4
+      if (e->d_red) {
+        // the residual echo detector's metrics travel in the same slot (audio_processing_impl.cc:1499-1505)
+        wap::EchoDetectorState* dr = &e->d_red[h->slot];
+        struct { int full, valid; float likelihood, recent_max; } rs;
+        static_assert(offsetof(wap::EchoDetectorState, slot_recent_max) - offsetof(wap::EchoDetectorState, slot_full) == 12,
+                      "the slot members are read as one block");
+        WAP_CUDA(cudaMemcpy(&rs, &dr->slot_full, sizeof(rs), cudaMemcpyDeviceToHost));
+        if (rs.full && rs.valid) {
+          st.has_residual_echo_likelihood = true;
+          st.residual_echo_likelihood = (double)rs.likelihood;
+          st.has_residual_echo_likelihood_recent_max = true;
+          st.residual_echo_likelihood_recent_max = (double)rs.recent_max;
+        }
+        const int zero = 0;
+        WAP_CUDA(cudaMemcpy(&dr->slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
+      }
       h->cached_stats = st;
       const int zero = 0;
       WAP_CUDA(cudaMemcpy(&e->d_states[h->slot].aec.s.stats_slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
@@ -1562,6 +1612,7 @@ size_t blob_bytes(const WapEngine* e) {
   if (e->d_rs) n += wap::kRsPerLeg * sizeof(wap::ResamplerState);
   if (e->d_extra) n += sizeof(wap::ExtraChannelState);
   if (e->d_cap_delay) n += (size_t)e->cap_delay_stride * sizeof(float);
+  if (e->d_red) n += sizeof(wap::EchoDetectorState);
   if (e->d_mc) n += sizeof(wap::McState);
   if (e->d_mc_ns) n += wap::kMcCh * sizeof(wap::NsState);
   return n;
@@ -1620,6 +1671,10 @@ WapError wap_stream_export_state(WapAudioProcessing* h, void* blob, size_t bytes
     WAP_CUDA(cudaMemcpy(p, e->d_cap_delay + (size_t)h->slot * e->cap_delay_stride, (size_t)e->cap_delay_stride * sizeof(float), cudaMemcpyDeviceToHost));
     p += (size_t)e->cap_delay_stride * sizeof(float);
   }
+  if (e->d_red) {
+    WAP_CUDA(cudaMemcpy(p, &e->d_red[h->slot], sizeof(wap::EchoDetectorState), cudaMemcpyDeviceToHost));
+    p += sizeof(wap::EchoDetectorState);
+  }
   if (e->d_mc) {
     WAP_CUDA(cudaMemcpy(p, &e->d_mc[h->slot], sizeof(wap::McState), cudaMemcpyDeviceToHost));
     p += sizeof(wap::McState);
@@ -1637,6 +1692,7 @@ void for_each_slab(WapEngine* e, int slot, const std::function<void(void*, size_
   if (e->d_rs) fn(&e->d_rs[(size_t)slot * wap::kRsPerLeg], wap::kRsPerLeg * sizeof(wap::ResamplerState));
   if (e->d_extra) fn(&e->d_extra[slot], sizeof(wap::ExtraChannelState));
   if (e->d_cap_delay) fn(e->d_cap_delay + (size_t)slot * e->cap_delay_stride, (size_t)e->cap_delay_stride * sizeof(float));
+  if (e->d_red) fn(&e->d_red[slot], sizeof(wap::EchoDetectorState));
   if (e->d_mc) fn(&e->d_mc[slot], sizeof(wap::McState));
   if (e->d_mc_ns) fn(&e->d_mc_ns[(size_t)slot * wap::kMcCh], wap::kMcCh * sizeof(wap::NsState));
 }
@@ -1716,6 +1772,10 @@ WapError wap_stream_import_state(WapAudioProcessing* h, const void* blob, size_t
   if (e->d_cap_delay) {
     WAP_CUDA(cudaMemcpy(e->d_cap_delay + (size_t)h->slot * e->cap_delay_stride, p, (size_t)e->cap_delay_stride * sizeof(float), cudaMemcpyHostToDevice));
     p += (size_t)e->cap_delay_stride * sizeof(float);
+  }
+  if (e->d_red) {
+    WAP_CUDA(cudaMemcpy(&e->d_red[h->slot], p, sizeof(wap::EchoDetectorState), cudaMemcpyHostToDevice));
+    p += sizeof(wap::EchoDetectorState);
   }
   if (e->d_mc) {
     WAP_CUDA(cudaMemcpy(&e->d_mc[h->slot], p, sizeof(wap::McState), cudaMemcpyHostToDevice));

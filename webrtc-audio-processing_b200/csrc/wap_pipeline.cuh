@@ -8,6 +8,7 @@
 
 #include "dsp_aec3.cuh"
 #include "dsp_agc2.cuh"
+#include "dsp_echo_detector.cuh"
 #include "dsp_front.cuh"
 #include "dsp_filters.cuh"
 #include "dsp_ns.cuh"
@@ -292,6 +293,7 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       // Muted: the (multi-channel) input frame comes back, channel by channel -- downmixed like the
       // capture_fullband_audio buffer's CopyFrom when the output has fewer channels than the input
       // (this path requires input rate == output rate).
+      if (a.red) red_capture_tick(a.red[slot], full, olen, false, tmp);
       if (cfg.in_channels != cfg.channels) {
         for (int i = lane_id(); i < olen; i += 32) {
           float v = load_raw_sample(a.capture, idx, olen, a.fmt, i, cfg.in_channels, capture_first_channel(cfg));
@@ -320,6 +322,8 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     }
     __syncwarp();
   }
+  // The residual echo detector looks at the merged frame (audio_processing_impl.cc:1462-1465)
+  if (a.red) red_capture_tick(a.red[slot], full, olen, output_used, tmp);
   // GainController2 runs on the merged full-band frame, only while the output is used
   // (audio_processing_impl.cc:1450-1477), before the PostFilter.
   if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, olen, tmp);

@@ -328,6 +328,24 @@ struct LevelState {
 };
 
 // One call leg.
+// ResidualEchoDetector (residual_echo_detector.h:60-90), the optional echo-likelihood statistic; a per-engine
+// arena of its own (wap_engine_enable_echo_detector).  All-zero is the state after construction.
+constexpr int kRedLookback = 650, kRedRenderBuffer = 30, kRedAggregation = 10 * 100;
+struct EchoDetectorState {
+  float render_buffer[kRedRenderBuffer];   // CircularBuffer
+  int rb_next, rb_count;
+  int frames_since_zero_buffer_size, seen_capture;   // seen_capture = !first_process_call_
+  float render_power[kRedLookback], render_power_mean[kRedLookback], render_power_std_dev[kRedLookback];
+  float covariance[kRedLookback];          // NormalizedCovarianceEstimator::covariance_ per lag
+  int next_insertion_index;
+  float render_mean, render_variance, capture_mean, capture_variance;   // MeanVarianceEstimator x 2
+  float reliability, echo_likelihood;
+  float mm_max; int mm_counter;            // MovingMax recent_likelihood_max_
+  // capture_.stats.residual_echo_likelihood(_recent_max) and their copy in the ApmStatsReporter slot
+  int stats_valid; float stats_likelihood, stats_recent_max;
+  int slot_full, slot_valid; float slot_likelihood, slot_recent_max;
+};
+
 struct alignas(16) StreamState {
   Biquad hpf[3];                // HighPassFilter (capture, channel 0)
   // 1 once a capture frame has been processed.  Until then the reference may

@@ -21,6 +21,7 @@ struct TickArgs {
   const int* delays_ms;   // [n] per-stream set_stream_delay_ms value (-1 unset) or nullptr
   int uniform_delay_ms;   // used when delays_ms == nullptr (-1 unset)
   int n;
+  EchoDetectorState* red; // [arena slot] residual echo detector, or nullptr (not enabled)
   const void* render;     // [n][frame] or nullptr
   const void* capture;    // [n][frame] or nullptr
   void* out;              // [n][frame]

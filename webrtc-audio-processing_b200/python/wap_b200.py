@@ -183,6 +183,7 @@ EXPORTS = [
     "wap_echo_canceller3_config_default", "wap_echo_canceller3_config_default_multichannel", "wap_echo_canceller3_config_sizeof",
     "wap_echo_canceller3_config_validate", "wap_echo_canceller3_config_supported", "wap_create_with_aec3_config",
     "wap_engine_create_with_aec3_config", "wap_engine_create_with_formats", "wap_stream_migrate",
+    "wap_engine_enable_echo_detector",
 ]
 
 _libs = {}
@@ -257,6 +258,7 @@ def load(path=None):
     L.wap_engine_create_with_aec3_config.argtypes = [C.c_int, i32, cfg, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_stream_migrate.restype = C.c_int
     L.wap_stream_migrate.argtypes = [vp, vp]
+    L.wap_engine_enable_echo_detector.argtypes = [vp]
     L.wap_engine_create_with_formats.restype = vp
     L.wap_engine_create_with_formats.argtypes = [C.c_int, i32, cfg, sc, sc, sc, C.POINTER(ec3), C.POINTER(ec3)]
     L.wap_version.restype = C.c_char_p
@@ -324,7 +326,7 @@ class Engine:
     """Batched engine: `n` call legs of one config class on one GPU."""
 
     def __init__(self, n_streams, rate=16000, channels=1, lib=None, device=0, capacity=None, aec3=None,
-                 aec3_multichannel=None, out_format=None, render_format=None, **cfg):
+                 aec3_multichannel=None, out_format=None, render_format=None, echo_detector=False, **cfg):
         """aec3: None (default EchoCanceller3Config), a dict of overrides keyed by the reference's member
         paths ("filter.refined.length_blocks": 10, ...) or a WapEchoCanceller3Config.  aec3_multichannel: the
         same for the multichannel config (overrides apply to CreateDefaultMultichannelConfig)."""
@@ -364,6 +366,12 @@ class Engine:
                 C.byref(self.aec3_mc) if self.aec3_mc is not None else None)
         if not self.h:
             raise RuntimeError("wap_engine_create failed (no CUDA device or unsupported config)")
+        if echo_detector:   # AudioProcessingBuilder::SetEchoDetector(CreateEchoDetector())
+            err = self.lib.wap_engine_enable_echo_detector(self.h)
+            if err:
+                self.lib.wap_engine_destroy(self.h)
+                self.h = None
+                raise RuntimeError("wap_engine_enable_echo_detector: " + ERRORS.get(err, str(err)))
         self.handles = (C.c_void_p * n_streams)()
         err = self.lib.wap_engine_create_streams(self.h, n_streams, self.handles)
         if err:
