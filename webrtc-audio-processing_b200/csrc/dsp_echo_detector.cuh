@@ -40,7 +40,7 @@ WAP_DEV void red_analyze_render(const TickArgs& a, int idx) {
     const float v = front_load_sample(a.render, idx, len, a.fmt, i, cfg.render_channels, -1);
     acc = acc + v * v;
   }
-  const float power = acc / (float)len;
+  const float power = fdiv(acc, (float)len);   // a true division also where len is a compile-time constant
   if (d.rb_count == 0) {
     d.frames_since_zero_buffer_size = 0;
   } else if (d.frames_since_zero_buffer_size >= kRedRenderBuffer) {
@@ -81,7 +81,7 @@ WAP_DEV void red_capture_tick(EchoDetectorState& d, const float* x, int len, boo
         d.render_power_std_dev[insert] = sqrtf(variance);
         float acc = 0.f;
         for (int i = 0; i < len; ++i) acc = acc + x[i] * x[i];
-        const float capture_power = acc / (float)len;
+        const float capture_power = fdiv(acc, (float)len);
         mean = d.capture_mean; variance = d.capture_variance;
         red_mean_variance_update(mean, variance, capture_power);
         d.capture_mean = mean; d.capture_variance = variance;

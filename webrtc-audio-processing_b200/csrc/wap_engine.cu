@@ -1250,6 +1250,17 @@ WapError wap_engine_enable_echo_detector(WapEngine* e) {
   if (e->free_slots.size() != (size_t)e->capacity) return WapError::BadStreamParameter;
   WAP_CUDA(cudaSetDevice(e->device));
   const size_t bytes = (size_t)e->capacity * sizeof(wap::EchoDetectorState);
+  // The capture side of the detector is compiled into the run-time-parameter kernel instances only (the
+  // default-config instances stay as they are): the engine switches to those.
+  if (!e->ec3_runtime) {
+    e->ec3_runtime = true;
+    e->echo_scratch_floats = wap::k_echo_scratch_floats_rt(e->cfg.num_bands, e->echo_class);
+    e->delay_scratch_floats = wap::k_delay_scratch_floats_rt();
+    const size_t smem_e = (size_t)4 * e->echo_scratch_floats * sizeof(float) + (size_t)e->echo_smem_pad;
+    const size_t smem_d = (size_t)4 * e->delay_scratch_floats * sizeof(float);
+    if (smem_e > 48 * 1024) WAP_CUDA(wap::set_k_echo_smem_rt((int)smem_e));
+    if (smem_d > 48 * 1024) WAP_CUDA(wap::set_k_delay_smem_rt((int)smem_d));
+  }
   WAP_CUDA(cudaMalloc((void**)&e->d_red, bytes));
   WAP_CUDA(cudaMemset(e->d_red, 0, bytes));
   return WapError::None;

@@ -293,7 +293,9 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
       // Muted: the (multi-channel) input frame comes back, channel by channel -- downmixed like the
       // capture_fullband_audio buffer's CopyFrom when the output has fewer channels than the input
       // (this path requires input rate == output rate).
+#if WAP_EC3_RUNTIME   // engines with the detector run the run-time-parameter kernel instances
       if (a.red) red_capture_tick(a.red[slot], full, olen, false, tmp);
+#endif
       if (cfg.in_channels != cfg.channels) {
         for (int i = lane_id(); i < olen; i += 32) {
           float v = load_raw_sample(a.capture, idx, olen, a.fmt, i, cfg.in_channels, capture_first_channel(cfg));
@@ -323,7 +325,11 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     __syncwarp();
   }
   // The residual echo detector looks at the merged frame (audio_processing_impl.cc:1462-1465)
+  // (only in the run-time-parameter kernel instances, which engines with the detector are switched to: the
+  // hook costs the default-config kernels one more spilled register, 0.3 % of k_echo, measured)
+#if WAP_EC3_RUNTIME
   if (a.red) red_capture_tick(a.red[slot], full, olen, output_used, tmp);
+#endif
   // GainController2 runs on the merged full-band frame, only while the output is used
   // (audio_processing_impl.cc:1450-1477), before the PostFilter.
   if (cfg.agc2_enabled && output_used) agc2_process(st.agc2, cfg, full, olen, tmp);
