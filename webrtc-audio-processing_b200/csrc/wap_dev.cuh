@@ -143,10 +143,37 @@ WAP_DEV void warp_prefetch_l1(const void* p, int bytes) {
   for (int off = lane_id() * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + off));
 #endif
 }
+// WAP_L2_POLICY (experiment knob, default 0): 1 = the tick-start prefetches are tagged evict_last and released with
+// applypriority when the leg's tick is over; 2 = the leg's state is re-touched with an evict_first policy when the
+// tick is over (dead until the next tick, 65 k legs later).
+#ifndef WAP_L2_POLICY
+#define WAP_L2_POLICY 0
+#endif
 WAP_DEV void warp_prefetch_l2(const void* p, int bytes) {
 #if !defined(WAP_EMU)
   const char* c = reinterpret_cast<const char*>(p);
+#if WAP_L2_POLICY == 1
+  for (int off = lane_id() * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(c + off));
+#else
   for (int off = lane_id() * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#endif
+#endif
+}
+WAP_DEV void warp_l2_release(const void* p, int bytes) {
+#if !defined(WAP_EMU) && WAP_L2_POLICY != 0
+  const unsigned long long a0 = reinterpret_cast<unsigned long long>(p) & ~127ull;
+  const unsigned long long a1 = reinterpret_cast<unsigned long long>(p) + (unsigned long long)bytes;
+#if WAP_L2_POLICY == 1
+  for (unsigned long long a = a0 + lane_id() * 128ull; a < a1; a += 32 * 128ull)
+    asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(a));
+#else
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  for (unsigned long long a = a0 + lane_id() * 128ull; a + 128 <= a1; a += 32 * 128ull) {
+    unsigned v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  }
+#endif
 #endif
 }
 

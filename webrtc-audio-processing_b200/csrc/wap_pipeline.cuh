@@ -277,6 +277,12 @@ WAP_DEV void echo_stream_tick(const TickArgs& a, int idx, float* scratch) {
     else two_band_synthesis(bands, full, reinterpret_cast<float*>(dsp), &st.capture_bands.synthesis[0][0]);
   }
   __syncwarp();
+#if WAP_L2_POLICY != 0
+  // the leg's AEC3 / NS state is dead until its next tick
+  if (cfg.ns_enabled) warp_l2_release(&st.ns, (int)offsetof(NsState, hist_lrt));
+  if (cfg.aec_enabled)
+    warp_l2_release(st.aec.Hr_re, (int)(reinterpret_cast<const char*>(st.aec.h_time) - reinterpret_cast<const char*>(st.aec.Hr_re)));
+#endif
   const int slot_rs = slot * kRsPerLeg;
   float* tmp = reinterpret_cast<float*>(dsp);
   int olen = flen;  // samples in `full` from here on
