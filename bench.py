@@ -358,11 +358,17 @@ def measure(a, torch, dist, L, wap_b200, dev, local, rank, world, headline):
     for _ in range(3):
         tick_host(t); t += 1
     barrier()
+    trace = [] if os.environ.get("WAP_BENCH_E2E_TRACE") else None   # per-tick wall times to stderr (diagnostics)
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         tick_host(t); t += 1
+        if trace is not None:
+            trace.append(round((time.perf_counter() - t0) * 1e3, 2))
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3
+    if trace is not None and rank == 0:
+        sys.stderr.write("e2e per-tick ms: %s\n" % trace)
 
     # ---- parity spot check against the compiled reference (rank 0's legs)
     check = None
