@@ -407,7 +407,7 @@ bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
 /* None when this library can run `config` (after Validate); UnsupportedConfig when a member that
  * fixes the engine's structure differs from what is built: delay.down_sampling_factor (4),
  * delay.num_filters (5), delay.fixed_capture_delay_samples (0..5000), delay.use_external_delay_estimator
- * (false), delay.detect_pre_echo (true), filter lengths (1..13 blocks, the initial ones not above the
+ * (false), filter lengths (1..13 blocks, the initial ones not above the
  * final ones), filter.export_linear_aec_output (false), erle.num_sections (1 .. refined filter blocks
  * behind the delay headroom),
  * ep_strength.default_len < 0 (adaptive reverb decay) with fewer than 10 refined filter blocks,

@@ -291,6 +291,8 @@ SWITCHES = {
     "adaptive_reverb_decay_stationarity": {"ep_strength.default_len": -0.9,
                                            "echo_audibility.use_stationarity_properties": 1},
     "negative_nearend_len": {"ep_strength.nearend_len": -0.4},
+    # delay.detect_pre_echo = false: plain highest-peak delay, no accumulated-error path in the matched filters
+    "no_pre_echo_detection": {"delay.detect_pre_echo": 0},
     # erle.num_sections > 1: SignalDependentErleEstimator
     "erle_2_sections": {"erle.num_sections": 2},
     "erle_4_sections": {"erle.num_sections": 4},
@@ -354,8 +356,24 @@ def _reverberant_leg(nf, seed=21, rt_samples=500, delay=150):
     return q(x), q(y)
 
 
+def _pre_echo_leg(nf, seed=41):
+    """Most of the echo energy in a dense cluster of early taps, the highest single tap 16 ms later: with pre-echo
+    detection the reported delay is the early one."""
+    rng = np.random.default_rng(seed)
+    n = nf * 160
+    t = np.arange(n) / 16000.0
+    x = rng.uniform(-9000, 9000, n) * ((t % 2.5) < 2.0)
+    h = np.zeros(700)
+    h[250:310] = 0.1 * rng.choice([-1, 1], 60)
+    h[500] += 0.3
+    y = np.convolve(x, h)[:n] + rng.uniform(-40, 40, n)
+    q = lambda v: np.clip(np.round(v), -32768, 32767).astype(np.int16)
+    return q(x), q(y)
+
+
 # legs on which the reference's output provably depends on the switch (asserted below)
 SWITCH_LEGS = {
+    "no_pre_echo_detection": lambda: [_pre_echo_leg(600)],
     "adaptive_reverb_decay": lambda: [_reverberant_leg(1500)],
     "adaptive_reverb_decay_long_room": lambda: [_reverberant_leg(1200, seed=22, rt_samples=900, delay=90)],
     "adaptive_reverb_decay_stationarity": lambda: [_reverberant_leg(900, seed=23, rt_samples=250)],

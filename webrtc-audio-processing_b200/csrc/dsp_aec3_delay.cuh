@@ -549,7 +549,8 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   // ---- MatchedFilter::Update
   float error_sum_anchor = 0.f;
   for (int k = 0; k < kSubBlock; ++k) error_sum_anchor += y[k] * y[k];
-  const int last_best = s.mf_last_detected_best_lag_filter;
+  // delay.detect_pre_echo = false: no filter takes the accumulated-error path (matched_filter.cc:686-687)
+  const int last_best = WAP_EC3(detect_pre_echo) ? s.mf_last_detected_best_lag_filter : -1;
   // The filter that won the previous block needs the accumulated-error side output and goes through
   // its own path; the others are processed two at a time, one per half-warp.  A filter whose window
   // crosses the end of the reference's ring during this block is paired with one that does not
@@ -653,8 +654,8 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
   int has_agg = 0, agg_quality = 0, agg_delay = 0;
   if (winner_index != -1) {
     const int headroom = WAP_EC3(delay_headroom_samples) / kDownSampling;
-    // PreEchoLagAggregator::Aggregate (:139-183)
-    {
+    // PreEchoLagAggregator::Aggregate (:139-183); it only exists with delay.detect_pre_echo (:53-56)
+    if (WAP_EC3(detect_pre_echo)) {
       int blk = imax(0, pre_echo_lag - headroom) >> 4;
       blk = imin(imax(blk, 0), kPreEchoHistSize - 1);
       if (lane == 0) {
@@ -724,7 +725,7 @@ WAP_DEV void aec3_get_delay(Aec3State& a, AecScratch& sc) {
       if (count > WAP_EC3(thr_converged) || (count > WAP_EC3(thr_initial) && !sig)) {
         has_agg = 1;
         agg_quality = sig ? kQualityRefined : kQualityCoarse;
-        agg_delay = s.pre_candidate;
+        agg_delay = WAP_EC3(detect_pre_echo) ? s.pre_candidate : cand;   // :98-100
       }
       __syncwarp();
       if (lane == 0) {
