@@ -71,6 +71,9 @@ def parse():
     ap.add_argument("--mc", type=int, default=0,
                     help="1: stereo legs with pipeline.multi_channel_render/_capture (multichannel AEC3, BASELINE config 4: "
                          "--mc 1 --rate 48000 --ns 0)")
+    ap.add_argument("--external-delay-estimator", type=int, default=0,
+                    help="1: EchoCanceller3Config::delay.use_external_delay_estimator (the render buffer follows "
+                         "set_stream_delay_ms, no matched filters) -- a side configuration, not the headline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE config 3 / 5 side lines")
@@ -83,7 +86,8 @@ def parse():
 def workload_name(a):
     parts = []
     if a.aec:
-        parts.append("AEC3(default EchoCanceller3Config)")
+        parts.append("AEC3(delay.use_external_delay_estimator, else default EchoCanceller3Config)"
+                     if getattr(a, "external_delay_estimator", 0) else "AEC3(default EchoCanceller3Config)")
     if a.ns:
         parts.append("NS(%s)" % ["low", "moderate", "high", "veryhigh"][a.ns_level])
     if getattr(a, "agc2_gain_db", None) is not None:
@@ -115,6 +119,9 @@ def channels(a):
 
 
 def ref_kwargs(a):
+    if getattr(a, "external_delay_estimator", 0):
+        return dict(kv={"aec": int(a.aec), "ns": int(a.ns), "ns_level": a.ns_level, "max_rate": a.max_rate,
+                        "ec3.delay.use_external_delay_estimator": 1})
     kw = dict(aec=bool(a.aec), ns=bool(a.ns), ns_level=a.ns_level, max_rate=a.max_rate)
     if getattr(a, "mc", 0):
         kw.update(mc_render=True, mc_capture=True)
@@ -147,6 +154,8 @@ def cpu_reference(a, seconds):
     if getattr(a, "mc", 0):
         kv = dict(aec=int(a.aec), ns=int(a.ns), ns_level=a.ns_level, max_rate=a.max_rate, mc_render=1, mc_capture=1)
         secs = ref.cpu_bench_kv(kv, a.rate, 2, legs, cores, warm, per_leg_frames, r, c, stride=r.shape[1])
+    elif getattr(a, "external_delay_estimator", 0):
+        secs = ref.cpu_bench_kv(ref_kwargs(a)["kv"], a.rate, 1, legs, cores, warm, per_leg_frames, r, c, stride=r.shape[1])
     else:
         secs = ref.cpu_bench(a.aec, a.ns, a.ns_level, a.rate, legs, cores, warm, per_leg_frames, r, c,
                              stride=r.shape[1])
@@ -278,6 +287,8 @@ def measure(a, torch, dist, L, wap_b200, dev, local, rank, world, headline):
     extra = {} if a.agc2_gain_db is None else dict(agc2=True, agc2_fixed_gain_db=a.agc2_gain_db)
     if getattr(a, "mc", 0):
         extra.update(mc_render=True, mc_capture=True)
+    if getattr(a, "external_delay_estimator", 0):
+        extra.update(aec3={"delay.use_external_delay_estimator": 1})
     eng = wap_b200.Engine(S, a.rate, channels=channels(a), lib=L, device=local, aec=bool(a.aec), ns=bool(a.ns),
                           ns_level=a.ns_level, max_rate=a.max_rate, **extra)
     first_leg = rank * S

@@ -406,8 +406,7 @@ size_t wap_echo_canceller3_config_sizeof(void);
 bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
 /* None when this library can run `config` (after Validate); UnsupportedConfig when a member that
  * fixes the engine's structure differs from what is built: delay.down_sampling_factor (4),
- * delay.num_filters (5), delay.fixed_capture_delay_samples (0..5000), delay.use_external_delay_estimator
- * (false), filter lengths (1..13 blocks, the initial ones not above the
+ * delay.num_filters (5), delay.fixed_capture_delay_samples (0..5000), filter lengths (1..13 blocks, the initial ones not above the
  * final ones), filter.export_linear_aec_output (false), erle.num_sections (1 .. refined filter blocks
  * behind the delay headroom),
  * ep_strength.default_len < 0 (adaptive reverb decay) with fewer than 10 refined filter blocks,
@@ -416,7 +415,7 @@ bool wap_echo_canceller3_config_validate(WapEchoCanceller3Config* config);
  * echo remover included, is a run-time parameter.  Multi-channel engines additionally need the
  * defaults of the boolean switches, the render high-pass filter, the fixed capture delay, the subband
  * nearend detector, non-negative ep_strength lengths and erle.num_sections 1 (wap_engine_create*
- * reports it). */
+ * reports it), delay.detect_pre_echo true and delay.use_external_delay_estimator false. */
 WapError wap_echo_canceller3_config_supported(const WapEchoCanceller3Config* config);
 /* wap_create_with_config / wap_engine_create with an injected AEC3 config
  * (BuiltinAudioProcessingBuilder::SetEchoCancellerConfig(config, multichannel_config)).

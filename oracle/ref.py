@@ -168,6 +168,10 @@ class RefApm:
         lib().ref_apm_stats(self.h, _p(s))
         return s
 
+    def set_stream_delay_ms(self, ms):
+        """The value passed to AudioProcessing::set_stream_delay_ms before every ProcessStream call (default 0)."""
+        L = lib(); L.ref_apm_set_stream_delay_ms.argtypes = [C.c_void_p, C.c_int]; L.ref_apm_set_stream_delay_ms(self.h, int(ms))
+
     def stats_echo_detector(self):
         """[has_likelihood, residual_echo_likelihood, has_recent_max, residual_echo_likelihood_recent_max]"""
         s = np.zeros(4, dtype=np.float64)

@@ -45,6 +45,7 @@ namespace {
 
 struct RefApm {
   webrtc::scoped_refptr<AudioProcessing> apm;
+  int stream_delay_ms = 0;   // passed to set_stream_delay_ms before every ProcessStream (ref_apm_set_stream_delay_ms)
 };
 
 AudioProcessing::Config MakeConfig(int aec, int ns, int ns_level, int max_rate,
@@ -293,7 +294,7 @@ int ref_apm_tick_i16(void* p, int rate, int render_ch, int capture_ch,
   }
   int e1 = 0;
   if (render) e1 = h->apm->ProcessReverseStream(render, rc, rc, render_out);
-  h->apm->set_stream_delay_ms(0);
+  h->apm->set_stream_delay_ms(h->stream_delay_ms);
   int e2 = h->apm->ProcessStream(capture, cc, cc, out);
   return e1 ? e1 : e2;
 }
@@ -317,7 +318,7 @@ int ref_apm_tick_f32(void* p, int rate, int render_ch, int capture_ch,
   }
   int e1 = 0;
   if (render) e1 = h->apm->ProcessReverseStream(rp.data(), rc, rc, rop.data());
-  h->apm->set_stream_delay_ms(0);
+  h->apm->set_stream_delay_ms(h->stream_delay_ms);
   int e2 = h->apm->ProcessStream(cp.data(), cc, cc, op.data());
   return e1 ? e1 : e2;
 }
@@ -331,7 +332,7 @@ int ref_apm_tick_fmt_i16(void* p, int rr, int rc, int ir, int ic, int orate, int
   std::vector<int16_t> scratch(rcfg.num_frames() * rc);
   int e1 = 0;
   if (render) e1 = h->apm->ProcessReverseStream(render, rcfg, rcfg, scratch.data());
-  h->apm->set_stream_delay_ms(0);
+  h->apm->set_stream_delay_ms(h->stream_delay_ms);
   int e2 = h->apm->ProcessStream(capture, icfg, ocfg, out);
   return e1 ? e1 : e2;
 }
@@ -352,7 +353,7 @@ int ref_apm_tick_fmt_f32(void* p, int rr, int rc, int ir, int ic, int orate, int
   for (int i = 0; i < oc; ++i) op[i] = out + (size_t)i * no;
   int e1 = 0;
   if (render) e1 = h->apm->ProcessReverseStream(rp.data(), rcfg, rcfg, rop.data());
-  h->apm->set_stream_delay_ms(0);
+  h->apm->set_stream_delay_ms(h->stream_delay_ms);
   int e2 = h->apm->ProcessStream(cp.data(), icfg, ocfg, op.data());
   return e1 ? e1 : e2;
 }
@@ -397,6 +398,8 @@ void ref_apm_stats(void* p, float* out6) {
   out6[4] = s.delay_ms.has_value();
   out6[5] = s.delay_ms.value_or(0);
 }
+
+void ref_apm_set_stream_delay_ms(void* p, int ms) { static_cast<RefApm*>(p)->stream_delay_ms = ms; }
 
 // residual echo detector statistics: [has_likelihood, likelihood, has_recent_max, recent_max]
 void ref_apm_stats_echo_detector(void* p, double* out4) {

@@ -88,8 +88,7 @@ def test_config_struct_defaults_match_the_reference(api_lib, oracle):
     # structural members must keep their defaults
     for path, v in (("delay.down_sampling_factor", 8), ("delay.num_filters", 6), ("filter.refined.length_blocks", 14),
                     ("filter.export_linear_aec_output", True), ("erle.num_sections", 14),
-                    ("delay.use_external_delay_estimator", True),
-                    ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
+                                        ("suppressor.subband_nearend_detection.nearend_average_blocks", 9)):
         c = L.wap_echo_canceller3_config_default()
         c.suppressor.use_subband_nearend_detection = True   # built with a smoother of at most three past blocks
         assert L.wap_echo_canceller3_config_supported(C.byref(c)) == 0
@@ -256,6 +255,37 @@ def test_optional_aec3_stages_match_the_reference(api_lib, oracle, name):
         assert d.max() == 0, (name, i, int(d.max()), int(np.argmax(d)) // n)
     ro_default, _, _ = oracle.RefApm(aec=True, ns=True, ns_level=1, max_rate=48000).run_i16(rate, legs[0][0], legs[0][1])
     assert not np.array_equal(ro_default, out[0])
+
+
+@pytest.mark.parametrize("rate,delay_ms,render_first", [(16000, 24, True), (16000, 0, False), (48000, 40, True)])
+def test_external_delay_estimator_matches_the_reference(api_lib, oracle, rate, delay_ms, render_first):
+    """delay.use_external_delay_estimator: no RenderDelayController (no matched filters at all); the render
+    buffer follows set_stream_delay_ms on every block (block_processor.cc:162-194, render_delay_buffer.cc:375-384).
+    render_first = False: the first ten capture frames arrive before any render frame."""
+    import wap_b200
+    over = {"delay.use_external_delay_estimator": 1}
+    nf, n = 320, rate // 100
+    far, near = synthetic_leg(3, nf) if rate == 16000 else synthetic_leg_48k(3, nf, 1.0)
+    eng = wap_b200.Engine(1, rate, lib=api_lib, aec=True, ns=False, max_rate=48000, aec3=over)
+    ref = oracle.RefApm(kv=_ref_kv(over, aec=1, ns=0, max_rate=48000))
+    ref.set_stream_delay_ms(delay_ms)
+    ref_default = oracle.RefApm(kv=_ref_kv({}, aec=1, ns=0, max_rate=48000))
+    ref_default.set_stream_delay_ms(delay_ms)
+    changed = False
+    for f in range(nf):
+        sl = slice(f * n, (f + 1) * n)
+        render = None if (not render_first and f < 10) else far[sl]
+        eng.set_stream_delay_ms(delay_ms)
+        out = eng.process(None if render is None else render.reshape(1, -1), near[sl].reshape(1, -1))
+        ro, _, err = ref.run_i16(rate, render, near[sl])
+        assert err == 0
+        assert np.array_equal(out[0], ro), (f, int(np.abs(out[0].astype(np.int32) - ro).max()))
+        rd, _, _ = ref_default.run_i16(rate, render, near[sl])
+        changed = changed or not np.array_equal(rd, ro)
+    st, rs = eng.stats(0), ref.stats()
+    assert bool(st.has_delay_ms) == bool(rs[4]) and st.delay_ms == int(rs[5])
+    eng.close()
+    assert changed
 
 
 SWITCHES = {

@@ -88,8 +88,12 @@ WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int
   Aec3Scalars& s = sc.s;
   CaptureBlockRec& rec = ts.crec[b];
   __syncwarp();
+  const bool external = WAP_EC3(use_external_delay_estimator) != 0;   // no delay controller at all
   if (!s.render_properly_started) {  // no render data yet: capture passes through
-    if (lane == 0) rec.process = 0;
+    if (lane == 0) {
+      rec.process = 0;
+      if (external) ++s.rdb_capture_calls;   // HandleSkippedCaptureProcessing
+    }
     return;
   }
   const bool first_capture = !s.capture_properly_started;
@@ -102,20 +106,42 @@ WAP_DEV void aec3_delay_block(Aec3State& a, AecScratch& sc, TickScratch& ts, int
       rdb_reset(s, WAP_EC3(default_delay));
     }
     __syncwarp();
-    delay_controller_reset(a, sc, true);
+    if (!external) delay_controller_reset(a, sc, true);
   }
   int delay_change = kDelayAdjNone;
   if (render_overrun) {
     delay_change = kDelayAdjBufferFlush;
-    delay_controller_reset(a, sc, true);
+    if (!external) delay_controller_reset(a, sc, true);
   }
   __syncwarp();
   if (lane == 0) {
     s.render_event = kEventNone;
+    if (external) ++s.rdb_capture_calls;
     sc.ired[0] = rdb_prepare_capture_processing(s, WAP_EC3(default_delay), WAP_EC3(excess_render_detection_interval_blocks),
                                                 WAP_EC3(max_allowed_excess_render_blocks));
   }
   __syncwarp();
+  if (external) {
+    // RenderDelayBufferImpl::AlignFromExternalDelay (render_delay_buffer.cc:375-384); the echo remover only
+    // runs once a buffer delay has been received (block_processor.cc:190-194); estimated_delay_ stays empty
+    if (lane == 0) {
+      if (s.has_external_delay) {
+        const int delay = s.rdb_render_calls - s.rdb_capture_calls + s.external_delay;
+        rdb_apply_total_delay(s, delay - WAP_EC3(delay_headroom_samples) / kBlock);
+      }
+      s.bp_has_estimated_delay = 0;
+      rec.process = s.has_external_delay ? 1 : 0;
+      rec.blocks_read = s.blocks_read;
+      rec.spectra_read = s.spectra_read;
+      rec.gain_change = ts.pad_[1];
+      rec.delay_change = delay_change;
+      rec.clock_drift = 0;
+      rec.est_has = 0;
+      rec.est_delay = 0;
+    }
+    __syncwarp();
+    return;
+  }
   if (sc.ired[0] == kEventRenderUnderrun) delay_controller_reset(a, sc, false);
 
   aec3_get_delay(a, sc);

@@ -74,6 +74,7 @@ WAP_DEV void front_render_insert(Aec3State& a, TickScratch& ts, int r, const flo
   Aec3Scalars& s = a.s;
   float x_energy = 0.f;  // DetectActiveRender: std::inner_product
   for (int i = 0; i < kBlock; ++i) x_energy += x[i] * x[i];
+  if (ep.use_external_delay_estimator) ++s.rdb_render_calls;
   if (s.has_delay) {
     if (!s.last_call_was_render) {
       s.last_call_was_render = 1;

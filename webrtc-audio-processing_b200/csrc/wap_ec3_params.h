@@ -77,6 +77,9 @@ struct Ec3Params {
   // delay.detect_pre_echo: the accumulated-error side of the matched filters and the PreEchoLagAggregator
   // (matched_filter.cc:686-687,754-770, matched_filter_lag_aggregator.cc:53-56,98-100)
   int detect_pre_echo;
+  // delay.use_external_delay_estimator: no RenderDelayController; the render buffer is aligned from the
+  // set_stream_delay_ms value on every block (block_processor.cc:162-187, render_delay_buffer.cc:375-384)
+  int use_external_delay_estimator;
 };
 
 // The default EchoCanceller3Config, member by member (same names as Ec3Params).
@@ -125,7 +128,7 @@ constexpr int render_pre_window_size = 1, render_post_window_size = 1, model_rev
 constexpr float render_linear_amplitude_gain = 1.f;
 constexpr int use_stationarity_properties = 0, use_stationarity_properties_at_init = 0;
 constexpr int erle_num_sections = 1;   // sd_boundaries: all zero unless erle_num_sections > 1
-constexpr int detect_pre_echo = 1;
+constexpr int detect_pre_echo = 1, use_external_delay_estimator = 0;
 }  // namespace ec3d
 
 inline Ec3Params ec3_default_params() {
@@ -169,7 +172,7 @@ inline Ec3Params ec3_default_params() {
   WAP_SET(render_pre_window_size); WAP_SET(render_post_window_size); WAP_SET(model_reverb_in_nonlinear_mode);
   WAP_SET(nearend_average_blocks); WAP_SET(render_linear_amplitude_gain);
   WAP_SET(use_stationarity_properties); WAP_SET(use_stationarity_properties_at_init);
-  WAP_SET(erle_num_sections); WAP_SET(detect_pre_echo);
+  WAP_SET(erle_num_sections); WAP_SET(detect_pre_echo); WAP_SET(use_external_delay_estimator);
 #undef WAP_SET
   return p;
 }

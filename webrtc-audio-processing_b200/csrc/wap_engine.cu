@@ -510,7 +510,7 @@ WapError ec3_config_supported(const WapEchoCanceller3Config& c) {
   const bool ok =
       c.delay.down_sampling_factor == 4 && c.delay.num_filters == 5 && c.delay.fixed_capture_delay_samples >= 0 &&
       c.delay.fixed_capture_delay_samples <= 5000 &&
-      !c.delay.use_external_delay_estimator && c.delay.default_delay >= 0 &&
+      c.delay.default_delay >= 0 &&
       c.delay.default_delay <= wap::kMaxRingDelay &&
       c.filter.refined.length_blocks >= 1 && c.filter.refined.length_blocks <= wap::kMaxPartitions &&
       c.filter.coarse.length_blocks >= 1 && c.filter.coarse.length_blocks <= wap::kMaxPartitions &&
@@ -642,6 +642,7 @@ wap::Ec3Params ec3_params_from_config(const WapEchoCanceller3Config& c) {
   // RenderDelayBufferImpl: std::pow(10.0f, render_power_gain_db / 20.f) (render_delay_buffer.cc:124-125)
   p.render_linear_amplitude_gain = powf(10.0f, c.render_levels.render_power_gain_db / 20.f);
   p.detect_pre_echo = c.delay.detect_pre_echo;
+  p.use_external_delay_estimator = c.delay.use_external_delay_estimator;
   p.erle_num_sections = c.erle.num_sections;
   if (c.erle.num_sections > 1) {
     // SetSectionsBoundaries / DefineFilterSectionSizes (signal_dependent_erle_estimator.cc:46-110): sections
@@ -1054,7 +1055,7 @@ WapEngine* wap_engine_create_with_formats(int cuda_device, int32_t max_streams, 
           c->render_levels.render_power_gain_db != 0.f || c->echo_audibility.use_stationarity_properties ||
           c->echo_audibility.use_stationarity_properties_at_init ||
           c->ep_strength.default_len < 0.f || c->ep_strength.nearend_len < 0.f || c->erle.num_sections != 1 ||
-          !c->delay.detect_pre_echo)
+          !c->delay.detect_pre_echo || c->delay.use_external_delay_estimator)
         err = WapError::UnsupportedConfig;
     }
     if (aec3.suppressor.use_subband_nearend_detection || aec3_mc.suppressor.use_subband_nearend_detection ||

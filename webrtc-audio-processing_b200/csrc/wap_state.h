@@ -200,6 +200,9 @@ struct Aec3Scalars {
   // and its LateReverbLinearRegressor (:56-61).  fq_usable_filter: FilteringQualityAnalyzer::LinearFilterUsable()
   // before the filter.use_linear_filter gate of fq_usable.
   int fq_usable_filter;
+  // RenderDelayBufferImpl::render_call_counter_ / capture_call_counter_ (render_delay_buffer.cc:94-95), kept
+  // with delay.use_external_delay_estimator only (AlignFromExternalDelay reads their difference)
+  int rdb_render_calls, rdb_capture_calls;
   int rd_late_start, rd_late_end, rd_block_to_analyze, rd_candidate_size, rd_region_identified;
   int rd_late_N, rd_late_n;
   float rd_late_nz, rd_late_nn, rd_late_count;
