@@ -246,7 +246,8 @@ WapError wap_stream_migrate(WapAudioProcessing* handle, WapEngine* destination);
  * modules/audio_processing/residual_echo_detector.cc); the seam has no entry point for it.  Call on a
  * new engine before its first leg is created: every leg then reports
  * WapStats::residual_echo_likelihood / _recent_max (audio_processing_impl.cc:1499-1505).
- * UnsupportedConfig: multi-channel engines and engines without AEC3; BadStreamParameter: legs exist. */
+ * UnsupportedConfig: multi-channel engines, and engines without AEC3 whose streams are resampled;
+ * BadStreamParameter: legs exist. */
 WapError wap_engine_enable_echo_detector(WapEngine* engine);
 
 /* Stage taps: internal signals of one leg as of the last processed 64-sample block / 10 ms frame,

@@ -32,14 +32,14 @@ def _residual_echo_leg(nf, seed=3, rate=16000):
     return q(x), q(y)
 
 
-def _compare(api_lib, rate, legs, every=1, mute=None, **cfg):
+def _compare(api_lib, rate, legs, every=1, mute=None, aec=True, **cfg):
     n = rate // 100
     nf = legs[0][1].size // n
-    kv = {"aec": 1, "ns": int(cfg.get("ns", True)), "max_rate": cfg.get("max_rate", 48000), "echo_detector": 1}
+    kv = {"aec": int(aec), "ns": int(cfg.get("ns", True)), "max_rate": cfg.get("max_rate", 48000), "echo_detector": 1}
     if "ns_level" in cfg:
         kv["ns_level"] = cfg["ns_level"]
     refs = [RefApm(kv=kv) for _ in legs]
-    eng = wap_b200.Engine(len(legs), rate, lib=api_lib, aec=True, echo_detector=True, **cfg)
+    eng = wap_b200.Engine(len(legs), rate, lib=api_lib, aec=aec, echo_detector=True, **cfg)
     seen = 0
     for f in range(nf):
         sl = slice(f * n, (f + 1) * n)
@@ -88,13 +88,20 @@ def test_echo_likelihood_at_a_resampled_rate(api_lib):
     _compare(api_lib, 24000, [(far, near)], ns=False)
 
 
+@pytest.mark.parametrize("rate", [16000, 48000])
+def test_echo_likelihood_without_echo_canceller(api_lib, rate):
+    # NS-only legs: the detector compares the (uncancelled) capture with the render powers
+    legs = [_residual_echo_leg(300, seed=5, rate=rate)]
+    assert _compare(api_lib, rate, legs, every=2, aec=False, ns=True) > 0.05
+
+
 def test_echo_detector_refusals_and_state_blob(api_lib):
     L = api_lib
-    # engines without AEC3 and multi-channel engines: not built
-    for kw in (dict(aec=False, ns=True), dict(aec=True, ns=False, mc_render=True, mc_capture=True)):
+    # multi-channel engines, and engines without AEC3 at a resampled rate: not built
+    for rate, kw in ((16000, dict(aec=True, ns=False, mc_render=True, mc_capture=True)), (24000, dict(aec=False, ns=True))):
         ch = 2 if kw.get("mc_render") else 1
         with pytest.raises(RuntimeError):
-            wap_b200.Engine(1, 16000, channels=ch, lib=L, echo_detector=True, **kw)
+            wap_b200.Engine(1, rate, channels=ch, lib=L, echo_detector=True, **kw)
     # after the first leg exists: refused
     eng = wap_b200.Engine(1, 16000, lib=L, aec=True, ns=False)
     assert L.wap_engine_enable_echo_detector(eng.h) == 5   # BadStreamParameter

@@ -1248,8 +1248,9 @@ WapError wap_engine_enable_echo_detector(WapEngine* e) {
   if (!e) return WapError::NullPointer;
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   if (e->d_red) return WapError::None;
-  // built for the mono AEC3 classes; before the first leg joins
-  if (e->cfg.mc || !e->cfg.aec_enabled) return WapError::UnsupportedConfig;
+  // built for the mono kernel classes (with or without AEC3; without it the render stream is not
+  // resampled, so only at a native rate); before the first leg joins
+  if (e->cfg.mc || (!e->cfg.aec_enabled && e->cfg.pre_stage)) return WapError::UnsupportedConfig;
   if (e->free_slots.size() != (size_t)e->capacity) return WapError::BadStreamParameter;
   WAP_CUDA(cudaSetDevice(e->device));
   const size_t bytes = (size_t)e->capacity * sizeof(wap::EchoDetectorState);
@@ -1561,43 +1562,50 @@ extern "C" {
 WapError wap_get_statistics(const WapAudioProcessing* hc, WapStats* out) {
   if (!hc || !out) return WapError::NullPointer;
   WapAudioProcessing* h = const_cast<WapAudioProcessing*>(hc);
-  if (h->engine && h->slot >= 0 && h->engine->cfg.aec_enabled) {
+  if (h->engine && h->slot >= 0 && (h->engine->cfg.aec_enabled || h->engine->d_red)) {
     WapEngine* e = h->engine;
     std::lock_guard<std::recursive_mutex> lk(e->mu);
     WAP_CUDA(cudaSetDevice(e->device));
     WAP_CUDA(cudaStreamSynchronize(e->stream));
-    wap::Aec3Scalars s;
-    WAP_CUDA(cudaMemcpy(&s, &e->d_states[h->slot].aec.s, sizeof(s), cudaMemcpyDeviceToHost));
-    if (s.stats_slot_full) {
-      WapStats st;
-      memset(&st, 0, sizeof(st));
-      st.has_echo_return_loss = true;
-      st.echo_return_loss = -10.0 * log10((double)s.stats_erl_time_domain);
-      st.has_echo_return_loss_enhancement = true;
-      // Log2TodB (aec3_common.cc:54-56): double product rounded to float.
-      st.echo_return_loss_enhancement = (double)(float)(3.0102999566398121 * (double)s.stats_erle_log2);
-      st.has_delay_ms = true;
-      st.delay_ms = s.stats_delay_blocks * 4;  // block_size_ms = 4
-      if (e->d_red) {
-        // the residual echo detector's metrics travel in the same slot (audio_processing_impl.cc:1499-1505)
-        wap::EchoDetectorState* dr = &e->d_red[h->slot];
-        struct { int full, valid; float likelihood, recent_max; } rs;
-        static_assert(offsetof(wap::EchoDetectorState, slot_recent_max) - offsetof(wap::EchoDetectorState, slot_full) == 12,
-                      "the slot members are read as one block");
-        WAP_CUDA(cudaMemcpy(&rs, &dr->slot_full, sizeof(rs), cudaMemcpyDeviceToHost));
-        if (rs.full && rs.valid) {
+    WapStats st;
+    memset(&st, 0, sizeof(st));
+    bool slot_full = false;
+    const int zero = 0;
+    if (e->cfg.aec_enabled) {
+      wap::Aec3Scalars s;
+      WAP_CUDA(cudaMemcpy(&s, &e->d_states[h->slot].aec.s, sizeof(s), cudaMemcpyDeviceToHost));
+      if (s.stats_slot_full) {
+        slot_full = true;
+        st.has_echo_return_loss = true;
+        st.echo_return_loss = -10.0 * log10((double)s.stats_erl_time_domain);
+        st.has_echo_return_loss_enhancement = true;
+        // Log2TodB (aec3_common.cc:54-56): double product rounded to float.
+        st.echo_return_loss_enhancement = (double)(float)(3.0102999566398121 * (double)s.stats_erle_log2);
+        st.has_delay_ms = true;
+        st.delay_ms = s.stats_delay_blocks * 4;  // block_size_ms = 4
+        WAP_CUDA(cudaMemcpy(&e->d_states[h->slot].aec.s.stats_slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
+      }
+    }
+    if (e->d_red) {
+      // the residual echo detector's metrics travel in the same slot (audio_processing_impl.cc:1499-1505);
+      // with AEC3 the two slots fill and empty together
+      wap::EchoDetectorState* dr = &e->d_red[h->slot];
+      struct { int full, valid; float likelihood, recent_max; } rs;
+      static_assert(offsetof(wap::EchoDetectorState, slot_recent_max) - offsetof(wap::EchoDetectorState, slot_full) == 12,
+                    "the slot members are read as one block");
+      WAP_CUDA(cudaMemcpy(&rs, &dr->slot_full, sizeof(rs), cudaMemcpyDeviceToHost));
+      if (rs.full) {
+        slot_full = true;
+        if (rs.valid) {
           st.has_residual_echo_likelihood = true;
           st.residual_echo_likelihood = (double)rs.likelihood;
           st.has_residual_echo_likelihood_recent_max = true;
           st.residual_echo_likelihood_recent_max = (double)rs.recent_max;
         }
-        const int zero = 0;
         WAP_CUDA(cudaMemcpy(&dr->slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
       }
-      h->cached_stats = st;
-      const int zero = 0;
-      WAP_CUDA(cudaMemcpy(&e->d_states[h->slot].aec.s.stats_slot_full, &zero, sizeof(int), cudaMemcpyHostToDevice));
     }
+    if (slot_full) h->cached_stats = st;
   }
   *out = h->cached_stats;
   return WapError::None;
