@@ -468,7 +468,10 @@ def run_b200(a):
                           ("BASELINE config 4: stereo 48 kHz multichannel AEC3 (2 render / 2 capture channels)",
                            dict(rate=48000, aec=1, ns=0, mc=1, streams=min(a.streams, 8192), settle=MC_SETTLE)),
                           ("BASELINE config 5: full chain AEC3+NS+AGC2",
-                           dict(agc2_gain_db=6.0))):
+                           dict(agc2_gain_db=6.0)),
+                          ("headline workload with EchoCanceller3Config::delay.use_external_delay_estimator "
+                           "(hosts that report their audio buffer delay: no matched filters)",
+                           dict(external_delay_estimator=1))):
             b = copy.copy(a)
             for k, v in upd.items():
                 setattr(b, k, v)
