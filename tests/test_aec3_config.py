@@ -328,6 +328,7 @@ SWITCHES = {
     "erle_4_sections": {"erle.num_sections": 4},
     "erle_6_sections_long_room": {"erle.num_sections": 6, "delay.delay_headroom_samples": 64},
     "erle_12_sections_no_onset_detection": {"erle.num_sections": 12, "erle.onset_detection": 0},
+    "erle_4_sections_adaptive_decay_48k": {"erle.num_sections": 4, "ep_strength.default_len": -0.8},
 }
 
 
@@ -429,7 +430,7 @@ def test_boolean_switches_of_the_echo_remover_match_the_reference(api_lib, oracl
     its default, on legs that reach the branch (16 kHz; the upper-band gain bound at 48 kHz)."""
     import wap_b200
     over = SWITCHES[name]
-    rate = 48000 if name in ("max_gain_during_echo", "render_power_gain_48k") else 16000
+    rate = 48000 if name in ("max_gain_during_echo", "render_power_gain_48k", "erle_4_sections_adaptive_decay_48k") else 16000
     n = rate // 100
     if name in SWITCH_LEGS:
         legs = SWITCH_LEGS[name]()
